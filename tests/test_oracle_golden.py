@@ -1,0 +1,162 @@
+"""The oracle (oracle/) against the golden vectors produced by the unmodified reference
+(tests/golden/make_golden.py) — and against the live reference when /root/reference exists."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import kf as okf, ukf as oukf, resample as ors
+
+HAVE_REF = os.path.isdir("/root/reference/filterpy")
+
+
+def close(a, b, rtol=1e-9, atol=1e-11):
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol)
+
+
+# ------------------------------------------------------------------ KF
+def test_kf_c1_batch_filter(golden):
+    g = golden("kf_c1")
+    zs = list(g["zs"])
+    out = okf.kf_batch_filter_single(g["x"], g["P"], zs, g["F"], g["Q"], g["H"], g["R"])
+    for got, key in zip(out, ["means", "covs", "means_p", "covs_p"]):
+        close(got, g[key], rtol=1e-12, atol=1e-13)
+    # known answers
+    x, P = okf.kf_predict_single(np.zeros(4), 10 * np.eye(4), g["F"], g["Q"])
+    x, P, y, K, S, SI = okf.kf_update_single(x, P, np.array([1., 2.]), g["H"], g["R"])
+    close(x, g["one_x"], 1e-13); close(P, g["one_P"], 1e-13)
+    close(S, g["one_S"], 1e-13); close(K, g["one_K"], 1e-13)
+    assert abs(x[0] - 0.9876558449574127) < 1e-14
+    ll = okf.log_likelihood_bank(y[None], S[None])[0]
+    assert abs(ll - float(g["one_loglik"])) < 1e-12
+    assert abs(ll - (-4.969596859557728)) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["kf_bank_4_2", "kf_bank_9_3", "kf_bank_1_1", "kf_bank_2_1",
+                                  "kf_bank_3_2", "kf_bank_6_3", "kf_bank_5_5"])
+def test_kf_bank_vs_reference(golden, name):
+    g = golden(name)
+    x, P = g["x"], g["P"]
+    alpha_sq = float(g["alpha"]) ** 2
+    for t in range(g["zs"].shape[0]):
+        if "B" in g:
+            xp, Pp = okf.kf_predict_bank(x, P, g["F"], g["Q"], alpha_sq, g["B"], g["us"][t])
+            o = okf.kf_update_bank(xp, Pp, g["zs"][t], g["H"], g["R"], g["valid"][t])
+            o["x_prior"], o["P_prior"] = xp, Pp
+        else:
+            o = okf.kf_step_bank(x, P, g["zs"][t], g["F"], g["H"], g["Q"], g["R"], alpha_sq, g["valid"][t])
+        x, P = o["x"], o["P"]
+        v = g["valid"][t]
+        close(x, g["ref_x"][t]); close(P, g["ref_P"][t])
+        close(o["x_prior"], g["ref_x_prior"][t]); close(o["P_prior"], g["ref_P_prior"][t])
+        for k in ["K", "S", "SI"]:
+            close(o[k][v], g["ref_" + k][t][v])
+        close(o["y"], g["ref_y"][t])
+        ll = okf.log_likelihood_bank(o["y"], o["S"])
+        close(ll[v], g["ref_loglik"][t][v], rtol=1e-9, atol=1e-9)
+
+
+def test_kf_c_port_matches(golden):
+    import ctypes
+    from oracle import cbuild
+    lib = cbuild.load()
+    for name in ["kf_bank_4_2", "kf_bank_9_3", "kf_bank_3_2"]:
+        g = golden(name)
+        if "B" in g:
+            continue
+        x = g["x"].copy(); P = g["P"].copy()
+        N, n = x.shape; m = g["H"].shape[-2]
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        for t in range(g["zs"].shape[0]):
+            z = np.ascontiguousarray(g["zs"][t]); v = np.ascontiguousarray(g["valid"][t].astype(np.uint8))
+            bad = lib.oracle_kf_step_f64(ctypes.c_int64(N), n, m, p(x), p(P),
+                                         p(g["F"]), ctypes.c_int64(n * n), p(g["H"]), ctypes.c_int64(m * n),
+                                         p(g["Q"]), ctypes.c_int64(n * n), p(g["R"]), ctypes.c_int64(m * m),
+                                         p(z), p(v), ctypes.c_double(float(g["alpha"]) ** 2), 1)
+            assert bad == 0
+            close(x, g["ref_x"][t]); close(P, g["ref_P"][t])
+
+
+# ------------------------------------------------------------------ UKF
+def test_merwe_sigma_points(golden):
+    g = golden("ukf_sigma")
+    a, b, k = float(g["alpha"]), float(g["beta"]), float(g["kappa"])
+    Wm, Wc = oukf.merwe_weights(6, a, b, k)
+    close(Wm, g["Wm"], 1e-14); close(Wc, g["Wc"], 1e-14)
+    Wm4, Wc4 = oukf.merwe_weights(4, .5, 2, 0)
+    close(Wm4, [-3] + [.5] * 8); close(Wc4, [-.25] + [.5] * 8)
+    close(oukf.merwe_sigma_points(g["x"], g["P"], a, b, k), g["sigmas"], 1e-13)
+
+
+@pytest.mark.parametrize("name,fxm,hxm", [("ukf_bank_rae", oukf.FX_CONST_VEL, oukf.HX_RANGE_AZ_EL),
+                                         ("ukf_bank_lin", oukf.FX_LINEAR, oukf.HX_LINEAR)])
+def test_ukf_bank_vs_reference(golden, name, fxm, hxm):
+    g = golden(name)
+    x, P = g["x"], g["P"]
+    a, b, k, dt = float(g["alpha"]), float(g["beta"]), float(g["kappa"]), float(g["dt"])
+    for t in range(g["zs"].shape[0]):
+        o = oukf.ukf_step_bank(x, P, g["zs"][t], g["Q"], g["R"], dt, a, b, k, fxm, hxm,
+                               F=g["F"], H=g["H"], valid=g["valid"][t])
+        x, P = o["x"], o["P"]
+        close(x, g["ref_x"][t], rtol=1e-9, atol=1e-9); close(P, g["ref_P"][t], rtol=1e-8, atol=1e-9)
+        close(o["x_prior"], g["ref_x_prior"][t]); close(o["P_prior"], g["ref_P_prior"][t], 1e-8, 1e-9)
+
+
+def test_ukf_single_matches_bank(golden):
+    g = golden("ukf_bank_lin")
+    a, b, k, dt = float(g["alpha"]), float(g["beta"]), float(g["kappa"]), float(g["dt"])
+    F, H = g["F"], g["H"]
+    x, P = g["x"][0], g["P"][0]
+    for t in range(3):
+        x, P, sf = oukf.ukf_predict_single(x, P, g["Q"][0], lambda s, dt: F @ s, dt, a, b, k)
+        x, P = oukf.ukf_update_single(x, P, sf, g["zs"][t, 0], g["R"][0], lambda s: H @ s, a, b, k)[:2]
+        close(x, g["ref_x"][t, 0], 1e-9, 1e-9); close(P, g["ref_P"][t, 0], 1e-8, 1e-9)
+
+
+# ------------------------------------------------------------------ resampling
+def test_resample_golden(golden):
+    g = golden("resample")
+    assert list(g["known_sys"]) == [1, 2, 3, 3]
+    assert list(ors.systematic_resample_loop([.1, .2, .3, .4], 0.5)) == [1, 2, 3, 3]
+    assert list(ors.stratified_resample_loop([.1, .2, .3, .4], np.full(4, .5))) == list(g["known_str"])
+    for (i, N, ok, ok_s, seed) in g["meta"]:
+        w, u, U = g["w%d" % i], float(g["u%d" % i]), g["U%d" % i]
+        for fn in (ors.systematic_resample_loop, ors.systematic_resample_vec, ors.systematic_resample_c):
+            if ok:
+                got = fn(w, u)
+                assert got.dtype == np.int32
+                assert np.array_equal(got, g["sys%d" % i]), (fn.__name__, i, N)
+            else:
+                with pytest.raises(IndexError):
+                    fn(w, u)
+        for fn in (ors.stratified_resample_loop, ors.stratified_resample_vec, ors.stratified_resample_c):
+            if ok_s:
+                assert np.array_equal(fn(w, U), g["str%d" % i]), (fn.__name__, i, N)
+            else:
+                with pytest.raises(IndexError):
+                    fn(w, U)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference not present (GPU box)")
+def test_live_reference_resample_and_kf():
+    sys.path.insert(0, "/root/reference")
+    from filterpy.monte_carlo import systematic_resample
+    from filterpy.kalman import KalmanFilter
+    from filterpy_b200.common import workloads as wl
+    w = wl.resample_weights(20000, "heavy", seed=5)
+    np.random.seed(123); st = np.random.get_state()
+    ref = systematic_resample(w)
+    np.random.set_state(st); u = np.random.random()
+    assert np.array_equal(ors.systematic_resample_vec(w, u), ref)
+    assert np.array_equal(ors.systematic_resample_c(w, u), ref)
+    b = wl.kf_bank_cv2d(5, seed=11, steps=2)
+    o = None; x, P = b["x"], b["P"]
+    for t in range(2):
+        o = okf.kf_step_bank(x, P, b["zs"][t], b["F"], b["H"], b["Q"], b["R"]); x, P = o["x"], o["P"]
+    for f in range(5):
+        kf = KalmanFilter(4, 2); kf.x = b["x"][f].copy(); kf.P = b["P"][f].copy()
+        kf.F, kf.H, kf.Q, kf.R = b["F"][f], b["H"][f], b["Q"][f], b["R"][f]
+        for t in range(2):
+            kf.predict(); kf.update(b["zs"][t, f])
+        close(x[f], kf.x, 1e-12); close(P[f], kf.P, 1e-12)
