@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py — the headline measurement (BASELINE.json metric) for the filterpy hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one fused predict+update of a 2^20-filter bank, dim_x=4, dim_z=2, fp32, every
+filter with its own F/H/Q/R (BASELINE.json configs[1]).  Weak scaling: every rank owns its own
+2^20-filter bank (banks are independent, no data-path collective).  Prints ONE JSON line:
+
+  value      filter-steps/s, whole job, inputs resident in HBM (CUDA events, max over ranks)
+  e2e        same metric through the public API with HOST buffers: per step the measurement z is
+             copied host->device from pinned memory and the posterior (x, P) device->host
+  roofline   achieved HBM GB/s of the fused kernel vs MEASURED_PEAKS.json
+  cpu_baseline  the oracle port (filterpy-shaped NumPy loop / vectorised NumPy / C) on host cores
+  resample   systematic_resample of 2^26 particles (BASELINE.json configs[4], single-GPU slice)
+
+`--impl reference` times the reference's CPU algorithm (the oracle port: the same per-filter
+np.dot call sequence filterpy executes) on all host cores, bounded sample per step.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_FILTERS = 1 << 20
+DIM_X, DIM_Z = 4, 2
+BYTES_PER_FILTER_STEP = (2 * DIM_X + 4 * DIM_X * DIM_X + DIM_Z + DIM_Z * DIM_X + DIM_Z * DIM_Z) * 4  # 344
+Z_RING = 4
+METRIC = "kf_predict_update_filter_steps_per_sec"
+UNIT = "filter-steps/s"
+WORKLOAD = "kf_bank 2^20 filters dim_x=4 dim_z=2 fp32, per-filter F/H/Q/R, fused predict+update"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._th = None
+
+    def _run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {
+                getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            }
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            while not self._stop.is_set():
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                r = get_reasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.02)
+        except Exception as e:  # no NVML: report nothing rather than guess
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def __enter__(self):
+        self._th = threading.Thread(target=self._run, daemon=True)
+        self._th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._th.join(timeout=2)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU legs
+def _loop_port_worker(args):
+    """filterpy-shaped port: a Python loop over filters, the reference's np.dot call sequence
+    (oracle.kf.*_single == kalman_filter.py:471-478, 533-556)."""
+    seed, nf, steps = args
+    from oracle import kf as okf
+    from filterpy_b200.common import workloads as wl
+    w = wl.kf_bank_cv2d(nf, seed=seed, steps=steps)
+    xs = [w["x"][i] for i in range(nf)]; Ps = [w["P"][i] for i in range(nf)]
+    t0 = time.perf_counter()
+    for t in range(steps):
+        for i in range(nf):
+            x, P = okf.kf_predict_single(xs[i], Ps[i], w["F"][i], w["Q"][i])
+            xs[i], Ps[i] = okf.kf_update_single(x, P, w["zs"][t, i], w["H"][i], w["R"][i])[:2]
+    return time.perf_counter() - t0
+
+
+def cpu_loop_port(cores, nf_per_core, steps):
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        t0 = time.perf_counter()
+        pool.map(_loop_port_worker, [(100 + i, nf_per_core, steps) for i in range(cores)])
+        wall = time.perf_counter() - t0
+    return cores * nf_per_core * steps / wall, wall
+
+
+def cpu_vectorised_port(nf, steps):
+    from oracle import kf as okf
+    from filterpy_b200.common import workloads as wl
+    w = wl.kf_bank_cv2d(nf, seed=1, steps=1)
+    x, P = w["x"], w["P"]
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o = okf.kf_step_bank(x, P, w["zs"][0], w["F"], w["H"], w["Q"], w["R"]); x, P = o["x"], o["P"]
+    wall = time.perf_counter() - t0
+    return nf * steps / wall, wall
+
+
+def cpu_c_port(nf, steps, threads):
+    import ctypes
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import cbuild
+    from filterpy_b200.common import workloads as wl
+    lib = cbuild.load()
+    w = wl.kf_bank_cv2d(nf, seed=2, steps=1)
+    x, P = w["x"].copy(), w["P"].copy()
+    z = np.ascontiguousarray(w["zs"][0])
+    chunk = (nf + threads - 1) // threads
+
+    def run(i):
+        a, b = i * chunk, min(nf, (i + 1) * chunk)
+        if a >= b:
+            return 0
+        p = lambda arr, off: ctypes.c_void_p(arr.ctypes.data + off * arr.itemsize)
+        return lib.oracle_kf_step_f64(ctypes.c_int64(b - a), 4, 2, p(x, a * 4), p(P, a * 16),
+                                      p(w["F"], a * 16), ctypes.c_int64(16), p(w["H"], a * 8), ctypes.c_int64(8),
+                                      p(w["Q"], a * 16), ctypes.c_int64(16), p(w["R"], a * 4), ctypes.c_int64(4),
+                                      p(z, a * 2), None, ctypes.c_double(1.0), 1)
+    with ThreadPoolExecutor(threads) as ex:
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            list(ex.map(run, range(threads)))
+        wall = time.perf_counter() - t0
+    return nf * steps / wall, wall
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port) on all host cores."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    nf_per_core = 2048          # bounded sample of the 2^20-filter bank per step
+    for _ in range(min(args.warmup, 1)):
+        cpu_loop_port(cores, 256, 1)
+    val, wall = cpu_loop_port(cores, nf_per_core, args.steps)
+    sample = "%d filters/core x %d cores x %d steps of the 2^20 bank (filterpy-shaped NumPy loop)" % (
+        nf_per_core, cores, args.steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU legs
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from filterpy_b200.kalman import KalmanFilter
+    from filterpy_b200.common import workloads as wl
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    K, W = args.steps, max(args.warmup, 3)
+    N = N_FILTERS
+
+    w = wl.kf_bank_cv2d(N, seed=1234 + rank, steps=Z_RING, dtype=np.float32)
+    kf = KalmanFilter(DIM_X, DIM_Z, n_filters=N, dtype=np.float32, device=dev, diagnostics=False)
+    for k in "xPFHQR":
+        setattr(kf, k, w[k])
+    z_dev = [torch.from_numpy(w["zs"][i]).to(dev) for i in range(Z_RING)]
+    z_pin = [torch.from_numpy(w["zs"][i]).pin_memory() for i in range(Z_RING)]
+    x_pin = torch.empty((N, DIM_X), dtype=torch.float32).pin_memory()
+    P_pin = torch.empty((N, DIM_X, DIM_X), dtype=torch.float32).pin_memory()
+    x0, P0 = kf.x.clone(), kf.P.clone()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def reset():
+        kf.x = x0; kf.P = P0
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---- value: inputs resident in HBM -----------------------------------------------------
+    def step_resident(i):
+        kf.predict()
+        kf.update(z_dev[i % Z_RING])
+
+    reset()
+    for i in range(W):
+        step_resident(i)
+    barrier()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    with ClockSampler(local_rank) as clk:
+        evs[0].record()
+        for i in range(K):
+            step_resident(i)
+            evs[i + 1].record()
+        barrier()
+    total_ms = max_over_ranks(evs[0].elapsed_time(evs[K]))
+    per_launch_ms = np.array([evs[i].elapsed_time(evs[i + 1]) for i in range(K)])
+    value = world * N * K / (total_ms * 1e-3)
+
+    # ---- e2e: host buffers, copies inside the timed region -----------------------------------
+    def step_e2e(i):
+        kf.predict()
+        kf.update(z_pin[i % Z_RING])                   # H2D of this step's measurements
+        x_pin.copy_(kf.x, non_blocking=True)           # D2H of the posterior
+        P_pin.copy_(kf.P, non_blocking=True)
+
+    reset()
+    for i in range(W):
+        step_e2e(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        step_e2e(i)
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = world * N * K / (e2e_ms * 1e-3)
+    h2d = N * DIM_Z * 4
+    d2h = N * (DIM_X + DIM_X * DIM_X) * 4
+
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    kern_ms = float(np.mean(per_launch_ms))
+    achieved = BYTES_PER_FILTER_STEP * N / (kern_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "filters_per_gpu": N, "parallelism": "bank sharded, %d rank(s)" % world,
+                   "l2": "inputs larger than L2 (344 MB touched per step vs 126 MB L2)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / K},
+        "gpu_launches": K,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "kernel": "kf42_f32_kernel<3,false,false>", "bytes_per_launch": BYTES_PER_FILTER_STEP * N,
+                     "kernel_ms": kern_ms, "kernel_ms_min": float(per_launch_ms.min())},
+        "clocks": clk.summary(),
+    }
+    if world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        lp, lp_wall = cpu_loop_port(cores, 1024, 2)
+        vp, vp_wall = cpu_vectorised_port(1 << 17, 3)
+        cp, cp_wall = cpu_c_port(1 << 19, 4, cores)
+        line["cpu_baseline"] = {
+            "value": lp, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "filterpy-shaped NumPy loop (oracle.kf.*_single), %d filters/core x %d cores x 2 steps, %.1f s"
+                      % (1024, cores, lp_wall),
+            "vectorised_numpy": {"value": vp, "cores": 1, "sample": "2^17 filters x 3 steps, %.1f s" % vp_wall},
+            "c_port": {"value": cp, "cores": cores, "sample": "2^19 filters x 4 steps fp64, %.1f s" % cp_wall},
+        }
+    extra = resample_leg(dev, args) if (world == 1 and not args.no_resample) else None
+    if extra is not None:
+        line["resample"] = extra
+    print(json.dumps(line), flush=True)
+
+
+def resample_leg(dev, args):
+    """systematic_resample of 2^26 particles on one GPU (BASELINE configs[4], single-GPU slice)."""
+    try:
+        import torch
+        from filterpy_b200.monte_carlo import resampling as rs
+    except Exception:
+        return None
+    if not hasattr(rs, "ResamplePlan"):
+        return None
+    from filterpy_b200.common import workloads as wl
+    N = 1 << 26
+    wts = wl.resample_weights(N, "heavy", seed=97)
+    wd = torch.from_numpy(wts).to(dev)
+    plan = rs.ResamplePlan(N, device=dev)
+    np.random.seed(7)
+    u = float(np.random.random())
+    for _ in range(3):
+        plan.systematic(wd, u)
+    torch.cuda.synchronize(dev)
+    reps = 10
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    ev[0].record()
+    for i in range(reps):
+        plan.systematic(wd, u)
+        ev[i + 1].record()
+    torch.cuda.synchronize(dev)
+    ms = np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(reps)])
+    peak, _ = peaks()
+    t = float(np.median(ms)) * 1e-3
+    out = {"metric": "systematic_resample_particles_per_sec", "particles": N, "value": N / t, "unit": "particles/s",
+           "ms": t * 1e3, "roofline": {"bound": "hbm", "achieved": 12.0 * N / t / 1e9, "peak": peak, "unit": "GB/s",
+                                       "frac": 12.0 * N / t / 1e9 / peak, "bytes_per_particle": 12},
+           "info": plan.info().tolist()}
+    if not args.no_cpu:
+        from oracle import resample as ors
+        ns = 1 << 23
+        ws = wts[:ns] / wts[:ns].sum()
+        t0 = time.perf_counter()
+        ors.systematic_resample_c(ws, u)
+        tc = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": ns / tc, "unit": "particles/s", "cores": 1, "kind": "port",
+                               "sample": "oracle.c sequential cumsum+merge on 2^23 particles, %.2f s" % tc}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-resample", action="store_true", help="skip the resample leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

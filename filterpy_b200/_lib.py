@@ -1,0 +1,143 @@
+"""ctypes binding of the C-ABI in ``include/bke.h`` (the drop-in boundary).
+
+The library is loaded from ``filterpy_b200/_C/libbke.so`` (built in-tree by ``_build.py``).
+There is no CPU fallback: if the library is missing and cannot be built, or a compute entry
+point reports no CUDA device, an exception is raised.
+"""
+import ctypes
+import os
+from ctypes import c_double, c_int32, c_int64, c_size_t, c_uint32, c_void_p
+
+from . import _build
+
+BKE_F32, BKE_F64 = 0, 1
+BKE_OK, BKE_ERR_BAD_ARG, BKE_ERR_UNSUPPORTED, BKE_ERR_CUDA = 0, 1, 2, 3
+BKE_STATUS_OK, BKE_STATUS_SINGULAR_S, BKE_STATUS_NOT_PD = 0, 1, 2
+BKE_DO_PREDICT, BKE_DO_UPDATE, BKE_UPDATE_FIRST = 1, 2, 4
+BKE_FX_LINEAR, BKE_FX_CONST_VEL = 0, 1
+BKE_HX_LINEAR, BKE_HX_RANGE_AZ_EL, BKE_HX_RANGE_BEARING = 0, 1, 2
+
+# every symbol include/bke.h declares (tests check that the library exports all of them)
+EXPORTED_SYMBOLS = [
+    "bke_abi_version", "bke_last_error", "bke_device_count",
+    "bke_kf_step", "bke_kf_batch_filter", "bke_ukf_step",
+    "bke_resample_workspace_bytes", "bke_systematic_resample", "bke_stratified_resample",
+    "bke_weights_sum", "bke_weights_scale",
+]
+
+
+class KfArgs(ctypes.Structure):
+    _fields_ = [
+        ("n_filters", c_int64),
+        ("dim_x", c_int32), ("dim_z", c_int32), ("dim_u", c_int32),
+        ("dtype", c_int32),
+        ("flags", c_uint32), ("reserved", c_uint32),
+        ("alpha_sq", c_double),
+        ("x", c_void_p), ("P", c_void_p),
+        ("x_out", c_void_p), ("P_out", c_void_p),
+        ("F", c_void_p), ("F_stride", c_int64),
+        ("H", c_void_p), ("H_stride", c_int64),
+        ("Q", c_void_p), ("Q_stride", c_int64),
+        ("R", c_void_p), ("R_stride", c_int64),
+        ("B", c_void_p), ("B_stride", c_int64),
+        ("u", c_void_p), ("u_stride", c_int64),
+        ("z", c_void_p), ("z_valid", c_void_p),
+        ("x_prior", c_void_p), ("P_prior", c_void_p),
+        ("K", c_void_p), ("y", c_void_p), ("S", c_void_p), ("SI", c_void_p),
+        ("log_likelihood", c_void_p),
+        ("status", c_void_p),
+    ]
+
+
+class KfBatchArgs(ctypes.Structure):
+    _fields_ = [
+        ("step", KfArgs),
+        ("n_steps", c_int64),
+        ("zs", c_void_p), ("zs_valid", c_void_p),
+        ("means", c_void_p), ("covariances", c_void_p),
+        ("means_p", c_void_p), ("covariances_p", c_void_p),
+    ]
+
+
+class UkfArgs(ctypes.Structure):
+    _fields_ = [
+        ("n_filters", c_int64),
+        ("dim_x", c_int32), ("dim_z", c_int32),
+        ("dtype", c_int32), ("flags", c_uint32),
+        ("fx_model", c_int32), ("hx_model", c_int32),
+        ("dt", c_double),
+        ("alpha", c_double), ("beta", c_double), ("kappa", c_double),
+        ("x", c_void_p), ("P", c_void_p),
+        ("x_out", c_void_p), ("P_out", c_void_p),
+        ("Q", c_void_p), ("Q_stride", c_int64),
+        ("R", c_void_p), ("R_stride", c_int64),
+        ("F", c_void_p), ("F_stride", c_int64),
+        ("H", c_void_p), ("H_stride", c_int64),
+        ("z", c_void_p), ("z_valid", c_void_p),
+        ("x_prior", c_void_p), ("P_prior", c_void_p),
+        ("K", c_void_p), ("y", c_void_p), ("S", c_void_p), ("SI", c_void_p),
+        ("log_likelihood", c_void_p),
+        ("status", c_void_p),
+    ]
+
+
+class BkeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    """Load (building first if the sources are newer) and type the library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    try:
+        if _build.needs_build():
+            _build.build()
+    except Exception as e:  # stale or missing and not buildable
+        if not os.path.exists(path):
+            raise BkeError("libbke.so is missing and could not be built (%s); the engine has no "
+                           "CPU fallback" % e)
+    lib = ctypes.CDLL(path)
+    lib.bke_abi_version.restype = ctypes.c_int
+    lib.bke_last_error.restype = ctypes.c_char_p
+    lib.bke_device_count.restype = ctypes.c_int
+    lib.bke_kf_step.argtypes = [ctypes.POINTER(KfArgs), c_void_p]
+    lib.bke_kf_step.restype = ctypes.c_int
+    lib.bke_kf_batch_filter.argtypes = [ctypes.POINTER(KfBatchArgs), c_void_p]
+    lib.bke_kf_batch_filter.restype = ctypes.c_int
+    lib.bke_ukf_step.argtypes = [ctypes.POINTER(UkfArgs), c_void_p]
+    lib.bke_ukf_step.restype = ctypes.c_int
+    lib.bke_resample_workspace_bytes.argtypes = [c_int64]
+    lib.bke_resample_workspace_bytes.restype = c_size_t
+    lib.bke_systematic_resample.argtypes = [c_int64, c_void_p, c_double, c_void_p, c_void_p, c_size_t,
+                                            c_void_p, c_void_p, c_void_p]
+    lib.bke_systematic_resample.restype = ctypes.c_int
+    lib.bke_stratified_resample.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                            c_void_p, c_void_p, c_void_p]
+    lib.bke_stratified_resample.restype = ctypes.c_int
+    lib.bke_weights_sum.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.bke_weights_sum.restype = ctypes.c_int
+    lib.bke_weights_scale.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.bke_weights_scale.restype = ctypes.c_int
+    if lib.bke_abi_version() != 1:
+        raise BkeError("libbke.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != BKE_OK:
+        msg = load().bke_last_error().decode("utf-8", "replace")
+        if rc == BKE_ERR_BAD_ARG:
+            raise ValueError(msg)
+        if rc == BKE_ERR_UNSUPPORTED:
+            raise NotImplementedError(msg)
+        raise BkeError(msg)

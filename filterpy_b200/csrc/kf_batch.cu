@@ -1,0 +1,181 @@
+// kf_batch.cu — KalmanFilter.batch_filter for a bank (filterpy/kalman/kalman_filter.py:826-993,
+// procedural twin :1664-1788): the T-epoch loop runs INSIDE the kernel.  One thread owns one
+// filter; x, P and the (time-constant) models F, Q, H, R stay in registers for all T epochs, each
+// epoch streams z[t] in (coalesced: consecutive threads read consecutive filters) and the four
+// outputs means/covariances/means_p/covariances_p out.  Algorithmic traffic per filter-step is
+// (m + 2n + 2n^2) scalars (168 B for 4/2 fp32) instead of the 344 B of a stand-alone step.
+//
+// Shapes without a register-tiled instantiation fall back to looping bke_kf_step on the host
+// (still on the GPU, one launch per epoch).
+#include <type_traits>
+#include "bke_internal.cuh"
+#include "kf_regtile.cuh"
+
+namespace bke {
+namespace {
+
+template <typename T>
+struct BatchP {
+    int64_t N, Tn;
+    bool update_first;
+    T alpha_sq;
+    const T *x, *P, *F, *Q, *H, *R, *zs;
+    int64_t sF, sQ, sH, sR;
+    const uint8_t *valid;
+    T *x_out, *P_out, *means, *covs, *means_p, *covs_p;
+    int32_t *status;
+};
+
+template <typename T, int CNT>
+__device__ __forceinline__ void load_vec(T *dst, const T *src)
+{
+#pragma unroll
+    for (int i = 0; i < CNT; i++) dst[i] = src[i];
+}
+template <typename T, int CNT>
+__device__ __forceinline__ void store_vec(T *dst, const T *src)
+{
+    constexpr int VEC = 16 / sizeof(T);
+    if constexpr (CNT % VEC == 0) {
+        using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+#pragma unroll
+        for (int i = 0; i < CNT / VEC; i++) reinterpret_cast<V *>(dst)[i] = *reinterpret_cast<const V *>(src + i * VEC);
+    } else {
+#pragma unroll
+        for (int i = 0; i < CNT; i++) dst[i] = src[i];
+    }
+}
+
+template <typename T, int N, int M>
+__global__ void __launch_bounds__(128) kf_batch_kernel(BatchP<T> p)
+{
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= p.N) return;
+    T x[N], P[N][N], F[N][N], Q[N][N], H[M][N], R[M][M];
+    load_vec<T, N>(x, p.x + f * N);
+    load_vec<T, N * N>(&P[0][0], p.P + f * N * N);
+    load_vec<T, N * N>(&F[0][0], p.F + f * p.sF);
+    load_vec<T, N * N>(&Q[0][0], p.Q + f * p.sQ);
+    load_vec<T, M * N>(&H[0][0], p.H + f * p.sH);
+    load_vec<T, M * M>(&R[0][0], p.R + f * p.sR);
+    int st = BKE_STATUS_OK;
+    for (int64_t t = 0; t < p.Tn; t++) {
+        const int64_t tf = t * p.N + f;
+        T z[M];
+        load_vec<T, M>(z, p.zs + tf * M);
+        const bool has_z = p.valid == nullptr || p.valid[tf] != 0;
+        auto upd = [&]() {
+            if (has_z) {
+                KfUpdateOut<T, N, M> o;
+                reg_update<T, N, M>(x, P, H, R, z, o);
+                if (!o.ok) st = BKE_STATUS_SINGULAR_S;
+            }
+            if (p.means) store_vec<T, N>(p.means + tf * N, x);
+            if (p.covs) store_vec<T, N * N>(p.covs + tf * N * N, &P[0][0]);
+        };
+        auto pred = [&]() {
+            reg_predict<T, N>(x, P, F, Q, p.alpha_sq);
+            if (p.means_p) store_vec<T, N>(p.means_p + tf * N, x);
+            if (p.covs_p) store_vec<T, N * N>(p.covs_p + tf * N * N, &P[0][0]);
+        };
+        if (p.update_first) { upd(); pred(); } else { pred(); upd(); }
+    }
+    store_vec<T, N>(p.x_out + f * N, x);
+    store_vec<T, N * N>(p.P_out + f * N * N, &P[0][0]);
+    if (p.status) p.status[f] = st;
+}
+
+template <typename T, int N, int M>
+int launch_reg(const bke_kf_batch_args &a, cudaStream_t s)
+{
+    const bke_kf_args &k = a.step;
+    BatchP<T> p;
+    p.N = k.n_filters; p.Tn = a.n_steps; p.update_first = k.flags & BKE_UPDATE_FIRST;
+    p.alpha_sq = (T)k.alpha_sq;
+    p.x = (const T *)k.x; p.P = (const T *)k.P; p.F = (const T *)k.F; p.Q = (const T *)k.Q;
+    p.H = (const T *)k.H; p.R = (const T *)k.R; p.zs = (const T *)a.zs;
+    p.sF = k.F_stride; p.sQ = k.Q_stride; p.sH = k.H_stride; p.sR = k.R_stride;
+    p.valid = a.zs_valid;
+    p.x_out = (T *)k.x_out; p.P_out = (T *)k.P_out;
+    p.means = (T *)a.means; p.covs = (T *)a.covariances; p.means_p = (T *)a.means_p; p.covs_p = (T *)a.covariances_p;
+    p.status = k.status;
+    int64_t grid = (p.N + 127) / 128;
+    kf_batch_kernel<T, N, M><<<(unsigned)grid, 128, 0, s>>>(p);
+    return check_cuda(cudaGetLastError(), "kf_batch_kernel launch");
+}
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int launch_host_loop(const bke_kf_batch_args &a, cudaStream_t s)
+{
+    // One bke_kf_step per epoch.  The posterior of epoch t is written straight into means[t] /
+    // covariances[t] and read from there by epoch t+1 (no copies); without those outputs the
+    // state ping-pongs in place in x_out / P_out.
+    const bke_kf_args &k0 = a.step;
+    const size_t es = k0.dtype == BKE_F32 ? 4 : 8;
+    const int64_t N = k0.n_filters, n = k0.dim_x, m = k0.dim_z;
+    const bool uf = k0.flags & BKE_UPDATE_FIRST;
+    const char *xin = (const char *)k0.x, *Pin = (const char *)k0.P;
+    for (int64_t t = 0; t < a.n_steps; t++) {
+        bke_kf_args k = k0;
+        k.flags = BKE_DO_PREDICT | BKE_DO_UPDATE | (uf ? BKE_UPDATE_FIRST : 0);
+        k.x = xin; k.P = Pin;
+        k.z = (const char *)a.zs + (size_t)t * N * m * es;
+        k.z_valid = a.zs_valid ? a.zs_valid + t * N : nullptr;
+        k.K = k.y = k.S = k.SI = k.log_likelihood = nullptr;
+        char *post_x = a.means ? (char *)a.means + (size_t)t * N * n * es : (char *)k0.x_out;
+        char *post_P = a.covariances ? (char *)a.covariances + (size_t)t * N * n * n * es : (char *)k0.P_out;
+        char *prior_x = a.means_p ? (char *)a.means_p + (size_t)t * N * n * es : nullptr;
+        char *prior_P = a.covariances_p ? (char *)a.covariances_p + (size_t)t * N * n * n * es : nullptr;
+        int rc;
+        if (!uf) {
+            k.x_out = post_x; k.P_out = post_P; k.x_prior = prior_x; k.P_prior = prior_P;
+            rc = launch_kf_fast(k, s);
+            if (rc == BKE_ERR_UNSUPPORTED) rc = launch_kf_generic(k, s);
+            if (rc) return rc;
+            xin = post_x; Pin = post_P;
+        } else {
+            // update -> means[t]; predict -> means_p[t] which also feeds epoch t+1
+            bke_kf_args ku = k; ku.flags = BKE_DO_UPDATE; ku.x_out = post_x; ku.P_out = post_P; ku.x_prior = ku.P_prior = nullptr;
+            rc = launch_kf_fast(ku, s);
+            if (rc == BKE_ERR_UNSUPPORTED) rc = launch_kf_generic(ku, s);
+            if (rc) return rc;
+            bke_kf_args kp = k; kp.flags = BKE_DO_PREDICT; kp.x = post_x; kp.P = post_P;
+            kp.x_out = prior_x ? prior_x : (char *)k0.x_out; kp.P_out = prior_P ? prior_P : (char *)k0.P_out;
+            kp.x_prior = kp.P_prior = nullptr; kp.status = nullptr;
+            rc = launch_kf_fast(kp, s);
+            if (rc == BKE_ERR_UNSUPPORTED) rc = launch_kf_generic(kp, s);
+            if (rc) return rc;
+            xin = (const char *)kp.x_out; Pin = (const char *)kp.P_out;
+        }
+    }
+    if (a.n_steps > 0) {
+        if (xin != (const char *)k0.x_out &&
+            check_cuda(cudaMemcpyAsync(k0.x_out, xin, (size_t)N * n * es, cudaMemcpyDeviceToDevice, s), "copy final x")) return BKE_ERR_CUDA;
+        if (Pin != (const char *)k0.P_out &&
+            check_cuda(cudaMemcpyAsync(k0.P_out, Pin, (size_t)N * n * n * es, cudaMemcpyDeviceToDevice, s), "copy final P")) return BKE_ERR_CUDA;
+    } else {
+        if (k0.x_out != k0.x && check_cuda(cudaMemcpyAsync(k0.x_out, k0.x, (size_t)N * n * es, cudaMemcpyDeviceToDevice, s), "copy x")) return BKE_ERR_CUDA;
+        if (k0.P_out != k0.P && check_cuda(cudaMemcpyAsync(k0.P_out, k0.P, (size_t)N * n * n * es, cudaMemcpyDeviceToDevice, s), "copy P")) return BKE_ERR_CUDA;
+    }
+    return BKE_OK;
+}
+
+}  // namespace
+
+int launch_kf_batch(const bke_kf_batch_args &a, cudaStream_t s)
+{
+    const bke_kf_args &k = a.step;
+    const bool no_ctrl = !(k.B && k.u);
+    const bool al = aligned16(k.x_out) && aligned16(k.P_out) && aligned16(a.means) && aligned16(a.covariances) &&
+                    aligned16(a.means_p) && aligned16(a.covariances_p);
+    if (no_ctrl && al && a.n_steps > 0) {
+        if (k.dtype == BKE_F32 && k.dim_x == 4 && k.dim_z == 2) return launch_reg<float, 4, 2>(a, s);
+        if (k.dtype == BKE_F32 && k.dim_x == 2 && k.dim_z == 1) return launch_reg<float, 2, 1>(a, s);
+        if (k.dtype == BKE_F64 && k.dim_x == 2 && k.dim_z == 1) return launch_reg<double, 2, 1>(a, s);
+        if (k.dtype == BKE_F64 && k.dim_x == 4 && k.dim_z == 2) return launch_reg<double, 4, 2>(a, s);
+    }
+    return launch_host_loop(a, s);
+}
+
+}  // namespace bke

@@ -1,0 +1,405 @@
+// kf_fast.cu — specialised fused predict+update for the benchmark shape (dim_x=4, dim_z=2, fp32).
+//
+// Mapping (B200 / sm_100a):
+//   * persistent CTAs of 128 threads; one CTA processes tiles of 128 consecutive filters;
+//   * per tile, ONE elected thread issues 7 TMA tensor copies (cp.async.bulk.tensor) that pull the
+//     tile's x, P, F, Q, H, R, z blocks — contiguous byte ranges of the dense AoS arrays the API is
+//     handed — into a shared-memory stage and complete on an mbarrier; a 2-stage ring keeps the
+//     next tiles' 33 KB in flight while the current tile computes (HBM latency is hidden by the
+//     ring, not by occupancy);
+//   * the 64-byte P/F/Q rows and 32-byte H rows land through the TMA 64B/32B swizzle, so that
+//     thread t reading ITS filter's row with LDS.128 (16-byte chunk c at position c ^ f(t)) is
+//     bank-conflict-free although the rows are 64 B apart;
+//   * each thread then owns one filter: the whole predict+update runs in registers
+//     (kf_regtile.cuh), results are written with 16-byte stores.
+// Shared models (stride 0) are read once per thread through the read-only path instead of TMA.
+//
+// Reference arithmetic: filterpy/kalman/kalman_filter.py:471-478, 533-556 (see kf_regtile.cuh).
+#include <cuda.h>
+#include "bke_internal.cuh"
+#include "kf_regtile.cuh"
+
+namespace bke {
+namespace {
+
+// ---------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const CUtensorMap *map, int c0, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.1d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0) : "memory");
+}
+
+// ---------------------------------------------------------------------------- tile geometry
+constexpr int TILE = 128;       // filters per tile == threads per CTA
+constexpr int STAGES = 2;
+
+template <typename T, int N, int M>
+struct Stage {
+    // byte sizes of one tile of each array
+    static constexpr int XB = TILE * N * sizeof(T);
+    static constexpr int PB = TILE * N * N * sizeof(T);
+    static constexpr int HB = TILE * M * N * sizeof(T);
+    static constexpr int RB = TILE * M * M * sizeof(T);
+    static constexpr int ZB = TILE * M * sizeof(T);
+    // offsets (all 1024-byte aligned: swizzled TMA destinations need it)
+    static constexpr int align_up(int v) { return (v + 1023) & ~1023; }
+    static constexpr int OP = 0;
+    static constexpr int OF = OP + align_up(PB);
+    static constexpr int OQ = OF + align_up(PB);
+    static constexpr int OH = OQ + align_up(PB);
+    static constexpr int OX = OH + align_up(HB);
+    static constexpr int OR_ = OX + align_up(XB);
+    static constexpr int OZ = OR_ + align_up(RB);
+    static constexpr int BYTES = OZ + align_up(ZB);
+};
+
+// read the 16-byte chunk c of row `row` (ROWB bytes per row) from a TMA-swizzled tile
+template <int ROWB>
+__device__ __forceinline__ float4 lds_chunk(const unsigned char *base, int row, int c)
+{
+    uint32_t off = (uint32_t)row * ROWB + (uint32_t)c * 16;
+    if constexpr (ROWB == 128) off ^= ((off >> 7) & 7u) << 4;
+    else if constexpr (ROWB == 64) off ^= ((off >> 7) & 3u) << 4;
+    else if constexpr (ROWB == 32) off ^= ((off >> 7) & 1u) << 4;
+    return *reinterpret_cast<const float4 *>(base + off);
+}
+
+struct Maps {
+    CUtensorMap x, P, F, Q, H, R, z;
+};
+
+template <int N, int M>
+struct FastP {
+    int64_t N_filters;
+    int num_tiles;
+    float alpha_sq;
+    const float *F, *Q, *H, *R;     // used when SHARED
+    float *x_out, *P_out;
+    const uint8_t *valid;
+    float *x_prior, *P_prior, *K, *y, *S, *SI, *ll;
+    int32_t *status;
+};
+
+// MODE: 3 = predict+update, 1 = predict only, 2 = update only
+template <int MODE, bool SHARED, bool EXTRAS>
+__global__ void __launch_bounds__(TILE, 3)
+kf42_f32_kernel(const __grid_constant__ Maps maps, const FastP<4, 2> p)
+{
+    constexpr int N = 4, M = 2;
+    using St = Stage<float, N, M>;
+    constexpr bool DO_P = MODE & 1, DO_U = MODE & 2;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t full[STAGES];
+
+    const int tid = threadIdx.x;
+    uint32_t tx_bytes = St::XB + St::PB;
+    if (!SHARED && DO_P) tx_bytes += 2 * St::PB;
+    if (!SHARED && DO_U) tx_bytes += St::HB + St::RB;
+    if (DO_U) tx_bytes += St::ZB;
+
+    auto issue = [&](int tile, int stage) {
+        unsigned char *sb = smem + stage * St::BYTES;
+        uint64_t *bar = &full[stage];
+        const int row0 = tile * TILE;
+        mbar_expect_tx(bar, tx_bytes);
+        tma_load_2d(sb + St::OP, &maps.P, 0, row0, bar);
+        tma_load_2d(sb + St::OX, &maps.x, 0, row0, bar);
+        if (!SHARED && DO_P) {
+            tma_load_2d(sb + St::OF, &maps.F, 0, row0, bar);
+            tma_load_2d(sb + St::OQ, &maps.Q, 0, row0, bar);
+        }
+        if (!SHARED && DO_U) {
+            tma_load_2d(sb + St::OH, &maps.H, 0, row0, bar);
+            tma_load_2d(sb + St::OR_, &maps.R, 0, row0, bar);
+        }
+        if (DO_U) tma_load_1d(sb + St::OZ, &maps.z, row0 * M, bar);
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            int tile = blockIdx.x + s * gridDim.x;
+            if (tile < p.num_tiles) issue(tile, s);
+        }
+    }
+
+    float F[N][N], Q[N][N], H[M][N], R[M][M];
+    if (SHARED) {
+        if (DO_P) {
+#pragma unroll
+            for (int i = 0; i < N; i++)
+#pragma unroll
+                for (int j = 0; j < N; j++) { F[i][j] = __ldg(p.F + i * N + j); Q[i][j] = __ldg(p.Q + i * N + j); }
+        }
+        if (DO_U) {
+#pragma unroll
+            for (int a = 0; a < M; a++) {
+#pragma unroll
+                for (int j = 0; j < N; j++) H[a][j] = __ldg(p.H + a * N + j);
+#pragma unroll
+                for (int b = 0; b < M; b++) R[a][b] = __ldg(p.R + a * M + b);
+            }
+        }
+    }
+
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++) {
+        const int stage = it % STAGES;
+        const uint32_t parity = (it / STAGES) & 1;
+        const unsigned char *sb = smem + stage * St::BYTES;
+        mbar_wait(&full[stage], parity);
+
+        float x[N], P[N][N], z[M];
+        {
+            float4 v = lds_chunk<16>(sb + St::OX, tid, 0);
+            x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+        }
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            float4 v = lds_chunk<64>(sb + St::OP, tid, i);
+            P[i][0] = v.x; P[i][1] = v.y; P[i][2] = v.z; P[i][3] = v.w;
+        }
+        if (!SHARED && DO_P) {
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                float4 v = lds_chunk<64>(sb + St::OF, tid, i);
+                F[i][0] = v.x; F[i][1] = v.y; F[i][2] = v.z; F[i][3] = v.w;
+                float4 q = lds_chunk<64>(sb + St::OQ, tid, i);
+                Q[i][0] = q.x; Q[i][1] = q.y; Q[i][2] = q.z; Q[i][3] = q.w;
+            }
+        }
+        if (!SHARED && DO_U) {
+#pragma unroll
+            for (int a = 0; a < M; a++) {
+                float4 v = lds_chunk<32>(sb + St::OH, tid, a);
+                H[a][0] = v.x; H[a][1] = v.y; H[a][2] = v.z; H[a][3] = v.w;
+            }
+            float4 r = lds_chunk<16>(sb + St::OR_, tid, 0);
+            R[0][0] = r.x; R[0][1] = r.y; R[1][0] = r.z; R[1][1] = r.w;
+        }
+        if (DO_U) {
+            float2 v = *reinterpret_cast<const float2 *>(sb + St::OZ + tid * 8);
+            z[0] = v.x; z[1] = v.y;
+        }
+        __syncthreads();      // every thread has drained the stage
+        if (tid == 0) {
+            int nt = tile + STAGES * gridDim.x;
+            if (nt < p.num_tiles) issue(nt, stage);
+        }
+
+        const int64_t f = (int64_t)tile * TILE + tid;
+        const bool live = f < p.N_filters;
+        int st = BKE_STATUS_OK;
+        if (DO_P) {
+            reg_predict<float, N>(x, P, F, Q, p.alpha_sq);
+            if (EXTRAS && live) {
+                if (p.x_prior) *reinterpret_cast<float4 *>(p.x_prior + f * N) = make_float4(x[0], x[1], x[2], x[3]);
+                if (p.P_prior) {
+#pragma unroll
+                    for (int i = 0; i < N; i++)
+                        *reinterpret_cast<float4 *>(p.P_prior + f * N * N + i * N) = make_float4(P[i][0], P[i][1], P[i][2], P[i][3]);
+                }
+            }
+        }
+        if (DO_U) {
+            bool has_z = true;
+            if (p.valid != nullptr && live) has_z = p.valid[f] != 0;
+            KfUpdateOut<float, N, M> o;
+            if (has_z) {
+                reg_update<float, N, M>(x, P, H, R, z, o);
+                if (!o.ok) st = BKE_STATUS_SINGULAR_S;
+            }
+            if (EXTRAS && live) {
+                if (!has_z) {
+                    if (p.y) *reinterpret_cast<float2 *>(p.y + f * M) = make_float2(0.f, 0.f);
+                } else {
+                    if (p.S) *reinterpret_cast<float4 *>(p.S + f * M * M) = make_float4(o.S[0][0], o.S[0][1], o.S[1][0], o.S[1][1]);
+                    if (o.ok) {
+                        if (p.y) *reinterpret_cast<float2 *>(p.y + f * M) = make_float2(o.y[0], o.y[1]);
+                        if (p.SI) *reinterpret_cast<float4 *>(p.SI + f * M * M) = make_float4(o.SI[0][0], o.SI[0][1], o.SI[1][0], o.SI[1][1]);
+                        if (p.K) {
+                            *reinterpret_cast<float4 *>(p.K + f * N * M) = make_float4(o.K[0][0], o.K[0][1], o.K[1][0], o.K[1][1]);
+                            *reinterpret_cast<float4 *>(p.K + f * N * M + 4) = make_float4(o.K[2][0], o.K[2][1], o.K[3][0], o.K[3][1]);
+                        }
+                        if (p.ll) {
+                            float q = 0.f;
+#pragma unroll
+                            for (int a = 0; a < M; a++) {
+                                float s = 0.f;
+#pragma unroll
+                                for (int b = 0; b < M; b++) s += o.SI[a][b] * o.y[b];
+                                q += o.y[a] * s;
+                            }
+                            p.ll[f] = -0.5f * (q + o.logdet + float(M) * float(LOG_2PI));
+                        }
+                    }
+                }
+            }
+        }
+        if (live) {
+            *reinterpret_cast<float4 *>(p.x_out + f * N) = make_float4(x[0], x[1], x[2], x[3]);
+#pragma unroll
+            for (int i = 0; i < N; i++)
+                *reinterpret_cast<float4 *>(p.P_out + f * N * N + i * N) = make_float4(P[i][0], P[i][1], P[i][2], P[i][3]);
+            if (EXTRAS && p.status) p.status[f] = st;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                             const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                             CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode()
+{
+    static EncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeFn)p;
+    }
+    return fn;
+}
+
+// rows of `row_elems` floats, `rows` of them; box = TILE rows
+bool make_map_2d(CUtensorMap *m, const void *base, int64_t rows, int row_elems)
+{
+    EncodeFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t gdim[2] = {(cuuint64_t)row_elems, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)row_elems * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)row_elems, (cuuint32_t)TILE};
+    cuuint32_t estr[2] = {1, 1};
+    int rowb = row_elems * (int)sizeof(float);
+    CUtensorMapSwizzle sw = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : rowb == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                       : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+bool make_map_1d(CUtensorMap *m, const void *base, int64_t elems, int box_elems)
+{
+    EncodeFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t gdim[1] = {(cuuint64_t)elems};
+    cuuint64_t gstride[1] = {0};
+    cuuint32_t box[1] = {(cuuint32_t)box_elems};
+    cuuint32_t estr[1] = {1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 1, const_cast<void *>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <int MODE, bool SHARED, bool EXTRAS>
+int launch_variant(const Maps &maps, const FastP<4, 2> &p, cudaStream_t s)
+{
+    using St = Stage<float, 4, 2>;
+    auto kern = kf42_f32_kernel<MODE, SHARED, EXTRAS>;
+    const int smem = STAGES * St::BYTES;
+    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
+    int ctas_per_sm = 3;
+    int grid = sm_count() * ctas_per_sm;
+    if (grid > p.num_tiles) grid = p.num_tiles;
+    kern<<<grid, TILE, smem, s>>>(maps, p);
+    return check_cuda(cudaGetLastError(), "kf42_f32_kernel launch");
+}
+
+}  // namespace
+
+int launch_kf_fast(const bke_kf_args &a, cudaStream_t s)
+{
+    if (!(a.dtype == BKE_F32 && a.dim_x == 4 && a.dim_z == 2)) return BKE_ERR_UNSUPPORTED;
+    if (a.B != nullptr && a.u != nullptr) return BKE_ERR_UNSUPPORTED;
+    if (a.flags & BKE_UPDATE_FIRST) return BKE_ERR_UNSUPPORTED;
+    const bool dp = a.flags & BKE_DO_PREDICT, du = a.flags & BKE_DO_UPDATE;
+    // every model either per-filter or shared, not a mixture
+    bool all_shared = true, all_dense = true;
+    if (dp) { all_shared &= (a.F_stride == 0 && a.Q_stride == 0); all_dense &= (a.F_stride != 0 && a.Q_stride != 0); }
+    if (du) { all_shared &= (a.H_stride == 0 && a.R_stride == 0); all_dense &= (a.H_stride != 0 && a.R_stride != 0); }
+    if (!all_shared && !all_dense) return BKE_ERR_UNSUPPORTED;
+    if (a.n_filters >= (int64_t)1 << 30) return BKE_ERR_UNSUPPORTED;
+    // TMA needs 16-byte aligned global bases
+    auto mis = [](const void *p) { return p != nullptr && (reinterpret_cast<uintptr_t>(p) & 15u) != 0; };
+    if (mis(a.x) || mis(a.P) || mis(a.F) || mis(a.Q) || mis(a.H) || mis(a.R) || mis(a.z) || mis(a.x_out) || mis(a.P_out) ||
+        mis(a.x_prior) || mis(a.P_prior) || mis(a.K) || mis(a.S) || mis(a.SI) || (a.y && (reinterpret_cast<uintptr_t>(a.y) & 7u)))
+        return BKE_ERR_UNSUPPORTED;
+    if (!get_encode()) return BKE_ERR_UNSUPPORTED;
+
+    const int64_t N = a.n_filters;
+    Maps maps;
+    memset(&maps, 0, sizeof(maps));
+    bool ok = make_map_2d(&maps.x, a.x, N, 4) && make_map_2d(&maps.P, a.P, N, 16);
+    if (all_dense && dp) ok = ok && make_map_2d(&maps.F, a.F, N, 16) && make_map_2d(&maps.Q, a.Q, N, 16);
+    if (all_dense && du) ok = ok && make_map_2d(&maps.H, a.H, N, 8) && make_map_2d(&maps.R, a.R, N, 4);
+    if (du) ok = ok && make_map_1d(&maps.z, a.z, N * 2, TILE * 2);
+    if (!ok) { set_error("cuTensorMapEncodeTiled failed"); return BKE_ERR_CUDA; }
+
+    FastP<4, 2> p;
+    p.N_filters = N;
+    p.num_tiles = (int)((N + TILE - 1) / TILE);
+    p.alpha_sq = (float)a.alpha_sq;
+    p.F = (const float *)a.F; p.Q = (const float *)a.Q; p.H = (const float *)a.H; p.R = (const float *)a.R;
+    p.x_out = (float *)a.x_out; p.P_out = (float *)a.P_out;
+    p.valid = a.z_valid;
+    p.x_prior = (float *)a.x_prior; p.P_prior = (float *)a.P_prior; p.K = (float *)a.K; p.y = (float *)a.y;
+    p.S = (float *)a.S; p.SI = (float *)a.SI; p.ll = (float *)a.log_likelihood; p.status = a.status;
+    const bool extras = a.x_prior || a.P_prior || a.K || a.y || a.S || a.SI || a.log_likelihood || a.status;
+
+#define BKE_DISPATCH(MODE)                                                                   \
+    do {                                                                                     \
+        if (all_shared) return extras ? launch_variant<MODE, true, true>(maps, p, s)         \
+                                      : launch_variant<MODE, true, false>(maps, p, s);       \
+        return extras ? launch_variant<MODE, false, true>(maps, p, s)                        \
+                      : launch_variant<MODE, false, false>(maps, p, s);                      \
+    } while (0)
+    if (dp && du) BKE_DISPATCH(3);
+    if (dp) BKE_DISPATCH(1);
+    BKE_DISPATCH(2);
+#undef BKE_DISPATCH
+}
+
+}  // namespace bke

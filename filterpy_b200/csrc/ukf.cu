@@ -1,0 +1,427 @@
+// ukf.cu — unscented Kalman filter bank (Merwe scaled sigma points), one thread per filter.
+//
+// Per filter (filterpy/kalman/UKF.py:364-411 predict, :413-491 update; sigma_points.py:160-177;
+// unscented_transform.py:99-128; reference @ 3b51149):
+//   U  = chol_upper((n+lambda) P)            rows of U are the sigma offsets (sigma_points.py:168-175)
+//   Xs = {x, x + U[k,:], x - U[k,:]}         2n+1 points, propagated through fx
+//   x- = sum Wm fx(Xs),  P- = sum Wc (fx(Xs)-x-)(..)' + Q           (unscented_transform.py:104-126)
+//   Xs = sigma_points(x-, P-)                 REGENERATED from the prior (UKF.py:407)
+//   Zs = hx(Xs);  z^ = sum Wm Zs;  S = sum Wc dz dz' + R;  Pxz = sum Wc dx dz'   (UKF.py:462-473)
+//   K = Pxz S^-1;  x = x- + K (z - z^);  P = P- - K S K'                        (UKF.py:476-481)
+//
+// Register plan: the covariance accumulators (P-, then S and Pxz), U and the means live in
+// registers; the 2n+1 propagated points are NOT stored — the cheap process models are evaluated
+// twice (mean pass, covariance pass) — while the measurement-space points (which may cost a sqrt
+// and two atan2 each) are parked in a conflict-free [point][component][thread] slab of shared
+// memory.  F / H of the linear models sit in shared memory too (broadcast when shared by the bank).
+// fx / hx are Python callables in the reference; here they come from the closed set in bke.h.
+#include <type_traits>
+#include "bke_internal.cuh"
+#include "kf_regtile.cuh"
+
+namespace bke {
+namespace {
+
+constexpr int UB = 128;      // threads (= filters) per CTA
+
+template <typename T>
+struct UkfP {
+    int64_t N;
+    unsigned flags;
+    T dt;
+    T scale;                 // n + lambda
+    T wm0, wc0, wi;          // Merwe weights (sigma_points.py:180-192)
+    const T *x, *P, *Q, *R, *F, *H, *z;
+    int64_t sQ, sR, sF, sH;
+    const uint8_t *valid;
+    T *x_out, *P_out, *x_prior, *P_prior, *K, *y, *S, *SI, *ll;
+    int32_t *status;
+};
+
+// upper Cholesky factor of A (upper triangle of A is read, like scipy.linalg.cholesky):
+// U'U = A, U upper triangular.  Returns false if A is not positive definite.
+template <typename T, int N>
+__device__ __forceinline__ bool chol_upper(const T (&A)[N][N], T (&U)[N][N])
+{
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        T d = A[j][j];
+#pragma unroll
+        for (int k = 0; k < j; k++) d -= U[k][j] * U[k][j];
+        ok = ok && (d > T(0));
+        T r = sqrt(d);
+        U[j][j] = r;
+        T inv = T(1) / r;
+#pragma unroll
+        for (int i = j + 1; i < N; i++) {
+            T s = A[j][i];
+#pragma unroll
+            for (int k = 0; k < j; k++) s -= U[k][j] * U[k][i];
+            U[j][i] = s * inv;
+        }
+    }
+    return ok;
+}
+
+// sigma point s of (x, U): x, x + U[k,:], x - U[k,:]   (sigma_points.py:171-175)
+template <typename T, int N, int S>
+__device__ __forceinline__ void sigma_point(const T (&x)[N], const T (&U)[N][N], T (&sp)[N])
+{
+    if constexpr (S == 0) {
+#pragma unroll
+        for (int i = 0; i < N; i++) sp[i] = x[i];
+    } else if constexpr (S <= N) {
+        constexpr int k = S - 1;
+#pragma unroll
+        for (int i = 0; i < N; i++) sp[i] = (i >= k) ? x[i] + U[k][i] : x[i];
+    } else {
+        constexpr int k = S - 1 - N;
+#pragma unroll
+        for (int i = 0; i < N; i++) sp[i] = (i >= k) ? x[i] - U[k][i] : x[i];
+    }
+}
+
+template <typename T, int N, int FX>
+__device__ __forceinline__ void apply_fx(const T (&s)[N], T (&f)[N], T dt, const T *Fs, int fstride)
+{
+    if constexpr (FX == BKE_FX_LINEAR) {
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            T a = Fs[(i * N) * fstride] * s[0];
+#pragma unroll
+            for (int j = 1; j < N; j++) a += Fs[(i * N + j) * fstride] * s[j];
+            f[i] = a;
+        }
+    } else {   // BKE_FX_CONST_VEL
+#pragma unroll
+        for (int i = 0; i < N; i += 2) { f[i] = s[i] + dt * s[i + 1]; f[i + 1] = s[i + 1]; }
+    }
+}
+
+template <typename T, int N, int M, int HX>
+__device__ __forceinline__ void apply_hx(const T (&s)[N], T (&h)[M], const T *Hs, int hstride)
+{
+    if constexpr (HX == BKE_HX_LINEAR) {
+#pragma unroll
+        for (int a = 0; a < M; a++) {
+            T v = Hs[(a * N) * hstride] * s[0];
+#pragma unroll
+            for (int j = 1; j < N; j++) v += Hs[(a * N + j) * hstride] * s[j];
+            h[a] = v;
+        }
+    } else if constexpr (HX == BKE_HX_RANGE_AZ_EL) {
+        T px = s[0], py = s[2], pz = s[4];
+        T rho2 = px * px + py * py;
+        h[0] = sqrt(rho2 + pz * pz);
+        h[1] = atan2(py, px);
+        h[2] = atan2(pz, sqrt(rho2));
+    } else {   // BKE_HX_RANGE_BEARING
+        T px = s[0], py = s[2];
+        h[0] = sqrt(px * px + py * py);
+        h[1] = atan2(py, px);
+    }
+}
+
+// compile-time loop over the 2N+1 sigma points
+template <int S, int END, typename Fn>
+__device__ __forceinline__ void for_sigma(Fn &&fn)
+{
+    if constexpr (S < END) {
+        fn(std::integral_constant<int, S>{});
+        for_sigma<S + 1, END>(fn);
+    }
+}
+
+template <typename T, int N, int M, int FX, int HX>
+__global__ void __launch_bounds__(UB) ukf_kernel(UkfP<T> p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NS = 2 * N + 1;
+    T *zs = reinterpret_cast<T *>(smem_raw);                 // [NS*M][UB]
+    T *Fs = zs + NS * M * UB;                                // [N*N] or [N*N][UB]
+    const bool do_p = p.flags & BKE_DO_PREDICT, do_u = p.flags & BKE_DO_UPDATE;
+    const int tid = threadIdx.x;
+    const int64_t f = (int64_t)blockIdx.x * UB + tid;
+    const bool live = f < p.N;
+    const int64_t fc = live ? f : p.N - 1;                   // clamp: dead threads redo the last filter
+
+    // stage F / H (linear models) in shared memory
+    int fstride = 1, foff = 0;
+    T *Hs = Fs;
+    if (FX == BKE_FX_LINEAR && do_p) {
+        if (p.sF == 0) { for (int e = tid; e < N * N; e += UB) Fs[e] = p.F[e]; Hs = Fs + N * N; }
+        else {
+            for (int e = 0; e < N * N; e++) Fs[e * UB + tid] = p.F[fc * p.sF + e];
+            fstride = UB; foff = tid; Hs = Fs + N * N * UB;
+        }
+    }
+    int hstride = 1, hoff = 0;
+    if (HX == BKE_HX_LINEAR && do_u) {
+        if (p.sH == 0) { for (int e = tid; e < M * N; e += UB) Hs[e] = p.H[e]; }
+        else {
+            for (int e = 0; e < M * N; e++) Hs[e * UB + tid] = p.H[fc * p.sH + e];
+            hstride = UB; hoff = tid;
+        }
+    }
+    __syncthreads();
+    const T *Fp = Fs + foff, *Hp = Hs + hoff;
+
+    T x[N], P[N][N];
+#pragma unroll
+    for (int i = 0; i < N; i++) x[i] = p.x[fc * N + i];
+#pragma unroll
+    for (int i = 0; i < N; i++)
+#pragma unroll
+        for (int j = 0; j < N; j++) P[i][j] = p.P[fc * N * N + i * N + j];
+    int st = BKE_STATUS_OK;
+    T U[N][N];
+
+    if (do_p) {
+        T A[N][N];
+#pragma unroll
+        for (int i = 0; i < N; i++)
+#pragma unroll
+            for (int j = 0; j < N; j++) A[i][j] = p.scale * P[i][j];
+        if (!chol_upper<T, N>(A, U)) st = BKE_STATUS_NOT_PD;
+        // pass 1: mean of the propagated points
+        T xm[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) xm[i] = T(0);
+        for_sigma<0, NS>([&](auto sc) {
+            constexpr int S = decltype(sc)::value;
+            T sp[N], fs[N];
+            sigma_point<T, N, S>(x, U, sp);
+            apply_fx<T, N, FX>(sp, fs, p.dt, Fp, fstride);
+            const T w = (S == 0) ? p.wm0 : p.wi;
+#pragma unroll
+            for (int i = 0; i < N; i++) xm[i] += w * fs[i];
+        });
+        // pass 2: covariance
+        T Pm[N][N];
+#pragma unroll
+        for (int i = 0; i < N; i++)
+#pragma unroll
+            for (int j = 0; j < N; j++) Pm[i][j] = T(0);
+        for_sigma<0, NS>([&](auto sc) {
+            constexpr int S = decltype(sc)::value;
+            T sp[N], fs[N];
+            sigma_point<T, N, S>(x, U, sp);
+            apply_fx<T, N, FX>(sp, fs, p.dt, Fp, fstride);
+            const T w = (S == 0) ? p.wc0 : p.wi;
+            T d[N];
+#pragma unroll
+            for (int i = 0; i < N; i++) d[i] = fs[i] - xm[i];
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                T wd = w * d[i];
+#pragma unroll
+                for (int j = 0; j < N; j++) Pm[i][j] += wd * d[j];
+            }
+        });
+        const T *Qf = p.Q + fc * p.sQ;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            x[i] = xm[i];
+#pragma unroll
+            for (int j = 0; j < N; j++) P[i][j] = Pm[i][j] + Qf[i * N + j];
+        }
+        if (live) {
+            if (p.x_prior) for (int i = 0; i < N; i++) p.x_prior[f * N + i] = x[i];
+            if (p.P_prior) for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) p.P_prior[f * N * N + i * N + j] = P[i][j];
+        }
+    }
+
+    if (do_u) {
+        const bool has_z = (p.valid == nullptr) || (p.valid[fc] != 0);
+        if (has_z && st == BKE_STATUS_OK) {
+            // sigma points regenerated from the prior (UKF.py:407)
+            T A[N][N];
+#pragma unroll
+            for (int i = 0; i < N; i++)
+#pragma unroll
+                for (int j = 0; j < N; j++) A[i][j] = p.scale * P[i][j];
+            if (!chol_upper<T, N>(A, U)) st = BKE_STATUS_NOT_PD;
+            T zm[M];
+#pragma unroll
+            for (int a = 0; a < M; a++) zm[a] = T(0);
+            for_sigma<0, NS>([&](auto sc) {
+                constexpr int S = decltype(sc)::value;
+                T sp[N], h[M];
+                sigma_point<T, N, S>(x, U, sp);
+                apply_hx<T, N, M, HX>(sp, h, Hp, hstride);
+                const T w = (S == 0) ? p.wm0 : p.wi;
+#pragma unroll
+                for (int a = 0; a < M; a++) { zm[a] += w * h[a]; zs[(S * M + a) * UB + tid] = h[a]; }
+            });
+            KfUpdateOut<T, N, M> o;
+            T Pxz[N][M];
+#pragma unroll
+            for (int a = 0; a < M; a++)
+#pragma unroll
+                for (int b = 0; b < M; b++) o.S[a][b] = T(0);
+#pragma unroll
+            for (int i = 0; i < N; i++)
+#pragma unroll
+                for (int a = 0; a < M; a++) Pxz[i][a] = T(0);
+            for_sigma<0, NS>([&](auto sc) {
+                constexpr int S = decltype(sc)::value;
+                T sp[N], dz[M], dx[N];
+                sigma_point<T, N, S>(x, U, sp);
+#pragma unroll
+                for (int i = 0; i < N; i++) dx[i] = sp[i] - x[i];
+#pragma unroll
+                for (int a = 0; a < M; a++) dz[a] = zs[(S * M + a) * UB + tid] - zm[a];
+                const T w = (S == 0) ? p.wc0 : p.wi;
+#pragma unroll
+                for (int a = 0; a < M; a++) {
+                    T wd = w * dz[a];
+#pragma unroll
+                    for (int b = 0; b < M; b++) o.S[a][b] += wd * dz[b];
+                }
+#pragma unroll
+                for (int i = 0; i < N; i++) {
+                    T wd = w * dx[i];
+#pragma unroll
+                    for (int a = 0; a < M; a++) Pxz[i][a] += wd * dz[a];
+                }
+            });
+            const T *Rf = p.R + fc * p.sR;
+#pragma unroll
+            for (int a = 0; a < M; a++)
+#pragma unroll
+                for (int b = 0; b < M; b++) o.S[a][b] += Rf[a * M + b];
+            o.ok = reg_inverse<T, M>(o.S, o.SI, o.logdet);
+            if (!o.ok) st = BKE_STATUS_SINGULAR_S;
+            if (o.ok && st == BKE_STATUS_OK) {
+#pragma unroll
+                for (int i = 0; i < N; i++)
+#pragma unroll
+                    for (int a = 0; a < M; a++) {
+                        T s = Pxz[i][0] * o.SI[0][a];
+#pragma unroll
+                        for (int b = 1; b < M; b++) s += Pxz[i][b] * o.SI[b][a];
+                        o.K[i][a] = s;
+                    }
+#pragma unroll
+                for (int a = 0; a < M; a++) o.y[a] = p.z[fc * M + a] - zm[a];
+#pragma unroll
+                for (int i = 0; i < N; i++) {
+                    T s = x[i];
+#pragma unroll
+                    for (int a = 0; a < M; a++) s += o.K[i][a] * o.y[a];
+                    x[i] = s;
+                }
+                // P = P - K (S K')
+                T SK[M][N];
+#pragma unroll
+                for (int a = 0; a < M; a++)
+#pragma unroll
+                    for (int j = 0; j < N; j++) {
+                        T s = o.S[a][0] * o.K[j][0];
+#pragma unroll
+                        for (int b = 1; b < M; b++) s += o.S[a][b] * o.K[j][b];
+                        SK[a][j] = s;
+                    }
+#pragma unroll
+                for (int i = 0; i < N; i++)
+#pragma unroll
+                    for (int j = 0; j < N; j++) {
+                        T s = o.K[i][0] * SK[0][j];
+#pragma unroll
+                        for (int a = 1; a < M; a++) s += o.K[i][a] * SK[a][j];
+                        P[i][j] -= s;
+                    }
+                if (live) {
+                    if (p.K) for (int i = 0; i < N; i++) for (int a = 0; a < M; a++) p.K[f * N * M + i * M + a] = o.K[i][a];
+                    if (p.y) for (int a = 0; a < M; a++) p.y[f * M + a] = o.y[a];
+                    if (p.S) for (int a = 0; a < M; a++) for (int b = 0; b < M; b++) p.S[f * M * M + a * M + b] = o.S[a][b];
+                    if (p.SI) for (int a = 0; a < M; a++) for (int b = 0; b < M; b++) p.SI[f * M * M + a * M + b] = o.SI[a][b];
+                    if (p.ll) {
+                        T q = T(0);
+#pragma unroll
+                        for (int a = 0; a < M; a++) {
+                            T s = T(0);
+#pragma unroll
+                            for (int b = 0; b < M; b++) s += o.SI[a][b] * o.y[b];
+                            q += o.y[a] * s;
+                        }
+                        p.ll[f] = T(-0.5) * (q + o.logdet + T(M) * T(LOG_2PI));
+                    }
+                }
+            }
+        }
+    }
+    if (live) {
+#pragma unroll
+        for (int i = 0; i < N; i++) p.x_out[f * N + i] = x[i];
+#pragma unroll
+        for (int i = 0; i < N; i++)
+#pragma unroll
+            for (int j = 0; j < N; j++) p.P_out[f * N * N + i * N + j] = P[i][j];
+        if (p.status) p.status[f] = st;
+    }
+}
+
+template <typename T, int N, int M, int FX, int HX>
+int launch_inst(const bke_ukf_args &a, cudaStream_t s)
+{
+    UkfP<T> p;
+    const double lambda_ = a.alpha * a.alpha * (N + a.kappa) - N;         // sigma_points.py:167
+    const double c = .5 / (N + lambda_);
+    p.N = a.n_filters; p.flags = a.flags; p.dt = (T)a.dt;
+    p.scale = (T)(lambda_ + N);
+    p.wm0 = (T)(lambda_ / (N + lambda_));
+    p.wc0 = (T)(lambda_ / (N + lambda_) + (1 - a.alpha * a.alpha + a.beta));
+    p.wi = (T)c;
+    p.x = (const T *)a.x; p.P = (const T *)a.P; p.Q = (const T *)a.Q; p.R = (const T *)a.R;
+    p.F = (const T *)a.F; p.H = (const T *)a.H; p.z = (const T *)a.z;
+    p.sQ = a.Q_stride; p.sR = a.R_stride; p.sF = a.F_stride; p.sH = a.H_stride;
+    p.valid = a.z_valid;
+    p.x_out = (T *)a.x_out; p.P_out = (T *)a.P_out; p.x_prior = (T *)a.x_prior; p.P_prior = (T *)a.P_prior;
+    p.K = (T *)a.K; p.y = (T *)a.y; p.S = (T *)a.S; p.SI = (T *)a.SI; p.ll = (T *)a.log_likelihood;
+    p.status = a.status;
+    size_t smem = sizeof(T) * ((2 * N + 1) * M * UB);
+    if (FX == BKE_FX_LINEAR) smem += sizeof(T) * (a.F_stride == 0 ? N * N : N * N * UB);
+    if (HX == BKE_HX_LINEAR) smem += sizeof(T) * (a.H_stride == 0 ? M * N : M * N * UB);
+    auto kern = ukf_kernel<T, N, M, FX, HX>;
+    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
+    int64_t grid = (p.N + UB - 1) / UB;
+    kern<<<(unsigned)grid, UB, smem, s>>>(p);
+    return check_cuda(cudaGetLastError(), "ukf_kernel launch");
+}
+
+template <typename T>
+int dispatch(const bke_ukf_args &a, cudaStream_t s)
+{
+    const int n = a.dim_x, m = a.dim_z, fx = a.fx_model, hx = a.hx_model;
+#define BKE_UKF(NN, MM, FXX, HXX) \
+    if (n == NN && m == MM && fx == FXX && hx == HXX) return launch_inst<T, NN, MM, FXX, HXX>(a, s);
+    BKE_UKF(6, 3, BKE_FX_CONST_VEL, BKE_HX_RANGE_AZ_EL)
+    BKE_UKF(6, 3, BKE_FX_CONST_VEL, BKE_HX_LINEAR)
+    BKE_UKF(6, 3, BKE_FX_LINEAR, BKE_HX_LINEAR)
+    BKE_UKF(6, 3, BKE_FX_LINEAR, BKE_HX_RANGE_AZ_EL)
+    BKE_UKF(4, 2, BKE_FX_CONST_VEL, BKE_HX_RANGE_BEARING)
+    BKE_UKF(4, 2, BKE_FX_LINEAR, BKE_HX_RANGE_BEARING)
+    BKE_UKF(4, 2, BKE_FX_CONST_VEL, BKE_HX_LINEAR)
+    BKE_UKF(4, 2, BKE_FX_LINEAR, BKE_HX_LINEAR)
+    BKE_UKF(1, 1, BKE_FX_LINEAR, BKE_HX_LINEAR)
+    BKE_UKF(2, 1, BKE_FX_LINEAR, BKE_HX_LINEAR)
+    BKE_UKF(2, 1, BKE_FX_CONST_VEL, BKE_HX_LINEAR)
+    BKE_UKF(2, 2, BKE_FX_LINEAR, BKE_HX_LINEAR)
+    BKE_UKF(3, 1, BKE_FX_LINEAR, BKE_HX_LINEAR)
+    BKE_UKF(3, 3, BKE_FX_LINEAR, BKE_HX_LINEAR)
+    BKE_UKF(4, 4, BKE_FX_LINEAR, BKE_HX_LINEAR)
+#undef BKE_UKF
+    set_error("bke_ukf_step: no kernel instance for dim_x=%d dim_z=%d fx_model=%d hx_model=%d", n, m, fx, hx);
+    return BKE_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+
+int launch_ukf(const bke_ukf_args &a, cudaStream_t s)
+{
+    return a.dtype == BKE_F32 ? dispatch<float>(a, s) : dispatch<double>(a, s);
+}
+
+}  // namespace bke

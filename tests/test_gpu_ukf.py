@@ -1,0 +1,108 @@
+"""GPU parity: UKF bank (CUDA through the C-ABI) vs the reference's golden vectors and the oracle."""
+import numpy as np
+import pytest
+
+from test_gpu_kf import rel_close, RTOL
+
+pytestmark = pytest.mark.gpu
+
+
+def build(g, dtype, kind, N=None, diagnostics=True):
+    from filterpy_b200.kalman import (UnscentedKalmanFilter, MerweScaledSigmaPoints, LinearFx, ConstVelFx,
+                                      LinearHx, RangeAzElHx)
+    pts = MerweScaledSigmaPoints(6, float(g["alpha"]), float(g["beta"]), float(g["kappa"]))
+    fx = LinearFx(g["F"]) if kind == "lin" else ConstVelFx()
+    hx = LinearHx(g["H"]) if kind == "lin" else RangeAzElHx()
+    N = g["x"].shape[0] if N is None else N
+    u = UnscentedKalmanFilter(6, 3, float(g["dt"]), hx, fx, pts, n_filters=N, dtype=dtype, diagnostics=diagnostics)
+    u.x = g["x"]; u.P = g["P"]; u.Q = g["Q"]; u.R = g["R"]
+    return u
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("name,kind", [("ukf_bank_rae", "rae"), ("ukf_bank_lin", "lin")])
+def test_ukf_bank_vs_reference_golden(golden, name, kind, dtype):
+    g = golden(name)
+    u = build(g, dtype, kind)
+    rtol = RTOL[dtype] * (5 if dtype is np.float32 else 1)
+    for t in range(g["zs"].shape[0]):
+        v = g["valid"][t]
+        u.predict(); u.update(g["zs"][t], valid=v)
+        rel_close(u.x.cpu().numpy(), g["ref_x"][t], rtol, "x t=%d" % t)
+        rel_close(u.P.cpu().numpy(), g["ref_P"][t], rtol, "P t=%d" % t)
+        rel_close(u.x_prior.cpu().numpy(), g["ref_x_prior"][t], rtol, "x_prior")
+        rel_close(u.P_prior.cpu().numpy(), g["ref_P_prior"][t], rtol, "P_prior")
+        rel_close(u.K.cpu().numpy()[v], g["ref_K"][t][v], rtol * 10, "K")
+        rel_close(u.S.cpu().numpy()[v], g["ref_S"][t][v], rtol * 10, "S")
+        assert int(u.status.sum().item()) == 0
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_ukf_256k_vs_oracle_subset(dtype):
+    """BASELINE config 4 size (2^18 filters, n=6, m=3, range/azimuth/elevation): full bank on the
+    GPU, a 4096-filter random subset checked against the oracle, 3 epochs."""
+    from filterpy_b200.common import workloads as wl
+    from oracle import ukf as oukf
+    N, T = 1 << 18, 3
+    w = wl.ukf_bank_cv3d(N, seed=2468, steps=T)
+    g = dict(w, alpha=0.5, beta=2.0, kappa=0.0, dt=0.1)
+    u = build(g, dtype, "rae", diagnostics=False)
+    sel = np.random.default_rng(0).choice(N, 4096, replace=False)
+    x, P = w["x"][sel], w["P"][sel]
+    for t in range(T):
+        u.predict(); u.update(w["zs"][t])
+        o = oukf.ukf_step_bank(x, P, w["zs"][t][sel], w["Q"][sel], w["R"][sel], 0.1, 0.5, 2.0, 0.0,
+                               oukf.FX_CONST_VEL, oukf.HX_RANGE_AZ_EL)
+        x, P = o["x"], o["P"]
+    rtol = RTOL[dtype] * (10 if dtype is np.float32 else 1)
+    rel_close(u.x.cpu().numpy()[sel], x, rtol, "x"); rel_close(u.P.cpu().numpy()[sel], P, rtol, "P")
+
+
+def test_ukf_matches_linear_kf_on_linear_model():
+    """test_ukf.py:893-979: on a linear model the UKF equals the linear KF (atol 1e-7 there)."""
+    from filterpy_b200.kalman import KalmanFilter
+    from filterpy_b200.common import workloads as wl
+    N, T = 512, 10
+    w = wl.ukf_bank_cv3d(N, seed=1, steps=T, linear_hx=True)
+    g = dict(w, alpha=0.5, beta=2.0, kappa=0.0, dt=0.1)
+    u = build(g, np.float64, "lin", diagnostics=False)
+    kf = KalmanFilter(6, 3, n_filters=N, diagnostics=False)
+    kf.x = w["x"]; kf.P = w["P"]; kf.F = w["F"]; kf.H = w["H"]; kf.Q = w["Q"]; kf.R = w["R"]
+    for t in range(T):
+        u.predict(); u.update(w["zs"][t])
+        kf.predict(); kf.update(w["zs"][t])
+    np.testing.assert_allclose(u.x.cpu().numpy(), kf.x.cpu().numpy(), rtol=1e-7, atol=1e-7)
+    np.testing.assert_allclose(u.P.cpu().numpy(), kf.P.cpu().numpy(), rtol=1e-6, atol=1e-7)
+
+
+def test_ukf_single_mode_batch_filter_equals_loop(golden):
+    """test_ukf.py:506: batch_filter == the predict/update loop (bit-equal there)."""
+    from filterpy_b200.kalman import UnscentedKalmanFilter, MerweScaledSigmaPoints, ConstVelFx, RangeAzElHx
+    g = golden("ukf_bank_rae")
+
+    def mk():
+        u = UnscentedKalmanFilter(6, 3, 0.1, RangeAzElHx(), ConstVelFx(), MerweScaledSigmaPoints(6, .5, 2., 0.))
+        u.x = g["x"][0]; u.P = g["P"][0]; u.Q = g["Q"][0]; u.R = g["R"][0]
+        return u
+    a, b = mk(), mk()
+    zs = [g["zs"][t, 0] for t in range(5)]
+    M, C = a.batch_filter(zs)
+    xs = []
+    for z in zs:
+        b.predict(); b.update(z); xs.append(b.x.copy())
+    assert M.shape == (5, 6) and C.shape == (5, 6, 6)
+    assert np.array_equal(M, np.array(xs))
+    with pytest.raises(NotImplementedError):
+        UnscentedKalmanFilter(6, 3, 0.1, lambda x: x[:3], lambda x, dt: x, MerweScaledSigmaPoints(6, .5, 2., 0.))
+    with pytest.raises(TypeError):
+        a.batch_filter(3.0)
+
+
+def test_ukf_not_pd_status():
+    from filterpy_b200.kalman import UnscentedKalmanFilter, MerweScaledSigmaPoints, ConstVelFx, LinearHx
+    H = np.zeros((1, 2)); H[0, 0] = 1
+    u = UnscentedKalmanFilter(2, 1, 1.0, LinearHx(H), ConstVelFx(), MerweScaledSigmaPoints(2, .5, 2., 1.), n_filters=3)
+    P = np.array([np.eye(2), -np.eye(2), np.eye(2)])
+    u.P = P
+    u.predict(); u.update(np.zeros((3, 1)))
+    assert u.status.cpu().numpy().tolist() == [0, 2, 0]
