@@ -94,6 +94,12 @@ __device__ __forceinline__ float4 lds_chunk(const unsigned char *base, int row, 
     return *reinterpret_cast<const float4 *>(base + off);
 }
 
+// make the compiler wait for (and keep) four loaded registers at this point of the program
+__device__ __forceinline__ void consume4(const float (&v)[4])
+{
+    asm volatile("" ::"f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+}
+
 struct Maps {
     CUtensorMap x, P, F, Q, H, R, z;
 };
@@ -215,6 +221,24 @@ kf42_f32_kernel(const __grid_constant__ Maps maps, const FastP<4, 2> p)
             float2 v = *reinterpret_cast<const float2 *>(sb + St::OZ + tid * 8);
             z[0] = v.x; z[1] = v.y;
         }
+        // The stage is about to be handed back to the TMA engine (async proxy).  A barrier alone
+        // does not order the LDS above against that: the loads may still sit in the LSU queue when
+        // the barrier releases, and a TMA refill served from L2 can land first (observed: a few
+        // filters per launch picked up rows of the NEXT tile).  Consuming every loaded register
+        // forces the scoreboard wait for the LDS results before the barrier.
+        consume4(x);
+#pragma unroll
+        for (int i = 0; i < N; i++) consume4(P[i]);
+        if (!SHARED && DO_P) {
+#pragma unroll
+            for (int i = 0; i < N; i++) { consume4(F[i]); consume4(Q[i]); }
+        }
+        if (!SHARED && DO_U) {
+#pragma unroll
+            for (int a = 0; a < M; a++) consume4(H[a]);
+            asm volatile("" ::"f"(R[0][0]), "f"(R[0][1]), "f"(R[1][0]), "f"(R[1][1]) : "memory");
+        }
+        if (DO_U) asm volatile("" ::"f"(z[0]), "f"(z[1]) : "memory");
         __syncthreads();      // every thread has drained the stage
         if (tid == 0) {
             int nt = tile + STAGES * gridDim.x;

@@ -38,6 +38,7 @@ constexpr int UMAX = 2048;               // tiles with raw elements before givin
 constexpr int EXPAND = 4096;             // outputs expanded per shared-memory pass
 constexpr int BIGRUN = 2 * EXPAND;       // runs this long go to the fill kernel
 constexpr int CHAIN_THREADS = 1024;
+constexpr int CHAIN_BATCH = 8;          // unclean tiles staged in shared memory per round of the chain
 
 typedef long long i64;
 typedef unsigned long long u64;
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_scan_tiles(Params p)
 struct TileAn {
     double w[IPT];
     SMap inc[IPT];         // inclusive segmented parity map at each element
-    int ek[IPT];           // binade assumed for the element (clean) or -1 (raw)
+    int ek[IPT];           // binade assumed for the element (clean), -2 (zero weight) or -1 (raw)
     int nraw;              // raw elements in the tile
     SMap total;            // tile aggregate
 };
@@ -334,7 +335,10 @@ __device__ __forceinline__ void analyse_tile(const Params &p, int t, TileAn &an,
         int e = efield(lo);
         bool clean = (efield(hi) == e) && (hi < 1.0e308);
         SMap el;
-        if (clean) {
+        if (an.w[k] == 0.0) {            // fl(S + 0) = S in every binade: a binade-neutral identity
+            el = SMap{0, 0, 0, -2};
+            an.ek[k] = -2;
+        } else if (clean) {
             Map m = elem_map(an.w[k], e);
             el = SMap{m.d0, m.d1, 0, e};
             an.ek[k] = e;
@@ -365,8 +369,8 @@ __global__ void __launch_bounds__(BLOCK) k_tile_maps(Params p)
     analyse_tile(p, t, an, sm);
     if (an.nraw == 0) {
         if (threadIdx.x == BLOCK - 1) {
-            if (an.total.k < 0) p.ws.hdr->fallback = 1;      // mixed binades inside one map (never expected)
-            p.ws.tile_k[t] = an.total.k < 0 ? 0 : an.total.k;
+            if (an.total.k == -3) p.ws.hdr->fallback = 1;    // mixed binades inside one map (never expected)
+            p.ws.tile_k[t] = an.total.k;                     // binade, or -2 for an all-zero tile
             p.ws.tile_map[2 * t] = an.total.d0;
             p.ws.tile_map[2 * t + 1] = an.total.d1;
             p.ws.tile_slot[t] = -1;
@@ -382,10 +386,10 @@ __global__ void __launch_bounds__(BLOCK) k_tile_maps(Params p)
         if (s < 0) p.ws.hdr->fallback = 1;
         s_slot = s;
         p.ws.tile_k[t] = -1;
-        p.ws.tile_slot[t] = s;
+        p.ws.tile_slot[t] = s < 0 ? 0 : s;
     }
     // raw flag of the element that follows each thread's last element
-    sm.first_raw[threadIdx.x] = (an.ek[0] < 0);
+    sm.first_raw[threadIdx.x] = (an.ek[0] == -1);
     if (threadIdx.x == 0) sm.first_raw[BLOCK] = 1;       // the tile end closes the last segment
     __syncthreads();
     const int s = s_slot;
@@ -397,13 +401,15 @@ __global__ void __launch_bounds__(BLOCK) k_tile_maps(Params p)
 #pragma unroll
     for (int k = 0; k < IPT; k++) {
         const int seg = an.inc[k].cnt;
-        if (an.ek[k] < 0) {
+        if (an.ek[k] == -1) {
             sl->wraw[seg - 1] = an.w[k];                 // the raw element that opens segment `seg`
         } else {
-            bool next_raw = (k + 1 < IPT) ? (an.ek[k + 1] < 0) : (sm.first_raw[threadIdx.x + 1] != 0);
+            bool next_raw = (k + 1 < IPT) ? (an.ek[k + 1] == -1) : (sm.first_raw[threadIdx.x + 1] != 0);
             if (next_raw) {
-                if (an.inc[k].k < 0) p.ws.hdr->fallback = 1;
-                sl->segk[seg] = an.ek[k]; sl->end0[seg] = an.inc[k].d0; sl->end1[seg] = an.inc[k].d1;
+                if (an.inc[k].k == -3) p.ws.hdr->fallback = 1;
+                // k == -2: only zero weights in the segment -> identity, recorded as empty
+                sl->segk[seg] = an.inc[k].k == -2 ? -1 : an.inc[k].k;
+                sl->end0[seg] = an.inc[k].d0; sl->end1[seg] = an.inc[k].d1;
             }
         }
     }
@@ -448,9 +454,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain(Params p, double carry)
     const int a = threadIdx.x * per, b = min(T, a + per);
     // element of tile t: clean -> its map (cnt 0); unclean -> reset marker (cnt 1, identity)
     auto tile_el = [&](int t) {
-        int k = ws.tile_k[t];
-        if (k < 0) return RunEl{0, 0, 1, -2};
-        return RunEl{ws.tile_map[2 * t], ws.tile_map[2 * t + 1], 0, k};
+        if (ws.tile_slot[t] >= 0) return RunEl{0, 0, 1, -2};
+        return RunEl{ws.tile_map[2 * t], ws.tile_map[2 * t + 1], 0, ws.tile_k[t]};
     };
     RunEl agg = RunEl{0, 0, 0, -2};
     for (int t = a; t < b; t++) agg = run_combine(agg, tile_el(t), &bad);
@@ -466,22 +471,45 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain(Params p, double carry)
         // exclusive value at tile t: composite of the clean tiles since the last unclean tile
         ws.run_map[2 * t] = run.d0; ws.run_map[2 * t + 1] = run.d1;
         ws.run_id[t] = run.cnt; ws.run_k[t] = run.k;
-        if (ws.tile_k[t] < 0) ws.ord2tile[run.cnt] = t;
+        if (ws.tile_slot[t] >= 0) ws.ord2tile[run.cnt] = t;
         run = run_combine(run, tile_el(t), &bad);
     }
     __threadfence_block();
     __syncthreads();
-    // sequential part: one thread walks the tiles that contain raw elements
-    if (threadIdx.x == 0) {
+    // sequential part: one thread walks the tiles that contain raw elements.  Their slot data is
+    // staged into shared memory by the whole block first (a dependent chain of global loads would
+    // cost ~1 us per hop), CHAIN_BATCH tiles at a time.
+    {
+        __shared__ Slot s_slots[CHAIN_BATCH];
+        __shared__ i64 s_rm[CHAIN_BATCH][2];
+        __shared__ int s_rk[CHAIN_BATCH];
+        __shared__ double s_S;
         const int U = ws.hdr->n_unclean;
-        double S = carry;
-        ws.S_run[0] = S;
-        for (int i = 0; i < U; i++) {
-            const int t = ws.ord2tile[i];
-            if (ws.run_k[t] != -2) S = apply_map(S, Map{ws.run_map[2 * t], ws.run_map[2 * t + 1]}, ws.run_k[t], &bad);
-            const Slot *sl = &ws.slots[ws.tile_slot[t]];
-            S = walk_slot(sl->segk, sl->end0, sl->end1, sl->wraw, sl->nraw, S, &bad, nullptr);
-            ws.S_run[i + 1] = S;
+        if (threadIdx.x == 0) { s_S = carry; ws.S_run[0] = carry; }
+        for (int i0 = 0; i0 < U; i0 += CHAIN_BATCH) {
+            const int nb = min(CHAIN_BATCH, U - i0);
+            __syncthreads();
+            for (int q = threadIdx.x; q < nb * (int)(sizeof(Slot) / sizeof(int)); q += CHAIN_THREADS) {
+                const int b = q / (int)(sizeof(Slot) / sizeof(int)), o = q % (int)(sizeof(Slot) / sizeof(int));
+                const int t = ws.ord2tile[i0 + b];
+                reinterpret_cast<int *>(&s_slots[b])[o] = reinterpret_cast<const int *>(&ws.slots[ws.tile_slot[t]])[o];
+            }
+            if (threadIdx.x < nb) {
+                const int t = ws.ord2tile[i0 + threadIdx.x];
+                s_rm[threadIdx.x][0] = ws.run_map[2 * t]; s_rm[threadIdx.x][1] = ws.run_map[2 * t + 1];
+                s_rk[threadIdx.x] = ws.run_k[t];
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double S = s_S;
+                for (int b = 0; b < nb; b++) {
+                    if (s_rk[b] != -2) S = apply_map(S, Map{s_rm[b][0], s_rm[b][1]}, s_rk[b], &bad);
+                    const Slot *sl = &s_slots[b];
+                    S = walk_slot(sl->segk, sl->end0, sl->end1, sl->wraw, sl->nraw, S, &bad, nullptr);
+                    ws.S_run[i0 + b + 1] = S;
+                }
+                s_S = S;
+            }
         }
     }
     __threadfence_block();
@@ -492,8 +520,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain(Params p, double carry)
         double S = ws.S_run[ws.run_id[t]];
         if (ws.run_k[t] != -2) S = apply_map(S, Map{ws.run_map[2 * t], ws.run_map[2 * t + 1]}, ws.run_k[t], &bad);
         ws.S_in[t] = S;
-        if (ws.tile_k[t] >= 0) {
-            double E = apply_map(S, Map{ws.tile_map[2 * t], ws.tile_map[2 * t + 1]}, ws.tile_k[t], &bad);
+        if (ws.tile_slot[t] < 0) {
+            double E = ws.tile_k[t] >= 0 ? apply_map(S, Map{ws.tile_map[2 * t], ws.tile_map[2 * t + 1]}, ws.tile_k[t], &bad) : S;
             if (t == T - 1) S_last = E;
         } else if (t == T - 1) {
             S_last = ws.S_run[ws.run_id[t] + 1];
@@ -572,17 +600,20 @@ __global__ void __launch_bounds__(BLOCK) k_emit(Params p)
     const double S_in = ws.S_in[t];
     // segment start states (exact)
     if (an.nraw > 0) {
-        sm.ts.first_raw[tid] = (an.ek[0] < 0);
+        sm.ts.first_raw[tid] = (an.ek[0] == -1);
         if (tid == 0) sm.ts.first_raw[BLOCK] = 1;
         for (int q = tid; q <= RMAX; q += BLOCK) { sm.segk[q] = -1; sm.end0[q] = 0; sm.end1[q] = 0; }
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < IPT; k++) {
             const int seg = an.inc[k].cnt;
-            if (an.ek[k] < 0) sm.wraw[seg - 1] = an.w[k];
+            if (an.ek[k] == -1) sm.wraw[seg - 1] = an.w[k];
             else {
-                bool next_raw = (k + 1 < IPT) ? (an.ek[k + 1] < 0) : (sm.ts.first_raw[tid + 1] != 0);
-                if (next_raw) { sm.segk[seg] = an.ek[k]; sm.end0[seg] = an.inc[k].d0; sm.end1[seg] = an.inc[k].d1; }
+                bool next_raw = (k + 1 < IPT) ? (an.ek[k + 1] == -1) : (sm.ts.first_raw[tid + 1] != 0);
+                if (next_raw) {
+                    sm.segk[seg] = an.inc[k].k == -2 ? -1 : an.inc[k].k;
+                    sm.end0[seg] = an.inc[k].d0; sm.end1[seg] = an.inc[k].d1;
+                }
             }
         }
         __syncthreads();
@@ -607,7 +638,8 @@ __global__ void __launch_bounds__(BLOCK) k_emit(Params p)
     for (int k = 0; k < IPT; k++) {
         const int seg = an.inc[k].cnt;
         double S0 = sm.segstate[seg];
-        double c = (an.ek[k] < 0) ? S0 : apply_map(S0, Map{an.inc[k].d0, an.inc[k].d1}, an.ek[k], &bad);
+        // raw element: the segment it opens starts at its own result; only zeros so far: unchanged
+        double c = (an.ek[k] == -1 || an.inc[k].k == -2) ? S0 : apply_map(S0, Map{an.inc[k].d0, an.inc[k].d1}, an.inc[k].k, &bad);
         i64 h;
         if (jbase + k < p.n) {
             h = p.U ? count_below_str(c, p.U, p.n, Nd) : count_below_sys(c, p.u, p.n, Nd, p.tau);

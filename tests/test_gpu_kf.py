@@ -126,7 +126,9 @@ def test_full_size_properties_f32():
     for k in "xPFHQR":
         setattr(sub, k, w[k][sl])
     sub.predict(); sub.update(w["zs"][0][sl])
-    assert torch.equal(kf.x[sl], sub.x) and torch.equal(kf.P[sl], sub.P)
+    dx = (kf.x[sl] - sub.x).abs().max().item(); dP = (kf.P[sl] - sub.P).abs().max().item()
+    nbad = int(((kf.P[sl] != sub.P).any(dim=2).any(dim=1)).sum().item())
+    assert torch.equal(kf.x[sl], sub.x) and torch.equal(kf.P[sl], sub.P), (dx, dP, nbad)
     P = kf.P
     assert float((P - P.transpose(1, 2)).abs().max() / P.abs().max()) < 1e-5
     kf2 = KalmanFilter(4, 2, n_filters=N, dtype=np.float32, diagnostics=False)

@@ -1,0 +1,122 @@
+"""Host-side logic that needs no GPU: shape rules, weights, workload generators, sharding."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from filterpy_b200.common.helpers import reshape_z
+from filterpy_b200.common import workloads as wl
+from filterpy_b200.kalman.sigma_points import MerweScaledSigmaPoints
+from filterpy_b200 import distributed as bd
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reshape_z_contract():
+    # filterpy/common/helpers.py:324-342 — accepted and rejected shapes (test_kf.py:529-654)
+    assert reshape_z(3.0, 1, 2).shape == (1, 1)
+    assert reshape_z([1., 2.], 2, 2).shape == (2, 1)
+    assert reshape_z([[1., 2.]], 2, 1).shape == (2,)
+    assert reshape_z([[1.], [2.]], 2, 1).shape == (2,)
+    assert reshape_z(3.0, 1, 0) == 3.0
+    for bad in ([1., 2., 3.], [[1., 2.], [3., 4.], [5., 6.]]):
+        with pytest.raises(ValueError):
+            reshape_z(bad, 2, 2)
+
+
+def test_merwe_weights_golden(golden):
+    g = golden("ukf_sigma")
+    p = MerweScaledSigmaPoints(6, float(g["alpha"]), float(g["beta"]), float(g["kappa"]))
+    np.testing.assert_allclose(p.Wm, g["Wm"], rtol=1e-15)
+    np.testing.assert_allclose(p.Wc, g["Wc"], rtol=1e-15)
+    assert p.num_sigmas() == 13
+    p4 = MerweScaledSigmaPoints(4, .5, 2, 0)
+    np.testing.assert_allclose(p4.Wm, g["Wm4"]); np.testing.assert_allclose(p4.Wc, g["Wc4"])
+    assert abs(p4.Wm.sum() - 1) < 1e-12       # test_ukf.py:102-109
+    with pytest.raises(NotImplementedError):
+        MerweScaledSigmaPoints(4, .5, 2, 0, sqrt_method=np.linalg.cholesky)
+
+
+def test_workloads_are_seeded_and_well_posed():
+    a = wl.kf_bank_cv2d(100, seed=5, steps=2); b = wl.kf_bank_cv2d(100, seed=5, steps=2)
+    assert all(np.array_equal(a[k], b[k]) for k in a)
+    assert a["F"].shape == (100, 4, 4) and a["H"].shape == (100, 2, 4) and a["zs"].shape == (2, 100, 2)
+    c = wl.kf_bank_ca3d(10, steps=1)
+    assert c["F"].shape == (10, 9, 9) and c["H"][0, 1, 3] == 1 and c["H"][0].sum() == 3
+    # Q blocks are symmetric PSD
+    assert np.allclose(c["Q"], np.swapaxes(c["Q"], 1, 2)) and np.linalg.eigvalsh(c["Q"]).min() > -1e-12
+    for kind in ["heavy", "uniform", "random", "zeros", "degenerate"]:
+        w = wl.resample_weights(1000, kind)
+        assert abs(w.sum() - 1) < 1e-12 and w.min() >= 0
+    d = wl.resample_weights(1000, "dyadic")
+    assert np.all(d * 2.0 ** 52 == np.floor(d * 2.0 ** 52))
+
+
+def test_shard_bounds():
+    b = bd.shard_bounds(10, 4)
+    assert b.tolist() == [0, 3, 6, 8, 10]
+    assert bd.shard_bounds(1 << 20, 8)[-1] == 1 << 20
+    x = np.arange(10)
+    parts = [bd.shard_of(x, r, 4) for r in range(4)]
+    assert np.array_equal(np.concatenate(parts), x)
+
+
+_WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from filterpy_b200 import distributed as bd
+from filterpy_b200.common import workloads as wl
+from oracle import kf as okf, resample as ors
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+# (1) bank sharding: every rank steps its slice with the oracle; the gathered result equals the full bank
+N = 37
+w = wl.kf_bank_cv2d(N, seed=3, steps=1)
+sl = {k: bd.shard_of(v, rank, world, axis=1 if k == "zs" else 0) for k, v in w.items()}
+o = okf.kf_step_bank(sl["x"], sl["P"], sl["zs"][0], sl["F"], sl["H"], sl["Q"], sl["R"])
+parts = [None] * world
+dist.all_gather_object(parts, o["x"])
+full = okf.kf_step_bank(w["x"], w["P"], w["zs"][0], w["F"], w["H"], w["Q"], w["R"])["x"]
+assert np.array_equal(np.concatenate(parts), full)
+# (2) particle-weight sum all-reduce + exclusive prefix of shard sums
+wts = wl.resample_weights(1001, "heavy", seed=1)
+mine = bd.shard_of(wts, rank, world)
+s = torch.tensor([mine.sum()], dtype=torch.float64)
+tot = bd.all_reduce_sum(s.clone())
+assert abs(float(tot) - wts.sum()) < 1e-12
+pre = bd.exclusive_prefix(s)
+b = bd.shard_bounds(len(wts), world)
+assert abs(float(pre) - wts[:b[rank]].sum()) < 1e-12
+# (3) sharded resampling semantics: rank r owns outputs [cnt(c_start), cnt(c_end)); concatenation == reference
+u = 0.3
+idx = ors.systematic_resample_vec(wts, u)
+c = np.cumsum(wts)
+pos = ors.positions_systematic(len(wts), u)
+lo = 0 if rank == 0 else int(np.searchsorted(pos, c[b[rank] - 1], side="left"))
+hi = int(np.searchsorted(pos, c[b[rank + 1] - 1], side="left"))
+local = idx[lo:hi]
+assert local.size == 0 or (local.min() >= b[rank] and local.max() < b[rank + 1])
+cnts = [None] * world
+dist.all_gather_object(cnts, (lo, hi))
+assert cnts[0][0] == 0 and all(cnts[i][1] == cnts[i + 1][0] for i in range(world - 1)) and cnts[-1][1] == len(wts)
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_gloo_world_size_2(tmp_path):
+    """The N>1 host path on CPU: 2 ranks over gloo (sharding, weight-sum all-reduce, shard prefix,
+    output-range ownership of a sharded resample)."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = 29500 + (os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script), ROOT]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout

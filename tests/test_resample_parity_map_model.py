@@ -38,6 +38,18 @@ def limit_of(e):
 
 
 def elem_map(w, e):
+    """Parity map of adding w in binade e, computed as csrc/resample.cu does: two IEEE adds on the
+    binade base (even mantissa) and base+1ulp (odd mantissa); bit patterns of positive doubles
+    are linear in units of the ulp inside a binade."""
+    base = e << 52
+    d0 = bits(from_bits(base) + w) - base
+    d1 = bits(from_bits(base + 1) + w) - (base + 1)
+    assert d1 - d0 in (-1, 0, 1)
+    return (d0, d1)
+
+
+def elem_map_reference(w, e):
+    """The same map from first principles (integer rounding of w / ulp)."""
     b = bits(w)
     ew = (b >> 52) & 0x7FF
     mw = (b & ((1 << 52) - 1)) | ((1 << 52) if ew else 0)
@@ -63,11 +75,12 @@ def compose(f, g):
 
 
 def apply_map(S, m, e):
-    assert efield(S) == e, "start state left the assumed binade"
-    si = sint(S)
-    si += m[1] if (si & 1) else m[0]
-    assert si < limit_of(e), "end state left the assumed binade"
-    return rebuild(e, si)
+    """State advanced on its BIT PATTERN (csrc/resample.cu:apply_map)."""
+    sb = bits(S)
+    assert (sb >> 52) == e, "start state left the assumed binade"
+    sb += m[1] if (sb & 1) else m[0]
+    assert (sb >> 52) == e, "end state left the assumed binade"
+    return from_bits(sb)
 
 
 def exact_cumsum_model(w, chunk=64):
@@ -153,3 +166,15 @@ def test_tie_rule_matches_ieee():
             w = mult * q
             m = elem_map(w, e)
             assert apply_map(S, m, e) == S + w, (S, mult)
+
+
+def test_dadd_trick_equals_integer_rounding():
+    rng = np.random.default_rng(0)
+    for e in (0, 1, 2, 500, 1000, 1022, 1023, 1030):
+        q = 2.0 ** (max(e, 1) - 1075)
+        top = 2.0 ** (max(e, 1) - 1023)
+        ws = list(rng.random(200) * top * 0.9) + [k * q * 0.5 for k in range(0, 40)] + [0.0, q / 2, q / 4, 3 * q / 4, q]
+        for w in ws:
+            m = elem_map(w, e)
+            if m[0] < (1 << 52) and m[1] < (1 << 52):
+                assert m == elem_map_reference(w, e), (e, w)
