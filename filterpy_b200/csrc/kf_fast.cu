@@ -16,6 +16,7 @@
 //
 // Reference arithmetic: filterpy/kalman/kalman_filter.py:471-478, 533-556 (see kf_regtile.cuh).
 #include <cuda.h>
+#include <stdlib.h>
 #include "bke_internal.cuh"
 #include "kf_regtile.cuh"
 
@@ -30,6 +31,7 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -61,7 +63,6 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const CUtensorMap *map, i
 
 // ---------------------------------------------------------------------------- tile geometry
 constexpr int TILE = 128;       // filters per tile == threads per CTA
-constexpr int STAGES = 2;
 
 template <typename T, int N, int M>
 struct Stage {
@@ -94,12 +95,6 @@ __device__ __forceinline__ float4 lds_chunk(const unsigned char *base, int row, 
     return *reinterpret_cast<const float4 *>(base + off);
 }
 
-// make the compiler wait for (and keep) four loaded registers at this point of the program
-__device__ __forceinline__ void consume4(const float (&v)[4])
-{
-    asm volatile("" ::"f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
-}
-
 struct Maps {
     CUtensorMap x, P, F, Q, H, R, z;
 };
@@ -117,7 +112,7 @@ struct FastP {
 };
 
 // MODE: 3 = predict+update, 1 = predict only, 2 = update only
-template <int MODE, bool SHARED, bool EXTRAS>
+template <int MODE, bool SHARED, bool EXTRAS, int STAGES>
 __global__ void __launch_bounds__(TILE, 3)
 kf42_f32_kernel(const __grid_constant__ Maps maps, const FastP<4, 2> p)
 {
@@ -222,23 +217,13 @@ kf42_f32_kernel(const __grid_constant__ Maps maps, const FastP<4, 2> p)
             z[0] = v.x; z[1] = v.y;
         }
         // The stage is about to be handed back to the TMA engine (async proxy).  A barrier alone
-        // does not order the LDS above against that: the loads may still sit in the LSU queue when
-        // the barrier releases, and a TMA refill served from L2 can land first (observed: a few
-        // filters per launch picked up rows of the NEXT tile).  Consuming every loaded register
-        // forces the scoreboard wait for the LDS results before the barrier.
-        consume4(x);
-#pragma unroll
-        for (int i = 0; i < N; i++) consume4(P[i]);
-        if (!SHARED && DO_P) {
-#pragma unroll
-            for (int i = 0; i < N; i++) { consume4(F[i]); consume4(Q[i]); }
-        }
-        if (!SHARED && DO_U) {
-#pragma unroll
-            for (int a = 0; a < M; a++) consume4(H[a]);
-            asm volatile("" ::"f"(R[0][0]), "f"(R[0][1]), "f"(R[1][0]), "f"(R[1][1]) : "memory");
-        }
-        if (DO_U) asm volatile("" ::"f"(z[0]), "f"(z[1]) : "memory");
+        // does not order the generic-proxy LDS above against that: the loads may still sit in the
+        // LSU queue when the barrier releases, and a TMA refill served from L2 can land first
+        // (observed in round 1: a few filters per launch picked up rows of the NEXT tile; an empty
+        // asm "use" of the registers does not help, the scoreboard wait rides on the first real
+        // consumer instruction).  The cross-proxy fence makes every thread's reads of the stage
+        // complete before it arrives at the barrier.
+        fence_proxy_async();
         __syncthreads();      // every thread has drained the stage
         if (tid == 0) {
             int nt = tile + STAGES * gridDim.x;
@@ -358,18 +343,33 @@ bool make_map_1d(CUtensorMap *m, const void *base, int64_t elems, int box_elems)
     return r == CUDA_SUCCESS;
 }
 
-template <int MODE, bool SHARED, bool EXTRAS>
-int launch_variant(const Maps &maps, const FastP<4, 2> &p, cudaStream_t s)
+// tuning knobs (environment, read once): BKE_KF_STAGES in {2,3}, BKE_KF_CTAS = resident CTAs per SM
+int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+template <int MODE, bool SHARED, bool EXTRAS, int STAGES>
+int launch_variant_s(const Maps &maps, const FastP<4, 2> &p, cudaStream_t s, int ctas_per_sm)
 {
     using St = Stage<float, 4, 2>;
-    auto kern = kf42_f32_kernel<MODE, SHARED, EXTRAS>;
+    auto kern = kf42_f32_kernel<MODE, SHARED, EXTRAS, STAGES>;
     const int smem = STAGES * St::BYTES;
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
-    int ctas_per_sm = 3;
     int grid = sm_count() * ctas_per_sm;
     if (grid > p.num_tiles) grid = p.num_tiles;
     kern<<<grid, TILE, smem, s>>>(maps, p);
     return check_cuda(cudaGetLastError(), "kf42_f32_kernel launch");
+}
+
+template <int MODE, bool SHARED, bool EXTRAS>
+int launch_variant(const Maps &maps, const FastP<4, 2> &p, cudaStream_t s)
+{
+    static const int stages = env_int("BKE_KF_STAGES", 2);
+    static const int ctas = env_int("BKE_KF_CTAS", 3);
+    if (stages == 3) return launch_variant_s<MODE, SHARED, EXTRAS, 3>(maps, p, s, ctas > 2 ? 2 : ctas);
+    return launch_variant_s<MODE, SHARED, EXTRAS, 2>(maps, p, s, ctas > 3 ? 3 : ctas);
 }
 
 }  // namespace

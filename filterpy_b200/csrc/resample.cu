@@ -6,25 +6,29 @@
 //
 // A parallel fp64 scan rounds in a different order than np.cumsum and flips output indices, so the
 // running sum is reproduced EXACTLY instead.  While the running sum S stays inside one binade
-// (exponent field e, ulp q = 2^(max(e,1)-1075)) it is an integer multiple of q, and adding a weight
-// w is the integer map  S/q -> S/q + d[parity(S/q)]  with d0 = d1 = rne(w/q) except for an exact
-// tie (fraction 1/2), which rounds to the even neighbour and therefore depends on the parity.
+// (exponent field e) it is an integer multiple of the binade's ulp q, its int64 BIT PATTERN is
+// linear in units of q, and adding a weight w is the integer map
+//       bits(S) -> bits(S) + d[parity(bits(S))],      d0 = rne(w/q) for an even mantissa,
+// d1 for an odd one; d1 != d0 only for an exact tie (round-half-even).  d0 and d1 come from two IEEE
+// adds on the binade base: d0 = bits(2^e + w) - bits(2^e), d1 = bits(nextafter(2^e) + w) - bits(..).
 // Such parity maps compose associatively ((f;g)[p] = f[p] + g[(p + f[p]) & 1]), so a parallel scan
-// over them reproduces the sequential rounding.  The few elements whose addition may leave the
-// binade ("raw" elements, found with an approximate scan and a rigorous error margin) are applied
-// by a true fp64 add in a tiny sequential chain.  Every assumption (start and end of a mapped
-// segment in the assumed binade) is verified with the exact values; if one fails, or the weights
-// contain negative / non-finite entries, a literal single-thread transcription of the reference
-// loop produces the result instead (info[1] = 1), so the output is always the reference's.
+// over them reproduces the sequential rounding.  Zero weights are identities in every binade.  The
+// few elements whose addition may leave the binade ("raw" elements, found with an approximate
+// scan and a rigorous error margin) are applied by a true fp64 add in a tiny sequential chain.
+// Every mapped segment is VERIFIED with the exact values (start and end inside the assumed
+// binade); if a check fails, or the weights contain negative / non-finite entries, a literal
+// single-thread transcription of the reference loop produces the result instead (info[1] = 1), so
+// the output is always the reference's.  tests/test_resample_parity_map_model.py checks this
+// arithmetic on the CPU against np.cumsum bit for bit.
 //
 // Passes (all on one stream, no host sync):
-//   A  tile sums (approximate, fp64 tree)            reads w
-//   B  exclusive scan of tile sums                   1 CTA
-//   C  per-tile parity maps / raw-element lists      reads w
-//   D  exact chain over tiles                        1 CTA
-//   E  exact c_j, output ranges, index expansion     reads w, writes indexes
-//   F  long runs (one particle copied >= 8192 times) writes indexes
-//   G  sequential fallback (normally exits at once)
+//   A  tile sums (approximate, fp64 tree), input validation      reads w (coalesced 16-byte loads)
+//   B  exclusive scan of the tile sums                           1 CTA, warp-striped
+//   C  per-tile parity maps / raw-element lists                  reads w
+//   D  exact chain over tiles                                    1 CTA: segmented scan + short walk
+//   E  exact c_j, output ranges, shared-memory index expansion   reads w, writes indexes (coalesced)
+//   F  long runs (one particle copied >= 8192 times)             writes indexes
+//   G  sequential fallback (normally exits at once), info
 #include "bke_internal.cuh"
 
 namespace bke {
@@ -38,142 +42,172 @@ constexpr int UMAX = 2048;               // tiles with raw elements before givin
 constexpr int EXPAND = 4096;             // outputs expanded per shared-memory pass
 constexpr int BIGRUN = 2 * EXPAND;       // runs this long go to the fill kernel
 constexpr int CHAIN_THREADS = 1024;
-constexpr int CHAIN_BATCH = 8;          // unclean tiles staged in shared memory per round of the chain
+constexpr int CHAIN_BATCH = 8;           // unclean tiles staged in shared memory per round of the chain
+constexpr int SEQMAX = 256;             // fully sequential tiles (dense raw zones) before giving up
+constexpr int SLOT_SEQ = -2;            // tile_slot code: every element of the tile is applied by a true add
+constexpr int K_ID = -2;                 // identity (only zero weights so far)
+constexpr int K_POISON = -3;             // elements of different binades were mixed (never expected)
 
 typedef long long i64;
 typedef unsigned long long u64;
 
-struct Map { i64 d0, d1; };
-// parity map since the last raw element + raw count + the binade the map was built for
-// (k: -2 = identity / nothing yet, -3 = poisoned: elements of different binades were mixed)
-struct SMap { i64 d0, d1; int cnt; int k; };
+// Parity map: d = d0, t = d1 - d0 in {-1,0,1}; cnt = raw elements seen; k = binade of the map.
+struct SM { i64 d; int t; int cnt; int k; };
 
-__device__ __forceinline__ Map compose(Map f, Map g)
-{
-    Map h;
-    h.d0 = f.d0 + ((f.d0 & 1) ? g.d1 : g.d0);
-    h.d1 = f.d1 + (((f.d1 + 1) & 1) ? g.d1 : g.d0);
-    return h;
-}
 __device__ __forceinline__ int merge_k(int a, int b)
 {
-    if (a == -2) return b;
-    if (b == -2) return a;
-    return a == b ? a : -3;
+    if (a == K_ID) return b;
+    if (b == K_ID) return a;
+    return a == b ? a : K_POISON;
 }
-__device__ __forceinline__ SMap combine(SMap a, SMap b)
+
+// a applied first, then b.  A raw element (cnt > 0) restarts the map.
+__device__ __forceinline__ SM combine(SM a, SM b)
 {
     if (b.cnt > 0) { b.cnt += a.cnt; return b; }
-    Map h = compose(Map{a.d0, a.d1}, Map{b.d0, b.d1});
-    return SMap{h.d0, h.d1, a.cnt, merge_k(a.k, b.k)};
-}
-
-__device__ __forceinline__ int efield(double s) { return (int)((u64)__double_as_longlong(s) >> 52) & 0x7ff; }
-__device__ __forceinline__ i64 sint(double s)
-{
-    u64 b = (u64)__double_as_longlong(s);
-    u64 m = b & 0xFFFFFFFFFFFFFull;
-    return (i64)(((b >> 52) & 0x7ff) ? (m | (1ull << 52)) : m);
-}
-__device__ __forceinline__ i64 limit_of(int e) { return e ? (1ll << 53) : (1ll << 52); }
-__device__ __forceinline__ double rebuild(int e, i64 si)
-{
-    u64 b = ((u64)e << 52) | ((u64)si & 0xFFFFFFFFFFFFFull);
-    return __longlong_as_double((i64)b);
-}
-
-// state S (exact, in binade e) advanced by a parity map; *bad is set when the assumption fails
-__device__ __forceinline__ double apply_map(double S, Map m, int e, int *bad)
-{
-    if (efield(S) != e) { *bad = 1; return S; }
-    i64 si = sint(S);
-    i64 d = (si & 1) ? m.d1 : m.d0;
-    si += d;
-    if (si >= limit_of(e) || d < 0) { *bad = 1; return S; }
-    return rebuild(e, si);
-}
-
-// parity map of adding w to a state in binade e (only called for elements classified clean)
-__device__ __forceinline__ Map elem_map(double w, int e)
-{
-    u64 b = (u64)__double_as_longlong(w);
-    int ew = (int)(b >> 52) & 0x7ff;
-    u64 mw = (b & 0xFFFFFFFFFFFFFull) | (ew ? (1ull << 52) : 0ull);
-    int sh = (ew > 1 ? ew : 1) - (e > 1 ? e : 1);       // exponent of w's ulp minus exponent of q
-    Map m;
-    if (sh >= 0) {
-        i64 a = (sh < 10) ? (i64)(mw << sh) : (i64)(1ll << 62);   // clean elements have sh <= 1
-        m.d0 = m.d1 = a;
-    } else {
-        int r = -sh;
-        if (r >= 64) { m.d0 = m.d1 = 0; return m; }
-        u64 a = mw >> r;
-        u64 rem = mw & ((1ull << r) - 1ull);
-        u64 half = 1ull << (r - 1);
-        if (rem > half) { m.d0 = m.d1 = (i64)(a + 1); }
-        else if (rem < half) { m.d0 = m.d1 = (i64)a; }
-        else { m.d0 = (i64)(a + (a & 1)); m.d1 = (i64)(a + 1 - (a & 1)); }
+    SM r;
+    r.cnt = a.cnt;
+    r.k = merge_k(a.k, b.k);
+    if ((a.t | b.t) == 0) { r.d = a.d + b.d; r.t = 0; }
+    else {
+        const i64 a1 = a.d + a.t;
+        const i64 h0 = a.d + b.d + ((a.d & 1) ? b.t : 0);
+        const i64 h1 = a1 + b.d + (((a1 + 1) & 1) ? b.t : 0);
+        r.d = h0; r.t = (int)(h1 - h0);
     }
-    return m;
+    return r;
 }
 
-// ------------------------------------------------------------------ block primitives (256 threads)
-__device__ __forceinline__ double block_excl_scan_double(double v, double *total, double *sh /*[8]*/)
+__device__ __forceinline__ SM sm_identity() { return SM{0, 0, 0, K_ID}; }
+
+// exact state (bit pattern of a non-negative double) advanced by a parity map of binade e
+__device__ __forceinline__ i64 apply_bits(i64 sb, i64 d, int t, int e, int *bad)
 {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    double inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        double t = __shfl_up_sync(FULL, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) sh[wid] = inc;
-    __syncthreads();
-    double base = 0.0, tot = 0.0;
-#pragma unroll
-    for (int k = 0; k < BLOCK / 32; k++) {
-        double s = sh[k];
-        if (k < wid) base += s;
-        tot += s;
-    }
-    __syncthreads();
-    *total = tot;
-    return base + (inc - v);
+    if ((int)(sb >> 52) != e) { *bad = 1; return sb; }
+    const i64 r = sb + d + ((sb & 1) ? t : 0);
+    if ((int)(r >> 52) != e) { *bad = 1; return sb; }
+    return r;
 }
 
-__device__ __forceinline__ SMap shfl_up_smap(SMap v, int o)
+// parity map of adding w (> 0) to a state in binade e: two IEEE adds on the binade base
+__device__ __forceinline__ SM elem_map(double w, int e)
 {
-    SMap r;
-    r.d0 = __shfl_up_sync(FULL, v.d0, o);
-    r.d1 = __shfl_up_sync(FULL, v.d1, o);
+    const i64 base = (i64)e << 52;
+    const i64 d0 = __double_as_longlong(__dadd_rn(__longlong_as_double(base), w)) - base;
+    const i64 d1 = __double_as_longlong(__dadd_rn(__longlong_as_double(base + 1), w)) - (base + 1);
+    return SM{d0, (int)(d1 - d0), 0, e};
+}
+
+// ------------------------------------------------------------------ warp / block primitives
+__device__ __forceinline__ SM shfl_up_sm(SM v, int o)
+{
+    SM r;
+    r.d = __shfl_up_sync(FULL, v.d, o);
+    r.t = __shfl_up_sync(FULL, v.t, o);
     r.cnt = __shfl_up_sync(FULL, v.cnt, o);
     r.k = __shfl_up_sync(FULL, v.k, o);
     return r;
 }
-
-// exclusive scan of SMap over the block; *total = aggregate of the whole block
-__device__ __forceinline__ SMap block_excl_scan_smap(SMap v, SMap *total, SMap *sh /*[8]*/)
+__device__ __forceinline__ SM shfl_sm(SM v, int src)
 {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    SMap inc = v;
+    SM r;
+    r.d = __shfl_sync(FULL, v.d, src);
+    r.t = __shfl_sync(FULL, v.t, src);
+    r.cnt = __shfl_sync(FULL, v.cnt, src);
+    r.k = __shfl_sync(FULL, v.k, src);
+    return r;
+}
+__device__ __forceinline__ SM warp_incl_scan_sm(SM v, int lane)
+{
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        SMap t = shfl_up_smap(inc, o);
-        if (lane >= o) inc = combine(t, inc);
+        SM t = shfl_up_sm(v, o);
+        if (lane >= o) v = combine(t, v);
     }
+    return v;
+}
+__device__ __forceinline__ double warp_incl_scan_d(double v, int lane)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double t = __shfl_up_sync(FULL, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// exclusive block scan of doubles (BLOCK threads); *total = block aggregate.
+// sh needs BLOCK/32 + 1 entries.  The 8 warp totals are scanned by warp 0 only.
+__device__ __forceinline__ double block_excl_scan_d(double v, double *total, double *sh)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const double inc = warp_incl_scan_d(v, lane);
     if (lane == 31) sh[wid] = inc;
     __syncthreads();
-    SMap base = SMap{0, 0, 0, -2}, tot = SMap{0, 0, 0, -2};
-#pragma unroll
-    for (int k = 0; k < BLOCK / 32; k++) {
-        SMap s = sh[k];
-        if (k < wid) base = combine(base, s);
-        tot = combine(tot, s);
+    if (wid == 0) {
+        const double a = (lane < BLOCK / 32) ? sh[lane] : 0.0;
+        const double ai = warp_incl_scan_d(a, lane);
+        if (lane < BLOCK / 32) sh[lane] = ai - a;
+        if (lane == BLOCK / 32 - 1) sh[BLOCK / 32] = ai;
     }
     __syncthreads();
-    SMap prev = shfl_up_smap(inc, 1);                  // inclusive of the previous lane
-    if (lane == 0) prev = SMap{0, 0, 0, -2};
-    *total = tot;
+    const double base = sh[wid];
+    *total = sh[BLOCK / 32];
+    __syncthreads();
+    return base + (inc - v);
+}
+
+__device__ __forceinline__ i64 warp_incl_scan_i64(i64 v, int lane)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const i64 t = __shfl_up_sync(FULL, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// exclusive block scan of int64 (plain sums: the tie-free fast path); sh needs BLOCK/32 + 1 entries
+__device__ __forceinline__ i64 block_excl_scan_i64(i64 v, i64 *total, i64 *sh)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const i64 inc = warp_incl_scan_i64(v, lane);
+    if (lane == 31) sh[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        const i64 a = (lane < BLOCK / 32) ? sh[lane] : 0;
+        const i64 ai = warp_incl_scan_i64(a, lane);
+        if (lane < BLOCK / 32) sh[lane] = ai - a;
+        if (lane == BLOCK / 32 - 1) sh[BLOCK / 32] = ai;
+    }
+    __syncthreads();
+    const i64 base = sh[wid];
+    *total = sh[BLOCK / 32];
+    __syncthreads();
+    return base + (inc - v);
+}
+
+// exclusive block scan of parity maps; *total = block aggregate; sh needs BLOCK/32 + 1 entries
+__device__ __forceinline__ SM block_excl_scan_sm(SM v, SM *total, SM *sh)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const SM inc = warp_incl_scan_sm(v, lane);
+    if (lane == 31) sh[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        const SM a = (lane < BLOCK / 32) ? sh[lane] : sm_identity();
+        const SM ai = warp_incl_scan_sm(a, lane);
+        SM ex = shfl_up_sm(ai, 1);
+        if (lane == 0) ex = sm_identity();
+        if (lane < BLOCK / 32) sh[lane] = ex;
+        if (lane == BLOCK / 32 - 1) sh[BLOCK / 32] = ai;
+    }
+    __syncthreads();
+    const SM base = sh[wid];
+    *total = sh[BLOCK / 32];
+    __syncthreads();
+    SM prev = shfl_up_sm(inc, 1);
+    if (lane == 0) prev = sm_identity();
     return combine(base, prev);
 }
 
@@ -184,14 +218,16 @@ struct Header {
     int n_runs;         // long runs queued for the fill kernel
     int overflow;       // positions >= cumsum[-1]
     int chain_bad;      // a verified assumption failed
-    int pad[3];
+    int n_seq;          // tiles walked element by element (more than RMAX raw elements)
+    int pad[2];
 };
 
 struct Slot {           // one tile with raw elements
     int tile;
     int nraw;
-    int segk[RMAX + 1];         // binade of segment s, -1 = empty segment
-    i64 end0[RMAX + 1], end1[RMAX + 1];
+    int segk[RMAX + 1];         // binade of segment s, -1 = empty / identity segment
+    int segt[RMAX + 1];
+    i64 segd[RMAX + 1];
     double wraw[RMAX];
 };
 
@@ -200,17 +236,19 @@ struct Run { i64 lo, hi; int j; int pad; };
 struct Ws {
     Header *hdr;
     double *tile_sum;       // [T]
-    double *tile_prefix;    // [T+1] approximate exclusive prefix (+ carry)
-    double *S_in;           // [T+1] exact state before each tile
-    i64 *tile_map;          // [T][2]
-    int *tile_k;            // [T]  binade, or -1 for a tile with raw elements
-    int *tile_slot;         // [T]
-    i64 *run_map;           // [T][2] composite of the clean tiles since the last unclean one
-    int *run_id;            // [T]
+    double *tile_prefix;    // [T+1] approximate exclusive prefix
+    i64 *S_in;              // [T+1] exact state (bit pattern) before each tile
+    i64 *tile_d;            // [T]   tile map (clean tiles)
+    int *tile_t;            // [T]
+    int *tile_k;            // [T]   binade, K_ID for an all-zero tile
+    int *tile_slot;         // [T]   -1 clean, >= 0 slot of a tile with raw elements, SLOT_SEQ sequential
+    i64 *run_d;             // [T]   composite of the clean tiles since the last unclean tile
+    int *run_t;             // [T]
+    int *run_cnt;           // [T]
     int *run_k;             // [T]
     Slot *slots;            // [UMAX]
-    double *S_run;          // [UMAX+1]
-    int *ord2tile;          // [UMAX]
+    i64 *S_run;             // [UMAX+SEQMAX+1]
+    int *ord2tile;          // [UMAX+SEQMAX]
     Run *runs;              // [max_runs]
     int max_runs;
     int T;
@@ -227,16 +265,18 @@ size_t carve(int64_t n, unsigned char *base, Ws *w)
     p = take(sizeof(Header));                 if (w) w->hdr = (Header *)p;
     p = take(sizeof(double) * T);             if (w) w->tile_sum = (double *)p;
     p = take(sizeof(double) * (T + 1));       if (w) w->tile_prefix = (double *)p;
-    p = take(sizeof(double) * (T + 1));       if (w) w->S_in = (double *)p;
-    p = take(sizeof(i64) * 2 * T);            if (w) w->tile_map = (i64 *)p;
+    p = take(sizeof(i64) * (T + 1));          if (w) w->S_in = (i64 *)p;
+    p = take(sizeof(i64) * T);                if (w) w->tile_d = (i64 *)p;
+    p = take(sizeof(int) * T);                if (w) w->tile_t = (int *)p;
     p = take(sizeof(int) * T);                if (w) w->tile_k = (int *)p;
     p = take(sizeof(int) * T);                if (w) w->tile_slot = (int *)p;
-    p = take(sizeof(i64) * 2 * T);            if (w) w->run_map = (i64 *)p;
-    p = take(sizeof(int) * T);                if (w) w->run_id = (int *)p;
+    p = take(sizeof(i64) * T);                if (w) w->run_d = (i64 *)p;
+    p = take(sizeof(int) * T);                if (w) w->run_t = (int *)p;
+    p = take(sizeof(int) * T);                if (w) w->run_cnt = (int *)p;
     p = take(sizeof(int) * T);                if (w) w->run_k = (int *)p;
     p = take(sizeof(Slot) * UMAX);            if (w) w->slots = (Slot *)p;
-    p = take(sizeof(double) * (UMAX + 1));    if (w) w->S_run = (double *)p;
-    p = take(sizeof(int) * UMAX);             if (w) w->ord2tile = (int *)p;
+    p = take(sizeof(i64) * (UMAX + SEQMAX + 1)); if (w) w->S_run = (i64 *)p;
+    p = take(sizeof(int) * (UMAX + SEQMAX));  if (w) w->ord2tile = (int *)p;
     int64_t max_runs = n / BIGRUN + 8;
     p = take(sizeof(Run) * max_runs);         if (w) { w->runs = (Run *)p; w->max_runs = (int)max_runs; w->T = (int)T; }
     return off;
@@ -248,8 +288,9 @@ struct Params {
     double u;              // systematic offset
     const double *U;       // stratified uniforms (NULL = systematic)
     int *idx;
-    double eps;            // relative margin of the approximate prefix
+    i64 eb;                // classification margin in ulps of the running sum
     double tau;            // fast-path margin of the position search
+    int aligned16;         // weights pointer is 16-byte aligned
     int *info;             // user info[8] or NULL
     double *cumsum_last;   // or NULL
     Ws ws;
@@ -258,275 +299,423 @@ struct Params {
 // ------------------------------------------------------------------ pass A: tile sums
 __global__ void __launch_bounds__(BLOCK) k_tile_sums(Params p)
 {
-    __shared__ double sh[BLOCK / 32];
+    __shared__ double sh[BLOCK / 32 + 1];
     const int t = blockIdx.x;
-    const i64 base = (i64)t * TILE + (i64)threadIdx.x * IPT;
+    const i64 base = (i64)t * TILE;
     double s = 0.0;
     bool bad = false;
+    if (p.aligned16 && base + TILE <= p.n) {
+        const double2 *src = reinterpret_cast<const double2 *>(p.w + base);
 #pragma unroll
-    for (int k = 0; k < IPT; k++) {
-        i64 j = base + k;
-        double w = (j < p.n) ? p.w[j] : 0.0;
-        if (!(w >= 0.0) || isinf(w)) bad = true;
-        s += w;
+        for (int i = 0; i < IPT / 2; i++) {
+            const double2 v = src[i * BLOCK + threadIdx.x];
+            if (!(v.x >= 0.0) || !(v.y >= 0.0) || isinf(v.x) || isinf(v.y)) bad = true;
+            s += v.x + v.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < IPT; i++) {
+            const i64 j = base + i * BLOCK + threadIdx.x;
+            const double w = (j < p.n) ? p.w[j] : 0.0;
+            if (!(w >= 0.0) || isinf(w)) bad = true;
+            s += w;
+        }
     }
     double tot;
-    block_excl_scan_double(s, &tot, sh);
+    block_excl_scan_d(s, &tot, sh);
     if (threadIdx.x == 0) p.ws.tile_sum[t] = tot;
     if (bad) p.ws.hdr->fallback = 1;
 }
 
 // ------------------------------------------------------------------ pass B: scan of tile sums
+// Warp w owns the contiguous range [w*per, (w+1)*per); it walks it 32 tiles at a time (coalesced)
+// with a warp scan and a running carry; the 32 warp totals are scanned by warp 0.
 __global__ void __launch_bounds__(CHAIN_THREADS) k_scan_tiles(Params p)
 {
-    __shared__ double sh[CHAIN_THREADS];
+    __shared__ double wtot[CHAIN_THREADS / 32];
     const int T = p.ws.T;
-    const int per = (T + CHAIN_THREADS - 1) / CHAIN_THREADS;
-    const int a = threadIdx.x * per;
-    const int b = min(T, a + per);
-    double s = 0.0;
-    for (int t = a; t < b; t++) s += p.ws.tile_sum[t];
-    sh[threadIdx.x] = s;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int per = ((T + CHAIN_THREADS - 1) / CHAIN_THREADS) * 32;      // tiles per warp, multiple of 32
+    const int a = min(T, wid * per), b = min(T, a + per);
+    double carry = 0.0;
+    constexpr int PF = 8;                                    // rows fetched ahead (hides the load latency)
+    for (int t0 = a; t0 < b; t0 += 32 * PF) {
+        double v[PF];
+#pragma unroll
+        for (int r = 0; r < PF; r++) { const int t = t0 + r * 32 + lane; v[r] = (t < b) ? p.ws.tile_sum[t] : 0.0; }
+#pragma unroll
+        for (int r = 0; r < PF; r++) {
+            const int t = t0 + r * 32 + lane;
+            const double inc = warp_incl_scan_d(v[r], lane);
+            if (t < b) p.ws.tile_prefix[t] = carry + (inc - v[r]);       // warp-local exclusive prefix
+            carry += __shfl_sync(FULL, inc, 31);
+        }
+    }
+    if (lane == 0) wtot[wid] = carry;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double run = 0.0;
-        for (int k = 0; k < CHAIN_THREADS; k++) { double v = sh[k]; sh[k] = run; run += v; }
-        p.ws.tile_prefix[T] = run;
+    if (wid == 0) {
+        const double v = wtot[lane];
+        const double inc = warp_incl_scan_d(v, lane);
+        wtot[lane] = inc - v;
+        if (lane == 31) p.ws.tile_prefix[T] = inc;
     }
     __syncthreads();
-    double run = sh[threadIdx.x];
-    for (int t = a; t < b; t++) { p.ws.tile_prefix[t] = run; run += p.ws.tile_sum[t]; }
+    const double off = wtot[wid];
+    for (int t = a + lane; t < b; t += 32) p.ws.tile_prefix[t] += off;
 }
 
 // ------------------------------------------------------------------ shared tile analysis (C and E)
 struct TileAn {
     double w[IPT];
-    SMap inc[IPT];         // inclusive segmented parity map at each element
-    int ek[IPT];           // binade assumed for the element (clean), -2 (zero weight) or -1 (raw)
-    int nraw;              // raw elements in the tile
-    SMap total;            // tile aggregate
+    SM inc[IPT];           // inclusive segmented parity map at each element
+    int ek[IPT];           // binade of the element (clean), K_ID (zero weight) or -1 (raw)
 };
 
-struct TileShared {
-    double shd[BLOCK / 32];
-    SMap shm[BLOCK / 32];
-    int first_raw[BLOCK + 1];    // raw flag of each thread's first element (+ sentinel)
-};
-
-__device__ __forceinline__ void analyse_tile(const Params &p, int t, TileAn &an, TileShared &sm)
+// Load the tile so that thread t owns elements [8t, 8t+8): coalesced 16-byte global loads, then a
+// transposition through shared memory whose 16-byte chunks are XOR-swizzled so that both the
+// row-major writes and the 64-byte-strided reads are bank-conflict-free.
+__device__ __forceinline__ void load_blocked(const Params &p, int t, double (&v)[IPT], double2 *buf /*[TILE/2]*/)
 {
-    const i64 base = (i64)t * TILE + (i64)threadIdx.x * IPT;
-    double s = 0.0;
+    const i64 base = (i64)t * TILE;
+    const int tid = threadIdx.x;
 #pragma unroll
-    for (int k = 0; k < IPT; k++) {
-        i64 j = base + k;
-        an.w[k] = (j < p.n) ? p.w[j] : 0.0;
-        s += an.w[k];
+    for (int i = 0; i < IPT / 2; i++) {
+        const int g = i * BLOCK + tid;                    // 16-byte chunk index in the tile
+        const i64 j = base + 2 * (i64)g;
+        double2 val;
+        if (p.aligned16 && j + 1 < p.n) val = *reinterpret_cast<const double2 *>(p.w + j);
+        else { val.x = (j < p.n) ? p.w[j] : 0.0; val.y = (j + 1 < p.n) ? p.w[j + 1] : 0.0; }
+        const int r = g >> 2, c = g & 3;
+        buf[r * 4 + (c ^ ((r >> 1) & 3))] = val;
     }
-    double tot;
-    double before = p.ws.tile_prefix[t] + block_excl_scan_double(s, &tot, sm.shd);
-    // classify + element maps, thread-local inclusive segmented scan
-    SMap run = SMap{0, 0, 0, -2};
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < IPT / 2; c++) {
+        const double2 val = buf[tid * 4 + (c ^ ((tid >> 1) & 3))];
+        v[2 * c] = val.x; v[2 * c + 1] = val.y;
+    }
+    __syncthreads();
+}
+
+// Is the add "state `before` -> `after`" safely inside ONE binade?  The exact running sum lies
+// within eb ulps of the approximate one, so both ends must be that far inside binade e.
+// Fast test on the high words (eb < 2^33 for n < 2^31), exact 64-bit test only near the edges.
+__device__ __forceinline__ bool clean_add(double before, double after, i64 eb, int *e_out)
+{
+    const int hb = __double2hiint(before), ha = __double2hiint(after);
+    const int e = hb >> 20;
+    *e_out = e;
+    if ((ha >> 20) != e) return false;
+    const int mb = hb & 0xFFFFF, ma = ha & 0xFFFFF;
+    if (mb >= 2 && ma <= 0xFFFFD) return true;
+    const i64 MANT = (1ll << 52) - 1;
+    const i64 bb = __double_as_longlong(before), ab = __double_as_longlong(after);
+    return ((bb & MANT) >= eb) && ((MANT + 1 - (ab & MANT)) > eb);
+}
+
+// classify the thread's elements and build their maps; returns the thread-local aggregate
+__device__ __forceinline__ SM classify(const Params &p, TileAn &an, double before)
+{
+    SM run = sm_identity();
 #pragma unroll
     for (int k = 0; k < IPT; k++) {
-        double after = before + an.w[k];
-        double lo = before * (1.0 - p.eps);
-        double hi = after * (1.0 + p.eps);
-        int e = efield(lo);
-        bool clean = (efield(hi) == e) && (hi < 1.0e308);
-        SMap el;
-        if (an.w[k] == 0.0) {            // fl(S + 0) = S in every binade: a binade-neutral identity
-            el = SMap{0, 0, 0, -2};
-            an.ek[k] = -2;
-        } else if (clean) {
-            Map m = elem_map(an.w[k], e);
-            el = SMap{m.d0, m.d1, 0, e};
-            an.ek[k] = e;
+        const double after = before + an.w[k];
+        SM el;
+        if (an.w[k] == 0.0) {             // fl(S + 0) = S in every binade
+            el = sm_identity();
+            an.ek[k] = K_ID;
         } else {
-            el = SMap{0, 0, 1, -2};
-            an.ek[k] = -1;
+            int e;
+            if (clean_add(before, after, p.eb, &e)) { el = elem_map(an.w[k], e); an.ek[k] = e; }
+            else { el = SM{0, 0, 1, K_ID}; an.ek[k] = -1; }
         }
         run = combine(run, el);
         an.inc[k] = run;
         before = after;
     }
-    SMap total;
-    SMap excl = block_excl_scan_smap(run, &total, sm.shm);
-#pragma unroll
-    for (int k = 0; k < IPT; k++) an.inc[k] = combine(excl, an.inc[k]);
-    an.nraw = total.cnt;
-    an.total = total;
+    return run;
 }
 
-// ------------------------------------------------------------------ pass C: per-tile maps
-__global__ void __launch_bounds__(BLOCK) k_tile_maps(Params p)
+// Fast path test + data: every non-zero element of the thread is a clean, tie-free add in binade
+// e0 (the binade of the tile's start state).  pre[k] = inclusive sum of the d0's.
+__device__ __forceinline__ bool classify_fast(const Params &p, const double (&w)[IPT], double before, int e0,
+                                              i64 (&pre)[IPT], bool *nonzero)
 {
-    __shared__ TileShared sm;
-    __shared__ int s_slot;
-    const int t = blockIdx.x;
-    if (p.ws.hdr->fallback) return;
-    TileAn an;
-    analyse_tile(p, t, an, sm);
-    if (an.nraw == 0) {
-        if (threadIdx.x == BLOCK - 1) {
-            if (an.total.k == -3) p.ws.hdr->fallback = 1;    // mixed binades inside one map (never expected)
-            p.ws.tile_k[t] = an.total.k;                     // binade, or -2 for an all-zero tile
-            p.ws.tile_map[2 * t] = an.total.d0;
-            p.ws.tile_map[2 * t + 1] = an.total.d1;
-            p.ws.tile_slot[t] = -1;
+    bool ok = true, nz = false;
+    i64 acc = 0;
+    const i64 base = (i64)e0 << 52;
+    const double B0 = __longlong_as_double(base), B1 = __longlong_as_double(base + 1);
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+        const double after = before + w[k];
+        if (w[k] != 0.0) {
+            nz = true;
+            int e;
+            const bool cl = clean_add(before, after, p.eb, &e);
+            const i64 d0 = __double_as_longlong(__dadd_rn(B0, w[k])) - base;
+            const i64 d1 = __double_as_longlong(__dadd_rn(B1, w[k])) - (base + 1);
+            ok = ok && cl && (e == e0) && (d0 == d1);
+            acc += d0;
         }
-        return;
+        pre[k] = acc;
+        before = after;
     }
-    if (threadIdx.x == 0) {
-        int s = -1;
-        if (an.nraw <= RMAX) {
-            s = atomicAdd(&p.ws.hdr->n_unclean, 1);
-            if (s >= UMAX) s = -1;
-        }
-        if (s < 0) p.ws.hdr->fallback = 1;
-        s_slot = s;
-        p.ws.tile_k[t] = -1;
-        p.ws.tile_slot[t] = s < 0 ? 0 : s;
-    }
-    // raw flag of the element that follows each thread's last element
-    sm.first_raw[threadIdx.x] = (an.ek[0] == -1);
-    if (threadIdx.x == 0) sm.first_raw[BLOCK] = 1;       // the tile end closes the last segment
-    __syncthreads();
-    const int s = s_slot;
-    if (s < 0) return;
-    Slot *sl = &p.ws.slots[s];
-    for (int q = threadIdx.x; q <= RMAX; q += BLOCK) { sl->segk[q] = -1; sl->end0[q] = 0; sl->end1[q] = 0; }
-    if (threadIdx.x == 0) { sl->tile = t; sl->nraw = an.nraw; }
-    __syncthreads();
+    *nonzero = nz;
+    return ok;
+}
+
+struct TileShared {
+    double shd[BLOCK / 32 + 1];
+    SM shm[BLOCK / 32 + 1];
+    i64 shi[BLOCK / 32 + 1];
+    int first_raw[BLOCK + 1];    // raw flag of each thread's first element (+ sentinel)
+};
+
+// record segment-end maps and raw weights (tiles with raw elements)
+__device__ __forceinline__ void export_segments(const TileAn &an, const TileShared &sm, int *segk, int *segt, i64 *segd,
+                                                double *wraw, int *poison)
+{
 #pragma unroll
     for (int k = 0; k < IPT; k++) {
         const int seg = an.inc[k].cnt;
         if (an.ek[k] == -1) {
-            sl->wraw[seg - 1] = an.w[k];                 // the raw element that opens segment `seg`
+            wraw[seg - 1] = an.w[k];                  // the raw element that opens segment `seg`
         } else {
-            bool next_raw = (k + 1 < IPT) ? (an.ek[k + 1] == -1) : (sm.first_raw[threadIdx.x + 1] != 0);
+            const bool next_raw = (k + 1 < IPT) ? (an.ek[k + 1] == -1) : (sm.first_raw[threadIdx.x + 1] != 0);
             if (next_raw) {
-                if (an.inc[k].k == -3) p.ws.hdr->fallback = 1;
-                // k == -2: only zero weights in the segment -> identity, recorded as empty
-                sl->segk[seg] = an.inc[k].k == -2 ? -1 : an.inc[k].k;
-                sl->end0[seg] = an.inc[k].d0; sl->end1[seg] = an.inc[k].d1;
+                if (an.inc[k].k == K_POISON) *poison = 1;
+                segk[seg] = an.inc[k].k == K_ID ? -1 : an.inc[k].k;      // identity segments are skipped
+                segt[seg] = an.inc[k].t;
+                segd[seg] = an.inc[k].d;
             }
         }
     }
 }
 
 // sequential walk through one tile with raw elements; returns the exact state after the tile.
-// segstate (optional, shared memory) receives the state at the start of every segment.
-__device__ double walk_slot(const int *segk, const i64 *end0, const i64 *end1, const double *wraw, int nraw,
-                            double S, int *bad, double *segstate)
+// segstate (optional) receives the state at the start of every segment.
+__device__ i64 walk_slot(const int *segk, const int *segt, const i64 *segd, const double *wraw, int nraw, i64 S,
+                         int *bad, i64 *segstate)
 {
     for (int s = 0; s <= nraw; s++) {
         if (segstate) segstate[s] = S;
-        if (segk[s] >= 0) S = apply_map(S, Map{end0[s], end1[s]}, segk[s], bad);
-        if (s < nraw) S = __dadd_rn(S, wraw[s]);
+        if (segk[s] >= 0) S = apply_bits(S, segd[s], segt[s], segk[s], bad);
+        if (s < nraw) S = __double_as_longlong(__dadd_rn(__longlong_as_double(S), wraw[s]));
     }
     return S;
 }
 
-// ------------------------------------------------------------------ pass D: exact chain over tiles
-struct RunEl { i64 d0, d1; int cnt; int k; };       // k: binade of the composite, -2 = identity
-__device__ __forceinline__ RunEl run_combine(RunEl a, RunEl b, int *bad)
+// ------------------------------------------------------------------ pass C: per-tile maps
+struct MapsShared {
+    TileShared ts;
+    double2 buf[TILE / 2];
+    int slot;
+};
+
+__global__ void __launch_bounds__(BLOCK) k_tile_maps(Params p)
 {
-    if (b.cnt > 0) { b.cnt += a.cnt; return b; }
-    if (a.k == -2) { b.cnt = a.cnt; return b; }
-    if (b.k == -2) return a;
-    if (a.k != b.k) *bad = 1;                        // clean tiles of one run share the binade
-    Map h = compose(Map{a.d0, a.d1}, Map{b.d0, b.d1});
-    return RunEl{h.d0, h.d1, a.cnt, a.k};
+    __shared__ MapsShared sm;
+    const int t = blockIdx.x;
+    if (p.ws.hdr->fallback) return;
+    TileAn an;
+    load_blocked(p, t, an.w, sm.buf);
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < IPT; k++) s += an.w[k];
+    double tot;
+    const double tp = p.ws.tile_prefix[t];
+    const double before = tp + block_excl_scan_d(s, &tot, sm.ts.shd);
+    {   // fast path: a tile of clean, tie-free adds in one binade -> a plain int64 sum
+        const int e0 = __double2hiint(tp) >> 20;
+        i64 pre[IPT];
+        bool nz;
+        const bool ok = classify_fast(p, an.w, before, e0, pre, &nz);
+        if (__syncthreads_and(ok)) {
+            i64 total;
+            block_excl_scan_i64(pre[IPT - 1], &total, sm.ts.shi);
+            const int any_nz = __syncthreads_or(nz);
+            if (threadIdx.x == 0) {
+                p.ws.tile_k[t] = any_nz ? e0 : K_ID; p.ws.tile_d[t] = total; p.ws.tile_t[t] = 0;
+                p.ws.tile_slot[t] = -1;
+            }
+            return;
+        }
+    }
+    const SM run = classify(p, an, before);
+    const int any_raw = __syncthreads_or(run.cnt > 0);
+    if (!any_raw) {
+        SM total;
+        block_excl_scan_sm(run, &total, sm.ts.shm);
+        if (threadIdx.x == 0) {
+            if (total.k == K_POISON) p.ws.hdr->fallback = 1;
+            p.ws.tile_k[t] = total.k; p.ws.tile_d[t] = total.d; p.ws.tile_t[t] = total.t;
+            p.ws.tile_slot[t] = -1;
+        }
+        return;
+    }
+    SM total;
+    const SM excl = block_excl_scan_sm(run, &total, sm.ts.shm);
+#pragma unroll
+    for (int k = 0; k < IPT; k++) an.inc[k] = combine(excl, an.inc[k]);
+    if (threadIdx.x == 0) {
+        int s2 = -1;
+        if (total.cnt <= RMAX) {
+            s2 = atomicAdd(&p.ws.hdr->n_unclean, 1);
+            if (s2 >= UMAX) { s2 = -1; p.ws.hdr->fallback = 1; }
+            p.ws.tile_slot[t] = s2 < 0 ? 0 : s2;
+        } else {
+            // a dense zone of raw elements (tiny weights next to a binade boundary, e.g. the tail of
+            // a degenerate weight vector approaching 1.0): the whole tile is walked with true adds
+            if (atomicAdd(&p.ws.hdr->n_seq, 1) >= SEQMAX) p.ws.hdr->fallback = 1;
+            p.ws.tile_slot[t] = SLOT_SEQ;
+        }
+        sm.slot = s2;
+        p.ws.tile_k[t] = -1;
+    }
+    sm.ts.first_raw[threadIdx.x] = (an.ek[0] == -1);
+    if (threadIdx.x == 0) sm.ts.first_raw[BLOCK] = 1;       // the tile end closes the last segment
+    __syncthreads();
+    const int s2 = sm.slot;
+    if (s2 < 0) return;
+    Slot *sl = &p.ws.slots[s2];
+    for (int q = threadIdx.x; q <= RMAX; q += BLOCK) { sl->segk[q] = -1; sl->segt[q] = 0; sl->segd[q] = 0; }
+    if (threadIdx.x == 0) { sl->tile = t; sl->nraw = total.cnt; }
+    __syncthreads();
+    int poison = 0;
+    export_segments(an, sm.ts, sl->segk, sl->segt, sl->segd, sl->wraw, &poison);
+    if (poison) p.ws.hdr->fallback = 1;
+}
+
+// ------------------------------------------------------------------ pass D: exact chain over tiles
+__device__ __forceinline__ SM tile_el(const Ws &ws, int t)
+{
+    if (ws.tile_slot[t] != -1) return SM{0, 0, 1, K_ID};     // unclean tile: restart marker
+    return SM{ws.tile_d[t], ws.tile_t[t], 0, ws.tile_k[t]};
 }
 
 __global__ void __launch_bounds__(CHAIN_THREADS) k_chain(Params p, double carry)
 {
-    __shared__ RunEl sh[CHAIN_THREADS];
+    __shared__ SM wtot[CHAIN_THREADS / 32];
+    __shared__ Slot s_slots[CHAIN_BATCH];
+    __shared__ double s_w[TILE];
+    __shared__ SM s_rm[CHAIN_BATCH];
+    __shared__ i64 s_S;
     __shared__ int s_bad;
     const Ws &ws = p.ws;
     if (ws.hdr->fallback) return;
     const int T = ws.T;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_bad = 0;
-    __syncthreads();
     int bad = 0;
-    const int per = (T + CHAIN_THREADS - 1) / CHAIN_THREADS;
-    const int a = threadIdx.x * per, b = min(T, a + per);
-    // element of tile t: clean -> its map (cnt 0); unclean -> reset marker (cnt 1, identity)
-    auto tile_el = [&](int t) {
-        if (ws.tile_slot[t] >= 0) return RunEl{0, 0, 1, -2};
-        return RunEl{ws.tile_map[2 * t], ws.tile_map[2 * t + 1], 0, ws.tile_k[t]};
-    };
-    RunEl agg = RunEl{0, 0, 0, -2};
-    for (int t = a; t < b; t++) agg = run_combine(agg, tile_el(t), &bad);
-    sh[threadIdx.x] = agg;
+    // ---- segmented exclusive scan of the tile maps (restart after every unclean tile) ----------
+    const int per = ((T + CHAIN_THREADS - 1) / CHAIN_THREADS) * 32;
+    const int a = min(T, wid * per), b = min(T, a + per);
+    SM carry_m = sm_identity();
+    constexpr int PF = 4;                                    // rows fetched ahead (hides the load latency)
+    for (int t0 = a; t0 < b; t0 += 32 * PF) {
+        SM v[PF];
+#pragma unroll
+        for (int r = 0; r < PF; r++) { const int t = t0 + r * 32 + lane; v[r] = (t < b) ? tile_el(ws, t) : sm_identity(); }
+#pragma unroll
+        for (int r = 0; r < PF; r++) {
+            const int t = t0 + r * 32 + lane;
+            const SM inc = warp_incl_scan_sm(v[r], lane);
+            SM prev = shfl_up_sm(inc, 1);
+            if (lane == 0) prev = sm_identity();
+            const SM ex = combine(carry_m, prev);             // warp-local exclusive value at tile t
+            if (t < b) { ws.run_d[t] = ex.d; ws.run_t[t] = ex.t; ws.run_cnt[t] = ex.cnt; ws.run_k[t] = ex.k; }
+            carry_m = combine(carry_m, shfl_sm(inc, 31));
+        }
+    }
+    if (lane == 0) wtot[wid] = carry_m;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        RunEl run = RunEl{0, 0, 0, -2};
-        for (int k = 0; k < CHAIN_THREADS; k++) { RunEl v = sh[k]; sh[k] = run; run = run_combine(run, v, &bad); }
+    if (wid == 0) {
+        const SM v = wtot[lane];
+        const SM inc = warp_incl_scan_sm(v, lane);
+        SM prev = shfl_up_sm(inc, 1);
+        if (lane == 0) prev = sm_identity();
+        wtot[lane] = prev;                                    // exclusive prefix of the warp ranges
     }
     __syncthreads();
-    RunEl run = sh[threadIdx.x];
-    for (int t = a; t < b; t++) {
-        // exclusive value at tile t: composite of the clean tiles since the last unclean tile
-        ws.run_map[2 * t] = run.d0; ws.run_map[2 * t + 1] = run.d1;
-        ws.run_id[t] = run.cnt; ws.run_k[t] = run.k;
-        if (ws.tile_slot[t] >= 0) ws.ord2tile[run.cnt] = t;
-        run = run_combine(run, tile_el(t), &bad);
+    const SM woff = wtot[wid];
+    for (int t = a + lane; t < b; t += 32) {
+        const SM loc = SM{ws.run_d[t], ws.run_t[t], ws.run_cnt[t], ws.run_k[t]};
+        const SM ex = combine(woff, loc);
+        if (ex.k == K_POISON) bad = 1;
+        ws.run_d[t] = ex.d; ws.run_t[t] = ex.t; ws.run_cnt[t] = ex.cnt; ws.run_k[t] = ex.k;
+        if (ws.tile_slot[t] != -1 && ex.cnt < UMAX + SEQMAX) ws.ord2tile[ex.cnt] = t;
     }
     __threadfence_block();
     __syncthreads();
-    // sequential part: one thread walks the tiles that contain raw elements.  Their slot data is
-    // staged into shared memory by the whole block first (a dependent chain of global loads would
-    // cost ~1 us per hop), CHAIN_BATCH tiles at a time.
+    // ---- sequential part: one thread walks the tiles that contain raw elements.  Their slot data
+    // is staged into shared memory by the whole block first (a dependent chain of global loads
+    // would cost ~1 us per hop), CHAIN_BATCH tiles at a time.
     {
-        __shared__ Slot s_slots[CHAIN_BATCH];
-        __shared__ i64 s_rm[CHAIN_BATCH][2];
-        __shared__ int s_rk[CHAIN_BATCH];
-        __shared__ double s_S;
-        const int U = ws.hdr->n_unclean;
-        if (threadIdx.x == 0) { s_S = carry; ws.S_run[0] = carry; }
-        for (int i0 = 0; i0 < U; i0 += CHAIN_BATCH) {
-            const int nb = min(CHAIN_BATCH, U - i0);
+        const int U = min(ws.hdr->n_unclean, UMAX) + min(ws.hdr->n_seq, SEQMAX);
+        if (threadIdx.x == 0) { s_S = __double_as_longlong(carry); ws.S_run[0] = s_S; }
+        constexpr int SLOT_INTS = (int)(sizeof(Slot) / sizeof(int));
+        int i0 = 0;
+        while (i0 < U) {
+            const int t_first = ws.ord2tile[i0];
             __syncthreads();
-            for (int q = threadIdx.x; q < nb * (int)(sizeof(Slot) / sizeof(int)); q += CHAIN_THREADS) {
-                const int b = q / (int)(sizeof(Slot) / sizeof(int)), o = q % (int)(sizeof(Slot) / sizeof(int));
-                const int t = ws.ord2tile[i0 + b];
-                reinterpret_cast<int *>(&s_slots[b])[o] = reinterpret_cast<const int *>(&ws.slots[ws.tile_slot[t]])[o];
+            if (ws.tile_slot[t_first] == SLOT_SEQ) {
+                // sequential tile: stage its weights, one thread adds them one by one
+                const i64 base = (i64)t_first * TILE;
+                for (int q = threadIdx.x; q < TILE; q += CHAIN_THREADS) s_w[q] = (base + q < p.n) ? p.w[base + q] : 0.0;
+                if (threadIdx.x == 0) s_rm[0] = SM{ws.run_d[t_first], ws.run_t[t_first], 0, ws.run_k[t_first]};
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    i64 S = s_S;
+                    if (s_rm[0].k >= 0) S = apply_bits(S, s_rm[0].d, s_rm[0].t, s_rm[0].k, &bad);
+                    double acc = __longlong_as_double(S);
+                    for (int q = 0; q < TILE; q++) acc = __dadd_rn(acc, s_w[q]);
+                    S = __double_as_longlong(acc);
+                    ws.S_run[i0 + 1] = S;
+                    s_S = S;
+                }
+                i0 += 1;
+                continue;
+            }
+            int nb = 1;                                       // consecutive slot-type tiles
+            while (nb < CHAIN_BATCH && i0 + nb < U && ws.tile_slot[ws.ord2tile[i0 + nb]] != SLOT_SEQ) nb++;
+            for (int q = threadIdx.x; q < nb * SLOT_INTS; q += CHAIN_THREADS) {
+                const int bb = q / SLOT_INTS, o = q % SLOT_INTS;
+                const int t = ws.ord2tile[i0 + bb];
+                reinterpret_cast<int *>(&s_slots[bb])[o] = reinterpret_cast<const int *>(&ws.slots[ws.tile_slot[t]])[o];
             }
             if (threadIdx.x < nb) {
                 const int t = ws.ord2tile[i0 + threadIdx.x];
-                s_rm[threadIdx.x][0] = ws.run_map[2 * t]; s_rm[threadIdx.x][1] = ws.run_map[2 * t + 1];
-                s_rk[threadIdx.x] = ws.run_k[t];
+                s_rm[threadIdx.x] = SM{ws.run_d[t], ws.run_t[t], 0, ws.run_k[t]};
             }
             __syncthreads();
             if (threadIdx.x == 0) {
-                double S = s_S;
-                for (int b = 0; b < nb; b++) {
-                    if (s_rk[b] != -2) S = apply_map(S, Map{s_rm[b][0], s_rm[b][1]}, s_rk[b], &bad);
-                    const Slot *sl = &s_slots[b];
-                    S = walk_slot(sl->segk, sl->end0, sl->end1, sl->wraw, sl->nraw, S, &bad, nullptr);
-                    ws.S_run[i0 + b + 1] = S;
+                i64 S = s_S;
+                for (int bb = 0; bb < nb; bb++) {
+                    if (s_rm[bb].k >= 0) S = apply_bits(S, s_rm[bb].d, s_rm[bb].t, s_rm[bb].k, &bad);
+                    const Slot *sl = &s_slots[bb];
+                    S = walk_slot(sl->segk, sl->segt, sl->segd, sl->wraw, sl->nraw, S, &bad, nullptr);
+                    ws.S_run[i0 + bb + 1] = S;
                 }
                 s_S = S;
             }
+            i0 += nb;
         }
     }
     __threadfence_block();
     __syncthreads();
-    // parallel part: exact state before every tile, with verification of the clean tiles
-    double S_last = 0.0;
-    for (int t = a; t < b; t++) {
-        double S = ws.S_run[ws.run_id[t]];
-        if (ws.run_k[t] != -2) S = apply_map(S, Map{ws.run_map[2 * t], ws.run_map[2 * t + 1]}, ws.run_k[t], &bad);
+    // ---- parallel part: exact state before every tile, with verification of the clean tiles ---
+    for (int t = a + lane; t < b; t += 32) {
+        i64 S = ws.S_run[ws.run_cnt[t]];
+        const int rk = ws.run_k[t];
+        if (rk >= 0) S = apply_bits(S, ws.run_d[t], ws.run_t[t], rk, &bad);
         ws.S_in[t] = S;
         if (ws.tile_slot[t] < 0) {
-            double E = ws.tile_k[t] >= 0 ? apply_map(S, Map{ws.tile_map[2 * t], ws.tile_map[2 * t + 1]}, ws.tile_k[t], &bad) : S;
-            if (t == T - 1) S_last = E;
+            const int tk = ws.tile_k[t];
+            const i64 E = tk >= 0 ? apply_bits(S, ws.tile_d[t], ws.tile_t[t], tk, &bad) : S;
+            if (t == T - 1) ws.S_in[T] = E;
         } else if (t == T - 1) {
-            S_last = ws.S_run[ws.run_id[t] + 1];
+            ws.S_in[T] = ws.S_run[ws.run_cnt[t] + 1];
         }
-        if (t == T - 1) ws.S_in[T] = S_last;
     }
     if (bad) s_bad = 1;
     __syncthreads();
@@ -539,16 +728,16 @@ __device__ __forceinline__ double pos_sys(i64 i, double u, double Nd) { return _
 // number of positions strictly below c (systematic)
 __device__ __forceinline__ i64 count_below_sys(double c, double u, i64 N, double Nd, double tau)
 {
-    double v = __dadd_rn(__dmul_rn(c, Nd), -u);
-    double fl = floor(v);
-    double fr = v - fl;
-    if (fr > tau && fr < 1.0 - tau && fabs(v) < 4.0e15) {
-        double g = fl + 1.0;
-        if (g < 0.0) g = 0.0;
-        if (g > Nd) g = Nd;
-        return (i64)g;
+    const double v = __dadd_rn(__dmul_rn(c, Nd), -u);
+    if (fabs(v) < 4.0e15) {
+        const i64 fl = __double2ll_rd(v);
+        const double fr = v - (double)fl;
+        if (fr > tau && fr < 1.0 - tau) {
+            const i64 g = fl + 1;
+            return g < 0 ? 0 : (g > N ? N : g);
+        }
     }
-    double g0d = fl + 1.0;
+    double g0d = floor(v) + 1.0;
     if (!(g0d > 0.0)) g0d = 0.0;
     if (g0d > Nd) g0d = Nd;
     i64 g = (i64)g0d;
@@ -576,16 +765,17 @@ __device__ __forceinline__ i64 count_below_str(double c, const double *U, i64 N,
 struct EmitShared {
     TileShared ts;
     int hi[TILE];                 // output end (exclusive) of every element, relative to tile_lo
-    int ebuf[EXPAND];
-    double segstate[RMAX + 1];
+    union { int ebuf[EXPAND]; double2 buf[TILE / 2]; };
+    i64 segstate[RMAX + 1];
     int segk[RMAX + 1];
-    i64 end0[RMAX + 1], end1[RMAX + 1];
+    int segt[RMAX + 1];
+    i64 segd[RMAX + 1];
     double wraw[RMAX];
     int warp_max[BLOCK / 32];
     i64 tile_lo;
-    int bad;
 };
 
+template <bool STRAT>
 __global__ void __launch_bounds__(BLOCK) k_emit(Params p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -596,95 +786,132 @@ __global__ void __launch_bounds__(BLOCK) k_emit(Params p)
     const int tid = threadIdx.x;
     const double Nd = (double)p.n;
     TileAn an;
-    analyse_tile(p, t, an, sm.ts);
-    const double S_in = ws.S_in[t];
-    // segment start states (exact)
-    if (an.nraw > 0) {
-        sm.ts.first_raw[tid] = (an.ek[0] == -1);
-        if (tid == 0) sm.ts.first_raw[BLOCK] = 1;
-        for (int q = tid; q <= RMAX; q += BLOCK) { sm.segk[q] = -1; sm.end0[q] = 0; sm.end1[q] = 0; }
-        __syncthreads();
+    load_blocked(p, t, an.w, sm.buf);
+    double s = 0.0;
 #pragma unroll
-        for (int k = 0; k < IPT; k++) {
-            const int seg = an.inc[k].cnt;
-            if (an.ek[k] == -1) sm.wraw[seg - 1] = an.w[k];
-            else {
-                bool next_raw = (k + 1 < IPT) ? (an.ek[k + 1] == -1) : (sm.ts.first_raw[tid + 1] != 0);
-                if (next_raw) {
-                    sm.segk[seg] = an.inc[k].k == -2 ? -1 : an.inc[k].k;
-                    sm.end0[seg] = an.inc[k].d0; sm.end1[seg] = an.inc[k].d1;
-                }
+    for (int k = 0; k < IPT; k++) s += an.w[k];
+    double tot;
+    const double tp = p.ws.tile_prefix[t];
+    const double before = tp + block_excl_scan_d(s, &tot, sm.ts.shd);
+    const i64 S_in = ws.S_in[t];
+    int bad = 0;
+    i64 cbits[IPT];                     // exact c_j (bit patterns) of the thread's elements
+    const bool seq_tile = ws.tile_slot[t] == SLOT_SEQ;
+    bool fast = false;
+    if (!seq_tile) {    // the same decision pass C took (same inputs, same code)
+        const int e0 = __double2hiint(tp) >> 20;
+        bool nz;
+        const bool ok = classify_fast(p, an.w, before, e0, cbits, &nz);
+        fast = __syncthreads_and(ok);
+        if (fast) {
+            i64 total_d;
+            const i64 ex = block_excl_scan_i64(cbits[IPT - 1], &total_d, sm.ts.shi);
+#pragma unroll
+            for (int k = 0; k < IPT; k++) cbits[k] += S_in + ex;
+        }
+    }
+    SM total = sm_identity();
+    if (!fast && !seq_tile) {
+        const SM run = classify(p, an, before);
+        const SM excl = block_excl_scan_sm(run, &total, sm.ts.shm);
+#pragma unroll
+        for (int k = 0; k < IPT; k++) an.inc[k] = combine(excl, an.inc[k]);
+    }
+    i64 seq_start = 0;
+    if (fast) {
+    } else if (seq_tile) {
+        // every element by a true add: thread 0 walks the tile once to get each thread's start state
+        double *wd = reinterpret_cast<double *>(sm.ebuf);
+        i64 *tstart = reinterpret_cast<i64 *>(sm.hi);
+#pragma unroll
+        for (int k = 0; k < IPT; k++) wd[tid * IPT + k] = an.w[k];
+        __syncthreads();
+        if (tid == 0) {
+            double acc = __longlong_as_double(S_in);
+            for (int th = 0; th < BLOCK; th++) {
+                tstart[th] = __double_as_longlong(acc);
+                for (int k = 0; k < IPT; k++) acc = __dadd_rn(acc, wd[th * IPT + k]);
             }
         }
         __syncthreads();
-        if (tid == 0) {
-            int bad = 0;
-            walk_slot(sm.segk, sm.end0, sm.end1, sm.wraw, an.nraw, S_in, &bad, sm.segstate);
-            sm.bad = bad;
-        }
+        seq_start = tstart[tid];
+        __syncthreads();
+    } else if (total.cnt > 0) {
+        sm.ts.first_raw[tid] = (an.ek[0] == -1);
+        if (tid == 0) sm.ts.first_raw[BLOCK] = 1;
+        for (int q = tid; q <= RMAX; q += BLOCK) { sm.segk[q] = -1; sm.segt[q] = 0; sm.segd[q] = 0; }
+        __syncthreads();
+        int poison = 0;
+        export_segments(an, sm.ts, sm.segk, sm.segt, sm.segd, sm.wraw, &poison);
+        __syncthreads();
+        if (tid == 0) walk_slot(sm.segk, sm.segt, sm.segd, sm.wraw, total.cnt, S_in, &bad, sm.segstate);
     } else if (tid == 0) {
         sm.segstate[0] = S_in;
-        sm.bad = 0;
     }
     if (tid == 0) {
-        sm.tile_lo = p.U ? count_below_str(S_in, p.U, p.n, Nd) : count_below_sys(S_in, p.u, p.n, Nd, p.tau);
+        const double c0 = __longlong_as_double(S_in);
+        sm.tile_lo = STRAT ? count_below_str(c0, p.U, p.n, Nd) : count_below_sys(c0, p.u, p.n, Nd, p.tau);
     }
     __syncthreads();
     const i64 tile_lo = sm.tile_lo;
     // exact c_j and the output range end of every element
     const i64 jbase = (i64)t * TILE + (i64)tid * IPT;
-    int bad = 0;
+    double seq_acc = __longlong_as_double(seq_start);
 #pragma unroll
     for (int k = 0; k < IPT; k++) {
-        const int seg = an.inc[k].cnt;
-        double S0 = sm.segstate[seg];
-        // raw element: the segment it opens starts at its own result; only zeros so far: unchanged
-        double c = (an.ek[k] == -1 || an.inc[k].k == -2) ? S0 : apply_map(S0, Map{an.inc[k].d0, an.inc[k].d1}, an.inc[k].k, &bad);
-        i64 h;
-        if (jbase + k < p.n) {
-            h = p.U ? count_below_str(c, p.U, p.n, Nd) : count_below_sys(c, p.u, p.n, Nd, p.tau);
+        i64 cb;
+        if (fast) {
+            cb = cbits[k];
+        } else if (seq_tile) {
+            seq_acc = __dadd_rn(seq_acc, an.w[k]);
+            cb = __double_as_longlong(seq_acc);
         } else {
-            h = -1;       // filled in below: padding elements own no output
+            const i64 S0 = sm.segstate[an.inc[k].cnt];
+            // a raw element: the segment it opens starts at its own result; only zeros so far: unchanged
+            cb = (an.ek[k] == -1 || an.inc[k].k < 0) ? S0 : apply_bits(S0, an.inc[k].d, an.inc[k].t, an.inc[k].k, &bad);
         }
-        i64 rel = (h < 0) ? -1 : (h - tile_lo);
-        sm.hi[tid * IPT + k] = (int)rel;
+        int rel = -1;                         // padding elements own no output (fixed below)
+        if (jbase + k < p.n) {
+            const double c = __longlong_as_double(cb);
+            const i64 h = STRAT ? count_below_str(c, p.U, p.n, Nd) : count_below_sys(c, p.u, p.n, Nd, p.tau);
+            rel = (int)(h - tile_lo);
+        }
+        sm.hi[tid * IPT + k] = rel;
     }
     if (bad) ws.hdr->chain_bad = 2;      // cannot happen after pass D verified the tile; recorded for tests
     __syncthreads();
-    // padding elements inherit the end of the last real element
     {
-        const i64 last_real = p.n - 1 - (i64)t * TILE;      // index in tile of the last real element
+        const i64 last_real = p.n - 1 - (i64)t * TILE;      // padding inherits the end of the last real element
         if (last_real < TILE - 1) {
-            int hv = sm.hi[last_real];
+            const int hv = sm.hi[last_real];
             __syncthreads();
             for (int q = tid; q < TILE; q += BLOCK) if (q > last_real) sm.hi[q] = hv;
+            __syncthreads();
         }
     }
-    __syncthreads();
     const int tile_cnt = sm.hi[TILE - 1];                   // outputs owned by this tile
     if (t == ws.T - 1 && tid == 0) {
-        if (p.cumsum_last) *p.cumsum_last = ws.S_in[ws.T];
-        i64 O1 = tile_lo + tile_cnt;
+        if (p.cumsum_last) *p.cumsum_last = __longlong_as_double(ws.S_in[ws.T]);
+        const i64 O1 = tile_lo + tile_cnt;
         if (O1 < p.n) {                                     // resampling.py:145 would raise IndexError
             ws.hdr->overflow = (int)(p.n - O1 > 0x7fffffff ? 0x7fffffff : p.n - O1);
-            int r = atomicAdd(&ws.hdr->n_runs, 1);
+            const int r = atomicAdd(&ws.hdr->n_runs, 1);
             if (r < ws.max_runs) ws.runs[r] = Run{O1, p.n, (int)(p.n - 1), 0};
         }
     }
     // expansion: outputs [tile_lo + cs, tile_lo + ce) per pass
     int cs = 0;
     while (cs < tile_cnt) {
-        // owner of output cs: first element with hi > cs
-        int lo_s = 0, hi_s = TILE - 1;
+        int lo_s = 0, hi_s = TILE - 1;                      // owner of output cs: first element with hi > cs
         while (lo_s < hi_s) {
-            int mid = (lo_s + hi_s) >> 1;
+            const int mid = (lo_s + hi_s) >> 1;
             if (sm.hi[mid] > cs) hi_s = mid; else lo_s = mid + 1;
         }
         const int owner = lo_s;
         const int owner_end = sm.hi[owner];
         if (owner_end - cs >= BIGRUN) {
             if (tid == 0) {
-                int r = atomicAdd(&ws.hdr->n_runs, 1);
+                const int r = atomicAdd(&ws.hdr->n_runs, 1);
                 if (r < ws.max_runs) ws.runs[r] = Run{tile_lo + cs, tile_lo + owner_end, (int)((i64)t * TILE + owner), 0};
                 else ws.hdr->fallback = 1;
             }
@@ -699,23 +926,19 @@ __global__ void __launch_bounds__(BLOCK) k_emit(Params p)
             const int e = tid * IPT + k;
             const int h = sm.hi[e];
             const int l = (e == 0) ? 0 : sm.hi[e - 1];
-            if (h > l && h > cs && l < ce) {
-                int start = l > cs ? l : cs;
-                sm.ebuf[start - cs] = e + 1;
-            }
+            if (h > l && h > cs && l < ce) sm.ebuf[(l > cs ? l : cs) - cs] = e + 1;
         }
         __syncthreads();
-        // inclusive max-scan over ebuf[0 .. ce-cs): 16 consecutive entries per thread
-        {
+        {   // inclusive max-scan over ebuf: 16 consecutive entries per thread
             constexpr int PER = EXPAND / BLOCK;
             int v[PER];
             int m = 0;
 #pragma unroll
-            for (int q = 0; q < PER; q++) { int x = sm.ebuf[tid * PER + q]; m = x > m ? x : m; v[q] = m; }
+            for (int q = 0; q < PER; q++) { const int x = sm.ebuf[tid * PER + q]; m = x > m ? x : m; v[q] = m; }
             const int lane = tid & 31, wid = tid >> 5;
             int inc = m;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc = y > inc ? y : inc; }
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc = y > inc ? y : inc; }
             if (lane == 31) sm.warp_max[wid] = inc;
             __syncthreads();
             int basem = 0;
@@ -754,17 +977,16 @@ __global__ void k_sequential(Params p, double carry)
     const Ws &ws = p.ws;
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (!ws.hdr->fallback) {
-        if (p.info) { p.info[0] = ws.hdr->overflow; p.info[1] = 0; p.info[2] = ws.hdr->n_unclean; p.info[3] = ws.hdr->n_runs; p.info[4] = ws.hdr->chain_bad; }
+        if (p.info) { p.info[0] = ws.hdr->overflow; p.info[1] = 0; p.info[2] = ws.hdr->n_unclean; p.info[3] = ws.hdr->n_runs; p.info[4] = ws.hdr->chain_bad; p.info[5] = ws.hdr->n_seq; }
         return;
     }
     // resampling.py:141-149 — cumulative sum and two-pointer merge, one element at a time
     const double Nd = (double)p.n;
     i64 i = 0, j = 0;
-    double c = __dadd_rn(carry, p.w[0]);
-    if (carry == 0.0) c = p.w[0];
+    double c = (carry == 0.0) ? p.w[0] : __dadd_rn(carry, p.w[0]);
     int overflow = 0;
     while (i < p.n) {
-        double pos = p.U ? pos_str(i, p.U, Nd) : pos_sys(i, p.u, Nd);
+        const double pos = p.U ? pos_str(i, p.U, Nd) : pos_sys(i, p.u, Nd);
         if (pos < c) { p.idx[i] = (int)j; i++; }
         else {
             j++;
@@ -776,7 +998,7 @@ __global__ void k_sequential(Params p, double carry)
         for (i64 q = j + 1; q < p.n; q++) c = __dadd_rn(c, p.w[q]);
         *p.cumsum_last = c;
     }
-    if (p.info) { p.info[0] = overflow; p.info[1] = 1; p.info[2] = ws.hdr->n_unclean; p.info[3] = ws.hdr->n_runs; p.info[4] = ws.hdr->chain_bad; }
+    if (p.info) { p.info[0] = overflow; p.info[1] = 1; p.info[2] = ws.hdr->n_unclean; p.info[3] = ws.hdr->n_runs; p.info[4] = ws.hdr->chain_bad; p.info[5] = ws.hdr->n_seq; }
 }
 
 // ------------------------------------------------------------------ weight sum / scale
@@ -790,10 +1012,8 @@ __global__ void __launch_bounds__(BLOCK) k_scale(i64 n, const double *w, const d
 __global__ void __launch_bounds__(CHAIN_THREADS) k_sum_tiles(const double *tile_sum, int T, double *out)
 {
     __shared__ double sh[CHAIN_THREADS];
-    const int per = (T + CHAIN_THREADS - 1) / CHAIN_THREADS;
-    const int a = threadIdx.x * per, b = min(T, a + per);
     double s = 0.0;
-    for (int t = a; t < b; t++) s += tile_sum[t];
+    for (int t = threadIdx.x; t < T; t += CHAIN_THREADS) s += tile_sum[t];
     sh[threadIdx.x] = s;
     __syncthreads();
     for (int o = CHAIN_THREADS / 2; o > 0; o >>= 1) {
@@ -817,18 +1037,23 @@ int run(i64 n, const double *w, double u, const double *U, int *idx, void *works
     Params p;
     carve(n, (unsigned char *)workspace, &p.ws);
     p.w = w; p.n = n; p.u = u; p.U = U; p.idx = idx; p.info = info; p.cumsum_last = cumsum_last;
-    p.eps = ldexp((double)n + 4096.0, -52);
-    double tau = ldexp((double)n, -46);
+    // |exact sequential sum - approximate tree sum| <= (n + 4096) * 2^-53 relative (non-negative
+    // terms), i.e. less than (n + 4096) ulps of the running sum; doubled, plus slack.
+    p.eb = 2 * (n + 4096) + (n >> 4);
+    const double tau = ldexp((double)n, -46);
     p.tau = tau > 1e-6 ? tau : 1e-6;
+    p.aligned16 = (reinterpret_cast<uintptr_t>(w) & 15) == 0;
     if (check_cuda(cudaMemsetAsync(p.ws.hdr, 0, sizeof(Header), s), "memset header")) return BKE_ERR_CUDA;
     const int T = p.ws.T;
     const int emit_smem = (int)sizeof(EmitShared);
-    if (check_cuda(cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, emit_smem), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
+    if (check_cuda(cudaFuncSetAttribute(k_emit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, emit_smem), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
+    if (check_cuda(cudaFuncSetAttribute(k_emit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, emit_smem), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
     k_tile_sums<<<T, BLOCK, 0, s>>>(p);
     k_scan_tiles<<<1, CHAIN_THREADS, 0, s>>>(p);
     k_tile_maps<<<T, BLOCK, 0, s>>>(p);
     k_chain<<<1, CHAIN_THREADS, 0, s>>>(p, 0.0);
-    k_emit<<<T, BLOCK, emit_smem, s>>>(p);
+    if (U) k_emit<true><<<T, BLOCK, emit_smem, s>>>(p);
+    else k_emit<false><<<T, BLOCK, emit_smem, s>>>(p);
     k_fill_runs<<<sm_count() * 4, 256, 0, s>>>(p);
     k_sequential<<<1, 32, 0, s>>>(p, 0.0);
     return check_cuda(cudaGetLastError(), "resample launch");
@@ -872,6 +1097,7 @@ int bke_weights_sum(int64_t n, const double *weights, double *sum_out, void *wor
     rs::Params p;
     rs::carve(n, (unsigned char *)workspace, &p.ws);
     p.w = weights; p.n = n;
+    p.aligned16 = (reinterpret_cast<uintptr_t>(weights) & 15) == 0;
     if (check_cuda(cudaMemsetAsync(p.ws.hdr, 0, sizeof(rs::Header), s), "memset header")) return BKE_ERR_CUDA;
     rs::k_tile_sums<<<p.ws.T, rs::BLOCK, 0, s>>>(p);
     rs::k_sum_tiles<<<1, rs::CHAIN_THREADS, 0, s>>>(p.ws.tile_sum, p.ws.T, sum_out);
