@@ -46,3 +46,26 @@ def ptr(t):
 
 def stream_ptr(device):
     return torch.cuda.current_stream(device).cuda_stream
+
+
+class StepGraph(object):
+    """A CUDA graph of a fixed sequence of engine calls (e.g. ``kf.predict(); kf.update(z_buf)`` for a
+    ring of measurement buffers).  Replaying it re-runs exactly those kernels on the same device
+    buffers with one launch: the inner loop of a tracker that refills ``z_buf`` every epoch pays no
+    per-kernel launch latency.  Capture needs calls that neither allocate nor synchronise, i.e. banks
+    built with ``diagnostics=False`` and device-resident inputs."""
+
+    def __init__(self, fn, device, warmup=2):
+        side = torch.cuda.Stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):           # lazy one-time work (function attributes, tensor maps) happens here
+                fn()
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=side):
+            fn()
+
+    def replay(self):
+        self.graph.replay()

@@ -216,15 +216,39 @@ kf42_f32_kernel(const __grid_constant__ Maps maps, const FastP<4, 2> p)
             float2 v = *reinterpret_cast<const float2 *>(sb + St::OZ + tid * 8);
             z[0] = v.x; z[1] = v.y;
         }
-        // The stage is about to be handed back to the TMA engine (async proxy).  A barrier alone
+        // The stage is about to be handed back to the TMA engine (async proxy).  A plain barrier
         // does not order the generic-proxy LDS above against that: the loads may still sit in the
         // LSU queue when the barrier releases, and a TMA refill served from L2 can land first
-        // (observed in round 1: a few filters per launch picked up rows of the NEXT tile; an empty
-        // asm "use" of the registers does not help, the scoreboard wait rides on the first real
-        // consumer instruction).  The cross-proxy fence makes every thread's reads of the stage
-        // complete before it arrives at the barrier.
-        fence_proxy_async();
-        __syncthreads();      // every thread has drained the stage
+        // (observed in round 1: a few filters per launch picked up rows of the NEXT tile).  Two
+        // fixes were measured: a cross-proxy fence (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, which also
+        // waits for the previous tile's global stores) and the one used here: fold every loaded
+        // register into the predicate of the barrier itself (BAR.RED), so the barrier instruction
+        // cannot issue before all LDS results have returned.
+        unsigned acc = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            acc ^= __float_as_uint(x[i]);
+#pragma unroll
+            for (int j = 0; j < N; j++) acc ^= __float_as_uint(P[i][j]);
+        }
+        if (!SHARED && DO_P) {
+#pragma unroll
+            for (int i = 0; i < N; i++)
+#pragma unroll
+                for (int j = 0; j < N; j++) acc ^= __float_as_uint(F[i][j]) ^ __float_as_uint(Q[i][j]);
+        }
+        if (!SHARED && DO_U) {
+#pragma unroll
+            for (int a = 0; a < M; a++) {
+#pragma unroll
+                for (int j = 0; j < N; j++) acc ^= __float_as_uint(H[a][j]);
+#pragma unroll
+                for (int b = 0; b < M; b++) acc ^= __float_as_uint(R[a][b]);
+            }
+        }
+        if (DO_U) acc ^= __float_as_uint(z[0]) ^ __float_as_uint(z[1]);
+        const int never = __syncthreads_and(acc == 0x7fc0beefu);     // every thread has drained the stage
+        if (never && p.num_tiles < 0) p.x_out[0] = 0.f;              // keeps `acc` alive; cannot happen
         if (tid == 0) {
             int nt = tile + STAGES * gridDim.x;
             if (nt < p.num_tiles) issue(nt, stage);
@@ -356,7 +380,13 @@ int launch_variant_s(const Maps &maps, const FastP<4, 2> &p, cudaStream_t s, int
     using St = Stage<float, 4, 2>;
     auto kern = kf42_f32_kernel<MODE, SHARED, EXTRAS, STAGES>;
     const int smem = STAGES * St::BYTES;
-    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
+    static bool configured[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
     int grid = sm_count() * ctas_per_sm;
     if (grid > p.num_tiles) grid = p.num_tiles;
     kern<<<grid, TILE, smem, s>>>(maps, p);
@@ -394,12 +424,25 @@ int launch_kf_fast(const bke_kf_args &a, cudaStream_t s)
     if (!get_encode()) return BKE_ERR_UNSUPPORTED;
 
     const int64_t N = a.n_filters;
-    Maps maps;
-    memset(&maps, 0, sizeof(maps));
-    bool ok = make_map_2d(&maps.x, a.x, N, 4) && make_map_2d(&maps.P, a.P, N, 16);
-    if (all_dense && dp) ok = ok && make_map_2d(&maps.F, a.F, N, 16) && make_map_2d(&maps.Q, a.Q, N, 16);
-    if (all_dense && du) ok = ok && make_map_2d(&maps.H, a.H, N, 8) && make_map_2d(&maps.R, a.R, N, 4);
-    if (du) ok = ok && make_map_1d(&maps.z, a.z, N * 2, TILE * 2);
+    // Tensor maps are pure functions of (base pointer, rows): a per-thread cache re-encodes only
+    // the ones whose array changed since the last call (in a filter loop: just z).
+    static thread_local Maps maps;
+    static thread_local const void *key_ptr[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    static thread_local int64_t key_n[7] = {-1, -1, -1, -1, -1, -1, -1};
+    bool ok = true;
+    auto cached2d = [&](int slot, CUtensorMap *m, const void *ptr, int row_elems) {
+        if (key_ptr[slot] == ptr && key_n[slot] == N) return;
+        ok = ok && make_map_2d(m, ptr, N, row_elems);
+        key_ptr[slot] = ptr; key_n[slot] = ok ? N : -1;
+    };
+    cached2d(0, &maps.x, a.x, 4);
+    cached2d(1, &maps.P, a.P, 16);
+    if (all_dense && dp) { cached2d(2, &maps.F, a.F, 16); cached2d(3, &maps.Q, a.Q, 16); }
+    if (all_dense && du) { cached2d(4, &maps.H, a.H, 8); cached2d(5, &maps.R, a.R, 4); }
+    if (du && !(key_ptr[6] == a.z && key_n[6] == N)) {
+        ok = ok && make_map_1d(&maps.z, a.z, N * 2, TILE * 2);
+        key_ptr[6] = a.z; key_n[6] = ok ? N : -1;
+    }
     if (!ok) { set_error("cuTensorMapEncodeTiled failed"); return BKE_ERR_CUDA; }
 
     FastP<4, 2> p;

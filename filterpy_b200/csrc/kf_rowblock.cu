@@ -1,0 +1,451 @@
+// kf_rowblock.cu — fused predict+update for shapes whose covariance does not fit one thread's
+// registers (BASELINE config 3: dim_x=9, dim_z=3, fp64; also 4/2 fp64, 6/3): a sub-warp of G lanes
+// owns one filter, each lane owns RPL consecutive ROWS of every n x n matrix.
+//
+//   * every row-block product C[r,:] = sum_k A[r,k] * B[k,:] keeps A's rows and C's rows in the
+//     owning lane's registers and reads B from shared memory — the same address for the G lanes of
+//     a filter (broadcast), 8-byte words of different filters fall into different banks;
+//   * per warp, FPW = 32/G filters form a tile; ONE lane pulls the tile's x, P, F, Q, H, R, z blocks
+//     (contiguous byte ranges of the dense AoS arrays) with 1-D bulk TMA copies
+//     (cp.async.bulk.shared::cluster.global, SASS UBLKCP) into a 2-stage ring with an mbarrier per
+//     stage; every warp runs its own ring (no block barriers anywhere);
+//   * intermediates reuse the stage: P' overwrites P, (I-KH) overwrites F, K / PH' overwrite Q;
+//   * the posterior rows go to a small staging buffer and leave with bulk TMA stores
+//     (cp.async.bulk.global.shared::cta); the cross-proxy fence that publishes them also orders
+//     every earlier shared-memory read before the stage is handed back to the TMA engine.
+//
+// Arithmetic per filter: filterpy/kalman/kalman_filter.py:471-478 (predict) and :533-556 (update,
+// Joseph form), reference @ 3b51149.  Algorithmic bytes per filter-step (9/3 fp64): 3048.
+#include <type_traits>
+#include "bke_internal.cuh"
+#include "kf_regtile.cuh"
+
+namespace bke {
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "RB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra RB_DONE;\n"
+        "bra RB_WAIT;\n"
+        "RB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *dst, const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <typename T>
+struct RbP {
+    int64_t N;                 // filters handled by this launch (a multiple of FPW)
+    T alpha_sq;
+    const T *x, *P, *F, *Q, *H, *R, *z;
+    T *x_out, *P_out;
+    const uint8_t *valid;
+    int32_t *status;
+};
+
+constexpr int RB_WARPS = 4;
+constexpr int RB_STAGES = 2;
+
+template <typename T, int N, int M, int RPL>
+struct RbGeom {
+    static constexpr int G = N / RPL;                 // lanes per filter
+    static constexpr int FPW = 32 / G;                // filters per warp tile
+    static constexpr int XB = FPW * N * sizeof(T);
+    static constexpr int PB = FPW * N * N * sizeof(T);
+    static constexpr int HB = FPW * M * N * sizeof(T);
+    static constexpr int RBY = FPW * M * M * sizeof(T);
+    static constexpr int ZB = FPW * M * sizeof(T);
+    static constexpr int a16(int v) { return (v + 15) & ~15; }
+    static constexpr int OX = 0;
+    static constexpr int OP = OX + a16(XB);
+    static constexpr int OF = OP + a16(PB);
+    static constexpr int OQ = OF + a16(PB);
+    static constexpr int OH = OQ + a16(PB);
+    static constexpr int OR_ = OH + a16(HB);
+    static constexpr int OZ = OR_ + a16(RBY);
+    static constexpr int STAGE = a16(OZ + a16(ZB));
+    static constexpr int OUT = a16(XB) + a16(PB);     // posterior staging (x then P)
+    static constexpr int WARP_BYTES = RB_STAGES * STAGE + OUT;
+    static constexpr uint32_t TX = XB + 3 * PB + HB + RBY + ZB;
+    static_assert(N % RPL == 0 && G >= 1 && G <= 32, "bad row-block shape");
+    static_assert(XB % 16 == 0 && PB % 16 == 0 && HB % 16 == 0 && RBY % 16 == 0 && ZB % 16 == 0, "bulk copies need 16-byte multiples");
+    static_assert(2 * N * M <= N * N, "K and PH' are parked in the Q slot");
+};
+
+template <typename T, int N, int M, int RPL>
+__global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
+{
+    using Gm = RbGeom<T, N, M, RPL>;
+    constexpr int G = Gm::G, FPW = Gm::FPW;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bars[RB_WARPS][RB_STAGES];
+
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    unsigned char *wbase = smem + (size_t)wib * Gm::WARP_BYTES;
+    unsigned char *outb = wbase + RB_STAGES * Gm::STAGE;
+    uint64_t *bar = bars[wib];
+    const bool active = lane < FPW * G;
+    const int fl = active ? lane / G : FPW - 1;            // filter within the tile (idle lanes mirror the last one)
+    const int rb = active ? lane % G : 0;
+    const int r0 = rb * RPL;
+
+    const int64_t tiles = p.N / FPW;
+    const int64_t wglobal = (int64_t)blockIdx.x * RB_WARPS + wib;
+    const int64_t wstride = (int64_t)gridDim.x * RB_WARPS;
+
+    auto issue = [&](int64_t tile, int stage) {
+        unsigned char *sb = wbase + stage * Gm::STAGE;
+        const int64_t f0 = tile * FPW;
+        mbar_expect_tx(&bar[stage], Gm::TX);
+        bulk_load(sb + Gm::OX, p.x + f0 * N, Gm::XB, &bar[stage]);
+        bulk_load(sb + Gm::OP, p.P + f0 * N * N, Gm::PB, &bar[stage]);
+        bulk_load(sb + Gm::OF, p.F + f0 * N * N, Gm::PB, &bar[stage]);
+        bulk_load(sb + Gm::OQ, p.Q + f0 * N * N, Gm::PB, &bar[stage]);
+        bulk_load(sb + Gm::OH, p.H + f0 * M * N, Gm::HB, &bar[stage]);
+        bulk_load(sb + Gm::OR_, p.R + f0 * M * M, Gm::RBY, &bar[stage]);
+        bulk_load(sb + Gm::OZ, p.z + f0 * M, Gm::ZB, &bar[stage]);
+    };
+
+    if (lane == 0) {
+        for (int s = 0; s < RB_STAGES; s++) mbar_init(&bar[s], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (lane == 0) {
+        for (int s = 0; s < RB_STAGES; s++) {
+            const int64_t tile = wglobal + s * wstride;
+            if (tile < tiles) issue(tile, s);
+        }
+    }
+
+    int it = 0;
+    for (int64_t tile = wglobal; tile < tiles; tile += wstride, it++) {
+        const int stage = it % RB_STAGES;
+        const uint32_t parity = (it / RB_STAGES) & 1;
+        unsigned char *sb = wbase + stage * Gm::STAGE;
+        mbar_wait(&bar[stage], parity);
+
+        T *sx = reinterpret_cast<T *>(sb + Gm::OX) + fl * N;
+        T *sP = reinterpret_cast<T *>(sb + Gm::OP) + fl * N * N;
+        T *sF = reinterpret_cast<T *>(sb + Gm::OF) + fl * N * N;
+        T *sQ = reinterpret_cast<T *>(sb + Gm::OQ) + fl * N * N;
+        const T *sH = reinterpret_cast<const T *>(sb + Gm::OH) + fl * M * N;
+        const T *sR = reinterpret_cast<const T *>(sb + Gm::OR_) + fl * M * M;
+        const T *sz = reinterpret_cast<const T *>(sb + Gm::OZ) + fl * M;
+        T *ox = reinterpret_cast<T *>(outb) + fl * N;
+        T *oP = reinterpret_cast<T *>(outb + Gm::a16(Gm::XB)) + fl * N * N;
+        const int64_t f = tile * FPW + fl;
+
+        // ---------------- predict: x' = F x ; P' = alpha^2 (F P) F' + Q -----------------------
+        T A[RPL][N];                 // this lane's rows of the left operand
+        T C[RPL][N];                 // this lane's rows of the result
+#pragma unroll
+        for (int i = 0; i < RPL; i++)
+#pragma unroll
+            for (int k = 0; k < N; k++) A[i][k] = sF[(r0 + i) * N + k];
+        T xr[RPL];
+#pragma unroll
+        for (int i = 0; i < RPL; i++) {
+            T s = T(0);
+#pragma unroll
+            for (int k = 0; k < N; k++) s += A[i][k] * sx[k];
+            xr[i] = s;
+        }
+        // C = F P (own rows)
+#pragma unroll
+        for (int i = 0; i < RPL; i++)
+#pragma unroll
+            for (int j = 0; j < N; j++) C[i][j] = T(0);
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            T b[N];
+#pragma unroll
+            for (int j = 0; j < N; j++) b[j] = sP[k * N + j];
+#pragma unroll
+            for (int i = 0; i < RPL; i++)
+#pragma unroll
+                for (int j = 0; j < N; j++) C[i][j] += A[i][k] * b[j];
+        }
+        // A = alpha^2 * C F' + Q (own rows of P')
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            T b[N];
+#pragma unroll
+            for (int k = 0; k < N; k++) b[k] = sF[j * N + k];
+#pragma unroll
+            for (int i = 0; i < RPL; i++) {
+                T s = T(0);
+#pragma unroll
+                for (int k = 0; k < N; k++) s += C[i][k] * b[k];
+                A[i][j] = p.alpha_sq * s + sQ[(r0 + i) * N + j];
+            }
+        }
+        __syncwarp();                               // every lane is done reading x, P (and F rows it needed as B)
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < RPL; i++) {
+                sx[r0 + i] = xr[i];
+#pragma unroll
+                for (int j = 0; j < N; j++) sP[(r0 + i) * N + j] = A[i][j];          // P' overwrites P
+            }
+        }
+        __syncwarp();
+
+        // ---------------- update ------------------------------------------------------------
+        const bool has_z = (p.valid == nullptr) || (p.valid[f] != 0);
+        const unsigned um = __ballot_sync(FULL, has_z);
+        int st = BKE_STATUS_OK;
+        T xo[RPL];
+#pragma unroll
+        for (int i = 0; i < RPL; i++) xo[i] = xr[i];
+        // A holds this lane's rows of P'; they become the output unless the update succeeds
+        if (has_z) {
+            T Hm[M][N];
+#pragma unroll
+            for (int a = 0; a < M; a++)
+#pragma unroll
+                for (int k = 0; k < N; k++) Hm[a][k] = sH[a * N + k];
+            T y[M];
+#pragma unroll
+            for (int a = 0; a < M; a++) {
+                T s = T(0);
+#pragma unroll
+                for (int k = 0; k < N; k++) s += Hm[a][k] * sx[k];
+                y[a] = sz[a] - s;
+            }
+            // own rows of P H'  -> parked in the Q slot (offset 0)
+            T PHT[RPL][M];
+#pragma unroll
+            for (int i = 0; i < RPL; i++)
+#pragma unroll
+                for (int a = 0; a < M; a++) {
+                    T s = T(0);
+#pragma unroll
+                    for (int k = 0; k < N; k++) s += A[i][k] * Hm[a][k];
+                    PHT[i][a] = s;
+                }
+            T *sPHT = sQ;                     // [N][M]
+            T *sK = sQ + N * M;               // [N][M]   (needs 2*N*M <= N*N)
+            __syncwarp(um);                   // Q rows were consumed above
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < RPL; i++)
+#pragma unroll
+                    for (int a = 0; a < M; a++) sPHT[(r0 + i) * M + a] = PHT[i][a];
+            }
+            __syncwarp(um);
+            KfUpdateOut<T, N, M> o;
+#pragma unroll
+            for (int a = 0; a < M; a++)
+#pragma unroll
+                for (int b = 0; b < M; b++) {
+                    T s = sR[a * M + b];
+#pragma unroll
+                    for (int k = 0; k < N; k++) s += Hm[a][k] * sPHT[k * M + b];
+                    o.S[a][b] = s;
+                }
+            o.ok = reg_inverse<T, M>(o.S, o.SI, o.logdet);
+            if (!o.ok) {
+                st = BKE_STATUS_SINGULAR_S;
+            }
+            // K rows, x, (I - K H) rows
+            T Kr[RPL][M];
+#pragma unroll
+            for (int i = 0; i < RPL; i++)
+#pragma unroll
+                for (int a = 0; a < M; a++) {
+                    T s = T(0);
+#pragma unroll
+                    for (int b = 0; b < M; b++) s += PHT[i][b] * o.SI[b][a];
+                    Kr[i][a] = s;
+                }
+#pragma unroll
+            for (int i = 0; i < RPL; i++) {
+                T s = xr[i];
+#pragma unroll
+                for (int a = 0; a < M; a++) s += Kr[i][a] * y[a];
+                if (o.ok) xo[i] = s;
+            }
+#pragma unroll
+            for (int i = 0; i < RPL; i++)
+#pragma unroll
+                for (int j = 0; j < N; j++) {
+                    T s = ((r0 + i) == j) ? T(1) : T(0);
+#pragma unroll
+                    for (int a = 0; a < M; a++) s -= Kr[i][a] * Hm[a][j];
+                    C[i][j] = s;                                   // own rows of I - K H
+                }
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < RPL; i++) {
+#pragma unroll
+                    for (int j = 0; j < N; j++) sF[(r0 + i) * N + j] = C[i][j];     // (I-KH) overwrites F
+#pragma unroll
+                    for (int a = 0; a < M; a++) sK[(r0 + i) * M + a] = Kr[i][a];
+                }
+            }
+            __syncwarp(um);
+            // T1 = (I-KH) P'  (own rows, into A2), then P = T1 (I-KH)' + (K R) K'
+            T T1[RPL][N];
+#pragma unroll
+            for (int i = 0; i < RPL; i++)
+#pragma unroll
+                for (int j = 0; j < N; j++) T1[i][j] = T(0);
+#pragma unroll
+            for (int k = 0; k < N; k++) {
+                T b[N];
+#pragma unroll
+                for (int j = 0; j < N; j++) b[j] = sP[k * N + j];
+#pragma unroll
+                for (int i = 0; i < RPL; i++)
+#pragma unroll
+                    for (int j = 0; j < N; j++) T1[i][j] += C[i][k] * b[j];
+            }
+            T KR[RPL][M];
+#pragma unroll
+            for (int i = 0; i < RPL; i++)
+#pragma unroll
+                for (int b = 0; b < M; b++) {
+                    T s = T(0);
+#pragma unroll
+                    for (int a = 0; a < M; a++) s += Kr[i][a] * sR[a * M + b];
+                    KR[i][b] = s;
+                }
+#pragma unroll
+            for (int j = 0; j < N; j++) {
+                T b[N], kb[M];
+#pragma unroll
+                for (int k = 0; k < N; k++) b[k] = sF[j * N + k];
+#pragma unroll
+                for (int a = 0; a < M; a++) kb[a] = sK[j * M + a];
+#pragma unroll
+                for (int i = 0; i < RPL; i++) {
+                    T s = T(0);
+#pragma unroll
+                    for (int k = 0; k < N; k++) s += T1[i][k] * b[k];
+#pragma unroll
+                    for (int a = 0; a < M; a++) s += KR[i][a] * kb[a];
+                    if (o.ok) A[i][j] = s;
+                }
+            }
+        }
+        // ---------------- posterior rows -> staging -> bulk TMA store ---------------------------
+        if (it > 0 && lane == 0) bulk_wait_read();          // the previous tile's stores have read the staging buffer
+        __syncwarp();
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < RPL; i++) {
+                ox[r0 + i] = xo[i];
+#pragma unroll
+                for (int j = 0; j < N; j++) oP[(r0 + i) * N + j] = A[i][j];
+            }
+            if (p.status && rb == 0) p.status[f] = st;
+        }
+        fence_proxy_async();      // publishes the staging buffer to the async proxy AND completes every earlier LDS of the stage
+        __syncwarp();
+        if (lane == 0) {
+            const int64_t f0 = tile * FPW;
+            bulk_store(p.x_out + f0 * N, outb, Gm::XB);
+            bulk_store(p.P_out + f0 * N * N, outb + Gm::a16(Gm::XB), Gm::PB);
+            bulk_commit();
+            const int64_t nt = tile + RB_STAGES * wstride;
+            if (nt < tiles) issue(nt, stage);
+        }
+        __syncwarp();
+    }
+    if (lane == 0) bulk_wait_all();
+}
+
+template <typename T, int N, int M, int RPL>
+int launch_rb(const bke_kf_args &a, cudaStream_t s)
+{
+    using Gm = RbGeom<T, N, M, RPL>;
+    const int64_t Nmain = (a.n_filters / Gm::FPW) * Gm::FPW;
+    const int64_t rem = a.n_filters - Nmain;
+    if (Nmain > 0) {
+        RbP<T> p;
+        p.N = Nmain; p.alpha_sq = (T)a.alpha_sq;
+        p.x = (const T *)a.x; p.P = (const T *)a.P; p.F = (const T *)a.F; p.Q = (const T *)a.Q;
+        p.H = (const T *)a.H; p.R = (const T *)a.R; p.z = (const T *)a.z;
+        p.x_out = (T *)a.x_out; p.P_out = (T *)a.P_out; p.valid = a.z_valid; p.status = a.status;
+        auto kern = kf_rowblock_kernel<T, N, M, RPL>;
+        const int smem = RB_WARPS * Gm::WARP_BYTES;
+        static bool configured[64] = {false};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !configured[dev]) {
+            if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
+            if (dev >= 0 && dev < 64) configured[dev] = true;
+        }
+        const int64_t tiles = Nmain / Gm::FPW;
+        int64_t grid = (tiles + RB_WARPS - 1) / RB_WARPS;
+        if (grid > sm_count()) grid = sm_count();
+        kern<<<(unsigned)grid, RB_WARPS * 32, smem, s>>>(p);
+        if (check_cuda(cudaGetLastError(), "kf_rowblock_kernel launch")) return BKE_ERR_CUDA;
+    }
+    if (rem > 0) {       // ragged tail (< one warp tile): the catch-all kernel on the last few filters
+        bke_kf_args t = a;
+        const size_t es = sizeof(T);
+        auto off = [&](const void *ptr, int64_t per) { return ptr ? (const void *)((const char *)ptr + (size_t)Nmain * per * es) : nullptr; };
+        t.n_filters = rem;
+        t.x = off(a.x, N); t.P = off(a.P, N * N); t.x_out = (void *)off(a.x_out, N); t.P_out = (void *)off(a.P_out, N * N);
+        t.F = off(a.F, N * N); t.Q = off(a.Q, N * N); t.H = off(a.H, M * N); t.R = off(a.R, M * M);
+        t.z = off(a.z, M);
+        t.z_valid = a.z_valid ? a.z_valid + Nmain : nullptr;
+        t.status = a.status ? a.status + Nmain : nullptr;
+        return launch_kf_generic(t, s);
+    }
+    return BKE_OK;
+}
+
+bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+int launch_kf_rowblock(const bke_kf_args &a, cudaStream_t s)
+{
+    // fused predict+update, per-filter dense models, no control input, no optional outputs
+    if ((a.flags & (BKE_DO_PREDICT | BKE_DO_UPDATE | BKE_UPDATE_FIRST)) != (BKE_DO_PREDICT | BKE_DO_UPDATE)) return BKE_ERR_UNSUPPORTED;
+    if (a.B && a.u) return BKE_ERR_UNSUPPORTED;
+    if (a.x_prior || a.P_prior || a.K || a.y || a.S || a.SI || a.log_likelihood) return BKE_ERR_UNSUPPORTED;
+    if (!a.F_stride || !a.Q_stride || !a.H_stride || !a.R_stride) return BKE_ERR_UNSUPPORTED;
+    if (!(al16(a.x) && al16(a.P) && al16(a.F) && al16(a.Q) && al16(a.H) && al16(a.R) && al16(a.z) && al16(a.x_out) && al16(a.P_out)))
+        return BKE_ERR_UNSUPPORTED;
+    const int n = a.dim_x, m = a.dim_z;
+    if (a.dtype == BKE_F64) {
+        if (n == 9 && m == 3) return launch_rb<double, 9, 3, 3>(a, s);
+        if (n == 4 && m == 2) return launch_rb<double, 4, 2, 2>(a, s);
+        if (n == 6 && m == 3) return launch_rb<double, 6, 3, 3>(a, s);
+    } else {
+        if (n == 6 && m == 3) return launch_rb<float, 6, 3, 3>(a, s);
+    }
+    return BKE_ERR_UNSUPPORTED;
+}
+
+}  // namespace bke

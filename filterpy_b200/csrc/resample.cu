@@ -45,6 +45,7 @@ constexpr int CHAIN_THREADS = 1024;
 constexpr int CHAIN_BATCH = 8;           // unclean tiles staged in shared memory per round of the chain
 constexpr int SEQMAX = 256;             // fully sequential tiles (dense raw zones) before giving up
 constexpr int SLOT_SEQ = -2;            // tile_slot code: every element of the tile is applied by a true add
+constexpr int SLOT_FAST = -3;           // tile_slot code: clean tile, tie-free, one binade -> plain int64 sums
 constexpr int K_ID = -2;                 // identity (only zero weights so far)
 constexpr int K_POISON = -3;             // elements of different binades were mixed (never expected)
 
@@ -371,22 +372,29 @@ struct TileAn {
     int ek[IPT];           // binade of the element (clean), K_ID (zero weight) or -1 (raw)
 };
 
-// Load the tile so that thread t owns elements [8t, 8t+8): coalesced 16-byte global loads, then a
-// transposition through shared memory whose 16-byte chunks are XOR-swizzled so that both the
-// row-major writes and the 64-byte-strided reads are bank-conflict-free.
-__device__ __forceinline__ void load_blocked(const Params &p, int t, double (&v)[IPT], double2 *buf /*[TILE/2]*/)
+// Tile loads: fetch_tile() issues the coalesced 16-byte global loads of a tile into registers (the
+// persistent kernels call it one tile AHEAD, so the HBM latency overlaps the previous tile's
+// arithmetic); to_blocked() transposes through shared memory so that thread t owns elements
+// [8t, 8t+8).  The 16-byte chunks are XOR-swizzled: both the row-major writes and the
+// 64-byte-strided reads are bank-conflict-free.
+__device__ __forceinline__ void fetch_tile(const Params &p, int t, double2 (&g)[IPT / 2])
 {
     const i64 base = (i64)t * TILE;
+#pragma unroll
+    for (int i = 0; i < IPT / 2; i++) {
+        const i64 j = base + 2 * (i64)(i * BLOCK + threadIdx.x);
+        if (p.aligned16 && j + 1 < p.n) g[i] = *reinterpret_cast<const double2 *>(p.w + j);
+        else { g[i].x = (j < p.n) ? p.w[j] : 0.0; g[i].y = (j + 1 < p.n) ? p.w[j + 1] : 0.0; }
+    }
+}
+__device__ __forceinline__ void to_blocked(const double2 (&g)[IPT / 2], double (&v)[IPT], double2 *buf /*[TILE/2]*/)
+{
     const int tid = threadIdx.x;
 #pragma unroll
     for (int i = 0; i < IPT / 2; i++) {
-        const int g = i * BLOCK + tid;                    // 16-byte chunk index in the tile
-        const i64 j = base + 2 * (i64)g;
-        double2 val;
-        if (p.aligned16 && j + 1 < p.n) val = *reinterpret_cast<const double2 *>(p.w + j);
-        else { val.x = (j < p.n) ? p.w[j] : 0.0; val.y = (j + 1 < p.n) ? p.w[j + 1] : 0.0; }
-        const int r = g >> 2, c = g & 3;
-        buf[r * 4 + (c ^ ((r >> 1) & 3))] = val;
+        const int c16 = i * BLOCK + tid;                  // 16-byte chunk index in the tile
+        const int r = c16 >> 2, c = c16 & 3;
+        buf[r * 4 + (c ^ ((r >> 1) & 3))] = g[i];
     }
     __syncthreads();
 #pragma unroll
@@ -464,6 +472,8 @@ __device__ __forceinline__ bool classify_fast(const Params &p, const double (&w)
     return ok;
 }
 
+__device__ __forceinline__ int pad32(int i) { return i + (i >> 5); }
+
 struct TileShared {
     double shd[BLOCK / 32 + 1];
     SM shm[BLOCK / 32 + 1];
@@ -512,84 +522,108 @@ struct MapsShared {
     int slot;
 };
 
-__global__ void __launch_bounds__(BLOCK) k_tile_maps(Params p)
+__global__ void __launch_bounds__(BLOCK, 2) k_tile_maps(Params p)
 {
     __shared__ MapsShared sm;
-    const int t = blockIdx.x;
     if (p.ws.hdr->fallback) return;
-    TileAn an;
-    load_blocked(p, t, an.w, sm.buf);
-    double s = 0.0;
+    const int T = p.ws.T;
+    double2 g[IPT / 2];
+    if ((int)blockIdx.x < T) fetch_tile(p, blockIdx.x, g);
+    for (int t = blockIdx.x; t < T; t += gridDim.x) {
+        const double tp = p.ws.tile_prefix[t], tp_next = p.ws.tile_prefix[t + 1];
+        int e0;
+        const bool tile_clean = clean_add(tp, tp_next, p.eb, &e0);     // the whole tile stays deep inside binade e0
+        if (tile_clean) {
+            // fast path: every add is clean; if none is a tie the tile's map is a plain int64 sum.
+            // A sum needs no particular element order: work on the striped registers directly.
+            const i64 base = (i64)e0 << 52;
+            const double B0 = __longlong_as_double(base), B1 = __longlong_as_double(base + 1);
+            i64 acc = 0;
+            bool ok = true, nz = false;
 #pragma unroll
-    for (int k = 0; k < IPT; k++) s += an.w[k];
-    double tot;
-    const double tp = p.ws.tile_prefix[t];
-    const double before = tp + block_excl_scan_d(s, &tot, sm.ts.shd);
-    {   // fast path: a tile of clean, tie-free adds in one binade -> a plain int64 sum
-        const int e0 = __double2hiint(tp) >> 20;
-        i64 pre[IPT];
-        bool nz;
-        const bool ok = classify_fast(p, an.w, before, e0, pre, &nz);
-        if (__syncthreads_and(ok)) {
-            i64 total;
-            block_excl_scan_i64(pre[IPT - 1], &total, sm.ts.shi);
-            const int any_nz = __syncthreads_or(nz);
+            for (int i = 0; i < IPT / 2; i++) {
+                const double w2[2] = {g[i].x, g[i].y};
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const i64 d0 = __double_as_longlong(__dadd_rn(B0, w2[h])) - base;
+                    const i64 d1 = __double_as_longlong(__dadd_rn(B1, w2[h])) - (base + 1);
+                    ok = ok && (d0 == d1);
+                    nz = nz || (w2[h] != 0.0);
+                    acc += d0;
+                }
+            }
+            if (__syncthreads_and(ok)) {
+                i64 total;
+                block_excl_scan_i64(acc, &total, sm.ts.shi);
+                const int any_nz = __syncthreads_or(nz);
+                if (threadIdx.x == 0) {
+                    p.ws.tile_k[t] = any_nz ? e0 : K_ID; p.ws.tile_d[t] = total; p.ws.tile_t[t] = 0;
+                    p.ws.tile_slot[t] = SLOT_FAST;
+                }
+                if (t + (int)gridDim.x < T) fetch_tile(p, t + gridDim.x, g);
+                continue;
+            }
+        }
+        TileAn an;
+        to_blocked(g, an.w, sm.buf);
+        if (t + (int)gridDim.x < T) fetch_tile(p, t + gridDim.x, g);      // next tile's loads fly during this tile
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < IPT; k++) s += an.w[k];
+        double tot;
+        const double before = tp + block_excl_scan_d(s, &tot, sm.ts.shd);
+        const SM run = classify(p, an, before);
+        const int any_raw = __syncthreads_or(run.cnt > 0);
+        if (!any_raw) {
+            SM total;
+            block_excl_scan_sm(run, &total, sm.ts.shm);
             if (threadIdx.x == 0) {
-                p.ws.tile_k[t] = any_nz ? e0 : K_ID; p.ws.tile_d[t] = total; p.ws.tile_t[t] = 0;
+                if (total.k == K_POISON) p.ws.hdr->fallback = 1;
+                p.ws.tile_k[t] = total.k; p.ws.tile_d[t] = total.d; p.ws.tile_t[t] = total.t;
                 p.ws.tile_slot[t] = -1;
             }
-            return;
+            continue;
         }
-    }
-    const SM run = classify(p, an, before);
-    const int any_raw = __syncthreads_or(run.cnt > 0);
-    if (!any_raw) {
         SM total;
-        block_excl_scan_sm(run, &total, sm.ts.shm);
-        if (threadIdx.x == 0) {
-            if (total.k == K_POISON) p.ws.hdr->fallback = 1;
-            p.ws.tile_k[t] = total.k; p.ws.tile_d[t] = total.d; p.ws.tile_t[t] = total.t;
-            p.ws.tile_slot[t] = -1;
-        }
-        return;
-    }
-    SM total;
-    const SM excl = block_excl_scan_sm(run, &total, sm.ts.shm);
+        const SM excl = block_excl_scan_sm(run, &total, sm.ts.shm);
 #pragma unroll
-    for (int k = 0; k < IPT; k++) an.inc[k] = combine(excl, an.inc[k]);
-    if (threadIdx.x == 0) {
-        int s2 = -1;
-        if (total.cnt <= RMAX) {
-            s2 = atomicAdd(&p.ws.hdr->n_unclean, 1);
-            if (s2 >= UMAX) { s2 = -1; p.ws.hdr->fallback = 1; }
-            p.ws.tile_slot[t] = s2 < 0 ? 0 : s2;
-        } else {
-            // a dense zone of raw elements (tiny weights next to a binade boundary, e.g. the tail of
-            // a degenerate weight vector approaching 1.0): the whole tile is walked with true adds
-            if (atomicAdd(&p.ws.hdr->n_seq, 1) >= SEQMAX) p.ws.hdr->fallback = 1;
-            p.ws.tile_slot[t] = SLOT_SEQ;
+        for (int k = 0; k < IPT; k++) an.inc[k] = combine(excl, an.inc[k]);
+        if (threadIdx.x == 0) {
+            int s2 = -1;
+            if (total.cnt <= RMAX) {
+                s2 = atomicAdd(&p.ws.hdr->n_unclean, 1);
+                if (s2 >= UMAX) { s2 = -1; p.ws.hdr->fallback = 1; }
+                p.ws.tile_slot[t] = s2 < 0 ? 0 : s2;
+            } else {
+                // a dense zone of raw elements (tiny weights next to a binade boundary, e.g. the tail of
+                // a degenerate weight vector approaching 1.0): the whole tile is walked with true adds
+                if (atomicAdd(&p.ws.hdr->n_seq, 1) >= SEQMAX) p.ws.hdr->fallback = 1;
+                p.ws.tile_slot[t] = SLOT_SEQ;
+            }
+            sm.slot = s2;
+            p.ws.tile_k[t] = -1;
         }
-        sm.slot = s2;
-        p.ws.tile_k[t] = -1;
+        sm.ts.first_raw[threadIdx.x] = (an.ek[0] == -1);
+        if (threadIdx.x == 0) sm.ts.first_raw[BLOCK] = 1;       // the tile end closes the last segment
+        __syncthreads();
+        const int s2 = sm.slot;
+        if (s2 >= 0) {
+            Slot *sl = &p.ws.slots[s2];
+            for (int q = threadIdx.x; q <= RMAX; q += BLOCK) { sl->segk[q] = -1; sl->segt[q] = 0; sl->segd[q] = 0; }
+            if (threadIdx.x == 0) { sl->tile = t; sl->nraw = total.cnt; }
+            __syncthreads();
+            int poison = 0;
+            export_segments(an, sm.ts, sl->segk, sl->segt, sl->segd, sl->wraw, &poison);
+            if (poison) p.ws.hdr->fallback = 1;
+        }
+        __syncthreads();
     }
-    sm.ts.first_raw[threadIdx.x] = (an.ek[0] == -1);
-    if (threadIdx.x == 0) sm.ts.first_raw[BLOCK] = 1;       // the tile end closes the last segment
-    __syncthreads();
-    const int s2 = sm.slot;
-    if (s2 < 0) return;
-    Slot *sl = &p.ws.slots[s2];
-    for (int q = threadIdx.x; q <= RMAX; q += BLOCK) { sl->segk[q] = -1; sl->segt[q] = 0; sl->segd[q] = 0; }
-    if (threadIdx.x == 0) { sl->tile = t; sl->nraw = total.cnt; }
-    __syncthreads();
-    int poison = 0;
-    export_segments(an, sm.ts, sl->segk, sl->segt, sl->segd, sl->wraw, &poison);
-    if (poison) p.ws.hdr->fallback = 1;
 }
 
 // ------------------------------------------------------------------ pass D: exact chain over tiles
 __device__ __forceinline__ SM tile_el(const Ws &ws, int t)
 {
-    if (ws.tile_slot[t] != -1) return SM{0, 0, 1, K_ID};     // unclean tile: restart marker
+    if (ws.tile_slot[t] >= 0 || ws.tile_slot[t] == SLOT_SEQ) return SM{0, 0, 1, K_ID};     // unclean tile: restart marker
     return SM{ws.tile_d[t], ws.tile_t[t], 0, ws.tile_k[t]};
 }
 
@@ -638,12 +672,24 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain(Params p, double carry)
     }
     __syncthreads();
     const SM woff = wtot[wid];
-    for (int t = a + lane; t < b; t += 32) {
-        const SM loc = SM{ws.run_d[t], ws.run_t[t], ws.run_cnt[t], ws.run_k[t]};
-        const SM ex = combine(woff, loc);
-        if (ex.k == K_POISON) bad = 1;
-        ws.run_d[t] = ex.d; ws.run_t[t] = ex.t; ws.run_cnt[t] = ex.cnt; ws.run_k[t] = ex.k;
-        if (ws.tile_slot[t] != -1 && ex.cnt < UMAX + SEQMAX) ws.ord2tile[ex.cnt] = t;
+    for (int t0 = a + lane; t0 < b; t0 += 32 * PF) {
+        SM loc[PF];
+        int slot[PF];
+#pragma unroll
+        for (int r = 0; r < PF; r++) {
+            const int t = t0 + r * 32;
+            if (t < b) { loc[r] = SM{ws.run_d[t], ws.run_t[t], ws.run_cnt[t], ws.run_k[t]}; slot[r] = ws.tile_slot[t]; }
+        }
+#pragma unroll
+        for (int r = 0; r < PF; r++) {
+            const int t = t0 + r * 32;
+            if (t < b) {
+                const SM ex = combine(woff, loc[r]);
+                if (ex.k == K_POISON) bad = 1;
+                ws.run_d[t] = ex.d; ws.run_t[t] = ex.t; ws.run_cnt[t] = ex.cnt; ws.run_k[t] = ex.k;
+                if ((slot[r] >= 0 || slot[r] == SLOT_SEQ) && ex.cnt < UMAX + SEQMAX) ws.ord2tile[ex.cnt] = t;
+            }
+        }
     }
     __threadfence_block();
     __syncthreads();
@@ -704,17 +750,38 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain(Params p, double carry)
     __threadfence_block();
     __syncthreads();
     // ---- parallel part: exact state before every tile, with verification of the clean tiles ---
-    for (int t = a + lane; t < b; t += 32) {
-        i64 S = ws.S_run[ws.run_cnt[t]];
-        const int rk = ws.run_k[t];
-        if (rk >= 0) S = apply_bits(S, ws.run_d[t], ws.run_t[t], rk, &bad);
-        ws.S_in[t] = S;
-        if (ws.tile_slot[t] < 0) {
-            const int tk = ws.tile_k[t];
-            const i64 E = tk >= 0 ? apply_bits(S, ws.tile_d[t], ws.tile_t[t], tk, &bad) : S;
-            if (t == T - 1) ws.S_in[T] = E;
-        } else if (t == T - 1) {
-            ws.S_in[T] = ws.S_run[ws.run_cnt[t] + 1];
+    {
+        const int U = min(ws.hdr->n_unclean, UMAX) + min(ws.hdr->n_seq, SEQMAX);
+        i64 *s_run = reinterpret_cast<i64 *>(s_w);            // the staging buffer is free now
+        const int cap = TILE;                                 // entries that fit (U + 1 <= 2305 may exceed it)
+        for (int q = threadIdx.x; q <= U && q < cap; q += CHAIN_THREADS) s_run[q] = ws.S_run[q];
+        __syncthreads();
+        for (int t0 = a + lane; t0 < b; t0 += 32 * PF) {
+            int rc[PF], rk[PF], rt[PF], tk[PF], tt[PF], slot[PF];
+            i64 rd[PF], td[PF];
+#pragma unroll
+            for (int r = 0; r < PF; r++) {
+                const int t = t0 + r * 32;
+                if (t < b) {
+                    rc[r] = ws.run_cnt[t]; rk[r] = ws.run_k[t]; rt[r] = ws.run_t[t]; rd[r] = ws.run_d[t];
+                    slot[r] = ws.tile_slot[t]; tk[r] = ws.tile_k[t]; tt[r] = ws.tile_t[t]; td[r] = ws.tile_d[t];
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < PF; r++) {
+                const int t = t0 + r * 32;
+                if (t < b) {
+                    i64 S = rc[r] < cap ? s_run[rc[r]] : ws.S_run[rc[r]];
+                    if (rk[r] >= 0) S = apply_bits(S, rd[r], rt[r], rk[r], &bad);
+                    ws.S_in[t] = S;
+                    if (slot[r] == -1 || slot[r] == SLOT_FAST) {
+                        const i64 E = tk[r] >= 0 ? apply_bits(S, td[r], tt[r], tk[r], &bad) : S;
+                        if (t == T - 1) ws.S_in[T] = E;
+                    } else if (t == T - 1) {
+                        ws.S_in[T] = ws.S_run[rc[r] + 1];
+                    }
+                }
+            }
         }
     }
     if (bad) s_bad = 1;
@@ -764,8 +831,8 @@ __device__ __forceinline__ i64 count_below_str(double c, const double *U, i64 N,
 // ------------------------------------------------------------------ pass E: emit indexes
 struct EmitShared {
     TileShared ts;
-    int hi[TILE];                 // output end (exclusive) of every element, relative to tile_lo
-    union { int ebuf[EXPAND]; double2 buf[TILE / 2]; };
+    int hi[TILE + TILE / 32];     // output end (exclusive) of every element, relative to tile_lo; index via pad32()
+    union { int ebuf[EXPAND + EXPAND / 32]; double2 buf[TILE / 2]; };   // ebuf index via pad32()
     i64 segstate[RMAX + 1];
     int segk[RMAX + 1];
     int segt[RMAX + 1];
@@ -776,39 +843,48 @@ struct EmitShared {
 };
 
 template <bool STRAT>
-__global__ void __launch_bounds__(BLOCK) k_emit(Params p)
+__global__ void __launch_bounds__(BLOCK, 2) k_emit(Params p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EmitShared &sm = *reinterpret_cast<EmitShared *>(smem_raw);
     const Ws &ws = p.ws;
     if (ws.hdr->fallback) return;
-    const int t = blockIdx.x;
     const int tid = threadIdx.x;
     const double Nd = (double)p.n;
+    double2 g[IPT / 2];
+    if ((int)blockIdx.x < ws.T) fetch_tile(p, blockIdx.x, g);
+    for (int t = blockIdx.x; t < ws.T; t += gridDim.x) {
     TileAn an;
-    load_blocked(p, t, an.w, sm.buf);
-    double s = 0.0;
-#pragma unroll
-    for (int k = 0; k < IPT; k++) s += an.w[k];
-    double tot;
-    const double tp = p.ws.tile_prefix[t];
-    const double before = tp + block_excl_scan_d(s, &tot, sm.ts.shd);
+    to_blocked(g, an.w, sm.buf);
+    if (t + (int)gridDim.x < ws.T) fetch_tile(p, t + gridDim.x, g);          // next tile's loads fly during this tile
     const i64 S_in = ws.S_in[t];
     int bad = 0;
     i64 cbits[IPT];                     // exact c_j (bit patterns) of the thread's elements
-    const bool seq_tile = ws.tile_slot[t] == SLOT_SEQ;
-    bool fast = false;
-    if (!seq_tile) {    // the same decision pass C took (same inputs, same code)
-        const int e0 = __double2hiint(tp) >> 20;
-        bool nz;
-        const bool ok = classify_fast(p, an.w, before, e0, cbits, &nz);
-        fast = __syncthreads_and(ok);
-        if (fast) {
-            i64 total_d;
-            const i64 ex = block_excl_scan_i64(cbits[IPT - 1], &total_d, sm.ts.shi);
+    const int kind = ws.tile_slot[t];
+    const bool seq_tile = kind == SLOT_SEQ;
+    const bool fast = kind == SLOT_FAST;
+    double before = 0.0;
+    if (fast) {
+        // clean, tie-free tile in binade e0 (pass C checked it): c_j = S_in + prefix sum of rne(w_j / ulp)
+        const int tk = ws.tile_k[t];
+        const i64 base = (i64)(tk >= 0 ? tk : 0) << 52;
+        const double B0 = __longlong_as_double(base);
+        i64 acc = 0;
 #pragma unroll
-            for (int k = 0; k < IPT; k++) cbits[k] += S_in + ex;
+        for (int k = 0; k < IPT; k++) {
+            acc += __double_as_longlong(__dadd_rn(B0, an.w[k])) - base;
+            cbits[k] = acc;
         }
+        i64 total_d;
+        const i64 ex = block_excl_scan_i64(acc, &total_d, sm.ts.shi);
+#pragma unroll
+        for (int k = 0; k < IPT; k++) cbits[k] += S_in + ex;
+    } else if (!seq_tile) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < IPT; k++) s += an.w[k];
+        double tot;
+        before = p.ws.tile_prefix[t] + block_excl_scan_d(s, &tot, sm.ts.shd);
     }
     SM total = sm_identity();
     if (!fast && !seq_tile) {
@@ -876,20 +952,20 @@ __global__ void __launch_bounds__(BLOCK) k_emit(Params p)
             const i64 h = STRAT ? count_below_str(c, p.U, p.n, Nd) : count_below_sys(c, p.u, p.n, Nd, p.tau);
             rel = (int)(h - tile_lo);
         }
-        sm.hi[tid * IPT + k] = rel;
+        sm.hi[pad32(tid * IPT + k)] = rel;
     }
     if (bad) ws.hdr->chain_bad = 2;      // cannot happen after pass D verified the tile; recorded for tests
     __syncthreads();
     {
         const i64 last_real = p.n - 1 - (i64)t * TILE;      // padding inherits the end of the last real element
         if (last_real < TILE - 1) {
-            const int hv = sm.hi[last_real];
+            const int hv = sm.hi[pad32((int)last_real)];
             __syncthreads();
-            for (int q = tid; q < TILE; q += BLOCK) if (q > last_real) sm.hi[q] = hv;
+            for (int q = tid; q < TILE; q += BLOCK) if (q > last_real) sm.hi[pad32(q)] = hv;
             __syncthreads();
         }
     }
-    const int tile_cnt = sm.hi[TILE - 1];                   // outputs owned by this tile
+    const int tile_cnt = sm.hi[pad32(TILE - 1)];            // outputs owned by this tile
     if (t == ws.T - 1 && tid == 0) {
         if (p.cumsum_last) *p.cumsum_last = __longlong_as_double(ws.S_in[ws.T]);
         const i64 O1 = tile_lo + tile_cnt;
@@ -905,10 +981,10 @@ __global__ void __launch_bounds__(BLOCK) k_emit(Params p)
         int lo_s = 0, hi_s = TILE - 1;                      // owner of output cs: first element with hi > cs
         while (lo_s < hi_s) {
             const int mid = (lo_s + hi_s) >> 1;
-            if (sm.hi[mid] > cs) hi_s = mid; else lo_s = mid + 1;
+            if (sm.hi[pad32(mid)] > cs) hi_s = mid; else lo_s = mid + 1;
         }
         const int owner = lo_s;
-        const int owner_end = sm.hi[owner];
+        const int owner_end = sm.hi[pad32(owner)];
         if (owner_end - cs >= BIGRUN) {
             if (tid == 0) {
                 const int r = atomicAdd(&ws.hdr->n_runs, 1);
@@ -919,14 +995,14 @@ __global__ void __launch_bounds__(BLOCK) k_emit(Params p)
             continue;
         }
         const int ce = min(tile_cnt, cs + EXPAND);
-        for (int q = tid; q < EXPAND; q += BLOCK) sm.ebuf[q] = 0;
+        for (int q = tid; q < EXPAND + EXPAND / 32; q += BLOCK) sm.ebuf[q] = 0;
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < IPT; k++) {
             const int e = tid * IPT + k;
-            const int h = sm.hi[e];
-            const int l = (e == 0) ? 0 : sm.hi[e - 1];
-            if (h > l && h > cs && l < ce) sm.ebuf[(l > cs ? l : cs) - cs] = e + 1;
+            const int h = sm.hi[pad32(e)];
+            const int l = (e == 0) ? 0 : sm.hi[pad32(e - 1)];
+            if (h > l && h > cs && l < ce) sm.ebuf[pad32((l > cs ? l : cs) - cs)] = e + 1;
         }
         __syncthreads();
         {   // inclusive max-scan over ebuf: 16 consecutive entries per thread
@@ -934,7 +1010,7 @@ __global__ void __launch_bounds__(BLOCK) k_emit(Params p)
             int v[PER];
             int m = 0;
 #pragma unroll
-            for (int q = 0; q < PER; q++) { const int x = sm.ebuf[tid * PER + q]; m = x > m ? x : m; v[q] = m; }
+            for (int q = 0; q < PER; q++) { const int x = sm.ebuf[pad32(tid * PER + q)]; m = x > m ? x : m; v[q] = m; }
             const int lane = tid & 31, wid = tid >> 5;
             int inc = m;
 #pragma unroll
@@ -947,14 +1023,16 @@ __global__ void __launch_bounds__(BLOCK) k_emit(Params p)
             if (lane == 0) prev = 0;
             basem = max(basem, prev);
 #pragma unroll
-            for (int q = 0; q < PER; q++) sm.ebuf[tid * PER + q] = max(v[q], basem);
+            for (int q = 0; q < PER; q++) sm.ebuf[pad32(tid * PER + q)] = max(v[q], basem);
         }
         __syncthreads();
         const int base_j = (int)((i64)t * TILE) - 1;
-        for (int q = tid; q < ce - cs; q += BLOCK) p.idx[tile_lo + cs + q] = base_j + sm.ebuf[q];
+        for (int q = tid; q < ce - cs; q += BLOCK) p.idx[tile_lo + cs + q] = base_j + sm.ebuf[pad32(q)];
         __syncthreads();
         cs = ce;
     }
+    __syncthreads();
+    }   // tile loop
 }
 
 // ------------------------------------------------------------------ pass F: long runs
@@ -1050,10 +1128,11 @@ int run(i64 n, const double *w, double u, const double *U, int *idx, void *works
     if (check_cuda(cudaFuncSetAttribute(k_emit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, emit_smem), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
     k_tile_sums<<<T, BLOCK, 0, s>>>(p);
     k_scan_tiles<<<1, CHAIN_THREADS, 0, s>>>(p);
-    k_tile_maps<<<T, BLOCK, 0, s>>>(p);
+    const int pgrid = T < sm_count() * 2 ? T : sm_count() * 2;
+    k_tile_maps<<<pgrid, BLOCK, 0, s>>>(p);
     k_chain<<<1, CHAIN_THREADS, 0, s>>>(p, 0.0);
-    if (U) k_emit<true><<<T, BLOCK, emit_smem, s>>>(p);
-    else k_emit<false><<<T, BLOCK, emit_smem, s>>>(p);
+    if (U) k_emit<true><<<pgrid, BLOCK, emit_smem, s>>>(p);
+    else k_emit<false><<<pgrid, BLOCK, emit_smem, s>>>(p);
     k_fill_runs<<<sm_count() * 4, 256, 0, s>>>(p);
     k_sequential<<<1, 32, 0, s>>>(p, 0.0);
     return check_cuda(cudaGetLastError(), "resample launch");
