@@ -22,7 +22,8 @@ EXPORTED_SYMBOLS = [
     "bke_abi_version", "bke_last_error", "bke_device_count",
     "bke_kf_step", "bke_kf_batch_filter", "bke_ukf_step",
     "bke_resample_workspace_bytes", "bke_systematic_resample", "bke_stratified_resample",
-    "bke_weights_sum", "bke_weights_scale",
+    "bke_weights_sum", "bke_weights_scale", "bke_resample_shard",
+    "bke_merwe_sigma_points", "bke_unscented_transform",
 ]
 
 
@@ -81,6 +82,19 @@ class UkfArgs(ctypes.Structure):
     ]
 
 
+class ResampleShardArgs(ctypes.Structure):
+    _fields_ = [
+        ("n_local", c_int64), ("n_global", c_int64), ("j_offset", c_int64), ("capacity", c_int64),
+        ("weights", c_void_p), ("uniforms", c_void_p),
+        ("u", c_double),
+        ("carry_approx", c_void_p), ("carry_exact", c_void_p),
+        ("indexes", c_void_p), ("out_range", c_void_p), ("carry_out", c_void_p),
+        ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+        ("info", c_void_p),
+        ("is_last", c_int32), ("phase", c_int32),
+    ]
+
+
 class BkeError(RuntimeError):
     pass
 
@@ -127,6 +141,14 @@ def load():
     lib.bke_weights_sum.restype = ctypes.c_int
     lib.bke_weights_scale.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.bke_weights_scale.restype = ctypes.c_int
+    lib.bke_resample_shard.argtypes = [ctypes.POINTER(ResampleShardArgs), c_void_p]
+    lib.bke_resample_shard.restype = ctypes.c_int
+    lib.bke_merwe_sigma_points.argtypes = [c_int64, c_int32, c_int32, c_double, c_double, c_double,
+                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.bke_merwe_sigma_points.restype = ctypes.c_int
+    lib.bke_unscented_transform.argtypes = [c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                            c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
+    lib.bke_unscented_transform.restype = ctypes.c_int
     if lib.bke_abi_version() != 1:
         raise BkeError("libbke.so ABI version mismatch")
     _lib = lib

@@ -220,7 +220,10 @@ struct Header {
     int overflow;       // positions >= cumsum[-1]
     int chain_bad;      // a verified assumption failed
     int n_seq;          // tiles walked element by element (more than RMAX raw elements)
-    int pad[2];
+    int cap_overflow;   // outputs that did not fit the caller's index buffer (sharded calls)
+    int n_slow;         // tiles on the slow list
+    i64 out_begin;      // first global output position owned by this call
+    i64 out_end;        // one past the last
 };
 
 struct Slot {           // one tile with raw elements
@@ -251,6 +254,7 @@ struct Ws {
     i64 *S_run;             // [UMAX+SEQMAX+1]
     int *ord2tile;          // [UMAX+SEQMAX]
     Run *runs;              // [max_runs]
+    int *slow_list;         // [T] tiles that did not qualify for the fast path (order irrelevant)
     int max_runs;
     int T;
 };
@@ -278,6 +282,7 @@ size_t carve(int64_t n, unsigned char *base, Ws *w)
     p = take(sizeof(Slot) * UMAX);            if (w) w->slots = (Slot *)p;
     p = take(sizeof(i64) * (UMAX + SEQMAX + 1)); if (w) w->S_run = (i64 *)p;
     p = take(sizeof(int) * (UMAX + SEQMAX));  if (w) w->ord2tile = (int *)p;
+    p = take(sizeof(int) * T);                if (w) w->slow_list = (int *)p;
     int64_t max_runs = n / BIGRUN + 8;
     p = take(sizeof(Run) * max_runs);         if (w) { w->runs = (Run *)p; w->max_runs = (int)max_runs; w->T = (int)T; }
     return off;
@@ -285,7 +290,14 @@ size_t carve(int64_t n, unsigned char *base, Ws *w)
 
 struct Params {
     const double *w;
-    i64 n;                 // particles in this call
+    i64 n;                 // particles in this call (this shard)
+    i64 ng;                // particles of the whole set: positions are (u + i) / ng
+    i64 j0;                // global index of this call's first particle
+    i64 cap;               // capacity of idx
+    int is_last;           // this call holds the end of the particle set
+    const double *carry_approx;   // device: approximate sum of the earlier shards (NULL = 0)
+    const double *carry_exact;    // device: exact running sum before this shard (NULL = 0)
+    i64 *out_range;        // device int64[2] (NULL ok): global output positions [begin, end) owned by this call
     double u;              // systematic offset
     const double *U;       // stratified uniforms (NULL = systematic)
     int *idx;
@@ -361,8 +373,12 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_scan_tiles(Params p)
         if (lane == 31) p.ws.tile_prefix[T] = inc;
     }
     __syncthreads();
-    const double off = wtot[wid];
+    __threadfence_block();
+    const double c0 = p.carry_approx ? *p.carry_approx : 0.0;
+    const double off = wtot[wid] + c0;
+#pragma unroll 8
     for (int t = a + lane; t < b; t += 32) p.ws.tile_prefix[t] += off;
+    if (threadIdx.x == 0 && c0 != 0.0) p.ws.tile_prefix[T] += c0;
 }
 
 // ------------------------------------------------------------------ shared tile analysis (C and E)
@@ -522,51 +538,66 @@ struct MapsShared {
     int slot;
 };
 
+// Fast kernel: every tile whose adds are all clean and tie-free in ONE binade (decided from the two
+// approximate tile prefixes and the elements themselves) gets its map as a plain int64 sum, straight
+// from the striped registers.  Everything else is queued for the general kernel.
+__global__ void __launch_bounds__(BLOCK, 4) k_tile_maps_fast(Params p)
+{
+    __shared__ i64 shi[BLOCK / 32 + 1];
+    if (p.ws.hdr->fallback) return;
+    const int T = p.ws.T;
+    double2 g[IPT / 2], gn[IPT / 2];
+    if ((int)blockIdx.x < T) fetch_tile(p, blockIdx.x, gn);
+    for (int t = blockIdx.x; t < T; t += gridDim.x) {
+#pragma unroll
+        for (int i = 0; i < IPT / 2; i++) g[i] = gn[i];
+        if (t + (int)gridDim.x < T) fetch_tile(p, t + gridDim.x, gn);     // next tile's loads fly during this tile
+        const double tp = p.ws.tile_prefix[t], tp_next = p.ws.tile_prefix[t + 1];
+        int e0;
+        const bool tile_clean = clean_add(tp, tp_next, p.eb, &e0);     // the whole tile stays deep inside binade e0
+        const i64 base = (i64)e0 << 52;
+        const double B0 = __longlong_as_double(base), B1 = __longlong_as_double(base + 1);
+        i64 acc = 0;
+        bool ok = tile_clean, nz = false;
+#pragma unroll
+        for (int i = 0; i < IPT / 2; i++) {
+            const double w2[2] = {g[i].x, g[i].y};
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const i64 d0 = __double_as_longlong(__dadd_rn(B0, w2[h])) - base;
+                const i64 d1 = __double_as_longlong(__dadd_rn(B1, w2[h])) - (base + 1);
+                ok = ok && (d0 == d1);
+                nz = nz || (w2[h] != 0.0);
+                acc += d0;
+            }
+        }
+        if (__syncthreads_and(ok)) {
+            i64 total;
+            block_excl_scan_i64(acc, &total, shi);
+            const int any_nz = __syncthreads_or(nz);
+            if (threadIdx.x == 0) {
+                p.ws.tile_k[t] = any_nz ? e0 : K_ID; p.ws.tile_d[t] = total; p.ws.tile_t[t] = 0;
+                p.ws.tile_slot[t] = SLOT_FAST;
+            }
+        } else if (threadIdx.x == 0) {
+            p.ws.slow_list[atomicAdd(&p.ws.hdr->n_slow, 1)] = t;
+        }
+    }
+}
+
+// General kernel over the slow list: ties, raw elements, sequential tiles.
 __global__ void __launch_bounds__(BLOCK, 2) k_tile_maps(Params p)
 {
     __shared__ MapsShared sm;
     if (p.ws.hdr->fallback) return;
-    const int T = p.ws.T;
-    double2 g[IPT / 2];
-    if ((int)blockIdx.x < T) fetch_tile(p, blockIdx.x, g);
-    for (int t = blockIdx.x; t < T; t += gridDim.x) {
-        const double tp = p.ws.tile_prefix[t], tp_next = p.ws.tile_prefix[t + 1];
-        int e0;
-        const bool tile_clean = clean_add(tp, tp_next, p.eb, &e0);     // the whole tile stays deep inside binade e0
-        if (tile_clean) {
-            // fast path: every add is clean; if none is a tie the tile's map is a plain int64 sum.
-            // A sum needs no particular element order: work on the striped registers directly.
-            const i64 base = (i64)e0 << 52;
-            const double B0 = __longlong_as_double(base), B1 = __longlong_as_double(base + 1);
-            i64 acc = 0;
-            bool ok = true, nz = false;
-#pragma unroll
-            for (int i = 0; i < IPT / 2; i++) {
-                const double w2[2] = {g[i].x, g[i].y};
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const i64 d0 = __double_as_longlong(__dadd_rn(B0, w2[h])) - base;
-                    const i64 d1 = __double_as_longlong(__dadd_rn(B1, w2[h])) - (base + 1);
-                    ok = ok && (d0 == d1);
-                    nz = nz || (w2[h] != 0.0);
-                    acc += d0;
-                }
-            }
-            if (__syncthreads_and(ok)) {
-                i64 total;
-                block_excl_scan_i64(acc, &total, sm.ts.shi);
-                const int any_nz = __syncthreads_or(nz);
-                if (threadIdx.x == 0) {
-                    p.ws.tile_k[t] = any_nz ? e0 : K_ID; p.ws.tile_d[t] = total; p.ws.tile_t[t] = 0;
-                    p.ws.tile_slot[t] = SLOT_FAST;
-                }
-                if (t + (int)gridDim.x < T) fetch_tile(p, t + gridDim.x, g);
-                continue;
-            }
-        }
+    const int n_slow = p.ws.hdr->n_slow;
+    for (int li = blockIdx.x; li < n_slow; li += gridDim.x) {
+        const int t = p.ws.slow_list[li];
+        const double tp = p.ws.tile_prefix[t];
+        double2 g[IPT / 2];
+        fetch_tile(p, t, g);
         TileAn an;
         to_blocked(g, an.w, sm.buf);
-        if (t + (int)gridDim.x < T) fetch_tile(p, t + gridDim.x, g);      // next tile's loads fly during this tile
         double s = 0.0;
 #pragma unroll
         for (int k = 0; k < IPT; k++) s += an.w[k];
@@ -620,14 +651,56 @@ __global__ void __launch_bounds__(BLOCK, 2) k_tile_maps(Params p)
     }
 }
 
+// ------------------------------------------------------------------ positions
+__device__ __forceinline__ double pos_sys(i64 i, double u, double Nd) { return __ddiv_rn(__dadd_rn(u, (double)i), Nd); }
+
+// number of positions strictly below c (systematic)
+__device__ __forceinline__ i64 count_below_sys(double c, double u, i64 N, double Nd, double tau)
+{
+    const double v = __dadd_rn(__dmul_rn(c, Nd), -u);
+    if (fabs(v) < 4.0e15) {
+        const i64 fl = __double2ll_rd(v);
+        const double fr = v - (double)fl;
+        if (fr > tau && fr < 1.0 - tau) {
+            const i64 g = fl + 1;
+            return g < 0 ? 0 : (g > N ? N : g);
+        }
+    }
+    double g0d = floor(v) + 1.0;
+    if (!(g0d > 0.0)) g0d = 0.0;
+    if (g0d > Nd) g0d = Nd;
+    i64 g = (i64)g0d;
+    while (g < N && pos_sys(g, u, Nd) < c) g++;
+    while (g > 0 && !(pos_sys(g - 1, u, Nd) < c)) g--;
+    return g;
+}
+
+__device__ __forceinline__ double pos_str(i64 i, const double *U, double Nd) { return __ddiv_rn(__dadd_rn(U[i], (double)i), Nd); }
+
+// number of positions strictly below c (stratified; positions are non-decreasing in i)
+__device__ __forceinline__ i64 count_below_str(double c, const double *U, i64 N, double Nd)
+{
+    double v = floor(__dmul_rn(c, Nd));
+    if (!(v > 1.0)) v = 1.0;
+    if (v > Nd) v = Nd;
+    i64 g = (i64)v - 1;                      // candidates start two below the real-valued crossing
+    if (g < 0) g = 0;
+    while (g < N && pos_str(g, U, Nd) < c) g++;
+    while (g > 0 && !(pos_str(g - 1, U, Nd) < c)) g--;
+    return g;
+}
+
 // ------------------------------------------------------------------ pass D: exact chain over tiles
 __device__ __forceinline__ SM tile_el(const Ws &ws, int t)
 {
-    if (ws.tile_slot[t] >= 0 || ws.tile_slot[t] == SLOT_SEQ) return SM{0, 0, 1, K_ID};     // unclean tile: restart marker
-    return SM{ws.tile_d[t], ws.tile_t[t], 0, ws.tile_k[t]};
+    const int slot = ws.tile_slot[t];                 // all four loads are issued together
+    const SM m = SM{ws.tile_d[t], ws.tile_t[t], 0, ws.tile_k[t]};
+    if (slot >= 0 || slot == SLOT_SEQ) return SM{0, 0, 1, K_ID};     // unclean tile: restart marker
+    return m;
 }
 
-__global__ void __launch_bounds__(CHAIN_THREADS) k_chain(Params p, double carry)
+template <bool STRAT>
+__global__ void __launch_bounds__(CHAIN_THREADS) k_chain(Params p)
 {
     __shared__ SM wtot[CHAIN_THREADS / 32];
     __shared__ Slot s_slots[CHAIN_BATCH];
@@ -698,7 +771,12 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain(Params p, double carry)
     // would cost ~1 us per hop), CHAIN_BATCH tiles at a time.
     {
         const int U = min(ws.hdr->n_unclean, UMAX) + min(ws.hdr->n_seq, SEQMAX);
-        if (threadIdx.x == 0) { s_S = __double_as_longlong(carry); ws.S_run[0] = s_S; }
+        if (threadIdx.x == 0) {
+            const double carry = p.carry_exact ? *p.carry_exact : 0.0;
+            s_S = __double_as_longlong(carry); ws.S_run[0] = s_S;
+            const double Ngd = (double)p.ng;
+            ws.hdr->out_begin = STRAT ? count_below_str(carry, p.U, p.ng, Ngd) : count_below_sys(carry, p.u, p.ng, Ngd, p.tau);
+        }
         constexpr int SLOT_INTS = (int)(sizeof(Slot) / sizeof(int));
         int i0 = 0;
         while (i0 < U) {
@@ -789,45 +867,6 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain(Params p, double carry)
     if (threadIdx.x == 0 && s_bad) { ws.hdr->fallback = 1; ws.hdr->chain_bad = 1; }
 }
 
-// ------------------------------------------------------------------ positions
-__device__ __forceinline__ double pos_sys(i64 i, double u, double Nd) { return __ddiv_rn(__dadd_rn(u, (double)i), Nd); }
-
-// number of positions strictly below c (systematic)
-__device__ __forceinline__ i64 count_below_sys(double c, double u, i64 N, double Nd, double tau)
-{
-    const double v = __dadd_rn(__dmul_rn(c, Nd), -u);
-    if (fabs(v) < 4.0e15) {
-        const i64 fl = __double2ll_rd(v);
-        const double fr = v - (double)fl;
-        if (fr > tau && fr < 1.0 - tau) {
-            const i64 g = fl + 1;
-            return g < 0 ? 0 : (g > N ? N : g);
-        }
-    }
-    double g0d = floor(v) + 1.0;
-    if (!(g0d > 0.0)) g0d = 0.0;
-    if (g0d > Nd) g0d = Nd;
-    i64 g = (i64)g0d;
-    while (g < N && pos_sys(g, u, Nd) < c) g++;
-    while (g > 0 && !(pos_sys(g - 1, u, Nd) < c)) g--;
-    return g;
-}
-
-__device__ __forceinline__ double pos_str(i64 i, const double *U, double Nd) { return __ddiv_rn(__dadd_rn(U[i], (double)i), Nd); }
-
-// number of positions strictly below c (stratified; positions are non-decreasing in i)
-__device__ __forceinline__ i64 count_below_str(double c, const double *U, i64 N, double Nd)
-{
-    double v = floor(__dmul_rn(c, Nd));
-    if (!(v > 1.0)) v = 1.0;
-    if (v > Nd) v = Nd;
-    i64 g = (i64)v - 1;                      // candidates start two below the real-valued crossing
-    if (g < 0) g = 0;
-    while (g < N && pos_str(g, U, Nd) < c) g++;
-    while (g > 0 && !(pos_str(g - 1, U, Nd) < c)) g--;
-    return g;
-}
-
 // ------------------------------------------------------------------ pass E: emit indexes
 struct EmitShared {
     TileShared ts;
@@ -839,122 +878,39 @@ struct EmitShared {
     i64 segd[RMAX + 1];
     double wraw[RMAX];
     int warp_max[BLOCK / 32];
-    i64 tile_lo;
 };
 
 template <bool STRAT>
-__global__ void __launch_bounds__(BLOCK, 2) k_emit(Params p)
+__device__ __forceinline__ i64 count_below(const Params &p, double c)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    EmitShared &sm = *reinterpret_cast<EmitShared *>(smem_raw);
+    const double Ngd = (double)p.ng;
+    return STRAT ? count_below_str(c, p.U, p.ng, Ngd) : count_below_sys(c, p.u, p.ng, Ngd, p.tau);
+}
+
+// store one index (global output position o) into the caller's buffer
+__device__ __forceinline__ void put_index(const Params &p, i64 o, int value)
+{
+    const i64 rel = o - p.ws.hdr->out_begin;
+    if (rel >= 0 && rel < p.cap) p.idx[rel] = value;
+    else p.ws.hdr->cap_overflow = 1;
+}
+
+// Common tail of the emit kernels: cbits[k] = exact c_j (bit pattern) of the thread's 8 elements.
+// Computes every element's output range end, then expands the tile's outputs through shared memory
+// (coalesced stores); particles copied >= BIGRUN times are queued for the fill kernel.
+template <bool STRAT>
+__device__ __forceinline__ void emit_tile(const Params &p, EmitShared &sm, int t, i64 S_in, const i64 (&cbits)[IPT])
+{
     const Ws &ws = p.ws;
-    if (ws.hdr->fallback) return;
     const int tid = threadIdx.x;
-    const double Nd = (double)p.n;
-    double2 g[IPT / 2];
-    if ((int)blockIdx.x < ws.T) fetch_tile(p, blockIdx.x, g);
-    for (int t = blockIdx.x; t < ws.T; t += gridDim.x) {
-    TileAn an;
-    to_blocked(g, an.w, sm.buf);
-    if (t + (int)gridDim.x < ws.T) fetch_tile(p, t + gridDim.x, g);          // next tile's loads fly during this tile
-    const i64 S_in = ws.S_in[t];
-    int bad = 0;
-    i64 cbits[IPT];                     // exact c_j (bit patterns) of the thread's elements
-    const int kind = ws.tile_slot[t];
-    const bool seq_tile = kind == SLOT_SEQ;
-    const bool fast = kind == SLOT_FAST;
-    double before = 0.0;
-    if (fast) {
-        // clean, tie-free tile in binade e0 (pass C checked it): c_j = S_in + prefix sum of rne(w_j / ulp)
-        const int tk = ws.tile_k[t];
-        const i64 base = (i64)(tk >= 0 ? tk : 0) << 52;
-        const double B0 = __longlong_as_double(base);
-        i64 acc = 0;
-#pragma unroll
-        for (int k = 0; k < IPT; k++) {
-            acc += __double_as_longlong(__dadd_rn(B0, an.w[k])) - base;
-            cbits[k] = acc;
-        }
-        i64 total_d;
-        const i64 ex = block_excl_scan_i64(acc, &total_d, sm.ts.shi);
-#pragma unroll
-        for (int k = 0; k < IPT; k++) cbits[k] += S_in + ex;
-    } else if (!seq_tile) {
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < IPT; k++) s += an.w[k];
-        double tot;
-        before = p.ws.tile_prefix[t] + block_excl_scan_d(s, &tot, sm.ts.shd);
-    }
-    SM total = sm_identity();
-    if (!fast && !seq_tile) {
-        const SM run = classify(p, an, before);
-        const SM excl = block_excl_scan_sm(run, &total, sm.ts.shm);
-#pragma unroll
-        for (int k = 0; k < IPT; k++) an.inc[k] = combine(excl, an.inc[k]);
-    }
-    i64 seq_start = 0;
-    if (fast) {
-    } else if (seq_tile) {
-        // every element by a true add: thread 0 walks the tile once to get each thread's start state
-        double *wd = reinterpret_cast<double *>(sm.ebuf);
-        i64 *tstart = reinterpret_cast<i64 *>(sm.hi);
-#pragma unroll
-        for (int k = 0; k < IPT; k++) wd[tid * IPT + k] = an.w[k];
-        __syncthreads();
-        if (tid == 0) {
-            double acc = __longlong_as_double(S_in);
-            for (int th = 0; th < BLOCK; th++) {
-                tstart[th] = __double_as_longlong(acc);
-                for (int k = 0; k < IPT; k++) acc = __dadd_rn(acc, wd[th * IPT + k]);
-            }
-        }
-        __syncthreads();
-        seq_start = tstart[tid];
-        __syncthreads();
-    } else if (total.cnt > 0) {
-        sm.ts.first_raw[tid] = (an.ek[0] == -1);
-        if (tid == 0) sm.ts.first_raw[BLOCK] = 1;
-        for (int q = tid; q <= RMAX; q += BLOCK) { sm.segk[q] = -1; sm.segt[q] = 0; sm.segd[q] = 0; }
-        __syncthreads();
-        int poison = 0;
-        export_segments(an, sm.ts, sm.segk, sm.segt, sm.segd, sm.wraw, &poison);
-        __syncthreads();
-        if (tid == 0) walk_slot(sm.segk, sm.segt, sm.segd, sm.wraw, total.cnt, S_in, &bad, sm.segstate);
-    } else if (tid == 0) {
-        sm.segstate[0] = S_in;
-    }
-    if (tid == 0) {
-        const double c0 = __longlong_as_double(S_in);
-        sm.tile_lo = STRAT ? count_below_str(c0, p.U, p.n, Nd) : count_below_sys(c0, p.u, p.n, Nd, p.tau);
-    }
-    __syncthreads();
-    const i64 tile_lo = sm.tile_lo;
-    // exact c_j and the output range end of every element
+    const i64 tile_lo = count_below<STRAT>(p, __longlong_as_double(S_in));       // every thread: no broadcast needed
     const i64 jbase = (i64)t * TILE + (i64)tid * IPT;
-    double seq_acc = __longlong_as_double(seq_start);
 #pragma unroll
     for (int k = 0; k < IPT; k++) {
-        i64 cb;
-        if (fast) {
-            cb = cbits[k];
-        } else if (seq_tile) {
-            seq_acc = __dadd_rn(seq_acc, an.w[k]);
-            cb = __double_as_longlong(seq_acc);
-        } else {
-            const i64 S0 = sm.segstate[an.inc[k].cnt];
-            // a raw element: the segment it opens starts at its own result; only zeros so far: unchanged
-            cb = (an.ek[k] == -1 || an.inc[k].k < 0) ? S0 : apply_bits(S0, an.inc[k].d, an.inc[k].t, an.inc[k].k, &bad);
-        }
         int rel = -1;                         // padding elements own no output (fixed below)
-        if (jbase + k < p.n) {
-            const double c = __longlong_as_double(cb);
-            const i64 h = STRAT ? count_below_str(c, p.U, p.n, Nd) : count_below_sys(c, p.u, p.n, Nd, p.tau);
-            rel = (int)(h - tile_lo);
-        }
+        if (jbase + k < p.n) rel = (int)(count_below<STRAT>(p, __longlong_as_double(cbits[k])) - tile_lo);
         sm.hi[pad32(tid * IPT + k)] = rel;
     }
-    if (bad) ws.hdr->chain_bad = 2;      // cannot happen after pass D verified the tile; recorded for tests
     __syncthreads();
     {
         const i64 last_real = p.n - 1 - (i64)t * TILE;      // padding inherits the end of the last real element
@@ -968,14 +924,16 @@ __global__ void __launch_bounds__(BLOCK, 2) k_emit(Params p)
     const int tile_cnt = sm.hi[pad32(TILE - 1)];            // outputs owned by this tile
     if (t == ws.T - 1 && tid == 0) {
         if (p.cumsum_last) *p.cumsum_last = __longlong_as_double(ws.S_in[ws.T]);
-        const i64 O1 = tile_lo + tile_cnt;
-        if (O1 < p.n) {                                     // resampling.py:145 would raise IndexError
-            ws.hdr->overflow = (int)(p.n - O1 > 0x7fffffff ? 0x7fffffff : p.n - O1);
+        i64 O1 = tile_lo + tile_cnt;
+        if (p.is_last && O1 < p.ng) {                       // resampling.py:145 would raise IndexError
+            ws.hdr->overflow = (int)(p.ng - O1 > 0x7fffffff ? 0x7fffffff : p.ng - O1);
             const int r = atomicAdd(&ws.hdr->n_runs, 1);
-            if (r < ws.max_runs) ws.runs[r] = Run{O1, p.n, (int)(p.n - 1), 0};
+            if (r < ws.max_runs) ws.runs[r] = Run{O1, p.ng, (int)(p.ng - 1), 0};
+            O1 = p.ng;
         }
+        ws.hdr->out_end = O1;
+        if (p.out_range) { p.out_range[0] = ws.hdr->out_begin; p.out_range[1] = O1; }
     }
-    // expansion: outputs [tile_lo + cs, tile_lo + ce) per pass
     int cs = 0;
     while (cs < tile_cnt) {
         int lo_s = 0, hi_s = TILE - 1;                      // owner of output cs: first element with hi > cs
@@ -988,7 +946,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_emit(Params p)
         if (owner_end - cs >= BIGRUN) {
             if (tid == 0) {
                 const int r = atomicAdd(&ws.hdr->n_runs, 1);
-                if (r < ws.max_runs) ws.runs[r] = Run{tile_lo + cs, tile_lo + owner_end, (int)((i64)t * TILE + owner), 0};
+                if (r < ws.max_runs) ws.runs[r] = Run{tile_lo + cs, tile_lo + owner_end, (int)(p.j0 + (i64)t * TILE + owner), 0};
                 else ws.hdr->fallback = 1;
             }
             cs = owner_end;
@@ -1026,13 +984,126 @@ __global__ void __launch_bounds__(BLOCK, 2) k_emit(Params p)
             for (int q = 0; q < PER; q++) sm.ebuf[pad32(tid * PER + q)] = max(v[q], basem);
         }
         __syncthreads();
-        const int base_j = (int)((i64)t * TILE) - 1;
-        for (int q = tid; q < ce - cs; q += BLOCK) p.idx[tile_lo + cs + q] = base_j + sm.ebuf[pad32(q)];
+        const int base_j = (int)(p.j0 + (i64)t * TILE) - 1;
+        const i64 rel0 = tile_lo + cs - ws.hdr->out_begin;
+        if (rel0 >= 0 && rel0 + (ce - cs) <= p.cap) {
+            for (int q = tid; q < ce - cs; q += BLOCK) p.idx[rel0 + q] = base_j + sm.ebuf[pad32(q)];
+        } else {
+            for (int q = tid; q < ce - cs; q += BLOCK) put_index(p, tile_lo + cs + q, base_j + sm.ebuf[pad32(q)]);
+        }
         __syncthreads();
         cs = ce;
     }
     __syncthreads();
-    }   // tile loop
+}
+
+// Fast emit: the tiles pass C marked SLOT_FAST (clean, tie-free, one binade):
+// c_j = S_in + prefix sum of rne(w_j / ulp), one IEEE add per element.
+template <bool STRAT>
+__global__ void __launch_bounds__(BLOCK, 3) k_emit_fast(Params p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    EmitShared &sm = *reinterpret_cast<EmitShared *>(smem_raw);
+    const Ws &ws = p.ws;
+    if (ws.hdr->fallback) return;
+    double2 g[IPT / 2];
+    if ((int)blockIdx.x < ws.T) fetch_tile(p, blockIdx.x, g);
+    for (int t = blockIdx.x; t < ws.T; t += gridDim.x) {
+        double w[IPT];
+        to_blocked(g, w, sm.buf);
+        if (t + (int)gridDim.x < ws.T) fetch_tile(p, t + gridDim.x, g);      // next tile's loads fly during this tile
+        if (ws.tile_slot[t] != SLOT_FAST) continue;                           // the general kernel owns this tile
+        const i64 S_in = ws.S_in[t];
+        const int tk = ws.tile_k[t];
+        const i64 base = (i64)(tk >= 0 ? tk : 0) << 52;
+        const double B0 = __longlong_as_double(base);
+        i64 cbits[IPT];
+        i64 acc = 0;
+#pragma unroll
+        for (int k = 0; k < IPT; k++) {
+            acc += __double_as_longlong(__dadd_rn(B0, w[k])) - base;
+            cbits[k] = acc;
+        }
+        i64 total_d;
+        const i64 ex = block_excl_scan_i64(acc, &total_d, sm.ts.shi);
+#pragma unroll
+        for (int k = 0; k < IPT; k++) cbits[k] += S_in + ex;
+        emit_tile<STRAT>(p, sm, t, S_in, cbits);
+    }
+}
+
+// General emit over the slow list: ties, raw elements, sequential tiles.
+template <bool STRAT>
+__global__ void __launch_bounds__(BLOCK, 2) k_emit_slow(Params p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    EmitShared &sm = *reinterpret_cast<EmitShared *>(smem_raw);
+    const Ws &ws = p.ws;
+    if (ws.hdr->fallback) return;
+    const int tid = threadIdx.x;
+    const int n_slow = ws.hdr->n_slow;
+    for (int li = blockIdx.x; li < n_slow; li += gridDim.x) {
+        const int t = ws.slow_list[li];
+        double2 g[IPT / 2];
+        fetch_tile(p, t, g);
+        TileAn an;
+        to_blocked(g, an.w, sm.buf);
+        const i64 S_in = ws.S_in[t];
+        int bad = 0;
+        i64 cbits[IPT];
+        if (ws.tile_slot[t] == SLOT_SEQ) {
+            // every element by a true add: thread 0 walks the tile once to get each thread's start state
+            double *wd = reinterpret_cast<double *>(sm.ebuf);
+            i64 *tstart = reinterpret_cast<i64 *>(sm.hi);
+#pragma unroll
+            for (int k = 0; k < IPT; k++) wd[tid * IPT + k] = an.w[k];
+            __syncthreads();
+            if (tid == 0) {
+                double acc = __longlong_as_double(S_in);
+                for (int th = 0; th < BLOCK; th++) {
+                    tstart[th] = __double_as_longlong(acc);
+                    for (int k = 0; k < IPT; k++) acc = __dadd_rn(acc, wd[th * IPT + k]);
+                }
+            }
+            __syncthreads();
+            double acc = __longlong_as_double(tstart[tid]);
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < IPT; k++) { acc = __dadd_rn(acc, an.w[k]); cbits[k] = __double_as_longlong(acc); }
+        } else {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < IPT; k++) s += an.w[k];
+            double tot;
+            const double before = ws.tile_prefix[t] + block_excl_scan_d(s, &tot, sm.ts.shd);
+            const SM run = classify(p, an, before);
+            SM total;
+            const SM excl = block_excl_scan_sm(run, &total, sm.ts.shm);
+#pragma unroll
+            for (int k = 0; k < IPT; k++) an.inc[k] = combine(excl, an.inc[k]);
+            if (total.cnt > 0) {      // segment start states (exact)
+                sm.ts.first_raw[tid] = (an.ek[0] == -1);
+                if (tid == 0) sm.ts.first_raw[BLOCK] = 1;
+                for (int q = tid; q <= RMAX; q += BLOCK) { sm.segk[q] = -1; sm.segt[q] = 0; sm.segd[q] = 0; }
+                __syncthreads();
+                int poison = 0;
+                export_segments(an, sm.ts, sm.segk, sm.segt, sm.segd, sm.wraw, &poison);
+                __syncthreads();
+                if (tid == 0) walk_slot(sm.segk, sm.segt, sm.segd, sm.wraw, total.cnt, S_in, &bad, sm.segstate);
+            } else if (tid == 0) {
+                sm.segstate[0] = S_in;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < IPT; k++) {
+                const i64 S0 = sm.segstate[an.inc[k].cnt];
+                // a raw element: the segment it opens starts at its own result; only zeros so far: unchanged
+                cbits[k] = (an.ek[k] == -1 || an.inc[k].k < 0) ? S0 : apply_bits(S0, an.inc[k].d, an.inc[k].t, an.inc[k].k, &bad);
+            }
+            if (bad) ws.hdr->chain_bad = 2;      // cannot happen after pass D verified the tile; recorded for tests
+        }
+        emit_tile<STRAT>(p, sm, t, S_in, cbits);
+    }
 }
 
 // ------------------------------------------------------------------ pass F: long runs
@@ -1042,41 +1113,69 @@ __global__ void __launch_bounds__(256) k_fill_runs(Params p)
     if (ws.hdr->fallback) return;
     int nr = ws.hdr->n_runs;
     if (nr > ws.max_runs) nr = ws.max_runs;
+    const i64 ob = ws.hdr->out_begin;
     for (int r = 0; r < nr; r++) {
         const Run run = ws.runs[r];
-        for (i64 i = run.lo + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < run.hi; i += (i64)gridDim.x * blockDim.x)
-            p.idx[i] = run.j;
+        for (i64 i = run.lo + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < run.hi; i += (i64)gridDim.x * blockDim.x) {
+            const i64 rel = i - ob;
+            if (rel >= 0 && rel < p.cap) p.idx[rel] = run.j;
+            else ws.hdr->cap_overflow = 1;
+        }
     }
 }
 
 // ------------------------------------------------------------------ pass G: literal sequential fallback
-__global__ void k_sequential(Params p, double carry)
+template <bool STRAT>
+__global__ void k_sequential(Params p)
 {
     const Ws &ws = p.ws;
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (!ws.hdr->fallback) {
-        if (p.info) { p.info[0] = ws.hdr->overflow; p.info[1] = 0; p.info[2] = ws.hdr->n_unclean; p.info[3] = ws.hdr->n_runs; p.info[4] = ws.hdr->chain_bad; p.info[5] = ws.hdr->n_seq; }
-        return;
+    auto write_info = [&](int overflow, int fb) {
+        if (p.info) {
+            p.info[0] = overflow; p.info[1] = fb; p.info[2] = ws.hdr->n_unclean; p.info[3] = ws.hdr->n_runs;
+            p.info[4] = ws.hdr->chain_bad; p.info[5] = ws.hdr->n_seq; p.info[6] = ws.hdr->cap_overflow; p.info[7] = ws.hdr->n_slow;
+        }
+    };
+    if (!ws.hdr->fallback) { write_info(ws.hdr->overflow, 0); return; }
+    // resampling.py:141-149 — cumulative sum and two-pointer merge, one element at a time.
+    // A shard starts from the exact running sum of the earlier shards and owns the positions from
+    // count_below(carry) up to count_below(its last cumulative sum).
+    const double Ngd = (double)p.ng;
+    const double carry = p.carry_exact ? *p.carry_exact : 0.0;
+    i64 lo = 0, hi = p.ng;                       // first i with pos_i >= carry (positions are non-decreasing)
+    while (lo < hi) {
+        const i64 mid = (lo + hi) >> 1;
+        const double pm = STRAT ? pos_str(mid, p.U, Ngd) : pos_sys(mid, p.u, Ngd);
+        if (pm < carry) lo = mid + 1; else hi = mid;
     }
-    // resampling.py:141-149 — cumulative sum and two-pointer merge, one element at a time
-    const double Nd = (double)p.n;
-    i64 i = 0, j = 0;
+    const i64 ob = lo;
+    ws.hdr->out_begin = ob;
+    ws.hdr->cap_overflow = 0;
+    i64 i = ob, j = 0;
     double c = (carry == 0.0) ? p.w[0] : __dadd_rn(carry, p.w[0]);
     int overflow = 0;
-    while (i < p.n) {
-        const double pos = p.U ? pos_str(i, p.U, Nd) : pos_sys(i, p.u, Nd);
-        if (pos < c) { p.idx[i] = (int)j; i++; }
-        else {
+    while (i < p.ng) {
+        const double pos = STRAT ? pos_str(i, p.U, Ngd) : pos_sys(i, p.u, Ngd);
+        if (pos < c) {
+            if (i - ob < p.cap) p.idx[i - ob] = (int)(p.j0 + j); else ws.hdr->cap_overflow = 1;
+            i++;
+        } else {
             j++;
-            if (j >= p.n) { overflow = (int)(p.n - i); for (; i < p.n; i++) p.idx[i] = (int)(p.n - 1); break; }
+            if (j >= p.n) {
+                if (p.is_last) {
+                    overflow = (int)(p.ng - i);
+                    for (; i < p.ng; i++) { if (i - ob < p.cap) p.idx[i - ob] = (int)(p.ng - 1); else ws.hdr->cap_overflow = 1; }
+                }
+                break;
+            }
             c = __dadd_rn(c, p.w[j]);
         }
     }
-    if (p.cumsum_last) {
-        for (i64 q = j + 1; q < p.n; q++) c = __dadd_rn(c, p.w[q]);
-        *p.cumsum_last = c;
-    }
-    if (p.info) { p.info[0] = overflow; p.info[1] = 1; p.info[2] = ws.hdr->n_unclean; p.info[3] = ws.hdr->n_runs; p.info[4] = ws.hdr->chain_bad; p.info[5] = ws.hdr->n_seq; }
+    for (i64 q = j + 1; q < p.n; q++) c = __dadd_rn(c, p.w[q]);
+    if (p.cumsum_last) *p.cumsum_last = c;
+    ws.hdr->out_end = i;
+    if (p.out_range) { p.out_range[0] = ob; p.out_range[1] = i; }
+    write_info(overflow, 1);
 }
 
 // ------------------------------------------------------------------ weight sum / scale
@@ -1101,40 +1200,77 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_sum_tiles(const double *tile_
     if (threadIdx.x == 0) *out = sh[0];
 }
 
-int run(i64 n, const double *w, double u, const double *U, int *idx, void *workspace, size_t ws_bytes,
-        int *info, double *cumsum_last, cudaStream_t s)
+struct RunArgs {
+    i64 n, ng, j0, cap;
+    const double *w, *U;
+    double u;
+    int *idx;
+    void *workspace; size_t ws_bytes;
+    int *info; double *cumsum_last;
+    const double *carry_approx, *carry_exact;
+    i64 *out_range;
+    int is_last;
+    int phase;           // bit 0: passes A-C (need carry_approx), bit 1: passes D-G (need carry_exact)
+};
+
+int run(const RunArgs &a, cudaStream_t s)
 {
-    if (n < 0) { set_error("n < 0"); return BKE_ERR_BAD_ARG; }
+    const i64 n = a.n;
+    if (n < 0 || a.ng < n || a.j0 < 0) { set_error("bad particle counts"); return BKE_ERR_BAD_ARG; }
     if (n == 0) return BKE_OK;
-    if (n >= ((i64)1 << 31)) { set_error("n must be < 2^31 (indexes are int32, resampling.py:141)"); return BKE_ERR_BAD_ARG; }
-    if (!w || !idx || !workspace) { set_error("weights, indexes and workspace must be non-NULL"); return BKE_ERR_BAD_ARG; }
-    if (!U && !(u >= 0.0 && u < 1.0)) { set_error("u must be in [0, 1)"); return BKE_ERR_BAD_ARG; }
+    if (a.ng >= ((i64)1 << 31)) { set_error("n must be < 2^31 (indexes are int32, resampling.py:141)"); return BKE_ERR_BAD_ARG; }
+    if (!a.w || !a.idx || !a.workspace) { set_error("weights, indexes and workspace must be non-NULL"); return BKE_ERR_BAD_ARG; }
+    if (!a.U && !(a.u >= 0.0 && a.u < 1.0)) { set_error("u must be in [0, 1)"); return BKE_ERR_BAD_ARG; }
     const size_t need = carve(n, nullptr, nullptr);
-    if (ws_bytes < need) { set_error("workspace too small: %zu < %zu", ws_bytes, need); return BKE_ERR_BAD_ARG; }
-    if (reinterpret_cast<uintptr_t>(workspace) & 255) { set_error("workspace must be 256-byte aligned"); return BKE_ERR_BAD_ARG; }
+    if (a.ws_bytes < need) { set_error("workspace too small: %zu < %zu", a.ws_bytes, need); return BKE_ERR_BAD_ARG; }
+    if (reinterpret_cast<uintptr_t>(a.workspace) & 255) { set_error("workspace must be 256-byte aligned"); return BKE_ERR_BAD_ARG; }
     Params p;
-    carve(n, (unsigned char *)workspace, &p.ws);
-    p.w = w; p.n = n; p.u = u; p.U = U; p.idx = idx; p.info = info; p.cumsum_last = cumsum_last;
-    // |exact sequential sum - approximate tree sum| <= (n + 4096) * 2^-53 relative (non-negative
-    // terms), i.e. less than (n + 4096) ulps of the running sum; doubled, plus slack.
-    p.eb = 2 * (n + 4096) + (n >> 4);
-    const double tau = ldexp((double)n, -46);
+    carve(n, (unsigned char *)a.workspace, &p.ws);
+    p.w = a.w; p.n = n; p.ng = a.ng; p.j0 = a.j0; p.cap = a.cap; p.is_last = a.is_last;
+    p.carry_approx = a.carry_approx; p.carry_exact = a.carry_exact; p.out_range = a.out_range;
+    p.u = a.u; p.U = a.U; p.idx = a.idx; p.info = a.info; p.cumsum_last = a.cumsum_last;
+    // |exact sequential sum - approximate tree sum| <= (N + 4096) * 2^-53 relative (non-negative
+    // terms), i.e. less than (N + 4096) ulps of the running sum; doubled, plus slack.
+    p.eb = 2 * (a.ng + 4096) + (a.ng >> 4);
+    const double tau = ldexp((double)a.ng, -46);
     p.tau = tau > 1e-6 ? tau : 1e-6;
-    p.aligned16 = (reinterpret_cast<uintptr_t>(w) & 15) == 0;
-    if (check_cuda(cudaMemsetAsync(p.ws.hdr, 0, sizeof(Header), s), "memset header")) return BKE_ERR_CUDA;
+    p.aligned16 = (reinterpret_cast<uintptr_t>(a.w) & 15) == 0;
     const int T = p.ws.T;
     const int emit_smem = (int)sizeof(EmitShared);
-    if (check_cuda(cudaFuncSetAttribute(k_emit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, emit_smem), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
-    if (check_cuda(cudaFuncSetAttribute(k_emit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, emit_smem), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
-    k_tile_sums<<<T, BLOCK, 0, s>>>(p);
-    k_scan_tiles<<<1, CHAIN_THREADS, 0, s>>>(p);
-    const int pgrid = T < sm_count() * 2 ? T : sm_count() * 2;
-    k_tile_maps<<<pgrid, BLOCK, 0, s>>>(p);
-    k_chain<<<1, CHAIN_THREADS, 0, s>>>(p, 0.0);
-    if (U) k_emit<true><<<pgrid, BLOCK, emit_smem, s>>>(p);
-    else k_emit<false><<<pgrid, BLOCK, emit_smem, s>>>(p);
-    k_fill_runs<<<sm_count() * 4, 256, 0, s>>>(p);
-    k_sequential<<<1, 32, 0, s>>>(p, 0.0);
+    static bool configured[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        if (check_cuda(cudaFuncSetAttribute(k_emit_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, emit_smem), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
+        if (check_cuda(cudaFuncSetAttribute(k_emit_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, emit_smem), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
+        if (check_cuda(cudaFuncSetAttribute(k_emit_slow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, emit_smem), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
+        if (check_cuda(cudaFuncSetAttribute(k_emit_slow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, emit_smem), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    const int sms = sm_count();
+    const int slow_grid = T < sms * 2 ? T : sms * 2;
+    if (a.phase & 1) {
+        if (check_cuda(cudaMemsetAsync(p.ws.hdr, 0, sizeof(Header), s), "memset header")) return BKE_ERR_CUDA;
+        k_tile_sums<<<T, BLOCK, 0, s>>>(p);
+        k_scan_tiles<<<1, CHAIN_THREADS, 0, s>>>(p);
+        k_tile_maps_fast<<<T < sms * 4 ? T : sms * 4, BLOCK, 0, s>>>(p);
+        k_tile_maps<<<slow_grid, BLOCK, 0, s>>>(p);
+    }
+    if (a.phase & 2) {
+        const int fast_grid = T < sms * 3 ? T : sms * 3;
+        if (a.U) {
+            k_chain<true><<<1, CHAIN_THREADS, 0, s>>>(p);
+            k_emit_fast<true><<<fast_grid, BLOCK, emit_smem, s>>>(p);
+            k_emit_slow<true><<<slow_grid, BLOCK, emit_smem, s>>>(p);
+        } else {
+            k_chain<false><<<1, CHAIN_THREADS, 0, s>>>(p);
+            k_emit_fast<false><<<fast_grid, BLOCK, emit_smem, s>>>(p);
+            k_emit_slow<false><<<slow_grid, BLOCK, emit_smem, s>>>(p);
+        }
+        k_fill_runs<<<sms * 4, 256, 0, s>>>(p);
+        if (a.U) k_sequential<true><<<1, 32, 0, s>>>(p);
+        else k_sequential<false><<<1, 32, 0, s>>>(p);
+    }
     return check_cuda(cudaGetLastError(), "resample launch");
 }
 
@@ -1151,17 +1287,41 @@ size_t bke_resample_workspace_bytes(int64_t n)
     return rs::carve(n, nullptr, nullptr);
 }
 
+static rs::RunArgs whole_array(int64_t n, const double *weights, double u, const double *U, int32_t *indexes,
+                               void *workspace, size_t workspace_bytes, int32_t *info, double *cumsum_last)
+{
+    rs::RunArgs a;
+    a.n = n; a.ng = n; a.j0 = 0; a.cap = n; a.w = weights; a.U = U; a.u = u; a.idx = indexes;
+    a.workspace = workspace; a.ws_bytes = workspace_bytes; a.info = info; a.cumsum_last = cumsum_last;
+    a.carry_approx = nullptr; a.carry_exact = nullptr; a.out_range = nullptr; a.is_last = 1; a.phase = 3;
+    return a;
+}
+
 int bke_systematic_resample(int64_t n, const double *weights, double u, int32_t *indexes, void *workspace,
                             size_t workspace_bytes, int32_t *info, double *cumsum_last, void *stream)
 {
-    return rs::run(n, weights, u, nullptr, indexes, workspace, workspace_bytes, info, cumsum_last, (cudaStream_t)stream);
+    return rs::run(whole_array(n, weights, u, nullptr, indexes, workspace, workspace_bytes, info, cumsum_last), (cudaStream_t)stream);
 }
 
 int bke_stratified_resample(int64_t n, const double *weights, const double *uniforms, int32_t *indexes,
                             void *workspace, size_t workspace_bytes, int32_t *info, double *cumsum_last, void *stream)
 {
     if (n > 0 && !uniforms) { set_error("uniforms is NULL"); return BKE_ERR_BAD_ARG; }
-    return rs::run(n, weights, 0.0, uniforms, indexes, workspace, workspace_bytes, info, cumsum_last, (cudaStream_t)stream);
+    return rs::run(whole_array(n, weights, 0.0, uniforms, indexes, workspace, workspace_bytes, info, cumsum_last), (cudaStream_t)stream);
+}
+
+int bke_resample_shard(const bke_resample_shard_args *args, void *stream)
+{
+    if (!args) { set_error("args is NULL"); return BKE_ERR_BAD_ARG; }
+    if (!(args->phase & 3)) { set_error("phase selects nothing"); return BKE_ERR_BAD_ARG; }
+    rs::RunArgs a;
+    a.n = args->n_local; a.ng = args->n_global; a.j0 = args->j_offset; a.cap = args->capacity;
+    a.w = args->weights; a.U = args->uniforms; a.u = args->u; a.idx = args->indexes;
+    a.workspace = args->workspace; a.ws_bytes = args->workspace_bytes; a.info = args->info; a.cumsum_last = args->carry_out;
+    a.carry_approx = args->carry_approx; a.carry_exact = args->carry_exact; a.out_range = reinterpret_cast<rs::i64 *>(args->out_range);
+    a.is_last = args->is_last; a.phase = args->phase;
+    if (a.j0 + a.n > a.ng) { set_error("shard exceeds the global particle count"); return BKE_ERR_BAD_ARG; }
+    return rs::run(a, (cudaStream_t)stream);
 }
 
 int bke_weights_sum(int64_t n, const double *weights, double *sum_out, void *workspace, size_t workspace_bytes,

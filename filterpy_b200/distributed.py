@@ -11,7 +11,8 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_bounds", "shard_of", "all_reduce_sum", "exclusive_prefix", "gather_counts"]
+__all__ = ["shard_bounds", "shard_of", "all_reduce_sum", "exclusive_prefix", "gather_counts",
+           "sharded_systematic_resample"]
 
 
 def shard_bounds(n, world):
@@ -58,3 +59,68 @@ def exclusive_prefix(value, group=None):
     for r in range(rank):
         acc = acc + allv[r]
     return acc.reshape(value.shape)
+
+
+def sharded_systematic_resample(weights_local, u, group=None, capacity=None, uniforms=None):
+    """Systematic (or, with ``uniforms`` = the replicated global U[N], stratified) resampling of a
+    particle set whose weights are sharded contiguously over the ranks of ``group`` — one process
+    per GPU, NCCL over NVLink.  Bit-identical to ``systematic_resample`` on the concatenated array.
+
+    Exchanges (all stream-ordered, no host synchronisation besides the size gather):
+      1. all-gather of the shard sizes (host ints) and of the approximate shard weight sums (one
+         double per rank) — the weight-sum exchange of the north star;
+      2. the exact running sum handed from rank r to rank r+1 (one double, point-to-point): the only
+         serial dependency; the heavy passes (tile sums, parity maps) run before it on every rank.
+
+    Returns ``(indexes, out_range)``: rank r owns the global output positions
+    ``[out_range[0], out_range[1])`` (device int64[2]); ``indexes[:out_range[1]-out_range[0]]`` holds
+    their GLOBAL particle numbers (int32).  ``capacity`` bounds the local output buffer (default
+    ``2 * n_local + 1024``; a shard holding more weight than that needs a larger one — info[6])."""
+    import ctypes
+    from . import _lib
+    from ._dev import stream_ptr
+    lib = _lib.load()
+    dev = weights_local.device
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    n_local = int(weights_local.numel())
+    sizes = [None] * world
+    if world > 1:
+        dist.all_gather_object(sizes, n_local, group=group)
+    else:
+        sizes = [n_local]
+    n_global = int(sum(sizes)); j_offset = int(sum(sizes[:rank]))
+    cap = int(capacity) if capacity is not None else 2 * n_local + 1024
+    ws_bytes = int(lib.bke_resample_workspace_bytes(n_local))
+    ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)
+    ws_ptr = ws.data_ptr() + ((-ws.data_ptr()) % 256)
+    idx = torch.empty(cap, dtype=torch.int32, device=dev)
+    info = torch.zeros(8, dtype=torch.int32, device=dev)
+    out_range = torch.zeros(2, dtype=torch.int64, device=dev)
+    carry_out = torch.zeros(1, dtype=torch.float64, device=dev)
+    local_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+    st = stream_ptr(dev)
+    _lib.check(lib.bke_weights_sum(n_local, weights_local.data_ptr(), local_sum.data_ptr(), ws_ptr, ws_bytes, st))
+    sums = gather_counts(local_sum[0], group)                        # approximate shard sums, every rank
+    carry_approx = sums[:rank].sum().reshape(1) if rank > 0 else torch.zeros(1, dtype=torch.float64, device=dev)
+    a = _lib.ResampleShardArgs()
+    a.n_local, a.n_global, a.j_offset, a.capacity = n_local, n_global, j_offset, cap
+    a.weights = weights_local.data_ptr()
+    a.uniforms = None if uniforms is None else uniforms.data_ptr()
+    a.u = float(u)
+    a.carry_approx = carry_approx.data_ptr()
+    a.indexes, a.out_range, a.carry_out = idx.data_ptr(), out_range.data_ptr(), carry_out.data_ptr()
+    a.workspace, a.workspace_bytes, a.info = ws_ptr, ws_bytes, info.data_ptr()
+    a.is_last = 1 if rank == world - 1 else 0
+    a.phase = 1
+    _lib.check(lib.bke_resample_shard(ctypes.byref(a), st))          # passes A-C: no dependency on other ranks
+    carry_in = torch.zeros(1, dtype=torch.float64, device=dev)
+    if rank > 0:
+        dist.recv(carry_in, src=dist.get_global_rank(group, rank - 1) if group is not None else rank - 1, group=group)
+        a.carry_exact = carry_in.data_ptr()
+    a.phase = 2
+    _lib.check(lib.bke_resample_shard(ctypes.byref(a), stream_ptr(dev)))   # exact chain + emit
+    if rank < world - 1:
+        dist.send(carry_out, dst=dist.get_global_rank(group, rank + 1) if group is not None else rank + 1, group=group)
+    keep = (ws, carry_approx, carry_in, local_sum, sums)
+    return idx, out_range, info, keep

@@ -3,3 +3,4 @@ from .kalman_filter import KalmanFilter, predict, update, batch_filter  # noqa: 
 from .sigma_points import MerweScaledSigmaPoints  # noqa: F401
 from .UKF import (UnscentedKalmanFilter, LinearFx, ConstVelFx, LinearHx, RangeAzElHx,  # noqa: F401
                   RangeBearingHx)
+from .unscented_transform import unscented_transform  # noqa: F401

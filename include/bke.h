@@ -152,6 +152,19 @@ typedef struct bke_ukf_args {
 
 int bke_ukf_step(const bke_ukf_args *args, void *stream);
 
+/* Stand-alone pieces of the unscented path for callers that use them directly:
+ *   MerweScaledSigmaPoints.sigma_points(x, P)   filterpy/kalman/sigma_points.py:124-177
+ *       x[N,n], P[N,n,n] -> sigmas[N,2n+1,n]; status[N] = BKE_STATUS_NOT_PD where scipy's cholesky
+ *       would raise (only the upper triangle of P is read, as scipy does);
+ *   unscented_transform(sigmas, Wm, Wc, noise_cov)   filterpy/kalman/unscented_transform.py:22-128
+ *       sigmas[N,k,n], Wm[k], Wc[k], noise_cov[n,n] (noise_stride 0) / [N,n,n] (n*n) / NULL
+ *       -> x_out[N,n], P_out[N,n,n]   (default mean / residual functions). */
+int bke_merwe_sigma_points(int64_t n_filters, int32_t dim_x, int32_t dtype, double alpha, double beta, double kappa,
+                           const void *x, const void *P, void *sigmas, int32_t *status, void *stream);
+int bke_unscented_transform(int64_t n_filters, int32_t n_sigmas, int32_t dim, int32_t dtype, const void *sigmas,
+                            const void *Wm, const void *Wc, const void *noise_cov, int64_t noise_stride,
+                            void *x_out, void *P_out, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Particle resampling.
  * Replaces systematic_resample(weights) / stratified_resample(weights)
@@ -167,9 +180,8 @@ int bke_ukf_step(const bke_ukf_args *args, void *stream);
  *       [1] 1 if the weights held a negative / non-finite entry and the literal sequential
  *       kernel was used, [2] number of binade-crossing tiles, [3] number of long runs.
  *   cumsum_last (device double, optional): cumsum(weights)[-1] as the reference would see it.
- * Multi-GPU (weights sharded contiguously across ranks): `carry_in` is the exact running sum
- * of all earlier shards (device double or NULL = 0), `global_offset`/`global_n` place the
- * shard in the global particle array, `out_begin`..: see bke_resample_shard below.
+ *       [5] tiles walked sequentially, [6] outputs that did not fit `capacity` (shards),
+ *       [7] tiles that needed the general (tie / raw element) path.
  */
 size_t bke_resample_workspace_bytes(int64_t n);
 
@@ -180,6 +192,37 @@ int bke_systematic_resample(int64_t n, const double *weights, double u, int32_t 
 int bke_stratified_resample(int64_t n, const double *weights, const double *uniforms,
                             int32_t *indexes, void *workspace, size_t workspace_bytes,
                             int32_t *info, double *cumsum_last, void *stream);
+
+/* One contiguous SHARD of a particle set that is spread over several GPUs (rank r holds particles
+ * [j_offset, j_offset + n_local) of n_global).  The result equals the single-array call bit for
+ * bit: shard r produces exactly the indexes of the global output positions
+ * [out_range[0], out_range[1]) — those whose position falls into this shard's span of the
+ * cumulative sum — with GLOBAL particle numbers, written to indexes[0 .. out_end - out_begin).
+ *   phase 1 (passes A-C; independent on every rank) needs `carry_approx`: the approximate
+ *           (tree-ordered, all-gathered) sum of all earlier shards, device double;
+ *   phase 2 (chain + emit) needs `carry_exact`: the exact running sum the previous rank's call
+ *           wrote to its `carry_out` (device double; NULL on rank 0).  That hand-off is the only
+ *           serial dependency between ranks; everything is stream-ordered, no host sync.
+ * `uniforms` (stratified) is the GLOBAL uniform array [n_global], replicated; NULL = systematic.
+ * `is_last` = 1 on the shard holding the end of the set (positions beyond the last cumulative sum
+ * are then reported in info[0] and filled with n_global - 1, as in the single-array call). */
+typedef struct bke_resample_shard_args {
+    int64_t n_local, n_global, j_offset, capacity;
+    const double *weights;
+    const double *uniforms;
+    double u;
+    const double *carry_approx;
+    const double *carry_exact;
+    int32_t *indexes;
+    int64_t *out_range;          /* device int64[2] */
+    double *carry_out;           /* device double */
+    void *workspace; size_t workspace_bytes;
+    int32_t *info;               /* device int32[8] or NULL */
+    int32_t is_last;
+    int32_t phase;               /* 1, 2 or 3 (= both) */
+} bke_resample_shard_args;
+
+int bke_resample_shard(const bke_resample_shard_args *args, void *stream);
 
 /* sum of weights (fp64, deterministic tree order) — the quantity that is all-reduced across
  * GPUs before a distributed resample; also used to normalise: weights_out[i] = weights[i] / sum

@@ -165,3 +165,69 @@ def test_full_size_64M_bit_exact_and_properties():
     idx = idx_d.cpu().numpy()
     want = ors.systematic_resample_c(w, u)
     assert np.array_equal(idx, want)
+
+
+@pytest.mark.parametrize("kind", ["heavy", "uniform", "degenerate", "zeros"])
+@pytest.mark.parametrize("shards", [2, 3, 8])
+def test_sharded_resample_equals_whole_array(kind, shards):
+    """bke_resample_shard: the shards of one particle set, processed the way the ranks of a multi-GPU
+    job do (approximate carry from the shard sums, exact carry handed from shard to shard), produce
+    exactly the single-array result — here all shards run on one GPU, in rank order."""
+    import ctypes
+    import torch
+    from filterpy_b200 import _lib
+    from filterpy_b200.common import workloads as wl
+    from filterpy_b200.distributed import shard_bounds
+    from oracle import resample as ors
+    N, u = 300007, 0.6180339887
+    w = wl.resample_weights(N, kind, seed=11)
+    want = ors.systematic_resample_c(w, u)
+    lib = _lib.load()
+    wd = torch.from_numpy(w).cuda()
+    b = shard_bounds(N, shards)
+    out = np.full(N, -1, dtype=np.int32)
+    st = torch.cuda.current_stream().cuda_stream
+    sums = []
+    state = []
+    for r in range(shards):
+        n_loc = int(b[r + 1] - b[r])
+        ws_bytes = int(lib.bke_resample_workspace_bytes(n_loc))
+        ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device="cuda")
+        ws_ptr = ws.data_ptr() + ((-ws.data_ptr()) % 256)
+        sl = wd[int(b[r]):int(b[r + 1])]
+        s = torch.zeros(1, dtype=torch.float64, device="cuda")
+        _lib.check(lib.bke_weights_sum(n_loc, sl.data_ptr(), s.data_ptr(), ws_ptr, ws_bytes, st))
+        sums.append(s)
+        state.append((n_loc, ws, ws_ptr, ws_bytes, sl))
+    carry_exact = None
+    covered = 0
+    for r in range(shards):
+        n_loc, ws, ws_ptr, ws_bytes, sl = state[r]
+        cap = N
+        idx = torch.full((cap,), -7, dtype=torch.int32, device="cuda")
+        info = torch.zeros(8, dtype=torch.int32, device="cuda")
+        rng_t = torch.zeros(2, dtype=torch.int64, device="cuda")
+        carry_out = torch.zeros(1, dtype=torch.float64, device="cuda")
+        capx = torch.stack(sums[:r]).sum().reshape(1) if r else torch.zeros(1, dtype=torch.float64, device="cuda")
+        a = _lib.ResampleShardArgs()
+        a.n_local, a.n_global, a.j_offset, a.capacity = n_loc, N, int(b[r]), cap
+        a.weights, a.u = sl.data_ptr(), u
+        a.carry_approx = capx.data_ptr()
+        a.carry_exact = None if carry_exact is None else carry_exact.data_ptr()
+        a.indexes, a.out_range, a.carry_out = idx.data_ptr(), rng_t.data_ptr(), carry_out.data_ptr()
+        a.workspace, a.workspace_bytes, a.info = ws_ptr, ws_bytes, info.data_ptr()
+        a.is_last = 1 if r == shards - 1 else 0
+        a.phase = 1
+        _lib.check(lib.bke_resample_shard(ctypes.byref(a), st))
+        a.phase = 2
+        _lib.check(lib.bke_resample_shard(ctypes.byref(a), st))
+        lo, hi = [int(v) for v in rng_t.cpu().numpy()]
+        inf = info.cpu().numpy()
+        assert inf[1] == 0 and inf[6] == 0, inf
+        assert lo == covered, (r, lo, covered)
+        out[lo:hi] = idx[:hi - lo].cpu().numpy()
+        covered = hi
+        carry_exact = carry_out
+        assert float(carry_out.item()) == np.cumsum(w[:int(b[r + 1])])[-1]
+    assert covered == N
+    assert np.array_equal(out, want)

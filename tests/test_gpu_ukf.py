@@ -106,3 +106,35 @@ def test_ukf_not_pd_status():
     u.P = P
     u.predict(); u.update(np.zeros((3, 1)))
     assert u.status.cpu().numpy().tolist() == [0, 2, 0]
+
+
+def test_sigma_points_and_unscented_transform_standalone(golden):
+    """sigma_points.py:124-177 / unscented_transform.py:99-128 as stand-alone calls (test_ukf.py:112-189)."""
+    import torch
+    from filterpy_b200.kalman import MerweScaledSigmaPoints, unscented_transform
+    from oracle import ukf as oukf
+    g = golden("ukf_sigma")
+    pts = MerweScaledSigmaPoints(6, float(g["alpha"]), float(g["beta"]), float(g["kappa"]))
+    sig = pts.sigma_points(g["x"], g["P"])
+    assert sig.shape == (13, 6)
+    np.testing.assert_allclose(sig, g["sigmas"], rtol=1e-12, atol=1e-13)
+    # sigma points + UT recover the mean and covariance (test_ukf.py:132-134)
+    x, P = unscented_transform(sig, pts.Wm, pts.Wc)
+    np.testing.assert_allclose(x, g["x"], atol=1e-12); np.testing.assert_allclose(P, g["P"], atol=1e-11)
+    # bank, both dtypes, against the oracle
+    rng = np.random.default_rng(0)
+    N = 1000
+    A = rng.standard_normal((N, 6, 6)); Pb = np.einsum("nij,nkj->nik", A, A) + np.eye(6); xb = rng.standard_normal((N, 6))
+    for dt, tol in ((torch.float64, 1e-10), (torch.float32, 2e-4)):
+        sb = pts.sigma_points(torch.from_numpy(xb).cuda().to(dt), torch.from_numpy(Pb).cuda().to(dt))
+        want = oukf.merwe_sigma_points(xb, Pb, pts.alpha, pts.beta, pts.kappa)
+        np.testing.assert_allclose(sb.cpu().numpy(), want, rtol=tol, atol=tol * 10)
+        Q = np.eye(6) * 0.1
+        xm, Pm = unscented_transform(sb, pts.Wm, pts.Wc, noise_cov=Q)
+        wx, wP = oukf.unscented_transform(want, pts.Wm, pts.Wc, Q)
+        np.testing.assert_allclose(xm.cpu().numpy(), wx, rtol=tol * 10, atol=tol * 100)
+        np.testing.assert_allclose(Pm.cpu().numpy(), wP, rtol=tol * 100, atol=tol * 1000)
+    with pytest.raises(np.linalg.LinAlgError):
+        pts.sigma_points(np.zeros(6), -np.eye(6))
+    with pytest.raises(NotImplementedError):
+        unscented_transform(sig, pts.Wm, pts.Wc, mean_fn=lambda s, w: s[0])
