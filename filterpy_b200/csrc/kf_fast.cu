@@ -54,6 +54,39 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// variants with an L2 eviction-priority hint (createpolicy): the state x, P is re-read by the NEXT
+// step and fits the 126 MB L2 (80 MB for 2^20 filters) -> evict_last; the models and measurements
+// stream through once per step -> evict_first, so that they do not push the state out.
+__device__ __forceinline__ void tma_load_2d_hint(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar, uint64_t pol)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d_hint(void *dst, const CUtensorMap *map, int c0, uint64_t *bar, uint64_t pol)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.1d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3}], [%2], %4;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "l"(pol) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void st_hint(float *addr, float4 v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+                 ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+
 __device__ __forceinline__ void tma_load_1d(void *dst, const CUtensorMap *map, int c0, uint64_t *bar)
 {
     asm volatile(
@@ -103,6 +136,7 @@ template <int N, int M>
 struct FastP {
     int64_t N_filters;
     int num_tiles;
+    int l2_hints;                   // 1: keep x, P in L2 between steps (evict_last), stream the rest (evict_first)
     float alpha_sq;
     const float *F, *Q, *H, *R;     // used when SHARED
     float *x_out, *P_out;
@@ -128,11 +162,26 @@ kf42_f32_kernel(const __grid_constant__ Maps maps, const FastP<4, 2> p)
     if (!SHARED && DO_U) tx_bytes += St::HB + St::RB;
     if (DO_U) tx_bytes += St::ZB;
 
+    const uint64_t pol_first = policy_evict_first(), pol_last = policy_evict_last();
     auto issue = [&](int tile, int stage) {
         unsigned char *sb = smem + stage * St::BYTES;
         uint64_t *bar = &full[stage];
         const int row0 = tile * TILE;
         mbar_expect_tx(bar, tx_bytes);
+        if (p.l2_hints) {
+            tma_load_2d_hint(sb + St::OP, &maps.P, 0, row0, bar, pol_last);
+            tma_load_2d_hint(sb + St::OX, &maps.x, 0, row0, bar, pol_last);
+            if (!SHARED && DO_P) {
+                tma_load_2d_hint(sb + St::OF, &maps.F, 0, row0, bar, pol_first);
+                tma_load_2d_hint(sb + St::OQ, &maps.Q, 0, row0, bar, pol_first);
+            }
+            if (!SHARED && DO_U) {
+                tma_load_2d_hint(sb + St::OH, &maps.H, 0, row0, bar, pol_first);
+                tma_load_2d_hint(sb + St::OR_, &maps.R, 0, row0, bar, pol_first);
+            }
+            if (DO_U) tma_load_1d_hint(sb + St::OZ, &maps.z, row0 * M, bar, pol_first);
+            return;
+        }
         tma_load_2d(sb + St::OP, &maps.P, 0, row0, bar);
         tma_load_2d(sb + St::OX, &maps.x, 0, row0, bar);
         if (!SHARED && DO_P) {
@@ -304,16 +353,31 @@ kf42_f32_kernel(const __grid_constant__ Maps maps, const FastP<4, 2> p)
             }
         }
         if (live) {
-            *reinterpret_cast<float4 *>(p.x_out + f * N) = make_float4(x[0], x[1], x[2], x[3]);
+            if (p.l2_hints) {
+                st_hint(p.x_out + f * N, make_float4(x[0], x[1], x[2], x[3]), pol_last);
 #pragma unroll
-            for (int i = 0; i < N; i++)
-                *reinterpret_cast<float4 *>(p.P_out + f * N * N + i * N) = make_float4(P[i][0], P[i][1], P[i][2], P[i][3]);
+                for (int i = 0; i < N; i++)
+                    st_hint(p.P_out + f * N * N + i * N, make_float4(P[i][0], P[i][1], P[i][2], P[i][3]), pol_last);
+            } else {
+                *reinterpret_cast<float4 *>(p.x_out + f * N) = make_float4(x[0], x[1], x[2], x[3]);
+#pragma unroll
+                for (int i = 0; i < N; i++)
+                    *reinterpret_cast<float4 *>(p.P_out + f * N * N + i * N) = make_float4(P[i][0], P[i][1], P[i][2], P[i][3]);
+            }
             if (EXTRAS && p.status) p.status[f] = st;
         }
     }
 }
 
 // ---------------------------------------------------------------------------- host side
+// tuning knobs (environment, read once): BKE_KF_STAGES in {2,3}, BKE_KF_CTAS = resident CTAs per SM,
+// BKE_KF_L2 = 0 disables the L2 eviction-priority hints
+int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
 typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                              const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -367,12 +431,6 @@ bool make_map_1d(CUtensorMap *m, const void *base, int64_t elems, int box_elems)
     return r == CUDA_SUCCESS;
 }
 
-// tuning knobs (environment, read once): BKE_KF_STAGES in {2,3}, BKE_KF_CTAS = resident CTAs per SM
-int env_int(const char *name, int dflt)
-{
-    const char *v = getenv(name);
-    return v ? atoi(v) : dflt;
-}
 
 template <int MODE, bool SHARED, bool EXTRAS, int STAGES>
 int launch_variant_s(const Maps &maps, const FastP<4, 2> &p, cudaStream_t s, int ctas_per_sm)
@@ -449,6 +507,11 @@ int launch_kf_fast(const bke_kf_args &a, cudaStream_t s)
     p.N_filters = N;
     p.num_tiles = (int)((N + TILE - 1) / TILE);
     p.alpha_sq = (float)a.alpha_sq;
+    {
+        // keep-the-state-in-L2 hints pay off when x, P fit the L2 together with the streaming traffic
+        static const int l2_env = env_int("BKE_KF_L2", 1);
+        p.l2_hints = l2_env && (N * 80 <= (int64_t)96 << 20) && a.x_out == a.x && a.P_out == a.P;
+    }
     p.F = (const float *)a.F; p.Q = (const float *)a.Q; p.H = (const float *)a.H; p.R = (const float *)a.R;
     p.x_out = (float *)a.x_out; p.P_out = (float *)a.P_out;
     p.valid = a.z_valid;

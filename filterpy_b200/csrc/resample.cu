@@ -35,11 +35,12 @@ namespace bke {
 namespace rs {
 
 constexpr int BLOCK = 256;
-constexpr int IPT = 8;
-constexpr int TILE = BLOCK * IPT;        // 2048 particles per tile
+constexpr int IPT = 16;
+constexpr int TILE = BLOCK * IPT;        // 4096 particles per tile
 constexpr int RMAX = 64;                 // raw elements per tile before giving up
 constexpr int UMAX = 2048;               // tiles with raw elements before giving up
-constexpr int EXPAND = 4096;             // outputs expanded per shared-memory pass
+constexpr int EXPAND = 8192;             // outputs expanded per shared-memory pass
+constexpr int INLINE_MAX = 64;           // copies of one particle a thread writes itself (more: general expansion)
 constexpr int BIGRUN = 2 * EXPAND;       // runs this long go to the fill kernel
 constexpr int CHAIN_THREADS = 1024;
 constexpr int CHAIN_BATCH = 8;           // unclean tiles staged in shared memory per round of the chain
@@ -405,17 +406,21 @@ __device__ __forceinline__ void fetch_tile(const Params &p, int t, double2 (&g)[
 }
 __device__ __forceinline__ void to_blocked(const double2 (&g)[IPT / 2], double (&v)[IPT], double2 *buf /*[TILE/2]*/)
 {
+    constexpr int CH = IPT / 2;                           // 16-byte chunks per thread row (4 or 8)
+    static_assert(CH == 4 || CH == 8, "swizzle written for 64- or 128-byte rows");
     const int tid = threadIdx.x;
 #pragma unroll
-    for (int i = 0; i < IPT / 2; i++) {
+    for (int i = 0; i < CH; i++) {
         const int c16 = i * BLOCK + tid;                  // 16-byte chunk index in the tile
-        const int r = c16 >> 2, c = c16 & 3;
-        buf[r * 4 + (c ^ ((r >> 1) & 3))] = g[i];
+        const int r = c16 / CH, c = c16 % CH;
+        const int sw = (CH == 4) ? ((r >> 1) & 3) : (r & 7);
+        buf[r * CH + (c ^ sw)] = g[i];
     }
     __syncthreads();
+    const int swt = (CH == 4) ? ((tid >> 1) & 3) : (tid & 7);
 #pragma unroll
-    for (int c = 0; c < IPT / 2; c++) {
-        const double2 val = buf[tid * 4 + (c ^ ((tid >> 1) & 3))];
+    for (int c = 0; c < CH; c++) {
+        const double2 val = buf[tid * CH + (c ^ swt)];
         v[2 * c] = val.x; v[2 * c + 1] = val.y;
     }
     __syncthreads();
@@ -541,7 +546,7 @@ struct MapsShared {
 // Fast kernel: every tile whose adds are all clean and tie-free in ONE binade (decided from the two
 // approximate tile prefixes and the elements themselves) gets its map as a plain int64 sum, straight
 // from the striped registers.  Everything else is queued for the general kernel.
-__global__ void __launch_bounds__(BLOCK, 4) k_tile_maps_fast(Params p)
+__global__ void __launch_bounds__(BLOCK, 3) k_tile_maps_fast(Params p)
 {
     __shared__ i64 shi[BLOCK / 32 + 1];
     if (p.ws.hdr->fallback) return;
@@ -654,17 +659,16 @@ __global__ void __launch_bounds__(BLOCK, 2) k_tile_maps(Params p)
 // ------------------------------------------------------------------ positions
 __device__ __forceinline__ double pos_sys(i64 i, double u, double Nd) { return __ddiv_rn(__dadd_rn(u, (double)i), Nd); }
 
-// number of positions strictly below c (systematic)
+// number of positions strictly below c (systematic): #{ i in [0,N) : fl(fl(u+i)/N) < c }.
+// Away from an integer (by tau, which dominates every rounding error of v and of pos_i) this is
+// floor(c N - u) + 1; within tau of an integer the positions are evaluated exactly.
 __device__ __forceinline__ i64 count_below_sys(double c, double u, i64 N, double Nd, double tau)
 {
     const double v = __dadd_rn(__dmul_rn(c, Nd), -u);
-    if (fabs(v) < 4.0e15) {
-        const i64 fl = __double2ll_rd(v);
-        const double fr = v - (double)fl;
-        if (fr > tau && fr < 1.0 - tau) {
-            const i64 g = fl + 1;
-            return g < 0 ? 0 : (g > N ? N : g);
-        }
+    const double r = rint(v);
+    if (fabs(v - r) > tau && fabs(v) < 4.0e15) {
+        const i64 g = (i64)r + (r > v ? 0 : 1);            // floor(v) + 1
+        return g < 0 ? 0 : (g > N ? N : g);
     }
     double g0d = floor(v) + 1.0;
     if (!(g0d > 0.0)) g0d = 0.0;
@@ -871,7 +875,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain(Params p)
 struct EmitShared {
     TileShared ts;
     int hi[TILE + TILE / 32];     // output end (exclusive) of every element, relative to tile_lo; index via pad32()
-    union { int ebuf[EXPAND + EXPAND / 32]; double2 buf[TILE / 2]; };   // ebuf index via pad32()
+    union { int ebuf[EXPAND + EXPAND / 32]; double2 buf[TILE / 2]; double wd[TILE]; };   // ebuf index via pad32()
     i64 segstate[RMAX + 1];
     int segk[RMAX + 1];
     int segt[RMAX + 1];
@@ -905,21 +909,47 @@ __device__ __forceinline__ void emit_tile(const Params &p, EmitShared &sm, int t
     const int tid = threadIdx.x;
     const i64 tile_lo = count_below<STRAT>(p, __longlong_as_double(S_in));       // every thread: no broadcast needed
     const i64 jbase = (i64)t * TILE + (i64)tid * IPT;
+    static_assert(32 % IPT == 0 || IPT % 32 == 0, "pad32 of a thread's elements assumed to share one pad offset");
+    const int hbase = pad32(tid * IPT);                    // pad32(tid*IPT + k) == hbase + k for k < IPT (IPT divides 32)
+    int hv[IPT];                                           // output range end of each element, relative to tile_lo
+    const bool full_tile = (i64)(t + 1) * TILE <= p.n;
+    if (!STRAT && full_tile) {
+        // branch-free fast evaluation of #{positions < c}: floor(c N - u) + 1 away from integers;
+        // the rare near-integer cases are collected and redone exactly below
+        const double Nd = (double)p.ng, u = p.u, tau = p.tau, lo_d = (double)tile_lo;
+        unsigned slow = 0;
 #pragma unroll
-    for (int k = 0; k < IPT; k++) {
-        int rel = -1;                         // padding elements own no output (fixed below)
-        if (jbase + k < p.n) rel = (int)(count_below<STRAT>(p, __longlong_as_double(cbits[k])) - tile_lo);
-        sm.hi[pad32(tid * IPT + k)] = rel;
-    }
-    __syncthreads();
-    {
-        const i64 last_real = p.n - 1 - (i64)t * TILE;      // padding inherits the end of the last real element
-        if (last_real < TILE - 1) {
-            const int hv = sm.hi[pad32((int)last_real)];
-            __syncthreads();
-            for (int q = tid; q < TILE; q += BLOCK) if (q > last_real) sm.hi[pad32(q)] = hv;
-            __syncthreads();
+        for (int k = 0; k < IPT; k++) {
+            const double v = fma(__longlong_as_double(cbits[k]), Nd, -u);
+            const double r = rint(v);
+            if (!(fabs(v - r) > tau)) slow |= 1u << k;
+            double g = r + (r > v ? 0.0 : 1.0);            // floor(v) + 1
+            g = g < 0.0 ? 0.0 : (g > Nd ? Nd : g);
+            hv[k] = (int)(g - lo_d);
         }
+        if (slow) {
+#pragma unroll
+            for (int k = 0; k < IPT; k++)
+                if (slow & (1u << k)) hv[k] = (int)(count_below<STRAT>(p, __longlong_as_double(cbits[k])) - tile_lo);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < IPT; k++) {
+            hv[k] = -1;                       // padding elements own no output (fixed below)
+            if (jbase + k < p.n) hv[k] = (int)(count_below<STRAT>(p, __longlong_as_double(cbits[k])) - tile_lo);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < IPT; k++) sm.hi[hbase + k] = hv[k];
+    __syncthreads();
+    if (!full_tile) {
+        const i64 last_real = p.n - 1 - (i64)t * TILE;      // padding inherits the end of the last real element
+        const int hvl = sm.hi[pad32((int)last_real)];
+        __syncthreads();
+        for (int q = tid; q < TILE; q += BLOCK) if (q > last_real) sm.hi[pad32(q)] = hvl;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < IPT; k++) hv[k] = sm.hi[hbase + k];
     }
     const int tile_cnt = sm.hi[pad32(TILE - 1)];            // outputs owned by this tile
     if (t == ws.T - 1 && tid == 0) {
@@ -934,6 +964,46 @@ __device__ __forceinline__ void emit_tile(const Params &p, EmitShared &sm, int t
         ws.hdr->out_end = O1;
         if (p.out_range) { p.out_range[0] = ws.hdr->out_begin; p.out_range[1] = O1; }
     }
+    // this thread's elements own the contiguous outputs [hv_prev, hv[IPT-1]) (relative to tile_lo)
+    const int hv_prev = (tid == 0) ? 0 : sm.hi[pad32(tid * IPT - 1)];
+    int maxc = hv[0] - hv_prev;
+#pragma unroll
+    for (int k = 1; k < IPT; k++) maxc = max(maxc, hv[k] - hv[k - 1]);
+    const int any_big = __syncthreads_or(maxc > INLINE_MAX);
+    const int base_j = (int)(p.j0 + (i64)t * TILE);
+    if (!any_big) {
+        // direct expansion: every thread writes the few copies of its own particles into the staging
+        // window (0, 1 or 2 copies without a loop), then the window leaves with coalesced stores
+        for (int cs = 0; cs < tile_cnt; cs += EXPAND) {
+            const int ce = min(tile_cnt, cs + EXPAND);
+            int l = hv_prev;
+#pragma unroll
+            for (int k = 0; k < IPT; k++) {
+                const int h = hv[k];
+                const int a0 = max(l, cs), a1 = min(h, ce);
+                if (a1 > a0) {
+                    const int val = tid * IPT + k;
+                    sm.ebuf[pad32(a0 - cs)] = val;
+                    if (a1 > a0 + 1) {
+                        sm.ebuf[pad32(a0 + 1 - cs)] = val;
+                        for (int o = a0 + 2; o < a1; o++) sm.ebuf[pad32(o - cs)] = val;
+                    }
+                }
+                l = h;
+            }
+            __syncthreads();
+            const i64 rel0 = tile_lo + cs - ws.hdr->out_begin;
+            if (rel0 >= 0 && rel0 + (ce - cs) <= p.cap) {
+                for (int q = tid; q < ce - cs; q += BLOCK) p.idx[rel0 + q] = base_j + sm.ebuf[pad32(q)];
+            } else {
+                for (int q = tid; q < ce - cs; q += BLOCK) put_index(p, tile_lo + cs + q, base_j + sm.ebuf[pad32(q)]);
+            }
+            __syncthreads();
+        }
+        return;
+    }
+    // general expansion (a particle with many copies in this tile): start markers + max-scan;
+    // runs of BIGRUN or more copies are queued for the fill kernel
     int cs = 0;
     while (cs < tile_cnt) {
         int lo_s = 0, hi_s = TILE - 1;                      // owner of output cs: first element with hi > cs
@@ -946,7 +1016,7 @@ __device__ __forceinline__ void emit_tile(const Params &p, EmitShared &sm, int t
         if (owner_end - cs >= BIGRUN) {
             if (tid == 0) {
                 const int r = atomicAdd(&ws.hdr->n_runs, 1);
-                if (r < ws.max_runs) ws.runs[r] = Run{tile_lo + cs, tile_lo + owner_end, (int)(p.j0 + (i64)t * TILE + owner), 0};
+                if (r < ws.max_runs) ws.runs[r] = Run{tile_lo + cs, tile_lo + owner_end, base_j + owner, 0};
                 else ws.hdr->fallback = 1;
             }
             cs = owner_end;
@@ -955,12 +1025,14 @@ __device__ __forceinline__ void emit_tile(const Params &p, EmitShared &sm, int t
         const int ce = min(tile_cnt, cs + EXPAND);
         for (int q = tid; q < EXPAND + EXPAND / 32; q += BLOCK) sm.ebuf[q] = 0;
         __syncthreads();
+        {
+            int l = hv_prev;
 #pragma unroll
-        for (int k = 0; k < IPT; k++) {
-            const int e = tid * IPT + k;
-            const int h = sm.hi[pad32(e)];
-            const int l = (e == 0) ? 0 : sm.hi[pad32(e - 1)];
-            if (h > l && h > cs && l < ce) sm.ebuf[pad32((l > cs ? l : cs) - cs)] = e + 1;
+            for (int k = 0; k < IPT; k++) {
+                const int h = hv[k];
+                if (h > l && h > cs && l < ce) sm.ebuf[pad32((l > cs ? l : cs) - cs)] = tid * IPT + k + 1;
+                l = h;
+            }
         }
         __syncthreads();
         {   // inclusive max-scan over ebuf: 16 consecutive entries per thread
@@ -984,12 +1056,11 @@ __device__ __forceinline__ void emit_tile(const Params &p, EmitShared &sm, int t
             for (int q = 0; q < PER; q++) sm.ebuf[pad32(tid * PER + q)] = max(v[q], basem);
         }
         __syncthreads();
-        const int base_j = (int)(p.j0 + (i64)t * TILE) - 1;
         const i64 rel0 = tile_lo + cs - ws.hdr->out_begin;
         if (rel0 >= 0 && rel0 + (ce - cs) <= p.cap) {
-            for (int q = tid; q < ce - cs; q += BLOCK) p.idx[rel0 + q] = base_j + sm.ebuf[pad32(q)];
+            for (int q = tid; q < ce - cs; q += BLOCK) p.idx[rel0 + q] = base_j - 1 + sm.ebuf[pad32(q)];
         } else {
-            for (int q = tid; q < ce - cs; q += BLOCK) put_index(p, tile_lo + cs + q, base_j + sm.ebuf[pad32(q)]);
+            for (int q = tid; q < ce - cs; q += BLOCK) put_index(p, tile_lo + cs + q, base_j - 1 + sm.ebuf[pad32(q)]);
         }
         __syncthreads();
         cs = ce;
@@ -1000,7 +1071,7 @@ __device__ __forceinline__ void emit_tile(const Params &p, EmitShared &sm, int t
 // Fast emit: the tiles pass C marked SLOT_FAST (clean, tie-free, one binade):
 // c_j = S_in + prefix sum of rne(w_j / ulp), one IEEE add per element.
 template <bool STRAT>
-__global__ void __launch_bounds__(BLOCK, 3) k_emit_fast(Params p)
+__global__ void __launch_bounds__(BLOCK, 2) k_emit_fast(Params p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EmitShared &sm = *reinterpret_cast<EmitShared *>(smem_raw);
@@ -1053,7 +1124,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_emit_slow(Params p)
         i64 cbits[IPT];
         if (ws.tile_slot[t] == SLOT_SEQ) {
             // every element by a true add: thread 0 walks the tile once to get each thread's start state
-            double *wd = reinterpret_cast<double *>(sm.ebuf);
+            double *wd = sm.wd;
             i64 *tstart = reinterpret_cast<i64 *>(sm.hi);
 #pragma unroll
             for (int k = 0; k < IPT; k++) wd[tid * IPT + k] = an.w[k];
@@ -1253,11 +1324,11 @@ int run(const RunArgs &a, cudaStream_t s)
         if (check_cuda(cudaMemsetAsync(p.ws.hdr, 0, sizeof(Header), s), "memset header")) return BKE_ERR_CUDA;
         k_tile_sums<<<T, BLOCK, 0, s>>>(p);
         k_scan_tiles<<<1, CHAIN_THREADS, 0, s>>>(p);
-        k_tile_maps_fast<<<T < sms * 4 ? T : sms * 4, BLOCK, 0, s>>>(p);
+        k_tile_maps_fast<<<T < sms * 3 ? T : sms * 3, BLOCK, 0, s>>>(p);
         k_tile_maps<<<slow_grid, BLOCK, 0, s>>>(p);
     }
     if (a.phase & 2) {
-        const int fast_grid = T < sms * 3 ? T : sms * 3;
+        const int fast_grid = T < sms * 2 ? T : sms * 2;
         if (a.U) {
             k_chain<true><<<1, CHAIN_THREADS, 0, s>>>(p);
             k_emit_fast<true><<<fast_grid, BLOCK, emit_smem, s>>>(p);

@@ -133,13 +133,30 @@ __device__ __forceinline__ void for_sigma(Fn &&fn)
     }
 }
 
+// Cooperative, coalesced movement of a tile's [filters][PER] block between global memory and a
+// shared-memory slab whose per-filter stride PAD is odd: the strided per-thread accesses of the
+// owning threads are then bank-conflict-free (a thread-per-filter LDG of AoS data would touch one
+// cache line per lane per instruction).
+template <typename T, int PER, int PAD>
+__device__ __forceinline__ void slab_load(T *slab, const T *g, int cnt)
+{
+    for (int e = threadIdx.x; e < cnt * PER; e += UB) slab[(e / PER) * PAD + (e % PER)] = g[e];
+}
+template <typename T, int PER, int PAD>
+__device__ __forceinline__ void slab_store(T *g, const T *slab, int cnt)
+{
+    for (int e = threadIdx.x; e < cnt * PER; e += UB) g[e] = slab[(e / PER) * PAD + (e % PER)];
+}
+
 template <typename T, int N, int M, int FX, int HX>
 __global__ void __launch_bounds__(UB) ukf_kernel(UkfP<T> p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NS = 2 * N + 1;
-    T *zs = reinterpret_cast<T *>(smem_raw);                 // [NS*M][UB]
-    T *Fs = zs + NS * M * UB;                                // [N*N] or [N*N][UB]
+    constexpr int PADP = (N * N) | 1;                        // odd per-filter stride of the P / Q slab
+    constexpr int SLAB = (NS * M > PADP ? NS * M : PADP) * UB;
+    T *zs = reinterpret_cast<T *>(smem_raw);                 // [NS*M][UB]; doubles as the staging slab for P, Q, P_out
+    T *Fs = zs + SLAB;                                       // [N*N] or [N*N][UB]
     const bool do_p = p.flags & BKE_DO_PREDICT, do_u = p.flags & BKE_DO_UPDATE;
     const int tid = threadIdx.x;
     const int64_t f = (int64_t)blockIdx.x * UB + tid;
@@ -167,13 +184,22 @@ __global__ void __launch_bounds__(UB) ukf_kernel(UkfP<T> p)
     __syncthreads();
     const T *Fp = Fs + foff, *Hp = Hs + hoff;
 
+    const int64_t tile0 = (int64_t)blockIdx.x * UB;
+    const int cnt = (int)((p.N - tile0) < UB ? (p.N - tile0) : UB);
+    const int tl = live ? tid : cnt - 1;                     // slab row of this thread's filter
     T x[N], P[N][N];
 #pragma unroll
     for (int i = 0; i < N; i++) x[i] = p.x[fc * N + i];
+    slab_load<T, N * N, PADP>(zs, p.P + tile0 * N * N, cnt);
+    __syncthreads();
 #pragma unroll
     for (int i = 0; i < N; i++)
 #pragma unroll
-        for (int j = 0; j < N; j++) P[i][j] = p.P[fc * N * N + i * N + j];
+        for (int j = 0; j < N; j++) P[i][j] = zs[tl * PADP + i * N + j];
+    __syncthreads();
+    const bool q_dense = do_p && p.sQ != 0;
+    if (q_dense) slab_load<T, N * N, PADP>(zs, p.Q + tile0 * N * N, cnt);     // parked until the end of predict
+    __syncthreads();
     int st = BKE_STATUS_OK;
     T U[N][N];
 
@@ -219,12 +245,11 @@ __global__ void __launch_bounds__(UB) ukf_kernel(UkfP<T> p)
                 for (int j = 0; j < N; j++) Pm[i][j] += wd * d[j];
             }
         });
-        const T *Qf = p.Q + fc * p.sQ;
 #pragma unroll
         for (int i = 0; i < N; i++) {
             x[i] = xm[i];
 #pragma unroll
-            for (int j = 0; j < N; j++) P[i][j] = Pm[i][j] + Qf[i * N + j];
+            for (int j = 0; j < N; j++) P[i][j] = Pm[i][j] + (q_dense ? zs[tl * PADP + i * N + j] : p.Q[i * N + j]);
         }
         if (live) {
             if (p.x_prior) for (int i = 0; i < N; i++) p.x_prior[f * N + i] = x[i];
@@ -232,6 +257,7 @@ __global__ void __launch_bounds__(UB) ukf_kernel(UkfP<T> p)
         }
     }
 
+    __syncthreads();                                         // Q has been consumed: the slab now holds hx(sigma points)
     if (do_u) {
         const bool has_z = (p.valid == nullptr) || (p.valid[fc] != 0);
         if (has_z && st == BKE_STATUS_OK) {
@@ -352,15 +378,18 @@ __global__ void __launch_bounds__(UB) ukf_kernel(UkfP<T> p)
             }
         }
     }
+    __syncthreads();                                         // the slab is free again: stage the posterior covariance
     if (live) {
 #pragma unroll
         for (int i = 0; i < N; i++) p.x_out[f * N + i] = x[i];
 #pragma unroll
         for (int i = 0; i < N; i++)
 #pragma unroll
-            for (int j = 0; j < N; j++) p.P_out[f * N * N + i * N + j] = P[i][j];
+            for (int j = 0; j < N; j++) zs[tid * PADP + i * N + j] = P[i][j];
         if (p.status) p.status[f] = st;
     }
+    __syncthreads();
+    slab_store<T, N * N, PADP>(p.P_out + tile0 * N * N, zs, cnt);
 }
 
 template <typename T, int N, int M, int FX, int HX>
@@ -381,7 +410,9 @@ int launch_inst(const bke_ukf_args &a, cudaStream_t s)
     p.x_out = (T *)a.x_out; p.P_out = (T *)a.P_out; p.x_prior = (T *)a.x_prior; p.P_prior = (T *)a.P_prior;
     p.K = (T *)a.K; p.y = (T *)a.y; p.S = (T *)a.S; p.SI = (T *)a.SI; p.ll = (T *)a.log_likelihood;
     p.status = a.status;
-    size_t smem = sizeof(T) * ((2 * N + 1) * M * UB);
+    constexpr int PADP = (N * N) | 1;
+    constexpr int SLABE = ((2 * N + 1) * M > PADP ? (2 * N + 1) * M : PADP) * UB;
+    size_t smem = sizeof(T) * SLABE;
     if (FX == BKE_FX_LINEAR) smem += sizeof(T) * (a.F_stride == 0 ? N * N : N * N * UB);
     if (HX == BKE_HX_LINEAR) smem += sizeof(T) * (a.H_stride == 0 ? M * N : M * N * UB);
     auto kern = ukf_kernel<T, N, M, FX, HX>;

@@ -48,7 +48,7 @@ def test_golden_vectors_from_reference(golden):
 
 
 @pytest.mark.parametrize("kind", ["heavy", "uniform", "random", "zeros", "degenerate", "dyadic"])
-@pytest.mark.parametrize("N", [2047, 2048, 2049, 100003, 1 << 20])
+@pytest.mark.parametrize("N", [2047, 2049, 4095, 4096, 4097, 100003, 1 << 20])
 def test_systematic_vs_oracle(kind, N):
     from filterpy_b200.common import workloads as wl
     from oracle import resample as ors
