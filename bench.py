@@ -48,6 +48,15 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused kernel, from the committed
+    `ncu --set full` capture (profiles/traffic.json); None when there is none."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["kf42_f32_kernel"]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
     def __init__(self, index):
@@ -118,9 +127,11 @@ def cpu_loop_port(cores, nf_per_core, steps):
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         t0 = time.perf_counter()
-        pool.map(_loop_port_worker, [(100 + i, nf_per_core, steps) for i in range(cores)])
+        times = pool.map(_loop_port_worker, [(100 + i, nf_per_core, steps) for i in range(cores)])
         wall = time.perf_counter() - t0
-    return cores * nf_per_core * steps / wall, wall
+    # throughput of `cores` workers running concurrently: each timed its own loop (input generation
+    # and process start-up excluded); the slowest worker bounds the step
+    return cores * nf_per_core * steps / max(times), wall
 
 
 def cpu_vectorised_port(nf, steps):
@@ -260,26 +271,55 @@ def run_ours(args, rank, world, local_rank):
     value = world * N * K / (total_ms * 1e-3)
 
     # ---- e2e: host buffers, copies inside the timed region -----------------------------------
-    def step_e2e(i):
-        kf.predict()
-        kf.update(z_pin[i % Z_RING])                   # H2D of this step's measurements
-        x_pin.copy_(kf.x, non_blocking=True)           # D2H of the posterior
-        P_pin.copy_(kf.P, non_blocking=True)
+    # Every step copies that step's measurements from pinned host memory to the device
+    # (kf.update is handed the HOST tensor), runs the fused step, and copies the posterior back to
+    # pinned host memory.  Primary figure: the posterior mean x (what a tracker reads every epoch);
+    # `e2e_full_posterior` also brings P back (92 MB/step: PCIe-bound).  The device->host copies
+    # run on a side stream from a snapshot of the state, so they overlap the next step's H2D copy
+    # and kernel (PCIe is full duplex); the timed region ends when every copy has landed.
+    copy_stream = torch.cuda.Stream(dev)
+    snap_x = [torch.empty_like(x0) for _ in range(2)]
+    snap_P = [torch.empty_like(P0) for _ in range(2)]
+    snap_free = [torch.cuda.Event() for _ in range(2)]
 
-    reset()
-    for i in range(W):
-        step_e2e(i)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(K):
-        step_e2e(i)
-    e1.record()
-    barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    def step_e2e(i, with_P):
+        kf.predict()
+        kf.update(z_pin[i % Z_RING])                   # H2D of this step's measurements + fused kernel
+        b = i & 1
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(snap_free[b])                   # the D2H that last used this snapshot is done
+        snap_x[b].copy_(kf.x)
+        if with_P:
+            snap_P[b].copy_(kf.P)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ready)
+            x_pin.copy_(snap_x[b], non_blocking=True)  # D2H of the posterior
+            if with_P:
+                P_pin.copy_(snap_P[b], non_blocking=True)
+            snap_free[b].record(copy_stream)
+
+    def run_e2e(with_P):
+        reset()
+        for i in range(W):
+            step_e2e(i, with_P)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            step_e2e(i, with_P)
+        torch.cuda.current_stream(dev).wait_stream(copy_stream)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    e2e_ms = run_e2e(False)
     e2e_value = world * N * K / (e2e_ms * 1e-3)
+    e2e_full_ms = run_e2e(True)
     h2d = N * DIM_Z * 4
-    d2h = N * (DIM_X + DIM_X * DIM_X) * 4
+    d2h = N * DIM_X * 4
+    d2h_full = N * (DIM_X + DIM_X * DIM_X) * 4
 
     if rank != 0:
         return
@@ -294,10 +334,13 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "inputs larger than L2 (344 MB touched per step vs 126 MB L2)",
                    "launch": ("CUDA graph of %d steps per replay" % Z_RING) if use_graph else "one launch per step"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms / K},
+                "ms_per_step": e2e_ms / K, "result": "posterior mean x[N,4] per step"},
+        "e2e_full_posterior": {"value": world * N * K / (e2e_full_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                               "d2h_bytes_per_step": d2h_full, "ms_per_step": e2e_full_ms / K,
+                               "result": "posterior x[N,4] and P[N,4,4] per step"},
         "gpu_launches": K,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
                      "kernel": "kf42_f32_kernel<3,false,false>", "bytes_per_launch": BYTES_PER_FILTER_STEP * N,
                      "kernel_ms": kern_ms, "kernel_ms_min": float(per_launch_ms.min())},
         "clocks": clk.summary(),

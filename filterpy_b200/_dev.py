@@ -35,7 +35,10 @@ def require_cuda(device):
 def to_dev(a, dtype, device):
     """numpy / list / scalar / torch tensor -> contiguous device tensor of `dtype`."""
     if isinstance(a, torch.Tensor):
-        return a.to(device=device, dtype=dtype).contiguous()
+        # a pinned host tensor is copied asynchronously on the current stream (stream-ordered with the
+        # kernels that consume it); the caller must not overwrite it before that stream has moved on
+        nb = (not a.is_cuda) and a.is_pinned()
+        return a.to(device=device, dtype=dtype, non_blocking=nb).contiguous()
     arr = np.ascontiguousarray(np.asarray(a, dtype=np.float64 if dtype == torch.float64 else np.float32))
     return torch.from_numpy(arr).to(device)
 

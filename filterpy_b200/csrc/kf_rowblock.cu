@@ -16,6 +16,7 @@
 //
 // Arithmetic per filter: filterpy/kalman/kalman_filter.py:471-478 (predict) and :533-556 (update,
 // Joseph form), reference @ 3b51149.  Algorithmic bytes per filter-step (9/3 fp64): 3048.
+#include <stdlib.h>
 #include <type_traits>
 #include "bke_internal.cuh"
 #include "kf_regtile.cuh"
@@ -69,10 +70,8 @@ struct RbP {
     int32_t *status;
 };
 
-constexpr int RB_WARPS = 4;
-constexpr int RB_STAGES = 2;
 
-template <typename T, int N, int M, int RPL>
+template <typename T, int N, int M, int RPL, int RB_STAGES>
 struct RbGeom {
     static constexpr int G = N / RPL;                 // lanes per filter
     static constexpr int FPW = 32 / G;                // filters per warp tile
@@ -90,7 +89,9 @@ struct RbGeom {
     static constexpr int OR_ = OH + a16(HB);
     static constexpr int OZ = OR_ + a16(RBY);
     static constexpr int STAGE = a16(OZ + a16(ZB));
-    static constexpr int OUT = a16(XB) + a16(PB);     // posterior staging (x then P)
+    // posterior staging (x then P): a separate buffer with a 2-stage ring; with ONE stage per warp
+    // the posterior is staged in the stage's own x / P slots (more warps fit an SM instead)
+    static constexpr int OUT = RB_STAGES > 1 ? a16(XB) + a16(PB) : 0;
     static constexpr int WARP_BYTES = RB_STAGES * STAGE + OUT;
     static constexpr uint32_t TX = XB + 3 * PB + HB + RBY + ZB;
     static_assert(N % RPL == 0 && G >= 1 && G <= 32, "bad row-block shape");
@@ -98,10 +99,10 @@ struct RbGeom {
     static_assert(2 * N * M <= N * N, "K and PH' are parked in the Q slot");
 };
 
-template <typename T, int N, int M, int RPL>
+template <typename T, int N, int M, int RPL, int RB_STAGES, int RB_WARPS>
 __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
 {
-    using Gm = RbGeom<T, N, M, RPL>;
+    using Gm = RbGeom<T, N, M, RPL, RB_STAGES>;
     constexpr int G = Gm::G, FPW = Gm::FPW;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bars[RB_WARPS][RB_STAGES];
@@ -158,8 +159,10 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
         const T *sH = reinterpret_cast<const T *>(sb + Gm::OH) + fl * M * N;
         const T *sR = reinterpret_cast<const T *>(sb + Gm::OR_) + fl * M * M;
         const T *sz = reinterpret_cast<const T *>(sb + Gm::OZ) + fl * M;
-        T *ox = reinterpret_cast<T *>(outb) + fl * N;
-        T *oP = reinterpret_cast<T *>(outb + Gm::a16(Gm::XB)) + fl * N * N;
+        unsigned char *out_x = RB_STAGES > 1 ? outb : sb + Gm::OX;
+        unsigned char *out_P = RB_STAGES > 1 ? outb + Gm::a16(Gm::XB) : sb + Gm::OP;
+        T *ox = reinterpret_cast<T *>(out_x) + fl * N;
+        T *oP = reinterpret_cast<T *>(out_P) + fl * N * N;
         const int64_t f = tile * FPW + fl;
 
         // ---------------- predict: x' = F x ; P' = alpha^2 (F P) F' + Q -----------------------
@@ -356,8 +359,8 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
             }
         }
         // ---------------- posterior rows -> staging -> bulk TMA store ---------------------------
-        if (it > 0 && lane == 0) bulk_wait_read();          // the previous tile's stores have read the staging buffer
-        __syncwarp();
+        if (RB_STAGES > 1 && it > 0 && lane == 0) bulk_wait_read();   // the previous tile's stores have read the staging buffer
+        __syncwarp();                                       // every lane is done with P', (I-KH), K in the stage
         if (active) {
 #pragma unroll
             for (int i = 0; i < RPL; i++) {
@@ -371,9 +374,10 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
         __syncwarp();
         if (lane == 0) {
             const int64_t f0 = tile * FPW;
-            bulk_store(p.x_out + f0 * N, outb, Gm::XB);
-            bulk_store(p.P_out + f0 * N * N, outb + Gm::a16(Gm::XB), Gm::PB);
+            bulk_store(p.x_out + f0 * N, out_x, Gm::XB);
+            bulk_store(p.P_out + f0 * N * N, out_P, Gm::PB);
             bulk_commit();
+            if (RB_STAGES == 1) bulk_wait_read();           // the stores have read the stage: it may be refilled
             const int64_t nt = tile + RB_STAGES * wstride;
             if (nt < tiles) issue(nt, stage);
         }
@@ -382,10 +386,10 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
     if (lane == 0) bulk_wait_all();
 }
 
-template <typename T, int N, int M, int RPL>
+template <typename T, int N, int M, int RPL, int RB_STAGES, int RB_WARPS>
 int launch_rb(const bke_kf_args &a, cudaStream_t s)
 {
-    using Gm = RbGeom<T, N, M, RPL>;
+    using Gm = RbGeom<T, N, M, RPL, RB_STAGES>;
     const int64_t Nmain = (a.n_filters / Gm::FPW) * Gm::FPW;
     const int64_t rem = a.n_filters - Nmain;
     if (Nmain > 0) {
@@ -394,7 +398,7 @@ int launch_rb(const bke_kf_args &a, cudaStream_t s)
         p.x = (const T *)a.x; p.P = (const T *)a.P; p.F = (const T *)a.F; p.Q = (const T *)a.Q;
         p.H = (const T *)a.H; p.R = (const T *)a.R; p.z = (const T *)a.z;
         p.x_out = (T *)a.x_out; p.P_out = (T *)a.P_out; p.valid = a.z_valid; p.status = a.status;
-        auto kern = kf_rowblock_kernel<T, N, M, RPL>;
+        auto kern = kf_rowblock_kernel<T, N, M, RPL, RB_STAGES, RB_WARPS>;
         const int smem = RB_WARPS * Gm::WARP_BYTES;
         static bool configured[64] = {false};
         int dev = 0;
@@ -438,12 +442,16 @@ int launch_kf_rowblock(const bke_kf_args &a, cudaStream_t s)
     if (!(al16(a.x) && al16(a.P) && al16(a.F) && al16(a.Q) && al16(a.H) && al16(a.R) && al16(a.z) && al16(a.x_out) && al16(a.P_out)))
         return BKE_ERR_UNSUPPORTED;
     const int n = a.dim_x, m = a.dim_z;
+    // 9/3 fp64: one stage per warp and 8 warps per SM (two per scheduler: the FP64 pipe of one warp's
+    // dependent DFMA chains is covered by the other) beat a 2-stage ring with 4 warps; BKE_RB_RING=1
+    // selects the ring for comparison.
+    static const bool ring = getenv("BKE_RB_RING") && atoi(getenv("BKE_RB_RING")) != 0;
     if (a.dtype == BKE_F64) {
-        if (n == 9 && m == 3) return launch_rb<double, 9, 3, 3>(a, s);
-        if (n == 4 && m == 2) return launch_rb<double, 4, 2, 2>(a, s);
-        if (n == 6 && m == 3) return launch_rb<double, 6, 3, 3>(a, s);
+        if (n == 9 && m == 3) return ring ? launch_rb<double, 9, 3, 3, 2, 4>(a, s) : launch_rb<double, 9, 3, 3, 1, 8>(a, s);
+        if (n == 4 && m == 2) return launch_rb<double, 4, 2, 2, 2, 4>(a, s);
+        if (n == 6 && m == 3) return launch_rb<double, 6, 3, 3, 2, 4>(a, s);
     } else {
-        if (n == 6 && m == 3) return launch_rb<float, 6, 3, 3>(a, s);
+        if (n == 6 && m == 3) return launch_rb<float, 6, 3, 3, 2, 4>(a, s);
     }
     return BKE_ERR_UNSUPPORTED;
 }
