@@ -448,10 +448,10 @@ int launch_kf_rowblock(const bke_kf_args &a, cudaStream_t s)
     static const bool ring = getenv("BKE_RB_RING") && atoi(getenv("BKE_RB_RING")) != 0;
     if (a.dtype == BKE_F64) {
         if (n == 9 && m == 3) return ring ? launch_rb<double, 9, 3, 3, 2, 4>(a, s) : launch_rb<double, 9, 3, 3, 1, 8>(a, s);
-        if (n == 4 && m == 2) return launch_rb<double, 4, 2, 2, 2, 4>(a, s);
-        if (n == 6 && m == 3) return launch_rb<double, 6, 3, 3, 2, 4>(a, s);
+        if (n == 4 && m == 2) return ring ? launch_rb<double, 4, 2, 2, 2, 4>(a, s) : launch_rb<double, 4, 2, 2, 1, 8>(a, s);
+        if (n == 6 && m == 3) return ring ? launch_rb<double, 6, 3, 3, 2, 4>(a, s) : launch_rb<double, 6, 3, 3, 1, 8>(a, s);
     } else {
-        if (n == 6 && m == 3) return launch_rb<float, 6, 3, 3, 2, 4>(a, s);
+        if (n == 6 && m == 3) return ring ? launch_rb<float, 6, 3, 3, 2, 4>(a, s) : launch_rb<float, 6, 3, 3, 1, 8>(a, s);
     }
     return BKE_ERR_UNSUPPORTED;
 }

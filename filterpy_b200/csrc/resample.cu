@@ -867,8 +867,12 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain(Params p)
         }
     }
     if (bad) s_bad = 1;
+    __threadfence_block();
     __syncthreads();
-    if (threadIdx.x == 0 && s_bad) { ws.hdr->fallback = 1; ws.hdr->chain_bad = 1; }
+    if (threadIdx.x == 0) {
+        if (s_bad) { ws.hdr->fallback = 1; ws.hdr->chain_bad = 1; }
+        else if (p.cumsum_last) *p.cumsum_last = __longlong_as_double(ws.S_in[T]);    // exact sum after this call's particles
+    }
 }
 
 // ------------------------------------------------------------------ pass E: emit indexes
@@ -953,7 +957,6 @@ __device__ __forceinline__ void emit_tile(const Params &p, EmitShared &sm, int t
     }
     const int tile_cnt = sm.hi[pad32(TILE - 1)];            // outputs owned by this tile
     if (t == ws.T - 1 && tid == 0) {
-        if (p.cumsum_last) *p.cumsum_last = __longlong_as_double(ws.S_in[ws.T]);
         i64 O1 = tile_lo + tile_cnt;
         if (p.is_last && O1 < p.ng) {                       // resampling.py:145 would raise IndexError
             ws.hdr->overflow = (int)(p.ng - O1 > 0x7fffffff ? 0x7fffffff : p.ng - O1);
@@ -1281,7 +1284,7 @@ struct RunArgs {
     const double *carry_approx, *carry_exact;
     i64 *out_range;
     int is_last;
-    int phase;           // bit 0: passes A-C (need carry_approx), bit 1: passes D-G (need carry_exact)
+    int phase;           // bit 0: passes A-C (need carry_approx), bit 1: pass D chain (needs carry_exact), bit 2: passes E-G
 };
 
 int run(const RunArgs &a, cudaStream_t s)
@@ -1328,13 +1331,15 @@ int run(const RunArgs &a, cudaStream_t s)
         k_tile_maps<<<slow_grid, BLOCK, 0, s>>>(p);
     }
     if (a.phase & 2) {
+        if (a.U) k_chain<true><<<1, CHAIN_THREADS, 0, s>>>(p);
+        else k_chain<false><<<1, CHAIN_THREADS, 0, s>>>(p);
+    }
+    if (a.phase & 4) {
         const int fast_grid = T < sms * 2 ? T : sms * 2;
         if (a.U) {
-            k_chain<true><<<1, CHAIN_THREADS, 0, s>>>(p);
             k_emit_fast<true><<<fast_grid, BLOCK, emit_smem, s>>>(p);
             k_emit_slow<true><<<slow_grid, BLOCK, emit_smem, s>>>(p);
         } else {
-            k_chain<false><<<1, CHAIN_THREADS, 0, s>>>(p);
             k_emit_fast<false><<<fast_grid, BLOCK, emit_smem, s>>>(p);
             k_emit_slow<false><<<slow_grid, BLOCK, emit_smem, s>>>(p);
         }
@@ -1364,7 +1369,7 @@ static rs::RunArgs whole_array(int64_t n, const double *weights, double u, const
     rs::RunArgs a;
     a.n = n; a.ng = n; a.j0 = 0; a.cap = n; a.w = weights; a.U = U; a.u = u; a.idx = indexes;
     a.workspace = workspace; a.ws_bytes = workspace_bytes; a.info = info; a.cumsum_last = cumsum_last;
-    a.carry_approx = nullptr; a.carry_exact = nullptr; a.out_range = nullptr; a.is_last = 1; a.phase = 3;
+    a.carry_approx = nullptr; a.carry_exact = nullptr; a.out_range = nullptr; a.is_last = 1; a.phase = 7;
     return a;
 }
 
@@ -1384,7 +1389,7 @@ int bke_stratified_resample(int64_t n, const double *weights, const double *unif
 int bke_resample_shard(const bke_resample_shard_args *args, void *stream)
 {
     if (!args) { set_error("args is NULL"); return BKE_ERR_BAD_ARG; }
-    if (!(args->phase & 3)) { set_error("phase selects nothing"); return BKE_ERR_BAD_ARG; }
+    if (!(args->phase & 7)) { set_error("phase selects nothing"); return BKE_ERR_BAD_ARG; }
     rs::RunArgs a;
     a.n = args->n_local; a.ng = args->n_global; a.j0 = args->j_offset; a.cap = args->capacity;
     a.w = args->weights; a.U = args->uniforms; a.u = args->u; a.idx = args->indexes;

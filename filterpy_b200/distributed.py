@@ -61,7 +61,7 @@ def exclusive_prefix(value, group=None):
     return acc.reshape(value.shape)
 
 
-def sharded_systematic_resample(weights_local, u, group=None, capacity=None, uniforms=None):
+def sharded_systematic_resample(weights_local, u, group=None, capacity=None, uniforms=None, sizes=None):
     """Systematic (or, with ``uniforms`` = the replicated global U[N], stratified) resampling of a
     particle set whose weights are sharded contiguously over the ranks of ``group`` — one process
     per GPU, NCCL over NVLink.  Bit-identical to ``systematic_resample`` on the concatenated array.
@@ -84,11 +84,12 @@ def sharded_systematic_resample(weights_local, u, group=None, capacity=None, uni
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     n_local = int(weights_local.numel())
-    sizes = [None] * world
-    if world > 1:
-        dist.all_gather_object(sizes, n_local, group=group)
-    else:
-        sizes = [n_local]
+    if sizes is None:                                        # pass the shard sizes when they are known: saves a host gather
+        sizes = [None] * world
+        if world > 1:
+            dist.all_gather_object(sizes, n_local, group=group)
+        else:
+            sizes = [n_local]
     n_global = int(sum(sizes)); j_offset = int(sum(sizes[:rank]))
     cap = int(capacity) if capacity is not None else 2 * n_local + 1024
     ws_bytes = int(lib.bke_resample_workspace_bytes(n_local))
@@ -119,8 +120,10 @@ def sharded_systematic_resample(weights_local, u, group=None, capacity=None, uni
         dist.recv(carry_in, src=dist.get_global_rank(group, rank - 1) if group is not None else rank - 1, group=group)
         a.carry_exact = carry_in.data_ptr()
     a.phase = 2
-    _lib.check(lib.bke_resample_shard(ctypes.byref(a), stream_ptr(dev)))   # exact chain + emit
-    if rank < world - 1:
+    _lib.check(lib.bke_resample_shard(ctypes.byref(a), stream_ptr(dev)))   # exact chain: produces carry_out
+    if rank < world - 1:                                                   # the next rank can start its chain now
         dist.send(carry_out, dst=dist.get_global_rank(group, rank + 1) if group is not None else rank + 1, group=group)
+    a.phase = 4
+    _lib.check(lib.bke_resample_shard(ctypes.byref(a), stream_ptr(dev)))   # emit the indexes
     keep = (ws, carry_approx, carry_in, local_sum, sums)
     return idx, out_range, info, keep

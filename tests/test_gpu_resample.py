@@ -221,6 +221,8 @@ def test_sharded_resample_equals_whole_array(kind, shards):
         _lib.check(lib.bke_resample_shard(ctypes.byref(a), st))
         a.phase = 2
         _lib.check(lib.bke_resample_shard(ctypes.byref(a), st))
+        a.phase = 4
+        _lib.check(lib.bke_resample_shard(ctypes.byref(a), st))
         lo, hi = [int(v) for v in rng_t.cpu().numpy()]
         inf = info.cpu().numpy()
         assert inf[1] == 0 and inf[6] == 0, inf
