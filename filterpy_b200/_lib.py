@@ -24,6 +24,7 @@ EXPORTED_SYMBOLS = [
     "bke_resample_workspace_bytes", "bke_systematic_resample", "bke_stratified_resample",
     "bke_weights_sum", "bke_weights_scale", "bke_resample_shard",
     "bke_merwe_sigma_points", "bke_unscented_transform",
+    "bke_kf_rts_smoother", "bke_mm_probabilities", "bke_mm_mix", "bke_mm_estimate", "bke_cumsum_exact", "bke_searchsorted", "bke_multinomial_resample", "bke_gather_rows",
 ]
 
 
@@ -95,6 +96,35 @@ class ResampleShardArgs(ctypes.Structure):
     ]
 
 
+class RtsArgs(ctypes.Structure):
+    _fields_ = [
+        ("n_filters", c_int64), ("n_steps", c_int64),
+        ("dim_x", c_int32), ("dtype", c_int32), ("model_shift", c_int32), ("reserved", c_int32),
+        ("Xs", c_void_p), ("Ps", c_void_p),
+        ("F", c_void_p), ("F_stride", c_int64), ("F_step_stride", c_int64),
+        ("Q", c_void_p), ("Q_stride", c_int64), ("Q_step_stride", c_int64),
+        ("x_out", c_void_p), ("P_out", c_void_p), ("K", c_void_p), ("Pp", c_void_p),
+        ("status", c_void_p),
+    ]
+
+
+BKE_MM_MAX_MODELS = 8
+BKE_MM_MMAE = 1
+BKE_MM_FROM_MU = 2
+
+
+class MmArgs(ctypes.Structure):
+    _fields_ = [
+        ("n_tracks", c_int64),
+        ("dim_x", c_int32), ("n_models", c_int32), ("dtype", c_int32), ("flags", c_uint32),
+        ("x", c_void_p * BKE_MM_MAX_MODELS), ("P", c_void_p * BKE_MM_MAX_MODELS),
+        ("log_likelihood", c_void_p * BKE_MM_MAX_MODELS),
+        ("x_out", c_void_p * BKE_MM_MAX_MODELS), ("P_out", c_void_p * BKE_MM_MAX_MODELS),
+        ("mu", c_void_p), ("cbar", c_void_p), ("omega", c_void_p), ("trans", c_void_p),
+        ("weights_stride", c_int64),
+    ]
+
+
 class BkeError(RuntimeError):
     pass
 
@@ -149,6 +179,21 @@ def load():
     lib.bke_unscented_transform.argtypes = [c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                             c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
     lib.bke_unscented_transform.restype = ctypes.c_int
+    lib.bke_kf_rts_smoother.argtypes = [ctypes.POINTER(RtsArgs), c_void_p]
+    lib.bke_kf_rts_smoother.restype = ctypes.c_int
+    for name in ("bke_mm_probabilities", "bke_mm_mix", "bke_mm_estimate"):
+        getattr(lib, name).argtypes = [ctypes.POINTER(MmArgs), c_void_p]
+        getattr(lib, name).restype = ctypes.c_int
+    lib.bke_cumsum_exact.argtypes = [c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_size_t, c_void_p, c_void_p]
+    lib.bke_cumsum_exact.restype = ctypes.c_int
+    lib.bke_searchsorted.argtypes = [c_int64, c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p]
+    lib.bke_searchsorted.restype = ctypes.c_int
+    lib.bke_multinomial_resample.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                             c_void_p, c_void_p]
+    lib.bke_multinomial_resample.restype = ctypes.c_int
+    lib.bke_gather_rows.argtypes = [c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
+                                    c_void_p]
+    lib.bke_gather_rows.restype = ctypes.c_int
     if lib.bke_abi_version() != 1:
         raise BkeError("libbke.so ABI version mismatch")
     _lib = lib

@@ -307,6 +307,8 @@ struct Params {
     int aligned16;         // weights pointer is 16-byte aligned
     int *info;             // user info[8] or NULL
     double *cumsum_last;   // or NULL
+    double *cumsum_out;    // non-NULL: write the exact np.cumsum(w) here instead of emitting indexes
+    int last_one;          // cumsum mode: store 1.0 as the last element (resampling.py:174)
     Ws ws;
 };
 
@@ -903,6 +905,22 @@ __device__ __forceinline__ void put_index(const Params &p, i64 o, int value)
     else p.ws.hdr->cap_overflow = 1;
 }
 
+// cumsum mode: the exact running sums leave as they are (each thread owns IPT consecutive elements = one 128-byte line)
+__device__ __forceinline__ void store_cumsum(const Params &p, int t, const i64 (&cbits)[IPT])
+{
+    const i64 j = (i64)t * TILE + (i64)threadIdx.x * IPT;
+    double *o = p.cumsum_out + j;
+    if (j + IPT <= p.n && (reinterpret_cast<uintptr_t>(o) & 15) == 0 && !(p.last_one && j + IPT == p.n)) {
+#pragma unroll
+        for (int k = 0; k < IPT; k += 2)
+            *reinterpret_cast<double2 *>(o + k) = make_double2(__longlong_as_double(cbits[k]), __longlong_as_double(cbits[k + 1]));
+    } else {
+#pragma unroll
+        for (int k = 0; k < IPT; k++)
+            if (j + k < p.n) o[k] = (p.last_one && j + k == p.n - 1) ? 1.0 : __longlong_as_double(cbits[k]);
+    }
+}
+
 // Common tail of the emit kernels: cbits[k] = exact c_j (bit pattern) of the thread's 8 elements.
 // Computes every element's output range end, then expands the tile's outputs through shared memory
 // (coalesced stores); particles copied >= BIGRUN times are queued for the fill kernel.
@@ -1102,6 +1120,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_emit_fast(Params p)
         const i64 ex = block_excl_scan_i64(acc, &total_d, sm.ts.shi);
 #pragma unroll
         for (int k = 0; k < IPT; k++) cbits[k] += S_in + ex;
+        if (p.cumsum_out) { store_cumsum(p, t, cbits); continue; }
         emit_tile<STRAT>(p, sm, t, S_in, cbits);
     }
 }
@@ -1176,6 +1195,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_emit_slow(Params p)
             }
             if (bad) ws.hdr->chain_bad = 2;      // cannot happen after pass D verified the tile; recorded for tests
         }
+        if (p.cumsum_out) { store_cumsum(p, t, cbits); __syncthreads(); continue; }
         emit_tile<STRAT>(p, sm, t, S_in, cbits);
     }
 }
@@ -1211,6 +1231,14 @@ __global__ void k_sequential(Params p)
         }
     };
     if (!ws.hdr->fallback) { write_info(ws.hdr->overflow, 0); return; }
+    if (p.cumsum_out) {                          // cumsum mode: np.cumsum, one add at a time
+        double c = 0.0;
+        for (i64 q = 0; q < p.n; q++) { c = (q == 0) ? p.w[0] : __dadd_rn(c, p.w[q]); p.cumsum_out[q] = c; }
+        if (p.cumsum_last) *p.cumsum_last = c;
+        if (p.last_one) p.cumsum_out[p.n - 1] = 1.0;
+        write_info(0, 1);
+        return;
+    }
     // resampling.py:141-149 — cumulative sum and two-pointer merge, one element at a time.
     // A shard starts from the exact running sum of the earlier shards and owns the positions from
     // count_below(carry) up to count_below(its last cumulative sum).
@@ -1274,6 +1302,54 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_sum_tiles(const double *tile_
     if (threadIdx.x == 0) *out = sh[0];
 }
 
+// ------------------------------------------------------------------ searchsorted / gather
+// np.searchsorted(a, keys, side): one key per thread.  The top levels of the search hit the same
+// few cache lines for every key (L2 / L1 resident); the last ~7 levels stay inside one 1 KB span.
+template <bool RIGHT>
+__global__ void __launch_bounds__(256) k_searchsorted(i64 n, const double *__restrict__ a, i64 nk,
+                                                      const double *__restrict__ keys, i64 *__restrict__ out)
+{
+    for (i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x; q < nk; q += (i64)gridDim.x * blockDim.x) {
+        const double key = keys[q];
+        i64 lo = 0, hi = n;
+        while (lo < hi) {
+            const i64 mid = lo + ((hi - lo) >> 1);
+            const double v = __ldg(a + mid);
+            const bool go_right = RIGHT ? !(key < v) : (v < key);
+            if (go_right) lo = mid + 1; else hi = mid;
+        }
+        out[q] = lo;
+    }
+}
+
+// dst[r, :] = src[idx[r], :] for rows of `cpr` chunks of type V (the particle gather that follows a
+// resample, docs/monte_carlo/resampling.rst:4-8).  Consecutive threads move consecutive chunks of a row.
+template <typename V, typename I>
+__global__ void __launch_bounds__(256) k_gather_rows(i64 n_out, i64 n_src, i64 cpr, const V *__restrict__ src,
+                                                     const I *__restrict__ idx, V *__restrict__ dst, int *err)
+{
+    const i64 total = n_out * cpr;
+    for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (i64)gridDim.x * blockDim.x) {
+        const i64 r = c / cpr, within = c - r * cpr;
+        const i64 j = (i64)idx[r];
+        if (j < 0 || j >= n_src) { if (err) *err = 1; continue; }
+        dst[c] = src[j * cpr + within];
+    }
+}
+
+template <typename V, typename I>
+int launch_gather(i64 n_out, i64 n_src, i64 row_bytes, const void *src, const void *idx, void *dst, int *err, cudaStream_t s)
+{
+    const i64 cpr = row_bytes / (i64)sizeof(V);
+    const i64 total = n_out * cpr;
+    i64 blocks = (total + 256 * 4 - 1) / (256 * 4);
+    const i64 cap = (i64)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    k_gather_rows<V, I><<<(unsigned)blocks, 256, 0, s>>>(n_out, n_src, cpr, (const V *)src, (const I *)idx, (V *)dst, err);
+    return check_cuda(cudaGetLastError(), "gather launch");
+}
+
 struct RunArgs {
     i64 n, ng, j0, cap;
     const double *w, *U;
@@ -1284,6 +1360,7 @@ struct RunArgs {
     const double *carry_approx, *carry_exact;
     i64 *out_range;
     int is_last;
+    double *cumsum_out; int last_one;
     int phase;           // bit 0: passes A-C (need carry_approx), bit 1: pass D chain (needs carry_exact), bit 2: passes E-G
 };
 
@@ -1293,7 +1370,7 @@ int run(const RunArgs &a, cudaStream_t s)
     if (n < 0 || a.ng < n || a.j0 < 0) { set_error("bad particle counts"); return BKE_ERR_BAD_ARG; }
     if (n == 0) return BKE_OK;
     if (a.ng >= ((i64)1 << 31)) { set_error("n must be < 2^31 (indexes are int32, resampling.py:141)"); return BKE_ERR_BAD_ARG; }
-    if (!a.w || !a.idx || !a.workspace) { set_error("weights, indexes and workspace must be non-NULL"); return BKE_ERR_BAD_ARG; }
+    if (!a.w || !(a.idx || a.cumsum_out) || !a.workspace) { set_error("weights, indexes and workspace must be non-NULL"); return BKE_ERR_BAD_ARG; }
     if (!a.U && !(a.u >= 0.0 && a.u < 1.0)) { set_error("u must be in [0, 1)"); return BKE_ERR_BAD_ARG; }
     const size_t need = carve(n, nullptr, nullptr);
     if (a.ws_bytes < need) { set_error("workspace too small: %zu < %zu", a.ws_bytes, need); return BKE_ERR_BAD_ARG; }
@@ -1303,6 +1380,7 @@ int run(const RunArgs &a, cudaStream_t s)
     p.w = a.w; p.n = n; p.ng = a.ng; p.j0 = a.j0; p.cap = a.cap; p.is_last = a.is_last;
     p.carry_approx = a.carry_approx; p.carry_exact = a.carry_exact; p.out_range = a.out_range;
     p.u = a.u; p.U = a.U; p.idx = a.idx; p.info = a.info; p.cumsum_last = a.cumsum_last;
+    p.cumsum_out = a.cumsum_out; p.last_one = a.last_one;
     // |exact sequential sum - approximate tree sum| <= (N + 4096) * 2^-53 relative (non-negative
     // terms), i.e. less than (N + 4096) ulps of the running sum; doubled, plus slack.
     p.eb = 2 * (a.ng + 4096) + (a.ng >> 4);
@@ -1370,6 +1448,7 @@ static rs::RunArgs whole_array(int64_t n, const double *weights, double u, const
     a.n = n; a.ng = n; a.j0 = 0; a.cap = n; a.w = weights; a.U = U; a.u = u; a.idx = indexes;
     a.workspace = workspace; a.ws_bytes = workspace_bytes; a.info = info; a.cumsum_last = cumsum_last;
     a.carry_approx = nullptr; a.carry_exact = nullptr; a.out_range = nullptr; a.is_last = 1; a.phase = 7;
+    a.cumsum_out = nullptr; a.last_one = 0;
     return a;
 }
 
@@ -1395,7 +1474,7 @@ int bke_resample_shard(const bke_resample_shard_args *args, void *stream)
     a.w = args->weights; a.U = args->uniforms; a.u = args->u; a.idx = args->indexes;
     a.workspace = args->workspace; a.ws_bytes = args->workspace_bytes; a.info = args->info; a.cumsum_last = args->carry_out;
     a.carry_approx = args->carry_approx; a.carry_exact = args->carry_exact; a.out_range = reinterpret_cast<rs::i64 *>(args->out_range);
-    a.is_last = args->is_last; a.phase = args->phase;
+    a.is_last = args->is_last; a.phase = args->phase; a.cumsum_out = nullptr; a.last_one = 0;
     if (a.j0 + a.n > a.ng) { set_error("shard exceeds the global particle count"); return BKE_ERR_BAD_ARG; }
     return rs::run(a, (cudaStream_t)stream);
 }
@@ -1428,6 +1507,59 @@ int bke_weights_scale(int64_t n, const double *weights, const double *divisor, d
     int64_t cap = (int64_t)sm_count() * 16;
     rs::k_scale<<<(unsigned)(blocks < cap ? blocks : cap), rs::BLOCK, 0, (cudaStream_t)stream>>>(n, weights, divisor, weights_out);
     return check_cuda(cudaGetLastError(), "weights_scale launch");
+}
+
+int bke_cumsum_exact(int64_t n, const double *weights, double *cumsum_out, int32_t last_one, void *workspace,
+                     size_t workspace_bytes, int32_t *info, void *stream)
+{
+    if (n > 0 && !cumsum_out) { set_error("cumsum_out is NULL"); return BKE_ERR_BAD_ARG; }
+    rs::RunArgs a = whole_array(n, weights, 0.0, nullptr, nullptr, workspace, workspace_bytes, info, nullptr);
+    a.cumsum_out = cumsum_out; a.last_one = last_one ? 1 : 0;
+    return rs::run(a, (cudaStream_t)stream);
+}
+
+int bke_searchsorted(int64_t n, const double *sorted, int64_t n_keys, const double *keys, int32_t side_right,
+                     int64_t *indexes, void *stream)
+{
+    if (n < 0 || n_keys < 0) { set_error("negative length"); return BKE_ERR_BAD_ARG; }
+    if (n_keys == 0) return BKE_OK;
+    if ((n > 0 && !sorted) || !keys || !indexes) { set_error("NULL argument"); return BKE_ERR_BAD_ARG; }
+    int64_t blocks = (n_keys + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 32;
+    if (blocks > cap) blocks = cap;
+    if (side_right) rs::k_searchsorted<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(n, sorted, n_keys, keys, (rs::i64 *)indexes);
+    else rs::k_searchsorted<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(n, sorted, n_keys, keys, (rs::i64 *)indexes);
+    return check_cuda(cudaGetLastError(), "searchsorted launch");
+}
+
+int bke_multinomial_resample(int64_t n, const double *weights, const double *uniforms, int64_t *indexes,
+                             double *cumsum_scratch, void *workspace, size_t workspace_bytes, int32_t *info,
+                             void *stream)
+{
+    if (n < 0) { set_error("n < 0"); return BKE_ERR_BAD_ARG; }
+    if (n == 0) return BKE_OK;
+    if (!uniforms || !indexes || !cumsum_scratch) { set_error("NULL argument"); return BKE_ERR_BAD_ARG; }
+    int rc = bke_cumsum_exact(n, weights, cumsum_scratch, 1, workspace, workspace_bytes, info, stream);
+    if (rc != BKE_OK) return rc;
+    return bke_searchsorted(n, cumsum_scratch, n, uniforms, 0, indexes, stream);
+}
+
+int bke_gather_rows(int64_t n_out, int64_t n_src, int64_t row_bytes, const void *src, const void *indexes,
+                    int32_t index_is_64, void *dst, int32_t *err, void *stream)
+{
+    if (n_out < 0 || n_src < 0 || row_bytes <= 0) { set_error("bad sizes"); return BKE_ERR_BAD_ARG; }
+    if (n_out == 0) return BKE_OK;
+    if (!src || !indexes || !dst) { set_error("NULL argument"); return BKE_ERR_BAD_ARG; }
+    if (src == dst) { set_error("gather cannot run in place"); return BKE_ERR_BAD_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | (uintptr_t)row_bytes;
+#define BKE_GATHER(V) (index_is_64 ? rs::launch_gather<V, long long>(n_out, n_src, row_bytes, src, indexes, dst, err, s) \
+                                   : rs::launch_gather<V, int>(n_out, n_src, row_bytes, src, indexes, dst, err, s))
+    if ((al & 15) == 0) return BKE_GATHER(uint4);
+    if ((al & 7) == 0) return BKE_GATHER(uint2);
+    if ((al & 3) == 0) return BKE_GATHER(unsigned);
+    return BKE_GATHER(unsigned char);
+#undef BKE_GATHER
 }
 
 }  // extern "C"

@@ -148,8 +148,8 @@ __device__ __forceinline__ void slab_store(T *g, const T *slab, int cnt)
     for (int e = threadIdx.x; e < cnt * PER; e += UB) g[e] = slab[(e / PER) * PAD + (e % PER)];
 }
 
-template <typename T, int N, int M, int FX, int HX>
-__global__ void __launch_bounds__(UB) ukf_kernel(UkfP<T> p)
+template <typename T, int N, int M, int FX, int HX, int OCC>
+__global__ void __launch_bounds__(UB, OCC) ukf_kernel(UkfP<T> p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NS = 2 * N + 1;
@@ -415,7 +415,10 @@ int launch_inst(const bke_ukf_args &a, cudaStream_t s)
     size_t smem = sizeof(T) * SLABE;
     if (FX == BKE_FX_LINEAR) smem += sizeof(T) * (a.F_stride == 0 ? N * N : N * N * UB);
     if (HX == BKE_HX_LINEAR) smem += sizeof(T) * (a.H_stride == 0 ? M * N : M * N * UB);
-    auto kern = ukf_kernel<T, N, M, FX, HX>;
+    static const int occ_env = [] { const char *e = getenv("BKE_UKF_OCC"); return e ? atoi(e) : 0; }();
+    auto kern = ukf_kernel<T, N, M, FX, HX, 1>;
+    if (N >= 6 && occ_env == 3) kern = ukf_kernel<T, N, M, FX, HX, (N >= 6 ? 3 : 1)>;
+    if (N >= 6 && occ_env == 4) kern = ukf_kernel<T, N, M, FX, HX, (N >= 6 ? 4 : 1)>;
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
     int64_t grid = (p.N + UB - 1) / UB;
     kern<<<(unsigned)grid, UB, smem, s>>>(p);

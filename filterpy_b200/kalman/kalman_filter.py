@@ -2,8 +2,8 @@
 
 Same names, argument meaning and error behaviour as the reference
 (``filterpy/kalman/kalman_filter.py``: ``__init__`` :387-434, ``predict`` :437-482, ``update``
-:485-561, ``batch_filter`` :826-993; procedural ``predict`` :1571, ``update`` :1401,
-``batch_filter`` :1664), with one addition: a leading ``n_filters`` axis.  All arithmetic runs in
+:485-561, ``batch_filter`` :826-993, ``rts_smoother`` :995-1074; procedural ``predict`` :1571,
+``update`` :1401, ``batch_filter`` :1664, ``rts_smoother`` :1792), with one addition: a leading ``n_filters`` axis.  All arithmetic runs in
 the hand-written CUDA kernels behind the C-ABI (``include/bke.h``); this file only validates
 shapes, owns the device tensors and fills the argument structs.  There is no CPU fallback.
 
@@ -29,7 +29,7 @@ from .. import _lib
 from .._dev import StepGraph, bke_dtype, ptr, require_cuda, resolve_dtype, stream_ptr, to_dev
 from ..common.helpers import reshape_z
 
-__all__ = ["KalmanFilter", "predict", "update", "batch_filter"]
+__all__ = ["KalmanFilter", "predict", "update", "batch_filter", "rts_smoother"]
 
 
 class KalmanFilter(object):
@@ -155,6 +155,15 @@ class KalmanFilter(object):
             raise ValueError("P must have shape (%d,%d) or (%d,%d,%d)" % (n, n, self.n_filters, n, n))
         self._P = t.contiguous().clone()
         self._version += 1
+
+    def _adopt_state(self, x_t, P_t):
+        """Re-bind the state to caller-owned device tensors (no copy); returns the old pair so that a
+        caller (IMMEstimator's mixing step) can double-buffer."""
+        self._flush()
+        old = (self._x, self._P)
+        self._x, self._P = x_t, P_t
+        self._version += 1
+        return old
 
     def _mk_model_prop(name, rows_attr, cols_attr):  # noqa: N805
         priv = "_" + name
@@ -468,9 +477,83 @@ class KalmanFilter(object):
         return (means[:, 0].cpu().numpy().reshape(shp), covs[:, 0].cpu().numpy(),
                 means_p[:, 0].cpu().numpy().reshape(shp), covs_p[:, 0].cpu().numpy())
 
+    def rts_smoother(self, Xs, Ps, Fs=None, Qs=None, inv=None):
+        """Rauch-Tung-Striebel smoother over ``batch_filter``'s output (kalman_filter.py:995-1074).
+
+        Bank mode: ``Xs[T,N,n]``, ``Ps[T,N,n,n]`` (the ``means`` / ``covariances`` tensors
+        ``batch_filter`` returns) -> ``(x, P, K, Pp)`` tensors of the same layout.  Single mode:
+        NumPy ``Xs (T,n)`` or ``(T,n,1)``, ``Ps (T,n,n)`` like the reference.  ``Fs`` / ``Qs`` are
+        per-epoch lists (length T; step k uses entry k+1, :1068) or None = the filter's F / Q.
+        Only the default ``inv`` (np.linalg.inv) is offered on the GPU."""
+        if inv is not None and inv is not np.linalg.inv:
+            raise NotImplementedError("rts_smoother: only the default inv (np.linalg.inv) runs on the GPU")
+        if len(Xs) != len(Ps):
+            raise ValueError('length of Xs and Ps must be the same')
+        self._flush()
+        n, N = self.dim_x, self.n_filters
+        return _rts(self, Xs, Ps, Fs, Qs, 1, self._single, N, n)
+
     def __repr__(self):
         return "KalmanFilter bank (B200): n_filters=%d dim_x=%d dim_z=%d dtype=%s device=%s" % (
             self.n_filters, self.dim_x, self.dim_z, self._dtype, self._device)
+
+
+def _rts(kf, Xs, Ps, Fs, Qs, shift, single, N, n):
+    """Shared body of the two rts_smoother forms: fills bke_rts_args and launches."""
+    dtype, device = kf._dtype, kf._device
+    is_np = not isinstance(Xs, torch.Tensor)
+    Xt = to_dev(Xs, dtype, device)
+    Pt = to_dev(Ps, dtype, device)
+    T = Xt.shape[0]
+    col = False
+    if single:
+        col = Xt.dim() == 3 and Xt.shape[-1] == 1
+        Xt = Xt.reshape(T, 1, n)
+        Pt = Pt.reshape(T, 1, n, n)
+    if tuple(Xt.shape) != (T, N, n) or tuple(Pt.shape) != (T, N, n, n):
+        raise ValueError("Xs / Ps must have shapes (T,%d,%d) / (T,%d,%d,%d), got %s / %s"
+                         % (N, n, N, n, n, tuple(Xt.shape), tuple(Pt.shape)))
+    Xt = Xt.contiguous(); Pt = Pt.contiguous()
+
+    def model(lst, default, name):
+        """-> (tensor, per-filter stride, per-epoch stride)"""
+        if lst is None:
+            return default, KalmanFilter._stride(default), 0
+        if len(lst) != T:
+            raise ValueError("%s must have one entry per epoch (%d), got %d" % (name, T, len(lst)))
+        mats = [to_dev(m, dtype, device) for m in lst]
+        if any(m.shape[-2:] != (n, n) for m in mats):
+            raise ValueError("%s entries must be (%d,%d)" % (name, n, n))
+        batched = [m.dim() == 3 for m in mats]
+        if any(batched) and not all(batched):
+            mats = [m if m.dim() == 3 else m.expand(N, n, n) for m in mats]
+        t = torch.stack(mats).contiguous()               # (T,n,n) or (T,N,n,n)
+        if t.dim() == 4:
+            return t, n * n, N * n * n
+        return t, 0, n * n
+
+    Ft, sF, tF = model(Fs, kf._F, "Fs")
+    Qt, sQ, tQ = model(Qs, kf._Q, "Qs")
+    kw = dict(dtype=dtype, device=device)
+    x = torch.empty(T, N, n, **kw); P = torch.empty(T, N, n, n, **kw)
+    K = torch.empty(T, N, n, n, **kw); Pp = torch.empty(T, N, n, n, **kw)
+    status = torch.zeros(N, dtype=torch.int32, device=device)
+    a = _lib.RtsArgs()
+    a.n_filters, a.n_steps, a.dim_x, a.dtype, a.model_shift = N, T, n, bke_dtype(dtype), shift
+    a.Xs, a.Ps = ptr(Xt), ptr(Pt)
+    a.F, a.F_stride, a.F_step_stride = ptr(Ft), sF, tF
+    a.Q, a.Q_stride, a.Q_step_stride = ptr(Qt), sQ, tQ
+    a.x_out, a.P_out, a.K, a.Pp = ptr(x), ptr(P), ptr(K), ptr(Pp)
+    a.status = ptr(status)
+    with torch.cuda.device(device):
+        _lib.check(_lib.load().bke_kf_rts_smoother(a, stream_ptr(device)))
+    if not single:
+        return x, P, K, Pp
+    if int(status[0].item()) != 0:
+        raise np.linalg.LinAlgError("Singular matrix")
+    shp = (T, n, 1) if col else (T, n)
+    out = (x[:, 0].reshape(shp), P[:, 0], K[:, 0], Pp[:, 0])
+    return tuple(o.cpu().numpy() for o in out) if is_np else out
 
 
 # ---------------------------------------------------------------------- procedural form
@@ -569,3 +652,19 @@ def batch_filter(x, P, zs, Fs, Qs, Hs, Rs, Bs=None, us=None, update_first=False,
         us, Bs = None, None
     return kf.batch_filter(zs, Fs=list(Fs), Qs=list(Qs), Hs=[np.atleast_2d(h) for h in Hs], Rs=list(Rs),
                            Bs=Bs, us=us, update_first=update_first, saver=saver)
+
+
+def rts_smoother(Xs, Ps, Fs, Qs, dtype=np.float64, device=None):
+    """Procedural RTS smoother (kalman_filter.py:1792-1858) for ONE filter, run on the GPU.
+    ``Fs`` / ``Qs``: one (n,n) matrix, or a per-epoch list (step k uses entry k, :1852)."""
+    if len(Xs) != len(Ps):
+        raise ValueError('length of Xs and Ps must be the same')
+    Xa = np.asarray(Xs, dtype=np.float64)
+    n = Xa.shape[1]
+    T = Xa.shape[0]
+    kf = KalmanFilter(n, 1, dtype=dtype, device=device, diagnostics=False)
+
+    def per_epoch(m):
+        a = np.asarray(m, dtype=np.float64)
+        return [a] * T if a.ndim == 2 else list(m)
+    return _rts(kf, Xa, np.asarray(Ps, dtype=np.float64), per_epoch(Fs), per_epoch(Qs), 0, True, 1, n)

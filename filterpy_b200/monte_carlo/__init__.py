@@ -1,2 +1,3 @@
 """GPU mirrors of ``filterpy.monte_carlo`` for the hot path."""
-from .resampling import systematic_resample, stratified_resample, ResamplePlan, normalize_weights  # noqa: F401
+from .resampling import (systematic_resample, stratified_resample, multinomial_resample, residual_resample,  # noqa: F401
+                         gather_particles, exact_cumsum, ResamplePlan, normalize_weights)

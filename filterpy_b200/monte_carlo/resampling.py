@@ -1,5 +1,6 @@
-"""GPU mirrors of ``filterpy.monte_carlo.systematic_resample`` / ``stratified_resample``
-(filterpy/monte_carlo/resampling.py:117-150 / :80-114).
+"""GPU mirrors of ``filterpy.monte_carlo.systematic_resample`` / ``stratified_resample`` /
+``multinomial_resample`` (filterpy/monte_carlo/resampling.py:117-150 / :80-114 / :153-176) and the
+particle gather that follows them (docs/monte_carlo/resampling.rst:4-8).
 
 Same call, same result: ``indexes`` is the ``int32`` array the reference returns for the same
 weights and the same uniform draw(s) — bit for bit, because the CUDA path reproduces the strictly
@@ -16,7 +17,8 @@ from numpy.random import random
 from .. import _lib
 from .._dev import require_cuda, stream_ptr
 
-__all__ = ["systematic_resample", "stratified_resample", "ResamplePlan", "normalize_weights"]
+__all__ = ["systematic_resample", "stratified_resample", "multinomial_resample", "residual_resample",
+           "gather_particles", "exact_cumsum", "ResamplePlan", "normalize_weights"]
 
 
 class ResamplePlan(object):
@@ -63,6 +65,30 @@ class ResamplePlan(object):
                 self._info.data_ptr(), self.cumsum_last.data_ptr(), stream_ptr(self.device)))
         return out
 
+    def cumsum(self, weights, out=None, last_one=False):
+        """``np.cumsum(weights)`` bit for bit (sequential fp64 order), on the device."""
+        self._check_w(weights)
+        out = torch.empty(self.n, dtype=torch.float64, device=self.device) if out is None else out
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.bke_cumsum_exact(self.n, weights.data_ptr(), out.data_ptr(), int(bool(last_one)),
+                                                  self._ws_ptr, self.ws_bytes, self._info.data_ptr(),
+                                                  stream_ptr(self.device)))
+        return out
+
+    def multinomial(self, weights, uniforms, out=None, scratch=None):
+        """resampling.py:173-176 for the given uniforms: int64 indexes."""
+        self._check_w(weights)
+        if not (isinstance(uniforms, torch.Tensor) and uniforms.is_cuda and uniforms.dtype == torch.float64
+                and uniforms.is_contiguous() and uniforms.numel() == self.n):
+            raise ValueError("uniforms must be a contiguous float64 CUDA tensor of %d elements" % self.n)
+        out = torch.empty(self.n, dtype=torch.int64, device=self.device) if out is None else out
+        scratch = torch.empty(self.n, dtype=torch.float64, device=self.device) if scratch is None else scratch
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.bke_multinomial_resample(
+                self.n, weights.data_ptr(), uniforms.data_ptr(), out.data_ptr(), scratch.data_ptr(),
+                self._ws_ptr, self.ws_bytes, self._info.data_ptr(), stream_ptr(self.device)))
+        return out
+
     def info(self):
         """int32[8] on the host: [0] positions >= cumsum[-1] (the reference raises IndexError),
         [1] sequential-fallback used, [2] tiles with raw elements, [3] long runs, [4] chain flag."""
@@ -89,7 +115,7 @@ def normalize_weights(weights, plan=None):
     return out, total
 
 
-def _run(weights, stratified):
+def _weights_on_device(weights):
     is_torch = isinstance(weights, torch.Tensor)
     if is_torch and weights.is_cuda:
         w = weights.to(torch.float64).contiguous()
@@ -97,6 +123,11 @@ def _run(weights, stratified):
     else:
         dev = require_cuda(None)
         w = torch.from_numpy(np.ascontiguousarray(np.asarray(weights, dtype=np.float64))).to(dev)
+    return is_torch, w, dev
+
+
+def _run(weights, stratified):
+    is_torch, w, dev = _weights_on_device(weights)
     n = w.numel()
     if n == 0:
         if stratified:
@@ -122,3 +153,82 @@ def systematic_resample(weights):
 def stratified_resample(weights):
     """resampling.py:80-114 on the GPU."""
     return _run(weights, True)
+
+
+def multinomial_resample(weights):
+    """resampling.py:153-176 on the GPU: ``searchsorted(cumsum(w) with [-1] = 1, random(N))``.
+    Returns int64 indexes (what ``np.searchsorted`` returns), ndarray or CUDA tensor like the input."""
+    is_torch, w, dev = _weights_on_device(weights)
+    n = w.numel()
+    if n == 0:
+        np.cumsum(np.zeros(0))[-1:]                       # the reference fails on cumulative_sum[-1] (:174)
+        raise IndexError("index -1 is out of bounds for axis 0 with size 0")
+    plan = ResamplePlan(n, dev)
+    U = torch.from_numpy(np.atleast_1d(random(n))).to(dev)   # resampling.py:176
+    idx = plan.multinomial(w, U)
+    return idx if is_torch else idx.cpu().numpy()
+
+
+def residual_resample(weights):
+    """resampling.py:27-76 is NOT offered: it forms ``residual = weights - num_copies`` (:69), which is
+    negative for every particle with N*w >= 1, so its cumulative sum is not monotone and the result of
+    ``np.searchsorted`` on it (:74) depends on NumPy's probing order and on the previous key — there
+    is no algorithm-level answer to be bit-exact against."""
+    raise NotImplementedError("residual_resample: the reference's result is implementation-defined "
+                              "(searchsorted over a non-monotone array, resampling.py:69-74)")
+
+
+def exact_cumsum(weights, last_one=False):
+    """``np.cumsum(weights)`` (fp64, strictly sequential order) computed on the GPU, bit for bit."""
+    is_torch, w, dev = _weights_on_device(weights)
+    if w.numel() == 0:
+        return w.clone() if is_torch else np.zeros(0)
+    out = ResamplePlan(w.numel(), dev).cumsum(w, last_one=last_one)
+    return out if is_torch else out.cpu().numpy()
+
+
+def gather_particles(particles, indexes, out=None, check=True):
+    """``particles[indexes]`` along axis 0 on the GPU — the step after every resample
+    (docs/monte_carlo/resampling.rst:4-8: ``particles[:] = particles[indexes]``).
+
+    ``particles`` is (N, ...) of any dtype, ``indexes`` int32 or int64 (what the resamplers return);
+    NumPy in -> NumPy out, CUDA tensors in -> CUDA tensor out.  Raises IndexError for an index outside
+    [0, N) like NumPy does (negative indexes are not wrapped); ``check=False`` skips that test and the
+    host synchronisation it costs."""
+    lib = _lib.load()
+    is_torch = isinstance(particles, torch.Tensor)
+    if is_torch and particles.is_cuda:
+        dev = particles.device
+        src = particles.contiguous()
+    else:
+        dev = require_cuda(None)
+        src = torch.from_numpy(np.ascontiguousarray(np.asarray(particles))).to(dev)
+    if isinstance(indexes, torch.Tensor):
+        idx = indexes.to(dev)
+    else:
+        idx = torch.from_numpy(np.ascontiguousarray(np.asarray(indexes))).to(dev)
+    if idx.dtype not in (torch.int32, torch.int64):
+        raise IndexError("arrays used as indices must be of integer type")
+    idx = idx.contiguous().reshape(-1)
+    if src.dim() == 0:
+        raise IndexError("too many indices for array")
+    n_src = src.shape[0]
+    n_out = idx.numel()
+    row_bytes = (src.numel() // max(n_src, 1)) * src.element_size()
+    shape = (n_out,) + tuple(src.shape[1:])
+    if out is None:
+        out = torch.empty(shape, dtype=src.dtype, device=dev)
+    elif not (isinstance(out, torch.Tensor) and out.is_cuda and out.is_contiguous() and tuple(out.shape) == shape
+              and out.dtype == src.dtype):
+        raise ValueError("out must be a contiguous CUDA tensor of shape %s" % (shape,))
+    if n_out and row_bytes:
+        if n_src == 0:
+            raise IndexError("index out of bounds for axis 0 with size 0")
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.bke_gather_rows(n_out, n_src, row_bytes, src.data_ptr(), idx.data_ptr(),
+                                           1 if idx.dtype == torch.int64 else 0, out.data_ptr(), err.data_ptr(),
+                                           stream_ptr(dev)))
+        if check and int(err.item()):
+            raise IndexError("index out of bounds for axis 0 with size %d" % n_src)
+    return out if (is_torch and particles.is_cuda) else out.cpu().numpy()

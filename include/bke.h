@@ -234,6 +234,86 @@ int bke_weights_sum(int64_t n, const double *weights, double *sum_out, void *wor
 int bke_weights_scale(int64_t n, const double *weights, const double *divisor, double *weights_out,
                       void *stream);
 
+/* ---- RTS smoother over batch_filter's outputs ----------------------------
+ *
+ * KalmanFilter.rts_smoother filterpy/kalman/kalman_filter.py:995-1074 and the procedural
+ * rts_smoother :1792-1858 for a bank: Xs[T,N,n], Ps[T,N,n,n] are batch_filter's `means` and
+ * `covariances`; outputs x_out[T,N,n], P_out[T,N,n,n], K[T,N,n,n], Pp[T,N,n,n] (K, Pp may be NULL).
+ * The model of recursion step k is F[(k + model_shift) * F_step_stride + i * F_stride] — the method
+ * uses Fs[k+1] (:1068, model_shift = 1), the procedural form Fs[k] (:1852, model_shift = 0);
+ * step strides of 0 mean one model for every epoch, filter strides of 0 one model for the bank.
+ * status[i] = BKE_STATUS_SINGULAR_S where np.linalg.inv(Pp) would raise. */
+typedef struct {
+    int64_t n_filters, n_steps;
+    int32_t dim_x, dtype;
+    int32_t model_shift, reserved;
+    const void *Xs, *Ps;
+    const void *F; int64_t F_stride, F_step_stride;
+    const void *Q; int64_t Q_stride, Q_step_stride;
+    void *x_out, *P_out, *K, *Pp;
+    int32_t *status;
+} bke_rts_args;
+
+int bke_kf_rts_smoother(const bke_rts_args *args, void *stream);
+
+/* ---- bank-level model mixing: IMMEstimator / MMAEFilterBank ------------
+ *
+ * N tracks, each followed by the same n_models filters; model j's states are the bank arrays
+ * x[j][N,n], P[j][N,n,n] (dtype), its per-track log-likelihoods log_likelihood[j][N] (dtype, what
+ * bke_kf_step writes).  mu[N,M], cbar[N,M], omega[N,M,M], trans[M,M] are fp64.
+ *   bke_mm_probabilities  filterpy/kalman/IMM.py:178-184 and :239-247: mu = cbar * L, normalised;
+ *                         cbar = mu . trans; omega[i,j] = trans[i,j] mu[i] / cbar[j], with
+ *                         L = exp(log_likelihood) floored at DBL_MIN (kalman_filter.py:1213-1223).
+ *                         With BKE_MM_MMAE: mu = mu * L, normalised (filterpy/kalman/mmae.py:180-184).
+ *   bke_mm_mix            IMM.py:201-213: x_out[i], P_out[i] = mixed initial conditions of model i
+ *                         from omega (weights_stride = M*M per track, 0 = one omega for the bank).
+ *   bke_mm_estimate       IMM.py:228-237: x_out[0], P_out[0] = combined estimate from mu
+ *                         (weights_stride = M per track, 0 = shared).  With BKE_MM_MMAE the covariance
+ *                         follows mmae.py:197-199 literally: term j uses y = x_j - x[j] (component j of
+ *                         the mixed state, a scalar) and only min(dim_x, M) terms are summed.
+ * Outputs must not alias inputs. */
+#define BKE_MM_MAX_MODELS 8
+#define BKE_MM_MMAE 1u
+#define BKE_MM_FROM_MU 2u   /* bke_mm_probabilities: keep mu as given (no likelihood step), only cbar and omega */
+typedef struct {
+    int64_t n_tracks;
+    int32_t dim_x, n_models, dtype;
+    uint32_t flags;
+    const void *x[BKE_MM_MAX_MODELS], *P[BKE_MM_MAX_MODELS];
+    const void *log_likelihood[BKE_MM_MAX_MODELS];
+    void *x_out[BKE_MM_MAX_MODELS], *P_out[BKE_MM_MAX_MODELS];
+    double *mu, *cbar, *omega;
+    const double *trans;
+    int64_t weights_stride;
+} bke_mm_args;
+
+int bke_mm_probabilities(const bke_mm_args *args, void *stream);
+int bke_mm_mix(const bke_mm_args *args, void *stream);
+int bke_mm_estimate(const bke_mm_args *args, void *stream);
+
+/* ---- the callers either side of a resample ------------------------------
+ *
+ * bke_cumsum_exact: cumsum_out[j] = np.cumsum(weights)[j] bit for bit (the strictly sequential fp64
+ *   accumulation, reproduced by the same parity-map scan as the resamplers); last_one != 0 stores 1.0
+ *   in the last element (filterpy/monte_carlo/resampling.py:174 `cumulative_sum[-1] = 1.`).
+ * bke_searchsorted: np.searchsorted(sorted, keys, side='left' | 'right') -> int64.
+ * bke_multinomial_resample: filterpy/monte_carlo/resampling.py:153-176 given the caller's uniforms
+ *   (`random(len(weights))`, :176); indexes are int64 like np.searchsorted's result; cumsum_scratch
+ *   is n doubles of device scratch.
+ * bke_gather_rows: dst[r, :] = src[indexes[r], :] for rows of row_bytes bytes — the
+ *   `particles[:] = particles[indexes]` that follows every resample (docs/monte_carlo/resampling.rst:4-8);
+ *   indexes int32 (systematic / stratified) or int64 (multinomial); *err is set to 1 if an index is
+ *   outside [0, n_src) (that row is left untouched).  src and dst must not alias. */
+int bke_cumsum_exact(int64_t n, const double *weights, double *cumsum_out, int32_t last_one, void *workspace,
+                     size_t workspace_bytes, int32_t *info, void *stream);
+int bke_searchsorted(int64_t n, const double *sorted, int64_t n_keys, const double *keys, int32_t side_right,
+                     int64_t *indexes, void *stream);
+int bke_multinomial_resample(int64_t n, const double *weights, const double *uniforms, int64_t *indexes,
+                             double *cumsum_scratch, void *workspace, size_t workspace_bytes, int32_t *info,
+                             void *stream);
+int bke_gather_rows(int64_t n_out, int64_t n_src, int64_t row_bytes, const void *src, const void *indexes,
+                    int32_t index_is_64, void *dst, int32_t *err, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,7 @@ Restates ``filterpy/kalman/kalman_filter.py`` (reference @ 3b51149):
 * ``KalmanFilter.update``   kalman_filter.py:485-561  (Joseph-form covariance update,
   ``np.linalg.inv`` for S)
 * ``KalmanFilter.batch_filter`` kalman_filter.py:826-993
+* ``KalmanFilter.rts_smoother`` kalman_filter.py:995-1074 and procedural ``rts_smoother`` :1792-1858
 
 Two flavours are provided:
 
@@ -150,3 +151,35 @@ def log_likelihood_bank(y, S):
     q = np.einsum("ni,nij,nj->n", y, SI, y)
     _, logdet = np.linalg.slogdet(S)
     return -0.5 * (q + logdet + m * np.log(2.0 * np.pi))
+
+
+def rts_smoother(Xs, Ps, Fs, Qs, shift=1):
+    """kalman_filter.py:1056-1074 (method, step k uses Fs[k+1]: shift=1) and :1840-1858 (procedural,
+    Fs[k]: shift=0), literal; Xs (T,n) or (T,n,1), Ps (T,n,n), Fs/Qs lists of length T."""
+    if len(Xs) != len(Ps):
+        raise ValueError('length of Xs and Ps must be the same')
+    n = Xs.shape[0]
+    dim_x = Xs.shape[1]
+    K = np.zeros((n, dim_x, dim_x))
+    x, P, Pp = Xs.copy(), Ps.copy(), Ps.copy()
+    for k in range(n - 2, -1, -1):
+        F, Q = Fs[k + shift], Qs[k + shift]
+        Pp[k] = np.dot(np.dot(F, P[k]), F.T) + Q
+        K[k] = np.dot(np.dot(P[k], F.T), np.linalg.inv(Pp[k]))
+        x[k] += np.dot(K[k], x[k + 1] - np.dot(F, x[k]))
+        P[k] += np.dot(np.dot(K[k], P[k + 1] - Pp[k]), K[k].T)
+    return x, P, K, Pp
+
+
+def rts_smoother_bank(Xs, Ps, F, Q, shift=1):
+    """The same for a bank: Xs (T,N,n), Ps (T,N,n,n), F/Q (n,n) shared, (N,n,n) per filter,
+    (T,n,n) is NOT accepted here (pass lists through rts_smoother per filter)."""
+    T, N, n = Xs.shape
+    outs = [np.empty_like(Xs), np.empty_like(Ps), np.empty_like(Ps), np.empty_like(Ps)]
+    for i in range(N):
+        Fi = F[i] if np.ndim(F) == 3 else F
+        Qi = Q[i] if np.ndim(Q) == 3 else Q
+        r = rts_smoother(Xs[:, i], Ps[:, i], [Fi] * T, [Qi] * T, shift)
+        for o, v in zip(outs, r):
+            o[:, i] = v
+    return tuple(outs)

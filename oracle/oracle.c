@@ -8,6 +8,8 @@
  *        filterpy/monte_carlo/resampling.py:117-150 / :80-114
  *        (np.cumsum = strictly sequential fp64 adds, :142; two-pointer merge :143-149;
  *         positions = (u + i) / N, :139 and (U[i] + i) / N, :103)
+ *   oracle_multinomial_resample
+ *        filterpy/monte_carlo/resampling.py:173-176 (np.cumsum, cumulative_sum[-1] = 1., np.searchsorted side='left')
  *   oracle_kf_step_f64
  *        filterpy/kalman/kalman_filter.py:471-478 (predict) and :533-556 (update, Joseph form)
  *        S^-1 by Gauss-Jordan with partial pivoting (the reference calls np.linalg.inv ->
@@ -63,6 +65,21 @@ int oracle_stratified_resample(const double *w, int64_t N, const double *U, int3
     int rc = merge_positions(cs, N, pos, idx);
     free(cs); free(pos);
     return rc;
+}
+
+void oracle_multinomial_resample(const double *w, int64_t N, const double *U, int64_t nk, double *cs, int64_t *idx)
+{
+    if (N <= 0) return;
+    oracle_cumsum_f64(w, N, cs);
+    cs[N - 1] = 1.0;                           /* resampling.py:174 */
+    for (int64_t q = 0; q < nk; q++) {         /* np.searchsorted(cs, U[q]), side='left': #{j : cs[j] < key} for sorted cs */
+        int64_t lo = 0, hi = N;
+        while (lo < hi) {
+            int64_t mid = lo + ((hi - lo) >> 1);
+            if (cs[mid] < U[q]) lo = mid + 1; else hi = mid;
+        }
+        idx[q] = lo;
+    }
 }
 
 /* ---------------------------------------------------------------- linear KF, fp64 */

@@ -4,6 +4,7 @@ Restates ``filterpy/monte_carlo/resampling.py`` (reference @ 3b51149):
 
 * ``systematic_resample``  resampling.py:117-150
 * ``stratified_resample``  resampling.py:80-114
+* ``multinomial_resample`` resampling.py:153-176
 
 The reference draws its uniforms from the process-global legacy RandomState
 (resampling.py:24,103,139); here the uniform(s) are explicit arguments so that a
@@ -78,6 +79,35 @@ def stratified_resample_vec(weights, U):
     return resample_vec(weights, positions_stratified(len(weights), U))
 
 
+def multinomial_resample_vec(weights, U):
+    """resampling.py:173-176 with the uniforms ``random(len(weights))`` passed in."""
+    cumulative_sum = np.cumsum(weights)
+    cumulative_sum[-1] = 1.
+    return np.searchsorted(cumulative_sum, U)
+
+
+def multinomial_resample_loop(weights, U):
+    """The same with the cumulative sum and the left bisection spelled out (pure Python; small N)."""
+    N = len(weights)
+    c = [0.0] * N
+    acc = None
+    for j in range(N):
+        acc = float(weights[j]) if j == 0 else acc + float(weights[j])
+        c[j] = acc
+    c[-1] = 1.
+    out = np.zeros(len(U), np.int64)
+    for q, key in enumerate(U):
+        lo, hi = 0, N
+        while lo < hi:
+            mid = (lo + hi) // 2
+            if c[mid] < key:
+                lo = mid + 1
+            else:
+                hi = mid
+        out[q] = lo
+    return out
+
+
 # --------------------------------------------------------------------------- C port
 def _clib():
     from . import cbuild
@@ -111,4 +141,19 @@ def stratified_resample_c(weights, U):
         U.ctypes.data_as(ctypes.c_void_p), idx.ctypes.data_as(ctypes.c_void_p))
     if rc != 0:
         raise IndexError("index %d is out of bounds for axis 0 with size %d" % (N, N))
+    return idx
+
+
+def multinomial_resample_c(weights, U):
+    """oracle.c:oracle_multinomial_resample — sequential cumsum, last := 1, left bisection per key."""
+    import ctypes
+    lib = _clib()
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    U = np.ascontiguousarray(U, dtype=np.float64)
+    N = w.shape[0]
+    idx = np.empty(U.shape[0], dtype=np.int64)
+    scratch = np.empty(N, dtype=np.float64)
+    lib.oracle_multinomial_resample(
+        w.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(N), U.ctypes.data_as(ctypes.c_void_p),
+        ctypes.c_int64(U.shape[0]), scratch.ctypes.data_as(ctypes.c_void_p), idx.ctypes.data_as(ctypes.c_void_p))
     return idx

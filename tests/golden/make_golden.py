@@ -22,7 +22,8 @@ sys.path.insert(0, "/root/reference")
 
 from filterpy.kalman import KalmanFilter, UnscentedKalmanFilter, MerweScaledSigmaPoints  # noqa: E402
 from filterpy.kalman import predict as kf_predict_proc, update as kf_update_proc          # noqa: E402
-from filterpy.monte_carlo import systematic_resample, stratified_resample                # noqa: E402
+from filterpy.monte_carlo import systematic_resample, stratified_resample, multinomial_resample  # noqa: E402
+from filterpy.kalman import rts_smoother as rts_proc                                      # noqa: E402
 import filterpy                                                                            # noqa: E402
 
 from filterpy_b200.common import workloads as wl                                          # noqa: E402
@@ -200,8 +201,129 @@ def gen_resample():
     save("resample", meta=np.array(meta), known_sys=ka, known_str=ka_s, **cases)
 
 
+def gen_multinomial():
+    cases = {}
+    meta = []
+    i = 0
+    for kind in ["heavy", "uniform", "zeros", "degenerate", "dyadic"]:
+        for N in [1, 2, 7, 1000, 4097]:
+            w = wl.resample_weights(N, kind, seed=31 + N)
+            np.random.seed(100 + i)
+            idx = multinomial_resample(w)
+            np.random.seed(100 + i)
+            U = np.random.random(N)
+            cases["w%d" % i] = w; cases["U%d" % i] = U; cases["idx%d" % i] = idx
+            meta.append((i, N, 100 + i))
+            i += 1
+    save("resample_multinomial", meta=np.array(meta), **cases)
+
+
+# ----------------------------------------------------------------------------- RTS smoother
+def gen_rts():
+    out = {}
+    # (1) the C1 single filter: batch_filter then the method (Fs[k+1]) and the procedural form (Fs[k])
+    w = wl.kf_single_cv2d(T=200, seed=3)
+    kf = KalmanFilter(4, 2)
+    kf.x = w["x"].copy(); kf.P = w["P"].copy()
+    kf.F, kf.H, kf.Q, kf.R = w["F"], w["H"], w["Q"], w["R"]
+    means, covs, _, _ = kf.batch_filter(list(w["zs"]))
+    x, P, K, Pp = kf.rts_smoother(means, covs)
+    out.update(c1_F=w["F"], c1_Q=w["Q"], c1_means=means, c1_covs=covs, c1_x=x, c1_P=P, c1_K=K, c1_Pp=Pp)
+    # per-epoch models: F_k = CV with dt_k, Q_k scaled
+    rng = np.random.default_rng(11)
+    T = means.shape[0]
+    Fs, Qs = [], []
+    for k in range(T):
+        dt = rng.uniform(0.5, 1.5)
+        F = np.eye(4); F[0, 1] = dt; F[2, 3] = dt
+        Fs.append(F); Qs.append(w["Q"] * rng.uniform(0.5, 2.0))
+    xm, Pm, Km, Ppm = kf.rts_smoother(means, covs, Fs=Fs, Qs=Qs)
+    xp, Pq, Kp, Ppp = rts_proc(means, covs, Fs, Qs)
+    out.update(tv_Fs=np.array(Fs), tv_Qs=np.array(Qs), tv_method_x=xm, tv_method_P=Pm, tv_method_K=Km, tv_method_Pp=Ppm,
+               tv_proc_x=xp, tv_proc_P=Pq, tv_proc_K=Kp, tv_proc_Pp=Ppp)
+    # (2) small banks with per-filter models: 4/2, 2/1, 6/3 (generic kernel), column-vector x
+    for name, bank in [("b42", wl.kf_bank_cv2d(24, seed=21)), ("b93", wl.kf_bank_ca3d(6, seed=22))]:
+        N, n = bank["x"].shape
+        T = 30
+        m = bank["H"].shape[-2]
+        zs = np.random.default_rng(5).normal(size=(T, N, m)) + np.einsum("nij,nj->ni", bank["H"], bank["x"])[None]
+        Xs = np.zeros((T, N, n)); Ps = np.zeros((T, N, n, n))
+        sm = [np.zeros((T, N, n)), np.zeros((T, N, n, n)), np.zeros((T, N, n, n)), np.zeros((T, N, n, n))]
+        for i in range(N):
+            f = KalmanFilter(n, m)
+            f.x = bank["x"][i].copy(); f.P = bank["P"][i].copy()
+            f.F, f.H, f.Q, f.R = bank["F"][i], bank["H"][i], bank["Q"][i], bank["R"][i]
+            mu, cov, _, _ = f.batch_filter(list(zs[:, i]))
+            Xs[:, i] = mu; Ps[:, i] = cov
+            r = f.rts_smoother(mu, cov)
+            for o, v in zip(sm, r):
+                o[:, i] = v
+        out.update({name + "_F": bank["F"], name + "_Q": bank["Q"], name + "_Xs": Xs, name + "_Ps": Ps,
+                    name + "_x": sm[0], name + "_P": sm[1], name + "_K": sm[2], name + "_Pp": sm[3]})
+    save("rts", **out)
+
+
+# ----------------------------------------------------------------------------- IMM / MMAE
+def mm_models(n_tracks, seed):
+    """Two / three CV models (different process noise) per track, dim_x=4, dim_z=2, 1-D x."""
+    rng = np.random.default_rng(seed)
+    c = wl.kf_single_cv2d(T=1, seed=0)
+    x0 = rng.normal(size=(n_tracks, 4)) * 3
+    P0 = np.array([np.diag(rng.uniform(1, 5, 4)) for _ in range(n_tracks)])
+    qs = [0.05, 1.0, 8.0]
+    return dict(F=c["F"], H=c["H"], R=c["R"], Qs=np.array([c["Q"] * q for q in qs]), x0=x0, P0=P0)
+
+
+def gen_mm():
+    from filterpy.kalman import IMMEstimator, MMAEFilterBank
+    out = {}
+    T, NT = 25, 12
+    for nm in (2, 3):
+        mdl = mm_models(NT, 40 + nm)
+        rng = np.random.default_rng(7 + nm)
+        zs = rng.normal(size=(T, NT, 2)) * 2 + np.cumsum(rng.normal(size=(T, NT, 2)), axis=0)
+        trans = np.array([[0.9, 0.1], [0.2, 0.8]]) if nm == 2 else np.array([[.9, .05, .05], [.1, .8, .1], [.05, .15, .8]])
+        mu0 = np.array([0.6, 0.4]) if nm == 2 else np.array([0.5, 0.3, 0.2])
+        rec = {k: np.zeros((T, NT) + shp) for k, shp in [("x", (4,)), ("P", (4, 4)), ("mu", (nm,)), ("xp", (4,)), ("Pp", (4, 4)),
+                                                           ("fx", (nm, 4)), ("fP", (nm, 4, 4))]}
+        mrec = {k: np.zeros((T, NT) + shp) for k, shp in [("x", (4,)), ("P", (4, 4)), ("p", (nm,))]}
+        for t_ in range(NT):
+            def mk():
+                fs = []
+                for j in range(nm):
+                    f = KalmanFilter(4, 2)
+                    f.x = mdl["x0"][t_].copy() + j; f.P = mdl["P0"][t_].copy()
+                    f.F, f.H, f.R, f.Q = mdl["F"], mdl["H"], mdl["R"], mdl["Qs"][j]
+                    fs.append(f)
+                return fs
+            imm = IMMEstimator(mk(), mu0, trans)
+            if t_ == 0:
+                out["imm%d_init_x" % nm] = imm.x.copy(); out["imm%d_init_P" % nm] = imm.P.copy()
+                out["imm%d_init_omega" % nm] = imm.omega.copy(); out["imm%d_init_cbar" % nm] = imm.cbar.copy()
+            for k in range(T):
+                imm.predict()
+                rec["xp"][k, t_] = imm.x; rec["Pp"][k, t_] = imm.P
+                imm.update(zs[k, t_])
+                rec["x"][k, t_] = imm.x; rec["P"][k, t_] = imm.P; rec["mu"][k, t_] = imm.mu
+                for j, f in enumerate(imm.filters):
+                    rec["fx"][k, t_, j] = f.x; rec["fP"][k, t_, j] = f.P
+            bank = MMAEFilterBank(mk(), list(mu0), dim_x=4)
+            for k in range(T):
+                bank.predict()
+                bank.update(zs[k, t_])
+                mrec["x"][k, t_] = bank.x; mrec["P"][k, t_] = bank.P; mrec["p"][k, t_] = bank.p
+        out.update({"m%d_zs" % nm: zs, "m%d_trans" % nm: trans, "m%d_mu0" % nm: mu0, "m%d_F" % nm: mdl["F"], "m%d_H" % nm: mdl["H"],
+                    "m%d_R" % nm: mdl["R"], "m%d_Qs" % nm: mdl["Qs"][:nm], "m%d_x0" % nm: mdl["x0"], "m%d_P0" % nm: mdl["P0"]})
+        out.update({"imm%d_%s" % (nm, k): v for k, v in rec.items()})
+        out.update({"mmae%d_%s" % (nm, k): v for k, v in mrec.items()})
+    save("mm", **out)
+
+
 if __name__ == "__main__":
     gen_kf_c1()
     gen_kf_banks()
     gen_ukf()
     gen_resample()
+    gen_multinomial()
+    gen_rts()
+    gen_mm()

@@ -160,3 +160,83 @@ def test_live_reference_resample_and_kf():
         for t in range(2):
             kf.predict(); kf.update(b["zs"][t, f])
         close(x[f], kf.x, 1e-12); close(P[f], kf.P, 1e-12)
+
+
+# ------------------------------------------------------------------ §8f rows: multinomial resample, RTS smoother
+def test_multinomial_oracle_vs_reference_vectors(golden):
+    g = golden("resample_multinomial")
+    for (i, N, seed) in g["meta"]:
+        w, U, ref = g["w%d" % i], g["U%d" % i], g["idx%d" % i]
+        assert ref.dtype == np.int64
+        assert np.array_equal(ors.multinomial_resample_vec(w, U), ref)
+        assert np.array_equal(ors.multinomial_resample_c(w, U), ref)
+        if N <= 1000:
+            assert np.array_equal(ors.multinomial_resample_loop(w, U), ref)
+
+
+def test_rts_oracle_vs_reference_vectors(golden):
+    g = golden("rts")
+    T = g["c1_means"].shape[0]
+    out = okf.rts_smoother(g["c1_means"], g["c1_covs"], [g["c1_F"]] * T, [g["c1_Q"]] * T, shift=1)
+    for got, key in zip(out, ["c1_x", "c1_P", "c1_K", "c1_Pp"]):
+        close(got, g[key], rtol=1e-12, atol=1e-13)
+    for form, shift in [("method", 1), ("proc", 0)]:
+        out = okf.rts_smoother(g["c1_means"], g["c1_covs"], list(g["tv_Fs"]), list(g["tv_Qs"]), shift=shift)
+        for got, key in zip(out, ["x", "P", "K", "Pp"]):
+            close(got, g["tv_%s_%s" % (form, key)], rtol=1e-12, atol=1e-13)
+    for name in ["b42", "b93"]:
+        out = okf.rts_smoother_bank(g[name + "_Xs"], g[name + "_Ps"], g[name + "_F"], g[name + "_Q"])
+        for got, key in zip(out, ["x", "P", "K", "Pp"]):
+            close(got, g[name + "_" + key], rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree not present")
+def test_multinomial_and_rts_live_reference():
+    sys.path.insert(0, "/root/reference")
+    try:
+        from filterpy.monte_carlo import multinomial_resample
+        from filterpy.kalman import KalmanFilter
+    finally:
+        sys.path.remove("/root/reference")
+    rng = np.random.default_rng(0)
+    w = rng.random(5000) ** 3
+    w /= w.sum()
+    np.random.seed(9); ref = multinomial_resample(w)
+    np.random.seed(9); U = np.random.random(len(w))
+    assert np.array_equal(ors.multinomial_resample_c(w, U), ref)
+    from filterpy_b200.common import workloads as wl
+    c = wl.kf_single_cv2d(T=50, seed=2)
+    kf = KalmanFilter(4, 2)
+    kf.x = c["x"].copy(); kf.P = c["P"].copy(); kf.F, kf.H, kf.Q, kf.R = c["F"], c["H"], c["Q"], c["R"]
+    mu, cov, _, _ = kf.batch_filter(list(c["zs"]))
+    ref = kf.rts_smoother(mu, cov)
+    out = okf.rts_smoother(mu, cov, [c["F"]] * 50, [c["Q"]] * 50)
+    for a, b in zip(out, ref):
+        close(a, b, rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.parametrize("nm", [2, 3])
+def test_imm_and_mmae_oracle_vs_reference_vectors(golden, nm):
+    from oracle import imm as oimm
+    g = golden("mm")
+    zs = g["m%d_zs" % nm]
+    T, NT, _ = zs.shape
+
+    def mk(t_):
+        return [dict(x=g["m%d_x0" % nm][t_].copy() + j, P=g["m%d_P0" % nm][t_].copy(), F=g["m%d_F" % nm],
+                     H=g["m%d_H" % nm], R=g["m%d_R" % nm], Q=g["m%d_Qs" % nm][j]) for j in range(nm)]
+    for t_ in range(NT):
+        imm = oimm.Imm(mk(t_), g["m%d_mu0" % nm], g["m%d_trans" % nm])
+        if t_ == 0:
+            close(imm.x, g["imm%d_init_x" % nm]); close(imm.P, g["imm%d_init_P" % nm])
+            close(imm.omega, g["imm%d_init_omega" % nm]); close(imm.cbar, g["imm%d_init_cbar" % nm])
+        bank = oimm.Mmae(mk(t_), g["m%d_mu0" % nm])
+        for k in range(T):
+            imm.predict()
+            close(imm.x, g["imm%d_xp" % nm][k, t_]); close(imm.P, g["imm%d_Pp" % nm][k, t_])
+            imm.update(zs[k, t_])
+            close(imm.x, g["imm%d_x" % nm][k, t_]); close(imm.P, g["imm%d_P" % nm][k, t_])
+            close(imm.mu, g["imm%d_mu" % nm][k, t_], rtol=1e-8)
+            bank.predict(); bank.update(zs[k, t_])
+            close(bank.x, g["mmae%d_x" % nm][k, t_]); close(bank.P, g["mmae%d_P" % nm][k, t_])
+            close(bank.p, g["mmae%d_p" % nm][k, t_], rtol=1e-8, atol=1e-300)
