@@ -188,8 +188,8 @@ def load():
     lib.bke_cumsum_exact.restype = ctypes.c_int
     lib.bke_searchsorted.argtypes = [c_int64, c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p]
     lib.bke_searchsorted.restype = ctypes.c_int
-    lib.bke_multinomial_resample.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
-                                             c_void_p, c_void_p]
+    lib.bke_multinomial_resample.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_size_t, c_void_p, c_void_p]
     lib.bke_multinomial_resample.restype = ctypes.c_int
     lib.bke_gather_rows.argtypes = [c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
                                     c_void_p]

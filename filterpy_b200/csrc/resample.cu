@@ -1322,6 +1322,35 @@ __global__ void __launch_bounds__(256) k_searchsorted(i64 n, const double *__res
     }
 }
 
+// multinomial: np.searchsorted(cs, keys) (side='left') with a bracket from a lookup table.
+// lut[b] = #{j : c_j <= b / n} is a systematic resample with u = 0 of the same weights; a key in
+// [b/n, (b+1)/n) has its answer between lut[b-1] and lut[b+1], a span of a particle or two for
+// weights that are not degenerate.  The bracket is verified against cs and widened to the whole
+// array when it does not hold, so the result never depends on the table being right.
+__global__ void __launch_bounds__(256) k_searchsorted_lut(i64 n, const double *__restrict__ cs, const int *__restrict__ lut,
+                                                          const double *__restrict__ keys, i64 *__restrict__ out)
+{
+    const double nd = (double)n;
+    for (i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (i64)gridDim.x * blockDim.x) {
+        const double key = keys[q];
+        i64 lo = 0, hi = n;
+        if (key >= 0.0 && key < 1.0) {
+            i64 b = (i64)(key * nd);
+            if (b >= n) b = n - 1;
+            lo = b >= 2 ? (i64)__ldg(lut + b - 2) : 0;              // one bucket of slack for the rounding of key * n
+            hi = b + 2 < n ? (i64)__ldg(lut + b + 2) : n;
+            if (lo > hi) { lo = 0; hi = n; }
+            if (lo > 0 && !(__ldg(cs + lo - 1) < key)) lo = 0;     // everything left of lo must be < key
+            if (hi < n && (__ldg(cs + hi) < key)) hi = n;          // cs[hi] must not be < key
+        }
+        while (lo < hi) {
+            const i64 mid = lo + ((hi - lo) >> 1);
+            if (__ldg(cs + mid) < key) lo = mid + 1; else hi = mid;
+        }
+        out[q] = lo;
+    }
+}
+
 // dst[r, :] = src[idx[r], :] for rows of `cpr` chunks of type V (the particle gather that follows a
 // resample, docs/monte_carlo/resampling.rst:4-8).  Consecutive threads move consecutive chunks of a row.
 template <typename V, typename I>
@@ -1533,15 +1562,24 @@ int bke_searchsorted(int64_t n, const double *sorted, int64_t n_keys, const doub
 }
 
 int bke_multinomial_resample(int64_t n, const double *weights, const double *uniforms, int64_t *indexes,
-                             double *cumsum_scratch, void *workspace, size_t workspace_bytes, int32_t *info,
-                             void *stream)
+                             double *cumsum_scratch, int32_t *lut_scratch, void *workspace, size_t workspace_bytes,
+                             int32_t *info, void *stream)
 {
     if (n < 0) { set_error("n < 0"); return BKE_ERR_BAD_ARG; }
     if (n == 0) return BKE_OK;
     if (!uniforms || !indexes || !cumsum_scratch) { set_error("NULL argument"); return BKE_ERR_BAD_ARG; }
     int rc = bke_cumsum_exact(n, weights, cumsum_scratch, 1, workspace, workspace_bytes, info, stream);
     if (rc != BKE_OK) return rc;
-    return bke_searchsorted(n, cumsum_scratch, n, uniforms, 0, indexes, stream);
+    if (!lut_scratch || n < 4096) return bke_searchsorted(n, cumsum_scratch, n, uniforms, 0, indexes, stream);
+    // bracket table: systematic resample with u = 0 (its overflow flag is irrelevant here: info is
+    // rewritten by nobody after this call, so keep the cumsum's info by passing NULL)
+    rc = bke_systematic_resample(n, weights, 0.0, lut_scratch, workspace, workspace_bytes, nullptr, nullptr, stream);
+    if (rc != BKE_OK) return rc;
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 32;
+    if (blocks > cap) blocks = cap;
+    rs::k_searchsorted_lut<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(n, cumsum_scratch, lut_scratch, uniforms, (rs::i64 *)indexes);
+    return check_cuda(cudaGetLastError(), "multinomial launch");
 }
 
 int bke_gather_rows(int64_t n_out, int64_t n_src, int64_t row_bytes, const void *src, const void *indexes,

@@ -123,6 +123,18 @@ __device__ __forceinline__ void apply_hx(const T (&s)[N], T (&h)[M], const T *Hs
     }
 }
 
+// position of (i, j), i <= j, in a packed upper triangle
+template <int N>
+__device__ __forceinline__ constexpr int tri_index(int i, int j) { return i * N - i * (i - 1) / 2 + (j - i); }
+
+// true when sigma offset row k (non-zero in the components >= k) leaves every input of hx unchanged,
+// so hx(x +- U[k,:]) == hx(x) bit for bit
+template <int HX, int N>
+__device__ __forceinline__ constexpr bool hx_ignores_row(int k)
+{
+    return HX == BKE_HX_RANGE_AZ_EL ? k > 4 : (HX == BKE_HX_RANGE_BEARING ? k > 2 : false);
+}
+
 // compile-time loop over the 2N+1 sigma points
 template <int S, int END, typename Fn>
 __device__ __forceinline__ void for_sigma(Fn &&fn)
@@ -154,8 +166,10 @@ __global__ void __launch_bounds__(UB, OCC) ukf_kernel(UkfP<T> p)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NS = 2 * N + 1;
     constexpr int PADP = (N * N) | 1;                        // odd per-filter stride of the P / Q slab
-    constexpr int SLAB = (NS * M > PADP ? NS * M : PADP) * UB;
+    constexpr int NT = N * (N + 1) / 2;
+    constexpr int SLAB = (NS * M + NT > PADP ? NS * M + NT : PADP) * UB;
     T *zs = reinterpret_cast<T *>(smem_raw);                 // [NS*M][UB]; doubles as the staging slab for P, Q, P_out
+    T *park = zs + NS * M * UB;                              // [NT][UB]: the prior covariance while the update works
     T *Fs = zs + SLAB;                                       // [N*N] or [N*N][UB]
     const bool do_p = p.flags & BKE_DO_PREDICT, do_u = p.flags & BKE_DO_UPDATE;
     const int tid = threadIdx.x;
@@ -223,12 +237,12 @@ __global__ void __launch_bounds__(UB, OCC) ukf_kernel(UkfP<T> p)
 #pragma unroll
             for (int i = 0; i < N; i++) xm[i] += w * fs[i];
         });
-        // pass 2: covariance
+        // pass 2: covariance (upper triangle; mirrored when Q is added)
         T Pm[N][N];
 #pragma unroll
         for (int i = 0; i < N; i++)
 #pragma unroll
-            for (int j = 0; j < N; j++) Pm[i][j] = T(0);
+            for (int j = i; j < N; j++) Pm[i][j] = T(0);
         for_sigma<0, NS>([&](auto sc) {
             constexpr int S = decltype(sc)::value;
             T sp[N], fs[N];
@@ -242,14 +256,17 @@ __global__ void __launch_bounds__(UB, OCC) ukf_kernel(UkfP<T> p)
             for (int i = 0; i < N; i++) {
                 T wd = w * d[i];
 #pragma unroll
-                for (int j = 0; j < N; j++) Pm[i][j] += wd * d[j];
+                for (int j = i; j < N; j++) Pm[i][j] += wd * d[j];
             }
         });
 #pragma unroll
         for (int i = 0; i < N; i++) {
             x[i] = xm[i];
 #pragma unroll
-            for (int j = 0; j < N; j++) P[i][j] = Pm[i][j] + (q_dense ? zs[tl * PADP + i * N + j] : p.Q[i * N + j]);
+            for (int j = i; j < N; j++) {
+                P[i][j] = Pm[i][j] + (q_dense ? zs[tl * PADP + i * N + j] : p.Q[i * N + j]);
+                if (j > i) P[j][i] = Pm[i][j] + (q_dense ? zs[tl * PADP + j * N + i] : p.Q[j * N + i]);
+            }
         }
         if (live) {
             if (p.x_prior) for (int i = 0; i < N; i++) p.x_prior[f * N + i] = x[i];
@@ -261,21 +278,50 @@ __global__ void __launch_bounds__(UB, OCC) ukf_kernel(UkfP<T> p)
     if (do_u) {
         const bool has_z = (p.valid == nullptr) || (p.valid[fc] != 0);
         if (has_z && st == BKE_STATUS_OK) {
-            // sigma points regenerated from the prior (UKF.py:407)
-            T A[N][N];
+            // sigma points regenerated from the prior (UKF.py:407); scipy's cholesky reads the upper triangle
+            {
+                T A[N][N];
+#pragma unroll
+                for (int i = 0; i < N; i++)
+#pragma unroll
+                    for (int j = i; j < N; j++) A[i][j] = p.scale * P[i][j];
+                if (!chol_upper<T, N>(A, U)) st = BKE_STATUS_NOT_PD;
+            }
+            // P is not needed again until the posterior: park its upper triangle in shared memory and
+            // free the registers.  A (never expected) non-symmetric P keeps its lower triangle in P_out.
+            bool asym = false;
 #pragma unroll
             for (int i = 0; i < N; i++)
 #pragma unroll
-                for (int j = 0; j < N; j++) A[i][j] = p.scale * P[i][j];
-            if (!chol_upper<T, N>(A, U)) st = BKE_STATUS_NOT_PD;
+                for (int j = i; j < N; j++) {
+                    park[tri_index<N>(i, j) * UB + tid] = P[i][j];
+                    if (j > i) asym = asym || (P[j][i] != P[i][j]);
+                }
+            if (asym && live) {
+#pragma unroll
+                for (int i = 0; i < N; i++)
+#pragma unroll
+                    for (int j = 0; j < i; j++) p.P_out[f * N * N + i * N + j] = P[i][j];
+            }
             T zm[M];
 #pragma unroll
             for (int a = 0; a < M; a++) zm[a] = T(0);
+            T h0[M];                                         // hx of the mean point, reused by offsets that leave hx's inputs alone
             for_sigma<0, NS>([&](auto sc) {
                 constexpr int S = decltype(sc)::value;
-                T sp[N], h[M];
-                sigma_point<T, N, S>(x, U, sp);
-                apply_hx<T, N, M, HX>(sp, h, Hp, hstride);
+                T h[M];
+                if constexpr (S > 0 && hx_ignores_row<HX, N>((S - 1) % N)) {
+#pragma unroll
+                    for (int a = 0; a < M; a++) h[a] = h0[a];
+                } else {
+                    T sp[N];
+                    sigma_point<T, N, S>(x, U, sp);
+                    apply_hx<T, N, M, HX>(sp, h, Hp, hstride);
+                }
+                if constexpr (S == 0) {
+#pragma unroll
+                    for (int a = 0; a < M; a++) h0[a] = h[a];
+                }
                 const T w = (S == 0) ? p.wm0 : p.wi;
 #pragma unroll
                 for (int a = 0; a < M; a++) { zm[a] += w * h[a]; zs[(S * M + a) * UB + tid] = h[a]; }
@@ -285,17 +331,14 @@ __global__ void __launch_bounds__(UB, OCC) ukf_kernel(UkfP<T> p)
 #pragma unroll
             for (int a = 0; a < M; a++)
 #pragma unroll
-                for (int b = 0; b < M; b++) o.S[a][b] = T(0);
+                for (int b = a; b < M; b++) o.S[a][b] = T(0);
 #pragma unroll
             for (int i = 0; i < N; i++)
 #pragma unroll
                 for (int a = 0; a < M; a++) Pxz[i][a] = T(0);
             for_sigma<0, NS>([&](auto sc) {
                 constexpr int S = decltype(sc)::value;
-                T sp[N], dz[M], dx[N];
-                sigma_point<T, N, S>(x, U, sp);
-#pragma unroll
-                for (int i = 0; i < N; i++) dx[i] = sp[i] - x[i];
+                T dz[M];
 #pragma unroll
                 for (int a = 0; a < M; a++) dz[a] = zs[(S * M + a) * UB + tid] - zm[a];
                 const T w = (S == 0) ? p.wc0 : p.wi;
@@ -303,23 +346,34 @@ __global__ void __launch_bounds__(UB, OCC) ukf_kernel(UkfP<T> p)
                 for (int a = 0; a < M; a++) {
                     T wd = w * dz[a];
 #pragma unroll
-                    for (int b = 0; b < M; b++) o.S[a][b] += wd * dz[b];
+                    for (int b = a; b < M; b++) o.S[a][b] += wd * dz[b];
                 }
+                // dx = sigma - x is the sigma offset itself: row k of +-U, zero left of the diagonal
+                if constexpr (S > 0) {
+                    constexpr int k = (S - 1) % N;
+                    const T ws = (S <= N) ? w : -w;
 #pragma unroll
-                for (int i = 0; i < N; i++) {
-                    T wd = w * dx[i];
+                    for (int i = k; i < N; i++) {
+                        T wd = ws * U[k][i];
 #pragma unroll
-                    for (int a = 0; a < M; a++) Pxz[i][a] += wd * dz[a];
+                        for (int a = 0; a < M; a++) Pxz[i][a] += wd * dz[a];
+                    }
                 }
             });
             const T *Rf = p.R + fc * p.sR;
 #pragma unroll
             for (int a = 0; a < M; a++)
 #pragma unroll
-                for (int b = 0; b < M; b++) o.S[a][b] += Rf[a * M + b];
+                for (int b = a; b < M; b++) {
+                    const T sab = o.S[a][b];
+                    o.S[a][b] = sab + Rf[a * M + b];
+                    if (b > a) o.S[b][a] = sab + Rf[b * M + a];
+                }
             o.ok = reg_inverse<T, M>(o.S, o.SI, o.logdet);
             if (!o.ok) st = BKE_STATUS_SINGULAR_S;
-            if (o.ok && st == BKE_STATUS_OK) {
+            const bool good = o.ok && st == BKE_STATUS_OK;
+            T SK[M][N];
+            if (good) {
 #pragma unroll
                 for (int i = 0; i < N; i++)
 #pragma unroll
@@ -338,26 +392,7 @@ __global__ void __launch_bounds__(UB, OCC) ukf_kernel(UkfP<T> p)
                     for (int a = 0; a < M; a++) s += o.K[i][a] * o.y[a];
                     x[i] = s;
                 }
-                // P = P - K (S K')
-                T SK[M][N];
-#pragma unroll
-                for (int a = 0; a < M; a++)
-#pragma unroll
-                    for (int j = 0; j < N; j++) {
-                        T s = o.S[a][0] * o.K[j][0];
-#pragma unroll
-                        for (int b = 1; b < M; b++) s += o.S[a][b] * o.K[j][b];
-                        SK[a][j] = s;
-                    }
-#pragma unroll
-                for (int i = 0; i < N; i++)
-#pragma unroll
-                    for (int j = 0; j < N; j++) {
-                        T s = o.K[i][0] * SK[0][j];
-#pragma unroll
-                        for (int a = 1; a < M; a++) s += o.K[i][a] * SK[a][j];
-                        P[i][j] -= s;
-                    }
+                // optional outputs leave now, while S, SI, y are still in registers
                 if (live) {
                     if (p.K) for (int i = 0; i < N; i++) for (int a = 0; a < M; a++) p.K[f * N * M + i * M + a] = o.K[i][a];
                     if (p.y) for (int a = 0; a < M; a++) p.y[f * M + a] = o.y[a];
@@ -375,6 +410,39 @@ __global__ void __launch_bounds__(UB, OCC) ukf_kernel(UkfP<T> p)
                         p.ll[f] = T(-0.5) * (q + o.logdet + T(M) * T(LOG_2PI));
                     }
                 }
+                // S K' for P = P - K (S K')
+#pragma unroll
+                for (int a = 0; a < M; a++)
+#pragma unroll
+                    for (int j = 0; j < N; j++) {
+                        T s = o.S[a][0] * o.K[j][0];
+#pragma unroll
+                        for (int b = 1; b < M; b++) s += o.S[a][b] * o.K[j][b];
+                        SK[a][j] = s;
+                    }
+            }
+            // the prior covariance comes back from its parking place
+#pragma unroll
+            for (int i = 0; i < N; i++)
+#pragma unroll
+                for (int j = i; j < N; j++) { P[i][j] = park[tri_index<N>(i, j) * UB + tid]; P[j][i] = P[i][j]; }
+            if (asym && live) {
+#pragma unroll
+                for (int i = 0; i < N; i++)
+#pragma unroll
+                    for (int j = 0; j < i; j++) P[i][j] = p.P_out[f * N * N + i * N + j];
+            }
+            if (good) {
+#pragma unroll
+                for (int i = 0; i < N; i++)
+#pragma unroll
+                    for (int j = i; j < N; j++) {
+                        T s = o.K[i][0] * SK[0][j];
+#pragma unroll
+                        for (int a = 1; a < M; a++) s += o.K[i][a] * SK[a][j];
+                        P[i][j] -= s;
+                        if (j > i) P[j][i] -= s;
+                    }
             }
         }
     }
@@ -411,14 +479,18 @@ int launch_inst(const bke_ukf_args &a, cudaStream_t s)
     p.K = (T *)a.K; p.y = (T *)a.y; p.S = (T *)a.S; p.SI = (T *)a.SI; p.ll = (T *)a.log_likelihood;
     p.status = a.status;
     constexpr int PADP = (N * N) | 1;
-    constexpr int SLABE = ((2 * N + 1) * M > PADP ? (2 * N + 1) * M : PADP) * UB;
+    constexpr int SLABE = ((2 * N + 1) * M + N * (N + 1) / 2 > PADP ? (2 * N + 1) * M + N * (N + 1) / 2 : PADP) * UB;
     size_t smem = sizeof(T) * SLABE;
     if (FX == BKE_FX_LINEAR) smem += sizeof(T) * (a.F_stride == 0 ? N * N : N * N * UB);
     if (HX == BKE_HX_LINEAR) smem += sizeof(T) * (a.H_stride == 0 ? M * N : M * N * UB);
+    // resident CTAs per SM the kernel is compiled for (registers are capped accordingly): measured best
+    // for n = 6 is 3 in fp64 (168 registers, ~300 B spilled to L1) and 4 in fp32 (128 registers, no spill)
     static const int occ_env = [] { const char *e = getenv("BKE_UKF_OCC"); return e ? atoi(e) : 0; }();
+    constexpr int OCC_DEFAULT = N >= 6 ? (sizeof(T) == 8 ? 3 : 4) : 1;
+    const int occ = (occ_env >= 1 && occ_env <= 4 && N >= 6) ? occ_env : OCC_DEFAULT;
     auto kern = ukf_kernel<T, N, M, FX, HX, 1>;
-    if (N >= 6 && occ_env == 3) kern = ukf_kernel<T, N, M, FX, HX, (N >= 6 ? 3 : 1)>;
-    if (N >= 6 && occ_env == 4) kern = ukf_kernel<T, N, M, FX, HX, (N >= 6 ? 4 : 1)>;
+    if (occ == 3) kern = ukf_kernel<T, N, M, FX, HX, (N >= 6 ? 3 : 1)>;
+    if (occ == 4) kern = ukf_kernel<T, N, M, FX, HX, (N >= 6 ? 4 : 1)>;
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
     int64_t grid = (p.N + UB - 1) / UB;
     kern<<<(unsigned)grid, UB, smem, s>>>(p);

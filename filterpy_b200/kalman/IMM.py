@@ -64,7 +64,7 @@ class IMMEstimator(object):
         if mu.shape != (nt, nm):
             raise ValueError("mu must have shape (%d,) or (%d,%d)" % (nm, nt, nm))
         kw = dict(dtype=torch.float64, device=self._device)
-        self._mu = torch.from_numpy(np.ascontiguousarray(mu)).to(self._device)
+        self._mu = torch.from_numpy(np.array(mu, dtype=np.float64, order='C')).to(self._device)
         self._M = torch.from_numpy(np.ascontiguousarray(np.asarray(M, dtype=np.float64))).to(self._device)
         if tuple(self._M.shape) != (nm, nm):
             raise ValueError("M must have shape (%d,%d)" % (nm, nm))
@@ -103,8 +103,10 @@ class IMMEstimator(object):
 
     @property
     def likelihood(self):
-        lk = torch.stack([f.likelihood if not f._single else torch.tensor([f.likelihood]) for f in self.filters], dim=-1)
-        return lk if not self._single else lk[0].cpu().numpy()
+        """per-model likelihood of the last measurement (IMM.py:154, :174-176): (N, M), or (M,) for one track."""
+        if self._single:
+            return np.array([f.likelihood for f in self.filters])
+        return torch.stack([f.likelihood for f in self.filters], dim=-1)
 
     # ------------------------------------------------------------------ steps
     def _call(self, fn, a):

@@ -36,7 +36,7 @@ class MMAEFilterBank(object):
             pa = np.broadcast_to(pa, (nt, nm))
         if pa.shape != (nt, nm):
             raise ValueError("p must have shape (%d,) or (%d,%d)" % (nm, nt, nm))
-        self._p = torch.from_numpy(np.ascontiguousarray(pa)).to(self._device)
+        self._p = torch.from_numpy(np.array(pa, dtype=np.float64, order='C')).to(self._device)
         self._x = f0._x.clone(); self._P = f0._P.clone()          # mmae.py:118-121
         self.z = f0.z
         self._x_prior = self._x.clone(); self._P_prior = self._P.clone()

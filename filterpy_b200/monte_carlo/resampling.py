@@ -75,17 +75,19 @@ class ResamplePlan(object):
                                                   stream_ptr(self.device)))
         return out
 
-    def multinomial(self, weights, uniforms, out=None, scratch=None):
-        """resampling.py:173-176 for the given uniforms: int64 indexes."""
+    def multinomial(self, weights, uniforms, out=None, scratch=None, lut=True):
+        """resampling.py:173-176 for the given uniforms: int64 indexes.  ``lut=False`` runs the plain
+        bisection without the bracket table (same result)."""
         self._check_w(weights)
         if not (isinstance(uniforms, torch.Tensor) and uniforms.is_cuda and uniforms.dtype == torch.float64
                 and uniforms.is_contiguous() and uniforms.numel() == self.n):
             raise ValueError("uniforms must be a contiguous float64 CUDA tensor of %d elements" % self.n)
         out = torch.empty(self.n, dtype=torch.int64, device=self.device) if out is None else out
         scratch = torch.empty(self.n, dtype=torch.float64, device=self.device) if scratch is None else scratch
+        lut_ptr = self.indexes.data_ptr() if lut else None           # the plan's int32[n] doubles as the table
         with torch.cuda.device(self.device):
             _lib.check(self._lib.bke_multinomial_resample(
-                self.n, weights.data_ptr(), uniforms.data_ptr(), out.data_ptr(), scratch.data_ptr(),
+                self.n, weights.data_ptr(), uniforms.data_ptr(), out.data_ptr(), scratch.data_ptr(), lut_ptr,
                 self._ws_ptr, self.ws_bytes, self._info.data_ptr(), stream_ptr(self.device)))
         return out
 

@@ -299,7 +299,9 @@ int bke_mm_estimate(const bke_mm_args *args, void *stream);
  * bke_searchsorted: np.searchsorted(sorted, keys, side='left' | 'right') -> int64.
  * bke_multinomial_resample: filterpy/monte_carlo/resampling.py:153-176 given the caller's uniforms
  *   (`random(len(weights))`, :176); indexes are int64 like np.searchsorted's result; cumsum_scratch
- *   is n doubles of device scratch.
+ *   is n doubles of device scratch; lut_scratch is n int32 of device scratch (or NULL): with it every
+ *   bisection starts from a bracket looked up in a systematic resample (u = 0) of the same weights —
+ *   same result, ~10x less random DRAM traffic.
  * bke_gather_rows: dst[r, :] = src[indexes[r], :] for rows of row_bytes bytes — the
  *   `particles[:] = particles[indexes]` that follows every resample (docs/monte_carlo/resampling.rst:4-8);
  *   indexes int32 (systematic / stratified) or int64 (multinomial); *err is set to 1 if an index is
@@ -309,8 +311,8 @@ int bke_cumsum_exact(int64_t n, const double *weights, double *cumsum_out, int32
 int bke_searchsorted(int64_t n, const double *sorted, int64_t n_keys, const double *keys, int32_t side_right,
                      int64_t *indexes, void *stream);
 int bke_multinomial_resample(int64_t n, const double *weights, const double *uniforms, int64_t *indexes,
-                             double *cumsum_scratch, void *workspace, size_t workspace_bytes, int32_t *info,
-                             void *stream);
+                             double *cumsum_scratch, int32_t *lut_scratch, void *workspace, size_t workspace_bytes,
+                             int32_t *info, void *stream);
 int bke_gather_rows(int64_t n_out, int64_t n_src, int64_t row_bytes, const void *src, const void *indexes,
                     int32_t index_is_64, void *dst, int32_t *err, void *stream);
 

@@ -50,7 +50,15 @@ def test_exact_cumsum_and_multinomial_vs_oracle(kind, N):
     assert c1[-1] == 1.0 and np.array_equal(c1[:-1], c[:-1])
     U = np.random.default_rng(N).random(N)
     idx, info = gpu_multinomial(w, U)
-    assert np.array_equal(idx, ors.multinomial_resample_c(w, U))
+    ref = ors.multinomial_resample_c(w, U)
+    assert np.array_equal(idx, ref)
+    # the plain bisection (no bracket table) and keys at / outside the ends give the same answers
+    Ud = torch.from_numpy(U).cuda()
+    assert np.array_equal(plan.multinomial(wd, Ud, lut=False).cpu().numpy(), ref)
+    edge = U.copy()
+    edge[:6] = [0.0, np.nextafter(1.0, 0.0), c[0], c[N // 2], np.nextafter(c[N // 2], 1.0), 1e-300]
+    got = plan.multinomial(wd, torch.from_numpy(edge).cuda()).cpu().numpy()
+    assert np.array_equal(got, ors.multinomial_resample_c(w, edge))
 
 
 def test_multinomial_public_function_reproduces_reference_rng_stream(golden):
