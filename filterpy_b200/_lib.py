@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "bke_resample_workspace_bytes", "bke_systematic_resample", "bke_stratified_resample",
     "bke_weights_sum", "bke_weights_scale", "bke_resample_shard",
     "bke_merwe_sigma_points", "bke_unscented_transform",
-    "bke_kf_rts_smoother", "bke_mm_probabilities", "bke_mm_mix", "bke_mm_estimate", "bke_cumsum_exact", "bke_searchsorted", "bke_multinomial_resample", "bke_gather_rows",
+    "bke_kf_rts_smoother", "bke_ukf_rts_smoother", "bke_mm_probabilities", "bke_mm_mix", "bke_mm_estimate", "bke_cumsum_exact", "bke_searchsorted", "bke_multinomial_resample", "bke_gather_rows",
 ]
 
 
@@ -48,6 +48,7 @@ class KfArgs(ctypes.Structure):
         ("K", c_void_p), ("y", c_void_p), ("S", c_void_p), ("SI", c_void_p),
         ("log_likelihood", c_void_p),
         ("status", c_void_p),
+        ("F_host", c_void_p), ("Q_host", c_void_p), ("H_host", c_void_p), ("R_host", c_void_p),
     ]
 
 
@@ -104,6 +105,20 @@ class RtsArgs(ctypes.Structure):
         ("F", c_void_p), ("F_stride", c_int64), ("F_step_stride", c_int64),
         ("Q", c_void_p), ("Q_stride", c_int64), ("Q_step_stride", c_int64),
         ("x_out", c_void_p), ("P_out", c_void_p), ("K", c_void_p), ("Pp", c_void_p),
+        ("status", c_void_p),
+    ]
+
+
+class UkfRtsArgs(ctypes.Structure):
+    _fields_ = [
+        ("n_filters", c_int64), ("n_steps", c_int64),
+        ("dim_x", c_int32), ("dtype", c_int32), ("fx_model", c_int32), ("reserved", c_int32),
+        ("alpha", c_double), ("beta", c_double), ("kappa", c_double), ("dt", c_double),
+        ("dts", c_void_p),
+        ("Xs", c_void_p), ("Ps", c_void_p),
+        ("Q", c_void_p), ("Q_stride", c_int64),
+        ("F", c_void_p), ("F_stride", c_int64),
+        ("x_out", c_void_p), ("P_out", c_void_p), ("K", c_void_p),
         ("status", c_void_p),
     ]
 
@@ -181,6 +196,8 @@ def load():
     lib.bke_unscented_transform.restype = ctypes.c_int
     lib.bke_kf_rts_smoother.argtypes = [ctypes.POINTER(RtsArgs), c_void_p]
     lib.bke_kf_rts_smoother.restype = ctypes.c_int
+    lib.bke_ukf_rts_smoother.argtypes = [ctypes.POINTER(UkfRtsArgs), c_void_p]
+    lib.bke_ukf_rts_smoother.restype = ctypes.c_int
     for name in ("bke_mm_probabilities", "bke_mm_mix", "bke_mm_estimate"):
         getattr(lib, name).argtypes = [ctypes.POINTER(MmArgs), c_void_p]
         getattr(lib, name).restype = ctypes.c_int

@@ -59,11 +59,24 @@ __global__ void __launch_bounds__(128) kf_batch_kernel(BatchP<T> p)
     load_vec<T, M * N>(&H[0][0], p.H + f * p.sH);
     load_vec<T, M * M>(&R[0][0], p.R + f * p.sR);
     int st = BKE_STATUS_OK;
+    // the measurement of epoch t+1 is fetched while epoch t computes: one exposed DRAM latency per
+    // epoch was the dominant stall of the first version (long_scoreboard 7 per issue)
+    T zn[M];
+    bool has_zn = true;
+    if (p.Tn > 0) {
+        load_vec<T, M>(zn, p.zs + f * M);
+        has_zn = p.valid == nullptr || p.valid[f] != 0;
+    }
     for (int64_t t = 0; t < p.Tn; t++) {
         const int64_t tf = t * p.N + f;
         T z[M];
-        load_vec<T, M>(z, p.zs + tf * M);
-        const bool has_z = p.valid == nullptr || p.valid[tf] != 0;
+#pragma unroll
+        for (int a = 0; a < M; a++) z[a] = zn[a];
+        const bool has_z = has_zn;
+        if (t + 1 < p.Tn) {
+            load_vec<T, M>(zn, p.zs + (tf + p.N) * M);
+            has_zn = p.valid == nullptr || p.valid[tf + p.N] != 0;
+        }
         auto upd = [&]() {
             if (has_z) {
                 KfUpdateOut<T, N, M> o;

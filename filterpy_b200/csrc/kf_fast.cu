@@ -17,6 +17,7 @@
 // Reference arithmetic: filterpy/kalman/kalman_filter.py:471-478, 533-556 (see kf_regtile.cuh).
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 #include "bke_internal.cuh"
 #include "kf_regtile.cuh"
 
@@ -97,7 +98,7 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const CUtensorMap *map, i
 // ---------------------------------------------------------------------------- tile geometry
 constexpr int TILE = 128;       // filters per tile == threads per CTA
 
-template <typename T, int N, int M>
+template <typename T, int N, int M, bool SHARED = false>
 struct Stage {
     // byte sizes of one tile of each array
     static constexpr int XB = TILE * N * sizeof(T);
@@ -107,13 +108,14 @@ struct Stage {
     static constexpr int ZB = TILE * M * sizeof(T);
     // offsets (all 1024-byte aligned: swizzled TMA destinations need it)
     static constexpr int align_up(int v) { return (v + 1023) & ~1023; }
+    // (a bank that shares its models stages only P, x, z: a third of the bytes, so more stages and CTAs fit)
     static constexpr int OP = 0;
     static constexpr int OF = OP + align_up(PB);
-    static constexpr int OQ = OF + align_up(PB);
-    static constexpr int OH = OQ + align_up(PB);
-    static constexpr int OX = OH + align_up(HB);
+    static constexpr int OQ = OF + (SHARED ? 0 : align_up(PB));
+    static constexpr int OH = OQ + (SHARED ? 0 : align_up(PB));
+    static constexpr int OX = OH + (SHARED ? 0 : align_up(HB));
     static constexpr int OR_ = OX + align_up(XB);
-    static constexpr int OZ = OR_ + align_up(RB);
+    static constexpr int OZ = OR_ + (SHARED ? 0 : align_up(RB));
     static constexpr int BYTES = OZ + align_up(ZB);
 };
 
@@ -138,7 +140,9 @@ struct FastP {
     int num_tiles;
     int l2_hints;                   // 1: keep x, P in L2 between steps (evict_last), stream the rest (evict_first)
     float alpha_sq;
-    const float *F, *Q, *H, *R;     // used when SHARED
+    const float *F, *Q, *H, *R;     // used when SHARED == 1
+    float Fh[N * N], Qh[N * N], Hh[M * N], Rh[M * M];   // used when SHARED == 2: the shared models ride in the launch
+                                                        // parameters, so every product with them reads the constant bank
     float *x_out, *P_out;
     const uint8_t *valid;
     float *x_prior, *P_prior, *K, *y, *S, *SI, *ll;
@@ -146,12 +150,14 @@ struct FastP {
 };
 
 // MODE: 3 = predict+update, 1 = predict only, 2 = update only
-template <int MODE, bool SHARED, bool EXTRAS, int STAGES>
-__global__ void __launch_bounds__(TILE, 3)
+// SHARED: 0 = per-filter models (staged by TMA), 1 = one model for the bank read from device memory,
+// 2 = one model for the bank carried in the kernel parameters
+template <int MODE, int SHARED, bool EXTRAS, int STAGES>
+__global__ void __launch_bounds__(TILE, SHARED == 2 ? 5 : (SHARED ? 4 : 3))
 kf42_f32_kernel(const __grid_constant__ Maps maps, const FastP<4, 2> p)
 {
     constexpr int N = 4, M = 2;
-    using St = Stage<float, N, M>;
+    using St = Stage<float, N, M, SHARED != 0>;
     constexpr bool DO_P = MODE & 1, DO_U = MODE & 2;
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) uint64_t full[STAGES];
@@ -208,7 +214,20 @@ kf42_f32_kernel(const __grid_constant__ Maps maps, const FastP<4, 2> p)
     }
 
     float F[N][N], Q[N][N], H[M][N], R[M][M];
-    if (SHARED) {
+    if (SHARED == 2) {
+#pragma unroll
+        for (int i = 0; i < N; i++)
+#pragma unroll
+            for (int j = 0; j < N; j++) { F[i][j] = p.Fh[i * N + j]; Q[i][j] = p.Qh[i * N + j]; }
+#pragma unroll
+        for (int a = 0; a < M; a++) {
+#pragma unroll
+            for (int j = 0; j < N; j++) H[a][j] = p.Hh[a * N + j];
+#pragma unroll
+            for (int b = 0; b < M; b++) R[a][b] = p.Rh[a * M + b];
+        }
+    }
+    if (SHARED == 1) {
         if (DO_P) {
 #pragma unroll
             for (int i = 0; i < N; i++)
@@ -432,10 +451,10 @@ bool make_map_1d(CUtensorMap *m, const void *base, int64_t elems, int box_elems)
 }
 
 
-template <int MODE, bool SHARED, bool EXTRAS, int STAGES>
+template <int MODE, int SHARED, bool EXTRAS, int STAGES>
 int launch_variant_s(const Maps &maps, const FastP<4, 2> &p, cudaStream_t s, int ctas_per_sm)
 {
-    using St = Stage<float, 4, 2>;
+    using St = Stage<float, 4, 2, SHARED != 0>;
     auto kern = kf42_f32_kernel<MODE, SHARED, EXTRAS, STAGES>;
     const int smem = STAGES * St::BYTES;
     static bool configured[64] = {false};
@@ -451,12 +470,19 @@ int launch_variant_s(const Maps &maps, const FastP<4, 2> &p, cudaStream_t s, int
     return check_cuda(cudaGetLastError(), "kf42_f32_kernel launch");
 }
 
-template <int MODE, bool SHARED, bool EXTRAS>
+template <int MODE, int SHARED, bool EXTRAS>
 int launch_variant(const Maps &maps, const FastP<4, 2> &p, cudaStream_t s)
 {
-    static const int stages = env_int("BKE_KF_STAGES", 2);
-    static const int ctas = env_int("BKE_KF_CTAS", 3);
-    if (stages == 3) return launch_variant_s<MODE, SHARED, EXTRAS, 3>(maps, p, s, ctas > 2 ? 2 : ctas);
+    static const int stages_env = env_int("BKE_KF_STAGES", 0);
+    static const int ctas_env = env_int("BKE_KF_CTAS", 0);
+    if (SHARED) {      // 11 KB per stage
+        constexpr int MAXC = SHARED == 2 ? 5 : 4;
+        const int ctas = ctas_env > 0 ? (ctas_env > MAXC ? MAXC : ctas_env) : MAXC;
+        if (stages_env == 3) return launch_variant_s<MODE, SHARED, EXTRAS, 3>(maps, p, s, ctas);
+        return launch_variant_s<MODE, SHARED, EXTRAS, 2>(maps, p, s, ctas);
+    }
+    const int ctas = ctas_env > 0 ? ctas_env : 3;
+    if (stages_env == 3) return launch_variant_s<MODE, SHARED, EXTRAS, 3>(maps, p, s, ctas > 2 ? 2 : ctas);
     return launch_variant_s<MODE, SHARED, EXTRAS, 2>(maps, p, s, ctas > 3 ? 3 : ctas);
 }
 
@@ -517,14 +543,23 @@ int launch_kf_fast(const bke_kf_args &a, cudaStream_t s)
     p.valid = a.z_valid;
     p.x_prior = (float *)a.x_prior; p.P_prior = (float *)a.P_prior; p.K = (float *)a.K; p.y = (float *)a.y;
     p.S = (float *)a.S; p.SI = (float *)a.SI; p.ll = (float *)a.log_likelihood; p.status = a.status;
+    // host copies of the shared models (optional): carried in the launch parameters
+    static const int hostm_env = env_int("BKE_KF_HOST_MODELS", 1);
+    const bool host_models = hostm_env && all_shared && a.F_host && a.Q_host && a.H_host && a.R_host;
+    if (host_models) {
+        memcpy(p.Fh, a.F_host, sizeof(p.Fh)); memcpy(p.Qh, a.Q_host, sizeof(p.Qh));
+        memcpy(p.Hh, a.H_host, sizeof(p.Hh)); memcpy(p.Rh, a.R_host, sizeof(p.Rh));
+    }
     const bool extras = a.x_prior || a.P_prior || a.K || a.y || a.S || a.SI || a.log_likelihood || a.status;
 
 #define BKE_DISPATCH(MODE)                                                                   \
     do {                                                                                     \
-        if (all_shared) return extras ? launch_variant<MODE, true, true>(maps, p, s)         \
-                                      : launch_variant<MODE, true, false>(maps, p, s);       \
-        return extras ? launch_variant<MODE, false, true>(maps, p, s)                        \
-                      : launch_variant<MODE, false, false>(maps, p, s);                      \
+        if (host_models) return extras ? launch_variant<MODE, 2, true>(maps, p, s)           \
+                                       : launch_variant<MODE, 2, false>(maps, p, s);         \
+        if (all_shared) return extras ? launch_variant<MODE, 1, true>(maps, p, s)            \
+                                      : launch_variant<MODE, 1, false>(maps, p, s);          \
+        return extras ? launch_variant<MODE, 0, true>(maps, p, s)                            \
+                      : launch_variant<MODE, 0, false>(maps, p, s);                          \
     } while (0)
     if (dp && du) BKE_DISPATCH(3);
     if (dp) BKE_DISPATCH(1);

@@ -11,9 +11,9 @@
 //   bke_mm_estimate        IMM.py:228-237   x = sum mu_j x_j, P = sum mu_j ((x_j - x)(x_j - x)' + P_j)
 //                          mmae.py:186-201  (with the reference's element-wise zip, see BKE_MM_MMAE)
 //
-// Work split: one thread per (track, element of [x | P]) so that consecutive threads touch
-// consecutive addresses of every model's AoS arrays; the few per-track scalars (mu, omega) are
-// re-read by the n + n^2 threads of a track from L1.  All HBM-bound: per track the mix reads and
+// Work split: one thread per element of the x arrays, then of the P arrays, so that consecutive
+// threads touch consecutive addresses of every model's bank arrays; the few per-track scalars (mu,
+// omega) are re-read by the threads of a track from L1.  All HBM-bound: per track the mix reads and
 // writes M (n + n^2) scalars.
 #include <float.h>
 #include "bke_internal.cuh"
@@ -35,81 +35,125 @@ struct MixP {
     const double *trans;         // M[M,M]
 };
 
+// Element-parallel kernels: one thread per element of the concatenated x arrays (N*n) or of the
+// concatenated P arrays (N*n*n), grid-stride; MM > 0 fixes the model count at compile time (loops
+// unroll, per-model values stay in registers), MM == 0 is the run-time fallback (M <= 8).
+// index / divisor with 32-bit arithmetic when the index fits (a 64-bit division costs ~80 instructions)
+__device__ __forceinline__ int64_t div_idx(int64_t a, int b, bool small)
+{
+    return small ? (int64_t)((uint32_t)a / (uint32_t)b) : a / b;
+}
+
+template <int MM>
+struct ModelCount {
+    int m;
+    __device__ __forceinline__ int get() const { return MM > 0 ? MM : m; }
+};
+
 // mixed initial conditions (IMM.py:201-213): for every target model i
 //   x0_i = sum_j omega[j,i] x_j ;  P0_i = sum_j omega[j,i] ((x_j - x0_i)(x_j - x0_i)' + P_j)
-template <typename T>
+template <typename T, int MM>
 __global__ void __launch_bounds__(256) k_mm_mix(MixP<T> p)
 {
-    const int n = p.n, M = p.M, E = n + n * n;
-    const int64_t total = p.N * E;
+    constexpr int MA = MM > 0 ? MM : BKE_MM_MAX_MODELS;
+    const int n = p.n, nn = n * n;
+    const int M = ModelCount<MM>{p.M}.get();
+    const int64_t nx = p.N * n, total = nx + p.N * nn;
+    const bool small = total <= 0xffffffffLL;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t t = g / E;
-        const int e = (int)(g - t * E);
-        const double *om = p.w + t * p.sw;
-        if (e < n) {
-            double xj[BKE_MM_MAX_MODELS];
-            for (int j = 0; j < M; j++) xj[j] = (double)p.x[j][t * n + e];
-            for (int i = 0; i < M; i++) {
-                double s = 0.0;
-                for (int j = 0; j < M; j++) s += xj[j] * om[j * M + i];
-                p.xo[i][t * n + e] = (T)s;
+        if (g < nx) {
+            const int64_t t = div_idx(g, n, small);
+            const double *om = p.w + t * p.sw;
+            double xj[MA];
+#pragma unroll
+            for (int j = 0; j < MA; j++) if (j < M) xj[j] = (double)p.x[j][g];
+#pragma unroll
+            for (int i = 0; i < MA; i++) {
+                if (i < M) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int j = 0; j < MA; j++) if (j < M) s += xj[j] * om[j * M + i];
+                    p.xo[i][g] = (T)s;
+                }
             }
         } else {
-            const int rc = e - n, r = rc / n, c = rc - r * n;
-            double xr[BKE_MM_MAX_MODELS], xc[BKE_MM_MAX_MODELS], Pj[BKE_MM_MAX_MODELS];
-            for (int j = 0; j < M; j++) {
-                xr[j] = (double)p.x[j][t * n + r];
-                xc[j] = (double)p.x[j][t * n + c];
-                Pj[j] = (double)p.P[j][t * n * n + rc];
+            const int64_t q = g - nx;
+            const int64_t t = div_idx(q, nn, small);
+            const int rc = (int)(q - t * nn), r = rc / n, c = rc - r * n;
+            const double *om = p.w + t * p.sw;
+            double xr[MA], xc[MA], Pj[MA];
+#pragma unroll
+            for (int j = 0; j < MA; j++) {
+                if (j < M) {
+                    xr[j] = (double)p.x[j][t * n + r];
+                    xc[j] = (double)p.x[j][t * n + c];
+                    Pj[j] = (double)p.P[j][q];
+                }
             }
-            for (int i = 0; i < M; i++) {
-                double mr = 0.0, mc = 0.0;
-                for (int j = 0; j < M; j++) { mr += xr[j] * om[j * M + i]; mc += xc[j] * om[j * M + i]; }
-                if (sizeof(T) == 4) { mr = (double)(T)mr; mc = (double)(T)mc; }     // the mixed mean as it is stored
-                double s = 0.0;
-                for (int j = 0; j < M; j++) s += om[j * M + i] * ((xr[j] - mr) * (xc[j] - mc) + Pj[j]);
-                p.Po[i][t * n * n + rc] = (T)s;
+#pragma unroll
+            for (int i = 0; i < MA; i++) {
+                if (i < M) {
+                    double mr = 0.0, mc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < MA; j++) if (j < M) { const double w = om[j * M + i]; mr += xr[j] * w; mc += xc[j] * w; }
+                    if (sizeof(T) == 4) { mr = (double)(T)mr; mc = (double)(T)mc; }     // the mixed mean as it is stored
+                    double s = 0.0;
+#pragma unroll
+                    for (int j = 0; j < MA; j++) if (j < M) s += om[j * M + i] * ((xr[j] - mr) * (xc[j] - mc) + Pj[j]);
+                    p.Po[i][q] = (T)s;
+                }
             }
         }
     }
 }
 
 // combined estimate (IMM.py:228-237; mmae.py:186-201 with BKE_MM_MMAE)
-template <typename T>
+template <typename T, int MM>
 __global__ void __launch_bounds__(256) k_mm_estimate(MixP<T> p)
 {
-    const int n = p.n, M = p.M, E = n + n * n;
+    constexpr int MA = MM > 0 ? MM : BKE_MM_MAX_MODELS;
+    const int n = p.n, nn = n * n;
+    const int M = ModelCount<MM>{p.M}.get();
     const bool mmae = p.flags & BKE_MM_MMAE;
-    const int64_t total = p.N * E;
+    const int64_t nx = p.N * n, total = nx + p.N * nn;
+    const bool small = total <= 0xffffffffLL;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t t = g / E;
-        const int e = (int)(g - t * E);
-        const double *mu = p.w + t * p.sw;
-        if (e < n) {
+        if (g < nx) {
+            const double *mu = p.w + div_idx(g, n, small) * p.sw;
             double s = 0.0;
-            for (int j = 0; j < M; j++) s += (double)p.x[j][t * n + e] * mu[j];
-            p.xo[0][t * n + e] = (T)s;
+#pragma unroll
+            for (int j = 0; j < MA; j++) if (j < M) s += (double)p.x[j][g] * mu[j];
+            p.xo[0][g] = (T)s;
         } else {
-            const int rc = e - n, r = rc / n, c = rc - r * n;
+            const int64_t q = g - nx;
+            const int64_t t = div_idx(q, nn, small);
+            const int rc = (int)(q - t * nn), r = rc / n, c = rc - r * n;
+            const double *mu = p.w + t * p.sw;
             double s = 0.0;
             if (!mmae) {
-                double mr = 0.0, mc = 0.0;
-                for (int j = 0; j < M; j++) { mr += (double)p.x[j][t * n + r] * mu[j]; mc += (double)p.x[j][t * n + c] * mu[j]; }
+                double xr[MA], xc[MA], mr = 0.0, mc = 0.0;
+#pragma unroll
+                for (int j = 0; j < MA; j++) {
+                    if (j < M) {
+                        xr[j] = (double)p.x[j][t * n + r]; xc[j] = (double)p.x[j][t * n + c];
+                        mr += xr[j] * mu[j]; mc += xc[j] * mu[j];
+                    }
+                }
                 if (sizeof(T) == 4) { mr = (double)(T)mr; mc = (double)(T)mc; }
-                for (int j = 0; j < M; j++)
-                    s += mu[j] * (((double)p.x[j][t * n + r] - mr) * ((double)p.x[j][t * n + c] - mc) + (double)p.P[j][t * n * n + rc]);
+#pragma unroll
+                for (int j = 0; j < MA; j++) if (j < M) s += mu[j] * ((xr[j] - mr) * (xc[j] - mc) + (double)p.P[j][q]);
             } else {
                 // mmae.py:197-199 zips the COMPONENTS of the mixed x with the filters: term j uses
                 // y = f_j.x - x[j] (a scalar), and only min(dim_x, M) terms exist
                 const int terms = M < n ? M : n;
                 for (int j = 0; j < terms; j++) {
                     double mj = 0.0;
-                    for (int q = 0; q < M; q++) mj += (double)p.x[q][t * n + j] * mu[q];
+                    for (int k = 0; k < M; k++) mj += (double)p.x[k][t * n + j] * mu[k];
                     if (sizeof(T) == 4) mj = (double)(T)mj;
-                    s += mu[j] * (((double)p.x[j][t * n + r] - mj) * ((double)p.x[j][t * n + c] - mj) + (double)p.P[j][t * n * n + rc]);
+                    s += mu[j] * (((double)p.x[j][t * n + r] - mj) * ((double)p.x[j][t * n + c] - mj) + (double)p.P[j][q]);
                 }
             }
-            p.Po[0][t * n * n + rc] = (T)s;
+            p.Po[0][q] = (T)s;
         }
     }
 }
@@ -168,14 +212,25 @@ int launch_t(const bke_mm_args &a, int op, cudaStream_t s)
     }
     p.mu = a.mu; p.cbar = a.cbar; p.omega = a.omega; p.trans = a.trans;
     const int64_t E = a.dim_x + (int64_t)a.dim_x * a.dim_x;
+    const unsigned ge = grid_for((p.N * E + 1) / 2);
     if (op == 0) {
         k_mm_probabilities<T><<<grid_for(p.N), 256, 0, s>>>(p);
     } else if (op == 1) {
         p.w = a.omega; p.sw = a.weights_stride;
-        k_mm_mix<T><<<grid_for(p.N * E), 256, 0, s>>>(p);
+        switch (p.M) {
+        case 2: k_mm_mix<T, 2><<<ge, 256, 0, s>>>(p); break;
+        case 3: k_mm_mix<T, 3><<<ge, 256, 0, s>>>(p); break;
+        case 4: k_mm_mix<T, 4><<<ge, 256, 0, s>>>(p); break;
+        default: k_mm_mix<T, 0><<<ge, 256, 0, s>>>(p);
+        }
     } else {
         p.w = a.mu; p.sw = a.weights_stride;
-        k_mm_estimate<T><<<grid_for(p.N * E), 256, 0, s>>>(p);
+        switch (p.M) {
+        case 2: k_mm_estimate<T, 2><<<ge, 256, 0, s>>>(p); break;
+        case 3: k_mm_estimate<T, 3><<<ge, 256, 0, s>>>(p); break;
+        case 4: k_mm_estimate<T, 4><<<ge, 256, 0, s>>>(p); break;
+        default: k_mm_estimate<T, 0><<<ge, 256, 0, s>>>(p);
+        }
     }
     return check_cuda(cudaGetLastError(), "mm launch");
 }

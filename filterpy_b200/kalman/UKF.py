@@ -17,6 +17,7 @@ residual_x, residual_z, state_add, per-call UT / fx / hx), raises NotImplemented
 CPU fallback.  As for the linear filter, ``n_filters=None`` gives a single-filter drop-in whose
 attributes are NumPy arrays (``x`` is 1-D, UKF.py:298).
 """
+import ctypes
 import math
 import sys
 
@@ -280,6 +281,58 @@ class UnscentedKalmanFilter(object):
             self._x_post.copy_(self._x); self._P_post.copy_(self._P)
         if self.diagnostics and self._single:
             self.check()
+
+    def rts_smoother(self, Xs, Ps, Qs=None, dts=None, UT=None):
+        """UKF.py:634-739 on the GPU.  Bank mode: ``Xs[T,N,n]``, ``Ps[T,N,n,n]`` (what
+        ``batch_filter`` returns) -> ``(xs, Ps, Ks)`` tensors; single mode NumPy ``(T,n)`` /
+        ``(T,n,n)``.  ``dts``: None (the filter's dt), a scalar, or one value per epoch.  ``Qs`` is
+        accepted and, exactly like the reference (:715 uses ``self.Q``), not used."""
+        _no_hook("UT", UT)
+        if len(Xs) != len(Ps):
+            raise ValueError('Xs and Ps must have the same length')
+        self._flush()
+        N, n = self.n_filters, self._dim_x
+        is_np = not isinstance(Xs, torch.Tensor)
+        Xt = to_dev(Xs, self._dtype, self._device)
+        Pt = to_dev(Ps, self._dtype, self._device)
+        T = Xt.shape[0]
+        if self._single:
+            Xt = Xt.reshape(T, 1, n); Pt = Pt.reshape(T, 1, n, n)
+        if tuple(Xt.shape) != (T, N, n) or tuple(Pt.shape) != (T, N, n, n):
+            raise ValueError("Xs / Ps must have shapes (T,%d,%d) / (T,%d,%d,%d)" % (N, n, N, n, n))
+        Xt = Xt.contiguous(); Pt = Pt.contiguous()
+        kw = dict(dtype=self._dtype, device=self._device)
+        xs = torch.empty(T, N, n, **kw); Pso = torch.empty(T, N, n, n, **kw); Ks = torch.empty(T, N, n, n, **kw)
+        status = torch.zeros(N, dtype=torch.int32, device=self._device)
+        a = _lib.UkfRtsArgs()
+        a.n_filters, a.n_steps, a.dim_x, a.dtype = N, T, n, bke_dtype(self._dtype)
+        a.fx_model = self.fx.model
+        a.alpha, a.beta, a.kappa = self.points_fn.alpha, self.points_fn.beta, self.points_fn.kappa
+        a.dt = float(self._dt)
+        dts_t = None
+        if dts is not None:
+            if np.isscalar(dts):
+                a.dt = float(dts)
+            else:
+                d = np.asarray(dts, dtype=np.float64).reshape(-1)
+                if d.shape[0] != T:
+                    raise ValueError("dts must have one entry per epoch (%d)" % T)
+                dts_t = torch.from_numpy(np.ascontiguousarray(d)).to(self._device)
+                a.dts = ptr(dts_t)
+        a.Xs, a.Ps = ptr(Xt), ptr(Pt)
+        a.Q, a.Q_stride = ptr(self._Q), self._stride(self._Q)
+        if self._F is not None:
+            a.F, a.F_stride = ptr(self._F), self._stride(self._F)
+        a.x_out, a.P_out, a.K = ptr(xs), ptr(Pso), ptr(Ks)
+        a.status = ptr(status)
+        with torch.cuda.device(self._device):
+            _lib.check(self._lib.bke_ukf_rts_smoother(ctypes.byref(a), stream_ptr(self._device)))
+        if not self._single:
+            return xs, Pso, Ks
+        if int(status[0].item()) != 0:
+            raise np.linalg.LinAlgError("matrix not positive definite / singular")
+        out = (xs[:, 0], Pso[:, 0], Ks[:, 0])
+        return tuple(o.cpu().numpy() for o in out) if is_np else out
 
     def batch_filter(self, zs, Rs=None, dts=None, UT=None, saver=None, valid=None):
         """UKF.py:524-632: predict/update over the epochs of ``zs`` (bank: ``zs[T,N,m]``), one fused

@@ -73,7 +73,9 @@ class KalmanFilter(object):
             self._SI = torch.zeros(N, m, m, **kw)
             self._ll = torch.full((N,), math.log(sys.float_info.min), **kw)
             self._status = torch.zeros(N, dtype=torch.int32, device=self._device)
+        self._host = {k: np.ascontiguousarray(getattr(self, "_" + k).cpu().numpy()) for k in "FQHR"}
         self._has_update = False
+        self._post_alias = False      # True: x_post / P_post are the live x / P (nothing has moved them since the update)
         self._version = 0            # bumped whenever a tensor the kernels read is re-bound
         self._args_cache = {}
 
@@ -125,6 +127,7 @@ class KalmanFilter(object):
                 self._x_col = False
             else:
                 raise ValueError("x must have shape (%d,1) or (%d,), got %s" % (n, n, tuple(t.shape)))
+            self._snapshot_post()
             self._x = t.reshape(1, n).clone()
             self._version += 1
         else:
@@ -134,6 +137,7 @@ class KalmanFilter(object):
                 t = t.expand(self.n_filters, n)
             if tuple(t.shape) != (self.n_filters, n):
                 raise ValueError("x must have shape (%d,%d), got %s" % (self.n_filters, n, tuple(t.shape)))
+            self._snapshot_post()
             self._x = t.contiguous().clone()
             self._version += 1
 
@@ -153,17 +157,25 @@ class KalmanFilter(object):
             t = t.expand(self.n_filters, n, n)
         if tuple(t.shape) != (self.n_filters, n, n):
             raise ValueError("P must have shape (%d,%d) or (%d,%d,%d)" % (n, n, self.n_filters, n, n))
+        self._snapshot_post()
         self._P = t.contiguous().clone()
         self._version += 1
 
     def _adopt_state(self, x_t, P_t):
-        """Re-bind the state to caller-owned device tensors (no copy); returns the old pair so that a
-        caller (IMMEstimator's mixing step) can double-buffer."""
+        """Re-bind the state to caller-owned device tensors (no copy) and hand back a spare pair, so
+        that a caller (IMMEstimator's mixing step) can double-buffer.  When x_post / P_post are
+        still the live state, the outgoing buffers BECOME the stored posterior and the previous
+        posterior buffers are the spare pair: a rotation instead of a copy."""
         self._flush()
-        old = (self._x, self._P)
+        if self.diagnostics and self._post_alias:
+            spare = (self._x_post, self._P_post)
+            self._x_post, self._P_post = self._x, self._P
+            self._post_alias = False
+        else:
+            spare = (self._x, self._P)
         self._x, self._P = x_t, P_t
         self._version += 1
-        return old
+        return spare
 
     def _mk_model_prop(name, rows_attr, cols_attr):  # noqa: N805
         priv = "_" + name
@@ -172,14 +184,24 @@ class KalmanFilter(object):
             t = getattr(self, priv)
             if t is None:
                 return None
-            return t.cpu().numpy() if self._single else t
+            if self._single:
+                return t.cpu().numpy()
+            if self._host.pop(name, None) is not None:      # the caller may edit the live tensor in place:
+                self._version += 1                          # the host copy can no longer be trusted
+            return t
 
         def set_(self, v):
             self._version += 1
+            self._host.pop(name, None)
             if v is None:
                 setattr(self, priv, None)
                 return
-            setattr(self, priv, self._model(v, getattr(self, rows_attr), getattr(self, cols_attr), name))
+            t = self._model(v, getattr(self, rows_attr), getattr(self, cols_attr), name)
+            setattr(self, priv, t)
+            if t.dim() == 2 and name in "FQHR":
+                # host copy of a model shared by the bank: lets the kernels carry it in their launch
+                # parameters (bke_kf_args.*_host)
+                self._host[name] = np.ascontiguousarray(t.cpu().numpy())
         return property(get, set_)
 
     F = _mk_model_prop("F", "dim_x", "dim_x")
@@ -216,8 +238,21 @@ class KalmanFilter(object):
 
     x_prior = property(lambda self: self._vec_out(self._diag("x_prior")))
     P_prior = property(lambda self: self._out(self._diag("P_prior")))
-    x_post = property(lambda self: self._vec_out(self._diag("x_post")))
-    P_post = property(lambda self: self._out(self._diag("P_post")))
+    # x_post / P_post (kalman_filter.py:560-561) equal x / P until the next predict runs: they are
+    # the live tensors until then, and are snapshotted only when a predict is launched on its own
+    x_post = property(lambda self: self._vec_out(self._diag("x" if self._post_alias_now() else "x_post")))
+    P_post = property(lambda self: self._out(self._diag("P" if self._post_alias_now() else "P_post")))
+
+    def _post_alias_now(self):
+        if not self.diagnostics:
+            raise AttributeError("x_post / P_post are only kept when the filter is built with diagnostics=True")
+        self._flush()
+        return self._post_alias
+
+    def _snapshot_post(self):
+        if self.diagnostics and self._post_alias:
+            self._x_post.copy_(self._x); self._P_post.copy_(self._P)
+        self._post_alias = False
     K = property(lambda self: self._out(self._diag("K")))
     y = property(lambda self: self._vec_out(self._diag("y")))
     S = property(lambda self: self._out(self._diag("S")))
@@ -282,7 +317,7 @@ class KalmanFilter(object):
                 self._launch(_lib.BKE_DO_PREDICT, pend, None, None, None, None)
             self._z = None
             if self.diagnostics:
-                self._x_post.copy_(self._x); self._P_post.copy_(self._P)
+                self._post_alias = True
                 self._y.zero_()
             return
         m = self.dim_z
@@ -329,9 +364,11 @@ class KalmanFilter(object):
             if hit is not None and hit[0] == self._version:
                 a = hit[1]
                 a.z = ptr(zt); a.z_valid = ptr(vt)
+                if not (flags & _lib.BKE_DO_UPDATE):
+                    self._snapshot_post()                   # a predict on its own is about to move x, P
                 self._call(a)
                 if self.diagnostics and (flags & _lib.BKE_DO_UPDATE):
-                    self._x_post.copy_(self._x); self._P_post.copy_(self._P)
+                    self._post_alias = True
                     if self._single:
                         self.check()
                 return
@@ -371,6 +408,10 @@ class KalmanFilter(object):
             a.z = ptr(zt)
             a.z_valid = ptr(vt)
             keep += [Rm, Hm, zt, vt]
+        if plain and len(self._host) == 4:                  # every model shared and known on the host
+            hm = [self._host[k] for k in "FQHR"]
+            a.F_host, a.Q_host, a.H_host, a.R_host = (h.ctypes.data for h in hm)
+            keep += hm
         if self.diagnostics:
             if flags & _lib.BKE_DO_PREDICT:
                 a.x_prior, a.P_prior = ptr(self._x_prior), ptr(self._P_prior)
@@ -378,11 +419,13 @@ class KalmanFilter(object):
                 a.K, a.y, a.S, a.SI = ptr(self._K), ptr(self._y), ptr(self._S), ptr(self._SI)
                 a.log_likelihood = ptr(self._ll)
                 a.status = ptr(self._status)
+        if not (flags & _lib.BKE_DO_UPDATE):
+            self._snapshot_post()                           # a predict on its own is about to move x, P
         self._call(a)
         if plain:
             self._args_cache[flags] = (self._version, a, keep)      # keep: the tensors `a` points into
         if self.diagnostics and (flags & _lib.BKE_DO_UPDATE):
-            self._x_post.copy_(self._x); self._P_post.copy_(self._P)
+            self._post_alias = True
             if self._single:
                 self.check()
 
@@ -469,7 +512,9 @@ class KalmanFilter(object):
                 if saver is not None:
                     saver.save()
         if self.diagnostics:
-            self._x_post.copy_(self._x); self._P_post.copy_(self._P)
+            self._post_alias = not update_first             # update_first ends on a predict (:980-985)
+            if update_first and T > 0:
+                self._x_post.copy_(means[T - 1]); self._P_post.copy_(covs[T - 1])
         if not self._single:
             return means, covs, means_p, covs_p
         self.check() if self.diagnostics else None

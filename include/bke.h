@@ -93,6 +93,10 @@ typedef struct bke_kf_args {
     void *x_prior, *P_prior;
     void *K, *y, *S, *SI, *log_likelihood;
     int32_t *status;
+    /* Optional HOST copies of models that are shared by the bank (stride 0), in `dtype`: when all
+     * four are given (and equal the device copies) a kernel may carry them in its launch parameters
+     * instead of loading them from device memory.  NULL = not available. */
+    const void *F_host, *Q_host, *H_host, *R_host;
 } bke_kf_args;
 
 int bke_kf_step(const bke_kf_args *args, void *stream);
@@ -255,6 +259,25 @@ typedef struct {
 } bke_rts_args;
 
 int bke_kf_rts_smoother(const bke_rts_args *args, void *stream);
+
+/* UnscentedKalmanFilter.rts_smoother filterpy/kalman/UKF.py:634-739 for a bank; same layout as
+ * bke_kf_rts_smoother.  Q is the filter's own Q (the reference never reads its Qs argument, :715);
+ * dts is a DEVICE array of n_steps doubles (step k uses dts[k], :712) or NULL = dt for every step;
+ * fx_model / F as in bke_ukf_args.  K may be NULL. */
+typedef struct {
+    int64_t n_filters, n_steps;
+    int32_t dim_x, dtype, fx_model, reserved;
+    double alpha, beta, kappa;
+    double dt;
+    const double *dts;
+    const void *Xs, *Ps;
+    const void *Q; int64_t Q_stride;
+    const void *F; int64_t F_stride;
+    void *x_out, *P_out, *K;
+    int32_t *status;
+} bke_ukf_rts_args;
+
+int bke_ukf_rts_smoother(const bke_ukf_rts_args *args, void *stream);
 
 /* ---- bank-level model mixing: IMMEstimator / MMAEFilterBank ------------
  *

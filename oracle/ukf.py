@@ -6,7 +6,7 @@ Restates (reference @ 3b51149):
   factor of (n+lambda) P; weights Wm/Wc)
 * ``unscented_transform``     unscented_transform.py:99-128
 * ``UnscentedKalmanFilter.predict / update / cross_variance / batch_filter``
-  UKF.py:364-411, 413-491, 493-504, 524-632.  Note UKF.py:407: after the first
+  UKF.py:364-411, 413-491, 493-504, 524-632; ``rts_smoother`` UKF.py:634-739.  Note UKF.py:407: after the first
   unscented transform the sigma points are REGENERATED from the prior, and
   UKF.py:481: P = P - K S K' (no symmetrisation).
 
@@ -145,3 +145,29 @@ def ukf_step_bank(x, P, z, Q, R, dt, alpha, beta, kappa,
         xn = np.where(v[:, None], xn, xp)
         Pn = np.where(v[:, None, None], Pn, Pp)
     return dict(x=xn, P=Pn, x_prior=xp, P_prior=Pp, y=y, K=K, S=S, SI=SI)
+
+
+def ukf_rts_smoother(Xs, Ps, Q, fx, dts, alpha, beta, kappa):
+    """UnscentedKalmanFilter.rts_smoother, UKF.py:696-739, for ONE filter: Xs (T,n), Ps (T,n,n),
+    Q the filter's own Q (the reference never reads its Qs argument, :715), fx a callable,
+    dts a list of T time steps -> (xs, Ps, Ks)."""
+    if len(Xs) != len(Ps):
+        raise ValueError('Xs and Ps must have the same length')
+    n, dim_x = Xs.shape
+    Wm, Wc = merwe_weights(dim_x, alpha, beta, kappa)
+    Ks = np.zeros((n, dim_x, dim_x))
+    xs, ps = Xs.copy(), Ps.copy()
+    for k in reversed(range(n - 1)):
+        sigmas = merwe_sigma_points(xs[k], ps[k], alpha, beta, kappa)         # :711
+        sigmas_f = np.array([fx(s, dts[k]) for s in sigmas])                  # :712-713
+        xb, Pb = unscented_transform(sigmas_f, Wm, Wc, Q)                     # :715-717
+        Pxb = 0
+        for i in range(sigmas.shape[0]):                                      # :720-724
+            y = sigmas_f[i] - xb
+            z = sigmas[i] - Xs[k]
+            Pxb = Pxb + Wc[i] * np.outer(z, y)
+        K = np.dot(Pxb, np.linalg.inv(Pb))                                    # :727
+        xs[k] += np.dot(K, xs[k + 1] - xb)                                    # :730
+        ps[k] += np.dot(K, ps[k + 1] - Pb).dot(K.T)                           # :731
+        Ks[k] = K
+    return xs, ps, Ks

@@ -263,6 +263,33 @@ def gen_rts():
     save("rts", **out)
 
 
+# ----------------------------------------------------------------------------- UKF RTS smoother
+def gen_ukf_rts():
+    alpha, beta, kappa = 0.5, 2.0, 0.0
+    out = {}
+    for name, linear in (("cv", False), ("lin", True)):
+        N, steps, dt = 6, 12, 0.1
+        w = wl.ukf_bank_cv3d(N, seed=1357, steps=steps, dt=dt, linear_hx=True)
+        F, Hlin = w["F"], w["H"]
+        fx = (lambda s, dt: F @ s) if linear else fx_cv
+        hx = lambda s: Hlin @ s                                   # noqa: E731
+        dts = list(np.random.default_rng(1).uniform(0.05, 0.15, steps)) if not linear else None
+        Xs = np.zeros((steps, N, 6)); Ps = np.zeros((steps, N, 6, 6))
+        sm = [np.zeros((steps, N, 6)), np.zeros((steps, N, 6, 6)), np.zeros((steps, N, 6, 6))]
+        for f in range(N):
+            u = UnscentedKalmanFilter(6, 3, dt, hx, fx, MerweScaledSigmaPoints(6, alpha, beta, kappa))
+            u.x = w["x"][f].copy(); u.P = w["P"][f].copy(); u.Q = w["Q"][f]; u.R = w["R"][f]
+            mu, cov = u.batch_filter(list(w["zs"][:, f]), dts=dts)
+            Xs[:, f] = mu; Ps[:, f] = cov
+            r = u.rts_smoother(mu, cov, dts=dts)
+            for o, v in zip(sm, r):
+                o[:, f] = v
+        out.update({name + "_Xs": Xs, name + "_Ps": Ps, name + "_x": sm[0], name + "_P": sm[1], name + "_K": sm[2],
+                    name + "_Q": w["Q"], name + "_F": F, name + "_dt": dt,
+                    name + "_dts": np.array(dts if dts is not None else [dt] * steps)})
+    save("ukf_rts", alpha=alpha, beta=beta, kappa=kappa, **out)
+
+
 # ----------------------------------------------------------------------------- IMM / MMAE
 def mm_models(n_tracks, seed):
     """Two / three CV models (different process noise) per track, dim_x=4, dim_z=2, 1-D x."""
@@ -326,4 +353,5 @@ if __name__ == "__main__":
     gen_resample()
     gen_multinomial()
     gen_rts()
+    gen_ukf_rts()
     gen_mm()

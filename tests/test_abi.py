@@ -23,13 +23,37 @@ def test_header_symbols_are_exported():
     assert lib.bke_abi_version() == 1
 
 
-def test_struct_layout_matches_header():
-    # the ctypes mirrors must have the C layout: 8-byte pointers/int64, 4-byte ints, natural padding
-    assert ctypes.sizeof(_lib.KfArgs) == 8 + 4 * 6 + 8 + 8 * 4 + 16 * 6 + 16 + 8 * 8
-    assert ctypes.sizeof(_lib.KfBatchArgs) == ctypes.sizeof(_lib.KfArgs) + 8 * 7
-    assert ctypes.sizeof(_lib.UkfArgs) == 8 + 4 * 6 + 8 * 4 + 8 * 4 + 16 * 4 + 16 + 8 * 8
+def test_struct_layout_matches_header(tmp_path):
+    """The ctypes mirrors must have the layout a C compiler gives the structs of include/bke.h:
+    a probe compiled with gcc prints sizeof / offsetof of every struct."""
+    import subprocess
+    structs = {"bke_kf_args": _lib.KfArgs, "bke_kf_batch_args": _lib.KfBatchArgs, "bke_ukf_args": _lib.UkfArgs,
+               "bke_resample_shard_args": _lib.ResampleShardArgs, "bke_rts_args": _lib.RtsArgs, "bke_ukf_rts_args": _lib.UkfRtsArgs,
+               "bke_mm_args": _lib.MmArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "bke.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append('printf("%s sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['return 0; }']
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)]).decode().split("\n")
+    seen = 0
+    for ln in out:
+        if not ln.strip():
+            continue
+        cname, fname, val = ln.split()
+        cls = structs[cname]
+        if fname == "sizeof":
+            assert ctypes.sizeof(cls) == int(val), (cname, ctypes.sizeof(cls), val)
+        else:
+            assert getattr(cls, fname).offset == int(val), (cname, fname)
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in structs.values())
     assert _lib.KfArgs.alpha_sq.offset == 32 and _lib.KfArgs.x.offset == 40
-    assert _lib.UkfArgs.dt.offset == 32
 
 
 def test_argument_validation_without_gpu():

@@ -299,3 +299,63 @@ def test_c3_size_slice_independence_f64():
     assert torch.equal(kf.x[sl], sub.x) and torch.equal(kf.P[sl], sub.P)
     o = okf.kf_step_bank(w["x"][sl], w["P"][sl], w["zs"][0][sl], w["F"][sl], w["H"][sl], w["Q"][sl], w["R"][sl])
     rel_close(sub.x.cpu().numpy(), o["x"], 1e-6, "x"); rel_close(sub.P.cpu().numpy(), o["P"], 1e-6, "P")
+
+
+def test_x_post_survives_predict_and_state_assignment(golden):
+    """x_post / P_post are lazy views of the state after an update (no per-step copy); they must
+    still hold the posterior once a predict has moved x, P (kalman_filter.py:560-561) or the user
+    assigned a new state."""
+    import torch
+    from filterpy_b200.kalman import KalmanFilter
+    g = golden("kf_bank_4_2")
+    N = g["x"].shape[0]
+    kf = KalmanFilter(4, 2, n_filters=N, dtype=np.float64)
+    kf.x, kf.P, kf.F, kf.H, kf.Q, kf.R = g["x"], g["P"], g["F"], g["H"], g["Q"], g["R"]
+    z = torch.from_numpy(g["zs"][0]).cuda()
+    kf.predict(); kf.update(z)
+    post_x = kf.x.clone(); post_P = kf.P.clone()
+    assert torch.equal(kf.x_post, post_x) and torch.equal(kf.P_post, post_P)
+    kf.predict()
+    prior_x = kf.x.clone()                                  # forces the stand-alone predict
+    assert not torch.equal(prior_x, post_x)
+    assert torch.equal(kf.x_post, post_x) and torch.equal(kf.P_post, post_P)
+    assert torch.equal(kf.x_prior, prior_x)
+    kf.update(torch.from_numpy(g["zs"][1]).cuda())
+    assert torch.equal(kf.x_post, kf.x)
+    post2 = kf.x.clone()
+    kf.x = np.zeros((N, 4))                                 # a new state does not rewrite the stored posterior
+    assert torch.equal(kf.x_post, post2)
+    kf.update(None)                                         # z=None: posterior := prior (:515-520)
+    assert torch.equal(kf.x_post, kf.x)
+
+
+@pytest.mark.parametrize("diagnostics", [False, True])
+def test_shared_models_in_launch_parameters_equal_device_models(golden, diagnostics):
+    """A bank that shares F/H/Q/R carries them in the launch parameters when the mirror still holds
+    host copies (bke_kf_args.*_host); reading an attribute hands out the live tensor, drops the
+    host copy and the kernel reads device memory instead.  Same arithmetic, same result."""
+    import torch
+    from filterpy_b200.kalman import KalmanFilter
+    g = golden("kf_bank_4_2")
+    N = g["x"].shape[0]
+    outs = []
+    for device_path in (False, True):
+        kf = KalmanFilter(4, 2, n_filters=N, dtype=np.float32, diagnostics=diagnostics)
+        kf.x, kf.P = g["x"], g["P"]
+        kf.F, kf.H, kf.Q, kf.R = g["F"][0], g["H"][0], g["Q"][0], g["R"][0]
+        assert len(kf._host) == 4
+        if device_path:
+            assert kf.F.shape == (4, 4) and kf.H.shape == (2, 4)         # getters invalidate the host copies
+            assert len(kf._host) == 2
+        for t in range(3):
+            kf.predict(); kf.update(torch.from_numpy(g["zs"][t].astype(np.float32)).cuda())
+        outs.append((kf.x.cpu().numpy(), kf.P.cpu().numpy()))
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])
+    # and both agree with the oracle on the same shared models
+    from oracle import kf as okf
+    x, P = g["x"].copy(), g["P"].copy()
+    for t in range(3):
+        x, P = okf.kf_predict_bank(x, P, g["F"][0], g["Q"][0])
+        x, P = okf.kf_update_bank(x, P, g["zs"][t], g["H"][0], g["R"][0])[:2]
+    np.testing.assert_allclose(outs[0][0], x, rtol=1e-3, atol=1e-3 * np.abs(x).max())

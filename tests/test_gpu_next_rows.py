@@ -274,3 +274,37 @@ def test_imm_single_track_drop_in_and_errors(golden):
         IMMEstimator([KalmanFilter(4, 2), KalmanFilter(3, 2)], [.5, .5], np.eye(2))
     with pytest.raises(ValueError):
         MMAEFilterBank([KalmanFilter(4, 2), KalmanFilter(4, 2)], [1.0], dim_x=4)
+
+
+# ------------------------------------------------------------------ UKF RTS smoother
+@pytest.mark.parametrize("name", ["cv", "lin"])
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-6), (np.float32, 2e-3)])
+def test_ukf_rts_bank_golden(golden, name, dtype, tol):
+    import torch
+    from filterpy_b200.kalman import (UnscentedKalmanFilter, MerweScaledSigmaPoints, ConstVelFx, LinearFx, LinearHx)
+    g = golden("ukf_rts")
+    Xs, Ps = g[name + "_Xs"], g[name + "_Ps"]
+    T, N, n = Xs.shape
+    fx = ConstVelFx() if name == "cv" else LinearFx(g[name + "_F"])
+    u = UnscentedKalmanFilter(6, 3, float(g[name + "_dt"]), LinearHx(np.eye(3, 6)), fx,
+                              MerweScaledSigmaPoints(6, float(g["alpha"]), float(g["beta"]), float(g["kappa"])),
+                              n_filters=N, dtype=dtype)
+    u.Q = g[name + "_Q"]
+    dts = list(g[name + "_dts"]) if name == "cv" else None
+    x, P, K = u.rts_smoother(torch.from_numpy(Xs), torch.from_numpy(Ps), dts=dts)
+    rel_close(x.cpu().numpy(), g[name + "_x"], tol)
+    rel_close(P.cpu().numpy(), g[name + "_P"], tol, atol_scale=4.0 if dtype == np.float32 else 1.0)
+    rel_close(K.cpu().numpy(), g[name + "_K"], tol * 10, atol_scale=4.0)
+    with pytest.raises(ValueError):
+        u.rts_smoother(torch.from_numpy(Xs[:-1]), torch.from_numpy(Ps))
+
+
+def test_ukf_rts_single_filter_drop_in(golden):
+    from filterpy_b200.kalman import UnscentedKalmanFilter, MerweScaledSigmaPoints, ConstVelFx, LinearHx
+    g = golden("ukf_rts")
+    u = UnscentedKalmanFilter(6, 3, float(g["cv_dt"]), LinearHx(np.eye(3, 6)), ConstVelFx(),
+                              MerweScaledSigmaPoints(6, float(g["alpha"]), float(g["beta"]), float(g["kappa"])))
+    u.Q = g["cv_Q"][2]
+    x, P, K = u.rts_smoother(g["cv_Xs"][:, 2], g["cv_Ps"][:, 2], dts=list(g["cv_dts"]))
+    assert x.shape == g["cv_x"][:, 2].shape and P.shape == g["cv_P"][:, 2].shape
+    rel_close(x, g["cv_x"][:, 2], 1e-6); rel_close(P, g["cv_P"][:, 2], 1e-6); rel_close(K, g["cv_K"][:, 2], 1e-5)

@@ -240,3 +240,22 @@ def test_imm_and_mmae_oracle_vs_reference_vectors(golden, nm):
             bank.predict(); bank.update(zs[k, t_])
             close(bank.x, g["mmae%d_x" % nm][k, t_]); close(bank.P, g["mmae%d_P" % nm][k, t_])
             close(bank.p, g["mmae%d_p" % nm][k, t_], rtol=1e-8, atol=1e-300)
+
+
+def test_ukf_rts_oracle_vs_reference_vectors(golden):
+    g = golden("ukf_rts")
+    al, be, ka = float(g["alpha"]), float(g["beta"]), float(g["kappa"])
+
+    def fx_cv(x, dt):
+        o = x.copy()
+        o[0::2] = x[0::2] + dt * x[1::2]
+        return o
+    for name in ("cv", "lin"):
+        F = g[name + "_F"]
+        fx = fx_cv if name == "cv" else (lambda s, dt: F @ s)
+        Xs, Ps = g[name + "_Xs"], g[name + "_Ps"]
+        for f in range(Xs.shape[1]):
+            x, P, K = oukf.ukf_rts_smoother(Xs[:, f], Ps[:, f], g[name + "_Q"][f], fx, list(g[name + "_dts"]), al, be, ka)
+            close(x, g[name + "_x"][:, f], rtol=1e-10, atol=1e-11)
+            close(P, g[name + "_P"][:, f], rtol=1e-10, atol=1e-11)
+            close(K, g[name + "_K"][:, f], rtol=1e-9, atol=1e-10)
