@@ -12,7 +12,7 @@ import torch
 import torch.distributed as dist
 
 __all__ = ["shard_bounds", "shard_of", "all_reduce_sum", "exclusive_prefix", "gather_counts",
-           "sharded_systematic_resample"]
+           "sharded_systematic_resample", "exchange_plan", "exchange_rows", "redistribute_after_resample"]
 
 
 def shard_bounds(n, world):
@@ -127,3 +127,80 @@ def sharded_systematic_resample(weights_local, u, group=None, capacity=None, uni
     _lib.check(lib.bke_resample_shard(ctypes.byref(a), stream_ptr(dev)))   # emit the indexes
     keep = (ws, carry_approx, carry_in, local_sum, sums)
     return idx, out_range, info, keep
+
+
+# --------------------------------------------------------------------------- particle re-sharding
+def exchange_plan(out_ranges, bounds, rank):
+    """Who sends what after a sharded resample (the gather ``particles[indexes]``
+    that follows a resample crosses shards).
+
+    Rank r emitted the indexes of the output positions ``out_ranges[r] = [o_r, o_r+1)``; every one
+    of them points into r's OWN particle shard, so r can gather those rows locally.  The new
+    particle set is sharded evenly again by ``bounds`` (``shard_bounds(n, world)``), so r must ship
+    the rows of positions ``[max(o_r, b_d), min(o_r+1, b_d+1))`` to rank d.  Returns
+    ``(sends, recvs)``: ``sends`` = list of (dst, lo, hi) in positions relative to o_r,
+    ``recvs`` = list of (src, lo, hi) relative to b_rank — both ordered by peer rank."""
+    world = len(bounds) - 1
+    o_lo, o_hi = int(out_ranges[rank][0]), int(out_ranges[rank][1])
+    sends, recvs = [], []
+    for d in range(world):
+        lo, hi = max(o_lo, int(bounds[d])), min(o_hi, int(bounds[d + 1]))
+        if hi > lo:
+            sends.append((d, lo - o_lo, hi - o_lo))
+    b_lo, b_hi = int(bounds[rank]), int(bounds[rank + 1])
+    for s_ in range(world):
+        lo, hi = max(int(out_ranges[s_][0]), b_lo), min(int(out_ranges[s_][1]), b_hi)
+        if hi > lo:
+            recvs.append((s_, lo - b_lo, hi - b_lo))
+    return sends, recvs
+
+
+def exchange_rows(rows, out, sends, recvs, group=None):
+    """Point-to-point all-to-all-v of contiguous row slices: ``rows[lo:hi]`` to every (dst, lo, hi)
+    of ``sends``, ``out[lo:hi]`` from every (src, lo, hi) of ``recvs``; slices for this rank itself
+    are copied.  Works on NCCL (GPU tensors, over NVLink) and gloo (CPU tensors, tests)."""
+    rank = dist.get_rank(group) if (dist.is_available() and dist.is_initialized()) else 0
+
+    def peer(r):
+        return dist.get_global_rank(group, r) if group is not None else r
+    ops = []
+    self_send = [x for x in sends if x[0] == rank]
+    self_recv = [x for x in recvs if x[0] == rank]
+    for (_, slo, shi), (_, rlo, rhi) in zip(self_send, self_recv):
+        out[rlo:rhi].copy_(rows[slo:shi])
+    for src, lo, hi in recvs:
+        if src != rank:
+            ops.append(dist.P2POp(dist.irecv, out[lo:hi], peer(src), group))
+    for dst, lo, hi in sends:
+        if dst != rank:
+            ops.append(dist.P2POp(dist.isend, rows[lo:hi], peer(dst), group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return out
+
+
+def redistribute_after_resample(particles_local, idx_local, out_range, n_global, group=None):
+    """The step after a sharded resample, on the GPU: ``new_particles = particles[indexes]`` with
+    the result sharded evenly again.  ``particles_local`` is this rank's shard (rows b_r..b_r+1),
+    ``idx_local`` / ``out_range`` what ``sharded_systematic_resample`` returned (global particle
+    numbers of the output positions ``[out_range[0], out_range[1])``).  Local gather with
+    ``bke_gather_rows``, then one point-to-point exchange of contiguous slices."""
+    from .monte_carlo import gather_particles
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    bounds = shard_bounds(n_global, world)
+    rng_t = out_range if isinstance(out_range, torch.Tensor) else torch.as_tensor(out_range)
+    if world > 1:
+        allr = [torch.zeros_like(rng_t) for _ in range(world)]
+        dist.all_gather(allr, rng_t.contiguous(), group=group)
+        out_ranges = [tuple(int(v) for v in t.tolist()) for t in allr]
+    else:
+        out_ranges = [tuple(int(v) for v in rng_t.tolist())]
+    cnt = out_ranges[rank][1] - out_ranges[rank][0]
+    local_idx = (idx_local[:cnt].to(torch.int64) - int(bounds[rank])).to(torch.int32)
+    rows = gather_particles(particles_local, local_idx)                 # every index is in this rank's shard
+    out = torch.empty((int(bounds[rank + 1] - bounds[rank]),) + tuple(particles_local.shape[1:]),
+                      dtype=particles_local.dtype, device=particles_local.device)
+    sends, recvs = exchange_plan(out_ranges, bounds, rank)
+    return exchange_rows(rows, out, sends, recvs, group)

@@ -36,4 +36,21 @@ if rank == 0:
     want = ors.systematic_resample_c(w, u)
     print("world", world, "N=2^%d" % lg, "bit-exact:", bool(np.array_equal(out, want)), "ranges", [(p[0], p[1]) for p in parts],
           "info", [p[3] for p in parts], "max-rank ms %.3f" % float(ms.item()), flush=True)
+# the step after: particles[idx], re-sharded evenly (local gather + slice exchange over NVLink)
+particles = np.random.default_rng(11).normal(size=(N, 4)).astype(np.float32)
+p_loc = torch.from_numpy(particles[int(b[rank]):int(b[rank + 1])]).cuda()
+for it in range(3):
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    new_loc = bd.redistribute_after_resample(p_loc, idx, rng_t, N)
+    e1.record()
+    torch.cuda.synchronize()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device="cuda"); dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+want_idx = ors.systematic_resample_c(w, u)
+ok_loc = bool(np.array_equal(new_loc.cpu().numpy(), particles[want_idx][int(b[rank]):int(b[rank + 1])]))
+oks = [None] * world
+dist.all_gather_object(oks, ok_loc)
+if rank == 0:
+    print("redistribute particles[idx]: exact on every rank:", all(oks), "max-rank ms %.3f" % float(ms2.item()), flush=True)
 dist.destroy_process_group()

@@ -102,6 +102,15 @@ assert local.size == 0 or (local.min() >= b[rank] and local.max() < b[rank + 1])
 cnts = [None] * world
 dist.all_gather_object(cnts, (lo, hi))
 assert cnts[0][0] == 0 and all(cnts[i][1] == cnts[i + 1][0] for i in range(world - 1)) and cnts[-1][1] == len(wts)
+# (4) re-sharding after the resample: local gather of the rank's own rows + contiguous slice exchange == particles[idx]
+particles = np.random.default_rng(5).normal(size=(len(wts), 3))
+mine_p = bd.shard_of(particles, rank, world)
+rows = torch.from_numpy(mine_p[local - b[rank]])                 # the local gather (bke_gather_rows on the GPU)
+sends, recvs = bd.exchange_plan(cnts, b, rank)
+assert sum(h - l for _, l, h in sends) == hi - lo and sum(h - l for _, l, h in recvs) == b[rank + 1] - b[rank]
+out = torch.empty(int(b[rank + 1] - b[rank]), 3, dtype=torch.float64)
+bd.exchange_rows(rows, out, sends, recvs)
+assert np.array_equal(out.numpy(), particles[idx][b[rank]:b[rank + 1]])
 dist.barrier()
 dist.destroy_process_group()
 sys.stdout.write("rank %d ok\n" % rank)
