@@ -64,16 +64,16 @@ __global__ void __launch_bounds__(256) k_mm_mix(MixP<T> p)
         if (g < nx) {
             const int64_t t = div_idx(g, n, small);
             const double *om = p.w + t * p.sw;
-            double xj[MA];
+            T xj[MA];
 #pragma unroll
-            for (int j = 0; j < MA; j++) if (j < M) xj[j] = (double)p.x[j][g];
+            for (int j = 0; j < MA; j++) if (j < M) xj[j] = p.x[j][g];
 #pragma unroll
             for (int i = 0; i < MA; i++) {
                 if (i < M) {
-                    double s = 0.0;
+                    T s = T(0);
 #pragma unroll
-                    for (int j = 0; j < MA; j++) if (j < M) s += xj[j] * om[j * M + i];
-                    p.xo[i][g] = (T)s;
+                    for (int j = 0; j < MA; j++) if (j < M) s += xj[j] * (T)om[j * M + i];
+                    p.xo[i][g] = s;
                 }
             }
         } else {
@@ -81,26 +81,26 @@ __global__ void __launch_bounds__(256) k_mm_mix(MixP<T> p)
             const int64_t t = div_idx(q, nn, small);
             const int rc = (int)(q - t * nn), r = rc / n, c = rc - r * n;
             const double *om = p.w + t * p.sw;
-            double xr[MA], xc[MA], Pj[MA];
+            T xr[MA], xc[MA], Pj[MA];
 #pragma unroll
             for (int j = 0; j < MA; j++) {
                 if (j < M) {
-                    xr[j] = (double)p.x[j][t * n + r];
-                    xc[j] = (double)p.x[j][t * n + c];
-                    Pj[j] = (double)p.P[j][q];
+                    xr[j] = p.x[j][t * n + r];
+                    xc[j] = p.x[j][t * n + c];
+                    Pj[j] = p.P[j][q];
                 }
             }
 #pragma unroll
             for (int i = 0; i < MA; i++) {
                 if (i < M) {
-                    double mr = 0.0, mc = 0.0;
+                    T w[MA];
+                    T mr = T(0), mc = T(0);                 // the mixed mean, in the precision it is stored in
 #pragma unroll
-                    for (int j = 0; j < MA; j++) if (j < M) { const double w = om[j * M + i]; mr += xr[j] * w; mc += xc[j] * w; }
-                    if (sizeof(T) == 4) { mr = (double)(T)mr; mc = (double)(T)mc; }     // the mixed mean as it is stored
-                    double s = 0.0;
+                    for (int j = 0; j < MA; j++) if (j < M) { w[j] = (T)om[j * M + i]; mr += xr[j] * w[j]; mc += xc[j] * w[j]; }
+                    T s = T(0);
 #pragma unroll
-                    for (int j = 0; j < MA; j++) if (j < M) s += om[j * M + i] * ((xr[j] - mr) * (xc[j] - mc) + Pj[j]);
-                    p.Po[i][q] = (T)s;
+                    for (int j = 0; j < MA; j++) if (j < M) s += w[j] * ((xr[j] - mr) * (xc[j] - mc) + Pj[j]);
+                    p.Po[i][q] = s;
                 }
             }
         }
@@ -120,40 +120,38 @@ __global__ void __launch_bounds__(256) k_mm_estimate(MixP<T> p)
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
         if (g < nx) {
             const double *mu = p.w + div_idx(g, n, small) * p.sw;
-            double s = 0.0;
+            T s = T(0);
 #pragma unroll
-            for (int j = 0; j < MA; j++) if (j < M) s += (double)p.x[j][g] * mu[j];
-            p.xo[0][g] = (T)s;
+            for (int j = 0; j < MA; j++) if (j < M) s += p.x[j][g] * (T)mu[j];
+            p.xo[0][g] = s;
         } else {
             const int64_t q = g - nx;
             const int64_t t = div_idx(q, nn, small);
             const int rc = (int)(q - t * nn), r = rc / n, c = rc - r * n;
             const double *mu = p.w + t * p.sw;
-            double s = 0.0;
+            T s = T(0);
             if (!mmae) {
-                double xr[MA], xc[MA], mr = 0.0, mc = 0.0;
+                T xr[MA], xc[MA], w[MA], mr = T(0), mc = T(0);
 #pragma unroll
                 for (int j = 0; j < MA; j++) {
                     if (j < M) {
-                        xr[j] = (double)p.x[j][t * n + r]; xc[j] = (double)p.x[j][t * n + c];
-                        mr += xr[j] * mu[j]; mc += xc[j] * mu[j];
+                        xr[j] = p.x[j][t * n + r]; xc[j] = p.x[j][t * n + c]; w[j] = (T)mu[j];
+                        mr += xr[j] * w[j]; mc += xc[j] * w[j];
                     }
                 }
-                if (sizeof(T) == 4) { mr = (double)(T)mr; mc = (double)(T)mc; }
 #pragma unroll
-                for (int j = 0; j < MA; j++) if (j < M) s += mu[j] * ((xr[j] - mr) * (xc[j] - mc) + (double)p.P[j][q]);
+                for (int j = 0; j < MA; j++) if (j < M) s += w[j] * ((xr[j] - mr) * (xc[j] - mc) + p.P[j][q]);
             } else {
                 // mmae.py:197-199 zips the COMPONENTS of the mixed x with the filters: term j uses
                 // y = f_j.x - x[j] (a scalar), and only min(dim_x, M) terms exist
                 const int terms = M < n ? M : n;
                 for (int j = 0; j < terms; j++) {
-                    double mj = 0.0;
-                    for (int k = 0; k < M; k++) mj += (double)p.x[k][t * n + j] * mu[k];
-                    if (sizeof(T) == 4) mj = (double)(T)mj;
-                    s += mu[j] * (((double)p.x[j][t * n + r] - mj) * ((double)p.x[j][t * n + c] - mj) + (double)p.P[j][q]);
+                    T mj = T(0);
+                    for (int k = 0; k < M; k++) mj += p.x[k][t * n + j] * (T)mu[k];
+                    s += (T)mu[j] * ((p.x[j][t * n + r] - mj) * (p.x[j][t * n + c] - mj) + p.P[j][q]);
                 }
             }
-            p.Po[0][q] = (T)s;
+            p.Po[0][q] = s;
         }
     }
 }

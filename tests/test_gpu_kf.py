@@ -356,6 +356,6 @@ def test_shared_models_in_launch_parameters_equal_device_models(golden, diagnost
     from oracle import kf as okf
     x, P = g["x"].copy(), g["P"].copy()
     for t in range(3):
-        x, P = okf.kf_predict_bank(x, P, g["F"][0], g["Q"][0])
-        x, P = okf.kf_update_bank(x, P, g["zs"][t], g["H"][0], g["R"][0])[:2]
+        o = okf.kf_step_bank(x, P, g["zs"][t], g["F"][0], g["H"][0], g["Q"][0], g["R"][0])
+        x, P = o["x"], o["P"]
     np.testing.assert_allclose(outs[0][0], x, rtol=1e-3, atol=1e-3 * np.abs(x).max())
