@@ -53,6 +53,20 @@ def build(force=False, verbose=False, extra_flags=()):
         raise RuntimeError("nvcc not found and %s is missing or stale" % LIB)
     os.makedirs(OUT_DIR, exist_ok=True)
     os.makedirs(OBJ_DIR, exist_ok=True)
+    # one builder at a time: the ranks of a torchrun job may all find the library stale
+    import fcntl
+    lock = open(os.path.join(OUT_DIR, ".build.lock"), "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if not force and not needs_build():
+            return LIB
+        return _build_locked(nvcc, force, verbose, extra_flags)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(nvcc, force, verbose, extra_flags):
     hdr_t = max(os.path.getmtime(p) for p in _deps())
 
     def compile_one(src):

@@ -476,8 +476,8 @@ int launch_variant(const Maps &maps, const FastP<4, 2> &p, cudaStream_t s)
     static const int stages_env = env_int("BKE_KF_STAGES", 0);
     static const int ctas_env = env_int("BKE_KF_CTAS", 0);
     if (SHARED) {      // 11 KB per stage
-        constexpr int MAXC = SHARED == 2 ? 5 : 4;
-        const int ctas = ctas_env > 0 ? (ctas_env > MAXC ? MAXC : ctas_env) : MAXC;
+        constexpr int MAXC = SHARED == 2 ? 7 : 4, DEFC = SHARED == 2 ? 5 : 4;
+        const int ctas = ctas_env > 0 ? (ctas_env > MAXC ? MAXC : ctas_env) : DEFC;
         if (stages_env == 3) return launch_variant_s<MODE, SHARED, EXTRAS, 3>(maps, p, s, ctas);
         return launch_variant_s<MODE, SHARED, EXTRAS, 2>(maps, p, s, ctas);
     }
