@@ -59,50 +59,76 @@ def ncu_traffic():
 
 # ----------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
+    """SM clock and throttle reasons sampled from NVML while a region runs.  NVML is initialised
+    when the object is built (outside any timed region); the thread polls every millisecond, so even
+    a few-millisecond region is covered.  ``with sampler.region("name"):`` may be used several
+    times; ``summary()`` reports the median over the device-timed steps and, when that region was
+    too short to be caught, over the e2e steps (``sampled_in`` says which)."""
+
     def __init__(self, index):
         self.index = index
-        self.samples = []
+        self.samples = {}
         self.reasons = set()
         self.max_mhz = None
+        self._h = None
         self._stop = threading.Event()
         self._th = None
-
-    def _run(self):
+        self._name = None
         try:
             import pynvml
+            self._nv = pynvml
             pynvml.nvmlInit()
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
-            names = {
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+            self._names = {
                 getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
                 getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
                 getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
                 getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
             }
-            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            self._get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
                 getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
-            while not self._stop.is_set():
-                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
-                r = get_reasons(h)
-                for bit, nm in names.items():
-                    if r & bit:
-                        self.reasons.add(nm)
-                time.sleep(0.02)
         except Exception as e:  # no NVML: report nothing rather than guess
             self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
 
+    def _sample(self):
+        self.samples.setdefault(self._name, []).append(self._nv.nvmlDeviceGetClockInfo(self._h, self._nv.NVML_CLOCK_SM))
+        r = self._get_reasons(self._h)
+        for bit, nm in self._names.items():
+            if r & bit:
+                self.reasons.add(nm)
+
+    def _run(self):
+        try:
+            while not self._stop.is_set():
+                self._sample()
+                time.sleep(0.001)
+        except Exception as e:
+            self.reasons.add("nvml_error:%s" % type(e).__name__)
+
+    def region(self, name):
+        self._name = name
+        return self
+
     def __enter__(self):
-        self._th = threading.Thread(target=self._run, daemon=True)
-        self._th.start()
+        if self._h is not None:
+            self._stop.clear()
+            self._th = threading.Thread(target=self._run, daemon=True)
+            self._th.start()
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._th.join(timeout=2)
+        if self._th is not None:
+            self._stop.set()
+            self._th.join(timeout=2)
+            self._th = None
 
     def summary(self):
-        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
-                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        for name in ("device_timed_steps", "e2e_steps"):
+            if self.samples.get(name):
+                return {"sm_mhz": float(np.median(self.samples[name])), "sm_max_mhz": self.max_mhz,
+                        "reasons": sorted(self.reasons), "sampled_in": name, "n_samples": len(self.samples[name])}
+        return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
 # ----------------------------------------------------------------------------- CPU legs
@@ -246,6 +272,7 @@ def run_ours(args, rank, world, local_rank):
         for i in range(Z_RING):
             step_resident(i)
 
+    clk = ClockSampler(local_rank)            # NVML is initialised here, outside every timed region
     use_graph = not args.no_graph
     graph = kf.capture(ring) if use_graph else None
     reset()
@@ -256,7 +283,7 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     reps, rem = (K // Z_RING, K % Z_RING) if graph is not None else (0, K)
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(reps + rem + 1)]
-    with ClockSampler(local_rank) as clk:
+    with clk.region("device_timed_steps"):
         evs[0].record()
         for r in range(reps):
             graph.replay()
@@ -306,12 +333,13 @@ def run_ours(args, rank, world, local_rank):
             step_e2e(i, with_P)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(K):
-            step_e2e(i, with_P)
-        torch.cuda.current_stream(dev).wait_stream(copy_stream)
-        e1.record()
-        barrier()
+        with clk.region("e2e_steps"):
+            e0.record()
+            for i in range(K):
+                step_e2e(i, with_P)
+            torch.cuda.current_stream(dev).wait_stream(copy_stream)
+            e1.record()
+            barrier()
         return max_over_ranks(e0.elapsed_time(e1))
 
     e2e_ms = run_e2e(False)
