@@ -101,6 +101,7 @@ int bke_kf_step(const bke_kf_args *args, void *stream)
     if (args->n_filters == 0) return BKE_OK;
     cudaStream_t s = (cudaStream_t)stream;
     rc = launch_kf_fast(*args, s);
+    if (rc == BKE_ERR_UNSUPPORTED) rc = launch_kf_direct(*args, s);
     if (rc == BKE_ERR_UNSUPPORTED) rc = launch_kf_rowblock(*args, s);
     if (rc == BKE_ERR_UNSUPPORTED) rc = launch_kf_generic(*args, s);
     return rc;

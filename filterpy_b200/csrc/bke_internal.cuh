@@ -27,6 +27,7 @@ int launch_kf_generic(const bke_kf_args &a, cudaStream_t s);
 // returns BKE_ERR_UNSUPPORTED when the specialised kernel does not cover the call
 int launch_kf_fast(const bke_kf_args &a, cudaStream_t s);
 int launch_kf_rowblock(const bke_kf_args &a, cudaStream_t s);
+int launch_kf_direct(const bke_kf_args &a, cudaStream_t s);
 int launch_kf_batch(const bke_kf_batch_args &a, cudaStream_t s);
 int launch_ukf(const bke_ukf_args &a, cudaStream_t s);
 

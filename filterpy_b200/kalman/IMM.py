@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from .. import _lib
-from .._dev import bke_dtype, ptr, stream_ptr
+from .._dev import StepGraph, bke_dtype, ptr, stream_ptr
 
 __all__ = ["IMMEstimator"]
 
@@ -148,6 +148,13 @@ class IMMEstimator(object):
         a = _mm_args(self.filters, flags=_lib.BKE_MM_FROM_MU)
         a.mu, a.cbar, a.omega, a.trans = ptr(self._mu), ptr(self._cbar), ptr(self._omega), ptr(self._M)
         self._call(self._lib.bke_mm_probabilities, a)
+
+    def capture(self, fn, warmup=2):
+        """Capture ``fn`` — a fixed sequence of ``predict()`` / ``update(z_buffer)`` calls — into a CUDA
+        graph (``.replay()``); one IMM step is ~15 small launches, so the host side dominates otherwise.
+        The model filters' state buffers rotate with period 3 (state, stored posterior, spare), so
+        ``fn`` must run a multiple of 3 steps for a replay to find the buffers where it left them."""
+        return StepGraph(fn, self._device, warmup)
 
     def __repr__(self):
         return "IMMEstimator (B200): %d models x %d tracks, dim_x=%d" % (self.N, self.n_tracks, self.filters[0].dim_x)

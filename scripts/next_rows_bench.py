@@ -86,6 +86,9 @@ def main():
     e = 4 + 16
     report("IMM predict+update, 2^20 tracks x 3 models 4/2 fp32 (mixing traffic only)", timeit(imm_step), N,
            (2 * M * e + 2 * (M * e + e)) * 4)
+    g3 = imm.capture(lambda: [imm_step() for _ in range(3)])
+    report("IMM predict+update as a CUDA graph of 3 steps (per step)", timeit(g3.replay) / 3, N,
+           (2 * M * e + 2 * (M * e + e)) * 4)
     ms_mix = timeit(lambda: imm._compute_state_estimate())
     report("IMM combined estimate alone", ms_mix, N, (M * e + e) * 4)
 
