@@ -80,6 +80,17 @@ static int validate_kf(const bke_kf_args *a, bool need_z)
 
 using namespace bke;
 
+namespace bke {
+int launch_kf_any(const bke_kf_args &a, cudaStream_t s)
+{
+    int rc = launch_kf_fast(a, s);
+    if (rc == BKE_ERR_UNSUPPORTED) rc = launch_kf_direct(a, s);
+    if (rc == BKE_ERR_UNSUPPORTED) rc = launch_kf_rowblock(a, s);
+    if (rc == BKE_ERR_UNSUPPORTED) rc = launch_kf_generic(a, s);
+    return rc;
+}
+}  // namespace bke
+
 extern "C" {
 
 int bke_abi_version(void) { return BKE_ABI_VERSION; }
@@ -100,11 +111,7 @@ int bke_kf_step(const bke_kf_args *args, void *stream)
     if ((rc = require_device())) return rc;
     if (args->n_filters == 0) return BKE_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    rc = launch_kf_fast(*args, s);
-    if (rc == BKE_ERR_UNSUPPORTED) rc = launch_kf_direct(*args, s);
-    if (rc == BKE_ERR_UNSUPPORTED) rc = launch_kf_rowblock(*args, s);
-    if (rc == BKE_ERR_UNSUPPORTED) rc = launch_kf_generic(*args, s);
-    return rc;
+    return launch_kf_any(*args, s);
 }
 
 int bke_kf_batch_filter(const bke_kf_batch_args *args, void *stream)

@@ -143,21 +143,18 @@ int launch_host_loop(const bke_kf_batch_args &a, cudaStream_t s)
         int rc;
         if (!uf) {
             k.x_out = post_x; k.P_out = post_P; k.x_prior = prior_x; k.P_prior = prior_P;
-            rc = launch_kf_fast(k, s);
-            if (rc == BKE_ERR_UNSUPPORTED) rc = launch_kf_generic(k, s);
+            rc = launch_kf_any(k, s);
             if (rc) return rc;
             xin = post_x; Pin = post_P;
         } else {
             // update -> means[t]; predict -> means_p[t] which also feeds epoch t+1
             bke_kf_args ku = k; ku.flags = BKE_DO_UPDATE; ku.x_out = post_x; ku.P_out = post_P; ku.x_prior = ku.P_prior = nullptr;
-            rc = launch_kf_fast(ku, s);
-            if (rc == BKE_ERR_UNSUPPORTED) rc = launch_kf_generic(ku, s);
+            rc = launch_kf_any(ku, s);
             if (rc) return rc;
             bke_kf_args kp = k; kp.flags = BKE_DO_PREDICT; kp.x = post_x; kp.P = post_P;
             kp.x_out = prior_x ? prior_x : (char *)k0.x_out; kp.P_out = prior_P ? prior_P : (char *)k0.P_out;
             kp.x_prior = kp.P_prior = nullptr; kp.status = nullptr;
-            rc = launch_kf_fast(kp, s);
-            if (rc == BKE_ERR_UNSUPPORTED) rc = launch_kf_generic(kp, s);
+            rc = launch_kf_any(kp, s);
             if (rc) return rc;
             xin = (const char *)kp.x_out; Pin = (const char *)kp.P_out;
         }

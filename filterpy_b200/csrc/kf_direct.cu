@@ -1,7 +1,7 @@
 // kf_direct.cu — thread-per-filter predict/update with the filter's arrays loaded straight from
 // global memory into a register tile (csrc/kf_regtile.cuh), for the small shapes that have neither
 // the TMA-staged kernel (4/2 fp32, csrc/kf_fast.cu) nor a good fit in the row-block kernel:
-// 4/2 fp64 (the reference's default dtype), 2/1 and 1/1.
+// 4/2 fp64 (the reference's default dtype), 1/1, 2/1, 2/2, 3/1, 4/1, 4/4, and 6/3, 6/2 in fp32.
 //
 // Same arithmetic as kf_fast.cu (filterpy/kalman/kalman_filter.py:471-478 predict, :533-556
 // update); every thread reads its own rows of the AoS arrays with 16-byte loads — a row is 32-128
@@ -147,6 +147,13 @@ int dispatch(const bke_kf_args &a, cudaStream_t s)
     if (a.dim_x == 2 && a.dim_z == 1) return launch_inst<T, 2, 1>(a, s);
     if (a.dim_x == 1 && a.dim_z == 1) return launch_inst<T, 1, 1>(a, s);
     if (a.dim_x == 2 && a.dim_z == 2) return launch_inst<T, 2, 2>(a, s);
+    if (a.dim_x == 3 && a.dim_z == 1) return launch_inst<T, 3, 1>(a, s);
+    if (a.dim_x == 4 && a.dim_z == 1) return launch_inst<T, 4, 1>(a, s);
+    if (a.dim_x == 4 && a.dim_z == 4) return launch_inst<T, 4, 4>(a, s);
+    if constexpr (sizeof(T) == 4) {      // a 6 x 6 fp64 tile does not fit the register file: row-block kernel
+        if (a.dim_x == 6 && a.dim_z == 3) return launch_inst<T, 6, 3>(a, s);
+        if (a.dim_x == 6 && a.dim_z == 2) return launch_inst<T, 6, 2>(a, s);
+    }
     return BKE_ERR_UNSUPPORTED;
 }
 

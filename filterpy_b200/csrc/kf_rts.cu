@@ -63,9 +63,12 @@ __global__ void __launch_bounds__(128) rts_reg_kernel(RtsP<T> p)
 {
     const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= p.N) return;
+    // fp32: F, Q and the prefetched epoch k-1 all live in registers (168); fp64 at n = 4 would need
+    // ~290, so Q is re-read every epoch (an L1 hit) and nothing is prefetched
+    constexpr bool LEAN = sizeof(T) == 8 && N >= 4;
     T F[N][N], Q[N][N];
     ld<T, N * N>(&F[0][0], p.F + f * p.sF);
-    ld<T, N * N>(&Q[0][0], p.Q + f * p.sQ);
+    if constexpr (!LEAN) ld<T, N * N>(&Q[0][0], p.Q + f * p.sQ);
     T xs[N], Ps[N][N];                                  // smoothed state of epoch k+1
     int64_t tf = (p.Tn - 1) * p.N + f;
     ld<T, N>(xs, p.Xs + tf * N);
@@ -89,9 +92,13 @@ __global__ void __launch_bounds__(128) rts_reg_kernel(RtsP<T> p)
     for (int64_t k = p.Tn - 2; k >= 0; k--) {
         // prefetch epoch k-1 while epoch k computes
         T xn[N], Pn[N][N];
-        if (k > 0) {
-            ld<T, N>(xn, p.Xs + (tf - p.N) * N);
-            ld<T, N * N>(&Pn[0][0], p.Ps + (tf - p.N) * N * N);
+        if constexpr (!LEAN) {
+            if (k > 0) {
+                ld<T, N>(xn, p.Xs + (tf - p.N) * N);
+                ld<T, N * N>(&Pn[0][0], p.Ps + (tf - p.N) * N * N);
+            }
+        } else {
+            ld<T, N * N>(&Q[0][0], p.Q + f * p.sQ);
         }
         T FP[N][N], Pp[N][N], PFt[N][N];
 #pragma unroll
@@ -167,11 +174,22 @@ __global__ void __launch_bounds__(128) rts_reg_kernel(RtsP<T> p)
         if (p.Pp) st<T, N * N>(p.Pp + tf * N * N, &Pp[0][0]);
 #pragma unroll
         for (int i = 0; i < N; i++) {
-            xs[i] = xk[i]; xk[i] = xn[i];
+            xs[i] = xk[i];
 #pragma unroll
-            for (int j = 0; j < N; j++) { Ps[i][j] = Pk[i][j]; Pk[i][j] = Pn[i][j]; }
+            for (int j = 0; j < N; j++) Ps[i][j] = Pk[i][j];
         }
         tf -= p.N;
+        if constexpr (!LEAN) {
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                xk[i] = xn[i];
+#pragma unroll
+                for (int j = 0; j < N; j++) Pk[i][j] = Pn[i][j];
+            }
+        } else if (k > 0) {
+            ld<T, N>(xk, p.Xs + tf * N);
+            ld<T, N * N>(&Pk[0][0], p.Ps + tf * N * N);
+        }
     }
     if (p.status) p.status[f] = stt;
 }

@@ -16,10 +16,13 @@
 // omega) are re-read by the threads of a track from L1.  All HBM-bound: per track the mix reads and
 // writes M (n + n^2) scalars.
 #include <float.h>
+#include <type_traits>
 #include "bke_internal.cuh"
 
 namespace bke {
 namespace {
+
+unsigned grid_for(int64_t work);
 
 template <typename T>
 struct MixP {
@@ -156,6 +159,109 @@ __global__ void __launch_bounds__(256) k_mm_estimate(MixP<T> p)
     }
 }
 
+// Row-parallel kernels for compile-time (dim_x, model count): one thread per (track, row r of P).  It
+// loads each model's whole x and row r of its P with 16-byte loads, forms the mixed mean once and
+// writes row r of every output covariance (plus element r of the mean): no redundant work across
+// the threads of a row, a quarter of the threads of the element-parallel form.
+template <typename T, int CNT>
+__device__ __forceinline__ void ld_row(T *dst, const T *src)
+{
+    constexpr int VEC = 16 / sizeof(T);
+    if constexpr (CNT % VEC == 0) {
+        using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+#pragma unroll
+        for (int i = 0; i < CNT / VEC; i++) *reinterpret_cast<V *>(dst + i * VEC) = __ldg(reinterpret_cast<const V *>(src) + i);
+    } else {
+#pragma unroll
+        for (int i = 0; i < CNT; i++) dst[i] = __ldg(src + i);
+    }
+}
+template <typename T, int CNT>
+__device__ __forceinline__ void st_row(T *dst, const T *src)
+{
+    constexpr int VEC = 16 / sizeof(T);
+    if constexpr (CNT % VEC == 0) {
+        using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+#pragma unroll
+        for (int i = 0; i < CNT / VEC; i++) reinterpret_cast<V *>(dst)[i] = *reinterpret_cast<const V *>(src + i * VEC);
+    } else {
+#pragma unroll
+        for (int i = 0; i < CNT; i++) dst[i] = src[i];
+    }
+}
+
+// MIX = true: IMM.py:201-213 for every target model; MIX = false: IMM.py:228-237 (one output)
+template <typename T, int NX, int MM, bool MIX>
+__global__ void __launch_bounds__(256) k_mm_rows(MixP<T> p)
+{
+    const int64_t total = p.N * NX;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = g / NX;
+        const int r = (int)(g - t * NX);
+        T xv[MM][NX], Pr[MM][NX];
+#pragma unroll
+        for (int j = 0; j < MM; j++) {
+            ld_row<T, NX>(xv[j], p.x[j] + t * NX);
+            ld_row<T, NX>(Pr[j], p.P[j] + g * NX);
+        }
+        const double *wd = p.w + t * p.sw;
+        constexpr int OUTS = MIX ? MM : 1;
+#pragma unroll
+        for (int i = 0; i < OUTS; i++) {
+            T w[MM], m[NX];
+#pragma unroll
+            for (int j = 0; j < MM; j++) w[j] = (T)(MIX ? wd[j * MM + i] : wd[j]);
+#pragma unroll
+            for (int c = 0; c < NX; c++) {
+                T a = T(0);
+#pragma unroll
+                for (int j = 0; j < MM; j++) a += xv[j][c] * w[j];
+                m[c] = a;
+            }
+            T mr = T(0), xr[MM];
+#pragma unroll
+            for (int c = 0; c < NX; c++) if (c == r) mr = m[c];
+#pragma unroll
+            for (int j = 0; j < MM; j++) {
+                T v = T(0);
+#pragma unroll
+                for (int c = 0; c < NX; c++) if (c == r) v = xv[j][c];
+                xr[j] = v - mr;
+            }
+            T out[NX];
+#pragma unroll
+            for (int c = 0; c < NX; c++) {
+                T sacc = T(0);
+#pragma unroll
+                for (int j = 0; j < MM; j++) sacc += w[j] * (xr[j] * (xv[j][c] - m[c]) + Pr[j][c]);
+                out[c] = sacc;
+            }
+            st_row<T, NX>(p.Po[i] + g * NX, out);
+            p.xo[i][g] = mr;
+        }
+    }
+}
+
+template <typename T, int NX, int MM>
+bool launch_rows(const MixP<T> &p, int op, cudaStream_t s)
+{
+    const unsigned grid = grid_for(p.N * NX);
+    if (op == 1) k_mm_rows<T, NX, MM, true><<<grid, 256, 0, s>>>(p);
+    else k_mm_rows<T, NX, MM, false><<<grid, 256, 0, s>>>(p);
+    return true;
+}
+
+template <typename T, int NX>
+bool launch_rows_m(const MixP<T> &p, int op, cudaStream_t s)
+{
+    switch (p.M) {
+    case 2: return launch_rows<T, NX, 2>(p, op, s);
+    case 3: return launch_rows<T, NX, 3>(p, op, s);
+    case 4: return launch_rows<T, NX, 4>(p, op, s);
+    default: return false;
+    }
+}
+
 // mode probabilities, one thread per track
 template <typename T>
 __global__ void __launch_bounds__(256) k_mm_probabilities(MixP<T> p)
@@ -175,18 +281,19 @@ __global__ void __launch_bounds__(256) k_mm_probabilities(MixP<T> p)
                 mu[j] = prior * L;
                 sum += mu[j];
             }
-            for (int j = 0; j < M; j++) { mu[j] /= sum; p.mu[t * M + j] = mu[j]; }
+            const double rs = 1.0 / sum;                    // one division per track; the products differ from x / sum by <= 1 ulp
+            for (int j = 0; j < M; j++) { mu[j] *= rs; p.mu[t * M + j] = mu[j]; }
         }
         if (mmae) continue;
         double cb[BKE_MM_MAX_MODELS];
         for (int j = 0; j < M; j++) {
             double s = 0.0;
             for (int i = 0; i < M; i++) s += mu[i] * p.trans[i * M + j];
-            cb[j] = s;
+            cb[j] = 1.0 / s;
             p.cbar[t * M + j] = s;
         }
         for (int i = 0; i < M; i++)
-            for (int j = 0; j < M; j++) p.omega[(t * M + i) * M + j] = (p.trans[i * M + j] * mu[i]) / cb[j];
+            for (int j = 0; j < M; j++) p.omega[(t * M + i) * M + j] = (p.trans[i * M + j] * mu[i]) * cb[j];
     }
 }
 
@@ -211,6 +318,20 @@ int launch_t(const bke_mm_args &a, int op, cudaStream_t s)
     p.mu = a.mu; p.cbar = a.cbar; p.omega = a.omega; p.trans = a.trans;
     const int64_t E = a.dim_x + (int64_t)a.dim_x * a.dim_x;
     const unsigned ge = grid_for((p.N * E + 1) / 2);
+    if (op != 0 && !(a.flags & BKE_MM_MMAE)) {
+        // row-parallel form for the common shapes, when 16-byte accesses are possible
+        bool aligned = true;
+        for (int j = 0; j < p.M; j++)
+            aligned = aligned && ((reinterpret_cast<uintptr_t>(p.x[j]) | reinterpret_cast<uintptr_t>(p.P[j])) & 15) == 0;
+        const int outs = op == 1 ? p.M : 1;
+        for (int j = 0; j < outs; j++) aligned = aligned && (reinterpret_cast<uintptr_t>(p.Po[j]) & 15) == 0;
+        p.w = op == 1 ? a.omega : a.mu; p.sw = a.weights_stride;
+        bool done = false;
+        if (aligned && p.n == 4) done = launch_rows_m<T, 4>(p, op, s);
+        else if (aligned && p.n == 6) done = launch_rows_m<T, 6>(p, op, s);
+        else if (aligned && p.n == 2) done = launch_rows_m<T, 2>(p, op, s);
+        if (done) return check_cuda(cudaGetLastError(), "mm launch");
+    }
     if (op == 0) {
         k_mm_probabilities<T><<<grid_for(p.N), 256, 0, s>>>(p);
     } else if (op == 1) {

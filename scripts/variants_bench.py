@@ -54,6 +54,15 @@ def main():
     kf_case("kf 4/2 f64 (row-block kernel) 2^20", 4, 2, 1 << 20, np.float64, lambda N, steps: wl.kf_bank_cv2d(N, steps=steps))
     kf_case("C3 kf 9/3 f64 (row-block kernel) 1.25M", 9, 3, 1250000, np.float64, lambda N, steps: wl.kf_bank_ca3d(N, steps=steps))
     kf_case("kf 9/3 f32 (generic kernel) 1.25M", 9, 3, 1250000, np.float32, lambda N, steps: wl.kf_bank_ca3d(N, steps=steps))
+    # 6/3 (3-D constant velocity with a linear position sensor): fp32 -> direct kernel, fp64 -> row-block kernel
+    def cv3d(N, steps):
+        u = wl.ukf_bank_cv3d(min(N, 1 << 14), steps=steps, linear_hx=True)
+        r = max(1, N // u["x"].shape[0])
+        tile = lambda a, lead: np.tile(a, (r,) + (1,) * (a.ndim - 1)) if lead else a     # noqa: E731
+        return {"x": tile(u["x"], 1), "P": tile(u["P"], 1), "F": np.tile(u["F"], (N, 1, 1)), "H": np.tile(u["H"], (N, 1, 1)),
+                "Q": tile(u["Q"], 1), "R": tile(u["R"], 1), "zs": np.tile(u["zs"], (1, r, 1))}
+    kf_case("kf 6/3 f32 per-filter models 2^19", 6, 3, 1 << 19, np.float32, cv3d)
+    kf_case("kf 6/3 f64 per-filter models 2^19", 6, 3, 1 << 19, np.float64, cv3d)
     # batch_filter: T epochs inside one kernel
     N, T = 1 << 18, 32
     w = wl.kf_bank_cv2d(N, steps=T, dtype=np.float32)

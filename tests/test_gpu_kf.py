@@ -359,3 +359,41 @@ def test_shared_models_in_launch_parameters_equal_device_models(golden, diagnost
         o = okf.kf_step_bank(x, P, g["zs"][t], g["F"][0], g["H"][0], g["Q"][0], g["R"][0])
         x, P = o["x"], o["P"]
     np.testing.assert_allclose(outs[0][0], x, rtol=1e-3, atol=1e-3 * np.abs(x).max())
+
+
+@pytest.mark.parametrize("n,m", [(1, 1), (2, 1), (2, 2), (3, 1), (4, 1), (4, 2), (4, 4), (6, 2), (6, 3)])
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-6), (np.float32, 1e-3)])
+@pytest.mark.parametrize("shared", [False, True])
+def test_small_shapes_random_models_vs_oracle(n, m, dtype, tol, shared):
+    """Every register-tile instance (and whatever kernel takes the other shapes) against the oracle
+    on random well-conditioned models: 3 fused steps, optional outputs included, a ragged bank."""
+    import torch
+    from filterpy_b200.kalman import KalmanFilter
+    from oracle import kf as okf
+    rng = np.random.default_rng(100 * n + m)
+    N = 1000 + 37
+
+    def spd(k, cnt, scale):
+        a = rng.normal(size=(cnt, k, k))
+        return scale * (a @ np.swapaxes(a, -1, -2) / k + np.eye(k))
+    cnt = 1 if shared else N
+    F = np.eye(n) + 0.1 * rng.normal(size=(cnt, n, n))
+    H = rng.normal(size=(cnt, m, n))
+    Q, R, P0 = spd(n, cnt, 0.05), spd(m, cnt, 0.5), spd(n, N, 2.0)
+    x0 = rng.normal(size=(N, n))
+    zs = rng.normal(size=(3, N, m))
+    kf = KalmanFilter(n, m, n_filters=N, dtype=dtype, diagnostics=True)
+    kf.x, kf.P = x0, P0
+    kf.F, kf.H, kf.Q, kf.R = (F[0], H[0], Q[0], R[0]) if shared else (F, H, Q, R)
+    x, P = x0, P0
+    for t in range(3):
+        kf.predict(); kf.update(torch.from_numpy(zs[t]))
+        o = okf.kf_step_bank(x, P, zs[t], F[0] if shared else F, H[0] if shared else H, Q[0] if shared else Q,
+                             R[0] if shared else R)
+        x, P = o["x"], o["P"]
+    kf.check()
+    scale = np.abs(P).max(axis=(1, 2))
+    for got, want in [(kf.x, x), (kf.P, P), (kf.K, o["K"]), (kf.S, o["S"]), (kf.y, o["y"]), (kf.x_prior, o["x_prior"])]:
+        got = got.cpu().numpy().astype(np.float64)
+        ref_mag = np.abs(want).reshape(N, -1).max(axis=1).reshape((N,) + (1,) * (want.ndim - 1))
+        assert np.all(np.abs(got - want) <= tol * (np.abs(want) + 0.05 * ref_mag + 1e-12)), (n, m, dtype)

@@ -308,3 +308,27 @@ def test_ukf_rts_single_filter_drop_in(golden):
     x, P, K = u.rts_smoother(g["cv_Xs"][:, 2], g["cv_Ps"][:, 2], dts=list(g["cv_dts"]))
     assert x.shape == g["cv_x"][:, 2].shape and P.shape == g["cv_P"][:, 2].shape
     rel_close(x, g["cv_x"][:, 2], 1e-6); rel_close(P, g["cv_P"][:, 2], 1e-6); rel_close(K, g["cv_K"][:, 2], 1e-5)
+
+
+def test_imm_cuda_graph_of_three_steps_equals_direct_steps(golden):
+    """The model filters rotate three state buffers; a graph of 3 IMM steps must leave them where a
+    replay expects them."""
+    import torch
+    from filterpy_b200.kalman import IMMEstimator
+    g = golden("mm")
+    z = torch.from_numpy(g["m3_zs"][0]).cuda()
+
+    def make():
+        return IMMEstimator(mm_filters(g, 3, np.float64), g["m3_mu0"], g["m3_trans"])
+    a, b = make(), make()
+
+    def step(imm):
+        imm.predict(); imm.update(z)
+    graph = b.capture(lambda: [step(b) for _ in range(3)], warmup=2)     # 6 warm-up steps run, the capture itself does not
+    graph.replay(); graph.replay()
+    for _ in range(12):
+        step(a)
+    torch.cuda.synchronize()
+    assert torch.equal(a.x, b.x) and torch.equal(a.P, b.P) and torch.equal(a.mu, b.mu)
+    for fa, fb in zip(a.filters, b.filters):
+        assert torch.equal(fa.x, fb.x) and torch.equal(fa.x_post, fb.x_post)
