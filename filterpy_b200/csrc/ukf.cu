@@ -23,6 +23,9 @@ namespace bke {
 namespace {
 
 constexpr int UB = 128;      // threads (= filters) per CTA
+#ifndef BKE_UKF_HX_UNROLL
+#define BKE_UKF_HX_UNROLL 1   // unroll factor of the run-time hx loop of the fp64 kernels
+#endif
 
 template <typename T>
 struct UkfP {
@@ -133,6 +136,23 @@ template <int HX, int N>
 __device__ __forceinline__ constexpr bool hx_ignores_row(int k)
 {
     return HX == BKE_HX_RANGE_AZ_EL ? k > 4 : (HX == BKE_HX_RANGE_BEARING ? k > 2 : false);
+}
+
+// the transcendental models from the position components alone (same arithmetic as apply_hx)
+template <typename T, int M, int HX>
+__device__ __forceinline__ void hx_positions(const T (&pos)[M], T (&h)[M])
+{
+    if constexpr (HX == BKE_HX_RANGE_AZ_EL) {
+        const T px = pos[0], py = pos[1], pz = pos[2];
+        const T rho2 = px * px + py * py;
+        h[0] = sqrt(rho2 + pz * pz);
+        h[1] = atan2(py, px);
+        h[2] = atan2(pz, sqrt(rho2));
+    } else {   // BKE_HX_RANGE_BEARING
+        const T px = pos[0], py = pos[1];
+        h[0] = sqrt(px * px + py * py);
+        h[1] = atan2(py, px);
+    }
 }
 
 // compile-time loop over the 2N+1 sigma points
@@ -306,26 +326,64 @@ __global__ void __launch_bounds__(UB, OCC) ukf_kernel(UkfP<T> p)
             T zm[M];
 #pragma unroll
             for (int a = 0; a < M; a++) zm[a] = T(0);
-            T h0[M];                                         // hx of the mean point, reused by offsets that leave hx's inputs alone
-            for_sigma<0, NS>([&](auto sc) {
-                constexpr int S = decltype(sc)::value;
-                T h[M];
-                if constexpr (S > 0 && hx_ignores_row<HX, N>((S - 1) % N)) {
+            // fp32: the 2n+1 evaluations stay unrolled (cheap bodies, and their independent chains overlap);
+            // fp64: a loop (see below)
+            if constexpr (HX == BKE_HX_LINEAR || sizeof(T) == 4) {
+                T h0[M];
+                for_sigma<0, NS>([&](auto sc) {
+                    constexpr int S = decltype(sc)::value;
+                    T sp[N], h[M];
+                    if constexpr (S > 0 && hx_ignores_row<HX, N>((S - 1) % N)) {
 #pragma unroll
-                    for (int a = 0; a < M; a++) h[a] = h0[a];
-                } else {
+                        for (int a = 0; a < M; a++) h[a] = h0[a];
+                    } else {
+                        sigma_point<T, N, S>(x, U, sp);
+                        apply_hx<T, N, M, HX>(sp, h, Hp, hstride);
+                    }
+                    if constexpr (S == 0) {
+#pragma unroll
+                        for (int a = 0; a < M; a++) h0[a] = h[a];
+                    }
+                    const T w = (S == 0) ? p.wm0 : p.wi;
+#pragma unroll
+                    for (int a = 0; a < M; a++) { zm[a] += w * h[a]; zs[(S * M + a) * UB + tid] = h[a]; }
+                });
+            } else {
+                // Transcendental measurement models: the inputs hx reads (M position components per
+                // sigma point) are parked in the slab first, then ONE run-time loop evaluates hx in
+                // place.  Unrolling 2n+1 inlined fp64 atan2/sqrt bodies made the kernel 117 KB of
+                // code (instruction-cache hit rate 83 %, `no_instruction` the second largest stall).
+                for_sigma<0, NS>([&](auto sc) {
+                    constexpr int S = decltype(sc)::value;
                     T sp[N];
                     sigma_point<T, N, S>(x, U, sp);
-                    apply_hx<T, N, M, HX>(sp, h, Hp, hstride);
-                }
-                if constexpr (S == 0) {
 #pragma unroll
-                    for (int a = 0; a < M; a++) h0[a] = h[a];
-                }
-                const T w = (S == 0) ? p.wm0 : p.wi;
+                    for (int a = 0; a < M; a++) zs[(S * M + a) * UB + tid] = sp[2 * a];      // positions sit at 0, 2, 4
+                });
+                T h0[M];
+                constexpr int HXU = BKE_UKF_HX_UNROLL;
+#pragma unroll HXU
+                for (int sidx = 0; sidx < NS; sidx++) {
+                    T h[M];
+                    const bool same = sidx > 0 && hx_ignores_row<HX, N>((sidx - 1) % N);      // offsets that leave the positions alone
+                    if (same) {
 #pragma unroll
-                for (int a = 0; a < M; a++) { zm[a] += w * h[a]; zs[(S * M + a) * UB + tid] = h[a]; }
-            });
+                        for (int a = 0; a < M; a++) h[a] = h0[a];
+                    } else {
+                        T pos[M];
+#pragma unroll
+                        for (int a = 0; a < M; a++) pos[a] = zs[(sidx * M + a) * UB + tid];
+                        hx_positions<T, M, HX>(pos, h);
+                    }
+                    if (sidx == 0) {
+#pragma unroll
+                        for (int a = 0; a < M; a++) h0[a] = h[a];
+                    }
+                    const T w = (sidx == 0) ? p.wm0 : p.wi;
+#pragma unroll
+                    for (int a = 0; a < M; a++) { zm[a] += w * h[a]; zs[(sidx * M + a) * UB + tid] = h[a]; }
+                }
+            }
             KfUpdateOut<T, N, M> o;
             T Pxz[N][M];
 #pragma unroll
@@ -487,10 +545,11 @@ int launch_inst(const bke_ukf_args &a, cudaStream_t s)
     // for n = 6 is 3 in fp64 (168 registers, ~300 B spilled to L1) and 4 in fp32 (128 registers, no spill)
     static const int occ_env = [] { const char *e = getenv("BKE_UKF_OCC"); return e ? atoi(e) : 0; }();
     constexpr int OCC_DEFAULT = N >= 6 ? (sizeof(T) == 8 ? 3 : 4) : 1;
-    const int occ = (occ_env >= 1 && occ_env <= 4 && N >= 6) ? occ_env : OCC_DEFAULT;
+    const int occ = (occ_env >= 1 && occ_env <= 5 && N >= 6) ? occ_env : OCC_DEFAULT;
     auto kern = ukf_kernel<T, N, M, FX, HX, 1>;
     if (occ == 3) kern = ukf_kernel<T, N, M, FX, HX, (N >= 6 ? 3 : 1)>;
     if (occ == 4) kern = ukf_kernel<T, N, M, FX, HX, (N >= 6 ? 4 : 1)>;
+    if (occ == 5) kern = ukf_kernel<T, N, M, FX, HX, (N >= 6 ? 5 : 1)>;
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
     int64_t grid = (p.N + UB - 1) / UB;
     kern<<<(unsigned)grid, UB, smem, s>>>(p);
