@@ -71,10 +71,23 @@ struct RbP {
 };
 
 
+// filters per warp tile: as many as fit 32 lanes, lowered until every array's tile is a multiple of
+// 16 bytes (what a bulk copy moves): 9/3 fp32 gets 8 filters (24 lanes busy) instead of 10
+template <typename T, int N, int M>
+constexpr int pick_fpw(int g)
+{
+    for (int f = 32 / g; f >= 1; f--) {
+        const int sz = f * (int)sizeof(T);
+        if ((sz * N) % 16 == 0 && (sz * N * N) % 16 == 0 && (sz * M * N) % 16 == 0 && (sz * M * M) % 16 == 0 && (sz * M) % 16 == 0)
+            return f;
+    }
+    return 0;
+}
+
 template <typename T, int N, int M, int RPL, int RB_STAGES>
 struct RbGeom {
     static constexpr int G = N / RPL;                 // lanes per filter
-    static constexpr int FPW = 32 / G;                // filters per warp tile
+    static constexpr int FPW = pick_fpw<T, N, M>(G);  // filters per warp tile
     static constexpr int XB = FPW * N * sizeof(T);
     static constexpr int PB = FPW * N * N * sizeof(T);
     static constexpr int HB = FPW * M * N * sizeof(T);
@@ -94,7 +107,7 @@ struct RbGeom {
     static constexpr int OUT = RB_STAGES > 1 ? a16(XB) + a16(PB) : 0;
     static constexpr int WARP_BYTES = RB_STAGES * STAGE + OUT;
     static constexpr uint32_t TX = XB + 3 * PB + HB + RBY + ZB;
-    static_assert(N % RPL == 0 && G >= 1 && G <= 32, "bad row-block shape");
+    static_assert(N % RPL == 0 && G >= 1 && G <= 32 && FPW >= 1, "bad row-block shape");
     static_assert(XB % 16 == 0 && PB % 16 == 0 && HB % 16 == 0 && RBY % 16 == 0 && ZB % 16 == 0, "bulk copies need 16-byte multiples");
     static_assert(2 * N * M <= N * N, "K and PH' are parked in the Q slot");
 };
@@ -452,6 +465,7 @@ int launch_kf_rowblock(const bke_kf_args &a, cudaStream_t s)
         if (n == 6 && m == 3) return ring ? launch_rb<double, 6, 3, 3, 2, 4>(a, s) : launch_rb<double, 6, 3, 3, 1, 8>(a, s);
     } else {
         if (n == 6 && m == 3) return ring ? launch_rb<float, 6, 3, 3, 2, 4>(a, s) : launch_rb<float, 6, 3, 3, 1, 8>(a, s);
+        if (n == 9 && m == 3) return launch_rb<float, 9, 3, 3, 1, 8>(a, s);        // 8 filters per warp tile (see pick_fpw)
     }
     return BKE_ERR_UNSUPPORTED;
 }

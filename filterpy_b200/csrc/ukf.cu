@@ -326,32 +326,21 @@ __global__ void __launch_bounds__(UB, OCC) ukf_kernel(UkfP<T> p)
             T zm[M];
 #pragma unroll
             for (int a = 0; a < M; a++) zm[a] = T(0);
-            // fp32: the 2n+1 evaluations stay unrolled (cheap bodies, and their independent chains overlap);
-            // fp64: a loop (see below)
-            if constexpr (HX == BKE_HX_LINEAR || sizeof(T) == 4) {
-                T h0[M];
+            if constexpr (HX == BKE_HX_LINEAR) {
                 for_sigma<0, NS>([&](auto sc) {
                     constexpr int S = decltype(sc)::value;
                     T sp[N], h[M];
-                    if constexpr (S > 0 && hx_ignores_row<HX, N>((S - 1) % N)) {
-#pragma unroll
-                        for (int a = 0; a < M; a++) h[a] = h0[a];
-                    } else {
-                        sigma_point<T, N, S>(x, U, sp);
-                        apply_hx<T, N, M, HX>(sp, h, Hp, hstride);
-                    }
-                    if constexpr (S == 0) {
-#pragma unroll
-                        for (int a = 0; a < M; a++) h0[a] = h[a];
-                    }
+                    sigma_point<T, N, S>(x, U, sp);
+                    apply_hx<T, N, M, HX>(sp, h, Hp, hstride);
                     const T w = (S == 0) ? p.wm0 : p.wi;
 #pragma unroll
                     for (int a = 0; a < M; a++) { zm[a] += w * h[a]; zs[(S * M + a) * UB + tid] = h[a]; }
                 });
             } else {
                 // Transcendental measurement models: the inputs hx reads (M position components per
-                // sigma point) are parked in the slab first, then ONE run-time loop evaluates hx in
-                // place.  Unrolling 2n+1 inlined fp64 atan2/sqrt bodies made the kernel 117 KB of
+                // sigma point) are parked in the slab first, then a run-time loop over the n offset
+                // rows evaluates hx in place for the +row / -row pair (two independent chains per
+                // iteration).  Unrolling 2n+1 inlined atan2/sqrt bodies made the fp64 kernel 117 KB of
                 // code (instruction-cache hit rate 83 %, `no_instruction` the second largest stall).
                 for_sigma<0, NS>([&](auto sc) {
                     constexpr int S = decltype(sc)::value;
@@ -361,27 +350,33 @@ __global__ void __launch_bounds__(UB, OCC) ukf_kernel(UkfP<T> p)
                     for (int a = 0; a < M; a++) zs[(S * M + a) * UB + tid] = sp[2 * a];      // positions sit at 0, 2, 4
                 });
                 T h0[M];
-                constexpr int HXU = BKE_UKF_HX_UNROLL;
-#pragma unroll HXU
-                for (int sidx = 0; sidx < NS; sidx++) {
-                    T h[M];
-                    const bool same = sidx > 0 && hx_ignores_row<HX, N>((sidx - 1) % N);      // offsets that leave the positions alone
-                    if (same) {
+                {
+                    T pos[M];
 #pragma unroll
-                        for (int a = 0; a < M; a++) h[a] = h0[a];
+                    for (int a = 0; a < M; a++) pos[a] = zs[a * UB + tid];
+                    hx_positions<T, M, HX>(pos, h0);
+#pragma unroll
+                    for (int a = 0; a < M; a++) { zm[a] += p.wm0 * h0[a]; zs[a * UB + tid] = h0[a]; }
+                }
+#pragma unroll 1
+                for (int k = 0; k < N; k++) {
+                    const int sa = k + 1, sb = k + 1 + N;
+                    T ha[M], hb[M];
+                    if (hx_ignores_row<HX, N>(k)) {               // this offset row leaves the positions alone
+#pragma unroll
+                        for (int a = 0; a < M; a++) { ha[a] = h0[a]; hb[a] = h0[a]; }
                     } else {
-                        T pos[M];
+                        T pa[M], pb[M];
 #pragma unroll
-                        for (int a = 0; a < M; a++) pos[a] = zs[(sidx * M + a) * UB + tid];
-                        hx_positions<T, M, HX>(pos, h);
+                        for (int a = 0; a < M; a++) { pa[a] = zs[(sa * M + a) * UB + tid]; pb[a] = zs[(sb * M + a) * UB + tid]; }
+                        hx_positions<T, M, HX>(pa, ha);
+                        hx_positions<T, M, HX>(pb, hb);
                     }
-                    if (sidx == 0) {
 #pragma unroll
-                        for (int a = 0; a < M; a++) h0[a] = h[a];
+                    for (int a = 0; a < M; a++) {
+                        zm[a] += p.wi * ha[a]; zm[a] += p.wi * hb[a];
+                        zs[(sa * M + a) * UB + tid] = ha[a]; zs[(sb * M + a) * UB + tid] = hb[a];
                     }
-                    const T w = (sidx == 0) ? p.wm0 : p.wi;
-#pragma unroll
-                    for (int a = 0; a < M; a++) { zm[a] += w * h[a]; zs[(sidx * M + a) * UB + tid] = h[a]; }
                 }
             }
             KfUpdateOut<T, N, M> o;
