@@ -537,9 +537,9 @@ int launch_inst(const bke_ukf_args &a, cudaStream_t s)
     if (FX == BKE_FX_LINEAR) smem += sizeof(T) * (a.F_stride == 0 ? N * N : N * N * UB);
     if (HX == BKE_HX_LINEAR) smem += sizeof(T) * (a.H_stride == 0 ? M * N : M * N * UB);
     // resident CTAs per SM the kernel is compiled for (registers are capped accordingly): measured best
-    // for n = 6 is 3 in fp64 (168 registers, ~300 B spilled to L1) and 4 in fp32 (128 registers, no spill)
+    // for n = 6 is 3 in fp64 (166 registers) and 5 in fp32 (95 registers), both without spills
     static const int occ_env = [] { const char *e = getenv("BKE_UKF_OCC"); return e ? atoi(e) : 0; }();
-    constexpr int OCC_DEFAULT = N >= 6 ? (sizeof(T) == 8 ? 3 : 4) : 1;
+    constexpr int OCC_DEFAULT = N >= 6 ? (sizeof(T) == 8 ? 3 : 5) : 1;
     const int occ = (occ_env >= 1 && occ_env <= 5 && N >= 6) ? occ_env : OCC_DEFAULT;
     auto kern = ukf_kernel<T, N, M, FX, HX, 1>;
     if (occ == 3) kern = ukf_kernel<T, N, M, FX, HX, (N >= 6 ? 3 : 1)>;
