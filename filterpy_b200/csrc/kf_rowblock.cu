@@ -460,6 +460,7 @@ int launch_kf_rowblock(const bke_kf_args &a, cudaStream_t s)
     // selects the ring for comparison.
     static const bool ring = getenv("BKE_RB_RING") && atoi(getenv("BKE_RB_RING")) != 0;
     if (a.dtype == BKE_F64) {
+        // (9 warps fit the shared memory but cap the kernel at 168 registers: 0.95 ms against 0.74 ms)
         if (n == 9 && m == 3) return ring ? launch_rb<double, 9, 3, 3, 2, 4>(a, s) : launch_rb<double, 9, 3, 3, 1, 8>(a, s);
         if (n == 4 && m == 2) return ring ? launch_rb<double, 4, 2, 2, 2, 4>(a, s) : launch_rb<double, 4, 2, 2, 1, 8>(a, s);
         if (n == 6 && m == 3) return ring ? launch_rb<double, 6, 3, 3, 2, 4>(a, s) : launch_rb<double, 6, 3, 3, 1, 8>(a, s);
