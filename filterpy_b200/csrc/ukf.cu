@@ -172,6 +172,23 @@ __device__ __forceinline__ void for_sigma(Fn &&fn)
 template <typename T, int PER, int PAD>
 __device__ __forceinline__ void slab_load(T *slab, const T *g, int cnt)
 {
+    if (cnt == UB) {
+        // full tile: all PER loads of a thread are in flight before the first store (a plain loop
+        // exposed one global-load latency per few iterations: the top long-scoreboard stall)
+        constexpr int CH = PER % 12 == 0 ? 12 : (PER % 9 == 0 ? 9 : (PER % 4 == 0 ? 4 : 1));
+#pragma unroll
+        for (int k0 = 0; k0 < PER; k0 += CH) {
+            T v[CH];
+#pragma unroll
+            for (int k = 0; k < CH; k++) v[k] = g[threadIdx.x + (k0 + k) * UB];
+#pragma unroll
+            for (int k = 0; k < CH; k++) {
+                const int e = threadIdx.x + (k0 + k) * UB;
+                slab[(e / PER) * PAD + (e % PER)] = v[k];
+            }
+        }
+        return;
+    }
     for (int e = threadIdx.x; e < cnt * PER; e += UB) slab[(e / PER) * PAD + (e % PER)] = g[e];
 }
 template <typename T, int PER, int PAD>
@@ -381,6 +398,18 @@ __global__ void __launch_bounds__(UB, OCC) ukf_kernel(UkfP<T> p)
             }
             KfUpdateOut<T, N, M> o;
             T Pxz[N][M];
+            // R and z are needed after the covariance pass below: fetch them now so that their latency
+            // hides behind it (they were the largest long-scoreboard stalls of the update)
+            T Rv[M][M], zv[M];
+            {
+                const T *Rf = p.R + fc * p.sR;
+#pragma unroll
+                for (int a = 0; a < M; a++) {
+                    zv[a] = p.z[fc * M + a];
+#pragma unroll
+                    for (int b = 0; b < M; b++) Rv[a][b] = Rf[a * M + b];
+                }
+            }
 #pragma unroll
             for (int a = 0; a < M; a++)
 #pragma unroll
@@ -413,14 +442,13 @@ __global__ void __launch_bounds__(UB, OCC) ukf_kernel(UkfP<T> p)
                     }
                 }
             });
-            const T *Rf = p.R + fc * p.sR;
 #pragma unroll
             for (int a = 0; a < M; a++)
 #pragma unroll
                 for (int b = a; b < M; b++) {
                     const T sab = o.S[a][b];
-                    o.S[a][b] = sab + Rf[a * M + b];
-                    if (b > a) o.S[b][a] = sab + Rf[b * M + a];
+                    o.S[a][b] = sab + Rv[a][b];
+                    if (b > a) o.S[b][a] = sab + Rv[b][a];
                 }
             o.ok = reg_inverse<T, M>(o.S, o.SI, o.logdet);
             if (!o.ok) st = BKE_STATUS_SINGULAR_S;
@@ -437,7 +465,7 @@ __global__ void __launch_bounds__(UB, OCC) ukf_kernel(UkfP<T> p)
                         o.K[i][a] = s;
                     }
 #pragma unroll
-                for (int a = 0; a < M; a++) o.y[a] = p.z[fc * M + a] - zm[a];
+                for (int a = 0; a < M; a++) o.y[a] = zv[a] - zm[a];
 #pragma unroll
                 for (int i = 0; i < N; i++) {
                     T s = x[i];
