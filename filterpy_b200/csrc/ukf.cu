@@ -53,9 +53,11 @@ __device__ __forceinline__ bool chol_upper(const T (&A)[N][N], T (&U)[N][N])
 #pragma unroll
         for (int k = 0; k < j; k++) d -= U[k][j] * U[k][j];
         ok = ok && (d > T(0));
-        T r = sqrt(d);
+        // 1/sqrt(d) once, then the diagonal as d * (1/sqrt(d)): a reciprocal square root and a product
+        // instead of a square root followed by a division on the critical path (both within ~1 ulp)
+        T inv = rsqrt(d);
+        T r = d * inv;
         U[j][j] = r;
-        T inv = T(1) / r;
 #pragma unroll
         for (int i = j + 1; i < N; i++) {
             T s = A[j][i];
@@ -152,6 +154,63 @@ __device__ __forceinline__ void hx_positions(const T (&pos)[M], T (&h)[M])
         const T px = pos[0], py = pos[1];
         h[0] = sqrt(px * px + py * py);
         h[1] = atan2(py, px);
+    }
+}
+
+// Angles of a sigma point relative to the mean point.  The sigma points sit within a few standard
+// deviations of the mean, so the angle between the two position vectors is small and
+//     atan2(py, px) = atan2(py0, px0) + atan2(px0 py - py0 px, px0 px + py0 py)
+// (exact geometry: the second term is the signed angle from the mean direction to the point) needs
+// only a short odd series for its arctangent: for |t| < 1/16 the series through t^13 (fp64) /
+// t^5 (fp32) is below half an ulp of the sum.  Wider angles take the library atan2.  The result is
+// wrapped into (-pi, pi] like atan2's.  A full fp64 atan2 is ~150 instructions; 2n of the 2n+1
+// evaluations per angle become a division and a 7-term polynomial.
+template <typename T>
+__device__ __forceinline__ bool atan_small(T cross, T dot, T &delta)
+{
+    if (!(fabs(cross) < T(0.0625) * dot)) return false;            // also false for dot <= 0 and NaN
+    const T t = cross / dot, t2 = t * t;
+    T pl;
+    if constexpr (sizeof(T) == 8) {
+        pl = T(1.0 / 13.0);
+        pl = pl * t2 - T(1.0 / 11.0);
+        pl = pl * t2 + T(1.0 / 9.0);
+        pl = pl * t2 - T(1.0 / 7.0);
+        pl = pl * t2 + T(1.0 / 5.0);
+        pl = pl * t2 - T(1.0 / 3.0);
+    } else {
+        pl = T(1.0 / 5.0);
+        pl = pl * t2 - T(1.0 / 3.0);
+    }
+    delta = t + t * (t2 * pl);
+    return true;
+}
+
+template <typename T>
+__device__ __forceinline__ T wrap_pi(T a)
+{
+    const T pi = T(3.14159265358979323846);
+    if (a > pi) a -= T(2) * pi;
+    else if (a <= -pi) a += T(2) * pi;
+    return a;
+}
+
+// hx of a sigma point given the mean point's positions pos0 (and its horizontal range rho0) and hx(mean) = h0
+template <typename T, int M, int HX>
+__device__ __forceinline__ void hx_positions_rel(const T (&pos)[M], const T (&pos0)[M], T rho0, const T (&h0)[M], T (&h)[M])
+{
+    const T px = pos[0], py = pos[1], px0 = pos0[0], py0 = pos0[1];
+    const T rho2 = px * px + py * py;
+    T d;
+    if constexpr (HX == BKE_HX_RANGE_AZ_EL) {
+        const T pz = pos[2], pz0 = pos0[2];
+        h[0] = sqrt(rho2 + pz * pz);
+        h[1] = atan_small<T>(px0 * py - py0 * px, px0 * px + py0 * py, d) ? wrap_pi<T>(h0[1] + d) : atan2(py, px);
+        const T rho = sqrt(rho2);
+        h[2] = atan_small<T>(rho0 * pz - pz0 * rho, rho0 * rho + pz0 * pz, d) ? h0[2] + d : atan2(pz, rho);
+    } else {   // BKE_HX_RANGE_BEARING
+        h[0] = sqrt(rho2);
+        h[1] = atan_small<T>(px0 * py - py0 * px, px0 * px + py0 * py, d) ? wrap_pi<T>(h0[1] + d) : atan2(py, px);
     }
 }
 
@@ -366,15 +425,15 @@ __global__ void __launch_bounds__(UB, OCC) ukf_kernel(UkfP<T> p)
 #pragma unroll
                     for (int a = 0; a < M; a++) zs[(S * M + a) * UB + tid] = sp[2 * a];      // positions sit at 0, 2, 4
                 });
-                T h0[M];
+                T h0[M], pos0[M];
                 {
-                    T pos[M];
 #pragma unroll
-                    for (int a = 0; a < M; a++) pos[a] = zs[a * UB + tid];
-                    hx_positions<T, M, HX>(pos, h0);
+                    for (int a = 0; a < M; a++) pos0[a] = zs[a * UB + tid];
+                    hx_positions<T, M, HX>(pos0, h0);
 #pragma unroll
                     for (int a = 0; a < M; a++) { zm[a] += p.wm0 * h0[a]; zs[a * UB + tid] = h0[a]; }
                 }
+                const T rho0 = sqrt(pos0[0] * pos0[0] + pos0[1] * pos0[1]);
 #pragma unroll 1
                 for (int k = 0; k < N; k++) {
                     const int sa = k + 1, sb = k + 1 + N;
@@ -386,8 +445,8 @@ __global__ void __launch_bounds__(UB, OCC) ukf_kernel(UkfP<T> p)
                         T pa[M], pb[M];
 #pragma unroll
                         for (int a = 0; a < M; a++) { pa[a] = zs[(sa * M + a) * UB + tid]; pb[a] = zs[(sb * M + a) * UB + tid]; }
-                        hx_positions<T, M, HX>(pa, ha);
-                        hx_positions<T, M, HX>(pb, hb);
+                        hx_positions_rel<T, M, HX>(pa, pos0, rho0, h0, ha);
+                        hx_positions_rel<T, M, HX>(pb, pos0, rho0, h0, hb);
                     }
 #pragma unroll
                     for (int a = 0; a < M; a++) {
