@@ -156,11 +156,15 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    try:
+    path = os.environ.get("BKE_LIB_PATH") or _build.LIB      # BKE_LIB_PATH: an explicitly chosen build (A/B measurements)
+    if os.environ.get("BKE_LIB_PATH"):
+        if not os.path.exists(path):
+            raise BkeError("BKE_LIB_PATH=%s does not exist" % path)
+    else:
+      try:
         if _build.needs_build():
             _build.build()
-    except Exception as e:  # stale or missing and not buildable
+      except Exception as e:  # stale or missing and not buildable
         if not os.path.exists(path):
             raise BkeError("libbke.so is missing and could not be built (%s); the engine has no "
                            "CPU fallback" % e)

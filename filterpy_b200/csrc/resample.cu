@@ -938,16 +938,19 @@ __device__ __forceinline__ void emit_tile(const Params &p, EmitShared &sm, int t
     if (!STRAT && full_tile) {
         // branch-free fast evaluation of #{positions < c}: floor(c N - u) + 1 away from integers;
         // the rare near-integer cases are collected and redone exactly below
-        const double Nd = (double)p.ng, u = p.u, tau = p.tau, lo_d = (double)tile_lo;
+        // (10 instructions per element: v, floor, fraction, |fraction - 1/2| against the margin, one
+        // conversion, integer clamp and offset — the first version spent 19 on fp64 selects and clamps)
+        const double Nd = (double)p.ng, u = p.u, half_m = 0.5 - p.tau;
+        const int n_m1 = (int)p.ng - 1, lo_m1 = (int)tile_lo - 1;
         unsigned slow = 0;
 #pragma unroll
         for (int k = 0; k < IPT; k++) {
-            const double v = fma(__longlong_as_double(cbits[k]), Nd, -u);
-            const double r = rint(v);
-            if (!(fabs(v - r) > tau)) slow |= 1u << k;
-            double g = r + (r > v ? 0.0 : 1.0);            // floor(v) + 1
-            g = g < 0.0 ? 0.0 : (g > Nd ? Nd : g);
-            hv[k] = (int)(g - lo_d);
+            const double v = fma(__longlong_as_double(cbits[k]), Nd, -u);     // >= -u > -1
+            const double fl = floor(v);
+            const double fr = v - fl;                                         // exact, in [0, 1)
+            if (!(fabs(fr - 0.5) < half_m)) slow |= 1u << k;                  // within tau of an integer
+            const int g = min(__double2int_rz(fl), n_m1);                     // floor(v), clamped (the conversion saturates)
+            hv[k] = g - lo_m1;                                                // floor(v) + 1 - tile_lo
         }
         if (slow) {
 #pragma unroll
@@ -1015,7 +1018,13 @@ __device__ __forceinline__ void emit_tile(const Params &p, EmitShared &sm, int t
             __syncthreads();
             const i64 rel0 = tile_lo + cs - ws.hdr->out_begin;
             if (rel0 >= 0 && rel0 + (ce - cs) <= p.cap) {
-                for (int q = tid; q < ce - cs; q += BLOCK) p.idx[rel0 + q] = base_j + sm.ebuf[pad32(q)];
+                // pad32(tid + BLOCK k) = pad32(tid) + (BLOCK + BLOCK/32) k: fixed strides on both sides,
+                // so the unrolled loop is LDS / IADD / STG with immediate offsets
+                int *dst = p.idx + rel0 + tid;
+                const int *src = sm.ebuf + pad32(tid);
+                const int n_out = ce - cs - tid;                                // outputs at and after this thread's first
+#pragma unroll 4
+                for (int kk = 0; kk * BLOCK < n_out; kk++) dst[kk * BLOCK] = base_j + src[kk * (BLOCK + BLOCK / 32)];
             } else {
                 for (int q = tid; q < ce - cs; q += BLOCK) put_index(p, tile_lo + cs + q, base_j + sm.ebuf[pad32(q)]);
             }
