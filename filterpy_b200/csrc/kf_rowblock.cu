@@ -68,6 +68,7 @@ struct RbP {
     T *x_out, *P_out;
     const uint8_t *valid;
     int32_t *status;
+    T *x_prior, *P_prior, *K, *y, *S, *SI, *ll;     // optional outputs (NULL = not wanted)
 };
 
 
@@ -112,7 +113,9 @@ struct RbGeom {
     static_assert(2 * N * M <= N * N, "K and PH' are parked in the Q slot");
 };
 
-template <typename T, int N, int M, int RPL, int RB_STAGES, int RB_WARPS>
+// EXTRAS: compile the optional outputs in (kept out of the plain instantiation: their branches and
+// live ranges cost the C3 kernel 9 % when they were run-time tests)
+template <typename T, int N, int M, int RPL, int RB_STAGES, int RB_WARPS, bool EXTRAS>
 __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
 {
     using Gm = RbGeom<T, N, M, RPL, RB_STAGES>;
@@ -223,6 +226,16 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
             }
         }
         __syncwarp();                               // every lane is done reading x, P (and F rows it needed as B)
+        if (EXTRAS && active && (p.x_prior || p.P_prior)) {   // optional outputs: every lane stores its own rows
+#pragma unroll
+            for (int i = 0; i < RPL; i++) {
+                if (p.x_prior) p.x_prior[f * N + r0 + i] = xr[i];
+                if (p.P_prior) {
+#pragma unroll
+                    for (int j = 0; j < N; j++) p.P_prior[f * N * N + (r0 + i) * N + j] = A[i][j];
+                }
+            }
+        }
         if (active) {
 #pragma unroll
             for (int i = 0; i < RPL; i++) {
@@ -317,6 +330,38 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
                     for (int a = 0; a < M; a++) s -= Kr[i][a] * Hm[a][j];
                     C[i][j] = s;                                   // own rows of I - K H
                 }
+            if (EXTRAS && active && (p.K || p.y || p.S || p.SI || p.ll)) {
+                // optional outputs (kalman_filter.py:533-544 attributes): S always, the rest when S was invertible
+                if (rb == 0 && p.S) {
+#pragma unroll
+                    for (int a = 0; a < M; a++)
+#pragma unroll
+                        for (int b = 0; b < M; b++) p.S[f * M * M + a * M + b] = o.S[a][b];
+                }
+                if (o.ok) {
+                    if (p.K) {
+#pragma unroll
+                        for (int i = 0; i < RPL; i++)
+#pragma unroll
+                            for (int a = 0; a < M; a++) p.K[f * N * M + (r0 + i) * M + a] = Kr[i][a];
+                    }
+                    if (rb == 0) {
+                        if (p.y) for (int a = 0; a < M; a++) p.y[f * M + a] = y[a];
+                        if (p.SI) for (int a = 0; a < M; a++) for (int b = 0; b < M; b++) p.SI[f * M * M + a * M + b] = o.SI[a][b];
+                        if (p.ll) {
+                            T q = T(0);
+#pragma unroll
+                            for (int a = 0; a < M; a++) {
+                                T sq = T(0);
+#pragma unroll
+                                for (int b = 0; b < M; b++) sq += o.SI[a][b] * y[b];
+                                q += y[a] * sq;
+                            }
+                            p.ll[f] = T(-0.5) * (q + o.logdet + T(M) * T(LOG_2PI));
+                        }
+                    }
+                }
+            }
             if (active) {
 #pragma unroll
                 for (int i = 0; i < RPL; i++) {
@@ -371,6 +416,9 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
                 }
             }
         }
+        if (EXTRAS && !has_z && active && rb == 0 && p.y) {  // z is None: y = 0 (kalman_filter.py:515-520)
+            for (int a = 0; a < M; a++) p.y[f * M + a] = T(0);
+        }
         // ---------------- posterior rows -> staging -> bulk TMA store ---------------------------
         if (RB_STAGES > 1 && it > 0 && lane == 0) bulk_wait_read();   // the previous tile's stores have read the staging buffer
         __syncwarp();                                       // every lane is done with P', (I-KH), K in the stage
@@ -411,14 +459,18 @@ int launch_rb(const bke_kf_args &a, cudaStream_t s)
         p.x = (const T *)a.x; p.P = (const T *)a.P; p.F = (const T *)a.F; p.Q = (const T *)a.Q;
         p.H = (const T *)a.H; p.R = (const T *)a.R; p.z = (const T *)a.z;
         p.x_out = (T *)a.x_out; p.P_out = (T *)a.P_out; p.valid = a.z_valid; p.status = a.status;
-        auto kern = kf_rowblock_kernel<T, N, M, RPL, RB_STAGES, RB_WARPS>;
+        p.x_prior = (T *)a.x_prior; p.P_prior = (T *)a.P_prior; p.K = (T *)a.K; p.y = (T *)a.y;
+        p.S = (T *)a.S; p.SI = (T *)a.SI; p.ll = (T *)a.log_likelihood;
+        const bool extras = a.x_prior || a.P_prior || a.K || a.y || a.S || a.SI || a.log_likelihood;
+        auto kern = extras ? kf_rowblock_kernel<T, N, M, RPL, RB_STAGES, RB_WARPS, true>
+                           : kf_rowblock_kernel<T, N, M, RPL, RB_STAGES, RB_WARPS, false>;
         const int smem = RB_WARPS * Gm::WARP_BYTES;
-        static bool configured[64] = {false};
+        static bool configured[2][64] = {{false}};
         int dev = 0;
         cudaGetDevice(&dev);
-        if (dev < 0 || dev >= 64 || !configured[dev]) {
+        if (dev < 0 || dev >= 64 || !configured[extras][dev]) {
             if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
-            if (dev >= 0 && dev < 64) configured[dev] = true;
+            if (dev >= 0 && dev < 64) configured[extras][dev] = true;
         }
         const int64_t tiles = Nmain / Gm::FPW;
         int64_t grid = (tiles + RB_WARPS - 1) / RB_WARPS;
@@ -434,6 +486,9 @@ int launch_rb(const bke_kf_args &a, cudaStream_t s)
         t.x = off(a.x, N); t.P = off(a.P, N * N); t.x_out = (void *)off(a.x_out, N); t.P_out = (void *)off(a.P_out, N * N);
         t.F = off(a.F, N * N); t.Q = off(a.Q, N * N); t.H = off(a.H, M * N); t.R = off(a.R, M * M);
         t.z = off(a.z, M);
+        t.x_prior = (void *)off(a.x_prior, N); t.P_prior = (void *)off(a.P_prior, N * N); t.K = (void *)off(a.K, N * M);
+        t.y = (void *)off(a.y, M); t.S = (void *)off(a.S, M * M); t.SI = (void *)off(a.SI, M * M);
+        t.log_likelihood = (void *)off(a.log_likelihood, 1);
         t.z_valid = a.z_valid ? a.z_valid + Nmain : nullptr;
         t.status = a.status ? a.status + Nmain : nullptr;
         return launch_kf_generic(t, s);
@@ -447,10 +502,9 @@ bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int launch_kf_rowblock(const bke_kf_args &a, cudaStream_t s)
 {
-    // fused predict+update, per-filter dense models, no control input, no optional outputs
+    // fused predict+update, per-filter dense models, no control input
     if ((a.flags & (BKE_DO_PREDICT | BKE_DO_UPDATE | BKE_UPDATE_FIRST)) != (BKE_DO_PREDICT | BKE_DO_UPDATE)) return BKE_ERR_UNSUPPORTED;
     if (a.B && a.u) return BKE_ERR_UNSUPPORTED;
-    if (a.x_prior || a.P_prior || a.K || a.y || a.S || a.SI || a.log_likelihood) return BKE_ERR_UNSUPPORTED;
     if (!a.F_stride || !a.Q_stride || !a.H_stride || !a.R_stride) return BKE_ERR_UNSUPPORTED;
     if (!(al16(a.x) && al16(a.P) && al16(a.F) && al16(a.Q) && al16(a.H) && al16(a.R) && al16(a.z) && al16(a.x_out) && al16(a.P_out)))
         return BKE_ERR_UNSUPPORTED;

@@ -23,6 +23,11 @@ namespace bke {
 namespace {
 
 constexpr int UB = 128;      // threads (= filters) per CTA
+#ifdef BKE_UKF_NO_EXTRAS
+constexpr bool UKF_EXTRAS = false;
+#else
+constexpr bool UKF_EXTRAS = true;
+#endif
 #ifndef BKE_UKF_HX_UNROLL
 #define BKE_UKF_HX_UNROLL 1   // unroll factor of the run-time hx loop of the fp64 kernels
 #endif
@@ -364,7 +369,7 @@ __global__ void __launch_bounds__(UB, OCC) ukf_kernel(UkfP<T> p)
                 if (j > i) P[j][i] = Pm[i][j] + (q_dense ? zs[tl * PADP + j * N + i] : p.Q[j * N + i]);
             }
         }
-        if (live) {
+        if (UKF_EXTRAS && live) {
             if (p.x_prior) for (int i = 0; i < N; i++) p.x_prior[f * N + i] = x[i];
             if (p.P_prior) for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) p.P_prior[f * N * N + i * N + j] = P[i][j];
         }
@@ -533,7 +538,7 @@ __global__ void __launch_bounds__(UB, OCC) ukf_kernel(UkfP<T> p)
                     x[i] = s;
                 }
                 // optional outputs leave now, while S, SI, y are still in registers
-                if (live) {
+                if (UKF_EXTRAS && live) {
                     if (p.K) for (int i = 0; i < N; i++) for (int a = 0; a < M; a++) p.K[f * N * M + i * M + a] = o.K[i][a];
                     if (p.y) for (int a = 0; a < M; a++) p.y[f * M + a] = o.y[a];
                     if (p.S) for (int a = 0; a < M; a++) for (int b = 0; b < M; b++) p.S[f * M * M + a * M + b] = o.S[a][b];

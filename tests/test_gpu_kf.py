@@ -361,12 +361,12 @@ def test_shared_models_in_launch_parameters_equal_device_models(golden, diagnost
     np.testing.assert_allclose(outs[0][0], x, rtol=1e-3, atol=1e-3 * np.abs(x).max())
 
 
-@pytest.mark.parametrize("n,m", [(1, 1), (2, 1), (2, 2), (3, 1), (4, 1), (4, 2), (4, 4), (6, 2), (6, 3)])
+@pytest.mark.parametrize("n,m", [(1, 1), (2, 1), (2, 2), (3, 1), (4, 1), (4, 2), (4, 4), (6, 2), (6, 3), (9, 3)])
 @pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-6), (np.float32, 1e-3)])
 @pytest.mark.parametrize("shared", [False, True])
 def test_small_shapes_random_models_vs_oracle(n, m, dtype, tol, shared):
-    """Every register-tile instance (and whatever kernel takes the other shapes) against the oracle
-    on random well-conditioned models: 3 fused steps, optional outputs included, a ragged bank."""
+    """Every register-tile and row-block instance (and whatever kernel takes the other shapes) against
+    the oracle on random well-conditioned models: 3 fused steps, optional outputs included, a ragged bank."""
     import torch
     from filterpy_b200.kalman import KalmanFilter
     from oracle import kf as okf
