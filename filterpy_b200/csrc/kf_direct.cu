@@ -55,7 +55,9 @@ __device__ __forceinline__ void stv(T *dst, const T *src)
     }
 }
 
-template <typename T, int N, int M>
+// EX: the optional outputs are compiled in (a separate instantiation keeps their tests and live
+// ranges out of the plain kernel)
+template <typename T, int N, int M, bool EX>
 __global__ void __launch_bounds__(128) kf_direct_kernel(DirP<T> p)
 {
     const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -70,13 +72,13 @@ __global__ void __launch_bounds__(128) kf_direct_kernel(DirP<T> p)
         ldv<T, N * N>(&F[0][0], p.F + f * p.sF);
         ldv<T, N * N>(&Q[0][0], p.Q + f * p.sQ);
         reg_predict<T, N>(x, P, F, Q, p.alpha_sq);
-        if (p.x_prior) stv<T, N>(p.x_prior + f * N, x);
-        if (p.P_prior) stv<T, N * N>(p.P_prior + f * N * N, &P[0][0]);
+        if (EX && p.x_prior) stv<T, N>(p.x_prior + f * N, x);
+        if (EX && p.P_prior) stv<T, N * N>(p.P_prior + f * N * N, &P[0][0]);
     }
     if (do_u) {
         const bool has_z = p.valid == nullptr || p.valid[f] != 0;
         if (!has_z) {
-            if (p.y) { T zero[M]; for (int a = 0; a < M; a++) zero[a] = T(0); stv<T, M>(p.y + f * M, zero); }
+            if (EX && p.y) { T zero[M]; for (int a = 0; a < M; a++) zero[a] = T(0); stv<T, M>(p.y + f * M, zero); }
         } else {
             T H[M][N], R[M][M], z[M];
             ldv<T, M * N>(&H[0][0], p.H + f * p.sH);
@@ -85,8 +87,8 @@ __global__ void __launch_bounds__(128) kf_direct_kernel(DirP<T> p)
             KfUpdateOut<T, N, M> o;
             reg_update<T, N, M>(x, P, H, R, z, o);
             if (!o.ok) st = BKE_STATUS_SINGULAR_S;
-            if (p.S) stv<T, M * M>(p.S + f * M * M, &o.S[0][0]);
-            if (o.ok) {
+            if (EX && p.S) stv<T, M * M>(p.S + f * M * M, &o.S[0][0]);
+            if (EX && o.ok) {
                 if (p.y) stv<T, M>(p.y + f * M, o.y);
                 if (p.SI) stv<T, M * M>(p.SI + f * M * M, &o.SI[0][0]);
                 if (p.K) stv<T, N * M>(p.K + f * N * M, &o.K[0][0]);
@@ -136,7 +138,9 @@ int launch_inst(const bke_kf_args &a, cudaStream_t s)
     p.x_out = (T *)a.x_out; p.P_out = (T *)a.P_out; p.x_prior = (T *)a.x_prior; p.P_prior = (T *)a.P_prior;
     p.K = (T *)a.K; p.y = (T *)a.y; p.S = (T *)a.S; p.SI = (T *)a.SI; p.ll = (T *)a.log_likelihood;
     p.status = a.status;
-    kf_direct_kernel<T, N, M><<<(unsigned)((p.N + 127) / 128), 128, 0, s>>>(p);
+    const bool ex = a.x_prior || a.P_prior || a.K || a.y || a.S || a.SI || a.log_likelihood;
+    if (ex) kf_direct_kernel<T, N, M, true><<<(unsigned)((p.N + 127) / 128), 128, 0, s>>>(p);
+    else kf_direct_kernel<T, N, M, false><<<(unsigned)((p.N + 127) / 128), 128, 0, s>>>(p);
     return check_cuda(cudaGetLastError(), "kf_direct_kernel launch");
 }
 
