@@ -131,3 +131,28 @@ def test_gloo_world_size_2(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert (tmp_path / "rank0.ok").exists() and (tmp_path / "rank1.ok").exists(), r.stdout[-2000:]
+
+
+def test_exchange_plan_covers_every_output_exactly_once():
+    """After a sharded resample rank r owns the output positions [o_r, o_r+1); the re-sharding plan
+    must move every position to the rank that owns it under the even split, exactly once."""
+    from filterpy_b200 import distributed as bd
+    rng = np.random.default_rng(0)
+    for world in (1, 2, 3, 8):
+        for n in (world, 17, 1000, 4097):
+            b = bd.shard_bounds(n, world)
+            cuts = np.sort(rng.integers(0, n + 1, size=world - 1)) if world > 1 else np.zeros(0, int)
+            edges = np.concatenate([[0], cuts, [n]])
+            out_ranges = [(int(edges[r]), int(edges[r + 1])) for r in range(world)]     # includes empty ranks
+            got = np.zeros(n, int)
+            for r in range(world):
+                sends, recvs = bd.exchange_plan(out_ranges, b, r)
+                for dst, lo, hi in sends:
+                    g_lo, g_hi = out_ranges[r][0] + lo, out_ranges[r][0] + hi
+                    assert b[dst] <= g_lo and g_hi <= b[dst + 1]
+                    got[g_lo:g_hi] += 1
+                assert sum(h - l for _, l, h in recvs) == b[r + 1] - b[r]
+                for src, lo, hi in recvs:
+                    g_lo, g_hi = b[r] + lo, b[r] + hi
+                    assert out_ranges[src][0] <= g_lo and g_hi <= out_ranges[src][1]
+            assert (got == 1).all()
