@@ -115,7 +115,9 @@ struct RbGeom {
 
 // EXTRAS: compile the optional outputs in (kept out of the plain instantiation: their branches and
 // live ranges cost the C3 kernel 9 % when they were run-time tests)
-template <typename T, int N, int M, int RPL, int RB_STAGES, int RB_WARPS, bool EXTRAS>
+// MODE: 3 = fused predict+update, 1 = predict only, 2 = update only (what is not needed is neither
+// loaded nor computed)
+template <typename T, int N, int M, int RPL, int RB_STAGES, int RB_WARPS, bool EXTRAS, int MODE>
 __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
 {
     using Gm = RbGeom<T, N, M, RPL, RB_STAGES>;
@@ -139,14 +141,19 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
     auto issue = [&](int64_t tile, int stage) {
         unsigned char *sb = wbase + stage * Gm::STAGE;
         const int64_t f0 = tile * FPW;
-        mbar_expect_tx(&bar[stage], Gm::TX);
+        constexpr uint32_t tx = Gm::XB + Gm::PB + ((MODE & 1) ? 2 * Gm::PB : 0) + ((MODE & 2) ? Gm::HB + Gm::RBY + Gm::ZB : 0);
+        mbar_expect_tx(&bar[stage], tx);
         bulk_load(sb + Gm::OX, p.x + f0 * N, Gm::XB, &bar[stage]);
         bulk_load(sb + Gm::OP, p.P + f0 * N * N, Gm::PB, &bar[stage]);
-        bulk_load(sb + Gm::OF, p.F + f0 * N * N, Gm::PB, &bar[stage]);
-        bulk_load(sb + Gm::OQ, p.Q + f0 * N * N, Gm::PB, &bar[stage]);
-        bulk_load(sb + Gm::OH, p.H + f0 * M * N, Gm::HB, &bar[stage]);
-        bulk_load(sb + Gm::OR_, p.R + f0 * M * M, Gm::RBY, &bar[stage]);
-        bulk_load(sb + Gm::OZ, p.z + f0 * M, Gm::ZB, &bar[stage]);
+        if constexpr (MODE & 1) {
+            bulk_load(sb + Gm::OF, p.F + f0 * N * N, Gm::PB, &bar[stage]);
+            bulk_load(sb + Gm::OQ, p.Q + f0 * N * N, Gm::PB, &bar[stage]);
+        }
+        if constexpr (MODE & 2) {
+            bulk_load(sb + Gm::OH, p.H + f0 * M * N, Gm::HB, &bar[stage]);
+            bulk_load(sb + Gm::OR_, p.R + f0 * M * M, Gm::RBY, &bar[stage]);
+            bulk_load(sb + Gm::OZ, p.z + f0 * M, Gm::ZB, &bar[stage]);
+        }
     };
 
     if (lane == 0) {
@@ -184,11 +191,19 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
         // ---------------- predict: x' = F x ; P' = alpha^2 (F P) F' + Q -----------------------
         T A[RPL][N];                 // this lane's rows of the left operand
         T C[RPL][N];                 // this lane's rows of the result
+        T xr[RPL];
+        if constexpr (!(MODE & 1)) {                  // update only: this lane's rows of P and x as they were loaded
+#pragma unroll
+            for (int i = 0; i < RPL; i++) {
+                xr[i] = sx[r0 + i];
+#pragma unroll
+                for (int k = 0; k < N; k++) A[i][k] = sP[(r0 + i) * N + k];
+            }
+        } else {
 #pragma unroll
         for (int i = 0; i < RPL; i++)
 #pragma unroll
             for (int k = 0; k < N; k++) A[i][k] = sF[(r0 + i) * N + k];
-        T xr[RPL];
 #pragma unroll
         for (int i = 0; i < RPL; i++) {
             T s = T(0);
@@ -245,9 +260,10 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
             }
         }
         __syncwarp();
+        }   // MODE & 1
 
         // ---------------- update ------------------------------------------------------------
-        const bool has_z = (p.valid == nullptr) || (p.valid[f] != 0);
+        const bool has_z = (MODE & 2) && ((p.valid == nullptr) || (p.valid[f] != 0));
         const unsigned um = __ballot_sync(FULL, has_z);
         int st = BKE_STATUS_OK;
         T xo[RPL];
@@ -416,7 +432,7 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
                 }
             }
         }
-        if (EXTRAS && !has_z && active && rb == 0 && p.y) {  // z is None: y = 0 (kalman_filter.py:515-520)
+        if (EXTRAS && (MODE & 2) && !has_z && active && rb == 0 && p.y) {  // z is None: y = 0 (kalman_filter.py:515-520)
             for (int a = 0; a < M; a++) p.y[f * M + a] = T(0);
         }
         // ---------------- posterior rows -> staging -> bulk TMA store ---------------------------
@@ -450,6 +466,7 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
 template <typename T, int N, int M, int RPL, int RB_STAGES, int RB_WARPS>
 int launch_rb(const bke_kf_args &a, cudaStream_t s)
 {
+    const int mode = (int)(a.flags & (BKE_DO_PREDICT | BKE_DO_UPDATE));
     using Gm = RbGeom<T, N, M, RPL, RB_STAGES>;
     const int64_t Nmain = (a.n_filters / Gm::FPW) * Gm::FPW;
     const int64_t rem = a.n_filters - Nmain;
@@ -462,15 +479,17 @@ int launch_rb(const bke_kf_args &a, cudaStream_t s)
         p.x_prior = (T *)a.x_prior; p.P_prior = (T *)a.P_prior; p.K = (T *)a.K; p.y = (T *)a.y;
         p.S = (T *)a.S; p.SI = (T *)a.SI; p.ll = (T *)a.log_likelihood;
         const bool extras = a.x_prior || a.P_prior || a.K || a.y || a.S || a.SI || a.log_likelihood;
-        auto kern = extras ? kf_rowblock_kernel<T, N, M, RPL, RB_STAGES, RB_WARPS, true>
-                           : kf_rowblock_kernel<T, N, M, RPL, RB_STAGES, RB_WARPS, false>;
+        auto kern = extras ? kf_rowblock_kernel<T, N, M, RPL, RB_STAGES, RB_WARPS, true, 3>
+                           : kf_rowblock_kernel<T, N, M, RPL, RB_STAGES, RB_WARPS, false, 3>;
+        if (mode == 1) kern = kf_rowblock_kernel<T, N, M, RPL, RB_STAGES, RB_WARPS, true, 1>;     // the single-mode kernels always
+        if (mode == 2) kern = kf_rowblock_kernel<T, N, M, RPL, RB_STAGES, RB_WARPS, true, 2>;     // carry the optional outputs
         const int smem = RB_WARPS * Gm::WARP_BYTES;
-        static bool configured[2][64] = {{false}};
+        static bool configured[4][64] = {{false}};
         int dev = 0;
         cudaGetDevice(&dev);
-        if (dev < 0 || dev >= 64 || !configured[extras][dev]) {
+        if (dev < 0 || dev >= 64 || !configured[mode == 3 ? (int)extras : 1 + mode][dev]) {
             if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
-            if (dev >= 0 && dev < 64) configured[extras][dev] = true;
+            if (dev >= 0 && dev < 64) configured[mode == 3 ? (int)extras : 1 + mode][dev] = true;
         }
         const int64_t tiles = Nmain / Gm::FPW;
         int64_t grid = (tiles + RB_WARPS - 1) / RB_WARPS;
@@ -503,11 +522,13 @@ bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 int launch_kf_rowblock(const bke_kf_args &a, cudaStream_t s)
 {
     // fused predict+update, per-filter dense models, no control input
-    if ((a.flags & (BKE_DO_PREDICT | BKE_DO_UPDATE | BKE_UPDATE_FIRST)) != (BKE_DO_PREDICT | BKE_DO_UPDATE)) return BKE_ERR_UNSUPPORTED;
+    if ((a.flags & BKE_UPDATE_FIRST) || !(a.flags & (BKE_DO_PREDICT | BKE_DO_UPDATE))) return BKE_ERR_UNSUPPORTED;
+    const bool dp = a.flags & BKE_DO_PREDICT, du = a.flags & BKE_DO_UPDATE;
     if (a.B && a.u) return BKE_ERR_UNSUPPORTED;
-    if (!a.F_stride || !a.Q_stride || !a.H_stride || !a.R_stride) return BKE_ERR_UNSUPPORTED;
-    if (!(al16(a.x) && al16(a.P) && al16(a.F) && al16(a.Q) && al16(a.H) && al16(a.R) && al16(a.z) && al16(a.x_out) && al16(a.P_out)))
-        return BKE_ERR_UNSUPPORTED;
+    if ((dp && (!a.F_stride || !a.Q_stride)) || (du && (!a.H_stride || !a.R_stride))) return BKE_ERR_UNSUPPORTED;
+    if (!(al16(a.x) && al16(a.P) && al16(a.x_out) && al16(a.P_out))) return BKE_ERR_UNSUPPORTED;
+    if (dp && !(al16(a.F) && al16(a.Q))) return BKE_ERR_UNSUPPORTED;
+    if (du && !(al16(a.H) && al16(a.R) && al16(a.z))) return BKE_ERR_UNSUPPORTED;
     const int n = a.dim_x, m = a.dim_z;
     // 9/3 fp64: one stage per warp and 8 warps per SM (two per scheduler: the FP64 pipe of one warp's
     // dependent DFMA chains is covered by the other) beat a 2-stage ring with 4 warps; BKE_RB_RING=1

@@ -397,3 +397,42 @@ def test_small_shapes_random_models_vs_oracle(n, m, dtype, tol, shared):
         got = got.cpu().numpy().astype(np.float64)
         ref_mag = np.abs(want).reshape(N, -1).max(axis=1).reshape((N,) + (1,) * (want.ndim - 1))
         assert np.all(np.abs(got - want) <= tol * (np.abs(want) + 0.05 * ref_mag + 1e-12)), (n, m, dtype)
+
+
+@pytest.mark.parametrize("n,m,dtype", [(9, 3, np.float64), (9, 3, np.float32), (6, 3, np.float64)])
+@pytest.mark.parametrize("diagnostics", [False, True])
+def test_rowblock_separate_predict_and_update_match_fused(n, m, dtype, diagnostics):
+    """The row-block kernel's predict-only and update-only modes (a stand-alone predict happens
+    whenever the state is read between predict() and update(), and in every IMM step) against
+    its fused mode, with a measurement mask and a ragged bank."""
+    import torch
+    from filterpy_b200.kalman import KalmanFilter
+    rng = np.random.default_rng(n * 10 + m)
+    N = 1037
+
+    def spd(k, scale):
+        a = rng.normal(size=(N, k, k))
+        return scale * (a @ np.swapaxes(a, -1, -2) / k + np.eye(k))
+    F = np.eye(n) + 0.1 * rng.normal(size=(N, n, n)); H = rng.normal(size=(N, m, n))
+    Q, R, P0, x0 = spd(n, 0.05), spd(m, 0.5), spd(n, 2.0), rng.normal(size=(N, n))
+    zs = rng.normal(size=(3, N, m)); valid = rng.random((3, N)) > 0.2
+    banks = []
+    for separate in (False, True):
+        kf = KalmanFilter(n, m, n_filters=N, dtype=dtype, diagnostics=diagnostics)
+        kf.x, kf.P, kf.F, kf.H, kf.Q, kf.R = x0, P0, F, H, Q, R
+        for t in range(3):
+            kf.predict()
+            if separate:
+                prior = kf.x.clone()                       # forces the stand-alone predict launch
+            kf.update(torch.from_numpy(zs[t]), valid=valid[t])
+        banks.append(kf)
+    tol = 1e-9 if dtype is np.float64 else 1e-4
+    a, b = banks
+    rel_close(b.x.cpu().numpy(), a.x.cpu().numpy(), tol, "x")
+    rel_close(b.P.cpu().numpy(), a.P.cpu().numpy(), tol, "P")
+    if diagnostics:
+        rel_close(b.K.cpu().numpy(), a.K.cpu().numpy(), tol * 10, "K")
+        rel_close(b.x_prior.cpu().numpy(), a.x_prior.cpu().numpy(), tol, "x_prior")
+        rel_close(b.P_prior.cpu().numpy(), a.P_prior.cpu().numpy(), tol, "P_prior")
+        np.testing.assert_allclose(b.log_likelihood.cpu().numpy()[valid[2]], a.log_likelihood.cpu().numpy()[valid[2]],
+                                   rtol=tol * 100, atol=tol * 100)
