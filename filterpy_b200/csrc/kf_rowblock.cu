@@ -107,6 +107,9 @@ struct RbGeom {
     // the posterior is staged in the stage's own x / P slots (more warps fit an SM instead)
     static constexpr int OUT = RB_STAGES > 1 ? a16(XB) + a16(PB) : 0;
     static constexpr int WARP_BYTES = RB_STAGES * STAGE + OUT;
+    // one copy of F, Q, H, R per warp for banks that share their models (kept for the whole launch)
+    static constexpr int SH_ELEMS = 2 * N * N + M * N + M * M;
+    static constexpr int SH_BYTES = a16(SH_ELEMS * (int)sizeof(T));
     static constexpr uint32_t TX = XB + 3 * PB + HB + RBY + ZB;
     static_assert(N % RPL == 0 && G >= 1 && G <= 32 && FPW >= 1, "bad row-block shape");
     static_assert(XB % 16 == 0 && PB % 16 == 0 && HB % 16 == 0 && RBY % 16 == 0 && ZB % 16 == 0, "bulk copies need 16-byte multiples");
@@ -117,7 +120,9 @@ struct RbGeom {
 // live ranges cost the C3 kernel 9 % when they were run-time tests)
 // MODE: 3 = fused predict+update, 1 = predict only, 2 = update only (what is not needed is neither
 // loaded nor computed)
-template <typename T, int N, int M, int RPL, int RB_STAGES, int RB_WARPS, bool EXTRAS, int MODE>
+// SHARED: F, H, Q, R are one matrix each for the whole bank (stride 0): every warp keeps a copy in
+// shared memory for the launch and the tiles carry only x, P, z
+template <typename T, int N, int M, int RPL, int RB_STAGES, int RB_WARPS, bool EXTRAS, int MODE, bool SHARED>
 __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
 {
     using Gm = RbGeom<T, N, M, RPL, RB_STAGES>;
@@ -141,21 +146,35 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
     auto issue = [&](int64_t tile, int stage) {
         unsigned char *sb = wbase + stage * Gm::STAGE;
         const int64_t f0 = tile * FPW;
-        constexpr uint32_t tx = Gm::XB + Gm::PB + ((MODE & 1) ? 2 * Gm::PB : 0) + ((MODE & 2) ? Gm::HB + Gm::RBY + Gm::ZB : 0);
+        constexpr uint32_t tx = Gm::XB + Gm::PB + ((MODE & 1) && !SHARED ? 2 * Gm::PB : 0) +
+                                ((MODE & 2) ? (SHARED ? 0 : Gm::HB + Gm::RBY) + Gm::ZB : 0);
         mbar_expect_tx(&bar[stage], tx);
         bulk_load(sb + Gm::OX, p.x + f0 * N, Gm::XB, &bar[stage]);
         bulk_load(sb + Gm::OP, p.P + f0 * N * N, Gm::PB, &bar[stage]);
-        if constexpr (MODE & 1) {
+        if constexpr ((MODE & 1) && !SHARED) {
             bulk_load(sb + Gm::OF, p.F + f0 * N * N, Gm::PB, &bar[stage]);
             bulk_load(sb + Gm::OQ, p.Q + f0 * N * N, Gm::PB, &bar[stage]);
         }
-        if constexpr (MODE & 2) {
+        if constexpr ((MODE & 2) && !SHARED) {
             bulk_load(sb + Gm::OH, p.H + f0 * M * N, Gm::HB, &bar[stage]);
             bulk_load(sb + Gm::OR_, p.R + f0 * M * M, Gm::RBY, &bar[stage]);
-            bulk_load(sb + Gm::OZ, p.z + f0 * M, Gm::ZB, &bar[stage]);
         }
+        if constexpr (MODE & 2) bulk_load(sb + Gm::OZ, p.z + f0 * M, Gm::ZB, &bar[stage]);
     };
 
+    // the shared models of this warp: after all warps' stages (generic-proxy loads and stores only)
+    T *shF = reinterpret_cast<T *>(smem + (size_t)RB_WARPS * Gm::WARP_BYTES + (size_t)wib * Gm::SH_BYTES);
+    T *shQ = shF + N * N, *shH = shQ + N * N, *shR = shH + M * N;
+    if constexpr (SHARED) {
+        for (int e = lane; e < N * N; e += 32) {
+            if (MODE & 1) { shF[e] = p.F[e]; shQ[e] = p.Q[e]; }
+        }
+        if (MODE & 2) {
+            for (int e = lane; e < M * N; e += 32) shH[e] = p.H[e];
+            for (int e = lane; e < M * M; e += 32) shR[e] = p.R[e];
+        }
+        __syncwarp();
+    }
     if (lane == 0) {
         for (int s = 0; s < RB_STAGES; s++) mbar_init(&bar[s], 1);
         fence_mbar_init();
@@ -179,8 +198,10 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
         T *sP = reinterpret_cast<T *>(sb + Gm::OP) + fl * N * N;
         T *sF = reinterpret_cast<T *>(sb + Gm::OF) + fl * N * N;
         T *sQ = reinterpret_cast<T *>(sb + Gm::OQ) + fl * N * N;
-        const T *sH = reinterpret_cast<const T *>(sb + Gm::OH) + fl * M * N;
-        const T *sR = reinterpret_cast<const T *>(sb + Gm::OR_) + fl * M * M;
+        const T *sH = SHARED ? shH : reinterpret_cast<const T *>(sb + Gm::OH) + fl * M * N;
+        const T *sR = SHARED ? shR : reinterpret_cast<const T *>(sb + Gm::OR_) + fl * M * M;
+        const T *rF = SHARED ? shF : sF;            // the MODELS F, Q (sF / sQ are also scratch for I - K H, K, P H')
+        const T *rQ = SHARED ? shQ : sQ;
         const T *sz = reinterpret_cast<const T *>(sb + Gm::OZ) + fl * M;
         unsigned char *out_x = RB_STAGES > 1 ? outb : sb + Gm::OX;
         unsigned char *out_P = RB_STAGES > 1 ? outb + Gm::a16(Gm::XB) : sb + Gm::OP;
@@ -203,7 +224,7 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
 #pragma unroll
         for (int i = 0; i < RPL; i++)
 #pragma unroll
-            for (int k = 0; k < N; k++) A[i][k] = sF[(r0 + i) * N + k];
+            for (int k = 0; k < N; k++) A[i][k] = rF[(r0 + i) * N + k];
 #pragma unroll
         for (int i = 0; i < RPL; i++) {
             T s = T(0);
@@ -231,13 +252,13 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
         for (int j = 0; j < N; j++) {
             T b[N];
 #pragma unroll
-            for (int k = 0; k < N; k++) b[k] = sF[j * N + k];
+            for (int k = 0; k < N; k++) b[k] = rF[j * N + k];
 #pragma unroll
             for (int i = 0; i < RPL; i++) {
                 T s = T(0);
 #pragma unroll
                 for (int k = 0; k < N; k++) s += C[i][k] * b[k];
-                A[i][j] = p.alpha_sq * s + sQ[(r0 + i) * N + j];
+                A[i][j] = p.alpha_sq * s + rQ[(r0 + i) * N + j];
             }
         }
         __syncwarp();                               // every lane is done reading x, P (and F rows it needed as B)
@@ -479,17 +500,26 @@ int launch_rb(const bke_kf_args &a, cudaStream_t s)
         p.x_prior = (T *)a.x_prior; p.P_prior = (T *)a.P_prior; p.K = (T *)a.K; p.y = (T *)a.y;
         p.S = (T *)a.S; p.SI = (T *)a.SI; p.ll = (T *)a.log_likelihood;
         const bool extras = a.x_prior || a.P_prior || a.K || a.y || a.S || a.SI || a.log_likelihood;
-        auto kern = extras ? kf_rowblock_kernel<T, N, M, RPL, RB_STAGES, RB_WARPS, true, 3>
-                           : kf_rowblock_kernel<T, N, M, RPL, RB_STAGES, RB_WARPS, false, 3>;
-        if (mode == 1) kern = kf_rowblock_kernel<T, N, M, RPL, RB_STAGES, RB_WARPS, true, 1>;     // the single-mode kernels always
-        if (mode == 2) kern = kf_rowblock_kernel<T, N, M, RPL, RB_STAGES, RB_WARPS, true, 2>;     // carry the optional outputs
-        const int smem = RB_WARPS * Gm::WARP_BYTES;
-        static bool configured[4][64] = {{false}};
+        // every model the call reads is shared by the bank (stride 0)?  (a mix goes to the catch-all kernel)
+        const bool dp = a.flags & BKE_DO_PREDICT, du = a.flags & BKE_DO_UPDATE;
+        const bool shared = (!dp || (a.F_stride == 0 && a.Q_stride == 0)) && (!du || (a.H_stride == 0 && a.R_stride == 0));
+        auto kern = extras ? kf_rowblock_kernel<T, N, M, RPL, RB_STAGES, RB_WARPS, true, 3, false>
+                           : kf_rowblock_kernel<T, N, M, RPL, RB_STAGES, RB_WARPS, false, 3, false>;
+        if (mode == 1) kern = kf_rowblock_kernel<T, N, M, RPL, RB_STAGES, RB_WARPS, true, 1, false>;     // the single-mode and the
+        if (mode == 2) kern = kf_rowblock_kernel<T, N, M, RPL, RB_STAGES, RB_WARPS, true, 2, false>;     // shared-model kernels always
+        if (shared) {                                                                                     // carry the optional outputs
+            kern = kf_rowblock_kernel<T, N, M, RPL, RB_STAGES, RB_WARPS, true, 3, true>;
+            if (mode == 1) kern = kf_rowblock_kernel<T, N, M, RPL, RB_STAGES, RB_WARPS, true, 1, true>;
+            if (mode == 2) kern = kf_rowblock_kernel<T, N, M, RPL, RB_STAGES, RB_WARPS, true, 2, true>;
+        }
+        const int smem = RB_WARPS * (Gm::WARP_BYTES + (shared ? Gm::SH_BYTES : 0));
+        const int cfg = (mode == 3 ? (int)extras : 1 + mode) + (shared ? 4 : 0);
+        static bool configured[8][64] = {{false}};
         int dev = 0;
         cudaGetDevice(&dev);
-        if (dev < 0 || dev >= 64 || !configured[mode == 3 ? (int)extras : 1 + mode][dev]) {
+        if (dev < 0 || dev >= 64 || !configured[cfg][dev]) {
             if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
-            if (dev >= 0 && dev < 64) configured[mode == 3 ? (int)extras : 1 + mode][dev] = true;
+            if (dev >= 0 && dev < 64) configured[cfg][dev] = true;
         }
         const int64_t tiles = Nmain / Gm::FPW;
         int64_t grid = (tiles + RB_WARPS - 1) / RB_WARPS;
@@ -503,7 +533,8 @@ int launch_rb(const bke_kf_args &a, cudaStream_t s)
         auto off = [&](const void *ptr, int64_t per) { return ptr ? (const void *)((const char *)ptr + (size_t)Nmain * per * es) : nullptr; };
         t.n_filters = rem;
         t.x = off(a.x, N); t.P = off(a.P, N * N); t.x_out = (void *)off(a.x_out, N); t.P_out = (void *)off(a.P_out, N * N);
-        t.F = off(a.F, N * N); t.Q = off(a.Q, N * N); t.H = off(a.H, M * N); t.R = off(a.R, M * M);
+        t.F = a.F_stride ? off(a.F, N * N) : a.F; t.Q = a.Q_stride ? off(a.Q, N * N) : a.Q;      // shared models are not offset
+        t.H = a.H_stride ? off(a.H, M * N) : a.H; t.R = a.R_stride ? off(a.R, M * M) : a.R;
         t.z = off(a.z, M);
         t.x_prior = (void *)off(a.x_prior, N); t.P_prior = (void *)off(a.P_prior, N * N); t.K = (void *)off(a.K, N * M);
         t.y = (void *)off(a.y, M); t.S = (void *)off(a.S, M * M); t.SI = (void *)off(a.SI, M * M);
@@ -525,10 +556,16 @@ int launch_kf_rowblock(const bke_kf_args &a, cudaStream_t s)
     if ((a.flags & BKE_UPDATE_FIRST) || !(a.flags & (BKE_DO_PREDICT | BKE_DO_UPDATE))) return BKE_ERR_UNSUPPORTED;
     const bool dp = a.flags & BKE_DO_PREDICT, du = a.flags & BKE_DO_UPDATE;
     if (a.B && a.u) return BKE_ERR_UNSUPPORTED;
-    if ((dp && (!a.F_stride || !a.Q_stride)) || (du && (!a.H_stride || !a.R_stride))) return BKE_ERR_UNSUPPORTED;
+    {   // the models the call reads are either all per-filter or all shared; a mix goes to the catch-all kernel
+        int dense = 0, shared = 0;
+        if (dp) { (a.F_stride ? dense : shared)++; (a.Q_stride ? dense : shared)++; }
+        if (du) { (a.H_stride ? dense : shared)++; (a.R_stride ? dense : shared)++; }
+        if (dense && shared) return BKE_ERR_UNSUPPORTED;
+    }
     if (!(al16(a.x) && al16(a.P) && al16(a.x_out) && al16(a.P_out))) return BKE_ERR_UNSUPPORTED;
-    if (dp && !(al16(a.F) && al16(a.Q))) return BKE_ERR_UNSUPPORTED;
-    if (du && !(al16(a.H) && al16(a.R) && al16(a.z))) return BKE_ERR_UNSUPPORTED;
+    if (dp && a.F_stride && !(al16(a.F) && al16(a.Q))) return BKE_ERR_UNSUPPORTED;
+    if (du && a.H_stride && !(al16(a.H) && al16(a.R))) return BKE_ERR_UNSUPPORTED;
+    if (du && !al16(a.z)) return BKE_ERR_UNSUPPORTED;
     const int n = a.dim_x, m = a.dim_z;
     // 9/3 fp64: one stage per warp and 8 warps per SM (two per scheduler: the FP64 pipe of one warp's
     // dependent DFMA chains is covered by the other) beat a 2-stage ring with 4 warps; BKE_RB_RING=1

@@ -53,6 +53,7 @@ def main():
     kf_case("C2 kf 4/2 f32 per-filter + diagnostics", 4, 2, 1 << 20, np.float32, lambda N, steps: wl.kf_bank_cv2d(N, steps=steps), diagnostics=True)
     kf_case("kf 4/2 f64 (register tile, direct loads) 2^20", 4, 2, 1 << 20, np.float64, lambda N, steps: wl.kf_bank_cv2d(N, steps=steps))
     kf_case("C3 kf 9/3 f64 (row-block kernel) 1.25M", 9, 3, 1250000, np.float64, lambda N, steps: wl.kf_bank_ca3d(N, steps=steps))
+    kf_case("C3 kf 9/3 f64 shared models 1.25M", 9, 3, 1250000, np.float64, lambda N, steps: wl.kf_bank_ca3d(N, steps=steps), shared=True)
     kf_case("C3 kf 9/3 f64 + all diagnostics outputs 1.25M", 9, 3, 1250000, np.float64, lambda N, steps: wl.kf_bank_ca3d(N, steps=steps), diagnostics=True)
     kf_case("kf 9/3 f32 (row-block kernel, 8 filters per warp) 1.25M", 9, 3, 1250000, np.float32, lambda N, steps: wl.kf_bank_ca3d(N, steps=steps))
     # 6/3 (3-D constant velocity with a linear position sensor): fp32 -> direct kernel, fp64 -> row-block kernel

@@ -401,7 +401,8 @@ def test_small_shapes_random_models_vs_oracle(n, m, dtype, tol, shared):
 
 @pytest.mark.parametrize("n,m,dtype", [(9, 3, np.float64), (9, 3, np.float32), (6, 3, np.float64)])
 @pytest.mark.parametrize("diagnostics", [False, True])
-def test_rowblock_separate_predict_and_update_match_fused(n, m, dtype, diagnostics):
+@pytest.mark.parametrize("shared", [False, True])
+def test_rowblock_separate_predict_and_update_match_fused(n, m, dtype, diagnostics, shared):
     """The row-block kernel's predict-only and update-only modes (a stand-alone predict happens
     whenever the state is read between predict() and update(), and in every IMM step) against
     its fused mode, with a measurement mask and a ragged bank."""
@@ -419,7 +420,8 @@ def test_rowblock_separate_predict_and_update_match_fused(n, m, dtype, diagnosti
     banks = []
     for separate in (False, True):
         kf = KalmanFilter(n, m, n_filters=N, dtype=dtype, diagnostics=diagnostics)
-        kf.x, kf.P, kf.F, kf.H, kf.Q, kf.R = x0, P0, F, H, Q, R
+        kf.x, kf.P = x0, P0
+        kf.F, kf.H, kf.Q, kf.R = (F[0], H[0], Q[0], R[0]) if shared else (F, H, Q, R)
         for t in range(3):
             kf.predict()
             if separate:
