@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "bke_abi_version", "bke_last_error", "bke_device_count",
     "bke_kf_step", "bke_kf_batch_filter", "bke_ukf_step",
     "bke_resample_workspace_bytes", "bke_systematic_resample", "bke_stratified_resample",
-    "bke_weights_sum", "bke_weights_scale", "bke_resample_shard",
+    "bke_weights_sum", "bke_weights_scale", "bke_resample_shard", "bke_resample_normalized",
     "bke_merwe_sigma_points", "bke_unscented_transform",
     "bke_kf_rts_smoother", "bke_ukf_rts_smoother", "bke_mm_probabilities", "bke_mm_mix", "bke_mm_estimate", "bke_cumsum_exact", "bke_searchsorted", "bke_multinomial_resample", "bke_gather_rows",
 ]
@@ -186,6 +186,9 @@ def load():
     lib.bke_stratified_resample.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                             c_void_p, c_void_p, c_void_p]
     lib.bke_stratified_resample.restype = ctypes.c_int
+    lib.bke_resample_normalized.argtypes = [c_int64, c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p,
+                                            c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]
+    lib.bke_resample_normalized.restype = ctypes.c_int
     lib.bke_weights_sum.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.bke_weights_sum.restype = ctypes.c_int
     lib.bke_weights_scale.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p]

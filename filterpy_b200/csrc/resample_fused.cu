@@ -1,0 +1,1003 @@
+// resample_fused.cu — systematic / stratified resampling and the exact cumulative sum as ONE
+// single-pass kernel: every weight is read from HBM once (8 B in, 4 B out per particle).
+//
+//   indexes[i] = #{ j : c_j <= pos_i },  c_j = fl(c_{j-1} + w_j)   (filterpy/monte_carlo/resampling.py:141-149)
+//   pos_i = fl(fl(u + i) / N) (:139)  or  fl(fl(U_i + i) / N) (:103)
+//
+// The running sum is reproduced EXACTLY (resample_common.cuh: inside one binade adding w is the
+// integer map bits(S) -> bits(S) + d[parity]); what is new here is how the tiles are chained:
+// a decoupled look-back in TWO stages, both on one 64-bit status word per tile.
+//
+//   stage 1 (producer warp)  approximate fp64 tile sum -> approximate prefix `tp`  (which binade
+//            the tile lives in, and which adds might leave it)
+//   stage 2 (consumer warps) the tile's parity map D computed in that binade -> exact state S_in
+//            (bit pattern of the reference's running sum before the tile), then every c_j,
+//            the output range of every particle and the index expansion.
+//
+// CTA = NW consumer warps + 1 producer warp, persistent, tiles handed out by an atomic counter
+// (so a tile only ever waits for tiles that are already running).  The producer warp claims the
+// next tile, pulls its 16*NW*32 weights into shared memory with ONE 2-D TMA copy (128-byte
+// swizzle: thread t reads its 16 consecutive weights with conflict-free LDS.128), sums them,
+// publishes / resolves stage 1 and hands the stage over while the consumers still work on the
+// previous tile: HBM latency and the first look-back are off the consumers' critical path.
+// A tile that is not "clean" (a possible binade crossing, ties) takes slow_tile(): the old
+// raw-element / segment walk, started before S_in arrives so that only the short walk is serial.
+//
+// Expansion: each particle with >= 1 copies stores (local index + 1) at its first output slot of
+// a zeroed shared-memory window; a max-scan over the slots fills the runs (no divergent copy
+// loop), and every thread leaves with 16-byte stores of 20 consecutive indexes.
+//
+// Everything is verified with the exact values (tile start / end inside the assumed binade); a
+// failed check or a negative / non-finite weight switches to the literal sequential kernel.
+#include <cuda.h>
+#include <stdlib.h>
+#include "resample_common.cuh"
+#include "resample_fused.cuh"
+
+namespace bke {
+namespace rs {
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t f_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void f_mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(f_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void f_fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void f_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void f_mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(f_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void f_mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(f_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool f_mbar_try(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(f_smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void f_mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!f_mbar_try(bar, parity)) {}
+}
+__device__ __forceinline__ void f_tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(f_smem_u32(dst)), "l"(map), "r"(f_smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// named barriers of the consumer warps (the producer warp never joins them)
+template <int NT> __device__ __forceinline__ void f_bar()
+{
+    asm volatile("barrier.cta.sync 1, %0;" ::"n"(NT) : "memory");
+}
+template <int NT> __device__ __forceinline__ int f_bar_and(int pred)
+{
+    int out;
+    asm volatile("{\n.reg .pred p, q;\nsetp.ne.b32 p, %1, 0;\nbarrier.cta.red.and.pred q, 1, %2, p;\nselp.b32 %0, 1, 0, q;\n}\n"
+                 : "=r"(out) : "r"(pred), "n"(NT) : "memory");
+    return out;
+}
+__device__ __forceinline__ u64 f_ld(const u64 *p)
+{
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void f_st(u64 *p, u64 v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// ------------------------------------------------------------------ status words
+// st1[i], st2[i] describe tile i-1; entry 0 is the carry into the call (always INCLUSIVE).
+//   st1: bits of an fp64 sum with the two lowest mantissa bits replaced by the flag
+//        (1 = this tile's sum, 2 = sum of everything up to and including this tile)
+//   st2: bit 63 = INCLUSIVE: bits 0..62 = exact running sum after the tile (a non-negative double)
+//        bit 62 = AGGREGATE: bits 0..59 = d0 of the tile's parity map, bits 60..61 = t + 1
+constexpr u64 ST1_AGG = 1, ST1_INCL = 2;
+constexpr u64 ST2_INCL = 1ull << 63, ST2_AGG = 1ull << 62;
+constexpr int SPIN_LIMIT = 1 << 20;
+
+__device__ __forceinline__ u64 st2_pack_agg(i64 d, int t) { return ST2_AGG | ((u64)(t + 1) << 60) | ((u64)d & ((1ull << 60) - 1)); }
+
+// one status word, polled until it is published (bounded: a timeout flags the sequential fallback)
+__device__ __forceinline__ u64 f_poll(const u64 *p, u64 mask, FHeader *hdr, u64 dflt)
+{
+    u64 v = f_ld(p);
+    if (v & mask) return v;
+    for (int spins = 0; spins < SPIN_LIMIT; spins++) {
+        __nanosleep(32);
+        v = f_ld(p);
+        if (v & mask) return v;
+        // once any look-back has given up, nobody waits any longer (the result comes from the fallback)
+        if ((spins & 1023) == 1023 && *reinterpret_cast<volatile int *>(&hdr->timeout)) return dflt;
+    }
+    hdr->timeout = 1; hdr->fallback = 1;
+    return dflt;
+}
+
+// stage 1: approximate sum of everything before tile t (all 32 lanes of the producer warp)
+__device__ __forceinline__ double f_lookback_sum(const FParams &p, int t, int lane)
+{
+    double run = 0.0;
+    int idx = t - lane;                                    // st1 index of tile t-1-lane
+    for (;;) {
+        u64 v = ST1_INCL;                                  // beyond the carry: 0.0, inclusive
+        if (idx >= 0) v = f_poll(p.st1 + idx, 3, p.hdr, ST1_INCL);
+        const unsigned incl = __ballot_sync(FULL, (v & 3) == ST1_INCL);
+        const int first = incl ? __ffs(incl) - 1 : 31;
+        double x = (lane <= first) ? __longlong_as_double((i64)(v & ~3ull)) : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+        run += x;
+        if (incl) break;
+        idx -= 32;
+    }
+    return run;
+}
+
+// stage 2: exact state before tile t (all 32 lanes of consumer warp 0).  The aggregates between
+// the nearest inclusive predecessor and this tile are composed in tile order; with tie-free maps
+// (t = 0, the normal case) that is a plain int64 sum.
+__device__ __forceinline__ i64 f_lookback_state(const FParams &p, int t, int lane)
+{
+    i64 acc_d = 0; int acc_t = 0;                          // composite of the aggregates seen so far (applied LAST)
+    int idx = t - lane;
+    for (;;) {
+        u64 v = ST2_INCL;
+        if (idx >= 0) v = f_poll(p.st2 + idx, ST2_INCL | ST2_AGG, p.hdr, ST2_INCL);
+        const unsigned incl = __ballot_sync(FULL, (v & ST2_INCL) != 0);
+        const int first = incl ? __ffs(incl) - 1 : 32;     // lanes < first hold aggregates
+        i64 d = 0; int tt = 0;
+        if (lane < first) { d = (i64)(v & ((1ull << 60) - 1)); tt = (int)((v >> 60) & 3) - 1; }
+        const unsigned ties = __ballot_sync(FULL, tt != 0);
+        if (ties == 0) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(FULL, d, o);
+        } else {
+            // ordered: lane L holds tile t-1-L, i.e. higher lanes are applied first
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const i64 pd = __shfl_down_sync(FULL, d, o);
+                const int pt = __shfl_down_sync(FULL, tt, o);
+                if (lane + o < 32) {
+                    const SM r = combine(SM{pd, pt, 0, K_ID}, SM{d, tt, 0, K_ID});
+                    d = r.d; tt = r.t;
+                }
+            }
+            d = __shfl_sync(FULL, d, 0); tt = __shfl_sync(FULL, tt, 0);
+        }
+        {   // this window lies before everything accumulated so far
+            const SM r = combine(SM{d, ties ? tt : 0, 0, K_ID}, SM{acc_d, acc_t, 0, K_ID});
+            acc_d = r.d; acc_t = r.t;
+        }
+        if (incl) {
+            const i64 S = (i64)(__shfl_sync(FULL, v, first) & ~ST2_INCL);
+            return S + acc_d + ((S & 1) ? acc_t : 0);
+        }
+        idx -= 32;
+    }
+}
+
+// ------------------------------------------------------------------ shared memory
+template <int NW>
+struct FSmem {
+    static constexpr int NT = NW * 32, TILE = NT * F_IPT, WIN = NT * F_SPT;
+    double w[F_STAGES][TILE];          // TMA destinations (128-byte swizzle): must stay first, 1024-aligned
+    int win[WIN];                      // output window (all zero between tiles)
+    i64 warp_tot[NW];
+    double warp_d[NW];
+    SM warp_sm[NW];
+    int warp_max[NW];
+    uint64_t full_tma[F_STAGES], ready[F_STAGES], empty[F_STAGES];
+    struct Info { int t; int bad; double tp; double tot; } info[F_STAGES];
+    i64 bc_S_in, bc_lo, bc_cnt;
+    int bc_ok, bc_skip;
+    // slow path (tiles with raw elements)
+    i64 segstate[RMAX + 1];
+    i64 segd[RMAX + 1];
+    double wraw[RMAX];
+    int segk[RMAX + 1];
+    int segt[RMAX + 1];
+    int first_raw[NT + 1];
+    i64 tstart[NT];
+};
+
+// byte offset of weight (row r = owning thread, 16-byte chunk c) inside a swizzled stage
+__device__ __forceinline__ uint32_t f_swz(int r, int c) { return (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4); }
+
+template <int NW> __device__ __forceinline__ double f_scan_d(double v, double *total, double *sh, int lane, int wid)
+{
+    const double inc = warp_incl_scan_d(v, lane);
+    if (lane == 31) sh[wid] = inc;
+    f_bar<NW * 32>();
+    double base = 0.0, tot = 0.0;
+#pragma unroll
+    for (int i = 0; i < NW; i++) { const double x = sh[i]; if (i < wid) base += x; tot += x; }
+    f_bar<NW * 32>();
+    *total = tot;
+    return base + (inc - v);
+}
+
+template <int NW> __device__ __forceinline__ SM f_scan_sm(SM v, SM *total, SM *sh, int lane, int wid)
+{
+    const SM inc = warp_incl_scan_sm(v, lane);
+    if (lane == 31) sh[wid] = inc;
+    f_bar<NW * 32>();
+    SM base = sm_identity(), tot = sm_identity();
+    for (int i = 0; i < NW; i++) { const SM x = sh[i]; if (i < wid) base = combine(base, x); tot = combine(tot, x); }
+    f_bar<NW * 32>();
+    *total = tot;
+    SM prev = shfl_up_sm(inc, 1);
+    if (lane == 0) prev = sm_identity();
+    return combine(base, prev);
+}
+
+template <int MODE>
+__device__ __forceinline__ i64 f_count_below(const FParams &p, double c)
+{
+    const double Ngd = (double)p.ng;
+    return (MODE == F_STRAT) ? count_below_str(c, p.U, p.ng, Ngd) : count_below_sys(c, p.u, p.ng, Ngd, p.tau);
+}
+
+__device__ __forceinline__ void f_put_index(const FParams &p, i64 out_begin, i64 o, int value)
+{
+    const i64 rel = o - out_begin;
+    if (rel >= 0 && rel < p.cap) p.idx[rel] = value;
+    else p.hdr->cap_overflow = 1;
+}
+
+// lane 0 of consumer warp 0, after the tile's exact end state is known and published
+template <int NW, int MODE>
+__device__ __forceinline__ void f_finish_tile(const FParams &p, FSmem<NW> &sm, int t, i64 S_in, i64 S_out, int good)
+{
+    i64 lo = 0, cnt = 0;
+    if (MODE != F_CUMSUM && good) {
+        lo = f_count_below<MODE>(p, __longlong_as_double(S_in));
+        cnt = f_count_below<MODE>(p, __longlong_as_double(S_out)) - lo;
+        if (cnt < 0) { cnt = 0; good = 0; }
+    }
+    sm.bc_S_in = S_in; sm.bc_lo = lo; sm.bc_cnt = cnt; sm.bc_ok = good;
+    if (!good) { p.hdr->fallback = 1; p.hdr->chain_bad = 1; }
+    if (t == p.T - 1) {
+        if (p.cumsum_last) *p.cumsum_last = __longlong_as_double(S_out);
+        if (MODE != F_CUMSUM) {
+            i64 O1 = lo + cnt;
+            if (p.is_last && O1 < p.ng) {                  // resampling.py:145 would raise IndexError
+                p.hdr->overflow = (int)(p.ng - O1 > 0x7fffffff ? 0x7fffffff : p.ng - O1);
+                const int r = atomicAdd(&p.hdr->n_runs, 1);
+                if (r < p.max_runs) p.runs[r] = Run{O1, p.ng, (int)(p.ng - 1), 0};
+                O1 = p.ng;
+            }
+            p.hdr->out_end = O1;
+            if (p.out_range) { p.out_range[0] = p.hdr->out_begin; p.out_range[1] = O1; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ slow path: ties, raw elements, dense raw zones
+// Leaves the exact c_j (bit patterns) of the tile in the stage buffer, at the positions of the
+// weights they belong to; returns 1 if the tile verified.  Everything up to the segment export
+// runs BEFORE the exact start state is known; only the walk over <= RMAX segments is serial.
+template <int NW, int MODE>
+__device__ __noinline__ int f_slow_tile(const FParams &p, FSmem<NW> &sm, int s, int t)
+{
+    constexpr int NT = NW * 32;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    unsigned char *sb = reinterpret_cast<unsigned char *>(sm.w[s]);
+    double w[F_IPT];
+#pragma unroll
+    for (int c = 0; c < F_IPT / 2; c++) {
+        const double2 v = *reinterpret_cast<const double2 *>(sb + f_swz(tid, c));
+        w[2 * c] = v.x; w[2 * c + 1] = v.y;
+    }
+    double ssum = 0.0;
+#pragma unroll
+    for (int k = 0; k < F_IPT; k++) ssum += w[k];
+    double tot;
+    double before = sm.info[s].tp + f_scan_d<NW>(ssum, &tot, sm.warp_d, lane, wid);
+    SM inc[F_IPT];
+    int ek[F_IPT];
+    SM run = sm_identity();
+#pragma unroll
+    for (int k = 0; k < F_IPT; k++) {
+        const double after = before + w[k];
+        SM el;
+        if (w[k] == 0.0) { el = sm_identity(); ek[k] = K_ID; }          // fl(S + 0) = S in every binade
+        else {
+            int e;
+            if (clean_add(before, after, p.eb, &e)) { el = elem_map(w[k], e); ek[k] = e; }
+            else { el = SM{0, 0, 1, K_ID}; ek[k] = -1; }
+        }
+        run = combine(run, el);
+        inc[k] = run;
+        before = after;
+    }
+    SM total;
+    const SM excl = f_scan_sm<NW>(run, &total, sm.warp_sm, lane, wid);
+#pragma unroll
+    for (int k = 0; k < F_IPT; k++) inc[k] = combine(excl, inc[k]);
+    const int nraw = total.cnt;
+    int bad = 0;
+    if (nraw > 0 && nraw <= RMAX) {
+        sm.first_raw[tid] = (ek[0] == -1);
+        if (tid == 0) sm.first_raw[NT] = 1;                 // the tile end closes the last segment
+        for (int q = tid; q <= RMAX; q += NT) { sm.segk[q] = -1; sm.segt[q] = 0; sm.segd[q] = 0; }
+        f_bar<NT>();
+#pragma unroll
+        for (int k = 0; k < F_IPT; k++) {
+            const int seg = inc[k].cnt;
+            if (ek[k] == -1) {
+                sm.wraw[seg - 1] = w[k];                    // the raw element that opens segment `seg`
+            } else {
+                const bool next_raw = (k + 1 < F_IPT) ? (ek[k + 1] == -1) : (sm.first_raw[tid + 1] != 0);
+                if (next_raw) {
+                    if (inc[k].k == K_POISON) bad = 1;
+                    sm.segk[seg] = inc[k].k == K_ID ? -1 : inc[k].k;    // identity segments are skipped
+                    sm.segt[seg] = inc[k].t;
+                    sm.segd[seg] = inc[k].d;
+                }
+            }
+        }
+    }
+    f_bar<NT>();
+    if (wid == 0) {
+        const bool agg_ok = (nraw == 0) && total.k != K_POISON && total.d >= 0 && total.d < (1ll << 59);
+        if (agg_ok && lane == 0) f_st(p.st2 + t + 1, st2_pack_agg(total.d, total.t));
+        const i64 S_in = f_lookback_state(p, t, lane);
+        if (lane == 0) {
+            int wbad = 0;
+            i64 S_out;
+            if (nraw == 0) {
+                S_out = total.k >= 0 ? apply_bits(S_in, total.d, total.t, total.k, &wbad) : S_in;
+                if (total.k == K_POISON) wbad = 1;
+                sm.segstate[0] = S_in;
+            } else if (nraw <= RMAX) {
+                i64 S = S_in;
+                for (int q = 0; q <= nraw; q++) {
+                    sm.segstate[q] = S;
+                    if (sm.segk[q] >= 0) S = apply_bits(S, sm.segd[q], sm.segt[q], sm.segk[q], &wbad);
+                    if (q < nraw) S = __double_as_longlong(__dadd_rn(__longlong_as_double(S), sm.wraw[q]));
+                }
+                S_out = S;
+                atomicAdd(&p.hdr->n_unclean, 1);
+            } else {
+                // a dense zone of raw elements (tiny weights next to a binade boundary): true adds, one by one
+                double acc = __longlong_as_double(S_in);
+                for (int th = 0; th < NT; th++) {
+                    sm.tstart[th] = __double_as_longlong(acc);
+#pragma unroll
+                    for (int c = 0; c < F_IPT / 2; c++) {
+                        const double2 v = *reinterpret_cast<const double2 *>(sb + f_swz(th, c));
+                        acc = __dadd_rn(acc, v.x);
+                        acc = __dadd_rn(acc, v.y);
+                    }
+                }
+                S_out = __double_as_longlong(acc);
+                atomicAdd(&p.hdr->n_seq, 1);
+            }
+            f_st(p.st2 + t + 1, ST2_INCL | (u64)S_out);
+            atomicAdd(&p.hdr->n_slow, 1);
+            f_finish_tile<NW, MODE>(p, sm, t, S_in, S_out, !wbad);
+        }
+    }
+    f_bar<NT>();
+    i64 cb[F_IPT];
+    if (nraw > RMAX) {
+        double acc = __longlong_as_double(sm.tstart[tid]);
+#pragma unroll
+        for (int k = 0; k < F_IPT; k++) { acc = __dadd_rn(acc, w[k]); cb[k] = __double_as_longlong(acc); }
+    } else {
+#pragma unroll
+        for (int k = 0; k < F_IPT; k++) {
+            const i64 S0 = sm.segstate[inc[k].cnt];
+            if (inc[k].k == K_POISON) bad = 1;
+            // a raw element: the segment it opens starts at its own result; only zeros so far: unchanged
+            cb[k] = (ek[k] == -1 || inc[k].k < 0) ? S0 : apply_bits(S0, inc[k].d, inc[k].t, inc[k].k, &bad);
+        }
+    }
+    if (bad) { p.hdr->fallback = 1; p.hdr->chain_bad = 2; }
+#pragma unroll
+    for (int c = 0; c < F_IPT / 2; c++)
+        *reinterpret_cast<longlong2 *>(sb + f_swz(tid, c)) = make_longlong2(cb[2 * c], cb[2 * c + 1]);
+    f_fence_proxy_async();                // generic-proxy writes to a stage the TMA engine will refill
+    return f_bar_and<NT>(!bad && sm.bc_ok);
+}
+
+// cumsum mode: the exact running sums leave as they are (each thread owns 16 consecutive elements = one 128-byte line)
+__device__ __forceinline__ void f_store_cumsum(const FParams &p, i64 j, const i64 (&cb)[F_IPT])
+{
+    double *o = p.cumsum_out + j;
+    if (j + F_IPT <= p.n && (reinterpret_cast<uintptr_t>(o) & 15) == 0 && !(p.last_one && j + F_IPT == p.n)) {
+#pragma unroll
+        for (int k = 0; k < F_IPT; k += 2)
+            *reinterpret_cast<double2 *>(o + k) = make_double2(__longlong_as_double(cb[k]), __longlong_as_double(cb[k + 1]));
+    } else {
+#pragma unroll
+        for (int k = 0; k < F_IPT; k++)
+            if (j + k < p.n) o[k] = (p.last_one && j + k == p.n - 1) ? 1.0 : __longlong_as_double(cb[k]);
+    }
+}
+
+// read this thread's F_SPT window slots (and clear them), running maximum, block max-scan:
+// m[i] = marker (local particle index + 1) of the particle that owns slot tid*F_SPT + i
+template <int NW>
+__device__ __forceinline__ void f_window_scan(FSmem<NW> &sm, int tid, int lane, int wid, int (&m)[F_SPT])
+{
+    constexpr int NT = NW * 32;
+    int4 *wv = reinterpret_cast<int4 *>(sm.win) + tid * (F_SPT / 4);
+#pragma unroll
+    for (int i = 0; i < F_SPT / 4; i++) {
+        const int4 q = wv[i];
+        m[4 * i] = q.x; m[4 * i + 1] = q.y; m[4 * i + 2] = q.z; m[4 * i + 3] = q.w;
+    }
+#pragma unroll
+    for (int i = 0; i < F_SPT / 4; i++) wv[i] = make_int4(0, 0, 0, 0);
+#pragma unroll
+    for (int i = 1; i < F_SPT; i++) m[i] = max(m[i], m[i - 1]);
+    int incm = m[F_SPT - 1];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, incm, o); if (lane >= o) incm = max(incm, y); }
+    int basem = __shfl_up_sync(FULL, incm, 1);
+    if (lane == 0) basem = 0;
+    if (lane == 31) sm.warp_max[wid] = incm;
+    f_bar<NT>();
+#pragma unroll
+    for (int i = 0; i < NW; i++) { const int x = sm.warp_max[i]; if (i < wid) basem = max(basem, x); }
+#pragma unroll
+    for (int i = 0; i < F_SPT; i++) m[i] = max(m[i], basem);
+}
+
+// ------------------------------------------------------------------ the kernel
+template <int NW, int MODE>
+__global__ void __launch_bounds__(NW * 32 + 32, NW == 8 ? 2 : 4)
+k_fused(const __grid_constant__ CUtensorMap wmap, const FParams p)
+{
+    constexpr int NT = NW * 32, TILE = NT * F_IPT, WIN = NT * F_SPT;
+    extern __shared__ __align__(1024) unsigned char f_smem_raw[];
+    FSmem<NW> &sm = *reinterpret_cast<FSmem<NW> *>(f_smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    if (tid == 0) {
+        for (int s = 0; s < F_STAGES; s++) { f_mbar_init(&sm.full_tma[s], 1); f_mbar_init(&sm.ready[s], 1); f_mbar_init(&sm.empty[s], NW); }
+        f_fence_mbar_init();
+    }
+    for (int q = tid; q < WIN; q += NT + 32) sm.win[q] = 0;
+    __syncthreads();
+
+    const double divisor = p.div ? *p.div : 1.0;
+
+    if (wid == NW) {
+        // ============================================================ producer warp
+        for (int q = 0;; q++) {
+            const int s = q % F_STAGES, use = q / F_STAGES;
+            if (use > 0) f_mbar_wait(&sm.empty[s], (use - 1) & 1);
+            int t = 0;
+            if (lane == 0) t = atomicAdd(&p.hdr->tile_counter, 1);
+            t = __shfl_sync(FULL, t, 0);
+            if (t >= p.T) {
+                if (lane == 0) { sm.info[s].t = -1; f_mbar_arrive(&sm.ready[s]); }
+                break;
+            }
+            double *dst = sm.w[s];
+            unsigned char *sb = reinterpret_cast<unsigned char *>(dst);
+            if (p.use_tma) {
+                if (lane == 0) {
+                    f_mbar_expect_tx(&sm.full_tma[s], TILE * 8);
+                    f_tma_load_2d(dst, &wmap, 0, t * NT, &sm.full_tma[s]);
+                }
+                f_mbar_wait(&sm.full_tma[s], use & 1);
+                // rows beyond n/16 arrive zero-filled; the last n % 16 weights are fetched by hand
+                const i64 R = p.n >> 4;
+                const int rem = (int)(p.n & 15);
+                if (rem && (R / NT) == t && lane < rem) {
+                    const int r = (int)(R - (i64)t * NT);
+                    *reinterpret_cast<double *>(sb + f_swz(r, lane >> 1) + (lane & 1) * 8) = p.w[R * 16 + lane];
+                }
+            } else {
+                const i64 j0 = (i64)t * TILE;
+                for (int i = lane; i < TILE; i += 32) {
+                    const i64 j = j0 + i;
+                    const double v = (j < p.n) ? p.w[j] : 0.0;
+                    *reinterpret_cast<double *>(sb + f_swz(i >> 4, (i >> 1) & 7) + (i & 1) * 8) = v;
+                }
+            }
+            __syncwarp();
+            // tile sum (any order: it is only the approximate prefix) and input validation
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            unsigned mx = 0;
+            const double2 *src = reinterpret_cast<const double2 *>(dst);
+#pragma unroll 8
+            for (int i = 0; i < TILE / 64; i += 2) {
+                const double2 u0 = src[i * 32 + lane], u1 = src[(i + 1) * 32 + lane];
+                a0 += u0.x; a1 += u0.y; a2 += u1.x; a3 += u1.y;
+                mx = max(mx, max(max((unsigned)__double2hiint(u0.x), (unsigned)__double2hiint(u0.y)),
+                                 max((unsigned)__double2hiint(u1.x), (unsigned)__double2hiint(u1.y))));
+            }
+            int bad = 0;
+            if (mx >= 0x7FF00000u) {                       // negative, inf or nan somewhere (or a harmless -0.0)
+                for (int i = 0; i < TILE / 64; i++) {
+                    const double2 u0 = src[i * 32 + lane];
+                    if (!(u0.x >= 0.0) || !(u0.y >= 0.0) || isinf(u0.x) || isinf(u0.y)) bad = 1;
+                }
+            }
+            bad = __any_sync(FULL, bad);
+            double tot = (a0 + a1) + (a2 + a3);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
+            if (p.div) tot = tot / divisor;
+            if (bad) { tot = 0.0; if (lane == 0) p.hdr->fallback = 1; }
+            if (lane == 0) f_st(p.st1 + t + 1, ((u64)__double_as_longlong(tot) & ~3ull) | ST1_AGG);
+            const double tp = f_lookback_sum(p, t, lane);
+            if (lane == 0) {
+                f_st(p.st1 + t + 1, ((u64)__double_as_longlong(tp + tot) & ~3ull) | ST1_INCL);
+                sm.info[s].t = t; sm.info[s].bad = bad; sm.info[s].tp = tp; sm.info[s].tot = tot;
+                f_mbar_arrive(&sm.ready[s]);
+            }
+        }
+        return;
+    }
+
+    // ================================================================ consumer warps
+    const i64 out_begin = p.hdr->out_begin;
+    const double Nd = (double)p.ng;
+    for (int q = 0;; q++) {
+        const int s = q % F_STAGES, use = q / F_STAGES;
+        f_mbar_wait(&sm.ready[s], use & 1);
+        const int t = sm.info[s].t;
+        if (t < 0) break;
+        if (p.use_tma) f_mbar_wait(&sm.full_tma[s], use & 1);       // already complete: acquires the TMA writes directly
+        const double tp = sm.info[s].tp, tot = sm.info[s].tot;
+        const int tile_bad = sm.info[s].bad;
+        unsigned char *sb = reinterpret_cast<unsigned char *>(sm.w[s]);
+        const i64 jthread = (i64)t * TILE + (i64)tid * F_IPT;       // first particle of this thread (local numbering)
+
+        double w[F_IPT];
+#pragma unroll
+        for (int c = 0; c < F_IPT / 2; c++) {
+            const double2 v = *reinterpret_cast<const double2 *>(sb + f_swz(tid, c));
+            w[2 * c] = v.x; w[2 * c + 1] = v.y;
+        }
+        if (p.div) {
+            // fused normalisation: w / S, the same IEEE division NumPy's `w / w.sum()` performs
+#pragma unroll
+            for (int k = 0; k < F_IPT; k++) w[k] = __ddiv_rn(w[k], divisor);
+#pragma unroll
+            for (int c = 0; c < F_IPT / 2; c++)
+                *reinterpret_cast<double2 *>(sb + f_swz(tid, c)) = make_double2(w[2 * c], w[2 * c + 1]);
+            f_fence_proxy_async();        // generic-proxy writes to a stage the TMA engine will refill
+            if (p.wnorm_out) {
+                double *o = p.wnorm_out + jthread;
+                if (jthread + F_IPT <= p.n && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+#pragma unroll
+                    for (int k = 0; k < F_IPT; k += 2) *reinterpret_cast<double2 *>(o + k) = make_double2(w[k], w[k + 1]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < F_IPT; k++) if (jthread + k < p.n) o[k] = w[k];
+                }
+            }
+        }
+
+        // ---- fast classification: the whole tile deep inside ONE binade, no ties -> plain int64 sums
+        int e0;
+        const bool ca = clean_add(tp, tp + tot, p.eb, &e0);
+        const bool tile_clean = !tile_bad && (ca || tot == 0.0);
+        const i64 base = (i64)e0 << 52;
+        const double B0 = __longlong_as_double(base), B1 = __longlong_as_double(base + 1);
+        i64 pre[F_IPT];
+        i64 acc = 0;
+        unsigned tie = 0;
+#pragma unroll
+        for (int k = 0; k < F_IPT; k++) {
+            const i64 b0 = __double_as_longlong(__dadd_rn(B0, w[k]));
+            const i64 b1 = __double_as_longlong(__dadd_rn(B1, w[k]));
+            tie |= ((unsigned)b0 + 1u) ^ (unsigned)b1;     // d1 != d0 only for an exact tie (round-half-even)
+            acc += b0 - base;
+            pre[k] = acc;
+        }
+        const i64 inc = warp_incl_scan_i64(acc, lane);
+        if (lane == 31) sm.warp_tot[wid] = inc;
+        const int fast = f_bar_and<NT>(tile_clean && tie == 0);
+
+        i64 cb[F_IPT];
+        i64 thread_start;                                   // exact state before this thread's first particle
+        int good;
+        if (tile_bad) {
+            // invalid weights: the sequential kernel will produce the result; keep the chain moving
+            if (wid == 0) {
+                const i64 S_in = f_lookback_state(p, t, lane);
+                if (lane == 0) f_st(p.st2 + t + 1, ST2_INCL | (u64)S_in);
+            }
+            __syncwarp();
+            if (lane == 0) { f_fence_proxy_async(); f_mbar_arrive(&sm.empty[s]); }
+            continue;
+        }
+        if (fast) {
+            // the stage is free once every consumer has its weights in registers (the barrier above
+            // depends on all of them)
+            if (lane == 0) f_mbar_arrive(&sm.empty[s]);
+            i64 ex = inc - acc, D = 0;
+#pragma unroll
+            for (int i = 0; i < NW; i++) { const i64 v = sm.warp_tot[i]; if (i < wid) ex += v; D += v; }
+            if (wid == 0) {
+                if (lane == 0) f_st(p.st2 + t + 1, st2_pack_agg(D, 0));
+                const i64 S_in = f_lookback_state(p, t, lane);
+                if (lane == 0) {
+                    const i64 S_out = S_in + D;
+                    const int ok = (tot == 0.0) || ((int)(S_in >> 52) == e0 && (int)(S_out >> 52) == e0);
+                    f_st(p.st2 + t + 1, ST2_INCL | (u64)S_out);
+                    f_finish_tile<NW, MODE>(p, sm, t, S_in, S_out, ok);
+                }
+            }
+            f_bar<NT>();
+            good = sm.bc_ok;
+            thread_start = sm.bc_S_in + ex;
+#pragma unroll
+            for (int k = 0; k < F_IPT; k++) cb[k] = thread_start + pre[k];
+        } else {
+            good = f_slow_tile<NW, MODE>(p, sm, s, t);
+#pragma unroll
+            for (int c = 0; c < F_IPT / 2; c++) {
+                const longlong2 v = *reinterpret_cast<const longlong2 *>(sb + f_swz(tid, c));
+                cb[2 * c] = v.x; cb[2 * c + 1] = v.y;
+            }
+            // state before the thread's first particle = the previous particle's c (the tile's S_in for thread 0)
+            {
+                const longlong2 v = *reinterpret_cast<const longlong2 *>(sb + f_swz(tid > 0 ? tid - 1 : 0, 7));
+                thread_start = tid > 0 ? v.y : sm.bc_S_in;
+            }
+            __syncwarp();
+            if (lane == 0) { f_fence_proxy_async(); f_mbar_arrive(&sm.empty[s]); }
+        }
+        const i64 tile_lo = sm.bc_lo;
+        const i64 tile_cnt = sm.bc_cnt;
+        if (!good) { f_bar<NT>(); continue; }
+        if (MODE == F_CUMSUM) { f_store_cumsum(p, jthread, cb); f_bar<NT>(); continue; }
+
+        // ---- output range end of every particle, relative to tile_lo: hv[k] = #{positions < c_k} - tile_lo
+        int hv[F_IPT], hv_prev;
+        if (MODE == F_SYS) {
+            // branch-free: floor(c N - u) + 1 away from integers; the rare near-integer cases are redone exactly
+            const double u = p.u, half_m = 0.5 - p.tau;
+            const int n_m1 = (int)p.ng - 1, lo_m1 = (int)tile_lo - 1;
+            unsigned slow = 0;
+            auto count1 = [&](i64 cbits, unsigned bit) -> int {
+                const double v = fma(__longlong_as_double(cbits), Nd, -u);    // >= -u > -1
+                const double fl = floor(v);
+                const double fr = v - fl;                                     // exact, in [0, 1)
+                if (!(fabs(fr - 0.5) < half_m)) slow |= bit;                  // within tau of an integer
+                return min(__double2int_rz(fl), n_m1) - lo_m1;                // floor(v) + 1 - tile_lo
+            };
+#pragma unroll
+            for (int k = 0; k < F_IPT; k++) hv[k] = count1(cb[k], 1u << k);
+            hv_prev = count1(thread_start, 1u << F_IPT);
+            if (slow) {
+#pragma unroll
+                for (int k = 0; k < F_IPT; k++)
+                    if (slow & (1u << k)) hv[k] = (int)(f_count_below<MODE>(p, __longlong_as_double(cb[k])) - tile_lo);
+                if (slow & (1u << F_IPT)) hv_prev = (int)(f_count_below<MODE>(p, __longlong_as_double(thread_start)) - tile_lo);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < F_IPT; k++) hv[k] = (int)(f_count_below<MODE>(p, __longlong_as_double(cb[k])) - tile_lo);
+            hv_prev = (int)(f_count_below<MODE>(p, __longlong_as_double(thread_start)) - tile_lo);
+        }
+
+        // ---- expansion
+        const int base_j = (int)(p.j0 + (i64)t * TILE) - 1;                   // markers are local index + 1
+        const i64 rel_lo = tile_lo - out_begin;
+        const int mis = (int)(((reinterpret_cast<uintptr_t>(p.idx) >> 2) + (uintptr_t)rel_lo) & 3);
+        if (tile_cnt + 3 <= WIN && rel_lo >= 0 && rel_lo + tile_cnt <= p.cap) {
+            // one window; slot 0 is 16-byte aligned in the index array, the tile's first output is slot `mis`
+            const int total = (int)tile_cnt + mis;
+            int l = hv_prev + mis;
+#pragma unroll
+            for (int k = 0; k < F_IPT; k++) {
+                const int h = hv[k] + mis;
+                if (h > l) sm.win[l] = tid * F_IPT + k + 1;
+                l = h;
+            }
+            f_bar<NT>();
+            int m[F_SPT];
+            f_window_scan<NW>(sm, tid, lane, wid, m);
+            const int s0 = tid * F_SPT;
+            int *dst = p.idx + (rel_lo - mis) + s0;
+            if (s0 >= mis && s0 + F_SPT <= total) {
+#pragma unroll
+                for (int i = 0; i < F_SPT; i += 4)
+                    *reinterpret_cast<int4 *>(dst + i) = make_int4(base_j + m[i], base_j + m[i + 1], base_j + m[i + 2], base_j + m[i + 3]);
+            } else if (s0 < total) {
+#pragma unroll
+                for (int i = 0; i < F_SPT; i++)
+                    if (s0 + i >= mis && s0 + i < total) dst[i] = base_j + m[i];
+            }
+            continue;      // the next tile's first barrier separates these window reads from its marker writes
+        }
+        // general expansion: several windows, runs of BIGRUN or more copies go to the fill kernel
+        if (tid == 0) atomicAdd(&p.hdr->n_general, 1);
+        const int cnt = (int)tile_cnt;
+        int cs = 0;
+        while (cs < cnt) {
+            if (tid == 0) sm.bc_skip = -1;
+            f_bar<NT>();
+            {
+                int l = hv_prev;
+#pragma unroll
+                for (int k = 0; k < F_IPT; k++) {
+                    const int h = hv[k];
+                    if (l <= cs && cs < h && h - cs >= BIGRUN) {
+                        sm.bc_skip = h;
+                        const int r = atomicAdd(&p.hdr->n_runs, 1);
+                        if (r < p.max_runs) p.runs[r] = Run{tile_lo + cs, tile_lo + h, base_j + tid * F_IPT + k + 1, 0};
+                        else p.hdr->fallback = 1;
+                    }
+                    l = h;
+                }
+            }
+            f_bar<NT>();
+            const int skip = sm.bc_skip;
+            if (skip >= 0) { cs = skip; f_bar<NT>(); continue; }
+            const int ce = (cnt - cs > WIN) ? cs + WIN : cnt;
+            {
+                int l = hv_prev;
+#pragma unroll
+                for (int k = 0; k < F_IPT; k++) {
+                    const int h = hv[k];
+                    const int a0 = max(l, cs);
+                    if (h > a0 && a0 < ce) sm.win[a0 - cs] = tid * F_IPT + k + 1;
+                    l = h;
+                }
+            }
+            f_bar<NT>();
+            int m[F_SPT];
+            f_window_scan<NW>(sm, tid, lane, wid, m);
+#pragma unroll
+            for (int i = 0; i < F_SPT; i++) {
+                const int sl = tid * F_SPT + i;
+                if (sl < ce - cs) f_put_index(p, out_begin, tile_lo + cs + sl, base_j + m[i]);
+            }
+            f_bar<NT>();
+            cs = ce;
+        }
+        f_bar<NT>();
+    }
+}
+
+// ------------------------------------------------------------------ init / epilogue kernels
+__global__ void __launch_bounds__(256) k_finit(FParams p)
+{
+    const i64 nst = (i64)p.T + 1;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x + 1; i < nst; i += (i64)gridDim.x * blockDim.x) { p.st1[i] = 0; p.st2[i] = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        FHeader h;
+        memset(&h, 0, sizeof(h));
+        const double ca = p.carry_approx ? *p.carry_approx : 0.0;
+        const double ce = p.carry_exact ? *p.carry_exact : 0.0;
+        const double Ngd = (double)p.ng;
+        h.out_begin = p.cumsum_out ? 0 : (p.U ? count_below_str(ce, p.U, p.ng, Ngd) : count_below_sys(ce, p.u, p.ng, Ngd, p.tau));
+        *p.hdr = h;
+        p.st1[0] = ((u64)__double_as_longlong(ca) & ~3ull) | ST1_INCL;
+        p.st2[0] = ST2_INCL | (u64)__double_as_longlong(ce);
+    }
+}
+
+// long runs (one particle copied >= BIGRUN times), then — only if something failed — the literal
+// sequential transcription of resampling.py:141-149, and the info block
+__global__ void __launch_bounds__(256) k_fepilogue(FParams p)
+{
+    FHeader *hdr = p.hdr;
+    if (!hdr->fallback && p.idx) {
+        int nr = hdr->n_runs;
+        if (nr > p.max_runs) nr = p.max_runs;
+        const i64 ob = hdr->out_begin;
+        for (int r = 0; r < nr; r++) {
+            const Run run = p.runs[r];
+            for (i64 i = run.lo + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < run.hi; i += (i64)gridDim.x * blockDim.x) {
+                const i64 rel = i - ob;
+                if (rel >= 0 && rel < p.cap) p.idx[rel] = run.j;
+                else hdr->cap_overflow = 1;
+            }
+        }
+    }
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    auto write_info = [&](int overflow, int fb) {
+        if (p.info) {
+            p.info[0] = overflow; p.info[1] = fb; p.info[2] = hdr->n_unclean; p.info[3] = hdr->n_runs;
+            p.info[4] = hdr->chain_bad | (hdr->timeout << 4); p.info[5] = hdr->n_seq; p.info[6] = hdr->cap_overflow; p.info[7] = hdr->n_slow;
+        }
+    };
+    if (!hdr->fallback) { write_info(hdr->overflow, 0); return; }
+    const double S = p.div ? *p.div : 1.0;
+    auto W = [&](i64 q) { return p.div ? __ddiv_rn(p.w[q], S) : p.w[q]; };
+    if (p.div && p.wnorm_out) for (i64 q = 0; q < p.n; q++) p.wnorm_out[q] = W(q);
+    if (p.cumsum_out) {                          // cumsum mode: np.cumsum, one add at a time
+        double c = 0.0;
+        for (i64 q = 0; q < p.n; q++) { c = (q == 0) ? W(0) : __dadd_rn(c, W(q)); p.cumsum_out[q] = c; }
+        if (p.cumsum_last) *p.cumsum_last = c;
+        if (p.last_one) p.cumsum_out[p.n - 1] = 1.0;
+        write_info(0, 1);
+        return;
+    }
+    // resampling.py:141-149 — cumulative sum and two-pointer merge, one element at a time.  A shard
+    // starts from the exact running sum of the earlier shards and owns the positions from
+    // count_below(carry) up to count_below(its last cumulative sum).
+    const double Ngd = (double)p.ng;
+    const double carry = p.carry_exact ? *p.carry_exact : 0.0;
+    auto pos = [&](i64 i) { return p.U ? pos_str(i, p.U, Ngd) : pos_sys(i, p.u, Ngd); };
+    i64 lo = 0, hi = p.ng;                       // first i with pos_i >= carry (positions are non-decreasing)
+    while (lo < hi) {
+        const i64 mid = (lo + hi) >> 1;
+        if (pos(mid) < carry) lo = mid + 1; else hi = mid;
+    }
+    const i64 ob = lo;
+    hdr->out_begin = ob;
+    hdr->cap_overflow = 0;
+    i64 i = ob, j = 0;
+    double c = (carry == 0.0) ? W(0) : __dadd_rn(carry, W(0));
+    int overflow = 0;
+    while (i < p.ng) {
+        if (pos(i) < c) {
+            if (i - ob < p.cap) p.idx[i - ob] = (int)(p.j0 + j); else hdr->cap_overflow = 1;
+            i++;
+        } else {
+            j++;
+            if (j >= p.n) {
+                if (p.is_last) {
+                    overflow = (int)(p.ng - i);
+                    for (; i < p.ng; i++) { if (i - ob < p.cap) p.idx[i - ob] = (int)(p.ng - 1); else hdr->cap_overflow = 1; }
+                }
+                break;
+            }
+            c = __dadd_rn(c, W(j));
+        }
+    }
+    for (i64 q = j + 1; q < p.n; q++) c = __dadd_rn(c, W(q));
+    if (p.cumsum_last) *p.cumsum_last = c;
+    hdr->out_end = i;
+    if (p.out_range) { p.out_range[0] = ob; p.out_range[1] = i; }
+    write_info(overflow, 1);
+}
+
+// ------------------------------------------------------------------ host side
+namespace {
+
+typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                             const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                             CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn f_get_encode()
+{
+    static EncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeFn)ptr;
+    }
+    return fn;
+}
+
+// the weights as rows of 16 doubles (128 bytes); a tile is a box of `box_rows` rows
+bool f_make_map(CUtensorMap *m, const double *base, int64_t rows, int box_rows)
+{
+    EncodeFn enc = f_get_encode();
+    if (!enc || rows < 1) return false;
+    cuuint64_t gdim[2] = {16, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {128};
+    cuuint32_t box[2] = {16, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), gdim, gstride, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int f_env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+template <int NW, int MODE>
+int f_launch(const CUtensorMap &map, const FParams &p, cudaStream_t s)
+{
+    auto kern = k_fused<NW, MODE>;
+    const int smem = (int)sizeof(FSmem<NW>);
+    static bool configured[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    const int ctas_env = f_env_int("BKE_RS_CTAS", 0);
+    const int per_sm = ctas_env > 0 ? ctas_env : (NW == 8 ? 2 : 4);
+    int grid = sm_count() * per_sm;
+    if (grid > p.T) grid = p.T;
+    kern<<<grid, NW * 32 + 32, smem, s>>>(map, p);
+    return check_cuda(cudaGetLastError(), "k_fused launch");
+}
+
+}  // namespace
+
+size_t f_carve(int64_t n, unsigned char *base, FParams *p)
+{
+    // the smallest tile any variant uses decides the number of status words
+    const int64_t Tmax = (n + 4 * 32 * F_IPT - 1) / (4 * 32 * F_IPT);
+    size_t off = 0;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    auto take = [&](size_t bytes) { size_t o = off; off += al(bytes); return base ? base + o : nullptr; };
+    unsigned char *q;
+    q = take(sizeof(FHeader));               if (p) p->hdr = (FHeader *)q;
+    q = take(sizeof(u64) * (Tmax + 1));      if (p) p->st1 = (u64 *)q;
+    q = take(sizeof(u64) * (Tmax + 1));      if (p) p->st2 = (u64 *)q;
+    const int64_t max_runs = n / BIGRUN + 8;
+    q = take(sizeof(Run) * max_runs);        if (p) { p->runs = (Run *)q; p->max_runs = (int)max_runs; }
+    return off;
+}
+
+int f_run(const FRunArgs &a, cudaStream_t s)
+{
+    const i64 n = a.n;
+    if (n < 0 || a.ng < n || a.j0 < 0) { set_error("bad particle counts"); return BKE_ERR_BAD_ARG; }
+    if (n == 0) return BKE_OK;
+    if (a.ng >= ((i64)1 << 31)) { set_error("n must be < 2^31 (indexes are int32, resampling.py:141)"); return BKE_ERR_BAD_ARG; }
+    if (!a.w || !(a.idx || a.cumsum_out) || !a.workspace) { set_error("weights, indexes and workspace must be non-NULL"); return BKE_ERR_BAD_ARG; }
+    if (!a.U && !a.cumsum_out && !(a.u >= 0.0 && a.u < 1.0)) { set_error("u must be in [0, 1)"); return BKE_ERR_BAD_ARG; }
+    const size_t need = f_carve(n, nullptr, nullptr);
+    if (a.ws_bytes < need) { set_error("workspace too small: %zu < %zu", a.ws_bytes, need); return BKE_ERR_BAD_ARG; }
+    if (reinterpret_cast<uintptr_t>(a.workspace) & 255) { set_error("workspace must be 256-byte aligned"); return BKE_ERR_BAD_ARG; }
+    FParams p;
+    memset(&p, 0, sizeof(p));
+    f_carve(n, (unsigned char *)a.workspace, &p);
+    const int nw_env = f_env_int("BKE_RS_WARPS", 8);
+    const int NW = (nw_env == 4) ? 4 : 8;
+    const int tile = NW * 32 * F_IPT;
+    p.w = a.w; p.n = n; p.ng = a.ng; p.j0 = a.j0; p.cap = a.cap; p.is_last = a.is_last;
+    p.carry_approx = a.carry_approx; p.carry_exact = a.carry_exact; p.out_range = a.out_range;
+    p.u = a.u; p.U = a.U; p.idx = a.idx; p.info = a.info; p.cumsum_last = a.cumsum_last;
+    p.cumsum_out = a.cumsum_out; p.last_one = a.last_one; p.div = a.div; p.wnorm_out = a.wnorm_out;
+    p.T = (int)((n + tile - 1) / tile);
+    // |exact sequential sum - approximate sum| in ulps of the running sum: N adds of the reference,
+    // the tree sums inside a tile, the T sequential adds and the 2 flag bits per published word of
+    // the look-back (and the division of a normalised call); doubled, plus slack.
+    const i64 Tg = a.ng / tile + 2;
+    p.eb = 2 * (a.ng + 16 * Tg + 2 * tile) + (a.ng >> 4);
+    const double tau = ldexp((double)a.ng, -46);
+    p.tau = tau > 1e-6 ? tau : 1e-6;
+    // TMA path: 16-byte aligned base and at least one full row of 16 weights
+    static thread_local CUtensorMap map;
+    static thread_local const void *map_ptr = nullptr;
+    static thread_local i64 map_n = -1;
+    static thread_local int map_nw = 0;
+    const int tma_env = f_env_int("BKE_RS_TMA", 1);
+    p.use_tma = tma_env && (reinterpret_cast<uintptr_t>(a.w) & 15) == 0 && (n >> 4) >= 1 && f_get_encode() != nullptr;
+    if (p.use_tma && !(map_ptr == a.w && map_n == n && map_nw == NW)) {
+        if (!f_make_map(&map, a.w, n >> 4, NW * 32)) p.use_tma = 0;
+        else { map_ptr = a.w; map_n = n; map_nw = NW; }
+    }
+    if (!p.use_tma) memset(&map, 0, sizeof(map)), map_ptr = nullptr;
+    const int init_blocks = (int)((p.T + 1 + 255) / 256) < 64 ? (int)((p.T + 1 + 255) / 256) : 64;
+    k_finit<<<init_blocks, 256, 0, s>>>(p);
+    int rc;
+    const int mode = a.cumsum_out ? F_CUMSUM : (a.U ? F_STRAT : F_SYS);
+#define BKE_F_DISPATCH(NWV)                                                    \
+    (mode == F_CUMSUM ? f_launch<NWV, F_CUMSUM>(map, p, s)                     \
+     : mode == F_STRAT ? f_launch<NWV, F_STRAT>(map, p, s)                     \
+                       : f_launch<NWV, F_SYS>(map, p, s))
+    rc = (NW == 4) ? BKE_F_DISPATCH(4) : BKE_F_DISPATCH(8);
+#undef BKE_F_DISPATCH
+    if (rc != BKE_OK) return rc;
+    k_fepilogue<<<sm_count() * 4, 256, 0, s>>>(p);
+    return check_cuda(cudaGetLastError(), "resample launch");
+}
+
+}  // namespace rs
+}  // namespace bke

@@ -65,6 +65,21 @@ class ResamplePlan(object):
                 self._info.data_ptr(), self.cumsum_last.data_ptr(), stream_ptr(self.device)))
         return out
 
+    def normalized(self, weights, u=None, uniforms=None, out=None, weights_out=None):
+        """Fused normalise + resample: ``systematic_resample(weights / S)`` (``stratified_resample`` when
+        ``uniforms`` is given) with ``S`` the engine's sum of the weights.  Returns (indexes, S tensor)."""
+        self._check_w(weights)
+        out = self.indexes if out is None else out
+        total = torch.zeros(1, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.bke_resample_normalized(
+                self.n, weights.data_ptr(), float(u if u is not None else 0.0),
+                uniforms.data_ptr() if uniforms is not None else None, out.data_ptr(),
+                weights_out.data_ptr() if weights_out is not None else None, total.data_ptr(),
+                self._ws_ptr, self.ws_bytes, self._info.data_ptr(), self.cumsum_last.data_ptr(),
+                stream_ptr(self.device)))
+        return out, total
+
     def cumsum(self, weights, out=None, last_one=False):
         """``np.cumsum(weights)`` bit for bit (sequential fp64 order), on the device."""
         self._check_w(weights)

@@ -197,6 +197,18 @@ int bke_stratified_resample(int64_t n, const double *weights, const double *unif
                             int32_t *indexes, void *workspace, size_t workspace_bytes,
                             int32_t *info, double *cumsum_last, void *stream);
 
+/* Fused normalise + resample (north_star: "single fused weight-normalise + inclusive-scan +
+ * inverse-CDF kernel"): S = sum(weights) (tree order, written to sum_out), then ONE pass over the
+ * weights that forms w / S (IEEE division, what NumPy's `w / w.sum()` computes given S), its exact
+ * sequential cumulative sum and the indexes — i.e. systematic_resample(weights / S)
+ * (resampling.py:117-150; stratified when `uniforms` != NULL, :80-114).  weights_out (optional)
+ * receives the normalised weights.  The un-normalised weights are read twice (sum, resample);
+ * nothing else is written. */
+int bke_resample_normalized(int64_t n, const double *weights, double u, const double *uniforms,
+                            int32_t *indexes, double *weights_out, double *sum_out,
+                            void *workspace, size_t workspace_bytes,
+                            int32_t *info, double *cumsum_last, void *stream);
+
 /* One contiguous SHARD of a particle set that is spread over several GPUs (rank r holds particles
  * [j_offset, j_offset + n_local) of n_global).  The result equals the single-array call bit for
  * bit: shard r produces exactly the indexes of the global output positions
