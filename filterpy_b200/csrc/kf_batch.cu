@@ -129,9 +129,12 @@ int launch_host_loop(const bke_kf_batch_args &a, cudaStream_t s)
     const int64_t N = k0.n_filters, n = k0.dim_x, m = k0.dim_z;
     const bool uf = k0.flags & BKE_UPDATE_FIRST;
     const char *xin = (const char *)k0.x, *Pin = (const char *)k0.P;
+    // status is sticky over the epochs (like the in-kernel time loop): zeroed once, then every
+    // per-epoch launch writes it only where the epoch failed
+    if (k0.status && check_cuda(cudaMemsetAsync(k0.status, 0, sizeof(int32_t) * (size_t)N, s), "memset status")) return BKE_ERR_CUDA;
     for (int64_t t = 0; t < a.n_steps; t++) {
         bke_kf_args k = k0;
-        k.flags = BKE_DO_PREDICT | BKE_DO_UPDATE | (uf ? BKE_UPDATE_FIRST : 0);
+        k.flags = BKE_DO_PREDICT | BKE_DO_UPDATE | (uf ? BKE_UPDATE_FIRST : 0) | BKE_STATUS_STICKY;
         k.x = xin; k.P = Pin;
         k.z = (const char *)a.zs + (size_t)t * N * m * es;
         k.z_valid = a.zs_valid ? a.zs_valid + t * N : nullptr;
@@ -148,7 +151,7 @@ int launch_host_loop(const bke_kf_batch_args &a, cudaStream_t s)
             xin = post_x; Pin = post_P;
         } else {
             // update -> means[t]; predict -> means_p[t] which also feeds epoch t+1
-            bke_kf_args ku = k; ku.flags = BKE_DO_UPDATE; ku.x_out = post_x; ku.P_out = post_P; ku.x_prior = ku.P_prior = nullptr;
+            bke_kf_args ku = k; ku.flags = BKE_DO_UPDATE | BKE_STATUS_STICKY; ku.x_out = post_x; ku.P_out = post_P; ku.x_prior = ku.P_prior = nullptr;
             rc = launch_kf_any(ku, s);
             if (rc) return rc;
             bke_kf_args kp = k; kp.flags = BKE_DO_PREDICT; kp.x = post_x; kp.P = post_P;

@@ -41,6 +41,21 @@ __device__ __forceinline__ void ldv(T *dst, const T *src)
         for (int i = 0; i < CNT; i++) dst[i] = __ldg(src + i);
     }
 }
+// plain (coherent) loads: for x and P, which alias x_out / P_out in the in-place call — ld.global.nc
+// requires memory that nobody writes during the kernel
+template <typename T, int CNT>
+__device__ __forceinline__ void ldv_rw(T *dst, const T *src)
+{
+    constexpr int VEC = 16 / sizeof(T);
+    if constexpr (CNT % VEC == 0) {
+        using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+#pragma unroll
+        for (int i = 0; i < CNT / VEC; i++) *reinterpret_cast<V *>(dst + i * VEC) = reinterpret_cast<const V *>(src)[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < CNT; i++) dst[i] = src[i];
+    }
+}
 template <typename T, int CNT>
 __device__ __forceinline__ void stv(T *dst, const T *src)
 {
@@ -64,8 +79,8 @@ __global__ void __launch_bounds__(128) kf_direct_kernel(DirP<T> p)
     if (f >= p.N) return;
     const bool do_p = p.flags & BKE_DO_PREDICT, do_u = p.flags & BKE_DO_UPDATE;
     T x[N], P[N][N];
-    ldv<T, N>(x, p.x + f * N);
-    ldv<T, N * N>(&P[0][0], p.P + f * N * N);
+    ldv_rw<T, N>(x, p.x + f * N);
+    ldv_rw<T, N * N>(&P[0][0], p.P + f * N * N);
     int st = BKE_STATUS_OK;
     if (do_p) {
         T F[N][N], Q[N][N];
@@ -108,7 +123,7 @@ __global__ void __launch_bounds__(128) kf_direct_kernel(DirP<T> p)
     }
     stv<T, N>(p.x_out + f * N, x);
     stv<T, N * N>(p.P_out + f * N * N, &P[0][0]);
-    if (p.status) p.status[f] = st;
+    if (p.status && (st != BKE_STATUS_OK || !(p.flags & BKE_STATUS_STICKY))) p.status[f] = st;
 }
 
 // 16-byte vector accesses are used for the arrays whose row is a multiple of 16 bytes: their base

@@ -147,6 +147,7 @@ struct FastP {
     const uint8_t *valid;
     float *x_prior, *P_prior, *K, *y, *S, *SI, *ll;
     int32_t *status;
+    int sticky;                       // BKE_STATUS_STICKY: write status only on failure
 };
 
 // MODE: 3 = predict+update, 1 = predict only, 2 = update only
@@ -383,7 +384,7 @@ kf42_f32_kernel(const __grid_constant__ Maps maps, const FastP<4, 2> p)
                 for (int i = 0; i < N; i++)
                     *reinterpret_cast<float4 *>(p.P_out + f * N * N + i * N) = make_float4(P[i][0], P[i][1], P[i][2], P[i][3]);
             }
-            if (EXTRAS && p.status) p.status[f] = st;
+            if (EXTRAS && p.status && (st != BKE_STATUS_OK || !p.sticky)) p.status[f] = st;
         }
     }
 }
@@ -543,6 +544,7 @@ int launch_kf_fast(const bke_kf_args &a, cudaStream_t s)
     p.valid = a.z_valid;
     p.x_prior = (float *)a.x_prior; p.P_prior = (float *)a.P_prior; p.K = (float *)a.K; p.y = (float *)a.y;
     p.S = (float *)a.S; p.SI = (float *)a.SI; p.ll = (float *)a.log_likelihood; p.status = a.status;
+    p.sticky = (a.flags & BKE_STATUS_STICKY) ? 1 : 0;
     // host copies of the shared models (optional): carried in the launch parameters
     static const int hostm_env = env_int("BKE_KF_HOST_MODELS", 1);
     const bool host_models = hostm_env && all_shared && a.F_host && a.Q_host && a.H_host && a.R_host;

@@ -29,6 +29,7 @@ struct KfP {
     const uint8_t *valid;
     T *x_prior, *P_prior, *K, *y, *S, *SI, *ll;
     int32_t *status;
+    int sticky;                       // BKE_STATUS_STICKY: write status only on failure
 };
 
 // C[r,c] = A[r,k] * B (B is [k,c], or [c,k] when TB), result handed to epi(e, i, j, value)
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(128) kf_generic_kernel(KfP<T> p, int per_warp_
         __syncwarp();
         for (int i = lane; i < n; i += 32) p.x_out[f * n + i] = x[i];
         for (int e = lane; e < nn; e += 32) p.P_out[f * nn + e] = P[e];
-        if (p.status && lane == 0) p.status[f] = st;
+        if (p.status && lane == 0 && (st != BKE_STATUS_OK || !p.sticky)) p.status[f] = st;
         __syncwarp();
     }
 }
@@ -244,6 +245,7 @@ int launch_t(const bke_kf_args &a, cudaStream_t s)
     p.valid = a.z_valid;
     p.x_prior = (T *)a.x_prior; p.P_prior = (T *)a.P_prior; p.K = (T *)a.K; p.y = (T *)a.y;
     p.S = (T *)a.S; p.SI = (T *)a.SI; p.ll = (T *)a.log_likelihood; p.status = a.status;
+    p.sticky = (a.flags & BKE_STATUS_STICKY) ? 1 : 0;
 
     const int n = p.n, m = p.m;
     // layout must match the kernel: x, xp, P, F, T1, T2, H, PHT, K, R, S, SI, SA, y, col

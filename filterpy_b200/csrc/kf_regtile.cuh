@@ -51,9 +51,10 @@ __device__ __forceinline__ void reg_predict(T (&x)[N], T (&P)[N][N], const T (&F
     for (int i = 0; i < N; i++) x[i] = xn[i];
 }
 
-// In-register inverse of a small M x M matrix by Gauss-Jordan without pivoting (S is symmetric
-// positive definite whenever R is and P is PSD, so the pivots are positive).  Returns false on a
-// zero pivot.  logdet = log det S.
+// In-register inverse of a small M x M matrix: closed form for M <= 2, Gauss-Jordan with partial
+// pivoting for M >= 3 (an indefinite but non-singular S — numerical drift of P, a user R that is not
+// PD — inverts exactly where np.linalg.inv does).  Returns false on a zero pivot = singular S.
+// logdet = log |det S|.
 template <typename T, int M>
 __device__ __forceinline__ bool reg_inverse(const T (&S)[M][M], T (&SI)[M][M], T &logdet)
 {
@@ -78,6 +79,22 @@ __device__ __forceinline__ bool reg_inverse(const T (&S)[M][M], T (&SI)[M][M], T
             for (int j = 0; j < M; j++) { A[i][j] = S[i][j]; SI[i][j] = (i == j) ? T(1) : T(0); }
 #pragma unroll
         for (int c = 0; c < M; c++) {
+            // partial pivoting, as np.linalg.inv (LU, kalman_filter.py:541): the largest |entry| of
+            // column c at or below the diagonal is bubbled into row c with predicated row swaps of
+            // [A | SI] (row operations on both sides leave SI = S^-1; |det| is unchanged)
+            T best = fabs(A[c][c]);
+#pragma unroll
+            for (int r = c + 1; r < M; r++) {
+                const T cand = fabs(A[r][c]);
+                const bool sw = cand > best;
+                best = sw ? cand : best;
+#pragma unroll
+                for (int j = 0; j < M; j++) {
+                    const T a0 = A[c][j], a1 = A[r][j], s0 = SI[c][j], s1 = SI[r][j];
+                    A[c][j] = sw ? a1 : a0; A[r][j] = sw ? a0 : a1;
+                    SI[c][j] = sw ? s1 : s0; SI[r][j] = sw ? s0 : s1;
+                }
+            }
             T piv = A[c][c];
             ok = ok && (piv != T(0));
             ld += log(fabs(piv));

@@ -68,6 +68,7 @@ struct RbP {
     T *x_out, *P_out;
     const uint8_t *valid;
     int32_t *status;
+    int sticky;                       // BKE_STATUS_STICKY: write status only on failure
     T *x_prior, *P_prior, *K, *y, *S, *SI, *ll;     // optional outputs (NULL = not wanted)
 };
 
@@ -466,7 +467,7 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
 #pragma unroll
                 for (int j = 0; j < N; j++) oP[(r0 + i) * N + j] = A[i][j];
             }
-            if (p.status && rb == 0) p.status[f] = st;
+            if (p.status && rb == 0 && (st != BKE_STATUS_OK || !p.sticky)) p.status[f] = st;
         }
         fence_proxy_async();      // publishes the staging buffer to the async proxy AND completes every earlier LDS of the stage
         __syncwarp();
@@ -496,7 +497,7 @@ int launch_rb(const bke_kf_args &a, cudaStream_t s)
         p.N = Nmain; p.alpha_sq = (T)a.alpha_sq;
         p.x = (const T *)a.x; p.P = (const T *)a.P; p.F = (const T *)a.F; p.Q = (const T *)a.Q;
         p.H = (const T *)a.H; p.R = (const T *)a.R; p.z = (const T *)a.z;
-        p.x_out = (T *)a.x_out; p.P_out = (T *)a.P_out; p.valid = a.z_valid; p.status = a.status;
+        p.x_out = (T *)a.x_out; p.P_out = (T *)a.P_out; p.valid = a.z_valid; p.status = a.status; p.sticky = (a.flags & BKE_STATUS_STICKY) ? 1 : 0;
         p.x_prior = (T *)a.x_prior; p.P_prior = (T *)a.P_prior; p.K = (T *)a.K; p.y = (T *)a.y;
         p.S = (T *)a.S; p.SI = (T *)a.SI; p.ll = (T *)a.log_likelihood;
         const bool extras = a.x_prior || a.P_prior || a.K || a.y || a.S || a.SI || a.log_likelihood;

@@ -101,101 +101,150 @@ __device__ __forceinline__ void f_st(u64 *p, u64 v)
 //        bit 62 = AGGREGATE: bits 0..59 = d0 of the tile's parity map, bits 60..61 = t + 1
 constexpr u64 ST1_AGG = 1, ST1_INCL = 2;
 constexpr u64 ST2_INCL = 1ull << 63, ST2_AGG = 1ull << 62;
-constexpr int SPIN_LIMIT = 1 << 20;
+constexpr int SPIN_LIMIT = 1 << 22;
 
 __device__ __forceinline__ u64 st2_pack_agg(i64 d, int t) { return ST2_AGG | ((u64)(t + 1) << 60) | ((u64)d & ((1ull << 60) - 1)); }
 
-// one status word, polled until it is published (bounded: a timeout flags the sequential fallback)
-__device__ __forceinline__ u64 f_poll(const u64 *p, u64 mask, FHeader *hdr, u64 dflt)
+// Look-back windows: every round a warp fetches up to 32 * LBK_MAX status words at once (ONE L2 round
+// trip), walks them in groups of 32 from the nearest predecessor outwards and stops at the nearest
+// INCLUSIVE word.  All tiles of a persistent grid start together, so a tile is typically a few
+// hundred tiles ahead of the inclusive frontier: the width of the window, not the number of
+// resident CTAs, sets how many round trips a look-back costs.
+constexpr int LBK_MAX = 8;
+
+// a blocked round (an unpublished word in front of the nearest inclusive one): back off, and give up
+// after SPIN_LIMIT rounds or once any look-back has given up (the result then comes from the fallback)
+__device__ __forceinline__ bool f_blocked(FHeader *hdr, int &spins, int sleep_ns)
 {
-    u64 v = f_ld(p);
-    if (v & mask) return v;
-    for (int spins = 0; spins < SPIN_LIMIT; spins++) {
-        __nanosleep(32);
-        v = f_ld(p);
-        if (v & mask) return v;
-        // once any look-back has given up, nobody waits any longer (the result comes from the fallback)
-        if ((spins & 1023) == 1023 && *reinterpret_cast<volatile int *>(&hdr->timeout)) return dflt;
-    }
-    hdr->timeout = 1; hdr->fallback = 1;
-    return dflt;
+    if (sleep_ns > 0) __nanosleep(sleep_ns);
+    spins++;
+    if ((spins & 1023) == 0 && *reinterpret_cast<volatile int *>(&hdr->timeout)) return true;
+    if (spins >= SPIN_LIMIT) { hdr->timeout = 1; hdr->fallback = 1; return true; }
+    return false;
 }
 
 // stage 1: approximate sum of everything before tile t (all 32 lanes of the producer warp)
 __device__ __forceinline__ double f_lookback_sum(const FParams &p, int t, int lane)
 {
-    double run = 0.0;
-    int idx = t - lane;                                    // st1 index of tile t-1-lane
-    for (;;) {
-        u64 v = ST1_INCL;                                  // beyond the carry: 0.0, inclusive
-        if (idx >= 0) v = f_poll(p.st1 + idx, 3, p.hdr, ST1_INCL);
-        const unsigned incl = __ballot_sync(FULL, (v & 3) == ST1_INCL);
-        const int first = incl ? __ffs(incl) - 1 : 31;
-        double x = (lane <= first) ? __longlong_as_double((i64)(v & ~3ull)) : 0.0;
+    double part = 0.0;                                     // this lane's share; reduced once at the end
+    int idx = t - lane;                                    // st1 index of tile t-1-lane (group 0 of the round)
+    int spins = 0;
+    bool done = false;
+    while (!done) {
+        u64 v[LBK_MAX];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
-        run += x;
-        if (incl) break;
-        idx -= 32;
-    }
-    return run;
-}
-
-// stage 2: exact state before tile t (all 32 lanes of consumer warp 0).  The aggregates between
-// the nearest inclusive predecessor and this tile are composed in tile order; with tie-free maps
-// (t = 0, the normal case) that is a plain int64 sum.
-__device__ __forceinline__ i64 f_lookback_state(const FParams &p, int t, int lane)
-{
-    i64 acc_d = 0; int acc_t = 0;                          // composite of the aggregates seen so far (applied LAST)
-    int idx = t - lane;
-    for (;;) {
-        u64 v = ST2_INCL;
-        if (idx >= 0) v = f_poll(p.st2 + idx, ST2_INCL | ST2_AGG, p.hdr, ST2_INCL);
-        const unsigned incl = __ballot_sync(FULL, (v & ST2_INCL) != 0);
-        const int first = incl ? __ffs(incl) - 1 : 32;     // lanes < first hold aggregates
-        i64 d = 0; int tt = 0;
-        if (lane < first) { d = (i64)(v & ((1ull << 60) - 1)); tt = (int)((v >> 60) & 3) - 1; }
-        const unsigned ties = __ballot_sync(FULL, tt != 0);
-        if (ties == 0) {
+        for (int j = 0; j < LBK_MAX; j++) {
+            const int i = idx - 32 * j;
+            v[j] = ST1_INCL;                               // beyond the carry: 0.0, inclusive
+            if (j < p.lbk && i >= 0) v[j] = f_ld(p.st1 + i);
+        }
+        bool blocked = false;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(FULL, d, o);
-        } else {
-            // ordered: lane L holds tile t-1-L, i.e. higher lanes are applied first
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const i64 pd = __shfl_down_sync(FULL, d, o);
-                const int pt = __shfl_down_sync(FULL, tt, o);
-                if (lane + o < 32) {
-                    const SM r = combine(SM{pd, pt, 0, K_ID}, SM{d, tt, 0, K_ID});
-                    d = r.d; tt = r.t;
+        for (int j = 0; j < LBK_MAX; j++) {
+            if (j < p.lbk && !done && !blocked) {
+                const unsigned incl = __ballot_sync(FULL, (v[j] & 3) == ST1_INCL);
+                const unsigned empty = __ballot_sync(FULL, (v[j] & 3) == 0);
+                const int first = incl ? __ffs(incl) - 1 : 32;
+                const unsigned closer = first >= 32 ? FULL : ((1u << first) - 1u);
+                if (empty & closer) blocked = true;
+                else {
+                    if (lane <= first) part += __longlong_as_double((i64)(v[j] & ~3ull));
+                    if (incl) done = true; else idx -= 32;
                 }
             }
-            d = __shfl_sync(FULL, d, 0); tt = __shfl_sync(FULL, tt, 0);
         }
-        {   // this window lies before everything accumulated so far
-            const SM r = combine(SM{d, ties ? tt : 0, 0, K_ID}, SM{acc_d, acc_t, 0, K_ID});
-            acc_d = r.d; acc_t = r.t;
-        }
-        if (incl) {
-            const i64 S = (i64)(__shfl_sync(FULL, v, first) & ~ST2_INCL);
-            return S + acc_d + ((S & 1) ? acc_t : 0);
-        }
-        idx -= 32;
+        if (blocked && f_blocked(p.hdr, spins, p.sleep_ns)) break;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+    return part;
+}
+
+// stage 2: exact state before tile t (all 32 lanes of a warp).  The aggregates between the nearest
+// inclusive predecessor and this tile are composed in tile order; with tie-free maps (t = 0, the
+// normal case) that is a plain int64 sum, kept per lane and reduced once.
+__device__ __forceinline__ i64 f_lookback_state(const FParams &p, int t, int lane)
+{
+    i64 part = 0;                                          // tie-free mode: this lane's share of the sum
+    bool general = false;                                  // a map with ties was met: ordered composition from here on
+    i64 acc_d = 0; int acc_t = 0;                          // general mode: composite of everything nearer (applied LAST)
+    i64 S = 0;
+    int idx = t - lane;
+    int spins = 0;
+    bool done = false;
+    while (!done) {
+        u64 v[LBK_MAX];
+#pragma unroll
+        for (int j = 0; j < LBK_MAX; j++) {
+            const int i = idx - 32 * j;
+            v[j] = ST2_INCL;
+            if (j < p.lbk && i >= 0) v[j] = f_ld(p.st2 + i);
+        }
+        bool blocked = false;
+#pragma unroll
+        for (int j = 0; j < LBK_MAX; j++) {
+            if (j < p.lbk && !done && !blocked) {
+                const unsigned incl = __ballot_sync(FULL, (v[j] & ST2_INCL) != 0);
+                const unsigned empty = __ballot_sync(FULL, (v[j] & (ST2_INCL | ST2_AGG)) == 0);
+                const int first = incl ? __ffs(incl) - 1 : 32;
+                const unsigned closer = first >= 32 ? FULL : ((1u << first) - 1u);
+                if (empty & closer) { blocked = true; continue; }
+                i64 d = 0; int tt = 0;
+                if (lane < first) { d = (i64)(v[j] & ((1ull << 60) - 1)); tt = (int)((v[j] >> 60) & 3) - 1; }
+                const unsigned ties = __ballot_sync(FULL, tt != 0);
+                if (!general && ties == 0) part += d;
+                else {
+                    if (!general) {
+                        general = true;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+                        acc_d = part; acc_t = 0;
+                    }
+                    // ordered: lane L holds tile (..)-L, i.e. higher lanes are applied first
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const i64 pd = __shfl_down_sync(FULL, d, o);
+                        const int pt = __shfl_down_sync(FULL, tt, o);
+                        if (lane + o < 32) {
+                            const SM r = combine(SM{pd, pt, 0, K_ID}, SM{d, tt, 0, K_ID});
+                            d = r.d; tt = r.t;
+                        }
+                    }
+                    d = __shfl_sync(FULL, d, 0); tt = __shfl_sync(FULL, tt, 0);
+                    const SM r = combine(SM{d, tt, 0, K_ID}, SM{acc_d, acc_t, 0, K_ID});   // this group lies before everything nearer
+                    acc_d = r.d; acc_t = r.t;
+                }
+                if (incl) { S = (i64)(__shfl_sync(FULL, v[j], first) & ~ST2_INCL); done = true; }
+                else idx -= 32;
+            }
+        }
+        if (blocked && f_blocked(p.hdr, spins, p.sleep_ns)) break;
+    }
+    if (!general) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+        acc_d = part; acc_t = 0;
+    }
+    return S + acc_d + ((S & 1) ? acc_t : 0);
 }
 
 // ------------------------------------------------------------------ shared memory
-template <int NW>
+enum { TM_FAST = 0, TM_SLOW = 1, TM_BAD = 2 };
+
+template <int NW, int STAGES>
 struct FSmem {
     static constexpr int NT = NW * 32, TILE = NT * F_IPT, WIN = NT * F_SPT;
-    double w[F_STAGES][TILE];          // TMA destinations (128-byte swizzle): must stay first, 1024-aligned
+    double w[STAGES][TILE];            // TMA destinations (128-byte swizzle): must stay first, 1024-aligned
+    i64 ex[STAGES][NT];                // fast tiles: parity-map offset of every consumer thread's first particle
     int win[WIN];                      // output window (all zero between tiles)
-    i64 warp_tot[NW];
     double warp_d[NW];
     SM warp_sm[NW];
     int warp_max[NW];
-    uint64_t full_tma[F_STAGES], ready[F_STAGES], empty[F_STAGES];
-    struct Info { int t; int bad; double tp; double tot; } info[F_STAGES];
+    uint64_t full_tma[STAGES], summed[STAGES], ready[STAGES], empty[STAGES];
+    struct Pre { double tot; int bad; int eg; int tie; int pad; } pre[STAGES];     // loader -> chain warp
+    int e_last;                        // binade of the last fast tile the chain warp resolved (the loader's guess)
+    struct Info { int t; int mode; int good; int e0; double tp; i64 S_in; i64 lo; i64 cnt; } info[STAGES];
+    int tile_of[STAGES];               // producer-private: tile loaded / loading in each stage (-1 = end of work)
     i64 bc_S_in, bc_lo, bc_cnt;
     int bc_ok, bc_skip;
     // slow path (tiles with raw elements)
@@ -252,17 +301,17 @@ __device__ __forceinline__ void f_put_index(const FParams &p, i64 out_begin, i64
     else p.hdr->cap_overflow = 1;
 }
 
-// lane 0 of consumer warp 0, after the tile's exact end state is known and published
-template <int NW, int MODE>
-__device__ __forceinline__ void f_finish_tile(const FParams &p, FSmem<NW> &sm, int t, i64 S_in, i64 S_out, int good)
+// one lane, after the tile's exact end state is known and published: the tile's output range
+// [lo, lo + cnt) and, for the last tile, the call's bookkeeping
+template <int MODE>
+__device__ __forceinline__ void f_finish_tile(const FParams &p, int t, i64 S_in, i64 S_out, int &good, i64 &lo, i64 &cnt)
 {
-    i64 lo = 0, cnt = 0;
+    lo = 0; cnt = 0;
     if (MODE != F_CUMSUM && good) {
         lo = f_count_below<MODE>(p, __longlong_as_double(S_in));
         cnt = f_count_below<MODE>(p, __longlong_as_double(S_out)) - lo;
         if (cnt < 0) { cnt = 0; good = 0; }
     }
-    sm.bc_S_in = S_in; sm.bc_lo = lo; sm.bc_cnt = cnt; sm.bc_ok = good;
     if (!good) { p.hdr->fallback = 1; p.hdr->chain_bad = 1; }
     if (t == p.T - 1) {
         if (p.cumsum_last) *p.cumsum_last = __longlong_as_double(S_out);
@@ -284,8 +333,8 @@ __device__ __forceinline__ void f_finish_tile(const FParams &p, FSmem<NW> &sm, i
 // Leaves the exact c_j (bit patterns) of the tile in the stage buffer, at the positions of the
 // weights they belong to; returns 1 if the tile verified.  Everything up to the segment export
 // runs BEFORE the exact start state is known; only the walk over <= RMAX segments is serial.
-template <int NW, int MODE>
-__device__ __noinline__ int f_slow_tile(const FParams &p, FSmem<NW> &sm, int s, int t)
+template <int NW, int STAGES, int MODE>
+__device__ __noinline__ int f_slow_tile(const FParams &p, FSmem<NW, STAGES> &sm, int s, int t)
 {
     constexpr int NT = NW * 32;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -383,7 +432,10 @@ __device__ __noinline__ int f_slow_tile(const FParams &p, FSmem<NW> &sm, int s, 
             }
             f_st(p.st2 + t + 1, ST2_INCL | (u64)S_out);
             atomicAdd(&p.hdr->n_slow, 1);
-            f_finish_tile<NW, MODE>(p, sm, t, S_in, S_out, !wbad);
+            int good = !wbad;
+            i64 lo, cnt;
+            f_finish_tile<MODE>(p, t, S_in, S_out, good, lo, cnt);
+            sm.bc_S_in = S_in; sm.bc_lo = lo; sm.bc_cnt = cnt; sm.bc_ok = good;
         }
     }
     f_bar<NT>();
@@ -426,8 +478,8 @@ __device__ __forceinline__ void f_store_cumsum(const FParams &p, i64 j, const i6
 
 // read this thread's F_SPT window slots (and clear them), running maximum, block max-scan:
 // m[i] = marker (local particle index + 1) of the particle that owns slot tid*F_SPT + i
-template <int NW>
-__device__ __forceinline__ void f_window_scan(FSmem<NW> &sm, int tid, int lane, int wid, int (&m)[F_SPT])
+template <int NW, int STAGES>
+__device__ __forceinline__ void f_window_scan(FSmem<NW, STAGES> &sm, int tid, int lane, int wid, int (&m)[F_SPT])
 {
     constexpr int NT = NW * 32;
     int4 *wv = reinterpret_cast<int4 *>(sm.win) + tid * (F_SPT / 4);
@@ -454,43 +506,79 @@ __device__ __forceinline__ void f_window_scan(FSmem<NW> &sm, int tid, int lane, 
 }
 
 // ------------------------------------------------------------------ the kernel
-template <int NW, int MODE>
-__global__ void __launch_bounds__(NW * 32 + 32, NW == 8 ? 2 : 4)
+// resident CTAs per SM that the shared-memory footprint of a variant allows (227 KB per SM)
+constexpr int f_ctas(int nw, int stages) { return nw == 8 ? (stages <= 2 ? 2 : 1) : (stages <= 2 ? 4 : (stages == 3 ? 3 : 2)); }
+
+template <int NW, int STAGES, int MODE>
+__global__ void __launch_bounds__(NW * 32 + 64, f_ctas(NW, STAGES))
 k_fused(const __grid_constant__ CUtensorMap wmap, const FParams p)
 {
-    constexpr int NT = NW * 32, TILE = NT * F_IPT, WIN = NT * F_SPT;
+    constexpr int NT = NW * 32, TILE = NT * F_IPT, WIN = NT * F_SPT, RPL = NT / 32;
     extern __shared__ __align__(1024) unsigned char f_smem_raw[];
-    FSmem<NW> &sm = *reinterpret_cast<FSmem<NW> *>(f_smem_raw);
+    FSmem<NW, STAGES> &sm = *reinterpret_cast<FSmem<NW, STAGES> *>(f_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
     if (tid == 0) {
-        for (int s = 0; s < F_STAGES; s++) { f_mbar_init(&sm.full_tma[s], 1); f_mbar_init(&sm.ready[s], 1); f_mbar_init(&sm.empty[s], NW); }
+        for (int s = 0; s < STAGES; s++) {
+            f_mbar_init(&sm.full_tma[s], 1); f_mbar_init(&sm.summed[s], 1); f_mbar_init(&sm.ready[s], 1); f_mbar_init(&sm.empty[s], NW);
+        }
+        sm.e_last = 1022;              // binade [0.5, 1): where a normalised running sum spends most of its life
         f_fence_mbar_init();
     }
-    for (int q = tid; q < WIN; q += NT + 32) sm.win[q] = 0;
+    for (int q = tid; q < WIN; q += NT + 64) sm.win[q] = 0;
     __syncthreads();
 
     const double divisor = p.div ? *p.div : 1.0;
 
     if (wid == NW) {
-        // ============================================================ producer warp
-        for (int q = 0;; q++) {
-            const int s = q % F_STAGES, use = q / F_STAGES;
-            if (use > 0) f_mbar_wait(&sm.empty[s], (use - 1) & 1);
-            int t = 0;
-            if (lane == 0) t = atomicAdd(&p.hdr->tile_counter, 1);
-            t = __shfl_sync(FULL, t, 0);
-            if (t >= p.T) {
-                if (lane == 0) { sm.info[s].t = -1; f_mbar_arrive(&sm.ready[s]); }
+        // ============================================================ loader warp
+        // Claims tiles, starts their TMA loads, sums them and publishes the stage-1 AGGREGATE as soon
+        // as the data is there.  It never waits for another CTA, so every tile's sum is published
+        // promptly — a look-back only ever waits for loads, not for somebody else's look-back.
+        // It also forms the row sums of the parity map in the binade the chain warp saw last
+        // (a guess that is right for all but a handful of tiles).
+        int q_issue = 0, q_proc = 0, exhausted = 0;
+        long long pf[3] = {0, 0, 0}, tk = clock64();
+        auto lap = [&](int i) { const long long now = clock64(); pf[i] += now - tk; tk = now; };
+        // claim tiles (in order) and start their loads while stages are free; `block`: wait for the first
+        auto issue = [&](bool block) {
+            while (!exhausted && q_issue < q_proc + STAGES) {
+                const int s = q_issue % STAGES, use = q_issue / STAGES;
+                if (use > 0) {
+                    if (block) f_mbar_wait(&sm.empty[s], (use - 1) & 1);
+                    else {
+                        int is_free = 0;
+                        if (lane == 0) is_free = f_mbar_try(&sm.empty[s], (use - 1) & 1) ? 1 : 0;
+                        if (!__shfl_sync(FULL, is_free, 0)) break;
+                    }
+                }
+                int t = 0;
+                if (lane == 0) t = atomicAdd(&p.hdr->tile_counter, 1);
+                t = __shfl_sync(FULL, t, 0);
+                if (t >= p.T) { exhausted = 1; t = -1; }
+                if (lane == 0) {
+                    sm.tile_of[s] = t;
+                    if (t >= 0 && p.use_tma) {
+                        f_mbar_expect_tx(&sm.full_tma[s], TILE * 8);
+                        f_tma_load_2d(sm.w[s], &wmap, 0, t * NT, &sm.full_tma[s]);
+                    }
+                }
+                q_issue++;
+                block = false;
+            }
+            __syncwarp();
+        };
+        for (;;) {
+            issue(q_proc == q_issue);
+            lap(0);
+            const int s = q_proc % STAGES, use = q_proc / STAGES;
+            const int t = sm.tile_of[s];
+            if (t < 0) {
+                if (lane == 0) f_mbar_arrive(&sm.summed[s]);
                 break;
             }
-            double *dst = sm.w[s];
-            unsigned char *sb = reinterpret_cast<unsigned char *>(dst);
+            unsigned char *sb = reinterpret_cast<unsigned char *>(sm.w[s]);
             if (p.use_tma) {
-                if (lane == 0) {
-                    f_mbar_expect_tx(&sm.full_tma[s], TILE * 8);
-                    f_tma_load_2d(dst, &wmap, 0, t * NT, &sm.full_tma[s]);
-                }
                 f_mbar_wait(&sm.full_tma[s], use & 1);
                 // rows beyond n/16 arrive zero-filled; the last n % 16 weights are fetched by hand
                 const i64 R = p.n >> 4;
@@ -508,70 +596,195 @@ k_fused(const __grid_constant__ CUtensorMap wmap, const FParams p)
                 }
             }
             __syncwarp();
-            // tile sum (any order: it is only the approximate prefix) and input validation
+            lap(1);
+            // tile sum (only the approximate prefix comes from it), validation, optional normalisation,
+            // speculative row sums.  Lane L owns rows L, L + 32, ...: consecutive lanes read
+            // consecutive swizzled rows (conflict-free).
+            const int eg = *reinterpret_cast<volatile int *>(&sm.e_last);
+            const i64 gbase = (i64)eg << 52;
+            const double G0 = __longlong_as_double(gbase), G1 = __longlong_as_double(gbase + 1);
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            unsigned mx = 0;
-            const double2 *src = reinterpret_cast<const double2 *>(dst);
-#pragma unroll 8
-            for (int i = 0; i < TILE / 64; i += 2) {
-                const double2 u0 = src[i * 32 + lane], u1 = src[(i + 1) * 32 + lane];
-                a0 += u0.x; a1 += u0.y; a2 += u1.x; a3 += u1.y;
-                mx = max(mx, max(max((unsigned)__double2hiint(u0.x), (unsigned)__double2hiint(u0.y)),
-                                 max((unsigned)__double2hiint(u1.x), (unsigned)__double2hiint(u1.y))));
+            unsigned mx = 0, tie = 0;
+#pragma unroll 2
+            for (int i = 0; i < RPL; i++) {
+                const int r = i * 32 + lane;
+                i64 racc = 0;
+#pragma unroll
+                for (int c = 0; c < F_IPT / 2; c++) {
+                    double2 v = *reinterpret_cast<const double2 *>(sb + f_swz(r, c));
+                    if (p.div) {
+                        // fused normalisation: w / S, the same IEEE division NumPy's `w / w.sum()` performs
+                        v.x = __ddiv_rn(v.x, divisor); v.y = __ddiv_rn(v.y, divisor);
+                        *reinterpret_cast<double2 *>(sb + f_swz(r, c)) = v;
+                    }
+                    if (c & 1) { a2 += v.x; a3 += v.y; } else { a0 += v.x; a1 += v.y; }
+                    mx = max(mx, max((unsigned)__double2hiint(v.x), (unsigned)__double2hiint(v.y)));
+                    const i64 x0 = __double_as_longlong(__dadd_rn(G0, v.x)), x1 = __double_as_longlong(__dadd_rn(G1, v.x));
+                    const i64 y0 = __double_as_longlong(__dadd_rn(G0, v.y)), y1 = __double_as_longlong(__dadd_rn(G1, v.y));
+                    tie |= (((unsigned)x0 + 1u) ^ (unsigned)x1) | (((unsigned)y0 + 1u) ^ (unsigned)y1);   // d1 != d0: an exact tie
+                    racc += (x0 - gbase) + (y0 - gbase);
+                }
+                sm.ex[s][r] = racc;
             }
+            if (p.div) f_fence_proxy_async();              // generic-proxy writes to a stage the TMA engine will refill
             int bad = 0;
             if (mx >= 0x7FF00000u) {                       // negative, inf or nan somewhere (or a harmless -0.0)
-                for (int i = 0; i < TILE / 64; i++) {
-                    const double2 u0 = src[i * 32 + lane];
-                    if (!(u0.x >= 0.0) || !(u0.y >= 0.0) || isinf(u0.x) || isinf(u0.y)) bad = 1;
-                }
+                for (int i = 0; i < RPL; i++)
+                    for (int c = 0; c < F_IPT / 2; c++) {
+                        const double2 v = *reinterpret_cast<const double2 *>(sb + f_swz(i * 32 + lane, c));
+                        if (!(v.x >= 0.0) || !(v.y >= 0.0) || isinf(v.x) || isinf(v.y)) bad = 1;
+                    }
             }
             bad = __any_sync(FULL, bad);
+            const int any_tie = __any_sync(FULL, tie != 0);
             double tot = (a0 + a1) + (a2 + a3);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
-            if (p.div) tot = tot / divisor;
             if (bad) { tot = 0.0; if (lane == 0) p.hdr->fallback = 1; }
-            if (lane == 0) f_st(p.st1 + t + 1, ((u64)__double_as_longlong(tot) & ~3ull) | ST1_AGG);
-            const double tp = f_lookback_sum(p, t, lane);
+            __syncwarp();
             if (lane == 0) {
-                f_st(p.st1 + t + 1, ((u64)__double_as_longlong(tp + tot) & ~3ull) | ST1_INCL);
-                sm.info[s].t = t; sm.info[s].bad = bad; sm.info[s].tp = tp; sm.info[s].tot = tot;
+                f_st(p.st1 + t + 1, ((u64)__double_as_longlong(tot) & ~3ull) | ST1_AGG);
+                sm.pre[s].tot = tot; sm.pre[s].bad = bad; sm.pre[s].eg = eg; sm.pre[s].tie = any_tie;
+                f_mbar_arrive(&sm.summed[s]);
+            }
+            lap(2);
+            q_proc++;
+        }
+        if (p.prof && lane == 0)
+            for (int i = 0; i < 3; i++) atomicAdd(reinterpret_cast<unsigned long long *>(&p.hdr->prof[i]), (unsigned long long)pf[i]);
+        return;
+    }
+    if (wid == NW + 1) {
+        // ============================================================ chain warp
+        // Resolves both look-backs for the tiles the loader has summed: approximate prefix -> which
+        // binade the tile lives in -> the tile's parity map -> exact state before the tile.
+        long long pf[4] = {0, 0, 0, 0}, tk = clock64();
+        auto lap = [&](int i) { const long long now = clock64(); pf[i] += now - tk; tk = now; };
+        for (int q = 0;; q++) {
+            const int s = q % STAGES, use = q / STAGES;
+            f_mbar_wait(&sm.summed[s], use & 1);
+            lap(0);
+            const int t = sm.tile_of[s];
+            if (t < 0) {
+                if (lane == 0) { sm.info[s].t = -1; f_mbar_arrive(&sm.ready[s]); }
+                break;
+            }
+            unsigned char *sb = reinterpret_cast<unsigned char *>(sm.w[s]);
+            const double tot = sm.pre[s].tot;
+            const int bad = sm.pre[s].bad, eg = sm.pre[s].eg;
+            int any_tie = sm.pre[s].tie;
+            const double tp = f_lookback_sum(p, t, lane);
+            if (lane == 0) f_st(p.st1 + t + 1, ((u64)__double_as_longlong(tp + tot) & ~3ull) | ST1_INCL);
+            lap(1);
+            int e0;
+            const bool ca = clean_add(tp, tp + tot, p.eb, &e0);
+            int mode = bad ? TM_BAD : ((ca || tot == 0.0) ? TM_FAST : TM_SLOW);
+            i64 S_in = 0, lo = 0, cnt = 0;
+            int good = 1;
+            if (mode == TM_FAST && tot == 0.0) {
+                for (int i = 0; i < RPL; i++) sm.ex[s][i * 32 + lane] = 0;
+                any_tie = 0;
+            } else if (mode == TM_FAST && e0 != eg) {
+                // the loader's guess was wrong (first tiles, a new binade): row sums again, in binade e0
+                const i64 base = (i64)e0 << 52;
+                const double B0 = __longlong_as_double(base), B1 = __longlong_as_double(base + 1);
+                unsigned tie = 0;
+#pragma unroll 2
+                for (int i = 0; i < RPL; i++) {
+                    const int r = i * 32 + lane;
+                    i64 racc = 0;
+#pragma unroll
+                    for (int c = 0; c < F_IPT / 2; c++) {
+                        const double2 v = *reinterpret_cast<const double2 *>(sb + f_swz(r, c));
+                        const i64 x0 = __double_as_longlong(__dadd_rn(B0, v.x)), x1 = __double_as_longlong(__dadd_rn(B1, v.x));
+                        const i64 y0 = __double_as_longlong(__dadd_rn(B0, v.y)), y1 = __double_as_longlong(__dadd_rn(B1, v.y));
+                        tie |= (((unsigned)x0 + 1u) ^ (unsigned)x1) | (((unsigned)y0 + 1u) ^ (unsigned)y1);
+                        racc += (x0 - base) + (y0 - base);
+                    }
+                    sm.ex[s][r] = racc;
+                }
+                any_tie = __any_sync(FULL, tie != 0);
+            }
+            if (mode == TM_FAST && tot != 0.0 && lane == 0) sm.e_last = e0;
+            if (mode == TM_FAST && any_tie) mode = TM_SLOW;      // ties: the general parity maps of the slow path
+            if (mode == TM_FAST) {
+                // exclusive offsets per row (= consumer thread) and the tile's map D
+                __syncwarp();
+                i64 v[RPL], run = 0;
+#pragma unroll
+                for (int j = 0; j < RPL; j++) { const i64 x = sm.ex[s][lane * RPL + j]; v[j] = run; run += x; }
+                const i64 inc = warp_incl_scan_i64(run, lane);
+                const i64 lane_ex = inc - run;
+#pragma unroll
+                for (int j = 0; j < RPL; j++) sm.ex[s][lane * RPL + j] = lane_ex + v[j];
+                const i64 D = __shfl_sync(FULL, inc, 31);
+                if (lane == 0) f_st(p.st2 + t + 1, st2_pack_agg(D, 0));
+                lap(2);
+                S_in = f_lookback_state(p, t, lane);
+                if (lane == 0) {
+                    const i64 S_out = S_in + D;
+                    good = (tot == 0.0) || ((int)(S_in >> 52) == e0 && (int)(S_out >> 52) == e0);
+                    f_st(p.st2 + t + 1, ST2_INCL | (u64)S_out);
+                    f_finish_tile<MODE>(p, t, S_in, S_out, good, lo, cnt);
+                }
+            } else if (mode == TM_BAD) {
+                // invalid weights: the sequential kernel will produce the result; keep the chain moving
+                lap(2);
+                S_in = f_lookback_state(p, t, lane);
+                if (lane == 0) f_st(p.st2 + t + 1, ST2_INCL | (u64)S_in);
+            } else lap(2);
+            __syncwarp();
+            if (lane == 0) {
+                sm.info[s].t = t; sm.info[s].mode = mode; sm.info[s].good = good; sm.info[s].e0 = e0;
+                sm.info[s].tp = tp; sm.info[s].S_in = S_in; sm.info[s].lo = lo; sm.info[s].cnt = cnt;
                 f_mbar_arrive(&sm.ready[s]);
             }
+            lap(3);
         }
+        if (p.prof && lane == 0)
+            for (int i = 0; i < 4; i++) atomicAdd(reinterpret_cast<unsigned long long *>(&p.hdr->prof[3 + i]), (unsigned long long)pf[i]);
         return;
     }
 
     // ================================================================ consumer warps
+    // Fast tiles arrive with everything resolved (exact start state, output range): no global wait.
     const i64 out_begin = p.hdr->out_begin;
     const double Nd = (double)p.ng;
+    long long cwait = 0, cwork = 0, ctk = clock64();
     for (int q = 0;; q++) {
-        const int s = q % F_STAGES, use = q / F_STAGES;
+        const int s = q % STAGES, use = q / STAGES;
+        { const long long now = clock64(); cwork += now - ctk; ctk = now; }
         f_mbar_wait(&sm.ready[s], use & 1);
+        { const long long now = clock64(); cwait += now - ctk; ctk = now; }
         const int t = sm.info[s].t;
-        if (t < 0) break;
+        if (t < 0) {
+            if (p.prof && tid == 0) {
+                atomicAdd(reinterpret_cast<unsigned long long *>(&p.hdr->prof[7]), (unsigned long long)cwait);
+                atomicAdd(reinterpret_cast<unsigned long long *>(&p.hdr->prof[8]), (unsigned long long)cwork);
+            }
+            break;
+        }
+        const int mode = sm.info[s].mode;
+        if (mode == TM_BAD) {
+            __syncwarp();
+            if (lane == 0) f_mbar_arrive(&sm.empty[s]);
+            continue;
+        }
         if (p.use_tma) f_mbar_wait(&sm.full_tma[s], use & 1);       // already complete: acquires the TMA writes directly
-        const double tp = sm.info[s].tp, tot = sm.info[s].tot;
-        const int tile_bad = sm.info[s].bad;
         unsigned char *sb = reinterpret_cast<unsigned char *>(sm.w[s]);
         const i64 jthread = (i64)t * TILE + (i64)tid * F_IPT;       // first particle of this thread (local numbering)
-
-        double w[F_IPT];
+        i64 cb[F_IPT];
+        i64 thread_start;                                   // exact state before this thread's first particle
+        i64 tile_lo, tile_cnt;
+        int good;
+        if (mode == TM_FAST || p.wnorm_out) {
+            double w[F_IPT];
 #pragma unroll
-        for (int c = 0; c < F_IPT / 2; c++) {
-            const double2 v = *reinterpret_cast<const double2 *>(sb + f_swz(tid, c));
-            w[2 * c] = v.x; w[2 * c + 1] = v.y;
-        }
-        if (p.div) {
-            // fused normalisation: w / S, the same IEEE division NumPy's `w / w.sum()` performs
-#pragma unroll
-            for (int k = 0; k < F_IPT; k++) w[k] = __ddiv_rn(w[k], divisor);
-#pragma unroll
-            for (int c = 0; c < F_IPT / 2; c++)
-                *reinterpret_cast<double2 *>(sb + f_swz(tid, c)) = make_double2(w[2 * c], w[2 * c + 1]);
-            f_fence_proxy_async();        // generic-proxy writes to a stage the TMA engine will refill
-            if (p.wnorm_out) {
+            for (int c = 0; c < F_IPT / 2; c++) {
+                const double2 v = *reinterpret_cast<const double2 *>(sb + f_swz(tid, c));
+                w[2 * c] = v.x; w[2 * c + 1] = v.y;
+            }
+            if (p.wnorm_out) {                              // the producer left the normalised weights in the stage
                 double *o = p.wnorm_out + jthread;
                 if (jthread + F_IPT <= p.n && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
 #pragma unroll
@@ -581,66 +794,25 @@ k_fused(const __grid_constant__ CUtensorMap wmap, const FParams p)
                     for (int k = 0; k < F_IPT; k++) if (jthread + k < p.n) o[k] = w[k];
                 }
             }
-        }
-
-        // ---- fast classification: the whole tile deep inside ONE binade, no ties -> plain int64 sums
-        int e0;
-        const bool ca = clean_add(tp, tp + tot, p.eb, &e0);
-        const bool tile_clean = !tile_bad && (ca || tot == 0.0);
-        const i64 base = (i64)e0 << 52;
-        const double B0 = __longlong_as_double(base), B1 = __longlong_as_double(base + 1);
-        i64 pre[F_IPT];
-        i64 acc = 0;
-        unsigned tie = 0;
+            if (mode == TM_FAST) {
+                good = sm.info[s].good; tile_lo = sm.info[s].lo; tile_cnt = sm.info[s].cnt;
+                const i64 base = (i64)sm.info[s].e0 << 52;
+                const double B0 = __longlong_as_double(base);
+                thread_start = sm.info[s].S_in + sm.ex[s][tid];
+                i64 c = thread_start;
 #pragma unroll
-        for (int k = 0; k < F_IPT; k++) {
-            const i64 b0 = __double_as_longlong(__dadd_rn(B0, w[k]));
-            const i64 b1 = __double_as_longlong(__dadd_rn(B1, w[k]));
-            tie |= ((unsigned)b0 + 1u) ^ (unsigned)b1;     // d1 != d0 only for an exact tie (round-half-even)
-            acc += b0 - base;
-            pre[k] = acc;
-        }
-        const i64 inc = warp_incl_scan_i64(acc, lane);
-        if (lane == 31) sm.warp_tot[wid] = inc;
-        const int fast = f_bar_and<NT>(tile_clean && tie == 0);
-
-        i64 cb[F_IPT];
-        i64 thread_start;                                   // exact state before this thread's first particle
-        int good;
-        if (tile_bad) {
-            // invalid weights: the sequential kernel will produce the result; keep the chain moving
-            if (wid == 0) {
-                const i64 S_in = f_lookback_state(p, t, lane);
-                if (lane == 0) f_st(p.st2 + t + 1, ST2_INCL | (u64)S_in);
-            }
-            __syncwarp();
-            if (lane == 0) { f_fence_proxy_async(); f_mbar_arrive(&sm.empty[s]); }
-            continue;
-        }
-        if (fast) {
-            // the stage is free once every consumer has its weights in registers (the barrier above
-            // depends on all of them)
-            if (lane == 0) f_mbar_arrive(&sm.empty[s]);
-            i64 ex = inc - acc, D = 0;
-#pragma unroll
-            for (int i = 0; i < NW; i++) { const i64 v = sm.warp_tot[i]; if (i < wid) ex += v; D += v; }
-            if (wid == 0) {
-                if (lane == 0) f_st(p.st2 + t + 1, st2_pack_agg(D, 0));
-                const i64 S_in = f_lookback_state(p, t, lane);
-                if (lane == 0) {
-                    const i64 S_out = S_in + D;
-                    const int ok = (tot == 0.0) || ((int)(S_in >> 52) == e0 && (int)(S_out >> 52) == e0);
-                    f_st(p.st2 + t + 1, ST2_INCL | (u64)S_out);
-                    f_finish_tile<NW, MODE>(p, sm, t, S_in, S_out, ok);
+                for (int k = 0; k < F_IPT; k++) {
+                    c += __double_as_longlong(__dadd_rn(B0, w[k])) - base;
+                    cb[k] = c;
                 }
             }
-            f_bar<NT>();
-            good = sm.bc_ok;
-            thread_start = sm.bc_S_in + ex;
-#pragma unroll
-            for (int k = 0; k < F_IPT; k++) cb[k] = thread_start + pre[k];
+        }
+        if (mode == TM_FAST) {
+            // the stage is free once this warp holds everything it needs in registers
+            __syncwarp();
+            if (lane == 0) f_mbar_arrive(&sm.empty[s]);
         } else {
-            good = f_slow_tile<NW, MODE>(p, sm, s, t);
+            good = f_slow_tile<NW, STAGES, MODE>(p, sm, s, t);
 #pragma unroll
             for (int c = 0; c < F_IPT / 2; c++) {
                 const longlong2 v = *reinterpret_cast<const longlong2 *>(sb + f_swz(tid, c));
@@ -651,13 +823,12 @@ k_fused(const __grid_constant__ CUtensorMap wmap, const FParams p)
                 const longlong2 v = *reinterpret_cast<const longlong2 *>(sb + f_swz(tid > 0 ? tid - 1 : 0, 7));
                 thread_start = tid > 0 ? v.y : sm.bc_S_in;
             }
+            tile_lo = sm.bc_lo; tile_cnt = sm.bc_cnt;
             __syncwarp();
             if (lane == 0) { f_fence_proxy_async(); f_mbar_arrive(&sm.empty[s]); }
         }
-        const i64 tile_lo = sm.bc_lo;
-        const i64 tile_cnt = sm.bc_cnt;
-        if (!good) { f_bar<NT>(); continue; }
-        if (MODE == F_CUMSUM) { f_store_cumsum(p, jthread, cb); f_bar<NT>(); continue; }
+        if (!good) continue;
+        if (MODE == F_CUMSUM) { f_store_cumsum(p, jthread, cb); continue; }
 
         // ---- output range end of every particle, relative to tile_lo: hv[k] = #{positions < c_k} - tile_lo
         int hv[F_IPT], hv_prev;
@@ -704,7 +875,7 @@ k_fused(const __grid_constant__ CUtensorMap wmap, const FParams p)
             }
             f_bar<NT>();
             int m[F_SPT];
-            f_window_scan<NW>(sm, tid, lane, wid, m);
+            f_window_scan<NW, STAGES>(sm, tid, lane, wid, m);
             const int s0 = tid * F_SPT;
             int *dst = p.idx + (rel_lo - mis) + s0;
             if (s0 >= mis && s0 + F_SPT <= total) {
@@ -755,7 +926,7 @@ k_fused(const __grid_constant__ CUtensorMap wmap, const FParams p)
             }
             f_bar<NT>();
             int m[F_SPT];
-            f_window_scan<NW>(sm, tid, lane, wid, m);
+            f_window_scan<NW, STAGES>(sm, tid, lane, wid, m);
 #pragma unroll
             for (int i = 0; i < F_SPT; i++) {
                 const int sl = tid * F_SPT + i;
@@ -805,6 +976,12 @@ __global__ void __launch_bounds__(256) k_fepilogue(FParams p)
         }
     }
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    if (p.prof) {
+        const double T = (double)p.T;
+        printf("RSPROF tiles=%d cycles/tile: loader[stage-wait %.0f | tma-wait %.0f | sum-pass %.0f]  chain[wait-summed %.0f | lookback1 %.0f | maps %.0f | lookback2+finish %.0f]  cons[wait-ready %.0f | work %.0f]  slow=%d general=%d\n",
+               p.T, hdr->prof[0] / T, hdr->prof[1] / T, hdr->prof[2] / T, hdr->prof[3] / T, hdr->prof[4] / T, hdr->prof[5] / T,
+               hdr->prof[6] / T, hdr->prof[7] / T, hdr->prof[8] / T, hdr->n_slow, hdr->n_general);
+    }
     auto write_info = [&](int overflow, int fb) {
         if (p.info) {
             p.info[0] = overflow; p.info[1] = fb; p.info[2] = hdr->n_unclean; p.info[3] = hdr->n_runs;
@@ -905,11 +1082,11 @@ int f_env_int(const char *name, int dflt)
     return v ? atoi(v) : dflt;
 }
 
-template <int NW, int MODE>
+template <int NW, int STAGES, int MODE>
 int f_launch(const CUtensorMap &map, const FParams &p, cudaStream_t s)
 {
-    auto kern = k_fused<NW, MODE>;
-    const int smem = (int)sizeof(FSmem<NW>);
+    auto kern = k_fused<NW, STAGES, MODE>;
+    const int smem = (int)sizeof(FSmem<NW, STAGES>);
     static bool configured[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -918,11 +1095,19 @@ int f_launch(const CUtensorMap &map, const FParams &p, cudaStream_t s)
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     const int ctas_env = f_env_int("BKE_RS_CTAS", 0);
-    const int per_sm = ctas_env > 0 ? ctas_env : (NW == 8 ? 2 : 4);
+    const int per_sm = ctas_env > 0 ? ctas_env : f_ctas(NW, STAGES);
     int grid = sm_count() * per_sm;
     if (grid > p.T) grid = p.T;
-    kern<<<grid, NW * 32 + 32, smem, s>>>(map, p);
+    kern<<<grid, NW * 32 + 64, smem, s>>>(map, p);
     return check_cuda(cudaGetLastError(), "k_fused launch");
+}
+
+template <int NW, int STAGES>
+int f_launch_mode(int mode, const CUtensorMap &map, const FParams &p, cudaStream_t s)
+{
+    if (mode == F_CUMSUM) return f_launch<NW, STAGES, F_CUMSUM>(map, p, s);
+    if (mode == F_STRAT) return f_launch<NW, STAGES, F_STRAT>(map, p, s);
+    return f_launch<NW, STAGES, F_SYS>(map, p, s);
 }
 
 }  // namespace
@@ -959,6 +1144,11 @@ int f_run(const FRunArgs &a, cudaStream_t s)
     f_carve(n, (unsigned char *)a.workspace, &p);
     const int nw_env = f_env_int("BKE_RS_WARPS", 8);
     const int NW = (nw_env == 4) ? 4 : 8;
+    p.sleep_ns = f_env_int("BKE_RS_SLEEP", 0);
+    p.prof = f_env_int("BKE_RS_PROF", 0);
+    p.lbk = f_env_int("BKE_RS_LBK", 4);
+    if (p.lbk < 1) p.lbk = 1;
+    if (p.lbk > LBK_MAX) p.lbk = LBK_MAX;
     const int tile = NW * 32 * F_IPT;
     p.w = a.w; p.n = n; p.ng = a.ng; p.j0 = a.j0; p.cap = a.cap; p.is_last = a.is_last;
     p.carry_approx = a.carry_approx; p.carry_exact = a.carry_exact; p.out_range = a.out_range;
@@ -988,12 +1178,9 @@ int f_run(const FRunArgs &a, cudaStream_t s)
     k_finit<<<init_blocks, 256, 0, s>>>(p);
     int rc;
     const int mode = a.cumsum_out ? F_CUMSUM : (a.U ? F_STRAT : F_SYS);
-#define BKE_F_DISPATCH(NWV)                                                    \
-    (mode == F_CUMSUM ? f_launch<NWV, F_CUMSUM>(map, p, s)                     \
-     : mode == F_STRAT ? f_launch<NWV, F_STRAT>(map, p, s)                     \
-                       : f_launch<NWV, F_SYS>(map, p, s))
-    rc = (NW == 4) ? BKE_F_DISPATCH(4) : BKE_F_DISPATCH(8);
-#undef BKE_F_DISPATCH
+    const int st = f_env_int("BKE_RS_STAGES", F_STAGES);
+    if (NW == 4) rc = st <= 2 ? f_launch_mode<4, 2>(mode, map, p, s) : (st == 3 ? f_launch_mode<4, 3>(mode, map, p, s) : f_launch_mode<4, 4>(mode, map, p, s));
+    else rc = st <= 2 ? f_launch_mode<8, 2>(mode, map, p, s) : f_launch_mode<8, 3>(mode, map, p, s);
     if (rc != BKE_OK) return rc;
     k_fepilogue<<<sm_count() * 4, 256, 0, s>>>(p);
     return check_cuda(cudaGetLastError(), "resample launch");

@@ -25,6 +25,7 @@ struct FHeader {
     int pad;
     i64 out_begin;      // first global output position owned by this call
     i64 out_end;        // one past the last
+    i64 prof[10];       // BKE_RS_PROF: cycles summed over CTAs (producer phases 0-5, consumer wait / work)
 };
 
 struct FParams {
@@ -54,6 +55,9 @@ struct FParams {
     Run *runs;
     int max_runs;
     int T;
+    int sleep_ns;          // back-off between two polls of a status word (0 = spin)
+    int prof;              // BKE_RS_PROF=1: per-phase cycle counters, printed by the epilogue kernel
+    int lbk;               // status words per lane and look-back round (window = 32 * lbk tiles)
 };
 
 struct FRunArgs {

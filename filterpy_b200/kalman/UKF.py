@@ -26,6 +26,7 @@ import torch
 
 from .. import _lib
 from .._dev import bke_dtype, ptr, require_cuda, resolve_dtype, stream_ptr, to_dev
+from .kalman_filter import _Linked
 
 __all__ = ["UnscentedKalmanFilter", "LinearFx", "ConstVelFx", "LinearHx", "RangeAzElHx", "RangeBearingHx"]
 
@@ -130,7 +131,7 @@ class UnscentedKalmanFilter(object):
     @property
     def x(self):
         self._flush()
-        return self._out(self._x)
+        return self._x if not self._single else _Linked(self._x[0].cpu().numpy(), self, "x")
 
     @x.setter
     def x(self, v):
@@ -145,7 +146,7 @@ class UnscentedKalmanFilter(object):
     @property
     def P(self):
         self._flush()
-        return self._out(self._P)
+        return self._P if not self._single else _Linked(self._P[0].cpu().numpy(), self, "P")
 
     @P.setter
     def P(self, v):
@@ -160,10 +161,23 @@ class UnscentedKalmanFilter(object):
             raise ValueError("P must have shape (%d,%d) or (%d,%d,%d)" % (n, n, self.n_filters, n, n))
         self._P = t.contiguous().clone()
 
-    Q = property(lambda self: self._Q.cpu().numpy() if self._single else self._Q,
-                 lambda self, v: setattr(self, "_Q", self._model(v, self._dim_x, self._dim_x, "Q")))
-    R = property(lambda self: self._R.cpu().numpy() if self._single else self._R,
-                 lambda self, v: setattr(self, "_R", self._model(v, self._dim_z, self._dim_z, "R")))
+    # A deferred predict() must run with the Q it was issued with (the reference's predict has
+    # already happened): the setters, and the bank-mode getters that hand out the live tensor,
+    # flush it first.  Single mode returns write-back arrays so that ``ukf.P[2, 2] = 100`` /
+    # ``ukf.Q[0, 0] = q`` reach the filter as they do in the reference.
+    def _get_model(self, name):
+        t = getattr(self, "_" + name)
+        if self._single:
+            return _Linked(t.cpu().numpy(), self, name)
+        self._flush()
+        return t
+
+    def _set_model(self, name, v, dim):
+        self._flush()
+        setattr(self, "_" + name, self._model(v, dim, dim, name))
+
+    Q = property(lambda self: self._get_model("Q"), lambda self, v: self._set_model("Q", v, self._dim_x))
+    R = property(lambda self: self._get_model("R"), lambda self, v: self._set_model("R", v, self._dim_z))
 
     def _diag(self, name):
         if not self.diagnostics:
@@ -226,7 +240,12 @@ class UnscentedKalmanFilter(object):
             self._launch(_lib.BKE_DO_PREDICT, dt, None, None, None)
 
     def update(self, z, R=None, UT=None, hx=None, valid=None, **hx_args):
-        """UKF.py:413-491.  ``z`` is ``(N, dim_z)`` in bank mode; ``z=None`` skips the update."""
+        """UKF.py:413-491.  ``z`` is ``(N, dim_z)`` in bank mode; ``z=None`` skips the update.
+
+        Difference from the reference: an ``update`` WITHOUT a preceding ``predict`` draws its sigma
+        points from the current (x, P) — what ``predict`` leaves behind (UKF.py:407) — whereas the
+        reference would silently reuse the stale ``self.sigmas_f`` of the last predict (zeros on a
+        fresh object).  After ``predict(); update(z)`` the two agree."""
         _no_hook("UT", UT); _no_hook("hx", hx)
         if hx_args:
             raise NotImplementedError("hx_args are arguments of a Python callback; not available on the GPU path")

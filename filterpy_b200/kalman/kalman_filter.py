@@ -32,6 +32,44 @@ from ..common.helpers import reshape_z
 __all__ = ["KalmanFilter", "predict", "update", "batch_filter", "rts_smoother"]
 
 
+class _Linked(np.ndarray):
+    """What the single-mode attribute getters hand out: a host copy of a device array that WRITES
+    BACK.  The reference's attributes are the live arrays, so the usual idioms ``kf.P[2, 2] = 100``,
+    ``kf.x[0] = z``, ``kf.F[0, 1] = dt``, ``kf.P *= 10`` must reach the filter; here they re-assign
+    the attribute (which uploads it).  Anything derived from it (slices, results) is a plain copy."""
+
+    def __new__(cls, arr, owner, name):
+        obj = np.array(arr, copy=True).view(cls)
+        obj._owner, obj._name = owner, name
+        return obj
+
+    def __array_finalize__(self, obj):
+        self._owner, self._name = None, None
+
+    def _push(self):
+        if self._owner is not None:
+            setattr(self._owner, self._name, np.array(self, copy=True).view(np.ndarray))
+
+    def __setitem__(self, key, value):
+        np.ndarray.__setitem__(self, key, value)
+        self._push()
+
+    def __getitem__(self, key):
+        r = np.ndarray.__getitem__(self, key)
+        return np.array(r, copy=True) if isinstance(r, np.ndarray) else r
+
+    def _inplace(self, op, other):
+        res = op(self.view(np.ndarray), other)
+        np.ndarray.__setitem__(self, Ellipsis, res)
+        self._push()
+        return self
+
+    def __iadd__(self, o): return self._inplace(np.add, o)
+    def __isub__(self, o): return self._inplace(np.subtract, o)
+    def __imul__(self, o): return self._inplace(np.multiply, o)
+    def __itruediv__(self, o): return self._inplace(np.true_divide, o)
+
+
 class KalmanFilter(object):
     def __init__(self, dim_x, dim_z, dim_u=0, n_filters=None, dtype=np.float64, device=None,
                  diagnostics=True):
@@ -113,7 +151,7 @@ class KalmanFilter(object):
         if not self._single:
             return self._x
         v = self._x[0].cpu().numpy()
-        return v.reshape(-1, 1) if self._x_col else v
+        return _Linked(v.reshape(-1, 1) if self._x_col else v, self, "x")
 
     @x.setter
     def x(self, v):
@@ -144,7 +182,7 @@ class KalmanFilter(object):
     @property
     def P(self):
         self._flush()
-        return self._out(self._P)
+        return self._P if not self._single else _Linked(self._P[0].cpu().numpy(), self, "P")
 
     @P.setter
     def P(self, v):
@@ -185,18 +223,28 @@ class KalmanFilter(object):
             if t is None:
                 return None
             if self._single:
-                return t.cpu().numpy()
-            if self._host.pop(name, None) is not None:      # the caller may edit the live tensor in place:
-                self._version += 1                          # the host copy can no longer be trusted
+                return _Linked(t.cpu().numpy(), self, name)
+            # the caller may edit the live tensor in place: a deferred predict must run with the
+            # model it was issued with (the reference's predict has already happened), and the
+            # host copy can no longer be trusted
+            self._flush()
+            if self._host.pop(name, None) is not None:
+                self._version += 1
             return t
 
         def set_(self, v):
+            self._flush()                                   # predict(); kf.F = F2; update(): the predict used the OLD F
             self._version += 1
             self._host.pop(name, None)
             if v is None:
                 setattr(self, priv, None)
                 return
-            t = self._model(v, getattr(self, rows_attr), getattr(self, cols_attr), name)
+            cols = getattr(self, cols_attr)
+            if name == "B" and cols == 0 and not np.isscalar(v):
+                cols = int(np.shape(v)[-1]) if np.ndim(v) >= 1 else 1     # the reference never checks B against dim_u
+                if np.ndim(v) == 1:
+                    v = np.asarray(v).reshape(-1, 1); cols = 1
+            t = self._model(v, getattr(self, rows_attr), cols, name)
             setattr(self, priv, t)
             if t.dim() == 2 and name in "FQHR":
                 # host copy of a model shared by the bank: lets the kernels carry it in their launch
@@ -220,6 +268,7 @@ class KalmanFilter(object):
     def alpha(self, value):
         if not np.isscalar(value) or value < 1:
             raise ValueError('alpha must be a float greater than 1')
+        self._flush()
         self._alpha_sq = float(value) ** 2
         self._version += 1
 

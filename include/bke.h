@@ -51,6 +51,9 @@ extern "C" {
 #define BKE_DO_PREDICT 1u            /* KalmanFilter.predict   kalman_filter.py:437-482 */
 #define BKE_DO_UPDATE 2u             /* KalmanFilter.update    kalman_filter.py:485-561 */
 #define BKE_UPDATE_FIRST 4u          /* batch_filter(update_first=True) order, kalman_filter.py:966-978 */
+#define BKE_STATUS_STICKY 8u         /* status[f] is only written when the step FAILS (the caller zeroed it): an
+                                        error of an earlier step survives.  bke_kf_batch_filter's status is
+                                        sticky over all epochs on every path. */
 
 int bke_abi_version(void);
 const char *bke_last_error(void);

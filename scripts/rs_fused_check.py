@@ -46,8 +46,10 @@ def main():
     quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
     print(torch.cuda.get_device_name(0), flush=True)
     rng = np.random.default_rng(0)
-    for nw in ("8", "4"):
+    for nw, st in (("8", "2"), ("4", "3"), ("8", "3"), ("4", "2"), ("4", "4")):
         os.environ["BKE_RS_WARPS"] = nw
+        os.environ["BKE_RS_STAGES"] = st
+        nw = nw + "/" + st
         for n in (1, 2, 15, 16, 17, 31, 33, 255, 2047, 4095, 4096, 4097, 8191, 8193, 65537, 300007):
             for kind in ("heavy", "uniform", "zeros", "degenerate", "dyadic"):
                 w = wl.resample_weights(n, kind, seed=n % 997)
