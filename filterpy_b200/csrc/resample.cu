@@ -1309,6 +1309,10 @@ int bke_resample_normalized(int64_t n, const double *weights, double u, const do
     return rs::f_run(f, (cudaStream_t)stream);
 }
 
+/* debugging aid (not part of the documented ABI): device buffer of uint64[T][10] that receives the
+ * global-timer stamps of every tile's pipeline events in the single-pass kernel; NULL switches it off */
+void bke_debug_resample_trace(void *device_buffer) { rs::f_set_trace(device_buffer); }
+
 int bke_resample_shard(const bke_resample_shard_args *args, void *stream)
 {
     if (!args) { set_error("args is NULL"); return BKE_ERR_BAD_ARG; }

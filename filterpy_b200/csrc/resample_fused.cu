@@ -93,6 +93,17 @@ __device__ __forceinline__ void f_st(u64 *p, u64 v)
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// ------------------------------------------------------------------ event trace (debugging aid)
+// bke_debug_resample_trace(buf): every tile writes the global-timer time of 10 pipeline events
+__device__ __forceinline__ void f_trace(const FParams &p, int t, int ev)
+{
+    if (p.trace) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        p.trace[(size_t)t * 10 + ev] = now;
+    }
+}
+
 // ------------------------------------------------------------------ status words
 // st1[i], st2[i] describe tile i-1; entry 0 is the carry into the call (always INCLUSIVE).
 //   st1: bits of an fp64 sum with the two lowest mantissa bits replaced by the flag
@@ -229,7 +240,9 @@ __device__ __forceinline__ i64 f_lookback_state(const FParams &p, int t, int lan
 }
 
 // ------------------------------------------------------------------ shared memory
-enum { TM_FAST = 0, TM_SLOW = 1, TM_BAD = 2 };
+enum { TM_FAST = 0, TM_SLOW = 1, TM_BAD = 2 };                       // what the consumers do with a tile
+enum { TK_CLEAN = 0, TK_CROSS = 1, TK_TIES = 2, TK_BAD = 3 };        // what stage 1 found out about it
+constexpr int MAX_CROSS = 24;                                        // crossing rows resolved by the chain warp
 
 template <int NW, int STAGES>
 struct FSmem {
@@ -240,10 +253,16 @@ struct FSmem {
     double warp_d[NW];
     SM warp_sm[NW];
     int warp_max[NW];
-    uint64_t full_tma[STAGES], summed[STAGES], ready[STAGES], empty[STAGES];
-    struct Pre { double tot; int bad; int eg; int tie; int pad; } pre[STAGES];     // loader -> chain warp
+    unsigned cross[STAGES][NT / 32];   // rows (consumer threads) whose 16 adds leave their binade: true adds there
+    uint64_t full_tma[STAGES], landed[STAGES], summed[STAGES], mapped[STAGES], ready[STAGES], empty[STAGES];
+    struct Part { double tot; int bad; int tie; } part[STAGES][2];                 // the two loaders' halves
+    int lcnt[STAGES];                  // loaders done with the tile (the second one publishes)
+    int eg[STAGES];                    // binade the loaders' speculative row sums were formed in
+    struct Pre { double tot; int bad; int eg; int tie; int pad; } pre[STAGES];     // loaders -> C1
+    struct Mid { int kind; int e0; double tp; double tot; i64 D; } mid[STAGES];     // C1 -> C2
+    int last_t;                        // trace: the tile the consumers processed last
     int e_last;                        // binade of the last fast tile the chain warp resolved (the loader's guess)
-    struct Info { int t; int mode; int good; int e0; double tp; i64 S_in; i64 lo; i64 cnt; } info[STAGES];
+    struct Info { int t; int mode; int good; int pad; double tp; i64 S_in; i64 base; i64 lo; i64 cnt; } info[STAGES];
     int tile_of[STAGES];               // producer-private: tile loaded / loading in each stage (-1 = end of work)
     i64 bc_S_in, bc_lo, bc_cnt;
     int bc_ok, bc_skip;
@@ -396,9 +415,7 @@ __device__ __noinline__ int f_slow_tile(const FParams &p, FSmem<NW, STAGES> &sm,
     }
     f_bar<NT>();
     if (wid == 0) {
-        const bool agg_ok = (nraw == 0) && total.k != K_POISON && total.d >= 0 && total.d < (1ll << 59);
-        if (agg_ok && lane == 0) f_st(p.st2 + t + 1, st2_pack_agg(total.d, total.t));
-        const i64 S_in = f_lookback_state(p, t, lane);
+        const i64 S_in = sm.info[s].S_in;                  // chain warp C2 resolved it before handing the tile over
         if (lane == 0) {
             int wbad = 0;
             i64 S_out;
@@ -505,12 +522,94 @@ __device__ __forceinline__ void f_window_scan(FSmem<NW, STAGES> &sm, int tid, in
     for (int i = 0; i < F_SPT; i++) m[i] = max(m[i], basem);
 }
 
+// Row sums of the tie-free parity map in binade e for rows >= r0 (lane L owns rows L, L + 32, ...:
+// rs[i] belongs to row 32 i + L; 0 for rows < r0); returns true if any of those rows holds an exact tie.
+template <int NW, int STAGES>
+__device__ __forceinline__ bool f_row_sums(FSmem<NW, STAGES> &sm, int s, int e, int r0, int lane, i64 (&rs)[NW])
+{
+    constexpr int RPL = NW;                                // rows per lane (NT / 32)
+    const unsigned char *sb = reinterpret_cast<const unsigned char *>(sm.w[s]);
+    const i64 base = (i64)e << 52;
+    const double B0 = __longlong_as_double(base), B1 = __longlong_as_double(base + 1);
+    unsigned tie = 0;
+#pragma unroll
+    for (int i = 0; i < RPL; i++) {
+        const int r = i * 32 + lane;
+        i64 racc = 0;
+        if (r >= r0) {
+#pragma unroll
+            for (int c = 0; c < F_IPT / 2; c++) {
+                const double2 v = *reinterpret_cast<const double2 *>(sb + f_swz(r, c));
+                const i64 x0 = __double_as_longlong(__dadd_rn(B0, v.x)), x1 = __double_as_longlong(__dadd_rn(B1, v.x));
+                const i64 y0 = __double_as_longlong(__dadd_rn(B0, v.y)), y1 = __double_as_longlong(__dadd_rn(B1, v.y));
+                tie |= (((unsigned)x0 + 1u) ^ (unsigned)x1) | (((unsigned)y0 + 1u) ^ (unsigned)y1);   // d1 != d0: an exact tie
+                racc += (x0 - base) + (y0 - base);
+            }
+        }
+        rs[i] = racc;
+    }
+    return __any_sync(FULL, tie != 0) != 0;
+}
+
+// A tile that may leave its binade, resolved from the EXACT state before it (chain warp C2):
+// rows whose adds all stay in the binade of their start state are integer maps; the row that
+// leaves it is walked with true adds; the rows after it are maps of the next binade, and so on.
+// On success sm.ex[s][r] = exact state before row r, sm.cross[s] marks the walked rows, *S_out =
+// state after the tile.  false: ties or more than MAX_CROSS crossings (the consumers' general path).
+template <int NW, int STAGES>
+__device__ __noinline__ bool f_resolve_exact(FSmem<NW, STAGES> &sm, int s, i64 S_in, i64 *S_out, int lane)
+{
+    constexpr int NT = NW * 32, RPL = NW;
+    const unsigned char *sb = reinterpret_cast<const unsigned char *>(sm.w[s]);
+    int r0 = 0;
+    i64 S = S_in;
+    for (int round = 0; r0 < NT; round++) {
+        if (round > MAX_CROSS) return false;
+        const int e = (int)(S >> 52);
+        i64 rsum[RPL];
+        if (f_row_sums<NW, STAGES>(sm, s, e, r0, lane, rsum)) return false;
+        i64 carry = S;                                     // state before row 32 i (rows < r0 contribute 0)
+        int found = -1;
+        i64 S_row = 0;
+#pragma unroll
+        for (int i = 0; i < RPL; i++) {
+            if (found >= 0) continue;
+            const int r = i * 32 + lane;
+            const i64 rs = rsum[i];
+            const i64 inc = warp_incl_scan_i64(rs, lane);
+            const i64 end_state = carry + inc, start_state = end_state - rs;
+            const bool leaves = r >= r0 && (int)(end_state >> 52) != e;
+            const unsigned m = __ballot_sync(FULL, leaves);
+            const int fc = m ? __ffs(m) - 1 : 32;
+            if (r >= r0 && lane <= fc) sm.ex[s][r] = start_state;      // rows up to and including the leaving one start here
+            if (m) { found = i * 32 + fc; S_row = __shfl_sync(FULL, start_state, fc); }
+            carry = __shfl_sync(FULL, end_state, 31);
+        }
+        __syncwarp();
+        if (found < 0) { *S_out = carry; return true; }
+        // the row that leaves the binade: true adds, one by one
+        double acc = __longlong_as_double(S_row);
+#pragma unroll
+        for (int c = 0; c < F_IPT / 2; c++) {
+            const double2 v = *reinterpret_cast<const double2 *>(sb + f_swz(found, c));
+            acc = __dadd_rn(acc, v.x);
+            acc = __dadd_rn(acc, v.y);
+        }
+        if (lane == 0) sm.cross[s][found >> 5] |= 1u << (found & 31);
+        __syncwarp();
+        S = __double_as_longlong(acc);
+        r0 = found + 1;
+    }
+    *S_out = S;
+    return true;
+}
+
 // ------------------------------------------------------------------ the kernel
 // resident CTAs per SM that the shared-memory footprint of a variant allows (227 KB per SM)
 constexpr int f_ctas(int nw, int stages) { return nw == 8 ? (stages <= 2 ? 2 : 1) : (stages <= 2 ? 4 : (stages == 3 ? 3 : 2)); }
 
 template <int NW, int STAGES, int MODE>
-__global__ void __launch_bounds__(NW * 32 + 64, f_ctas(NW, STAGES))
+__global__ void __launch_bounds__(NW * 32 + 128, f_ctas(NW, STAGES))
 k_fused(const __grid_constant__ CUtensorMap wmap, const FParams p)
 {
     constexpr int NT = NW * 32, TILE = NT * F_IPT, WIN = NT * F_SPT, RPL = NT / 32;
@@ -520,23 +619,27 @@ k_fused(const __grid_constant__ CUtensorMap wmap, const FParams p)
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) {
-            f_mbar_init(&sm.full_tma[s], 1); f_mbar_init(&sm.summed[s], 1); f_mbar_init(&sm.ready[s], 1); f_mbar_init(&sm.empty[s], NW);
+            f_mbar_init(&sm.full_tma[s], 1); f_mbar_init(&sm.landed[s], 1); f_mbar_init(&sm.summed[s], 1); f_mbar_init(&sm.mapped[s], 1);
+            f_mbar_init(&sm.ready[s], 1); f_mbar_init(&sm.empty[s], NW);
+            sm.lcnt[s] = 0;
         }
+        sm.last_t = -1;
         sm.e_last = 1022;              // binade [0.5, 1): where a normalised running sum spends most of its life
         f_fence_mbar_init();
     }
-    for (int q = tid; q < WIN; q += NT + 64) sm.win[q] = 0;
+    for (int q = tid; q < WIN; q += NT + 128) sm.win[q] = 0;
     __syncthreads();
 
     const double divisor = p.div ? *p.div : 1.0;
 
-    if (wid == NW) {
-        // ============================================================ loader warp
-        // Claims tiles, starts their TMA loads, sums them and publishes the stage-1 AGGREGATE as soon
-        // as the data is there.  It never waits for another CTA, so every tile's sum is published
-        // promptly — a look-back only ever waits for loads, not for somebody else's look-back.
-        // It also forms the row sums of the parity map in the binade the chain warp saw last
-        // (a guess that is right for all but a handful of tiles).
+    if (wid >= NW && wid <= NW + 1) {
+        // ============================================================ loader warps L0, L1
+        // L0 claims tiles and starts their TMA loads.  Both loaders then sum one half of the tile's
+        // rows each; whoever finishes second publishes the stage-1 AGGREGATE.  The loaders never wait
+        // for another CTA, so every tile's sum is published as soon as its data has arrived — a
+        // look-back only ever waits for loads, not for somebody else's look-back.  They also form the
+        // row sums of the parity map in the binade the chain saw last (right for all but a handful of tiles).
+        const int h = wid - NW;
         int q_issue = 0, q_proc = 0, exhausted = 0;
         long long pf[3] = {0, 0, 0}, tk = clock64();
         auto lap = [&](int i) { const long long now = clock64(); pf[i] += now - tk; tk = now; };
@@ -558,6 +661,7 @@ k_fused(const __grid_constant__ CUtensorMap wmap, const FParams p)
                 if (t >= p.T) { exhausted = 1; t = -1; }
                 if (lane == 0) {
                     sm.tile_of[s] = t;
+                    if (t >= 0) f_trace(p, t, 0);
                     if (t >= 0 && p.use_tma) {
                         f_mbar_expect_tx(&sm.full_tma[s], TILE * 8);
                         f_tma_load_2d(sm.w[s], &wmap, 0, t * NT, &sm.full_tma[s]);
@@ -568,45 +672,59 @@ k_fused(const __grid_constant__ CUtensorMap wmap, const FParams p)
             }
             __syncwarp();
         };
-        for (;;) {
-            issue(q_proc == q_issue);
-            lap(0);
+        for (;; q_proc++) {
             const int s = q_proc % STAGES, use = q_proc / STAGES;
+            unsigned char *sb = reinterpret_cast<unsigned char *>(sm.w[s]);
+            if (h == 0) {
+                issue(q_proc == q_issue);
+                lap(0);
+                const int t0 = sm.tile_of[s];
+                if (t0 >= 0) {
+                    if (p.use_tma) {
+                        f_mbar_wait(&sm.full_tma[s], use & 1);
+                        // rows beyond n/16 arrive zero-filled; the last n % 16 weights are fetched by hand
+                        const i64 R = p.n >> 4;
+                        const int rem = (int)(p.n & 15);
+                        if (rem && (R / NT) == t0 && lane < rem) {
+                            const int r = (int)(R - (i64)t0 * NT);
+                            *reinterpret_cast<double *>(sb + f_swz(r, lane >> 1) + (lane & 1) * 8) = p.w[R * 16 + lane];
+                        }
+                    } else {
+                        const i64 j0 = (i64)t0 * TILE;
+                        for (int i = lane; i < TILE; i += 32) {
+                            const i64 j = j0 + i;
+                            const double v = (j < p.n) ? p.w[j] : 0.0;
+                            *reinterpret_cast<double *>(sb + f_swz(i >> 4, (i >> 1) & 7) + (i & 1) * 8) = v;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    sm.eg[s] = *reinterpret_cast<volatile int *>(&sm.e_last);
+                    if (t0 >= 0) f_trace(p, t0, 1);
+                    f_mbar_arrive(&sm.landed[s]);
+                }
+                __syncwarp();
+                lap(1);
+            } else {
+                f_mbar_wait(&sm.landed[s], use & 1);
+            }
             const int t = sm.tile_of[s];
             if (t < 0) {
-                if (lane == 0) f_mbar_arrive(&sm.summed[s]);
+                if (h == 0 && lane == 0) f_mbar_arrive(&sm.summed[s]);
                 break;
             }
-            unsigned char *sb = reinterpret_cast<unsigned char *>(sm.w[s]);
-            if (p.use_tma) {
-                f_mbar_wait(&sm.full_tma[s], use & 1);
-                // rows beyond n/16 arrive zero-filled; the last n % 16 weights are fetched by hand
-                const i64 R = p.n >> 4;
-                const int rem = (int)(p.n & 15);
-                if (rem && (R / NT) == t && lane < rem) {
-                    const int r = (int)(R - (i64)t * NT);
-                    *reinterpret_cast<double *>(sb + f_swz(r, lane >> 1) + (lane & 1) * 8) = p.w[R * 16 + lane];
-                }
-            } else {
-                const i64 j0 = (i64)t * TILE;
-                for (int i = lane; i < TILE; i += 32) {
-                    const i64 j = j0 + i;
-                    const double v = (j < p.n) ? p.w[j] : 0.0;
-                    *reinterpret_cast<double *>(sb + f_swz(i >> 4, (i >> 1) & 7) + (i & 1) * 8) = v;
-                }
-            }
-            __syncwarp();
-            lap(1);
+            if (h == 1 && p.use_tma) f_mbar_wait(&sm.full_tma[s], use & 1);     // already complete: acquires the TMA writes directly
             // tile sum (only the approximate prefix comes from it), validation, optional normalisation,
-            // speculative row sums.  Lane L owns rows L, L + 32, ...: consecutive lanes read
-            // consecutive swizzled rows (conflict-free).
-            const int eg = *reinterpret_cast<volatile int *>(&sm.e_last);
+            // speculative row sums.  Lane L owns rows L, L + 32, ... of this loader's half: consecutive
+            // lanes read consecutive swizzled rows (conflict-free).
+            const int eg = sm.eg[s];
             const i64 gbase = (i64)eg << 52;
             const double G0 = __longlong_as_double(gbase), G1 = __longlong_as_double(gbase + 1);
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             unsigned mx = 0, tie = 0;
 #pragma unroll 2
-            for (int i = 0; i < RPL; i++) {
+            for (int i = h * (RPL / 2); i < (h + 1) * (RPL / 2); i++) {
                 const int r = i * 32 + lane;
                 i64 racc = 0;
 #pragma unroll
@@ -629,7 +747,7 @@ k_fused(const __grid_constant__ CUtensorMap wmap, const FParams p)
             if (p.div) f_fence_proxy_async();              // generic-proxy writes to a stage the TMA engine will refill
             int bad = 0;
             if (mx >= 0x7FF00000u) {                       // negative, inf or nan somewhere (or a harmless -0.0)
-                for (int i = 0; i < RPL; i++)
+                for (int i = h * (RPL / 2); i < (h + 1) * (RPL / 2); i++)
                     for (int c = 0; c < F_IPT / 2; c++) {
                         const double2 v = *reinterpret_cast<const double2 *>(sb + f_swz(i * 32 + lane, c));
                         if (!(v.x >= 0.0) || !(v.y >= 0.0) || isinf(v.x) || isinf(v.y)) bad = 1;
@@ -640,25 +758,33 @@ k_fused(const __grid_constant__ CUtensorMap wmap, const FParams p)
             double tot = (a0 + a1) + (a2 + a3);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
-            if (bad) { tot = 0.0; if (lane == 0) p.hdr->fallback = 1; }
             __syncwarp();
             if (lane == 0) {
-                f_st(p.st1 + t + 1, ((u64)__double_as_longlong(tot) & ~3ull) | ST1_AGG);
-                sm.pre[s].tot = tot; sm.pre[s].bad = bad; sm.pre[s].eg = eg; sm.pre[s].tie = any_tie;
-                f_mbar_arrive(&sm.summed[s]);
+                sm.part[s][h].tot = tot; sm.part[s][h].bad = bad; sm.part[s][h].tie = any_tie;
+                __threadfence_block();
+                if (atomicAdd(&sm.lcnt[s], 1) == 1) {      // the second loader to finish publishes the tile's sum
+                    __threadfence_block();
+                    sm.lcnt[s] = 0;
+                    double tt = sm.part[s][0].tot + sm.part[s][1].tot;
+                    const int tb = sm.part[s][0].bad | sm.part[s][1].bad;
+                    if (tb) { tt = 0.0; p.hdr->fallback = 1; }
+                    f_st(p.st1 + t + 1, ((u64)__double_as_longlong(tt) & ~3ull) | ST1_AGG);
+                    sm.pre[s].tot = tt; sm.pre[s].bad = tb; sm.pre[s].eg = eg; sm.pre[s].tie = sm.part[s][0].tie | sm.part[s][1].tie;
+                    f_trace(p, t, 2);
+                    f_mbar_arrive(&sm.summed[s]);
+                }
             }
-            lap(2);
-            q_proc++;
+            if (h == 0) lap(2);
         }
-        if (p.prof && lane == 0)
+        if (h == 0 && p.prof && lane == 0)
             for (int i = 0; i < 3; i++) atomicAdd(reinterpret_cast<unsigned long long *>(&p.hdr->prof[i]), (unsigned long long)pf[i]);
         return;
     }
-    if (wid == NW + 1) {
-        // ============================================================ chain warp
-        // Resolves both look-backs for the tiles the loader has summed: approximate prefix -> which
-        // binade the tile lives in -> the tile's parity map -> exact state before the tile.
-        long long pf[4] = {0, 0, 0, 0}, tk = clock64();
+    if (wid == NW + 2) {
+        // ============================================================ chain warp C1 (stage 1)
+        // approximate prefix -> which binade the tile lives in -> for a tile deep inside one binade the
+        // parity map D, published as the stage-2 AGGREGATE right away (it never waits for stage 2)
+        long long pf[3] = {0, 0, 0}, tk = clock64();
         auto lap = [&](int i) { const long long now = clock64(); pf[i] += now - tk; tk = now; };
         for (int q = 0;; q++) {
             const int s = q % STAGES, use = q / STAGES;
@@ -666,48 +792,36 @@ k_fused(const __grid_constant__ CUtensorMap wmap, const FParams p)
             lap(0);
             const int t = sm.tile_of[s];
             if (t < 0) {
-                if (lane == 0) { sm.info[s].t = -1; f_mbar_arrive(&sm.ready[s]); }
+                if (lane == 0) f_mbar_arrive(&sm.mapped[s]);
                 break;
             }
             unsigned char *sb = reinterpret_cast<unsigned char *>(sm.w[s]);
+            if (lane == 0) f_trace(p, t, 3);
             const double tot = sm.pre[s].tot;
             const int bad = sm.pre[s].bad, eg = sm.pre[s].eg;
             int any_tie = sm.pre[s].tie;
             const double tp = f_lookback_sum(p, t, lane);
-            if (lane == 0) f_st(p.st1 + t + 1, ((u64)__double_as_longlong(tp + tot) & ~3ull) | ST1_INCL);
+            if (lane == 0) { f_st(p.st1 + t + 1, ((u64)__double_as_longlong(tp + tot) & ~3ull) | ST1_INCL); f_trace(p, t, 4); }
             lap(1);
             int e0;
             const bool ca = clean_add(tp, tp + tot, p.eb, &e0);
-            int mode = bad ? TM_BAD : ((ca || tot == 0.0) ? TM_FAST : TM_SLOW);
-            i64 S_in = 0, lo = 0, cnt = 0;
-            int good = 1;
-            if (mode == TM_FAST && tot == 0.0) {
-                for (int i = 0; i < RPL; i++) sm.ex[s][i * 32 + lane] = 0;
-                any_tie = 0;
-            } else if (mode == TM_FAST && e0 != eg) {
-                // the loader's guess was wrong (first tiles, a new binade): row sums again, in binade e0
-                const i64 base = (i64)e0 << 52;
-                const double B0 = __longlong_as_double(base), B1 = __longlong_as_double(base + 1);
-                unsigned tie = 0;
-#pragma unroll 2
-                for (int i = 0; i < RPL; i++) {
-                    const int r = i * 32 + lane;
-                    i64 racc = 0;
+            int kind = bad ? TK_BAD : ((ca || tot == 0.0) ? TK_CLEAN : TK_CROSS);
+            i64 D = 0;
+            if (kind == TK_CLEAN) {
+                if (tot == 0.0) {
+                    for (int i = 0; i < RPL; i++) sm.ex[s][i * 32 + lane] = 0;
+                    any_tie = 0;
+                } else if (e0 != eg) {
+                    // the loaders' guess was wrong (first tiles, a new binade): row sums again, in binade e0
+                    i64 rsum[RPL];
+                    any_tie = f_row_sums<NW, STAGES>(sm, s, e0, 0, lane, rsum) ? 1 : 0;
 #pragma unroll
-                    for (int c = 0; c < F_IPT / 2; c++) {
-                        const double2 v = *reinterpret_cast<const double2 *>(sb + f_swz(r, c));
-                        const i64 x0 = __double_as_longlong(__dadd_rn(B0, v.x)), x1 = __double_as_longlong(__dadd_rn(B1, v.x));
-                        const i64 y0 = __double_as_longlong(__dadd_rn(B0, v.y)), y1 = __double_as_longlong(__dadd_rn(B1, v.y));
-                        tie |= (((unsigned)x0 + 1u) ^ (unsigned)x1) | (((unsigned)y0 + 1u) ^ (unsigned)y1);
-                        racc += (x0 - base) + (y0 - base);
-                    }
-                    sm.ex[s][r] = racc;
+                    for (int i = 0; i < RPL; i++) sm.ex[s][i * 32 + lane] = rsum[i];
                 }
-                any_tie = __any_sync(FULL, tie != 0);
+                if (tot != 0.0 && lane == 0) sm.e_last = e0;
+                if (any_tie) kind = TK_TIES;               // ties: the general parity maps of the slow path
             }
-            if (mode == TM_FAST && tot != 0.0 && lane == 0) sm.e_last = e0;
-            if (mode == TM_FAST && any_tie) mode = TM_SLOW;      // ties: the general parity maps of the slow path
-            if (mode == TM_FAST) {
+            if (kind == TK_CLEAN) {
                 // exclusive offsets per row (= consumer thread) and the tile's map D
                 __syncwarp();
                 i64 v[RPL], run = 0;
@@ -717,32 +831,71 @@ k_fused(const __grid_constant__ CUtensorMap wmap, const FParams p)
                 const i64 lane_ex = inc - run;
 #pragma unroll
                 for (int j = 0; j < RPL; j++) sm.ex[s][lane * RPL + j] = lane_ex + v[j];
-                const i64 D = __shfl_sync(FULL, inc, 31);
-                if (lane == 0) f_st(p.st2 + t + 1, st2_pack_agg(D, 0));
-                lap(2);
-                S_in = f_lookback_state(p, t, lane);
-                if (lane == 0) {
-                    const i64 S_out = S_in + D;
-                    good = (tot == 0.0) || ((int)(S_in >> 52) == e0 && (int)(S_out >> 52) == e0);
-                    f_st(p.st2 + t + 1, ST2_INCL | (u64)S_out);
-                    f_finish_tile<MODE>(p, t, S_in, S_out, good, lo, cnt);
-                }
-            } else if (mode == TM_BAD) {
-                // invalid weights: the sequential kernel will produce the result; keep the chain moving
-                lap(2);
-                S_in = f_lookback_state(p, t, lane);
-                if (lane == 0) f_st(p.st2 + t + 1, ST2_INCL | (u64)S_in);
-            } else lap(2);
+                D = __shfl_sync(FULL, inc, 31);
+                if (lane == 0) { f_st(p.st2 + t + 1, st2_pack_agg(D, 0)); f_trace(p, t, 5); }
+            }
             __syncwarp();
             if (lane == 0) {
-                sm.info[s].t = t; sm.info[s].mode = mode; sm.info[s].good = good; sm.info[s].e0 = e0;
-                sm.info[s].tp = tp; sm.info[s].S_in = S_in; sm.info[s].lo = lo; sm.info[s].cnt = cnt;
-                f_mbar_arrive(&sm.ready[s]);
+                sm.mid[s].kind = kind; sm.mid[s].e0 = e0; sm.mid[s].tp = tp; sm.mid[s].tot = tot; sm.mid[s].D = D;
+                f_mbar_arrive(&sm.mapped[s]);
             }
-            lap(3);
+            lap(2);
         }
         if (p.prof && lane == 0)
-            for (int i = 0; i < 4; i++) atomicAdd(reinterpret_cast<unsigned long long *>(&p.hdr->prof[3 + i]), (unsigned long long)pf[i]);
+            for (int i = 0; i < 3; i++) atomicAdd(reinterpret_cast<unsigned long long *>(&p.hdr->prof[3 + i]), (unsigned long long)pf[i]);
+        return;
+    }
+    if (wid == NW + 3) {
+        // ============================================================ chain warp C2 (stage 2)
+        // exact state before the tile; tiles that may cross a binade are resolved here, exactly, from
+        // that state (no margins): map arithmetic up to the row that leaves the binade, true adds
+        // inside that row, map arithmetic of the next binade after it
+        long long pf[3] = {0, 0, 0}, tk = clock64();
+        auto lap = [&](int i) { const long long now = clock64(); pf[i] += now - tk; tk = now; };
+        for (int q = 0;; q++) {
+            const int s = q % STAGES, use = q / STAGES;
+            f_mbar_wait(&sm.mapped[s], use & 1);
+            lap(0);
+            const int t = sm.tile_of[s];
+            if (t < 0) {
+                if (lane == 0) { sm.info[s].t = -1; f_mbar_arrive(&sm.ready[s]); }
+                break;
+            }
+            const int kind = sm.mid[s].kind, e0 = sm.mid[s].e0;
+            const double tot = sm.mid[s].tot;
+            const i64 D = sm.mid[s].D;
+            const i64 S_in = f_lookback_state(p, t, lane);
+            lap(1);
+            int mode, good = 1;
+            i64 S_out = S_in, base = 0, lo = 0, cnt = 0;
+            if (lane < NT / 32) sm.cross[s][lane] = 0;
+            if (kind == TK_CLEAN) {
+                S_out = S_in + D;
+                good = (tot == 0.0) || ((int)(S_in >> 52) == e0 && (int)(S_out >> 52) == e0);
+                base = S_in;
+                mode = TM_FAST;
+            } else if (kind == TK_BAD) {
+                mode = TM_BAD;                             // invalid weights: the sequential kernel will produce the result
+            } else if (kind == TK_CROSS && f_resolve_exact<NW, STAGES>(sm, s, S_in, &S_out, lane)) {
+                mode = TM_FAST;                            // ex[] now holds the exact state before every row
+                if (lane == 0) { atomicAdd(&p.hdr->n_unclean, 1); sm.e_last = (int)(S_out >> 52); }
+            } else {
+                mode = TM_SLOW;                            // ties / too many crossings: the consumers' general path publishes
+            }
+            if (lane == 0) {
+                if (mode != TM_SLOW) { f_st(p.st2 + t + 1, ST2_INCL | (u64)S_out); f_trace(p, t, 6); }
+                if (mode == TM_FAST) f_finish_tile<MODE>(p, t, S_in, S_out, good, lo, cnt);
+                sm.info[s].t = t; sm.info[s].mode = mode; sm.info[s].good = good;
+                sm.info[s].tp = __longlong_as_double(S_in); sm.info[s].S_in = S_in; sm.info[s].base = base;
+                sm.info[s].lo = lo; sm.info[s].cnt = cnt;
+                f_trace(p, t, 7);
+            }
+            __syncwarp();
+            if (lane == 0) f_mbar_arrive(&sm.ready[s]);
+            lap(2);
+        }
+        if (p.prof && lane == 0)
+            for (int i = 0; i < 3; i++) atomicAdd(reinterpret_cast<unsigned long long *>(&p.hdr->prof[6 + i]), (unsigned long long)pf[i]);
         return;
     }
 
@@ -759,8 +912,8 @@ k_fused(const __grid_constant__ CUtensorMap wmap, const FParams p)
         const int t = sm.info[s].t;
         if (t < 0) {
             if (p.prof && tid == 0) {
-                atomicAdd(reinterpret_cast<unsigned long long *>(&p.hdr->prof[7]), (unsigned long long)cwait);
-                atomicAdd(reinterpret_cast<unsigned long long *>(&p.hdr->prof[8]), (unsigned long long)cwork);
+                atomicAdd(reinterpret_cast<unsigned long long *>(&p.hdr->prof[9]), (unsigned long long)cwait);
+                atomicAdd(reinterpret_cast<unsigned long long *>(&p.hdr->prof[10]), (unsigned long long)cwork);
             }
             break;
         }
@@ -770,6 +923,7 @@ k_fused(const __grid_constant__ CUtensorMap wmap, const FParams p)
             if (lane == 0) f_mbar_arrive(&sm.empty[s]);
             continue;
         }
+        if (tid == 0) { f_trace(p, t, 8); if (q > 0 && sm.last_t >= 0) f_trace(p, sm.last_t, 9); sm.last_t = t; }
         if (p.use_tma) f_mbar_wait(&sm.full_tma[s], use & 1);       // already complete: acquires the TMA writes directly
         unsigned char *sb = reinterpret_cast<unsigned char *>(sm.w[s]);
         const i64 jthread = (i64)t * TILE + (i64)tid * F_IPT;       // first particle of this thread (local numbering)
@@ -796,14 +950,24 @@ k_fused(const __grid_constant__ CUtensorMap wmap, const FParams p)
             }
             if (mode == TM_FAST) {
                 good = sm.info[s].good; tile_lo = sm.info[s].lo; tile_cnt = sm.info[s].cnt;
-                const i64 base = (i64)sm.info[s].e0 << 52;
-                const double B0 = __longlong_as_double(base);
-                thread_start = sm.info[s].S_in + sm.ex[s][tid];
+                thread_start = sm.info[s].base + sm.ex[s][tid];
                 i64 c = thread_start;
+                if ((sm.cross[s][wid] >> lane) & 1) {
+                    // this row's adds leave the binade of its start state: true adds
 #pragma unroll
-                for (int k = 0; k < F_IPT; k++) {
-                    c += __double_as_longlong(__dadd_rn(B0, w[k])) - base;
-                    cb[k] = c;
+                    for (int k = 0; k < F_IPT; k++) {
+                        c = __double_as_longlong(__dadd_rn(__longlong_as_double(c), w[k]));
+                        cb[k] = c;
+                    }
+                } else {
+                    // every add stays in the binade of the row's start state: bits(S) += d0
+                    const i64 base = (thread_start >> 52) << 52;
+                    const double B0 = __longlong_as_double(base);
+#pragma unroll
+                    for (int k = 0; k < F_IPT; k++) {
+                        c += __double_as_longlong(__dadd_rn(B0, w[k])) - base;
+                        cb[k] = c;
+                    }
                 }
             }
         }
@@ -978,9 +1142,9 @@ __global__ void __launch_bounds__(256) k_fepilogue(FParams p)
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     if (p.prof) {
         const double T = (double)p.T;
-        printf("RSPROF tiles=%d cycles/tile: loader[stage-wait %.0f | tma-wait %.0f | sum-pass %.0f]  chain[wait-summed %.0f | lookback1 %.0f | maps %.0f | lookback2+finish %.0f]  cons[wait-ready %.0f | work %.0f]  slow=%d general=%d\n",
+        printf("RSPROF tiles=%d cycles/tile: L0[stage-wait %.0f | tma-wait %.0f | sum-pass %.0f]  C1[wait-summed %.0f | lookback1 %.0f | maps %.0f]  C2[wait-mapped %.0f | lookback2 %.0f | finish %.0f]  cons[wait-ready %.0f | work %.0f]  crossing=%d slow=%d general=%d\n",
                p.T, hdr->prof[0] / T, hdr->prof[1] / T, hdr->prof[2] / T, hdr->prof[3] / T, hdr->prof[4] / T, hdr->prof[5] / T,
-               hdr->prof[6] / T, hdr->prof[7] / T, hdr->prof[8] / T, hdr->n_slow, hdr->n_general);
+               hdr->prof[6] / T, hdr->prof[7] / T, hdr->prof[8] / T, hdr->prof[9] / T, hdr->prof[10] / T, hdr->n_unclean, hdr->n_slow, hdr->n_general);
     }
     auto write_info = [&](int overflow, int fb) {
         if (p.info) {
@@ -1098,7 +1262,7 @@ int f_launch(const CUtensorMap &map, const FParams &p, cudaStream_t s)
     const int per_sm = ctas_env > 0 ? ctas_env : f_ctas(NW, STAGES);
     int grid = sm_count() * per_sm;
     if (grid > p.T) grid = p.T;
-    kern<<<grid, NW * 32 + 64, smem, s>>>(map, p);
+    kern<<<grid, NW * 32 + 128, smem, s>>>(map, p);
     return check_cuda(cudaGetLastError(), "k_fused launch");
 }
 
@@ -1111,6 +1275,9 @@ int f_launch_mode(int mode, const CUtensorMap &map, const FParams &p, cudaStream
 }
 
 }  // namespace
+
+static unsigned long long *g_trace = nullptr;
+void f_set_trace(void *buf) { g_trace = (unsigned long long *)buf; }
 
 size_t f_carve(int64_t n, unsigned char *base, FParams *p)
 {
@@ -1146,6 +1313,7 @@ int f_run(const FRunArgs &a, cudaStream_t s)
     const int NW = (nw_env == 4) ? 4 : 8;
     p.sleep_ns = f_env_int("BKE_RS_SLEEP", 0);
     p.prof = f_env_int("BKE_RS_PROF", 0);
+    p.trace = g_trace;
     p.lbk = f_env_int("BKE_RS_LBK", 4);
     if (p.lbk < 1) p.lbk = 1;
     if (p.lbk > LBK_MAX) p.lbk = LBK_MAX;

@@ -25,7 +25,7 @@ struct FHeader {
     int pad;
     i64 out_begin;      // first global output position owned by this call
     i64 out_end;        // one past the last
-    i64 prof[10];       // BKE_RS_PROF: cycles summed over CTAs (producer phases 0-5, consumer wait / work)
+    i64 prof[12];       // BKE_RS_PROF: cycles summed over CTAs (producer phases 0-5, consumer wait / work)
 };
 
 struct FParams {
@@ -56,6 +56,7 @@ struct FParams {
     int max_runs;
     int T;
     int sleep_ns;          // back-off between two polls of a status word (0 = spin)
+    unsigned long long *trace;   // debugging: [T][10] global-timer stamps of pipeline events, or NULL
     int prof;              // BKE_RS_PROF=1: per-phase cycle counters, printed by the epilogue kernel
     int lbk;               // status words per lane and look-back round (window = 32 * lbk tiles)
 };
@@ -76,6 +77,7 @@ struct FRunArgs {
 
 size_t f_carve(int64_t n, unsigned char *base, FParams *p);
 int f_run(const FRunArgs &a, cudaStream_t s);
+void f_set_trace(void *buf);
 
 }  // namespace rs
 }  // namespace bke
