@@ -240,33 +240,46 @@ __device__ __forceinline__ i64 f_lookback_state(const FParams &p, int t, int lan
 }
 
 // ------------------------------------------------------------------ shared memory
-enum { TM_FAST = 0, TM_SLOW = 1, TM_BAD = 2 };                       // what the consumers do with a tile
+enum { TM_FAST = 0, TM_SLOW = 1, TM_BAD = 2 };                       // what the consumers do with a tile at emit time
 enum { TK_CLEAN = 0, TK_CROSS = 1, TK_TIES = 2, TK_BAD = 3 };        // what stage 1 found out about it
 constexpr int MAX_CROSS = 24;                                        // crossing rows resolved by the chain warp
+constexpr int RING = 8;                                              // tiles a CTA has between "fronted" and "emitted"
 
-template <int NW, int STAGES>
+// one tile of this CTA on its way from front (sum + map) to emit
+struct FSlot {
+    int t;                  // tile, -1 = end of work
+    int eg;                 // binade the front formed its map in (a guess: the binade the chain saw last)
+    int bad, tie;           // front: invalid weights / an exact tie somewhere
+    double tot;             // front: approximate sum of the tile
+    i64 D;                  // front (or C1, when the guess was wrong): tie-free parity map of the tile in binade eg / e0
+    i64 D1; int tie1, pad1; // front: the same in binade eg + 1 (a running sum only ever moves up)
+    int kind, e0;           // C1
+    int mode, good, cross;  // C2: what emit does; verified; per-row start states are in the crossing pool
+    int pad;
+    i64 S_in, lo, cnt;      // C2: exact state before the tile, its output range
+};
+
+template <int NW>
 struct FSmem {
     static constexpr int NT = NW * 32, TILE = NT * F_IPT, WIN = NT * F_SPT;
-    double w[STAGES][TILE];            // TMA destinations (128-byte swizzle): must stay first, 1024-aligned
-    i64 ex[STAGES][NT];                // fast tiles: parity-map offset of every consumer thread's first particle
+    double wf[TILE];                   // front buffer  \\ TMA destinations (128-byte swizzle): must stay first,
+    double we[TILE];                   // emit buffer   /  1024-aligned
     int win[WIN];                      // output window (all zero between tiles)
+    i64 xrow[NT];                      // crossing pool: exact state before every row of ONE tile that leaves its binade
+    unsigned xmask[NT / 32];           // ... and the rows (consumer threads) that are walked with true adds
+    struct FPart { double tot; i64 D; i64 D1; int tie; int tie1; int bad; int pad; } fpart[2][NW];      // front: per-warp partials (double buffered)
+    i64 warp_i[NW];
     double warp_d[NW];
     SM warp_sm[NW];
     int warp_max[NW];
-    unsigned cross[STAGES][NT / 32];   // rows (consumer threads) whose 16 adds leave their binade: true adds there
-    uint64_t full_tma[STAGES], landed[STAGES], summed[STAGES], mapped[STAGES], ready[STAGES], empty[STAGES];
-    struct Part { double tot; int bad; int tie; } part[STAGES][2];                 // the two loaders' halves
-    int lcnt[STAGES];                  // loaders done with the tile (the second one publishes)
-    int eg[STAGES];                    // binade the loaders' speculative row sums were formed in
-    struct Pre { double tot; int bad; int eg; int tie; int pad; } pre[STAGES];     // loaders -> C1
-    struct Mid { int kind; int e0; double tp; double tot; i64 D; } mid[STAGES];     // C1 -> C2
-    int last_t;                        // trace: the tile the consumers processed last
-    int e_last;                        // binade of the last fast tile the chain warp resolved (the loader's guess)
-    struct Info { int t; int mode; int good; int pad; double tp; i64 S_in; i64 base; i64 lo; i64 cnt; } info[STAGES];
-    int tile_of[STAGES];               // producer-private: tile loaded / loading in each stage (-1 = end of work)
+    uint64_t full_f, empty_f, full_e, empty_e, xfree;
+    uint64_t claimed[RING], fronted[RING], mapped[RING], resolved[RING], freed[RING];
+    FSlot ring[RING];
+    int e_last;                        // binade of the last tile the chain resolved (the front's guess)
+    int last_t;                        // trace: the tile the consumers emitted last
     i64 bc_S_in, bc_lo, bc_cnt;
     int bc_ok, bc_skip;
-    // slow path (tiles with raw elements)
+    // slow path (tiles with ties)
     i64 segstate[RMAX + 1];
     i64 segd[RMAX + 1];
     double wraw[RMAX];
@@ -352,12 +365,12 @@ __device__ __forceinline__ void f_finish_tile(const FParams &p, int t, i64 S_in,
 // Leaves the exact c_j (bit patterns) of the tile in the stage buffer, at the positions of the
 // weights they belong to; returns 1 if the tile verified.  Everything up to the segment export
 // runs BEFORE the exact start state is known; only the walk over <= RMAX segments is serial.
-template <int NW, int STAGES, int MODE>
-__device__ __noinline__ int f_slow_tile(const FParams &p, FSmem<NW, STAGES> &sm, int s, int t)
+template <int NW, int MODE>
+__device__ __noinline__ int f_slow_tile(const FParams &p, FSmem<NW> &sm, int t, i64 S_in_known)
 {
     constexpr int NT = NW * 32;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    unsigned char *sb = reinterpret_cast<unsigned char *>(sm.w[s]);
+    unsigned char *sb = reinterpret_cast<unsigned char *>(sm.we);
     double w[F_IPT];
 #pragma unroll
     for (int c = 0; c < F_IPT / 2; c++) {
@@ -368,7 +381,8 @@ __device__ __noinline__ int f_slow_tile(const FParams &p, FSmem<NW, STAGES> &sm,
 #pragma unroll
     for (int k = 0; k < F_IPT; k++) ssum += w[k];
     double tot;
-    double before = sm.info[s].tp + f_scan_d<NW>(ssum, &tot, sm.warp_d, lane, wid);
+    // the exact state before the tile is known (chain warp C2): it is the "approximate" prefix of the classification
+    double before = __longlong_as_double(S_in_known) + f_scan_d<NW>(ssum, &tot, sm.warp_d, lane, wid);
     SM inc[F_IPT];
     int ek[F_IPT];
     SM run = sm_identity();
@@ -415,7 +429,7 @@ __device__ __noinline__ int f_slow_tile(const FParams &p, FSmem<NW, STAGES> &sm,
     }
     f_bar<NT>();
     if (wid == 0) {
-        const i64 S_in = sm.info[s].S_in;                  // chain warp C2 resolved it before handing the tile over
+        const i64 S_in = S_in_known;
         if (lane == 0) {
             int wbad = 0;
             i64 S_out;
@@ -495,8 +509,8 @@ __device__ __forceinline__ void f_store_cumsum(const FParams &p, i64 j, const i6
 
 // read this thread's F_SPT window slots (and clear them), running maximum, block max-scan:
 // m[i] = marker (local particle index + 1) of the particle that owns slot tid*F_SPT + i
-template <int NW, int STAGES>
-__device__ __forceinline__ void f_window_scan(FSmem<NW, STAGES> &sm, int tid, int lane, int wid, int (&m)[F_SPT])
+template <int NW>
+__device__ __forceinline__ void f_window_scan(FSmem<NW> &sm, int tid, int lane, int wid, int (&m)[F_SPT])
 {
     constexpr int NT = NW * 32;
     int4 *wv = reinterpret_cast<int4 *>(sm.win) + tid * (F_SPT / 4);
@@ -522,57 +536,65 @@ __device__ __forceinline__ void f_window_scan(FSmem<NW, STAGES> &sm, int tid, in
     for (int i = 0; i < F_SPT; i++) m[i] = max(m[i], basem);
 }
 
-// Row sums of the tie-free parity map in binade e for rows >= r0 (lane L owns rows L, L + 32, ...:
-// rs[i] belongs to row 32 i + L; 0 for rows < r0); returns true if any of those rows holds an exact tie.
-template <int NW, int STAGES>
-__device__ __forceinline__ bool f_row_sums(FSmem<NW, STAGES> &sm, int s, int e, int r0, int lane, i64 (&rs)[NW])
+// Row sums of the tie-free parity map of tile t in binade e, read from GLOBAL memory (the rare paths
+// of the chain warps: a wrong binade guess, a tile that leaves its binade).  Lane L owns rows
+// L, L + 32, ...: rs[i] belongs to row 32 i + L (0 for rows < r0); bit i of the result is set when
+// that row holds an exact tie.
+template <int NW>
+__device__ __noinline__ unsigned f_row_sums_g(const FParams &p, int t, int e, int r0, int lane, double divisor, i64 (&rs)[NW])
 {
-    constexpr int RPL = NW;                                // rows per lane (NT / 32)
-    const unsigned char *sb = reinterpret_cast<const unsigned char *>(sm.w[s]);
     const i64 base = (i64)e << 52;
     const double B0 = __longlong_as_double(base), B1 = __longlong_as_double(base + 1);
-    unsigned tie = 0;
+    unsigned ties = 0;
 #pragma unroll
-    for (int i = 0; i < RPL; i++) {
+    for (int i = 0; i < NW; i++) {
         const int r = i * 32 + lane;
         i64 racc = 0;
+        unsigned tie = 0;
         if (r >= r0) {
+            const i64 j0 = (i64)t * (NW * 32 * F_IPT) + (i64)r * F_IPT;
+            double vv[F_IPT];
 #pragma unroll
-            for (int c = 0; c < F_IPT / 2; c++) {
-                const double2 v = *reinterpret_cast<const double2 *>(sb + f_swz(r, c));
-                const i64 x0 = __double_as_longlong(__dadd_rn(B0, v.x)), x1 = __double_as_longlong(__dadd_rn(B1, v.x));
-                const i64 y0 = __double_as_longlong(__dadd_rn(B0, v.y)), y1 = __double_as_longlong(__dadd_rn(B1, v.y));
-                tie |= (((unsigned)x0 + 1u) ^ (unsigned)x1) | (((unsigned)y0 + 1u) ^ (unsigned)y1);   // d1 != d0: an exact tie
-                racc += (x0 - base) + (y0 - base);
+            for (int k = 0; k < F_IPT; k++) vv[k] = (j0 + k < p.n) ? p.w[j0 + k] : 0.0;
+#pragma unroll
+            for (int k = 0; k < F_IPT; k++) {
+                double v = vv[k];
+                if (p.div) v = __ddiv_rn(v, divisor);
+                const i64 x0 = __double_as_longlong(__dadd_rn(B0, v)), x1 = __double_as_longlong(__dadd_rn(B1, v));
+                tie |= ((unsigned)x0 + 1u) ^ (unsigned)x1;             // d1 != d0: an exact tie
+                racc += x0 - base;
             }
         }
         rs[i] = racc;
+        if (tie) ties |= 1u << i;
     }
-    return __any_sync(FULL, tie != 0) != 0;
+    return ties;
 }
 
-// A tile that may leave its binade, resolved from the EXACT state before it (chain warp C2):
-// rows whose adds all stay in the binade of their start state are integer maps; the row that
-// leaves it is walked with true adds; the rows after it are maps of the next binade, and so on.
-// On success sm.ex[s][r] = exact state before row r, sm.cross[s] marks the walked rows, *S_out =
-// state after the tile.  false: ties or more than MAX_CROSS crossings (the consumers' general path).
-template <int NW, int STAGES>
-__device__ __noinline__ bool f_resolve_exact(FSmem<NW, STAGES> &sm, int s, i64 S_in, i64 *S_out, int lane)
+// A tile that may leave its binade, resolved from the EXACT state before it (chain warp C2, weights
+// read from global memory): rows whose adds all stay in the binade of their start state are integer
+// maps; the row that leaves it is walked with true adds; the rows after it are maps of the next
+// binade, and so on.  On success sm.xrow[r] = exact state before row r, sm.xmask marks the walked
+// rows, *S_out = state after the tile.  false: a tie in a mapped row, or more than MAX_CROSS crossings.
+template <int NW>
+__device__ __noinline__ bool f_resolve_exact(const FParams &p, FSmem<NW> &sm, int t, i64 S_in, i64 *S_out, int lane, double divisor)
 {
-    constexpr int NT = NW * 32, RPL = NW;
-    const unsigned char *sb = reinterpret_cast<const unsigned char *>(sm.w[s]);
+    constexpr int NT = NW * 32;
+    if (lane < NT / 32) sm.xmask[lane] = 0;
+    __syncwarp();
     int r0 = 0;
     i64 S = S_in;
     for (int round = 0; r0 < NT; round++) {
         if (round > MAX_CROSS) return false;
         const int e = (int)(S >> 52);
-        i64 rsum[RPL];
-        if (f_row_sums<NW, STAGES>(sm, s, e, r0, lane, rsum)) return false;
+        i64 rsum[NW];
+        const unsigned ties = f_row_sums_g<NW>(p, t, e, r0, lane, divisor, rsum);
         i64 carry = S;                                     // state before row 32 i (rows < r0 contribute 0)
         int found = -1;
         i64 S_row = 0;
+        bool tie_used = false;
 #pragma unroll
-        for (int i = 0; i < RPL; i++) {
+        for (int i = 0; i < NW; i++) {
             if (found >= 0) continue;
             const int r = i * 32 + lane;
             const i64 rs = rsum[i];
@@ -581,21 +603,25 @@ __device__ __noinline__ bool f_resolve_exact(FSmem<NW, STAGES> &sm, int s, i64 S
             const bool leaves = r >= r0 && (int)(end_state >> 52) != e;
             const unsigned m = __ballot_sync(FULL, leaves);
             const int fc = m ? __ffs(m) - 1 : 32;
-            if (r >= r0 && lane <= fc) sm.ex[s][r] = start_state;      // rows up to and including the leaving one start here
+            if (r >= r0 && lane <= fc) sm.xrow[r] = start_state;       // rows up to and including the leaving one start here
+            if (r >= r0 && lane < fc && ((ties >> i) & 1)) tie_used = true;   // a tie in a row that is applied as a map
             if (m) { found = i * 32 + fc; S_row = __shfl_sync(FULL, start_state, fc); }
             carry = __shfl_sync(FULL, end_state, 31);
         }
-        __syncwarp();
+        if (__any_sync(FULL, tie_used)) return false;
         if (found < 0) { *S_out = carry; return true; }
         // the row that leaves the binade: true adds, one by one
         double acc = __longlong_as_double(S_row);
-#pragma unroll
-        for (int c = 0; c < F_IPT / 2; c++) {
-            const double2 v = *reinterpret_cast<const double2 *>(sb + f_swz(found, c));
-            acc = __dadd_rn(acc, v.x);
-            acc = __dadd_rn(acc, v.y);
+        {
+            const i64 j0 = (i64)t * (NT * F_IPT) + (i64)found * F_IPT;
+#pragma unroll 4
+            for (int k = 0; k < F_IPT; k++) {
+                double v = (j0 + k < p.n) ? p.w[j0 + k] : 0.0;
+                if (p.div) v = __ddiv_rn(v, divisor);
+                acc = __dadd_rn(acc, v);
+            }
         }
-        if (lane == 0) sm.cross[s][found >> 5] |= 1u << (found & 31);
+        if (lane == 0) sm.xmask[found >> 5] |= 1u << (found & 31);
         __syncwarp();
         S = __double_as_longlong(acc);
         r0 = found + 1;
@@ -606,292 +632,197 @@ __device__ __noinline__ bool f_resolve_exact(FSmem<NW, STAGES> &sm, int s, i64 S
 
 // ------------------------------------------------------------------ the kernel
 // resident CTAs per SM that the shared-memory footprint of a variant allows (227 KB per SM)
-constexpr int f_ctas(int nw, int stages) { return nw == 8 ? (stages <= 2 ? 2 : 1) : (stages <= 2 ? 4 : (stages == 3 ? 3 : 2)); }
+constexpr int f_ctas(int nw) { return nw == 8 ? 2 : 4; }
 
-template <int NW, int STAGES, int MODE>
-__global__ void __launch_bounds__(NW * 32 + 128, f_ctas(NW, STAGES))
+// Roles inside a CTA (NW consumer warps + 3 helper warps):
+//   consumers  iteration k: FRONT tile k of this CTA (sum, validation, parity map in the guessed
+//              binade -> stage-1 AGGREGATE published at once), then EMIT tile k - DELTA (by then the
+//              chain has resolved its exact start state; its weights come back from L2, not HBM)
+//   L          claims tiles, TMA-loads the front buffer (from HBM) and the emit buffer (from L2)
+//   C1         stage-1 look-back: approximate prefix -> binade -> stage-2 AGGREGATE
+//   C2         stage-2 look-back: exact state before the tile -> INCLUSIVE; tiles that leave their binade
+// The chain (C1, C2) runs DELTA tiles per CTA — several hundred tiles of the grid — ahead of the
+// emit front, so a look-back never stalls the warps that do the work.
+template <int NW, int DELTA, int MODE>
+__global__ void __launch_bounds__(NW * 32 + 128, f_ctas(NW))
 k_fused(const __grid_constant__ CUtensorMap wmap, const FParams p)
 {
-    constexpr int NT = NW * 32, TILE = NT * F_IPT, WIN = NT * F_SPT, RPL = NT / 32;
+    constexpr int NT = NW * 32, TILE = NT * F_IPT, WIN = NT * F_SPT;
+    static_assert(DELTA + 2 <= RING, "ring too small");
     extern __shared__ __align__(1024) unsigned char f_smem_raw[];
-    FSmem<NW, STAGES> &sm = *reinterpret_cast<FSmem<NW, STAGES> *>(f_smem_raw);
+    FSmem<NW> &sm = *reinterpret_cast<FSmem<NW> *>(f_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; s++) {
-            f_mbar_init(&sm.full_tma[s], 1); f_mbar_init(&sm.landed[s], 1); f_mbar_init(&sm.summed[s], 1); f_mbar_init(&sm.mapped[s], 1);
-            f_mbar_init(&sm.ready[s], 1); f_mbar_init(&sm.empty[s], NW);
-            sm.lcnt[s] = 0;
+        f_mbar_init(&sm.full_f, 1); f_mbar_init(&sm.empty_f, NW); f_mbar_init(&sm.full_e, 1); f_mbar_init(&sm.empty_e, NW);
+        f_mbar_init(&sm.xfree, NW);
+        for (int i = 0; i < RING; i++) {
+            f_mbar_init(&sm.claimed[i], 1); f_mbar_init(&sm.fronted[i], 1); f_mbar_init(&sm.mapped[i], 1); f_mbar_init(&sm.resolved[i], 1); f_mbar_init(&sm.freed[i], NW);
         }
-        sm.last_t = -1;
         sm.e_last = 1022;              // binade [0.5, 1): where a normalised running sum spends most of its life
+        sm.last_t = -1;
         f_fence_mbar_init();
     }
     for (int q = tid; q < WIN; q += NT + 128) sm.win[q] = 0;
     __syncthreads();
 
     const double divisor = p.div ? *p.div : 1.0;
+    const bool tail_generic = (p.n & 15) != 0;             // the last tile of a ragged array is staged by hand
 
-    if (wid >= NW && wid <= NW + 1) {
-        // ============================================================ loader warps L0, L1
-        // L0 claims tiles and starts their TMA loads.  Both loaders then sum one half of the tile's
-        // rows each; whoever finishes second publishes the stage-1 AGGREGATE.  The loaders never wait
-        // for another CTA, so every tile's sum is published as soon as its data has arrived — a
-        // look-back only ever waits for loads, not for somebody else's look-back.  They also form the
-        // row sums of the parity map in the binade the chain saw last (right for all but a handful of tiles).
-        const int h = wid - NW;
-        int q_issue = 0, q_proc = 0, exhausted = 0;
-        long long pf[3] = {0, 0, 0}, tk = clock64();
-        auto lap = [&](int i) { const long long now = clock64(); pf[i] += now - tk; tk = now; };
-        // claim tiles (in order) and start their loads while stages are free; `block`: wait for the first
-        auto issue = [&](bool block) {
-            while (!exhausted && q_issue < q_proc + STAGES) {
-                const int s = q_issue % STAGES, use = q_issue / STAGES;
-                if (use > 0) {
-                    if (block) f_mbar_wait(&sm.empty[s], (use - 1) & 1);
-                    else {
-                        int is_free = 0;
-                        if (lane == 0) is_free = f_mbar_try(&sm.empty[s], (use - 1) & 1) ? 1 : 0;
-                        if (!__shfl_sync(FULL, is_free, 0)) break;
-                    }
+    if (wid == NW || wid == NW + 3) {
+        // ============================================================ loader warps: LF (front buffer, from HBM; claims the tiles)
+        // and LE (emit buffer: the same tiles again DELTA iterations later, from L2).  Both block on mbarriers only.
+        auto load_tile = [&](int t, double *dst, uint64_t *full) {
+            if (p.use_tma && !(tail_generic && t == p.T - 1)) {
+                if (lane == 0) { f_mbar_expect_tx(full, TILE * 8); f_tma_load_2d(dst, &wmap, 0, t * NT, full); }
+            } else {
+                unsigned char *sb = reinterpret_cast<unsigned char *>(dst);
+                const i64 j0 = (i64)t * TILE;
+                for (int i = lane; i < TILE; i += 32) {
+                    const i64 j = j0 + i;
+                    const double v = (j < p.n) ? p.w[j] : 0.0;
+                    *reinterpret_cast<double *>(sb + f_swz(i >> 4, (i >> 1) & 7) + (i & 1) * 8) = v;
                 }
+                f_fence_proxy_async();                     // generic-proxy writes to a buffer the TMA engine also fills
+                __syncwarp();
+                if (lane == 0) f_mbar_arrive(full);
+            }
+        };
+        if (wid == NW) {
+            for (int kf = 0;; kf++) {
+                // front load kf: its ring slot must be free, the front buffer consumed
+                const int slot = kf % RING, use = kf / RING;
+                if (use > 0) f_mbar_wait(&sm.freed[slot], (use - 1) & 1);
+                if (kf > 0) f_mbar_wait(&sm.empty_f, (kf - 1) & 1);
                 int t = 0;
                 if (lane == 0) t = atomicAdd(&p.hdr->tile_counter, 1);
                 t = __shfl_sync(FULL, t, 0);
-                if (t >= p.T) { exhausted = 1; t = -1; }
+                if (t >= p.T) t = -1;
                 if (lane == 0) {
-                    sm.tile_of[s] = t;
+                    sm.ring[slot].eg = *reinterpret_cast<volatile int *>(&sm.e_last);
+                    sm.ring[slot].t = t;
                     if (t >= 0) f_trace(p, t, 0);
-                    if (t >= 0 && p.use_tma) {
-                        f_mbar_expect_tx(&sm.full_tma[s], TILE * 8);
-                        f_tma_load_2d(sm.w[s], &wmap, 0, t * NT, &sm.full_tma[s]);
-                    }
-                }
-                q_issue++;
-                block = false;
-            }
-            __syncwarp();
-        };
-        for (;; q_proc++) {
-            const int s = q_proc % STAGES, use = q_proc / STAGES;
-            unsigned char *sb = reinterpret_cast<unsigned char *>(sm.w[s]);
-            if (h == 0) {
-                issue(q_proc == q_issue);
-                lap(0);
-                const int t0 = sm.tile_of[s];
-                if (t0 >= 0) {
-                    if (p.use_tma) {
-                        f_mbar_wait(&sm.full_tma[s], use & 1);
-                        // rows beyond n/16 arrive zero-filled; the last n % 16 weights are fetched by hand
-                        const i64 R = p.n >> 4;
-                        const int rem = (int)(p.n & 15);
-                        if (rem && (R / NT) == t0 && lane < rem) {
-                            const int r = (int)(R - (i64)t0 * NT);
-                            *reinterpret_cast<double *>(sb + f_swz(r, lane >> 1) + (lane & 1) * 8) = p.w[R * 16 + lane];
-                        }
-                    } else {
-                        const i64 j0 = (i64)t0 * TILE;
-                        for (int i = lane; i < TILE; i += 32) {
-                            const i64 j = j0 + i;
-                            const double v = (j < p.n) ? p.w[j] : 0.0;
-                            *reinterpret_cast<double *>(sb + f_swz(i >> 4, (i >> 1) & 7) + (i & 1) * 8) = v;
-                        }
-                    }
                 }
                 __syncwarp();
-                if (lane == 0) {
-                    sm.eg[s] = *reinterpret_cast<volatile int *>(&sm.e_last);
-                    if (t0 >= 0) f_trace(p, t0, 1);
-                    f_mbar_arrive(&sm.landed[s]);
-                }
-                __syncwarp();
-                lap(1);
-            } else {
-                f_mbar_wait(&sm.landed[s], use & 1);
+                if (lane == 0) f_mbar_arrive(&sm.claimed[slot]);       // LE may read the slot's tile
+                if (t < 0) { if (lane == 0) f_mbar_arrive(&sm.full_f); break; }      // end of work travels down the pipeline
+                load_tile(t, sm.wf, &sm.full_f);
             }
-            const int t = sm.tile_of[s];
-            if (t < 0) {
-                if (h == 0 && lane == 0) f_mbar_arrive(&sm.summed[s]);
-                break;
+        } else {
+            for (int ke = 0;; ke++) {
+                const int slot = ke % RING, use = ke / RING;
+                f_mbar_wait(&sm.claimed[slot], use & 1);
+                const int t = sm.ring[slot].t;
+                if (t < 0) break;
+                if (ke > 0) f_mbar_wait(&sm.empty_e, (ke - 1) & 1);
+                load_tile(t, sm.we, &sm.full_e);
             }
-            if (h == 1 && p.use_tma) f_mbar_wait(&sm.full_tma[s], use & 1);     // already complete: acquires the TMA writes directly
-            // tile sum (only the approximate prefix comes from it), validation, optional normalisation,
-            // speculative row sums.  Lane L owns rows L, L + 32, ... of this loader's half: consecutive
-            // lanes read consecutive swizzled rows (conflict-free).
-            const int eg = sm.eg[s];
-            const i64 gbase = (i64)eg << 52;
-            const double G0 = __longlong_as_double(gbase), G1 = __longlong_as_double(gbase + 1);
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            unsigned mx = 0, tie = 0;
-#pragma unroll 2
-            for (int i = h * (RPL / 2); i < (h + 1) * (RPL / 2); i++) {
-                const int r = i * 32 + lane;
-                i64 racc = 0;
-#pragma unroll
-                for (int c = 0; c < F_IPT / 2; c++) {
-                    double2 v = *reinterpret_cast<const double2 *>(sb + f_swz(r, c));
-                    if (p.div) {
-                        // fused normalisation: w / S, the same IEEE division NumPy's `w / w.sum()` performs
-                        v.x = __ddiv_rn(v.x, divisor); v.y = __ddiv_rn(v.y, divisor);
-                        *reinterpret_cast<double2 *>(sb + f_swz(r, c)) = v;
-                    }
-                    if (c & 1) { a2 += v.x; a3 += v.y; } else { a0 += v.x; a1 += v.y; }
-                    mx = max(mx, max((unsigned)__double2hiint(v.x), (unsigned)__double2hiint(v.y)));
-                    const i64 x0 = __double_as_longlong(__dadd_rn(G0, v.x)), x1 = __double_as_longlong(__dadd_rn(G1, v.x));
-                    const i64 y0 = __double_as_longlong(__dadd_rn(G0, v.y)), y1 = __double_as_longlong(__dadd_rn(G1, v.y));
-                    tie |= (((unsigned)x0 + 1u) ^ (unsigned)x1) | (((unsigned)y0 + 1u) ^ (unsigned)y1);   // d1 != d0: an exact tie
-                    racc += (x0 - gbase) + (y0 - gbase);
-                }
-                sm.ex[s][r] = racc;
-            }
-            if (p.div) f_fence_proxy_async();              // generic-proxy writes to a stage the TMA engine will refill
-            int bad = 0;
-            if (mx >= 0x7FF00000u) {                       // negative, inf or nan somewhere (or a harmless -0.0)
-                for (int i = h * (RPL / 2); i < (h + 1) * (RPL / 2); i++)
-                    for (int c = 0; c < F_IPT / 2; c++) {
-                        const double2 v = *reinterpret_cast<const double2 *>(sb + f_swz(i * 32 + lane, c));
-                        if (!(v.x >= 0.0) || !(v.y >= 0.0) || isinf(v.x) || isinf(v.y)) bad = 1;
-                    }
-            }
-            bad = __any_sync(FULL, bad);
-            const int any_tie = __any_sync(FULL, tie != 0);
-            double tot = (a0 + a1) + (a2 + a3);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
-            __syncwarp();
-            if (lane == 0) {
-                sm.part[s][h].tot = tot; sm.part[s][h].bad = bad; sm.part[s][h].tie = any_tie;
-                __threadfence_block();
-                if (atomicAdd(&sm.lcnt[s], 1) == 1) {      // the second loader to finish publishes the tile's sum
-                    __threadfence_block();
-                    sm.lcnt[s] = 0;
-                    double tt = sm.part[s][0].tot + sm.part[s][1].tot;
-                    const int tb = sm.part[s][0].bad | sm.part[s][1].bad;
-                    if (tb) { tt = 0.0; p.hdr->fallback = 1; }
-                    f_st(p.st1 + t + 1, ((u64)__double_as_longlong(tt) & ~3ull) | ST1_AGG);
-                    sm.pre[s].tot = tt; sm.pre[s].bad = tb; sm.pre[s].eg = eg; sm.pre[s].tie = sm.part[s][0].tie | sm.part[s][1].tie;
-                    f_trace(p, t, 2);
-                    f_mbar_arrive(&sm.summed[s]);
-                }
-            }
-            if (h == 0) lap(2);
         }
-        if (h == 0 && p.prof && lane == 0)
-            for (int i = 0; i < 3; i++) atomicAdd(reinterpret_cast<unsigned long long *>(&p.hdr->prof[i]), (unsigned long long)pf[i]);
         return;
     }
-    if (wid == NW + 2) {
+    if (wid == NW + 1) {
         // ============================================================ chain warp C1 (stage 1)
         // approximate prefix -> which binade the tile lives in -> for a tile deep inside one binade the
-        // parity map D, published as the stage-2 AGGREGATE right away (it never waits for stage 2)
+        // stage-2 AGGREGATE (its parity map D), published right away (C1 never waits for stage 2)
         long long pf[3] = {0, 0, 0}, tk = clock64();
         auto lap = [&](int i) { const long long now = clock64(); pf[i] += now - tk; tk = now; };
-        for (int q = 0;; q++) {
-            const int s = q % STAGES, use = q / STAGES;
-            f_mbar_wait(&sm.summed[s], use & 1);
+        for (int k = 0;; k++) {
+            const int si = k % RING, use = k / RING;
+            FSlot &sl = sm.ring[si];
+            f_mbar_wait(&sm.fronted[si], use & 1);
             lap(0);
-            const int t = sm.tile_of[s];
+            const int t = sl.t;
             if (t < 0) {
-                if (lane == 0) f_mbar_arrive(&sm.mapped[s]);
+                if (lane == 0) f_mbar_arrive(&sm.mapped[si]);
                 break;
             }
-            unsigned char *sb = reinterpret_cast<unsigned char *>(sm.w[s]);
             if (lane == 0) f_trace(p, t, 3);
-            const double tot = sm.pre[s].tot;
-            const int bad = sm.pre[s].bad, eg = sm.pre[s].eg;
-            int any_tie = sm.pre[s].tie;
+            const double tot = sl.tot;
+            const int bad = sl.bad, eg = sl.eg;
+            int any_tie = sl.tie;
+            i64 D = sl.D;
             const double tp = f_lookback_sum(p, t, lane);
             if (lane == 0) { f_st(p.st1 + t + 1, ((u64)__double_as_longlong(tp + tot) & ~3ull) | ST1_INCL); f_trace(p, t, 4); }
             lap(1);
             int e0;
             const bool ca = clean_add(tp, tp + tot, p.eb, &e0);
             int kind = bad ? TK_BAD : ((ca || tot == 0.0) ? TK_CLEAN : TK_CROSS);
-            i64 D = 0;
             if (kind == TK_CLEAN) {
-                if (tot == 0.0) {
-                    for (int i = 0; i < RPL; i++) sm.ex[s][i * 32 + lane] = 0;
-                    any_tie = 0;
-                } else if (e0 != eg) {
-                    // the loaders' guess was wrong (first tiles, a new binade): row sums again, in binade e0
-                    i64 rsum[RPL];
-                    any_tie = f_row_sums<NW, STAGES>(sm, s, e0, 0, lane, rsum) ? 1 : 0;
+                if (tot == 0.0) { D = 0; any_tie = 0; }
+                else if (e0 == eg + 1) { D = sl.D1; any_tie = sl.tie1; }      // the front's second candidate
+                else if (e0 != eg) {
+                    // the front's guess was wrong (first tiles, a new binade): the map again, in binade e0
+                    i64 rsum[NW];
+                    any_tie = f_row_sums_g<NW>(p, t, e0, 0, lane, divisor, rsum) != 0;
+                    any_tie = __any_sync(FULL, any_tie);
+                    D = 0;
 #pragma unroll
-                    for (int i = 0; i < RPL; i++) sm.ex[s][i * 32 + lane] = rsum[i];
+                    for (int i = 0; i < NW; i++) D += rsum[i];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) D += __shfl_xor_sync(FULL, D, o);
                 }
                 if (tot != 0.0 && lane == 0) sm.e_last = e0;
                 if (any_tie) kind = TK_TIES;               // ties: the general parity maps of the slow path
             }
-            if (kind == TK_CLEAN) {
-                // exclusive offsets per row (= consumer thread) and the tile's map D
-                __syncwarp();
-                i64 v[RPL], run = 0;
-#pragma unroll
-                for (int j = 0; j < RPL; j++) { const i64 x = sm.ex[s][lane * RPL + j]; v[j] = run; run += x; }
-                const i64 inc = warp_incl_scan_i64(run, lane);
-                const i64 lane_ex = inc - run;
-#pragma unroll
-                for (int j = 0; j < RPL; j++) sm.ex[s][lane * RPL + j] = lane_ex + v[j];
-                D = __shfl_sync(FULL, inc, 31);
-                if (lane == 0) { f_st(p.st2 + t + 1, st2_pack_agg(D, 0)); f_trace(p, t, 5); }
-            }
+            if (kind == TK_CLEAN && lane == 0) { f_st(p.st2 + t + 1, st2_pack_agg(D, 0)); f_trace(p, t, 5); }
+            if (lane == 0) { sl.kind = kind; sl.e0 = e0; sl.D = D; }
             __syncwarp();
-            if (lane == 0) {
-                sm.mid[s].kind = kind; sm.mid[s].e0 = e0; sm.mid[s].tp = tp; sm.mid[s].tot = tot; sm.mid[s].D = D;
-                f_mbar_arrive(&sm.mapped[s]);
-            }
+            if (lane == 0) f_mbar_arrive(&sm.mapped[si]);
             lap(2);
         }
         if (p.prof && lane == 0)
             for (int i = 0; i < 3; i++) atomicAdd(reinterpret_cast<unsigned long long *>(&p.hdr->prof[3 + i]), (unsigned long long)pf[i]);
         return;
     }
-    if (wid == NW + 3) {
+    if (wid == NW + 2) {
         // ============================================================ chain warp C2 (stage 2)
-        // exact state before the tile; tiles that may cross a binade are resolved here, exactly, from
-        // that state (no margins): map arithmetic up to the row that leaves the binade, true adds
-        // inside that row, map arithmetic of the next binade after it
+        // exact state before the tile; tiles that may leave their binade are resolved here, exactly,
+        // from that state (no margins)
         long long pf[3] = {0, 0, 0}, tk = clock64();
         auto lap = [&](int i) { const long long now = clock64(); pf[i] += now - tk; tk = now; };
-        for (int q = 0;; q++) {
-            const int s = q % STAGES, use = q / STAGES;
-            f_mbar_wait(&sm.mapped[s], use & 1);
+        int xuse = 0;
+        for (int k = 0;; k++) {
+            const int si = k % RING, use = k / RING;
+            FSlot &sl = sm.ring[si];
+            f_mbar_wait(&sm.mapped[si], use & 1);
             lap(0);
-            const int t = sm.tile_of[s];
+            const int t = sl.t;
             if (t < 0) {
-                if (lane == 0) { sm.info[s].t = -1; f_mbar_arrive(&sm.ready[s]); }
+                if (lane == 0) f_mbar_arrive(&sm.resolved[si]);
                 break;
             }
-            const int kind = sm.mid[s].kind, e0 = sm.mid[s].e0;
-            const double tot = sm.mid[s].tot;
-            const i64 D = sm.mid[s].D;
+            const int kind = sl.kind, e0 = sl.e0;
+            const double tot = sl.tot;
+            const i64 D = sl.D;
             const i64 S_in = f_lookback_state(p, t, lane);
             lap(1);
-            int mode, good = 1;
-            i64 S_out = S_in, base = 0, lo = 0, cnt = 0;
-            if (lane < NT / 32) sm.cross[s][lane] = 0;
+            int mode, good = 1, cross = 0;
+            i64 S_out = S_in, lo = 0, cnt = 0;
             if (kind == TK_CLEAN) {
                 S_out = S_in + D;
                 good = (tot == 0.0) || ((int)(S_in >> 52) == e0 && (int)(S_out >> 52) == e0);
-                base = S_in;
                 mode = TM_FAST;
             } else if (kind == TK_BAD) {
                 mode = TM_BAD;                             // invalid weights: the sequential kernel will produce the result
-            } else if (kind == TK_CROSS && f_resolve_exact<NW, STAGES>(sm, s, S_in, &S_out, lane)) {
-                mode = TM_FAST;                            // ex[] now holds the exact state before every row
-                if (lane == 0) { atomicAdd(&p.hdr->n_unclean, 1); sm.e_last = (int)(S_out >> 52); }
             } else {
                 mode = TM_SLOW;                            // ties / too many crossings: the consumers' general path publishes
+                if (kind == TK_CROSS) {
+                    if (xuse > 0) f_mbar_wait(&sm.xfree, (xuse - 1) & 1);       // the pool's previous tile has been emitted
+                    if (f_resolve_exact<NW>(p, sm, t, S_in, &S_out, lane, divisor)) {
+                        mode = TM_FAST; cross = 1; xuse++;
+                        if (lane == 0) { atomicAdd(&p.hdr->n_unclean, 1); sm.e_last = (int)(S_out >> 52); }
+                    }
+                }
             }
+            // a failed resolve leaves the pool unused: keep xfree's phase in step by not counting the use
             if (lane == 0) {
                 if (mode != TM_SLOW) { f_st(p.st2 + t + 1, ST2_INCL | (u64)S_out); f_trace(p, t, 6); }
                 if (mode == TM_FAST) f_finish_tile<MODE>(p, t, S_in, S_out, good, lo, cnt);
-                sm.info[s].t = t; sm.info[s].mode = mode; sm.info[s].good = good;
-                sm.info[s].tp = __longlong_as_double(S_in); sm.info[s].S_in = S_in; sm.info[s].base = base;
-                sm.info[s].lo = lo; sm.info[s].cnt = cnt;
+                sl.mode = mode; sl.good = good; sl.cross = cross; sl.S_in = S_in; sl.lo = lo; sl.cnt = cnt;
                 f_trace(p, t, 7);
             }
             __syncwarp();
-            if (lane == 0) f_mbar_arrive(&sm.ready[s]);
+            if (lane == 0) f_mbar_arrive(&sm.resolved[si]);
             lap(2);
         }
         if (p.prof && lane == 0)
@@ -900,83 +831,185 @@ k_fused(const __grid_constant__ CUtensorMap wmap, const FParams p)
     }
 
     // ================================================================ consumer warps
-    // Fast tiles arrive with everything resolved (exact start state, output range): no global wait.
     const i64 out_begin = p.hdr->out_begin;
     const double Nd = (double)p.ng;
-    long long cwait = 0, cwork = 0, ctk = clock64();
-    for (int q = 0;; q++) {
-        const int s = q % STAGES, use = q / STAGES;
-        { const long long now = clock64(); cwork += now - ctk; ctk = now; }
-        f_mbar_wait(&sm.ready[s], use & 1);
-        { const long long now = clock64(); cwait += now - ctk; ctk = now; }
-        const int t = sm.info[s].t;
-        if (t < 0) {
-            if (p.prof && tid == 0) {
-                atomicAdd(reinterpret_cast<unsigned long long *>(&p.hdr->prof[9]), (unsigned long long)cwait);
-                atomicAdd(reinterpret_cast<unsigned long long *>(&p.hdr->prof[10]), (unsigned long long)cwork);
+    long long cwait = 0, cfront = 0, cemit = 0, ctk = clock64();
+    auto clap = [&](long long &acc) { const long long now = clock64(); acc += now - ctk; ctk = now; };
+    bool front_done = false;
+    for (int k = 0;; k++) {
+        // ------------------------------------------------------------ FRONT tile k of this CTA
+        if (!front_done) {
+            f_mbar_wait(&sm.full_f, k & 1);
+            clap(cwait);
+            FSlot &sl = sm.ring[k % RING];
+            const int t = sl.t;
+            if (t < 0) {
+                front_done = true;
+                if (tid == 0) f_mbar_arrive(&sm.fronted[k % RING]);
+            } else {
+                const unsigned char *sb = reinterpret_cast<const unsigned char *>(sm.wf);
+                double w[F_IPT];
+#pragma unroll
+                for (int c = 0; c < F_IPT / 2; c++) {
+                    const double2 v = *reinterpret_cast<const double2 *>(sb + f_swz(tid, c));
+                    w[2 * c] = v.x; w[2 * c + 1] = v.y;
+                }
+                const int eg = sl.eg;
+                const i64 gbase = (i64)eg << 52, hbase = (i64)(eg + 1) << 52;
+                const double G0 = __longlong_as_double(gbase), G1 = __longlong_as_double(gbase + 1);
+                const double H0 = __longlong_as_double(hbase), H1 = __longlong_as_double(hbase + 1);
+                double a0 = 0.0, a1 = 0.0;
+                i64 d = 0, dh = 0;
+                unsigned mx = 0, tie = 0, tieh = 0;
+#pragma unroll
+                for (int i = 0; i < F_IPT; i++) {
+                    if (p.div) w[i] = __ddiv_rn(w[i], divisor);        // fused normalisation: w / S (IEEE division, as NumPy's w / w.sum())
+                    if (i & 1) a1 += w[i]; else a0 += w[i];
+                    mx = max(mx, (unsigned)__double2hiint(w[i]));
+                    const i64 x0 = __double_as_longlong(__dadd_rn(G0, w[i])), x1 = __double_as_longlong(__dadd_rn(G1, w[i]));
+                    tie |= ((unsigned)x0 + 1u) ^ (unsigned)x1;         // d1 != d0: an exact tie
+                    d += x0 - gbase;
+                    const i64 y0 = __double_as_longlong(__dadd_rn(H0, w[i])), y1 = __double_as_longlong(__dadd_rn(H1, w[i]));
+                    tieh |= ((unsigned)y0 + 1u) ^ (unsigned)y1;
+                    dh += y0 - hbase;
+                }
+                // the front buffer is free once every lane of this warp has its weights
+                __syncwarp();
+                if (lane == 0) f_mbar_arrive(&sm.empty_f);
+                int bad = 0;
+                if (mx >= 0x7FF00000u) {                   // negative, inf or nan (or a harmless -0.0)
+#pragma unroll
+                    for (int i = 0; i < F_IPT; i++) if (!(w[i] >= 0.0) || isinf(w[i])) bad = 1;
+                }
+                double tot = a0 + a1;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    tot += __shfl_xor_sync(FULL, tot, o);
+                    d += __shfl_xor_sync(FULL, d, o);
+                    dh += __shfl_xor_sync(FULL, dh, o);
+                }
+                const int wtie = __any_sync(FULL, tie != 0), wtieh = __any_sync(FULL, tieh != 0), wbad = __any_sync(FULL, bad);
+                if (lane == 0) {
+                    sm.fpart[k & 1][wid].tot = tot; sm.fpart[k & 1][wid].D = d; sm.fpart[k & 1][wid].D1 = dh;
+                    sm.fpart[k & 1][wid].tie = wtie; sm.fpart[k & 1][wid].tie1 = wtieh; sm.fpart[k & 1][wid].bad = wbad;
+                }
+                f_bar<NT>();
+                if (tid == 0) {
+                    double tt = 0.0; i64 D = 0, Dh = 0; int ttie = 0, ttieh = 0, tbad = 0;
+#pragma unroll
+                    for (int i = 0; i < NW; i++) {
+                        tt += sm.fpart[k & 1][i].tot; D += sm.fpart[k & 1][i].D; Dh += sm.fpart[k & 1][i].D1;
+                        ttie |= sm.fpart[k & 1][i].tie; ttieh |= sm.fpart[k & 1][i].tie1; tbad |= sm.fpart[k & 1][i].bad;
+                    }
+                    if (tbad) { tt = 0.0; p.hdr->fallback = 1; }
+                    f_st(p.st1 + t + 1, ((u64)__double_as_longlong(tt) & ~3ull) | ST1_AGG);
+                    sl.tot = tt; sl.D = D; sl.tie = ttie; sl.D1 = Dh; sl.tie1 = ttieh; sl.bad = tbad;
+                    f_trace(p, t, 2);
+                    f_mbar_arrive(&sm.fronted[k % RING]);
+                }
             }
-            break;
+            clap(cfront);
         }
-        const int mode = sm.info[s].mode;
-        if (mode == TM_BAD) {
-            __syncwarp();
-            if (lane == 0) f_mbar_arrive(&sm.empty[s]);
-            continue;
-        }
-        if (tid == 0) { f_trace(p, t, 8); if (q > 0 && sm.last_t >= 0) f_trace(p, sm.last_t, 9); sm.last_t = t; }
-        if (p.use_tma) f_mbar_wait(&sm.full_tma[s], use & 1);       // already complete: acquires the TMA writes directly
-        unsigned char *sb = reinterpret_cast<unsigned char *>(sm.w[s]);
+        if (k < DELTA) continue;
+        // ------------------------------------------------------------ EMIT tile k - DELTA of this CTA
+        const int m_idx = k - DELTA, si = m_idx % RING;
+        FSlot &sl = sm.ring[si];
+        f_mbar_wait(&sm.resolved[si], (m_idx / RING) & 1);
+        const int t = sl.t;
+        if (t < 0) break;
+        f_mbar_wait(&sm.full_e, m_idx & 1);
+        clap(cwait);
+        const int mode = sl.mode, cross = sl.cross;
+        int good = sl.good;
+        const i64 S_in = sl.S_in;
+        i64 tile_lo = sl.lo, tile_cnt = sl.cnt;
+        if (tid == 0) { f_trace(p, t, 8); if (sm.last_t >= 0) f_trace(p, sm.last_t, 9); sm.last_t = t; }
+        unsigned char *sb = reinterpret_cast<unsigned char *>(sm.we);
         const i64 jthread = (i64)t * TILE + (i64)tid * F_IPT;       // first particle of this thread (local numbering)
         i64 cb[F_IPT];
-        i64 thread_start;                                   // exact state before this thread's first particle
-        i64 tile_lo, tile_cnt;
-        int good;
-        if (mode == TM_FAST || p.wnorm_out) {
+        i64 thread_start = 0;                               // exact state before this thread's first particle
+        if (mode == TM_BAD) {
+            __syncwarp();
+            if (lane == 0) { f_mbar_arrive(&sm.empty_e); f_mbar_arrive(&sm.freed[si]); }
+            clap(cemit);
+            continue;
+        }
+        if (mode == TM_FAST) {
             double w[F_IPT];
 #pragma unroll
             for (int c = 0; c < F_IPT / 2; c++) {
                 const double2 v = *reinterpret_cast<const double2 *>(sb + f_swz(tid, c));
                 w[2 * c] = v.x; w[2 * c + 1] = v.y;
             }
-            if (p.wnorm_out) {                              // the producer left the normalised weights in the stage
-                double *o = p.wnorm_out + jthread;
-                if (jthread + F_IPT <= p.n && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+            if (p.div) {
 #pragma unroll
-                    for (int k = 0; k < F_IPT; k += 2) *reinterpret_cast<double2 *>(o + k) = make_double2(w[k], w[k + 1]);
-                } else {
+                for (int i = 0; i < F_IPT; i++) w[i] = __ddiv_rn(w[i], divisor);
+                if (p.wnorm_out) {
+                    double *o = p.wnorm_out + jthread;
+                    if (jthread + F_IPT <= p.n && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
 #pragma unroll
-                    for (int k = 0; k < F_IPT; k++) if (jthread + k < p.n) o[k] = w[k];
+                        for (int i = 0; i < F_IPT; i += 2) *reinterpret_cast<double2 *>(o + i) = make_double2(w[i], w[i + 1]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < F_IPT; i++) if (jthread + i < p.n) o[i] = w[i];
+                    }
                 }
             }
-            if (mode == TM_FAST) {
-                good = sm.info[s].good; tile_lo = sm.info[s].lo; tile_cnt = sm.info[s].cnt;
-                thread_start = sm.info[s].base + sm.ex[s][tid];
+            if (!cross) {
+                // every add of the tile stays in the binade of S_in: bits(S) += d0; block scan of the thread totals
+                const i64 base = (S_in >> 52) << 52;
+                const double B0 = __longlong_as_double(base);
+                i64 acc = 0;
+#pragma unroll
+                for (int i = 0; i < F_IPT; i++) {
+                    acc += __double_as_longlong(__dadd_rn(B0, w[i])) - base;
+                    cb[i] = acc;
+                }
+                const i64 inc = warp_incl_scan_i64(acc, lane);
+                if (lane == 31) sm.warp_i[wid] = inc;
+                __syncwarp();
+                if (lane == 0) { f_mbar_arrive(&sm.empty_e); f_mbar_arrive(&sm.freed[si]); }
+                f_bar<NT>();
+                i64 ex = inc - acc;
+#pragma unroll
+                for (int i = 0; i < NW; i++) { const i64 v = sm.warp_i[i]; if (i < wid) ex += v; }
+                thread_start = S_in + ex;
+#pragma unroll
+                for (int i = 0; i < F_IPT; i++) cb[i] += thread_start;
+            } else {
+                // the chain left the exact state before every row in the crossing pool
+                thread_start = sm.xrow[tid];
+                const bool walk = (sm.xmask[wid] >> lane) & 1;
+                __syncwarp();
+                if (lane == 0) { f_mbar_arrive(&sm.empty_e); f_mbar_arrive(&sm.freed[si]); f_mbar_arrive(&sm.xfree); }
                 i64 c = thread_start;
-                if ((sm.cross[s][wid] >> lane) & 1) {
+                if (walk) {
                     // this row's adds leave the binade of its start state: true adds
 #pragma unroll
-                    for (int k = 0; k < F_IPT; k++) {
-                        c = __double_as_longlong(__dadd_rn(__longlong_as_double(c), w[k]));
-                        cb[k] = c;
-                    }
+                    for (int i = 0; i < F_IPT; i++) { c = __double_as_longlong(__dadd_rn(__longlong_as_double(c), w[i])); cb[i] = c; }
                 } else {
-                    // every add stays in the binade of the row's start state: bits(S) += d0
                     const i64 base = (thread_start >> 52) << 52;
                     const double B0 = __longlong_as_double(base);
 #pragma unroll
-                    for (int k = 0; k < F_IPT; k++) {
-                        c += __double_as_longlong(__dadd_rn(B0, w[k])) - base;
-                        cb[k] = c;
-                    }
+                    for (int i = 0; i < F_IPT; i++) { c += __double_as_longlong(__dadd_rn(B0, w[i])) - base; cb[i] = c; }
                 }
             }
-        }
-        if (mode == TM_FAST) {
-            // the stage is free once this warp holds everything it needs in registers
-            __syncwarp();
-            if (lane == 0) f_mbar_arrive(&sm.empty[s]);
         } else {
-            good = f_slow_tile<NW, STAGES, MODE>(p, sm, s, t);
+            // general path (ties): needs the normalised weights in the buffer
+            if (p.div) {
+#pragma unroll
+                for (int c = 0; c < F_IPT / 2; c++) {
+                    double2 v = *reinterpret_cast<const double2 *>(sb + f_swz(tid, c));
+                    v.x = __ddiv_rn(v.x, divisor); v.y = __ddiv_rn(v.y, divisor);
+                    *reinterpret_cast<double2 *>(sb + f_swz(tid, c)) = v;
+                    if (p.wnorm_out) {
+                        if (jthread + 2 * c < p.n) p.wnorm_out[jthread + 2 * c] = v.x;
+                        if (jthread + 2 * c + 1 < p.n) p.wnorm_out[jthread + 2 * c + 1] = v.y;
+                    }
+                }
+                f_bar<NT>();
+            }
+            good = f_slow_tile<NW, MODE>(p, sm, t, S_in);
 #pragma unroll
             for (int c = 0; c < F_IPT / 2; c++) {
                 const longlong2 v = *reinterpret_cast<const longlong2 *>(sb + f_swz(tid, c));
@@ -989,10 +1022,10 @@ k_fused(const __grid_constant__ CUtensorMap wmap, const FParams p)
             }
             tile_lo = sm.bc_lo; tile_cnt = sm.bc_cnt;
             __syncwarp();
-            if (lane == 0) { f_fence_proxy_async(); f_mbar_arrive(&sm.empty[s]); }
+            if (lane == 0) { f_fence_proxy_async(); f_mbar_arrive(&sm.empty_e); f_mbar_arrive(&sm.freed[si]); }
         }
-        if (!good) continue;
-        if (MODE == F_CUMSUM) { f_store_cumsum(p, jthread, cb); continue; }
+        if (!good) { f_bar<NT>(); clap(cemit); continue; }
+        if (MODE == F_CUMSUM) { f_store_cumsum(p, jthread, cb); f_bar<NT>(); clap(cemit); continue; }
 
         // ---- output range end of every particle, relative to tile_lo: hv[k] = #{positions < c_k} - tile_lo
         int hv[F_IPT], hv_prev;
@@ -1009,17 +1042,17 @@ k_fused(const __grid_constant__ CUtensorMap wmap, const FParams p)
                 return min(__double2int_rz(fl), n_m1) - lo_m1;                // floor(v) + 1 - tile_lo
             };
 #pragma unroll
-            for (int k = 0; k < F_IPT; k++) hv[k] = count1(cb[k], 1u << k);
+            for (int i = 0; i < F_IPT; i++) hv[i] = count1(cb[i], 1u << i);
             hv_prev = count1(thread_start, 1u << F_IPT);
             if (slow) {
 #pragma unroll
-                for (int k = 0; k < F_IPT; k++)
-                    if (slow & (1u << k)) hv[k] = (int)(f_count_below<MODE>(p, __longlong_as_double(cb[k])) - tile_lo);
+                for (int i = 0; i < F_IPT; i++)
+                    if (slow & (1u << i)) hv[i] = (int)(f_count_below<MODE>(p, __longlong_as_double(cb[i])) - tile_lo);
                 if (slow & (1u << F_IPT)) hv_prev = (int)(f_count_below<MODE>(p, __longlong_as_double(thread_start)) - tile_lo);
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < F_IPT; k++) hv[k] = (int)(f_count_below<MODE>(p, __longlong_as_double(cb[k])) - tile_lo);
+            for (int i = 0; i < F_IPT; i++) hv[i] = (int)(f_count_below<MODE>(p, __longlong_as_double(cb[i])) - tile_lo);
             hv_prev = (int)(f_count_below<MODE>(p, __longlong_as_double(thread_start)) - tile_lo);
         }
 
@@ -1032,14 +1065,14 @@ k_fused(const __grid_constant__ CUtensorMap wmap, const FParams p)
             const int total = (int)tile_cnt + mis;
             int l = hv_prev + mis;
 #pragma unroll
-            for (int k = 0; k < F_IPT; k++) {
-                const int h = hv[k] + mis;
-                if (h > l) sm.win[l] = tid * F_IPT + k + 1;
+            for (int i = 0; i < F_IPT; i++) {
+                const int h = hv[i] + mis;
+                if (h > l) sm.win[l] = tid * F_IPT + i + 1;
                 l = h;
             }
             f_bar<NT>();
             int m[F_SPT];
-            f_window_scan<NW, STAGES>(sm, tid, lane, wid, m);
+            f_window_scan<NW>(sm, tid, lane, wid, m);
             const int s0 = tid * F_SPT;
             int *dst = p.idx + (rel_lo - mis) + s0;
             if (s0 >= mis && s0 + F_SPT <= total) {
@@ -1051,7 +1084,8 @@ k_fused(const __grid_constant__ CUtensorMap wmap, const FParams p)
                 for (int i = 0; i < F_SPT; i++)
                     if (s0 + i >= mis && s0 + i < total) dst[i] = base_j + m[i];
             }
-            continue;      // the next tile's first barrier separates these window reads from its marker writes
+            clap(cemit);
+            continue;      // the next barrier separates these window reads from the next tile's marker writes
         }
         // general expansion: several windows, runs of BIGRUN or more copies go to the fill kernel
         if (tid == 0) atomicAdd(&p.hdr->n_general, 1);
@@ -1063,12 +1097,12 @@ k_fused(const __grid_constant__ CUtensorMap wmap, const FParams p)
             {
                 int l = hv_prev;
 #pragma unroll
-                for (int k = 0; k < F_IPT; k++) {
-                    const int h = hv[k];
+                for (int i = 0; i < F_IPT; i++) {
+                    const int h = hv[i];
                     if (l <= cs && cs < h && h - cs >= BIGRUN) {
                         sm.bc_skip = h;
                         const int r = atomicAdd(&p.hdr->n_runs, 1);
-                        if (r < p.max_runs) p.runs[r] = Run{tile_lo + cs, tile_lo + h, base_j + tid * F_IPT + k + 1, 0};
+                        if (r < p.max_runs) p.runs[r] = Run{tile_lo + cs, tile_lo + h, base_j + tid * F_IPT + i + 1, 0};
                         else p.hdr->fallback = 1;
                     }
                     l = h;
@@ -1081,25 +1115,31 @@ k_fused(const __grid_constant__ CUtensorMap wmap, const FParams p)
             {
                 int l = hv_prev;
 #pragma unroll
-                for (int k = 0; k < F_IPT; k++) {
-                    const int h = hv[k];
+                for (int i = 0; i < F_IPT; i++) {
+                    const int h = hv[i];
                     const int a0 = max(l, cs);
-                    if (h > a0 && a0 < ce) sm.win[a0 - cs] = tid * F_IPT + k + 1;
+                    if (h > a0 && a0 < ce) sm.win[a0 - cs] = tid * F_IPT + i + 1;
                     l = h;
                 }
             }
             f_bar<NT>();
             int m[F_SPT];
-            f_window_scan<NW, STAGES>(sm, tid, lane, wid, m);
+            f_window_scan<NW>(sm, tid, lane, wid, m);
 #pragma unroll
             for (int i = 0; i < F_SPT; i++) {
-                const int sl = tid * F_SPT + i;
-                if (sl < ce - cs) f_put_index(p, out_begin, tile_lo + cs + sl, base_j + m[i]);
+                const int sl2 = tid * F_SPT + i;
+                if (sl2 < ce - cs) f_put_index(p, out_begin, tile_lo + cs + sl2, base_j + m[i]);
             }
             f_bar<NT>();
             cs = ce;
         }
         f_bar<NT>();
+        clap(cemit);
+    }
+    if (p.prof && tid == 0) {
+        atomicAdd(reinterpret_cast<unsigned long long *>(&p.hdr->prof[9]), (unsigned long long)cwait);
+        atomicAdd(reinterpret_cast<unsigned long long *>(&p.hdr->prof[10]), (unsigned long long)cfront);
+        atomicAdd(reinterpret_cast<unsigned long long *>(&p.hdr->prof[11]), (unsigned long long)cemit);
     }
 }
 
@@ -1142,9 +1182,9 @@ __global__ void __launch_bounds__(256) k_fepilogue(FParams p)
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     if (p.prof) {
         const double T = (double)p.T;
-        printf("RSPROF tiles=%d cycles/tile: L0[stage-wait %.0f | tma-wait %.0f | sum-pass %.0f]  C1[wait-summed %.0f | lookback1 %.0f | maps %.0f]  C2[wait-mapped %.0f | lookback2 %.0f | finish %.0f]  cons[wait-ready %.0f | work %.0f]  crossing=%d slow=%d general=%d\n",
-               p.T, hdr->prof[0] / T, hdr->prof[1] / T, hdr->prof[2] / T, hdr->prof[3] / T, hdr->prof[4] / T, hdr->prof[5] / T,
-               hdr->prof[6] / T, hdr->prof[7] / T, hdr->prof[8] / T, hdr->prof[9] / T, hdr->prof[10] / T, hdr->n_unclean, hdr->n_slow, hdr->n_general);
+printf("RSPROF tiles=%d cycles/tile: C1[wait-fronted %.0f | lookback1 %.0f | map %.0f]  C2[wait-mapped %.0f | lookback2 %.0f | finish %.0f]  cons[wait %.0f | front %.0f | emit %.0f]  crossing=%d slow=%d general=%d\n",
+               p.T, hdr->prof[3] / T, hdr->prof[4] / T, hdr->prof[5] / T, hdr->prof[6] / T, hdr->prof[7] / T, hdr->prof[8] / T,
+               hdr->prof[9] / T, hdr->prof[10] / T, hdr->prof[11] / T, hdr->n_unclean, hdr->n_slow, hdr->n_general);
     }
     auto write_info = [&](int overflow, int fb) {
         if (p.info) {
@@ -1246,11 +1286,11 @@ int f_env_int(const char *name, int dflt)
     return v ? atoi(v) : dflt;
 }
 
-template <int NW, int STAGES, int MODE>
+template <int NW, int DELTA, int MODE>
 int f_launch(const CUtensorMap &map, const FParams &p, cudaStream_t s)
 {
-    auto kern = k_fused<NW, STAGES, MODE>;
-    const int smem = (int)sizeof(FSmem<NW, STAGES>);
+    auto kern = k_fused<NW, DELTA, MODE>;
+    const int smem = (int)sizeof(FSmem<NW>);
     static bool configured[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1259,19 +1299,19 @@ int f_launch(const CUtensorMap &map, const FParams &p, cudaStream_t s)
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     const int ctas_env = f_env_int("BKE_RS_CTAS", 0);
-    const int per_sm = ctas_env > 0 ? ctas_env : f_ctas(NW, STAGES);
+    const int per_sm = ctas_env > 0 ? ctas_env : f_ctas(NW);
     int grid = sm_count() * per_sm;
     if (grid > p.T) grid = p.T;
     kern<<<grid, NW * 32 + 128, smem, s>>>(map, p);
     return check_cuda(cudaGetLastError(), "k_fused launch");
 }
 
-template <int NW, int STAGES>
+template <int NW, int DELTA>
 int f_launch_mode(int mode, const CUtensorMap &map, const FParams &p, cudaStream_t s)
 {
-    if (mode == F_CUMSUM) return f_launch<NW, STAGES, F_CUMSUM>(map, p, s);
-    if (mode == F_STRAT) return f_launch<NW, STAGES, F_STRAT>(map, p, s);
-    return f_launch<NW, STAGES, F_SYS>(map, p, s);
+    if (mode == F_CUMSUM) return f_launch<NW, DELTA, F_CUMSUM>(map, p, s);
+    if (mode == F_STRAT) return f_launch<NW, DELTA, F_STRAT>(map, p, s);
+    return f_launch<NW, DELTA, F_SYS>(map, p, s);
 }
 
 }  // namespace
@@ -1346,9 +1386,10 @@ int f_run(const FRunArgs &a, cudaStream_t s)
     k_finit<<<init_blocks, 256, 0, s>>>(p);
     int rc;
     const int mode = a.cumsum_out ? F_CUMSUM : (a.U ? F_STRAT : F_SYS);
-    const int st = f_env_int("BKE_RS_STAGES", F_STAGES);
-    if (NW == 4) rc = st <= 2 ? f_launch_mode<4, 2>(mode, map, p, s) : (st == 3 ? f_launch_mode<4, 3>(mode, map, p, s) : f_launch_mode<4, 4>(mode, map, p, s));
-    else rc = st <= 2 ? f_launch_mode<8, 2>(mode, map, p, s) : f_launch_mode<8, 3>(mode, map, p, s);
+    // BKE_RS_STAGES = DELTA: how many tiles per CTA the front (sum, map, chain) runs ahead of the emit
+    const int st = f_env_int("BKE_RS_STAGES", 3);
+    if (NW == 4) rc = st <= 2 ? f_launch_mode<4, 2>(mode, map, p, s) : (st == 3 ? f_launch_mode<4, 3>(mode, map, p, s) : f_launch_mode<4, 5>(mode, map, p, s));
+    else rc = st <= 2 ? f_launch_mode<8, 2>(mode, map, p, s) : (st == 3 ? f_launch_mode<8, 3>(mode, map, p, s) : f_launch_mode<8, 5>(mode, map, p, s));
     if (rc != BKE_OK) return rc;
     k_fepilogue<<<sm_count() * 4, 256, 0, s>>>(p);
     return check_cuda(cudaGetLastError(), "resample launch");

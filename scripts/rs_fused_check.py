@@ -46,7 +46,7 @@ def main():
     quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
     print(torch.cuda.get_device_name(0), flush=True)
     rng = np.random.default_rng(0)
-    for nw, st in (("8", "2"), ("4", "3"), ("8", "3"), ("4", "2"), ("4", "4")):
+    for nw, st in (("8", "3"), ("4", "3"), ("8", "2"), ("8", "5")):
         os.environ["BKE_RS_WARPS"] = nw
         os.environ["BKE_RS_STAGES"] = st
         nw = nw + "/" + st

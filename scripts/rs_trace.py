@@ -30,6 +30,7 @@ plan.systematic(w, 0.0763)
 torch.cuda.synchronize()
 lib.bke_debug_resample_trace(None)
 a = tr.cpu().numpy().reshape(T, 10).astype(np.float64)
+a[:, 1] = a[:, 0]          # "landed" is no longer recorded
 t0 = a[:, 0].min()
 a = (a - t0) / 1e3          # microseconds
 ok = (a > -1).all(axis=1) & (a[:, 6] > 0)
