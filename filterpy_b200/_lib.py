@@ -23,6 +23,7 @@ EXPORTED_SYMBOLS = [
     "bke_kf_step", "bke_kf_batch_filter", "bke_ukf_step",
     "bke_resample_workspace_bytes", "bke_systematic_resample", "bke_stratified_resample",
     "bke_weights_sum", "bke_weights_scale", "bke_resample_shard", "bke_resample_normalized",
+    "bke_resample_composite_bytes", "bke_resample_shard_compose", "bke_resample_compose_carry",
     "bke_merwe_sigma_points", "bke_unscented_transform",
     "bke_kf_rts_smoother", "bke_ukf_rts_smoother", "bke_mm_probabilities", "bke_mm_mix", "bke_mm_estimate", "bke_cumsum_exact", "bke_searchsorted", "bke_multinomial_resample", "bke_gather_rows",
 ]
@@ -193,6 +194,12 @@ def load():
     lib.bke_weights_sum.restype = ctypes.c_int
     lib.bke_weights_scale.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.bke_weights_scale.restype = ctypes.c_int
+    lib.bke_resample_composite_bytes.argtypes = []
+    lib.bke_resample_composite_bytes.restype = c_size_t
+    lib.bke_resample_shard_compose.argtypes = [ctypes.POINTER(ResampleShardArgs), c_void_p, c_void_p]
+    lib.bke_resample_shard_compose.restype = ctypes.c_int
+    lib.bke_resample_compose_carry.argtypes = [c_int32, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.bke_resample_compose_carry.restype = ctypes.c_int
     lib.bke_resample_shard.argtypes = [ctypes.POINTER(ResampleShardArgs), c_void_p]
     lib.bke_resample_shard.restype = ctypes.c_int
     lib.bke_merwe_sigma_points.argtypes = [c_int64, c_int32, c_int32, c_double, c_double, c_double,

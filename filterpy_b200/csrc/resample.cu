@@ -476,22 +476,13 @@ __device__ __forceinline__ SM tile_el(const Ws &ws, int t)
     return m;
 }
 
-template <bool STRAT>
-__global__ void __launch_bounds__(CHAIN_THREADS) k_chain(Params p)
+// Segmented exclusive scan of the tile maps (restart after every unclean tile): afterwards
+// run_*[t] = composite of the clean tiles since the last unclean tile before t, run_cnt[t] = number of
+// unclean tiles before t, ord2tile[i] = i-th unclean tile.  One CTA of CHAIN_THREADS threads.
+__device__ __forceinline__ void chain_scan(const Ws &ws, SM *wtot, int &bad)
 {
-    __shared__ SM wtot[CHAIN_THREADS / 32];
-    __shared__ Slot s_slots[CHAIN_BATCH];
-    __shared__ double s_w[TILE];
-    __shared__ SM s_rm[CHAIN_BATCH];
-    __shared__ i64 s_S;
-    __shared__ int s_bad;
-    const Ws &ws = p.ws;
-    if (ws.hdr->fallback) return;
     const int T = ws.T;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_bad = 0;
-    int bad = 0;
-    // ---- segmented exclusive scan of the tile maps (restart after every unclean tile) ----------
     const int per = ((T + CHAIN_THREADS - 1) / CHAIN_THREADS) * 32;
     const int a = min(T, wid * per), b = min(T, a + per);
     SM carry_m = sm_identity();
@@ -543,6 +534,27 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain(Params p)
     }
     __threadfence_block();
     __syncthreads();
+}
+
+template <bool STRAT>
+__global__ void __launch_bounds__(CHAIN_THREADS) k_chain(Params p)
+{
+    __shared__ SM wtot[CHAIN_THREADS / 32];
+    __shared__ Slot s_slots[CHAIN_BATCH];
+    __shared__ double s_w[TILE];
+    __shared__ SM s_rm[CHAIN_BATCH];
+    __shared__ i64 s_S;
+    __shared__ int s_bad;
+    const Ws &ws = p.ws;
+    if (ws.hdr->fallback) return;
+    const int T = ws.T;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_bad = 0;
+    int bad = 0;
+    chain_scan(ws, wtot, bad);
+    constexpr int PF = 4;
+    const int per = ((T + CHAIN_THREADS - 1) / CHAIN_THREADS) * 32;
+    const int a = min(T, wid * per), b = min(T, a + per);
     // ---- sequential part: one thread walks the tiles that contain raw elements.  Their slot data
     // is staged into shared memory by the whole block first (a dependent chain of global loads
     // would cost ~1 us per hop), CHAIN_BATCH tiles at a time.
@@ -646,6 +658,79 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain(Params p)
         if (s_bad) { ws.hdr->fallback = 1; ws.hdr->chain_bad = 1; }
         else if (p.cumsum_last) *p.cumsum_last = __longlong_as_double(ws.S_in[T]);    // exact sum after this call's particles
     }
+}
+
+// ------------------------------------------------------------------ multi-GPU: the shard's composite
+// What a LATER shard needs from this one is the map "exact running sum before the shard -> exact
+// running sum after it".  It is not a single parity map (the shard may cross binades), but a short
+// list: MAP entries (composites of clean stretches) and RAW entries (elements applied by a true
+// add), in order.  It depends only on passes A-C (approximate carry), so every rank forms it at
+// once; an all-gather of the lists lets rank r derive its exact carry locally — no rank waits for
+// another rank's chain (SURVEY §7 hard part 2).
+constexpr int COMP_MAX = 1000;
+struct CompEntry { int type; int k; int t; int pad; i64 d; };      // type 0 = MAP (k, t, d), 1 = RAW (d = bits of w)
+struct Composite { int n; int bad; int pad[2]; CompEntry e[COMP_MAX]; };
+
+__global__ void __launch_bounds__(CHAIN_THREADS) k_compose(Params p, Composite *out)
+{
+    __shared__ SM wtot[CHAIN_THREADS / 32];
+    const Ws &ws = p.ws;
+    if (threadIdx.x == 0) { out->n = 0; out->bad = ws.hdr->fallback ? 1 : 0; }
+    if (ws.hdr->fallback) return;
+    int bad = 0;
+    chain_scan(ws, wtot, bad);
+    __threadfence_block();
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const int T = ws.T;
+    const int U = ws.hdr->n_unclean + ws.hdr->n_seq;
+    int n = 0;
+    bool cbad = ws.hdr->n_unclean > UMAX || ws.hdr->n_seq > 0;       // dense raw zones cannot be summarised: serial hand-over
+    auto push_map = [&](int k, int t, i64 d) {
+        if (k == K_ID) return;
+        if (k == K_POISON || n >= COMP_MAX) { cbad = true; return; }
+        out->e[n++] = CompEntry{0, k, t, 0, d};
+    };
+    for (int i = 0; i < U && !cbad; i++) {
+        const int tile = ws.ord2tile[i];
+        push_map(ws.run_k[tile], ws.run_t[tile], ws.run_d[tile]);
+        const Slot *sl = &ws.slots[ws.tile_slot[tile]];
+        for (int q = 0; q <= sl->nraw && !cbad; q++) {
+            if (sl->segk[q] >= 0) push_map(sl->segk[q], sl->segt[q], sl->segd[q]);
+            if (q < sl->nraw) {
+                if (n >= COMP_MAX) cbad = true;
+                else out->e[n++] = CompEntry{1, 0, 0, 0, __double_as_longlong(sl->wraw[q])};
+            }
+        }
+    }
+    if (!cbad) {
+        const SM el = tile_el(ws, T - 1);
+        if (el.cnt == 0) {                                   // the shard ends with clean tiles
+            const SM tail = combine(SM{ws.run_d[T - 1], ws.run_t[T - 1], 0, ws.run_k[T - 1]}, el);
+            push_map(tail.k, tail.t, tail.d);
+        }
+    }
+    out->n = n;
+    out->bad = (cbad || bad) ? 1 : 0;
+}
+
+// exact running sum before shard `n_before`: the composites of the earlier shards applied in order to 0
+__global__ void k_compose_carry(int n_before, const Composite *comps, double *carry, int *status)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    i64 S = 0;
+    int bad = 0;
+    for (int r = 0; r < n_before; r++) {
+        const Composite *c = comps + r;
+        if (c->bad) bad = 1;
+        for (int i = 0; i < c->n && !bad; i++) {
+            const CompEntry e = c->e[i];
+            if (e.type == 0) S = apply_bits(S, e.d, e.t, e.k, &bad);
+            else S = __double_as_longlong(__dadd_rn(__longlong_as_double(S), __longlong_as_double(e.d)));
+        }
+    }
+    *carry = __longlong_as_double(S);
+    if (status) *status = bad;
 }
 
 // ------------------------------------------------------------------ pass E: emit indexes
@@ -902,6 +987,230 @@ __global__ void __launch_bounds__(BLOCK, 2) k_emit_fast(Params p)
         for (int k = 0; k < IPT; k++) cbits[k] += S_in + ex;
         if (p.cumsum_out) { store_cumsum(p, t, cbits); continue; }
         emit_tile<STRAT>(p, sm, t, S_in, cbits);
+    }
+}
+
+
+// ------------------------------------------------------------------ pass E, second generation: TMA-staged marker / max-scan emit
+// The tiles pass C marked SLOT_FAST (clean, tie-free, one binade): c_j = S_in + prefix sum of
+// rne(w_j / ulp).  CTA = 8 consumer warps + 1 loader warp; the loader pulls the next tile into shared
+// memory with ONE 2-D TMA copy (128-byte swizzle: thread t reads its 16 consecutive weights with
+// conflict-free LDS.128) while the consumers work on the current one.  Expansion: every particle with
+// >= 1 copies stores (local index + 1) at its first output slot of a zeroed window, a max-scan over the
+// slots fills the runs (no divergent copy loop) and every thread leaves with 16-byte stores of 20
+// consecutive indexes.  (The same consumer code is the emit phase of the experimental single-pass
+// kernel, csrc/resample_fused.cu.)
+constexpr int E2_NW = 8, E2_NT = E2_NW * 32, E2_SPT = 20, E2_WIN = E2_NT * E2_SPT, E2_STAGES = 2;
+static_assert(E2_NT * IPT == TILE, "the second-generation emit uses the tile size of passes A-D");
+
+struct Emit2Shared {
+    double w[E2_STAGES][TILE];         // TMA destinations (128-byte swizzle): must stay first, 1024-aligned
+    int win[E2_WIN];                   // output window (all zero between tiles)
+    i64 warp_tot[E2_NW];
+    int warp_max[E2_NW];
+    uint64_t full[E2_STAGES], empty[E2_STAGES];
+    int skip;
+};
+
+template <bool STRAT>
+__global__ void __launch_bounds__(E2_NT + 32, 2) k_emit2(const __grid_constant__ CUtensorMap wmap, Params p)
+{
+    constexpr int NT = E2_NT, NW = E2_NW, WIN = E2_WIN, SPT = E2_SPT;
+    extern __shared__ __align__(1024) unsigned char e2_smem[];
+    Emit2Shared &sm = *reinterpret_cast<Emit2Shared *>(e2_smem);
+    const Ws &ws = p.ws;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < E2_STAGES; s++) { f_mbar_init(&sm.full[s], 1); f_mbar_init(&sm.empty[s], NW); }
+        f_fence_mbar_init();
+    }
+    for (int q = tid; q < WIN; q += NT + 32) sm.win[q] = 0;
+    __syncthreads();
+    if (ws.hdr->fallback) return;
+    const int T = ws.T;
+    if (wid == NW) {
+        // loader warp: tiles blockIdx.x, blockIdx.x + gridDim.x, ... ; tiles of the slow list are not loaded
+        int q = 0;
+        for (int t = blockIdx.x; t < T; t += gridDim.x) {
+            if (ws.tile_slot[t] != SLOT_FAST) continue;
+            const int s = q % E2_STAGES, use = q / E2_STAGES;
+            if (use > 0) f_mbar_wait(&sm.empty[s], (use - 1) & 1);
+            if (lane == 0) { f_mbar_expect_tx(&sm.full[s], TILE * 8); f_tma_load_2d(sm.w[s], &wmap, 0, t * NT, &sm.full[s]); }
+            q++;
+        }
+        return;
+    }
+    const i64 out_begin = ws.hdr->out_begin;
+    const double Nd = (double)p.ng;
+    int q = 0;
+    for (int t = blockIdx.x; t < T; t += gridDim.x) {
+        if (ws.tile_slot[t] != SLOT_FAST) continue;                           // the general kernel owns this tile
+        const int s = q % E2_STAGES, use = q / E2_STAGES;
+        q++;
+        const i64 S_in = ws.S_in[t];
+        const int tk = ws.tile_k[t];
+        f_mbar_wait(&sm.full[s], use & 1);
+        const unsigned char *sb = reinterpret_cast<const unsigned char *>(sm.w[s]);
+        const i64 base = (i64)(tk >= 0 ? tk : 0) << 52;
+        const double B0 = __longlong_as_double(base);
+        i64 cb[IPT];
+        i64 acc = 0;
+#pragma unroll
+        for (int c = 0; c < IPT / 2; c++) {
+            const double2 v = *reinterpret_cast<const double2 *>(sb + f_swz(tid, c));
+            acc += __double_as_longlong(__dadd_rn(B0, v.x)) - base; cb[2 * c] = acc;
+            acc += __double_as_longlong(__dadd_rn(B0, v.y)) - base; cb[2 * c + 1] = acc;
+        }
+        const i64 inc = warp_incl_scan_i64(acc, lane);
+        if (lane == 31) sm.warp_tot[wid] = inc;
+        __syncwarp();
+        if (lane == 0) f_mbar_arrive(&sm.empty[s]);                           // this warp holds its weights in registers
+        f_bar<NT>();
+        i64 ex = inc - acc, D = 0;
+#pragma unroll
+        for (int i = 0; i < NW; i++) { const i64 v = sm.warp_tot[i]; if (i < wid) ex += v; D += v; }
+        const i64 thread_start = S_in + ex;
+#pragma unroll
+        for (int i = 0; i < IPT; i++) cb[i] += thread_start;
+        // the tile's output range (every thread: the values are uniform, no broadcast needed)
+        const i64 tile_lo = count_below<STRAT>(p, __longlong_as_double(S_in));
+        const i64 tile_cnt = count_below<STRAT>(p, __longlong_as_double(S_in + D)) - tile_lo;
+        if (t == T - 1 && tid == 0) {
+            i64 O1 = tile_lo + tile_cnt;
+            if (p.is_last && O1 < p.ng) {                       // resampling.py:145 would raise IndexError
+                ws.hdr->overflow = (int)(p.ng - O1 > 0x7fffffff ? 0x7fffffff : p.ng - O1);
+                const int r = atomicAdd(&ws.hdr->n_runs, 1);
+                if (r < ws.max_runs) ws.runs[r] = Run{O1, p.ng, (int)(p.ng - 1), 0};
+                O1 = p.ng;
+            }
+            ws.hdr->out_end = O1;
+            if (p.out_range) { p.out_range[0] = out_begin; p.out_range[1] = O1; }
+        }
+        // ---- output range end of every particle, relative to tile_lo: hv[k] = #{positions < c_k} - tile_lo
+        int hv[IPT], hv_prev;
+        if (!STRAT) {
+            // branch-free: floor(c N - u) + 1 away from integers; the rare near-integer cases are redone exactly
+            const double u = p.u, half_m = 0.5 - p.tau;
+            const int n_m1 = (int)p.ng - 1, lo_m1 = (int)tile_lo - 1;
+            unsigned slow = 0;
+            auto count1 = [&](i64 cbits, unsigned bit) -> int {
+                const double v = fma(__longlong_as_double(cbits), Nd, -u);    // >= -u > -1
+                const double fl = floor(v);
+                const double fr = v - fl;                                     // exact, in [0, 1)
+                if (!(fabs(fr - 0.5) < half_m)) slow |= bit;                  // within tau of an integer
+                return min(__double2int_rz(fl), n_m1) - lo_m1;                // floor(v) + 1 - tile_lo
+            };
+#pragma unroll
+            for (int i = 0; i < IPT; i++) hv[i] = count1(cb[i], 1u << i);
+            hv_prev = count1(thread_start, 1u << IPT);
+            if (slow) {
+#pragma unroll
+                for (int i = 0; i < IPT; i++)
+                    if (slow & (1u << i)) hv[i] = (int)(count_below<STRAT>(p, __longlong_as_double(cb[i])) - tile_lo);
+                if (slow & (1u << IPT)) hv_prev = (int)(count_below<STRAT>(p, __longlong_as_double(thread_start)) - tile_lo);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < IPT; i++) hv[i] = (int)(count_below<STRAT>(p, __longlong_as_double(cb[i])) - tile_lo);
+            hv_prev = (int)(count_below<STRAT>(p, __longlong_as_double(thread_start)) - tile_lo);
+        }
+        // ---- expansion
+        auto window_scan = [&](int (&m)[SPT]) {
+            // read this thread's SPT window slots (and clear them), running maximum, block max-scan
+            int4 *wv = reinterpret_cast<int4 *>(sm.win) + tid * (SPT / 4);
+#pragma unroll
+            for (int i = 0; i < SPT / 4; i++) { const int4 v = wv[i]; m[4 * i] = v.x; m[4 * i + 1] = v.y; m[4 * i + 2] = v.z; m[4 * i + 3] = v.w; }
+#pragma unroll
+            for (int i = 0; i < SPT / 4; i++) wv[i] = make_int4(0, 0, 0, 0);
+#pragma unroll
+            for (int i = 1; i < SPT; i++) m[i] = max(m[i], m[i - 1]);
+            int incm = m[SPT - 1];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, incm, o); if (lane >= o) incm = max(incm, y); }
+            int basem = __shfl_up_sync(FULL, incm, 1);
+            if (lane == 0) basem = 0;
+            if (lane == 31) sm.warp_max[wid] = incm;
+            f_bar<NT>();
+#pragma unroll
+            for (int i = 0; i < NW; i++) { const int x = sm.warp_max[i]; if (i < wid) basem = max(basem, x); }
+#pragma unroll
+            for (int i = 0; i < SPT; i++) m[i] = max(m[i], basem);
+        };
+        const int base_j = (int)(p.j0 + (i64)t * TILE) - 1;                   // markers are local index + 1
+        const i64 rel_lo = tile_lo - out_begin;
+        const int mis = (int)(((reinterpret_cast<uintptr_t>(p.idx) >> 2) + (uintptr_t)rel_lo) & 3);
+        if (tile_cnt + 3 <= WIN && rel_lo >= 0 && rel_lo + tile_cnt <= p.cap) {
+            // one window; slot 0 is 16-byte aligned in the index array, the tile's first output is slot `mis`
+            const int total = (int)tile_cnt + mis;
+            int l = hv_prev + mis;
+#pragma unroll
+            for (int i = 0; i < IPT; i++) {
+                const int h = hv[i] + mis;
+                if (h > l) sm.win[l] = tid * IPT + i + 1;
+                l = h;
+            }
+            f_bar<NT>();
+            int m[SPT];
+            window_scan(m);
+            const int s0 = tid * SPT;
+            int *dst = p.idx + (rel_lo - mis) + s0;
+            if (s0 >= mis && s0 + SPT <= total) {
+#pragma unroll
+                for (int i = 0; i < SPT; i += 4)
+                    *reinterpret_cast<int4 *>(dst + i) = make_int4(base_j + m[i], base_j + m[i + 1], base_j + m[i + 2], base_j + m[i + 3]);
+            } else if (s0 < total) {
+#pragma unroll
+                for (int i = 0; i < SPT; i++)
+                    if (s0 + i >= mis && s0 + i < total) dst[i] = base_j + m[i];
+            }
+            continue;      // the next tile's barrier separates these window reads from its marker writes
+        }
+        // general expansion: several windows, runs of BIGRUN or more copies go to the fill kernel
+        const int cnt = (int)tile_cnt;
+        int cs = 0;
+        while (cs < cnt) {
+            if (tid == 0) sm.skip = -1;
+            f_bar<NT>();
+            {
+                int l = hv_prev;
+#pragma unroll
+                for (int i = 0; i < IPT; i++) {
+                    const int h = hv[i];
+                    if (l <= cs && cs < h && h - cs >= BIGRUN) {
+                        sm.skip = h;
+                        const int r = atomicAdd(&ws.hdr->n_runs, 1);
+                        if (r < ws.max_runs) ws.runs[r] = Run{tile_lo + cs, tile_lo + h, base_j + tid * IPT + i + 1, 0};
+                        else ws.hdr->fallback = 1;
+                    }
+                    l = h;
+                }
+            }
+            f_bar<NT>();
+            const int skip = sm.skip;
+            if (skip >= 0) { cs = skip; f_bar<NT>(); continue; }
+            const int ce = (cnt - cs > WIN) ? cs + WIN : cnt;
+            {
+                int l = hv_prev;
+#pragma unroll
+                for (int i = 0; i < IPT; i++) {
+                    const int h = hv[i];
+                    const int a0 = max(l, cs);
+                    if (h > a0 && a0 < ce) sm.win[a0 - cs] = tid * IPT + i + 1;
+                    l = h;
+                }
+            }
+            f_bar<NT>();
+            int m[SPT];
+            window_scan(m);
+#pragma unroll
+            for (int i = 0; i < SPT; i++) {
+                const int sl = tid * SPT + i;
+                if (sl < ce - cs) put_index(p, tile_lo + cs + sl, base_j + m[i]);
+            }
+            f_bar<NT>();
+            cs = ce;
+        }
+        f_bar<NT>();
     }
 }
 
@@ -1173,12 +1482,14 @@ struct RunArgs {
     int phase;           // bit 0: passes A-C (need carry_approx), bit 1: pass D chain (needs carry_exact), bit 2: passes E-G
 };
 
-// BKE_RS_IMPL=old keeps the multi-pass pipeline below for whole-array calls (A/B comparisons);
-// the default is the single-pass kernel of resample_fused.cu
+// BKE_RS_IMPL=fused (or "new") selects the experimental single-pass kernel of resample_fused.cu for
+// whole-array calls: 12 B/particle of HBM traffic instead of 28, bit-exact on every test, but its
+// two-stage look-back chain does not yet keep up with the emit: the default
+// is the multi-pass pipeline below with the second-generation emit kernel.
 static bool use_fused()
 {
     const char *e = getenv("BKE_RS_IMPL");
-    return !(e && e[0] == 'o');
+    return e && (e[0] == 'f' || e[0] == 'n');
 }
 
 int run(const RunArgs &a, cudaStream_t s)
@@ -1239,7 +1550,24 @@ int run(const RunArgs &a, cudaStream_t s)
     }
     if (a.phase & 4) {
         const int fast_grid = T < sms * 2 ? T : sms * 2;
-        if (a.U) {
+        // second-generation emit (TMA-staged, marker / max-scan expansion) whenever the weights qualify for
+        // TMA and indexes are produced; BKE_RS_EMIT=1 keeps the first-generation kernel
+        CUtensorMap wmap;
+        const char *emit_env = getenv("BKE_RS_EMIT");
+        const bool emit2 = !(emit_env && emit_env[0] == '1') && !a.cumsum_out && (n % 16) == 0 && f_weights_map(a.w, n, E2_NT, &wmap);
+        if (emit2) {
+            const int smem2 = (int)sizeof(Emit2Shared);
+            static bool configured2[64] = {false};
+            if (dev < 0 || dev >= 64 || !configured2[dev]) {
+                if (check_cuda(cudaFuncSetAttribute(k_emit2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
+                if (check_cuda(cudaFuncSetAttribute(k_emit2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
+                if (dev >= 0 && dev < 64) configured2[dev] = true;
+            }
+            if (a.U) k_emit2<true><<<fast_grid, E2_NT + 32, smem2, s>>>(wmap, p);
+            else k_emit2<false><<<fast_grid, E2_NT + 32, smem2, s>>>(wmap, p);
+            if (a.U) k_emit_slow<true><<<slow_grid, BLOCK, emit_smem, s>>>(p);
+            else k_emit_slow<false><<<slow_grid, BLOCK, emit_smem, s>>>(p);
+        } else if (a.U) {
             k_emit_fast<true><<<fast_grid, BLOCK, emit_smem, s>>>(p);
             k_emit_slow<true><<<slow_grid, BLOCK, emit_smem, s>>>(p);
         } else {
@@ -1307,6 +1635,28 @@ int bke_resample_normalized(int64_t n, const double *weights, double u, const do
     f.carry_approx = nullptr; f.carry_exact = nullptr; f.out_range = nullptr; f.is_last = 1;
     f.cumsum_out = nullptr; f.last_one = 0; f.div = sum_out; f.wnorm_out = weights_out;
     return rs::f_run(f, (cudaStream_t)stream);
+}
+
+size_t bke_resample_composite_bytes(void) { return sizeof(rs::Composite); }
+
+int bke_resample_shard_compose(const bke_resample_shard_args *args, void *composite_out, void *stream)
+{
+    if (!args || !composite_out) { set_error("NULL argument"); return BKE_ERR_BAD_ARG; }
+    if (args->n_local <= 0) { return check_cuda(cudaMemsetAsync(composite_out, 0, 16, (cudaStream_t)stream), "memset"); }
+    rs::Params p;
+    if (rs::carve(args->n_local, nullptr, nullptr) > args->workspace_bytes) { set_error("workspace too small"); return BKE_ERR_BAD_ARG; }
+    rs::carve(args->n_local, (unsigned char *)args->workspace, &p.ws);
+    p.n = args->n_local;
+    rs::k_compose<<<1, rs::CHAIN_THREADS, 0, (cudaStream_t)stream>>>(p, (rs::Composite *)composite_out);
+    return check_cuda(cudaGetLastError(), "compose launch");
+}
+
+int bke_resample_compose_carry(int32_t n_shards_before, const void *composites, double *carry_exact, int32_t *status,
+                               void *stream)
+{
+    if (n_shards_before < 0 || !carry_exact || (n_shards_before > 0 && !composites)) { set_error("bad arguments"); return BKE_ERR_BAD_ARG; }
+    rs::k_compose_carry<<<1, 32, 0, (cudaStream_t)stream>>>(n_shards_before, (const rs::Composite *)composites, carry_exact, status);
+    return check_cuda(cudaGetLastError(), "compose carry launch");
 }
 
 /* debugging aid (not part of the documented ABI): device buffer of uint64[T][10] that receives the

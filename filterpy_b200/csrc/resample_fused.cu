@@ -37,62 +37,6 @@
 namespace bke {
 namespace rs {
 
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t f_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void f_mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(f_smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void f_fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void f_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void f_mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(f_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void f_mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(f_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool f_mbar_try(uint64_t *bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                 : "=r"(ok) : "r"(f_smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void f_mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    while (!f_mbar_try(bar, parity)) {}
-}
-__device__ __forceinline__ void f_tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(f_smem_u32(dst)), "l"(map), "r"(f_smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-// named barriers of the consumer warps (the producer warp never joins them)
-template <int NT> __device__ __forceinline__ void f_bar()
-{
-    asm volatile("barrier.cta.sync 1, %0;" ::"n"(NT) : "memory");
-}
-template <int NT> __device__ __forceinline__ int f_bar_and(int pred)
-{
-    int out;
-    asm volatile("{\n.reg .pred p, q;\nsetp.ne.b32 p, %1, 0;\nbarrier.cta.red.and.pred q, 1, %2, p;\nselp.b32 %0, 1, 0, q;\n}\n"
-                 : "=r"(out) : "r"(pred), "n"(NT) : "memory");
-    return out;
-}
-__device__ __forceinline__ u64 f_ld(const u64 *p)
-{
-    u64 v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void f_st(u64 *p, u64 v)
-{
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
 // ------------------------------------------------------------------ event trace (debugging aid)
 // bke_debug_resample_trace(buf): every tile writes the global-timer time of 10 pipeline events
 __device__ __forceinline__ void f_trace(const FParams &p, int t, int ev)
@@ -289,8 +233,6 @@ struct FSmem {
     i64 tstart[NT];
 };
 
-// byte offset of weight (row r = owning thread, 16-byte chunk c) inside a swizzled stage
-__device__ __forceinline__ uint32_t f_swz(int r, int c) { return (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4); }
 
 template <int NW> __device__ __forceinline__ double f_scan_d(double v, double *total, double *sh, int lane, int wid)
 {
@@ -1280,6 +1222,25 @@ bool f_make_map(CUtensorMap *m, const double *base, int64_t rows, int box_rows)
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+}  // namespace
+
+bool f_weights_map(const double *w, int64_t n, int box_rows, CUtensorMap *out)
+{
+    static thread_local CUtensorMap map;
+    static thread_local const void *map_ptr = nullptr;
+    static thread_local int64_t map_n = -1;
+    static thread_local int map_rows = 0;
+    if ((reinterpret_cast<uintptr_t>(w) & 15) != 0 || (n >> 4) < 1 || f_get_encode() == nullptr) return false;
+    if (!(map_ptr == w && map_n == n && map_rows == box_rows)) {
+        if (!f_make_map(&map, w, n >> 4, box_rows)) { map_ptr = nullptr; return false; }
+        map_ptr = w; map_n = n; map_rows = box_rows;
+    }
+    *out = map;
+    return true;
+}
+
+namespace {
+
 int f_env_int(const char *name, int dflt)
 {
     const char *v = getenv(name);
@@ -1371,17 +1332,9 @@ int f_run(const FRunArgs &a, cudaStream_t s)
     const double tau = ldexp((double)a.ng, -46);
     p.tau = tau > 1e-6 ? tau : 1e-6;
     // TMA path: 16-byte aligned base and at least one full row of 16 weights
-    static thread_local CUtensorMap map;
-    static thread_local const void *map_ptr = nullptr;
-    static thread_local i64 map_n = -1;
-    static thread_local int map_nw = 0;
-    const int tma_env = f_env_int("BKE_RS_TMA", 1);
-    p.use_tma = tma_env && (reinterpret_cast<uintptr_t>(a.w) & 15) == 0 && (n >> 4) >= 1 && f_get_encode() != nullptr;
-    if (p.use_tma && !(map_ptr == a.w && map_n == n && map_nw == NW)) {
-        if (!f_make_map(&map, a.w, n >> 4, NW * 32)) p.use_tma = 0;
-        else { map_ptr = a.w; map_n = n; map_nw = NW; }
-    }
-    if (!p.use_tma) memset(&map, 0, sizeof(map)), map_ptr = nullptr;
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    p.use_tma = f_env_int("BKE_RS_TMA", 1) && f_weights_map(a.w, n, NW * 32, &map);
     const int init_blocks = (int)((p.T + 1 + 255) / 256) < 64 ? (int)((p.T + 1 + 255) / 256) : 64;
     k_finit<<<init_blocks, 256, 0, s>>>(p);
     int rc;

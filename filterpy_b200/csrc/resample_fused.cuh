@@ -1,5 +1,6 @@
 // resample_fused.cuh — interface of the single-pass resampling kernel (csrc/resample_fused.cu).
 #pragma once
+#include <cuda.h>
 #include "resample_common.cuh"
 
 namespace bke {
@@ -74,6 +75,69 @@ struct FRunArgs {
     double *cumsum_out; int last_one;
     const double *div; double *wnorm_out;
 };
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t f_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void f_mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(f_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void f_fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void f_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void f_mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(f_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void f_mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(f_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool f_mbar_try(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(f_smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void f_mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!f_mbar_try(bar, parity)) {}
+}
+__device__ __forceinline__ void f_tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(f_smem_u32(dst)), "l"(map), "r"(f_smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// named barriers of the consumer warps (the producer warp never joins them)
+template <int NT> __device__ __forceinline__ void f_bar()
+{
+    asm volatile("barrier.cta.sync 1, %0;" ::"n"(NT) : "memory");
+}
+template <int NT> __device__ __forceinline__ int f_bar_and(int pred)
+{
+    int out;
+    asm volatile("{\n.reg .pred p, q;\nsetp.ne.b32 p, %1, 0;\nbarrier.cta.red.and.pred q, 1, %2, p;\nselp.b32 %0, 1, 0, q;\n}\n"
+                 : "=r"(out) : "r"(pred), "n"(NT) : "memory");
+    return out;
+}
+__device__ __forceinline__ u64 f_ld(const u64 *p)
+{
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void f_st(u64 *p, u64 v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// byte offset of weight (row r = owning thread, 16-byte chunk c) inside a swizzled stage
+__device__ __forceinline__ uint32_t f_swz(int r, int c) { return (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4); }
+
+// tensor map of the weights as rows of 16 doubles with a box of `box_rows` rows (cached per thread);
+// false when the driver entry point is missing or the pointer / size does not qualify for TMA
+bool f_weights_map(const double *w, int64_t n, int box_rows, CUtensorMap *out);
 
 size_t f_carve(int64_t n, unsigned char *base, FParams *p);
 int f_run(const FRunArgs &a, cudaStream_t s);

@@ -4,8 +4,9 @@ gloo in the CPU tests).
 Filter banks shard embarrassingly: every rank owns a contiguous slice of the N axis and runs the
 same kernels on it; there is NO data-path collective.  Particle sets shard the same
 way; the only exchange is the weight-sum all-reduce before a resample (north_star), plus — for a
-resample that must equal the single-array reference bit for bit — the exact running sum handed
-from shard r to shard r+1 (see ``sharded_systematic_resample``).
+resample that must equal the single-array reference bit for bit — an all-gather of the shards'
+composite parity maps, from which every rank derives its exact carry locally
+(see ``sharded_systematic_resample``).
 """
 import numpy as np
 import torch
@@ -61,21 +62,30 @@ def exclusive_prefix(value, group=None):
     return acc.reshape(value.shape)
 
 
-def sharded_systematic_resample(weights_local, u, group=None, capacity=None, uniforms=None, sizes=None):
+def sharded_systematic_resample(weights_local, u, group=None, capacity=None, uniforms=None, sizes=None,
+                                method="compose", local_sum=None):
     """Systematic (or, with ``uniforms`` = the replicated global U[N], stratified) resampling of a
     particle set whose weights are sharded contiguously over the ranks of ``group`` — one process
     per GPU, NCCL over NVLink.  Bit-identical to ``systematic_resample`` on the concatenated array.
 
-    Exchanges (all stream-ordered, no host synchronisation besides the size gather):
-      1. all-gather of the shard sizes (host ints) and of the approximate shard weight sums (one
-         double per rank) — the weight-sum exchange of the north star;
-      2. the exact running sum handed from rank r to rank r+1 (one double, point-to-point): the only
-         serial dependency; the heavy passes (tile sums, parity maps) run before it on every rank.
+    Exchanges (all stream-ordered, no host synchronisation besides the optional size gather):
+      1. all-gather of the approximate shard weight sums (one double per rank) — the weight-sum
+         exchange of the north star (``local_sum``: pass it when the caller already has it, e.g. from
+         normalising the weights);
+      2. ``method="compose"`` (default): all-gather of every shard's COMPOSITE — the short list of
+         parity maps / true adds that carries the exact running sum across the shard, formed from
+         the approximate carry alone — after which every rank derives its exact carry locally: no
+         rank waits for another rank's chain.  ``method="relay"``: the exact running sum handed from
+         rank r to rank r+1 (one double, point-to-point; serial over the ranks).  A shard whose
+         composite cannot be formed (a dense zone of tiny weights next to a binade boundary) sets
+         bit 8 of ``info[4]``: call again with ``method="relay"``.
 
-    Returns ``(indexes, out_range)``: rank r owns the global output positions
+    Returns ``(indexes, out_range, info, keep)``: rank r owns the global output positions
     ``[out_range[0], out_range[1])`` (device int64[2]); ``indexes[:out_range[1]-out_range[0]]`` holds
-    their GLOBAL particle numbers (int32).  ``capacity`` bounds the local output buffer (default
-    ``2 * n_local + 1024``; a shard holding more weight than that needs a larger one — info[6])."""
+    their GLOBAL particle numbers (int32); ``info`` is the device int32[8] of ``bke.h``; ``keep``
+    holds the scratch tensors the stream-ordered launches still use.  ``capacity`` bounds the local
+    output buffer (default ``2 * n_local + 1024``; a shard holding more weight than that needs a
+    larger one — info[6])."""
     import ctypes
     from . import _lib
     from ._dev import stream_ptr
@@ -92,40 +102,53 @@ def sharded_systematic_resample(weights_local, u, group=None, capacity=None, uni
             sizes = [n_local]
     n_global = int(sum(sizes)); j_offset = int(sum(sizes[:rank]))
     cap = int(capacity) if capacity is not None else 2 * n_local + 1024
-    ws_bytes = int(lib.bke_resample_workspace_bytes(n_local))
-    ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)
-    ws_ptr = ws.data_ptr() + ((-ws.data_ptr()) % 256)
-    idx = torch.empty(cap, dtype=torch.int32, device=dev)
-    info = torch.zeros(8, dtype=torch.int32, device=dev)
-    out_range = torch.zeros(2, dtype=torch.int64, device=dev)
-    carry_out = torch.zeros(1, dtype=torch.float64, device=dev)
-    local_sum = torch.zeros(1, dtype=torch.float64, device=dev)
-    st = stream_ptr(dev)
-    _lib.check(lib.bke_weights_sum(n_local, weights_local.data_ptr(), local_sum.data_ptr(), ws_ptr, ws_bytes, st))
-    sums = gather_counts(local_sum[0], group)                        # approximate shard sums, every rank
-    carry_approx = sums[:rank].sum().reshape(1) if rank > 0 else torch.zeros(1, dtype=torch.float64, device=dev)
-    a = _lib.ResampleShardArgs()
-    a.n_local, a.n_global, a.j_offset, a.capacity = n_local, n_global, j_offset, cap
-    a.weights = weights_local.data_ptr()
-    a.uniforms = None if uniforms is None else uniforms.data_ptr()
-    a.u = float(u)
-    a.carry_approx = carry_approx.data_ptr()
-    a.indexes, a.out_range, a.carry_out = idx.data_ptr(), out_range.data_ptr(), carry_out.data_ptr()
-    a.workspace, a.workspace_bytes, a.info = ws_ptr, ws_bytes, info.data_ptr()
-    a.is_last = 1 if rank == world - 1 else 0
-    a.phase = 1
-    _lib.check(lib.bke_resample_shard(ctypes.byref(a), st))          # passes A-C: no dependency on other ranks
-    carry_in = torch.zeros(1, dtype=torch.float64, device=dev)
-    if rank > 0:
-        dist.recv(carry_in, src=dist.get_global_rank(group, rank - 1) if group is not None else rank - 1, group=group)
-        a.carry_exact = carry_in.data_ptr()
-    a.phase = 2
-    _lib.check(lib.bke_resample_shard(ctypes.byref(a), stream_ptr(dev)))   # exact chain: produces carry_out
-    if rank < world - 1:                                                   # the next rank can start its chain now
-        dist.send(carry_out, dst=dist.get_global_rank(group, rank + 1) if group is not None else rank + 1, group=group)
-    a.phase = 4
-    _lib.check(lib.bke_resample_shard(ctypes.byref(a), stream_ptr(dev)))   # emit the indexes
-    keep = (ws, carry_approx, carry_in, local_sum, sums)
+    with torch.cuda.device(dev):                             # the launches bind to the device of the weights
+        ws_bytes = int(lib.bke_resample_workspace_bytes(n_local))
+        ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)
+        ws_ptr = ws.data_ptr() + ((-ws.data_ptr()) % 256)
+        idx = torch.empty(cap, dtype=torch.int32, device=dev)
+        info = torch.zeros(8, dtype=torch.int32, device=dev)
+        out_range = torch.zeros(2, dtype=torch.int64, device=dev)
+        carry_out = torch.zeros(1, dtype=torch.float64, device=dev)
+        st = stream_ptr(dev)
+        if local_sum is None:
+            local_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+            _lib.check(lib.bke_weights_sum(n_local, weights_local.data_ptr(), local_sum.data_ptr(), ws_ptr, ws_bytes, st))
+        sums = gather_counts(local_sum.reshape(-1)[0], group)            # approximate shard sums, every rank
+        carry_approx = sums[:rank].sum().reshape(1) if rank > 0 else torch.zeros(1, dtype=torch.float64, device=dev)
+        a = _lib.ResampleShardArgs()
+        a.n_local, a.n_global, a.j_offset, a.capacity = n_local, n_global, j_offset, cap
+        a.weights = weights_local.data_ptr()
+        a.uniforms = None if uniforms is None else uniforms.data_ptr()
+        a.u = float(u)
+        a.carry_approx = carry_approx.data_ptr()
+        a.indexes, a.out_range, a.carry_out = idx.data_ptr(), out_range.data_ptr(), carry_out.data_ptr()
+        a.workspace, a.workspace_bytes, a.info = ws_ptr, ws_bytes, info.data_ptr()
+        a.is_last = 1 if rank == world - 1 else 0
+        a.phase = 1
+        _lib.check(lib.bke_resample_shard(ctypes.byref(a), st))          # passes A-C: no dependency on other ranks
+        carry_in = torch.zeros(1, dtype=torch.float64, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        comp = allc = None
+        if world > 1 and method == "compose":
+            cbytes = int(lib.bke_resample_composite_bytes())
+            comp = torch.empty(cbytes, dtype=torch.uint8, device=dev)
+            allc = torch.empty(world * cbytes, dtype=torch.uint8, device=dev)
+            _lib.check(lib.bke_resample_shard_compose(ctypes.byref(a), comp.data_ptr(), st))
+            dist.all_gather_into_tensor(allc, comp, group=group)
+            _lib.check(lib.bke_resample_compose_carry(rank, allc.data_ptr(), carry_in.data_ptr(), status.data_ptr(), st))
+            a.carry_exact = carry_in.data_ptr()
+        elif rank > 0:
+            dist.recv(carry_in, src=dist.get_global_rank(group, rank - 1) if group is not None else rank - 1, group=group)
+            a.carry_exact = carry_in.data_ptr()
+        a.phase = 2
+        _lib.check(lib.bke_resample_shard(ctypes.byref(a), stream_ptr(dev)))   # exact chain: produces carry_out
+        if world > 1 and method != "compose" and rank < world - 1:             # the next rank can start its chain now
+            dist.send(carry_out, dst=dist.get_global_rank(group, rank + 1) if group is not None else rank + 1, group=group)
+        a.phase = 4
+        _lib.check(lib.bke_resample_shard(ctypes.byref(a), stream_ptr(dev)))   # emit the indexes
+        info[4:5] += status * 256                                             # bit 8: a composite could not be formed
+    keep = (ws, carry_approx, carry_in, local_sum, sums, comp, allc, status, carry_out)
     return idx, out_range, info, keep
 
 
@@ -180,7 +203,7 @@ def exchange_rows(rows, out, sends, recvs, group=None):
     return out
 
 
-def redistribute_after_resample(particles_local, idx_local, out_range, n_global, group=None):
+def redistribute_after_resample(particles_local, idx_local, out_range, n_global, group=None, j_offset=None):
     """The step after a sharded resample, on the GPU: ``new_particles = particles[indexes]`` with
     the result sharded evenly again.  ``particles_local`` is this rank's shard (rows b_r..b_r+1),
     ``idx_local`` / ``out_range`` what ``sharded_systematic_resample`` returned (global particle
@@ -198,7 +221,12 @@ def redistribute_after_resample(particles_local, idx_local, out_range, n_global,
     else:
         out_ranges = [tuple(int(v) for v in rng_t.tolist())]
     cnt = out_ranges[rank][1] - out_ranges[rank][0]
-    local_idx = (idx_local[:cnt].to(torch.int64) - int(bounds[rank])).to(torch.int32)
+    # ``j_offset``: global number of this rank's first particle — differs from bounds[rank] when the
+    # weights were sharded with custom ``sizes``; the NEW set is always sharded evenly by ``bounds``
+    j0 = int(bounds[rank]) if j_offset is None else int(j_offset)
+    if int(particles_local.shape[0]) != int(bounds[rank + 1] - bounds[rank]) and j_offset is None:
+        raise ValueError("particles_local does not match shard_bounds(n_global): pass j_offset for custom shard sizes")
+    local_idx = (idx_local[:cnt].to(torch.int64) - j0).to(torch.int32)
     rows = gather_particles(particles_local, local_idx)                 # every index is in this rank's shard
     out = torch.empty((int(bounds[rank + 1] - bounds[rank]),) + tuple(particles_local.shape[1:]),
                       dtype=particles_local.dtype, device=particles_local.device)

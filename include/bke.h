@@ -245,6 +245,19 @@ typedef struct bke_resample_shard_args {
 
 int bke_resample_shard(const bke_resample_shard_args *args, void *stream);
 
+/* Multi-GPU without a serial hand-over: after phase 1 every rank summarises its shard as a
+ * COMPOSITE — the ordered list of parity maps and true adds that takes the exact running sum from
+ * the start of the shard to its end (it depends on the approximate carry only) — of
+ * bke_resample_composite_bytes() bytes.  The ranks all-gather their composites (NCCL), and
+ * bke_resample_compose_carry applies those of the n_shards_before earlier shards, in order, to 0:
+ * the exact carry of this rank, on the device, to be passed as `carry_exact` of phases 2 and 4.
+ * *status != 0: a composite could not be formed (a dense zone of tiny weights next to a binade
+ * boundary) — use the rank-to-rank hand-over of `carry_out` instead. */
+size_t bke_resample_composite_bytes(void);
+int bke_resample_shard_compose(const bke_resample_shard_args *args, void *composite_out, void *stream);
+int bke_resample_compose_carry(int32_t n_shards_before, const void *composites, double *carry_exact,
+                               int32_t *status, void *stream);
+
 /* sum of weights (fp64, deterministic tree order) — the quantity that is all-reduced across
  * GPUs before a distributed resample; also used to normalise: weights_out[i] = weights[i] / sum
  * (IEEE division, the same elementwise operation as NumPy's `w / w.sum()` given that sum). */
