@@ -57,6 +57,36 @@ def ncu_traffic():
         return None
 
 
+# ----------------------------------------------------------------------------- NUMA affinity
+def pin_to_gpu_numa(local_rank):
+    """Bind this process to the CPUs of the NUMA node its GPU hangs off (NVML PCI bus id ->
+    /sys/bus/pci/devices/<id>/numa_node -> /sys/devices/system/node/node<k>/cpulist) BEFORE any pinned
+    buffer is allocated: with several ranks per socket the host<->device copies of the e2e leg
+    otherwise fight over the wrong memory controller.  Returns a description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:                    # NVML: 00000000:1B:00.0, sysfs: 0000:1b:00.0
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return {"numa_node": None, "note": "no NUMA information for %s" % bus}
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed)}
+    except Exception as e:                                   # never fail the bench over affinity
+        return {"numa_node": None, "note": "%s: %s" % (type(e).__name__, e)}
+
+
 # ----------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
     """SM clock and throttle reasons sampled from NVML while a region runs.  NVML is initialised
@@ -132,13 +162,44 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU legs
+def reference_importable():
+    """The unmodified reference (filterpy 1.4.5) when a copy is importable on this box: baseline/_ref
+    (pip --target install made by __graft_entry__.build() where /root/reference exists) or
+    /root/reference itself.  Returns the sys.path entry or None."""
+    for cand in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if os.path.isdir(os.path.join(cand, "filterpy", "kalman")):
+            return cand
+    return None
+
+
 def _loop_port_worker(args):
-    """filterpy-shaped port: a Python loop over filters, the reference's np.dot call sequence
-    (oracle.kf.*_single == kalman_filter.py:471-478, 533-556)."""
-    seed, nf, steps = args
-    from oracle import kf as okf
+    """One worker = one host core.  kind "reference": real filterpy.kalman.KalmanFilter objects,
+    predict(); update(z) in a Python loop — the reference as shipped.  kind "port": the oracle's
+    per-filter functions with the reference's np.dot call sequence (oracle.kf.*_single ==
+    kalman_filter.py:471-478, 533-556)."""
+    seed, nf, steps, ref_path, core = args
+    try:
+        os.sched_setaffinity(0, {core})                     # one worker per core, BLAS threads off (set before the fork)
+    except Exception:
+        pass
     from filterpy_b200.common import workloads as wl
     w = wl.kf_bank_cv2d(nf, seed=seed, steps=steps)
+    if ref_path is not None:
+        if ref_path not in sys.path:
+            sys.path.insert(0, ref_path)
+        from filterpy.kalman import KalmanFilter as RefKF
+        kfs = []
+        for i in range(nf):
+            f = RefKF(dim_x=DIM_X, dim_z=DIM_Z)
+            f.x = w["x"][i].copy(); f.P = w["P"][i].copy(); f.F = w["F"][i]; f.H = w["H"][i]; f.Q = w["Q"][i]; f.R = w["R"][i]
+            kfs.append(f)
+        t0 = time.perf_counter()
+        for t in range(steps):
+            zt = w["zs"][t]
+            for i in range(nf):
+                kfs[i].predict(); kfs[i].update(zt[i])
+        return time.perf_counter() - t0
+    from oracle import kf as okf
     xs = [w["x"][i] for i in range(nf)]; Ps = [w["P"][i] for i in range(nf)]
     t0 = time.perf_counter()
     for t in range(steps):
@@ -148,16 +209,26 @@ def _loop_port_worker(args):
     return time.perf_counter() - t0
 
 
-def cpu_loop_port(cores, nf_per_core, steps):
+def cpu_loop_port(cores, nf_per_core, steps, ref_path=None):
+    """Returns (filter-steps/s, wall seconds, per-worker seconds)."""
     import multiprocessing as mp
+    for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ[v] = "1"                                 # inherited by the forked workers: no BLAS thread pools fighting
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    avail = sorted(os.sched_getaffinity(0))
+    cores = min(cores, len(avail))
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         t0 = time.perf_counter()
-        times = pool.map(_loop_port_worker, [(100 + i, nf_per_core, steps) for i in range(cores)])
+        times = pool.map(_loop_port_worker, [(100 + i, nf_per_core, steps, ref_path, avail[i]) for i in range(cores)])
         wall = time.perf_counter() - t0
     # throughput of `cores` workers running concurrently: each timed its own loop (input generation
     # and process start-up excluded); the slowest worker bounds the step
-    return cores * nf_per_core * steps / max(times), wall
+    return cores * nf_per_core * steps / max(times), wall, times
 
 
 def cpu_vectorised_port(nf, steps):
@@ -204,19 +275,23 @@ def run_reference(args, rank, world):
     """--impl reference: the reference's CPU algorithm (oracle port) on all host cores."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) or 1
     nf_per_core = 2048          # bounded sample of the 2^20-filter bank per step
+    ref_path = reference_importable()
+    kind = "reference" if ref_path else "port"
     for _ in range(min(args.warmup, 1)):
-        cpu_loop_port(cores, 256, 1)
-    val, wall = cpu_loop_port(cores, nf_per_core, args.steps)
-    sample = "%d filters/core x %d cores x %d steps of the 2^20 bank (filterpy-shaped NumPy loop)" % (
-        nf_per_core, cores, args.steps)
+        cpu_loop_port(cores, 256, 1, ref_path)
+    val, wall, times = cpu_loop_port(cores, nf_per_core, args.steps, ref_path)
+    sample = "%d filters/core x %d cores x %d steps of the 2^20 bank (%s), one pinned worker per core, BLAS threads = 1, worker seconds min/median/max %.2f/%.2f/%.2f" % (
+        nf_per_core, cores, args.steps,
+        "real filterpy.kalman.KalmanFilter objects from %s" % ref_path if ref_path else "filterpy-shaped NumPy loop, oracle port",
+        min(times), float(np.median(times)), max(times))
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -232,6 +307,8 @@ def run_ours(args, rank, world, local_rank):
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    all_cpus = os.sched_getaffinity(0)
+    affinity = pin_to_gpu_numa(local_rank) if not args.no_pin else {"numa_node": None, "note": "disabled"}
     K, W = args.steps, max(args.warmup, 3)
     N = N_FILTERS
 
@@ -349,9 +426,19 @@ def run_ours(args, rank, world, local_rank):
     d2h = N * DIM_X * 4
     d2h_full = N * (DIM_X + DIM_X * DIM_X) * 4
 
+    # ---- the other BASELINE configurations, weak-scaled like C2 (every rank its own bank), and the
+    # particle path: the GLOBAL 2^26-particle set sharded over the ranks
+    peak, peak_src = peaks()
+    extras = {}
+    if not args.no_extra:
+        kf = None; graph = None                             # free the C2 bank before the next ones are built
+        torch.cuda.empty_cache()
+        extras = extra_legs(dev, rank, world, peak, max_over_ranks, barrier)
+    res = None
+    if not args.no_resample:
+        res = resample_leg(dev, args, rank, world, peak, max_over_ranks, barrier)
     if rank != 0:
         return
-    peak, peak_src = peaks()
     kern_ms = float(np.mean(per_launch_ms))
     achieved = BYTES_PER_FILTER_STEP * N / (kern_ms * 1e-3) / 1e9
     line = {
@@ -372,67 +459,182 @@ def run_ours(args, rank, world, local_rank):
                      "kernel": "kf42_f32_kernel<3,false,false>", "bytes_per_launch": BYTES_PER_FILTER_STEP * N,
                      "kernel_ms": kern_ms, "kernel_ms_min": float(per_launch_ms.min())},
         "clocks": clk.summary(),
+        "affinity": affinity,
     }
+    line.update(extras)
+    if res is not None:
+        line["resample"] = res
     if world == 1 and not args.no_cpu:
+        try:
+            os.sched_setaffinity(0, all_cpus)               # the CPU legs use every host core again
+        except Exception:
+            pass
         cores = os.cpu_count() or 1
-        lp, lp_wall = cpu_loop_port(cores, 1024, 2)
+        cores = len(os.sched_getaffinity(0)) or cores
+        ref_path = reference_importable()
+        lp, lp_wall, _ = cpu_loop_port(cores, 1024, 2, ref_path)
         vp, vp_wall = cpu_vectorised_port(1 << 17, 3)
         cp, cp_wall = cpu_c_port(1 << 19, 4, cores)
         line["cpu_baseline"] = {
-            "value": lp, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "filterpy-shaped NumPy loop (oracle.kf.*_single), %d filters/core x %d cores x 2 steps, %.1f s"
-                      % (1024, cores, lp_wall),
+            "value": lp, "unit": UNIT, "cores": cores, "kind": "reference" if ref_path else "port",
+            "sample": "%s, %d filters/core x %d pinned cores x 2 steps, BLAS threads = 1, %.1f s"
+                      % ("real filterpy.kalman.KalmanFilter objects" if ref_path else "filterpy-shaped NumPy loop (oracle.kf.*_single)",
+                         1024, cores, lp_wall),
             "vectorised_numpy": {"value": vp, "cores": 1, "sample": "2^17 filters x 3 steps, %.1f s" % vp_wall},
             "c_port": {"value": cp, "cores": cores, "sample": "2^19 filters x 4 steps fp64, %.1f s" % cp_wall},
         }
-    extra = resample_leg(dev, args) if (world == 1 and not args.no_resample) else None
-    if extra is not None:
-        line["resample"] = extra
     print(json.dumps(line), flush=True)
 
 
-def resample_leg(dev, args):
-    """systematic_resample of 2^26 particles on one GPU (BASELINE configs[4], single-GPU slice)."""
-    try:
-        import torch
-        from filterpy_b200.monte_carlo import resampling as rs
-    except Exception:
-        return None
-    if not hasattr(rs, "ResamplePlan"):
-        return None
+def timed_steps(fn, reps, warm, dev, max_over_ranks, barrier):
+    """mean device time (ms) of one call of fn: CUDA events around `reps` calls, max over ranks"""
+    import torch
+    for _ in range(warm):
+        fn()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    barrier()
+    return max_over_ranks(e0.elapsed_time(e1)) / reps
+
+
+def extra_legs(dev, rank, world, peak, max_over_ranks, barrier):
+    """BASELINE configs 3 and 4 and the drop-in default of config 2 (diagnostics=True: K, S, SI, y,
+    priors, log-likelihood written every step), each with the roofline of its kernel; weak scaling."""
+    import torch
+    from filterpy_b200.kalman import (KalmanFilter, UnscentedKalmanFilter, MerweScaledSigmaPoints, ConstVelFx, RangeAzElHx)
+    from filterpy_b200.common import workloads as wl
+    out = {}
+
+    def roof(ms, units, bpu, kernel):
+        gbs = units * bpu / (ms * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                "bytes_per_launch": units * bpu, "kernel_ms": ms, "kernel": kernel}
+
+    # C2 with the optional outputs (what a filterpy object exposes after every update)
+    N = N_FILTERS
+    w = wl.kf_bank_cv2d(N, seed=1234 + rank, steps=1, dtype=np.float32)
+    kf = KalmanFilter(DIM_X, DIM_Z, n_filters=N, dtype=np.float32, device=dev, diagnostics=True)
+    for k in "xPFHQR":
+        setattr(kf, k, w[k])
+    z = torch.from_numpy(w["zs"][0]).to(dev)
+
+    def step2():
+        kf.predict(); kf.update(z)
+    ms = timed_steps(step2, 20, 3, dev, max_over_ranks, barrier)
+    extra_b = (DIM_X + DIM_X * DIM_X + DIM_X * DIM_Z + DIM_Z + 2 * DIM_Z * DIM_Z + 1) * 4 + 4      # priors, K, y, S, SI, loglik, status
+    out["kf_c2_diagnostics"] = {"workload": "config 2 with diagnostics=True (x_prior, P_prior, K, y, S, SI, log-likelihood, status written)",
+                                "value": world * N / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "dtype": "f32",
+                                "roofline": roof(ms, N, BYTES_PER_FILTER_STEP + extra_b, "kf42_f32_kernel<3,false,true>")}
+    del kf, z, w
+    torch.cuda.empty_cache()
+
+    # C3: 10 M filters 9/3 fp64 over 8 GPUs = 1.25 M per rank
+    N3 = 1250000
+    small = wl.kf_bank_ca3d(50000, seed=4321 + rank, steps=1)
+    w3 = {k: np.concatenate([v] * 25, axis=1 if k == "zs" else 0) for k, v in small.items()}
+    kf3 = KalmanFilter(9, 3, n_filters=N3, dtype=np.float64, device=dev, diagnostics=False)
+    for k in "xPFHQR":
+        setattr(kf3, k, w3[k])
+    z3 = torch.from_numpy(w3["zs"][0]).to(dev)
+
+    def step3():
+        kf3.predict(); kf3.update(z3)
+    ms = timed_steps(step3, 10, 3, dev, max_over_ranks, barrier)
+    bpu3 = (2 * 9 + 4 * 81 + 3 + 27 + 9) * 8
+    out["kf_c3"] = {"workload": "config 3: 9/3 fp64, per-filter F/H/Q/R, 1.25 M filters per GPU (10 M over 8)",
+                    "filters_per_gpu": N3, "value": world * N3 / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "dtype": "f64",
+                    "roofline": roof(ms, N3, bpu3, "kf_rowblock_kernel<double,9,3>")}
+    del kf3, z3, w3, small
+    torch.cuda.empty_cache()
+
+    # C4: UKF Merwe 6/3, 2^18 filters, CV + range/azimuth/elevation, fp64
+    N4 = 1 << 18
+    uw = wl.ukf_bank_cv3d(N4, seed=2468 + rank, steps=1)
+    u = UnscentedKalmanFilter(6, 3, 0.1, RangeAzElHx(), ConstVelFx(), MerweScaledSigmaPoints(6, .5, 2., 0.),
+                              n_filters=N4, dtype=np.float64, device=dev, diagnostics=False)
+    u.x = uw["x"]; u.P = uw["P"]; u.Q = uw["Q"]; u.R = uw["R"]
+    z4 = torch.from_numpy(uw["zs"][0]).to(dev)
+
+    def step4():
+        u.predict(); u.update(z4)
+    ms = timed_steps(step4, 20, 3, dev, max_over_ranks, barrier)
+    bpu4 = (2 * 6 + 3 * 36 + 3 + 9) * 8
+    out["ukf_c4"] = {"workload": "config 4: UKF MerweScaledSigmaPoints(6, .5, 2, 0), CV + range/azimuth/elevation, 2^18 filters per GPU",
+                     "filters_per_gpu": N4, "value": world * N4 / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "dtype": "f64",
+                     "roofline": roof(ms, N4, bpu4, "ukf_kernel<double,6,3,CV,RangeAzEl>")}
+    return out
+
+
+def resample_leg(dev, args, rank, world, peak, max_over_ranks, barrier):
+    """BASELINE configs[4]: systematic_resample of the GLOBAL 2^26-particle set.  One GPU: the
+    single-array call.  N GPUs: the weights sharded contiguously, one all-gather of the shard sums
+    and one of the shard composites (NCCL), every rank emits its span of the output
+    (filterpy_b200.distributed.sharded_systematic_resample); particles/s = 2^26 / max-rank time.
+    The result is checked against the C oracle (every rank its own span) once, outside the timing."""
+    import torch
+    import torch.distributed as dist
+    from filterpy_b200.monte_carlo import resampling as rs
+    from filterpy_b200 import distributed as bd
     from filterpy_b200.common import workloads as wl
     N = 1 << 26
     wts = wl.resample_weights(N, "heavy", seed=97)
-    wd = torch.from_numpy(wts).to(dev)
-    plan = rs.ResamplePlan(N, device=dev)
     np.random.seed(7)
     u = float(np.random.random())
-    for _ in range(3):
-        plan.systematic(wd, u)
-    torch.cuda.synchronize(dev)
     reps = 10
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
-    ev[0].record()
-    for i in range(reps):
+    info = None
+    if world == 1:
+        wd = torch.from_numpy(wts).to(dev)
+        plan = rs.ResamplePlan(N, device=dev)
+        ms = timed_steps(lambda: plan.systematic(wd, u), reps, 3, dev, max_over_ranks, barrier)
+        got, lo = plan.indexes, 0
+        info = plan.info().tolist()
+        exchange = "none (single array)"
+        # stratified at the same size (resampling.py:80-114; 20 B/particle: the uniforms are read too)
+        U = torch.from_numpy(np.random.default_rng(5).random(N)).to(dev)
+        ms_str = timed_steps(lambda: plan.stratified(wd, U), 5, 2, dev, max_over_ranks, barrier)
         plan.systematic(wd, u)
-        ev[i + 1].record()
-    torch.cuda.synchronize(dev)
-    ms = np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(reps)])
-    peak, _ = peaks()
-    t = float(np.median(ms)) * 1e-3
-    out = {"metric": "systematic_resample_particles_per_sec", "particles": N, "value": N / t, "unit": "particles/s",
-           "ms": t * 1e3, "roofline": {"bound": "hbm", "achieved": 12.0 * N / t / 1e9, "peak": peak, "unit": "GB/s",
-                                       "frac": 12.0 * N / t / 1e9 / peak, "bytes_per_particle": 12},
-           "info": plan.info().tolist()}
+    else:
+        b = bd.shard_bounds(N, world)
+        sizes = [int(b[r + 1] - b[r]) for r in range(world)]
+        w_loc = torch.from_numpy(wts[int(b[rank]):int(b[rank + 1])]).to(dev)
+        splan = bd.ShardedResamplePlan(sizes, device=dev)
+        ms = timed_steps(lambda: splan.resample(w_loc, u), reps, 3, dev, max_over_ranks, barrier)
+        lo, hi = [int(v) for v in splan.out_range.cpu().numpy()]
+        got = splan.indexes[:hi - lo]
+        info = splan.info.cpu().numpy().tolist() + [int(splan.status.item())]
+        exchange = "all-gather of %d shard sums + all-gather of %d shard composites (NCCL), no serial hand-over" % (world, world)
+        ms_str = None
+    t = ms * 1e-3
+    out = {"metric": "systematic_resample_particles_per_sec", "particles": N, "n_gpus": world, "value": N / t, "unit": "particles/s",
+           "ms": ms, "exchange": exchange,
+           "roofline": {"bound": "hbm", "achieved": 12.0 * N / world / t / 1e9, "peak": peak, "unit": "GB/s per GPU",
+                        "frac": 12.0 * N / world / t / 1e9 / peak, "bytes_per_particle": 12},
+           "info": info}
+    if ms_str is not None:
+        out["stratified"] = {"ms": ms_str, "value": N / (ms_str * 1e-3), "unit": "particles/s",
+                             "roofline_frac": 20.0 * N / (ms_str * 1e-3) / 1e9 / peak, "bytes_per_particle": 20}
     if not args.no_cpu:
+        # bit-exactness against the oracle, and the CPU baseline (rank 0 times it)
         from oracle import resample as ors
-        ns = 1 << 23
-        ws = wts[:ns] / wts[:ns].sum()
         t0 = time.perf_counter()
-        ors.systematic_resample_c(ws, u)
+        want = ors.systematic_resample_c(wts, u)
         tc = time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": ns / tc, "unit": "particles/s", "cores": 1, "kind": "port",
-                               "sample": "oracle.c sequential cumsum+merge on 2^23 particles, %.2f s" % tc}
+        mine = got.cpu().numpy()
+        ok = bool(np.array_equal(mine, want[lo:lo + len(mine)]))
+        if world > 1:
+            flag = torch.tensor([1 if ok else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = bool(flag.item())
+            cover = torch.tensor([len(mine)], device=dev, dtype=torch.int64)
+            dist.all_reduce(cover)
+            ok = ok and int(cover.item()) == N
+        out["bit_exact_vs_oracle"] = ok
+        out["cpu_baseline"] = {"value": N / tc, "unit": "particles/s", "cores": 1, "kind": "port",
+                               "sample": "oracle.c sequential cumsum + merge on all 2^26 particles, %.2f s" % tc}
     return out
 
 
@@ -445,6 +647,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-resample", action="store_true", help="skip the resample leg")
     ap.add_argument("--no-graph", action="store_true", help="launch every step directly instead of CUDA-graph replays")
+    ap.add_argument("--no-pin", action="store_true", help="do not bind the rank to its GPU's NUMA node")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C2-diagnostics / C3 / C4 legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "bke_kf_step", "bke_kf_batch_filter", "bke_ukf_step",
     "bke_resample_workspace_bytes", "bke_systematic_resample", "bke_stratified_resample",
     "bke_weights_sum", "bke_weights_scale", "bke_resample_shard", "bke_resample_normalized",
-    "bke_resample_composite_bytes", "bke_resample_shard_compose", "bke_resample_compose_carry",
+    "bke_resample_composite_bytes", "bke_resample_shard_compose", "bke_resample_compose_carry", "bke_resample_shard_stage",
     "bke_merwe_sigma_points", "bke_unscented_transform",
     "bke_kf_rts_smoother", "bke_ukf_rts_smoother", "bke_mm_probabilities", "bke_mm_mix", "bke_mm_estimate", "bke_cumsum_exact", "bke_searchsorted", "bke_multinomial_resample", "bke_gather_rows",
 ]
@@ -95,6 +95,16 @@ class ResampleShardArgs(ctypes.Structure):
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
         ("info", c_void_p),
         ("is_last", c_int32), ("phase", c_int32),
+    ]
+
+
+class ResampleShardExt(ctypes.Structure):
+    _fields_ = [
+        ("shard_sum_out", c_void_p), ("shard_sums_all", c_void_p),
+        ("composite_out", c_void_p), ("composites_all", c_void_p),
+        ("carry_approx_buf", c_void_p), ("carry_exact_buf", c_void_p),
+        ("compose_status", c_void_p),
+        ("shard_rank", c_int32), ("n_shards", c_int32),
     ]
 
 
@@ -200,6 +210,8 @@ def load():
     lib.bke_resample_shard_compose.restype = ctypes.c_int
     lib.bke_resample_compose_carry.argtypes = [c_int32, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.bke_resample_compose_carry.restype = ctypes.c_int
+    lib.bke_resample_shard_stage.argtypes = [ctypes.POINTER(ResampleShardArgs), ctypes.POINTER(ResampleShardExt), c_int32, c_void_p]
+    lib.bke_resample_shard_stage.restype = ctypes.c_int
     lib.bke_resample_shard.argtypes = [ctypes.POINTER(ResampleShardArgs), c_void_p]
     lib.bke_resample_shard.restype = ctypes.c_int
     lib.bke_merwe_sigma_points.argtypes = [c_int64, c_int32, c_int32, c_double, c_double, c_double,

@@ -1538,8 +1538,10 @@ int run(const RunArgs &a, cudaStream_t s)
     const int sms = sm_count();
     const int slow_grid = T < sms * 2 ? T : sms * 2;
     if (a.phase & 1) {
-        if (check_cuda(cudaMemsetAsync(p.ws.hdr, 0, sizeof(Header), s), "memset header")) return BKE_ERR_CUDA;
-        k_tile_sums<<<T, BLOCK, 0, s>>>(p);
+        if (!(a.phase & 8)) {                       // bit 8: the header reset and pass A have run already (bke_resample_shard_stage)
+            if (check_cuda(cudaMemsetAsync(p.ws.hdr, 0, sizeof(Header), s), "memset header")) return BKE_ERR_CUDA;
+            k_tile_sums<<<T, BLOCK, 0, s>>>(p);
+        }
         k_scan_tiles<<<1, CHAIN_THREADS, 0, s>>>(p);
         k_tile_maps_fast<<<T < sms * 3 ? T : sms * 3, BLOCK, 0, s>>>(p);
         k_tile_maps<<<slow_grid, BLOCK, 0, s>>>(p);
@@ -1637,7 +1639,64 @@ int bke_resample_normalized(int64_t n, const double *weights, double u, const do
     return rs::f_run(f, (cudaStream_t)stream);
 }
 
+namespace bke { namespace rs {
+__global__ void k_carry_approx(int n_before, const double *sums, double *out)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double c = 0.0;
+        for (int r = 0; r < n_before; r++) c += sums[r];      // left to right: every rank forms the same value
+        *out = c;
+    }
+}
+} }
+
 size_t bke_resample_composite_bytes(void) { return sizeof(rs::Composite); }
+
+int bke_resample_shard_stage(const bke_resample_shard_args *args, const bke_resample_shard_ext *ext, int32_t stage, void *stream)
+{
+    if (!args || !ext) { set_error("NULL argument"); return BKE_ERR_BAD_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (args->n_local <= 0) { set_error("empty shards are not supported by the staged call"); return BKE_ERR_BAD_ARG; }
+    if (rs::carve(args->n_local, nullptr, nullptr) > args->workspace_bytes) { set_error("workspace too small"); return BKE_ERR_BAD_ARG; }
+    bke_resample_shard_args a = *args;
+    if (stage == 1) {
+        // header reset, pass A (tile sums, validation), the shard's approximate sum
+        if (!ext->shard_sum_out) { set_error("shard_sum_out is NULL"); return BKE_ERR_BAD_ARG; }
+        rs::Params p;
+        rs::carve(a.n_local, (unsigned char *)a.workspace, &p.ws);
+        p.w = a.weights; p.n = a.n_local;
+        p.aligned16 = (reinterpret_cast<uintptr_t>(a.weights) & 15) == 0;
+        if (check_cuda(cudaMemsetAsync(p.ws.hdr, 0, sizeof(rs::Header), s), "memset header")) return BKE_ERR_CUDA;
+        rs::k_tile_sums<<<p.ws.T, rs::BLOCK, 0, s>>>(p);
+        rs::k_sum_tiles<<<1, rs::CHAIN_THREADS, 0, s>>>(p.ws.tile_sum, p.ws.T, ext->shard_sum_out);
+        return check_cuda(cudaGetLastError(), "shard stage 1 launch");
+    }
+    if (stage == 2) {
+        // approximate carry from the all-gathered sums, passes B and C, the shard's composite
+        if (!ext->shard_sums_all || !ext->carry_approx_buf || !ext->composite_out) { set_error("stage 2 buffers missing"); return BKE_ERR_BAD_ARG; }
+        rs::k_carry_approx<<<1, 32, 0, s>>>(ext->shard_rank, ext->shard_sums_all, ext->carry_approx_buf);
+        a.carry_approx = ext->carry_approx_buf;
+        a.phase = 1 | 8;
+        int rc = bke_resample_shard(&a, stream);
+        if (rc != BKE_OK) return rc;
+        return bke_resample_shard_compose(&a, ext->composite_out, stream);
+    }
+    if (stage == 3) {
+        // exact carry from the all-gathered composites, exact chain, emit
+        if (!ext->composites_all || !ext->carry_exact_buf || !ext->carry_approx_buf) { set_error("stage 3 buffers missing"); return BKE_ERR_BAD_ARG; }
+        int rc = bke_resample_compose_carry(ext->shard_rank, ext->composites_all, ext->carry_exact_buf, ext->compose_status, stream);
+        if (rc != BKE_OK) return rc;
+        a.carry_approx = ext->carry_approx_buf;
+        a.carry_exact = ext->carry_exact_buf;
+        a.phase = 2;
+        rc = bke_resample_shard(&a, stream);
+        if (rc != BKE_OK) return rc;
+        a.phase = 4;
+        return bke_resample_shard(&a, stream);
+    }
+    set_error("stage must be 1, 2 or 3");
+    return BKE_ERR_BAD_ARG;
+}
 
 int bke_resample_shard_compose(const bke_resample_shard_args *args, void *composite_out, void *stream)
 {
@@ -1667,6 +1726,7 @@ int bke_resample_shard(const bke_resample_shard_args *args, void *stream)
 {
     if (!args) { set_error("args is NULL"); return BKE_ERR_BAD_ARG; }
     if (!(args->phase & 7)) { set_error("phase selects nothing"); return BKE_ERR_BAD_ARG; }
+    if ((args->phase & 8) && !(args->phase & 1)) { set_error("phase bit 8 modifies phase 1"); return BKE_ERR_BAD_ARG; }
     rs::RunArgs a;
     a.n = args->n_local; a.ng = args->n_global; a.j0 = args->j_offset; a.cap = args->capacity;
     a.w = args->weights; a.U = args->uniforms; a.u = args->u; a.idx = args->indexes;

@@ -13,7 +13,7 @@ import torch
 import torch.distributed as dist
 
 __all__ = ["shard_bounds", "shard_of", "all_reduce_sum", "exclusive_prefix", "gather_counts",
-           "sharded_systematic_resample", "exchange_plan", "exchange_rows", "redistribute_after_resample"]
+           "sharded_systematic_resample", "ShardedResamplePlan", "exchange_plan", "exchange_rows", "redistribute_after_resample"]
 
 
 def shard_bounds(n, world):
@@ -150,6 +150,99 @@ def sharded_systematic_resample(weights_local, u, group=None, capacity=None, uni
         info[4:5] += status * 256                                             # bit 8: a composite could not be formed
     keep = (ws, carry_approx, carry_in, local_sum, sums, comp, allc, status, carry_out)
     return idx, out_range, info, keep
+
+
+class ShardedResamplePlan(object):
+    """Pre-allocated multi-GPU resample: one process per GPU, the weights sharded contiguously
+    (``sizes`` = particles per rank).  Per call: three C-ABI calls and two NCCL all-gathers, nothing
+    allocated, no host synchronisation —
+
+        stage 1 (pass A, shard sum)  ->  all-gather of the shard sums (world doubles)
+        stage 2 (passes B, C, the shard's composite)  ->  all-gather of the composites
+        stage 3 (exact carry from the composites, exact chain, emit)
+
+    No rank waits for another rank's chain (the composites depend on the approximate carry only).
+    ``resample(weights_local, u)`` returns ``(indexes, out_range)`` as
+    ``sharded_systematic_resample``; ``info`` / ``status`` are device tensors (bit 8 of info[4] or
+    status != 0: a composite could not be formed — fall back to ``sharded_systematic_resample(...,
+    method="relay")``)."""
+
+    def __init__(self, sizes, group=None, device=None, capacity=None, uniforms=None):
+        import ctypes
+        from . import _lib
+        self._ctypes, self._lib_mod = ctypes, _lib
+        self.lib = _lib.load()
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if len(sizes) != self.world:
+            raise ValueError("sizes must have one entry per rank")
+        self.sizes = [int(v) for v in sizes]
+        self.n_local = self.sizes[self.rank]
+        self.n_global = int(sum(self.sizes))
+        self.j_offset = int(sum(self.sizes[:self.rank]))
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.device = dev
+        cap = int(capacity) if capacity is not None else 2 * self.n_local + 1024
+        self.capacity = cap
+        lib = self.lib
+        self.ws_bytes = int(lib.bke_resample_workspace_bytes(self.n_local))
+        self.ws = torch.empty(self.ws_bytes + 256, dtype=torch.uint8, device=dev)
+        self.ws_ptr = self.ws.data_ptr() + ((-self.ws.data_ptr()) % 256)
+        self.indexes = torch.empty(cap, dtype=torch.int32, device=dev)
+        self.info = torch.zeros(8, dtype=torch.int32, device=dev)
+        self.out_range = torch.zeros(2, dtype=torch.int64, device=dev)
+        self.carry_out = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.local_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.all_sums = torch.zeros(self.world, dtype=torch.float64, device=dev)
+        cbytes = int(lib.bke_resample_composite_bytes())
+        self.comp = torch.zeros(cbytes, dtype=torch.uint8, device=dev)
+        self.all_comp = torch.zeros(self.world * cbytes, dtype=torch.uint8, device=dev)
+        self.scratch = torch.zeros(2, dtype=torch.float64, device=dev)
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.uniforms = uniforms
+        a = _lib.ResampleShardArgs()
+        a.n_local, a.n_global, a.j_offset, a.capacity = self.n_local, self.n_global, self.j_offset, cap
+        a.uniforms = None if uniforms is None else uniforms.data_ptr()
+        a.indexes, a.out_range, a.carry_out = self.indexes.data_ptr(), self.out_range.data_ptr(), self.carry_out.data_ptr()
+        a.workspace, a.workspace_bytes, a.info = self.ws_ptr, self.ws_bytes, self.info.data_ptr()
+        a.is_last = 1 if self.rank == self.world - 1 else 0
+        a.phase = 7
+        self._a = a
+        e = _lib.ResampleShardExt()
+        e.shard_sum_out = self.local_sum.data_ptr()
+        e.shard_sums_all = self.all_sums.data_ptr()
+        e.composite_out = self.comp.data_ptr()
+        e.composites_all = self.all_comp.data_ptr()
+        e.carry_approx_buf = self.scratch.data_ptr()
+        e.carry_exact_buf = self.scratch.data_ptr() + 8
+        e.compose_status = self.status.data_ptr()
+        e.shard_rank, e.n_shards = self.rank, self.world
+        self._e = e
+
+    def resample(self, weights_local, u):
+        from ._dev import stream_ptr
+        if not (weights_local.is_cuda and weights_local.dtype == torch.float64 and weights_local.is_contiguous()
+                and weights_local.numel() == self.n_local):
+            raise ValueError("weights_local must be a contiguous float64 CUDA tensor of %d elements" % self.n_local)
+        ct, lm, lib = self._ctypes, self._lib_mod, self.lib
+        a, e = self._a, self._e
+        a.weights = weights_local.data_ptr()
+        a.u = float(u)
+        with torch.cuda.device(self.device):
+            st = stream_ptr(self.device)
+            lm.check(lib.bke_resample_shard_stage(ct.byref(a), ct.byref(e), 1, st))
+            if self.world > 1:
+                dist.all_gather_into_tensor(self.all_sums, self.local_sum, group=self.group)
+            else:
+                self.all_sums.copy_(self.local_sum)
+            lm.check(lib.bke_resample_shard_stage(ct.byref(a), ct.byref(e), 2, st))
+            if self.world > 1:
+                dist.all_gather_into_tensor(self.all_comp, self.comp, group=self.group)
+            else:
+                self.all_comp.copy_(self.comp)
+            lm.check(lib.bke_resample_shard_stage(ct.byref(a), ct.byref(e), 3, st))
+        return self.indexes, self.out_range
 
 
 # --------------------------------------------------------------------------- particle re-sharding

@@ -496,7 +496,9 @@ class KalmanFilter(object):
         per-epoch ``Fs/Qs/Hs/Rs/Bs/us`` or a ``saver`` run one fused launch per epoch."""
         self._flush()
         N, n, m = self.n_filters, self.dim_x, self.dim_z
-        T = np.size(zs, 0) if not isinstance(zs, torch.Tensor) else zs.shape[0]
+        # (the reference's np.size(zs, 0), kalman_filter.py:951; a list that mixes None with arrays is
+        # ragged for NumPy >= 1.24, so lists are measured with len)
+        T = zs.shape[0] if isinstance(zs, torch.Tensor) else (len(zs) if isinstance(zs, (list, tuple)) else np.size(zs, 0))
         if self._single:
             zarr = np.zeros((T, 1, m))
             vmask = np.ones((T, 1), dtype=bool)
@@ -741,7 +743,7 @@ def batch_filter(x, P, zs, Fs, Qs, Hs, Rs, Bs=None, us=None, update_first=False,
     H0 = np.atleast_2d(Hs[0])
     kf = KalmanFilter(n, H0.shape[0], dtype=dtype, device=device, diagnostics=True)
     kf.x = x; kf.P = P
-    T = np.size(zs, 0)
+    T = len(zs) if isinstance(zs, (list, tuple)) else np.size(zs, 0)
     if us is None:
         us, Bs = None, None
     return kf.batch_filter(zs, Fs=list(Fs), Qs=list(Qs), Hs=[np.atleast_2d(h) for h in Hs], Rs=list(Rs),

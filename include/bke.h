@@ -240,7 +240,8 @@ typedef struct bke_resample_shard_args {
     void *workspace; size_t workspace_bytes;
     int32_t *info;               /* device int32[8] or NULL */
     int32_t is_last;
-    int32_t phase;               /* bit mask of 1, 2, 4 (7 = everything) */
+    int32_t phase;               /* bit mask of 1, 2, 4 (7 = everything); 8 with 1: the header reset and pass A
+                                    have already run (bke_resample_shard_stage) */
 } bke_resample_shard_args;
 
 int bke_resample_shard(const bke_resample_shard_args *args, void *stream);
@@ -254,6 +255,28 @@ int bke_resample_shard(const bke_resample_shard_args *args, void *stream);
  * *status != 0: a composite could not be formed (a dense zone of tiny weights next to a binade
  * boundary) — use the rank-to-rank hand-over of `carry_out` instead. */
 size_t bke_resample_composite_bytes(void);
+
+/* The same sequence with one call per exchange (what filterpy_b200.distributed.ShardedResamplePlan
+ * issues; everything stream-ordered):
+ *   stage 1  header reset, pass A, this shard's approximate sum -> *shard_sum_out
+ *            [ all-gather shard_sum_out -> shard_sums_all ]
+ *   stage 2  approximate carry = shard_sums_all[0] + ... + shard_sums_all[shard_rank - 1], passes B
+ *            and C, the shard's composite -> composite_out
+ *            [ all-gather composite_out -> composites_all ]
+ *   stage 3  exact carry from composites_all (*compose_status != 0: see above), exact chain, emit.
+ * `carry_approx` / `carry_exact` of `args` are ignored (the two scratch doubles of `ext` are used). */
+typedef struct bke_resample_shard_ext {
+    double *shard_sum_out;
+    const double *shard_sums_all;
+    void *composite_out;
+    const void *composites_all;
+    double *carry_approx_buf;
+    double *carry_exact_buf;
+    int32_t *compose_status;
+    int32_t shard_rank, n_shards;
+} bke_resample_shard_ext;
+int bke_resample_shard_stage(const bke_resample_shard_args *args, const bke_resample_shard_ext *ext,
+                             int32_t stage, void *stream);
 int bke_resample_shard_compose(const bke_resample_shard_args *args, void *composite_out, void *stream);
 int bke_resample_compose_carry(int32_t n_shards_before, const void *composites, double *carry_exact,
                                int32_t *status, void *stream);

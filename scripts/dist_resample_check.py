@@ -24,7 +24,13 @@ for it in range(6):
     torch.cuda.synchronize(); dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    idx, rng_t, info, keep = bd.sharded_systematic_resample(w_loc, u, sizes=[int(b[r + 1] - b[r]) for r in range(world)], method=method)
+    if method == "plan":
+        if it == 0:
+            splan = bd.ShardedResamplePlan([int(b[r + 1] - b[r]) for r in range(world)])
+        idx, rng_t = splan.resample(w_loc, u)
+        info = splan.info
+    else:
+        idx, rng_t, info, keep = bd.sharded_systematic_resample(w_loc, u, sizes=[int(b[r + 1] - b[r]) for r in range(world)], method=method)
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda"); dist.all_reduce(ms, op=dist.ReduceOp.MAX)

@@ -28,7 +28,7 @@ def test_struct_layout_matches_header(tmp_path):
     a probe compiled with gcc prints sizeof / offsetof of every struct."""
     import subprocess
     structs = {"bke_kf_args": _lib.KfArgs, "bke_kf_batch_args": _lib.KfBatchArgs, "bke_ukf_args": _lib.UkfArgs,
-               "bke_resample_shard_args": _lib.ResampleShardArgs, "bke_rts_args": _lib.RtsArgs, "bke_ukf_rts_args": _lib.UkfRtsArgs,
+               "bke_resample_shard_args": _lib.ResampleShardArgs, "bke_resample_shard_ext": _lib.ResampleShardExt, "bke_rts_args": _lib.RtsArgs, "bke_ukf_rts_args": _lib.UkfRtsArgs,
                "bke_mm_args": _lib.MmArgs}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "bke.h"', 'int main(void) {']
     for cname, cls in structs.items():

@@ -233,3 +233,119 @@ def test_sharded_resample_equals_whole_array(kind, shards):
         assert float(carry_out.item()) == np.cumsum(w[:int(b[r + 1])])[-1]
     assert covered == N
     assert np.array_equal(out, want)
+
+
+@pytest.mark.parametrize("kind", ["heavy", "uniform", "zeros", "random"])
+@pytest.mark.parametrize("shards", [2, 3, 8])
+def test_shard_composites_give_the_exact_carry(kind, shards):
+    """The multi-GPU exchange without a serial hand-over: every shard's COMPOSITE (formed after
+    phase 1, from the approximate carry alone) applied in order to 0 must give exactly the running
+    sum np.cumsum has before the next shard — and the shards emitted with those carries must equal
+    the single-array result.  All shards run on one GPU here; tests/…::test_nccl_* runs the ranks."""
+    import ctypes
+    import torch
+    from filterpy_b200 import _lib
+    from filterpy_b200.common import workloads as wl
+    from filterpy_b200.distributed import shard_bounds
+    from oracle import resample as ors
+    N, u = 300007, 0.6180339887
+    w = wl.resample_weights(N, kind, seed=13)
+    want = ors.systematic_resample_c(w, u)
+    csum = np.cumsum(w)
+    lib = _lib.load()
+    wd = torch.from_numpy(w).cuda()
+    b = shard_bounds(N, shards)
+    st = torch.cuda.current_stream().cuda_stream
+    cbytes = int(lib.bke_resample_composite_bytes())
+    allc = torch.zeros(shards * cbytes, dtype=torch.uint8, device="cuda")
+    sums, args, keep = [], [], []
+    for r in range(shards):
+        n_loc = int(b[r + 1] - b[r])
+        ws_bytes = int(lib.bke_resample_workspace_bytes(n_loc))
+        ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device="cuda")
+        ws_ptr = ws.data_ptr() + ((-ws.data_ptr()) % 256)
+        sl = wd[int(b[r]):int(b[r + 1])]
+        s = torch.zeros(1, dtype=torch.float64, device="cuda")
+        _lib.check(lib.bke_weights_sum(n_loc, sl.data_ptr(), s.data_ptr(), ws_ptr, ws_bytes, st))
+        sums.append(s)
+        keep.append((ws, sl))
+        args.append((n_loc, ws_ptr, ws_bytes, sl))
+    outs = []
+    for r in range(shards):                       # phase 1 + composite: independent of every other shard's chain
+        n_loc, ws_ptr, ws_bytes, sl = args[r]
+        idx = torch.full((N,), -7, dtype=torch.int32, device="cuda")
+        info = torch.zeros(8, dtype=torch.int32, device="cuda")
+        rng_t = torch.zeros(2, dtype=torch.int64, device="cuda")
+        carry_out = torch.zeros(1, dtype=torch.float64, device="cuda")
+        capx = torch.stack(sums[:r]).sum().reshape(1) if r else torch.zeros(1, dtype=torch.float64, device="cuda")
+        a = _lib.ResampleShardArgs()
+        a.n_local, a.n_global, a.j_offset, a.capacity = n_loc, N, int(b[r]), N
+        a.weights, a.u = sl.data_ptr(), u
+        a.carry_approx = capx.data_ptr()
+        a.indexes, a.out_range, a.carry_out = idx.data_ptr(), rng_t.data_ptr(), carry_out.data_ptr()
+        a.workspace, a.workspace_bytes, a.info = ws_ptr, ws_bytes, info.data_ptr()
+        a.is_last = 1 if r == shards - 1 else 0
+        a.phase = 1
+        _lib.check(lib.bke_resample_shard(ctypes.byref(a), st))
+        _lib.check(lib.bke_resample_shard_compose(ctypes.byref(a), allc.data_ptr() + r * cbytes, st))
+        outs.append((a, idx, info, rng_t, carry_out, capx))
+    out = np.full(N, -1, dtype=np.int32)
+    covered = 0
+    for r in range(shards):
+        a, idx, info, rng_t, carry_out, capx = outs[r]
+        carry = torch.zeros(1, dtype=torch.float64, device="cuda")
+        status = torch.zeros(1, dtype=torch.int32, device="cuda")
+        _lib.check(lib.bke_resample_compose_carry(r, allc.data_ptr(), carry.data_ptr(), status.data_ptr(), st))
+        assert int(status.item()) == 0, (kind, shards, r)
+        assert float(carry.item()) == (csum[int(b[r]) - 1] if r else 0.0), (kind, shards, r)
+        a.carry_exact = carry.data_ptr()
+        a.phase = 2
+        _lib.check(lib.bke_resample_shard(ctypes.byref(a), st))
+        a.phase = 4
+        _lib.check(lib.bke_resample_shard(ctypes.byref(a), st))
+        lo, hi = [int(v) for v in rng_t.cpu().numpy()]
+        inf = info.cpu().numpy()
+        assert inf[1] == 0 and inf[6] == 0, inf
+        assert lo == covered
+        out[lo:hi] = idx[:hi - lo].cpu().numpy()
+        covered = hi
+    assert covered == N
+    assert np.array_equal(out, want)
+
+
+def test_nccl_sharded_resample_two_ranks():
+    """The NCCL path of filterpy_b200.distributed (one process per GPU, torchrun): bit-equal to the C
+    oracle for both exchange methods.  Needs two visible GPUs."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for method in ("plan", "compose", "relay"):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+               "--master-addr", "127.0.0.1", "--master-port", "29517",
+               os.path.join(root, "scripts", "dist_resample_check.py"), "22", method]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert "bit-exact: True" in r.stdout, r.stdout[-2000:]
+        assert "exact on every rank: True" in r.stdout, r.stdout[-2000:]
+
+
+@pytest.mark.parametrize("kind", ["heavy", "zeros"])
+def test_sharded_plan_single_rank_equals_oracle(kind):
+    """ShardedResamplePlan with one rank (no process group): the staged C-ABI sequence (sum ->
+    composite -> exact carry -> emit) must reproduce the single-array result."""
+    import torch
+    from filterpy_b200.common import workloads as wl
+    from filterpy_b200.distributed import ShardedResamplePlan
+    from oracle import resample as ors
+    N, u = 500000, 0.271828
+    w = wl.resample_weights(N, kind, seed=5)
+    plan = ShardedResamplePlan([N])
+    for _ in range(2):                                    # twice: the plan's buffers are reused
+        idx, rng_t = plan.resample(torch.from_numpy(w).cuda(), u)
+    lo, hi = [int(v) for v in rng_t.cpu().numpy()]
+    assert (lo, hi) == (0, N) and int(plan.status.item()) == 0 and plan.info.cpu().numpy()[1] == 0
+    assert np.array_equal(idx[:N].cpu().numpy(), ors.systematic_resample_c(w, u))
