@@ -36,7 +36,7 @@ class _Linked(np.ndarray):
     """What the single-mode attribute getters hand out: a host copy of a device array that WRITES
     BACK.  The reference's attributes are the live arrays, so the usual idioms ``kf.P[2, 2] = 100``,
     ``kf.x[0] = z``, ``kf.F[0, 1] = dt``, ``kf.P *= 10`` must reach the filter; here they re-assign
-    the attribute (which uploads it).  Anything derived from it (slices, results) is a plain copy."""
+    the attribute (which uploads it).  Views derived from it (``kf.P[2]``) do not write back."""
 
     def __new__(cls, arr, owner, name):
         obj = np.array(arr, copy=True).view(cls)
@@ -53,10 +53,6 @@ class _Linked(np.ndarray):
     def __setitem__(self, key, value):
         np.ndarray.__setitem__(self, key, value)
         self._push()
-
-    def __getitem__(self, key):
-        r = np.ndarray.__getitem__(self, key)
-        return np.array(r, copy=True) if isinstance(r, np.ndarray) else r
 
     def _inplace(self, op, other):
         res = op(self.view(np.ndarray), other)

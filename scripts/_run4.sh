@@ -1,11 +1,9 @@
 mkdir -p gpurun_out
-rm -f gpurun_out/relerr.log
-( BKE_TEST_ERRLOG=gpurun_out/relerr.log timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -6
-  echo "== memcheck"
-  timeout 900 compute-sanitizer --tool memcheck --log-file gpurun_out/memcheck_r2.log python -m pytest tests/test_gpu_kf.py tests/test_gpu_ukf.py tests/test_gpu_resample.py tests/test_gpu_parity_holes.py -q -m gpu -k "golden or singular or small_shapes or indefinite or sticky or composites or plan_single or rowblock_separate" -x 2>&1 | tail -3
-  tail -3 gpurun_out/memcheck_r2.log
-  echo "== racecheck"
-  timeout 900 compute-sanitizer --tool racecheck --log-file gpurun_out/racecheck_r2.log python -m pytest tests/test_gpu_kf.py tests/test_gpu_ukf.py tests/test_gpu_resample.py -q -m gpu -k "bank_vs_reference_golden or ukf_bank_vs_reference_golden or golden_vectors_from_reference or plan_single" -x 2>&1 | tail -3
-  tail -3 gpurun_out/racecheck_r2.log
-) > gpurun_out/full2.log 2>&1
-cat gpurun_out/full2.log | cut -c1-400
+export RS_REPS=5
+( BKE_RS_IMPL=fused timeout 500 python scripts/rs_fused_check.py quick 2>&1 | grep "^FAIL\|FAILS\|rror" | head -20;
+  BKE_RS_IMPL=fused BKE_RS_STAGES=5 BKE_RS_PROF=1 timeout 100 python scripts/rs_onebinade.py 26 2>&1 | grep "ONEBINADE\|RSPROF" | tail -2
+  BKE_RS_PROF=1 timeout 120 python scripts/rs_sweep.py 26 heavy new:8:2:0:5 new:8:2:0:3 new:8:2:0:8 new:4:4:0:6 2>&1 | grep "SWEEP\|RSPROF" | awk '/SWEEP/{print last; print} {last=$0}'
+  BKE_RS_PROF=1 timeout 120 python scripts/rs_sweep.py 26 uniform new:8:2:0:5 2>&1 | grep "SWEEP\|RSPROF" | tail -2
+  BKE_RS_IMPL=fused timeout 200 python scripts/rs_trace.py 26 heavy 2>&1 | tail -26
+) > gpurun_out/sweep10.log 2>&1
+cat gpurun_out/sweep10.log

@@ -50,9 +50,7 @@ def make_bank(g, dtype, diagnostics=True):
                                   "kf_bank_3_2", "kf_bank_6_3", "kf_bank_5_5"])
 def test_bank_vs_reference_golden(golden, name, dtype):
     g = golden(name)
-    rtol = RTOL[dtype]
-    if dtype is np.float32 and name in ("kf_bank_9_3",):
-        rtol = 3e-3          # alpha=1.02 fading + 9x9 fp32 accumulates a little more
+    rtol = RTOL[dtype]       # measured in round 2 (BKE_TEST_ERRLOG): fp32 worst case 6.3e-5 (x), 5.5e-6 on the 9/3 bank
     kf = make_bank(g, dtype)
     for t in range(g["zs"].shape[0]):
         v = g["valid"][t]
@@ -65,9 +63,9 @@ def test_bank_vs_reference_golden(golden, name, dtype):
         rel_close(kf.K.cpu().numpy()[v], g["ref_K"][t][v], rtol, "K")
         rel_close(kf.S.cpu().numpy()[v], g["ref_S"][t][v], rtol, "S")
         rel_close(kf.SI.cpu().numpy()[v], g["ref_SI"][t][v], rtol, "SI")
-        rel_close(kf.y.cpu().numpy(), g["ref_y"][t], max(rtol, 1e-6) * 10, "y")
+        rel_close(kf.y.cpu().numpy(), g["ref_y"][t], max(rtol, 1e-5), "y")      # y = z - Hx cancels: fp64 1e-5 of the filter's scale
         ll = kf.log_likelihood.cpu().numpy()[v]
-        np.testing.assert_allclose(ll, g["ref_loglik"][t][v], rtol=rtol * 10, atol=rtol * 10)
+        np.testing.assert_allclose(ll, g["ref_loglik"][t][v], rtol=rtol, atol=rtol)
         assert int(kf.status.sum().item()) == 0
 
 
@@ -177,7 +175,7 @@ def test_batch_filter_bank_vs_oracle(dtype, shape, update_first):
     got = kf.batch_filter(w["zs"], update_first=update_first, valid=valid)
     want = okf.kf_batch_filter_bank(w["x"], w["P"], w["zs"], w["F"], w["H"], w["Q"], w["R"], valid=valid,
                                     update_first=update_first)
-    rtol = RTOL[dtype] * (3 if dtype is np.float32 else 1)
+    rtol = RTOL[dtype]       # fp32: 1e-3 (north_star); measured worst case 3.7e-4
     for a, b, nm in zip(got, want, ["means", "covs", "means_p", "covs_p"]):
         rel_close(a.cpu().numpy(), b, rtol, nm)
     last = want[2][-1] if update_first else want[0][-1]
@@ -281,7 +279,7 @@ def test_rowblock_kernel_vs_oracle(shape, dtype, N):
     for t in range(2):
         kf.predict(); kf.update(w["zs"][t], valid=valid[t])
         o = okf.kf_step_bank(x, P, w["zs"][t], w["F"], w["H"], w["Q"], w["R"], 1.01 ** 2, valid[t]); x, P = o["x"], o["P"]
-    rtol = RTOL[dtype] * (3 if dtype is np.float32 else 1)
+    rtol = RTOL[dtype]       # fp32: 1e-3 (north_star); measured worst case 3.7e-4
     rel_close(kf.x.cpu().numpy(), x, rtol, "x"); rel_close(kf.P.cpu().numpy(), P, rtol, "P")
 
 

@@ -24,7 +24,7 @@ def build(g, dtype, kind, N=None, diagnostics=True):
 def test_ukf_bank_vs_reference_golden(golden, name, kind, dtype):
     g = golden(name)
     u = build(g, dtype, kind)
-    rtol = RTOL[dtype] * (5 if dtype is np.float32 else 1)
+    rtol = RTOL[dtype]       # fp32: 1e-3 (north_star); measured worst case 9.2e-4 (P_prior of the range/az/el bank)
     for t in range(g["zs"].shape[0]):
         v = g["valid"][t]
         u.predict(); u.update(g["zs"][t], valid=v)
@@ -32,8 +32,8 @@ def test_ukf_bank_vs_reference_golden(golden, name, kind, dtype):
         rel_close(u.P.cpu().numpy(), g["ref_P"][t], rtol, "P t=%d" % t)
         rel_close(u.x_prior.cpu().numpy(), g["ref_x_prior"][t], rtol, "x_prior")
         rel_close(u.P_prior.cpu().numpy(), g["ref_P_prior"][t], rtol, "P_prior")
-        rel_close(u.K.cpu().numpy()[v], g["ref_K"][t][v], rtol * 10, "K")
-        rel_close(u.S.cpu().numpy()[v], g["ref_S"][t][v], rtol * 10, "S")
+        rel_close(u.K.cpu().numpy()[v], g["ref_K"][t][v], max(rtol, 1e-5), "K")
+        rel_close(u.S.cpu().numpy()[v], g["ref_S"][t][v], max(rtol, 1e-5), "S")
         assert int(u.status.sum().item()) == 0
 
 
@@ -54,7 +54,7 @@ def test_ukf_256k_vs_oracle_subset(dtype):
         o = oukf.ukf_step_bank(x, P, w["zs"][t][sel], w["Q"][sel], w["R"][sel], 0.1, 0.5, 2.0, 0.0,
                                oukf.FX_CONST_VEL, oukf.HX_RANGE_AZ_EL)
         x, P = o["x"], o["P"]
-    rtol = RTOL[dtype] * (10 if dtype is np.float32 else 1)
+    rtol = RTOL[dtype]       # fp32: 1e-3 (north_star); measured worst case 8.8e-4 after 3 steps of the 2^18 bank
     rel_close(u.x.cpu().numpy()[sel], x, rtol, "x"); rel_close(u.P.cpu().numpy()[sel], P, rtol, "P")
 
 
