@@ -132,6 +132,7 @@ struct Params {
     double *cumsum_last;   // or NULL
     double *cumsum_out;    // non-NULL: write the exact np.cumsum(w) here instead of emitting indexes
     int last_one;          // cumsum mode: store 1.0 as the last element (resampling.py:174)
+    int scan_done;         // the segmented scan of the tile maps (chain_scan) has been run by k_compose
     Ws ws;
 };
 
@@ -551,7 +552,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain(Params p)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_bad = 0;
     int bad = 0;
-    chain_scan(ws, wtot, bad);
+    if (!p.scan_done) chain_scan(ws, wtot, bad);       // (k_compose has run it already in the staged multi-GPU sequence)
     constexpr int PF = 4;
     const int per = ((T + CHAIN_THREADS - 1) / CHAIN_THREADS) * 32;
     const int a = min(T, wid * per), b = min(T, a + per);
@@ -1000,9 +1001,10 @@ __global__ void __launch_bounds__(BLOCK, 2) k_emit_fast(Params p)
 // slots fills the runs (no divergent copy loop) and every thread leaves with 16-byte stores of 20
 // consecutive indexes.  (The same consumer code is the emit phase of the experimental single-pass
 // kernel, csrc/resample_fused.cu.)
-constexpr int E2_NW = 8, E2_NT = E2_NW * 32, E2_SPT = 20, E2_WIN = E2_NT * E2_SPT, E2_STAGES = 2;
+constexpr int E2_NW = 8, E2_NT = E2_NW * 32, E2_SPT = 20, E2_WIN = E2_NT * E2_SPT;
 static_assert(E2_NT * IPT == TILE, "the second-generation emit uses the tile size of passes A-D");
 
+template <int E2_STAGES>
 struct Emit2Shared {
     double w[E2_STAGES][TILE];         // TMA destinations (128-byte swizzle): must stay first, 1024-aligned
     int win[E2_WIN];                   // output window (all zero between tiles)
@@ -1012,12 +1014,15 @@ struct Emit2Shared {
     int skip;
 };
 
-template <bool STRAT>
-__global__ void __launch_bounds__(E2_NT + 32, 2) k_emit2(const __grid_constant__ CUtensorMap wmap, Params p)
+// <E2_STAGES, E2_CTAS>: <2, 2> two 32 KB stages, 96 registers; <1, 3> one stage (the next tile's TMA is
+// issued as soon as the warps hold the current one in registers and lands long before it is needed),
+// 72 registers, three CTAs per SM
+template <bool STRAT, int E2_STAGES, int E2_CTAS>
+__global__ void __launch_bounds__(E2_NT + 32, E2_CTAS) k_emit2(const __grid_constant__ CUtensorMap wmap, Params p)
 {
     constexpr int NT = E2_NT, NW = E2_NW, WIN = E2_WIN, SPT = E2_SPT;
     extern __shared__ __align__(1024) unsigned char e2_smem[];
-    Emit2Shared &sm = *reinterpret_cast<Emit2Shared *>(e2_smem);
+    Emit2Shared<E2_STAGES> &sm = *reinterpret_cast<Emit2Shared<E2_STAGES> *>(e2_smem);
     const Ws &ws = p.ws;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) {
@@ -1517,6 +1522,7 @@ int run(const RunArgs &a, cudaStream_t s)
     p.carry_approx = a.carry_approx; p.carry_exact = a.carry_exact; p.out_range = a.out_range;
     p.u = a.u; p.U = a.U; p.idx = a.idx; p.info = a.info; p.cumsum_last = a.cumsum_last;
     p.cumsum_out = a.cumsum_out; p.last_one = a.last_one;
+    p.scan_done = (a.phase & 16) ? 1 : 0;
     // |exact sequential sum - approximate tree sum| <= (N + 4096) * 2^-53 relative (non-negative
     // terms), i.e. less than (N + 4096) ulps of the running sum; doubled, plus slack.
     p.eb = 2 * (a.ng + 4096) + (a.ng >> 4);
@@ -1558,15 +1564,17 @@ int run(const RunArgs &a, cudaStream_t s)
         const char *emit_env = getenv("BKE_RS_EMIT");
         const bool emit2 = !(emit_env && emit_env[0] == '1') && !a.cumsum_out && (n % 16) == 0 && f_weights_map(a.w, n, E2_NT, &wmap);
         if (emit2) {
-            const int smem2 = (int)sizeof(Emit2Shared);
-            static bool configured2[64] = {false};
-            if (dev < 0 || dev >= 64 || !configured2[dev]) {
-                if (check_cuda(cudaFuncSetAttribute(k_emit2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
-                if (check_cuda(cudaFuncSetAttribute(k_emit2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
-                if (dev >= 0 && dev < 64) configured2[dev] = true;
-            }
-            if (a.U) k_emit2<true><<<fast_grid, E2_NT + 32, smem2, s>>>(wmap, p);
-            else k_emit2<false><<<fast_grid, E2_NT + 32, smem2, s>>>(wmap, p);
+            static const int e2_variant = [] { const char *e = getenv("BKE_RS_E2"); return e ? atoi(e) : 0; }();
+            auto launch2 = [&](auto kern, int smem2, int ctas) -> int {
+                if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
+                const int g = T < sms * ctas ? T : sms * ctas;
+                kern<<<g, E2_NT + 32, smem2, s>>>(wmap, p);
+                return BKE_OK;
+            };
+            int rc2;
+            if (e2_variant == 1) rc2 = a.U ? launch2(k_emit2<true, 1, 3>, (int)sizeof(Emit2Shared<1>), 3) : launch2(k_emit2<false, 1, 3>, (int)sizeof(Emit2Shared<1>), 3);
+            else rc2 = a.U ? launch2(k_emit2<true, 2, 2>, (int)sizeof(Emit2Shared<2>), 2) : launch2(k_emit2<false, 2, 2>, (int)sizeof(Emit2Shared<2>), 2);
+            if (rc2 != BKE_OK) return rc2;
             if (a.U) k_emit_slow<true><<<slow_grid, BLOCK, emit_smem, s>>>(p);
             else k_emit_slow<false><<<slow_grid, BLOCK, emit_smem, s>>>(p);
         } else if (a.U) {
@@ -1688,7 +1696,7 @@ int bke_resample_shard_stage(const bke_resample_shard_args *args, const bke_resa
         if (rc != BKE_OK) return rc;
         a.carry_approx = ext->carry_approx_buf;
         a.carry_exact = ext->carry_exact_buf;
-        a.phase = 2;
+        a.phase = 2 | 16;                                  // 16: k_compose has left the scanned tile maps in the workspace
         rc = bke_resample_shard(&a, stream);
         if (rc != BKE_OK) return rc;
         a.phase = 4;
