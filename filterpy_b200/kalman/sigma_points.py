@@ -11,7 +11,7 @@ import torch
 from .. import _lib
 from .._dev import bke_dtype, require_cuda, stream_ptr
 
-__all__ = ["MerweScaledSigmaPoints"]
+__all__ = ["MerweScaledSigmaPoints", "JulierSigmaPoints"]
 
 
 class MerweScaledSigmaPoints(object):
@@ -77,3 +77,23 @@ class MerweScaledSigmaPoints(object):
     def __repr__(self):
         return "MerweScaledSigmaPoints(n=%d, alpha=%g, beta=%g, kappa=%g)" % (
             self.n, self.alpha, self.beta, self.kappa)
+
+
+class JulierSigmaPoints(MerweScaledSigmaPoints):
+    """Host mirror of ``filterpy.kalman.JulierSigmaPoints`` (filterpy/kalman/sigma_points.py:211-383):
+    sigma offsets = rows of chol_upper((n + kappa) P) (:352-361), Wm = Wc = [kappa, .5, .5, ...] / (n + kappa)
+    (:367-373).  That is the Merwe parameterisation with alpha = 1, beta = 0 (lambda = kappa), so the
+    fused UKF kernel and the stand-alone sigma-point kernel serve it unchanged."""
+
+    def __init__(self, n, kappa=0., sqrt_method=None, subtract=None):
+        MerweScaledSigmaPoints.__init__(self, n, 1.0, 0.0, kappa, sqrt_method=sqrt_method, subtract=subtract)
+
+    def _compute_weights(self):
+        """sigma_points.py:367-373."""
+        n, k = self.n, self.kappa
+        self.Wm = np.full(2 * n + 1, .5 / (n + k))
+        self.Wm[0] = k / (n + k)
+        self.Wc = self.Wm
+
+    def __repr__(self):
+        return "JulierSigmaPoints(n=%d, kappa=%g)" % (self.n, self.kappa)

@@ -163,6 +163,43 @@ def gen_ukf():
              **{"ref_" + k: np.array(v) for k, v in out.items()})
 
 
+def gen_ukf_julier():
+    """UKF banks driven by JulierSigmaPoints (sigma_points.py:211-383): kappa > 0 with the range/az/el
+    model, kappa < 0 (negative centre weight) with the linear one."""
+    from filterpy.kalman import JulierSigmaPoints
+    P = np.array([[4, .5, 0, 0], [.5, 2, 0, 0], [0, 0, 3, .2], [0, 0, .2, 1]], float)
+    x = np.arange(4.0)
+    sig = {}
+    for i, k in enumerate([0.0, 1.0, -1.0, 2.5]):
+        pts = JulierSigmaPoints(4, k)
+        sig.update({"kappa%d" % i: k, "sigmas%d" % i: pts.sigma_points(x, P), "Wm%d" % i: pts.Wm, "Wc%d" % i: pts.Wc})
+    save("julier_sigma", x=x, P=P, **sig)
+    for name, linear, kappa in (("ukf_julier_rae", False, 1.5), ("ukf_julier_lin", True, -2.0)):
+        N, steps, dt = 16, 5, 0.1
+        w = wl.ukf_bank_cv3d(N, seed=8642, steps=steps, dt=dt, linear_hx=linear)
+        F, Hlin = w["F"], w["H"]
+        fx = (lambda s, dt: F @ s) if linear else fx_cv
+        hx = (lambda s: Hlin @ s) if linear else hx_rae
+        valid = np.random.default_rng(4).random((steps, N)) >= 0.1
+        keys = ["x", "P", "x_prior", "P_prior", "K", "S", "y"]
+        out = {k: [] for k in keys}
+        ukfs = []
+        for f in range(N):
+            u = UnscentedKalmanFilter(6, 3, dt, hx, fx, JulierSigmaPoints(6, kappa))
+            u.x = w["x"][f].copy(); u.P = w["P"][f].copy(); u.Q = w["Q"][f]; u.R = w["R"][f]
+            ukfs.append(u)
+        for t in range(steps):
+            rec = {k: [] for k in keys}
+            for f, u in enumerate(ukfs):
+                u.predict()
+                u.update(w["zs"][t, f] if valid[t, f] else None)
+                for k in keys:
+                    rec[k].append(np.array(getattr(u, k), float).copy())
+            for k in keys:
+                out[k].append(np.array(rec[k]))
+        save(name, **w, valid=valid, dt=dt, kappa=kappa, **{"ref_" + k: np.array(v) for k, v in out.items()})
+
+
 # ----------------------------------------------------------------------------- resampling
 def gen_resample():
     cases = {}
@@ -347,6 +384,10 @@ def gen_mm():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:                       # e.g. `make_golden.py gen_ukf_julier`: only the named generators
+        for g in sys.argv[1:]:
+            globals()[g]()
+        sys.exit(0)
     gen_kf_c1()
     gen_kf_banks()
     gen_ukf()
@@ -355,3 +396,4 @@ if __name__ == "__main__":
     gen_rts()
     gen_ukf_rts()
     gen_mm()
+    gen_ukf_julier()

@@ -38,6 +38,39 @@ def test_ukf_bank_vs_reference_golden(golden, name, kind, dtype):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("name,kind", [("ukf_julier_rae", "rae"), ("ukf_julier_lin", "lin")])
+def test_ukf_julier_bank_vs_reference_golden(golden, name, kind, dtype):
+    """UKF bank on JulierSigmaPoints (sigma_points.py:211-383) against vectors from the reference;
+    the linear case has kappa < 0, i.e. a negative centre weight."""
+    from filterpy_b200.kalman import UnscentedKalmanFilter, JulierSigmaPoints, LinearFx, ConstVelFx, LinearHx, RangeAzElHx
+    g = golden(name)
+    pts = JulierSigmaPoints(6, float(g["kappa"]))
+    fx = LinearFx(g["F"]) if kind == "lin" else ConstVelFx()
+    hx = LinearHx(g["H"]) if kind == "lin" else RangeAzElHx()
+    u = UnscentedKalmanFilter(6, 3, float(g["dt"]), hx, fx, pts, n_filters=g["x"].shape[0], dtype=dtype)
+    u.x = g["x"]; u.P = g["P"]; u.Q = g["Q"]; u.R = g["R"]
+    rtol = RTOL[dtype]
+    for t in range(g["zs"].shape[0]):
+        v = g["valid"][t]
+        u.predict(); u.update(g["zs"][t], valid=v)
+        rel_close(u.x.cpu().numpy(), g["ref_x"][t], rtol, "x t=%d" % t)
+        rel_close(u.P.cpu().numpy(), g["ref_P"][t], rtol, "P t=%d" % t)
+        rel_close(u.x_prior.cpu().numpy(), g["ref_x_prior"][t], rtol, "x_prior")
+        rel_close(u.P_prior.cpu().numpy(), g["ref_P_prior"][t], rtol, "P_prior")
+        rel_close(u.K.cpu().numpy()[v], g["ref_K"][t][v], max(rtol, 1e-5), "K")
+        rel_close(u.S.cpu().numpy()[v], g["ref_S"][t][v], max(rtol, 1e-5), "S")
+        assert int(u.status.sum().item()) == 0
+
+
+def test_julier_sigma_points_standalone(golden):
+    from filterpy_b200.kalman import JulierSigmaPoints
+    g = golden("julier_sigma")
+    for i in range(4):
+        pts = JulierSigmaPoints(4, float(g["kappa%d" % i]))
+        rel_close(pts.sigma_points(g["x"], g["P"]), g["sigmas%d" % i], 1e-12, "julier sigmas kappa=%g" % pts.kappa)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_ukf_256k_vs_oracle_subset(dtype):
     """BASELINE config 4 size (2^18 filters, n=6, m=3, range/azimuth/elevation): full bank on the
     GPU, a 4096-filter random subset checked against the oracle, 3 epochs."""

@@ -103,6 +103,36 @@ def test_ukf_bank_vs_reference(golden, name, fxm, hxm):
         close(o["x_prior"], g["ref_x_prior"][t]); close(o["P_prior"], g["ref_P_prior"][t], 1e-8, 1e-9)
 
 
+@pytest.mark.parametrize("name,fxm,hxm", [("ukf_julier_rae", oukf.FX_CONST_VEL, oukf.HX_RANGE_AZ_EL),
+                                         ("ukf_julier_lin", oukf.FX_LINEAR, oukf.HX_LINEAR)])
+def test_ukf_julier_bank_vs_reference(golden, name, fxm, hxm):
+    """JulierSigmaPoints(kappa) (sigma_points.py:211-383) == the Merwe parameterisation alpha=1, beta=0."""
+    g = golden(name)
+    x, P = g["x"], g["P"]
+    k, dt = float(g["kappa"]), float(g["dt"])
+    for t in range(g["zs"].shape[0]):
+        o = oukf.ukf_step_bank(x, P, g["zs"][t], g["Q"], g["R"], dt, 1.0, 0.0, k, fxm, hxm,
+                               F=g["F"], H=g["H"], valid=g["valid"][t])
+        x, P = o["x"], o["P"]
+        close(x, g["ref_x"][t], rtol=1e-9, atol=1e-9); close(P, g["ref_P"][t], rtol=1e-8, atol=1e-9)
+        close(o["x_prior"], g["ref_x_prior"][t]); close(o["P_prior"], g["ref_P_prior"][t], 1e-8, 1e-9)
+
+
+def test_julier_weights_and_sigma_points(golden):
+    from filterpy_b200.kalman import JulierSigmaPoints
+    g = golden("julier_sigma")
+    for i in range(4):
+        k = float(g["kappa%d" % i])
+        pts = JulierSigmaPoints(4, k)
+        assert pts.num_sigmas() == 9 and (pts.alpha, pts.beta, pts.kappa) == (1.0, 0.0, k)
+        close(pts.Wm, g["Wm%d" % i], 1e-15); close(pts.Wc, g["Wc%d" % i], 1e-15)
+        Wm, Wc = oukf.merwe_weights(4, 1.0, 0.0, k)
+        close(Wm, g["Wm%d" % i], 1e-14); close(Wc, g["Wc%d" % i], 1e-14)
+        close(oukf.merwe_sigma_points(g["x"], g["P"], 1.0, 0.0, k), g["sigmas%d" % i], 1e-13)
+    with pytest.raises(NotImplementedError):
+        JulierSigmaPoints(4, 0., sqrt_method=np.linalg.cholesky)
+
+
 def test_ukf_single_matches_bank(golden):
     g = golden("ukf_bank_lin")
     a, b, k, dt = float(g["alpha"]), float(g["beta"]), float(g["kappa"]), float(g["dt"])
