@@ -79,11 +79,14 @@ struct Ws {
     int *ord2tile;          // [UMAX+SEQMAX]
     Run *runs;              // [max_runs]
     int *slow_list;         // [T] tiles that did not qualify for the fast path (order irrelevant)
+    u64 *st1;               // [T] status words of k_front's look-back (directly after the header: one memset clears both)
+    SM *ctot;               // [CHAIN_CTAS] composite of each chain CTA's tile range
     int max_runs;
     int T;
 };
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+constexpr int CHAIN_CTAS = 8;           // pass D runs as one thread-block cluster of this many CTAs
 
 size_t carve(int64_t n, unsigned char *base, Ws *w)
 {
@@ -92,6 +95,8 @@ size_t carve(int64_t n, unsigned char *base, Ws *w)
     auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return base ? base + o : nullptr; };
     unsigned char *p;
     p = take(sizeof(Header));                 if (w) w->hdr = (Header *)p;
+    p = take(sizeof(u64) * T);                if (w) w->st1 = (u64 *)p;
+    p = take(sizeof(SM) * CHAIN_CTAS);        if (w) w->ctot = (SM *)p;
     p = take(sizeof(double) * T);             if (w) w->tile_sum = (double *)p;
     p = take(sizeof(double) * (T + 1));       if (w) w->tile_prefix = (double *)p;
     p = take(sizeof(i64) * (T + 1));          if (w) w->S_in = (i64 *)p;
@@ -401,6 +406,139 @@ __global__ void __launch_bounds__(BLOCK, 3) k_tile_maps_fast(Params p)
     }
 }
 
+// ------------------------------------------------------------------ passes A + B + C in one launch
+// One CTA per tile, in blockIdx order.  The tile is read ONCE: its sum is published as a 64-bit status
+// word (value with the two low mantissa bits replaced by a flag: 1 = aggregate, 2 = inclusive prefix;
+// the perturbation is far inside the classification margin eb), warp 0 looks back over the earlier
+// tiles' words for the approximate exclusive prefix (decoupled look-back, one warp-wide window of 32
+// tiles per poll), and the fast-path map of k_tile_maps_fast is then computed from the registers the
+// loads landed in.  The approximate prefixes only have to be within eb of the exact running sum, which
+// holds for any summation order of non-negative terms.
+constexpr u64 ST_AGG = 1, ST_INCL = 2;
+constexpr int FRONT_SPINS = 1 << 20;      // polls of a blocked window before giving up (-> sequential fallback)
+constexpr int FRONT_LBK = 8;              // status words per lane and poll: a window of 256 tiles
+
+// With ~600 tiles in flight and one tile retiring every ~6 ns the nearest tile that already owns an
+// inclusive prefix is ~200 tiles back (poll latency / tile period), so a 32-tile window would need
+// 6-7 dependent polls; eight independent loads per lane cover that distance in one round trip.
+__device__ __forceinline__ double front_lookback(const Params &p, int t, int lane)
+{
+    double part = 0.0;                                     // this lane's share, reduced at the end
+    int idx = t - 1 - lane;
+    int spins = 0;
+    bool done = false;
+    while (!done) {
+        u64 v[FRONT_LBK];
+#pragma unroll
+        for (int j = 0; j < FRONT_LBK; j++) {
+            const int i = idx - 32 * j;
+            v[j] = (i >= 0) ? f_ld(p.ws.st1 + i) : ST_INCL;           // before the first tile: 0.0, inclusive
+        }
+        bool blocked = false;
+#pragma unroll
+        for (int j = 0; j < FRONT_LBK; j++) {
+            if (!done && !blocked) {
+                const unsigned incl = __ballot_sync(FULL, (v[j] & 3) == ST_INCL);
+                const unsigned empty = __ballot_sync(FULL, (v[j] & 3) == 0);
+                const int first = incl ? __ffs(incl) - 1 : 32;        // nearest tile with an inclusive prefix
+                const unsigned closer = first >= 32 ? FULL : ((1u << first) - 1u);
+                if (empty & closer) blocked = true;                   // a word this side of it is not there yet
+                else {
+                    if (lane <= first) part += __longlong_as_double((i64)(v[j] & ~3ull));
+                    if (incl) done = true; else idx -= 32;
+                }
+            }
+        }
+        if (blocked) {
+            if (++spins > FRONT_SPINS) { if (lane == 0) p.ws.hdr->fallback = 1; break; }
+            __nanosleep(40);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+    return part;
+}
+
+// Warps 0-7 own the tile's data; warp 8 starts the look-back the moment the CTA starts (it needs nothing
+// of this tile), so the prefix is usually there when the tile's own sum is.
+__global__ void __launch_bounds__(BLOCK + 32, 4) k_front(Params p)
+{
+    __shared__ double shd[BLOCK / 32];
+    __shared__ i64 shi[BLOCK / 32 + 1];
+    __shared__ double s_ex, s_tot;
+    const int t = blockIdx.x, T = p.ws.T;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (wid == BLOCK / 32) {
+        const double ex = front_lookback(p, t, lane);
+        if (lane == 0) s_ex = ex;
+        __syncthreads();
+        if (lane == 0) {
+            const double tot = s_tot;
+            f_st(p.ws.st1 + t, ((u64)__double_as_longlong(ex + tot) & ~3ull) | ST_INCL);
+            const double tp = (p.carry_approx ? *p.carry_approx : 0.0) + ex;
+            p.ws.tile_prefix[t] = tp;
+            if (t == T - 1) p.ws.tile_prefix[T] = tp + tot;
+        }
+        return;
+    }
+    double2 g[IPT / 2];
+    fetch_tile(p, t, g);
+    double s = 0.0;
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < IPT / 2; i++) {
+        if (!(g[i].x >= 0.0) || !(g[i].y >= 0.0) || isinf(g[i].x) || isinf(g[i].y)) bad = true;
+        s += g[i].x + g[i].y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    if (lane == 0) shd[wid] = s;
+    if (threadIdx.x == 0) shi[BLOCK / 32] = 0;             // "some weight of the tile is non-zero"
+    if (bad) p.ws.hdr->fallback = 1;
+    f_bar<BLOCK>();
+    if (wid == 0) {
+        double tot = 0.0;
+#pragma unroll
+        for (int i = 0; i < BLOCK / 32; i++) tot += shd[i];
+        if (lane == 0) { f_st(p.ws.st1 + t, ((u64)__double_as_longlong(tot) & ~3ull) | ST_AGG); p.ws.tile_sum[t] = tot; s_tot = tot; }
+    }
+    __syncthreads();
+    const double tp = (p.carry_approx ? *p.carry_approx : 0.0) + s_ex;
+    int e0;
+    const bool tile_clean = clean_add(tp, tp + s_tot, p.eb, &e0);      // the whole tile stays deep inside binade e0
+    const i64 base = (i64)e0 << 52;
+    const double B0 = __longlong_as_double(base), B1 = __longlong_as_double(base + 1);
+    i64 acc = 0;
+    bool ok = tile_clean, nz = false;
+#pragma unroll
+    for (int i = 0; i < IPT / 2; i++) {
+        const double w2[2] = {g[i].x, g[i].y};
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const i64 d0 = __double_as_longlong(__dadd_rn(B0, w2[h])) - base;
+            const i64 d1 = __double_as_longlong(__dadd_rn(B1, w2[h])) - (base + 1);
+            ok = ok && (d0 == d1);
+            nz = nz || (w2[h] != 0.0);
+            acc += d0;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+    nz = __any_sync(FULL, nz);
+    if (lane == 0) { shi[wid] = acc; if (nz) shi[BLOCK / 32] = 1; }
+    if (f_bar_and<BLOCK>(ok)) {
+        if (threadIdx.x == 0) {
+            i64 total = 0;
+#pragma unroll
+            for (int i = 0; i < BLOCK / 32; i++) total += shi[i];
+            p.ws.tile_k[t] = shi[BLOCK / 32] ? e0 : K_ID; p.ws.tile_d[t] = total; p.ws.tile_t[t] = 0;
+            p.ws.tile_slot[t] = SLOT_FAST;
+        }
+    } else if (threadIdx.x == 0) {
+        p.ws.slow_list[atomicAdd(&p.ws.hdr->n_slow, 1)] = t;
+    }
+}
+
 // General kernel over the slow list: ties, raw elements, sequential tiles.
 __global__ void __launch_bounds__(BLOCK, 2) k_tile_maps(Params p)
 {
@@ -479,13 +617,33 @@ __device__ __forceinline__ SM tile_el(const Ws &ws, int t)
 
 // Segmented exclusive scan of the tile maps (restart after every unclean tile): afterwards
 // run_*[t] = composite of the clean tiles since the last unclean tile before t, run_cnt[t] = number of
-// unclean tiles before t, ord2tile[i] = i-th unclean tile.  One CTA of CHAIN_THREADS threads.
-__device__ __forceinline__ void chain_scan(const Ws &ws, SM *wtot, int &bad)
+// unclean tiles before t, ord2tile[i] = i-th unclean tile.  NC CTAs of CHAIN_THREADS threads (one
+// thread-block cluster when NC > 1; csync() is its barrier): CTA `rank` owns a contiguous range of
+// tiles, the CTA totals meet in ws.ctot.
+struct ChainRange { int a, b; };
+__device__ __forceinline__ ChainRange chain_range(int T, int rank, int NC)
+{
+    const int wid = threadIdx.x >> 5;
+    const int per = ((T + CHAIN_THREADS * NC - 1) / (CHAIN_THREADS * NC)) * 32;      // tiles per warp, multiple of 32
+    const i64 a64 = (i64)(rank * (CHAIN_THREADS / 32) + wid) * per;
+    const int a = (int)(a64 < T ? a64 : T);
+    return ChainRange{a, min(T, a + per)};
+}
+
+// the CTA whose range holds tile T-1
+__device__ __forceinline__ bool chain_owns_last(int T, int rank, int NC)
+{
+    const int per = ((T + CHAIN_THREADS * NC - 1) / (CHAIN_THREADS * NC)) * 32;
+    return (T - 1) / (per * (CHAIN_THREADS / 32)) == rank;
+}
+
+template <typename Sync>
+__device__ __forceinline__ void chain_scan(const Ws &ws, SM *wtot, int &bad, int rank, int NC, Sync csync)
 {
     const int T = ws.T;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int per = ((T + CHAIN_THREADS - 1) / CHAIN_THREADS) * 32;
-    const int a = min(T, wid * per), b = min(T, a + per);
+    const ChainRange cr = chain_range(T, rank, NC);
+    const int a = cr.a, b = cr.b;
     SM carry_m = sm_identity();
     constexpr int PF = 4;                                    // rows fetched ahead (hides the load latency)
     for (int t0 = a; t0 < b; t0 += 32 * PF) {
@@ -511,9 +669,15 @@ __device__ __forceinline__ void chain_scan(const Ws &ws, SM *wtot, int &bad)
         SM prev = shfl_up_sm(inc, 1);
         if (lane == 0) prev = sm_identity();
         wtot[lane] = prev;                                    // exclusive prefix of the warp ranges
+        if (NC > 1 && lane == 31) { ws.ctot[rank] = inc; __threadfence(); }      // this CTA's composite
     }
-    __syncthreads();
-    const SM woff = wtot[wid];
+    if (NC > 1) csync(); else __syncthreads();
+    SM woff = wtot[wid];
+    if (NC > 1) {
+        SM coff = sm_identity();
+        for (int c = 0; c < rank; c++) coff = combine(coff, ws.ctot[c]);
+        woff = combine(coff, woff);
+    }
     for (int t0 = a + lane; t0 < b; t0 += 32 * PF) {
         SM loc[PF];
         int slot[PF];
@@ -533,13 +697,22 @@ __device__ __forceinline__ void chain_scan(const Ws &ws, SM *wtot, int &bad)
             }
         }
     }
-    __threadfence_block();
-    __syncthreads();
+    __threadfence();
+    if (NC > 1) csync(); else __syncthreads();
 }
 
-template <bool STRAT>
-__global__ void __launch_bounds__(CHAIN_THREADS) k_chain(Params p)
+// NC = 1: one CTA; NC = CHAIN_CTAS: one thread-block cluster, every CTA scans / finishes its own range of
+// tiles (the single CTA was bound by what one SM can move: ~4.6 MB of tile records at 2^26), CTA 0 walks
+// the tiles with raw elements while the others wait at the cluster barrier.
+template <bool STRAT, int NC>
+__device__ __forceinline__ void chain_body(const Params &p, int rank)
 {
+    auto csync = [] {
+        if (NC > 1) {
+            asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+            asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+        }
+    };
     __shared__ SM wtot[CHAIN_THREADS / 32];
     __shared__ Slot s_slots[CHAIN_BATCH];
     __shared__ double s_w[TILE];
@@ -549,17 +722,17 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain(Params p)
     const Ws &ws = p.ws;
     if (ws.hdr->fallback) return;
     const int T = ws.T;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) s_bad = 0;
     int bad = 0;
-    if (!p.scan_done) chain_scan(ws, wtot, bad);       // (k_compose has run it already in the staged multi-GPU sequence)
+    if (!p.scan_done) chain_scan(ws, wtot, bad, rank, NC, csync);     // (k_compose has run it already in the staged multi-GPU sequence)
     constexpr int PF = 4;
-    const int per = ((T + CHAIN_THREADS - 1) / CHAIN_THREADS) * 32;
-    const int a = min(T, wid * per), b = min(T, a + per);
+    const ChainRange cr = chain_range(T, rank, NC);
+    const int a = cr.a, b = cr.b;
     // ---- sequential part: one thread walks the tiles that contain raw elements.  Their slot data
     // is staged into shared memory by the whole block first (a dependent chain of global loads
     // would cost ~1 us per hop), CHAIN_BATCH tiles at a time.
-    {
+    if (rank == 0) {
         const int U = min(ws.hdr->n_unclean, UMAX) + min(ws.hdr->n_seq, SEQMAX);
         if (threadIdx.x == 0) {
             const double carry = p.carry_exact ? *p.carry_exact : 0.0;
@@ -615,8 +788,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain(Params p)
             i0 += nb;
         }
     }
-    __threadfence_block();
-    __syncthreads();
+    __threadfence();
+    if (NC > 1) csync(); else __syncthreads();
     // ---- parallel part: exact state before every tile, with verification of the clean tiles ---
     {
         const int U = min(ws.hdr->n_unclean, UMAX) + min(ws.hdr->n_seq, SEQMAX);
@@ -657,8 +830,19 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain(Params p)
     __syncthreads();
     if (threadIdx.x == 0) {
         if (s_bad) { ws.hdr->fallback = 1; ws.hdr->chain_bad = 1; }
-        else if (p.cumsum_last) *p.cumsum_last = __longlong_as_double(ws.S_in[T]);    // exact sum after this call's particles
+        // exact sum after this call's particles: written by the CTA that owns the last tile (the sequential
+        // kernel rewrites it when any CTA raised the fallback flag)
+        else if (p.cumsum_last && chain_owns_last(T, rank, NC)) *p.cumsum_last = __longlong_as_double(ws.S_in[T]);
     }
+}
+
+template <bool STRAT>
+__global__ void __launch_bounds__(CHAIN_THREADS) k_chain(Params p) { chain_body<STRAT, 1>(p, 0); }
+
+template <bool STRAT>
+__global__ void __cluster_dims__(CHAIN_CTAS, 1, 1) __launch_bounds__(CHAIN_THREADS) k_chain_cluster(Params p)
+{
+    chain_body<STRAT, CHAIN_CTAS>(p, (int)blockIdx.x);
 }
 
 // ------------------------------------------------------------------ multi-GPU: the shard's composite
@@ -679,7 +863,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_compose(Params p, Composite *
     if (threadIdx.x == 0) { out->n = 0; out->bad = ws.hdr->fallback ? 1 : 0; }
     if (ws.hdr->fallback) return;
     int bad = 0;
-    chain_scan(ws, wtot, bad);
+    chain_scan(ws, wtot, bad, 0, 1, [] {});
     __threadfence_block();
     __syncthreads();
     if (threadIdx.x != 0) return;
@@ -1544,16 +1728,32 @@ int run(const RunArgs &a, cudaStream_t s)
     const int sms = sm_count();
     const int slow_grid = T < sms * 2 ? T : sms * 2;
     if (a.phase & 1) {
-        if (!(a.phase & 8)) {                       // bit 8: the header reset and pass A have run already (bke_resample_shard_stage)
-            if (check_cuda(cudaMemsetAsync(p.ws.hdr, 0, sizeof(Header), s), "memset header")) return BKE_ERR_CUDA;
-            k_tile_sums<<<T, BLOCK, 0, s>>>(p);
+        // BKE_RS_FRONT=1: tile sums, their scan (decoupled look-back) and the fast maps in ONE pass over the
+        // weights.  Measured slower than the three launches it replaces (234-335 us vs 180 us at 2^26: with
+        // ~600 tiles in flight the nearest inclusive prefix is ~200 tiles back and the polling competes with
+        // the streaming loads; profiles/r2_resample_front.md), so it is an experiment, not the default.
+        static const bool fused_front = [] { const char *e = getenv("BKE_RS_FRONT"); return e && e[0] == '1'; }();
+        if (!(a.phase & 8) && fused_front) {
+            const size_t clr = (size_t)((unsigned char *)(p.ws.st1 + T) - (unsigned char *)p.ws.hdr);
+            if (check_cuda(cudaMemsetAsync(p.ws.hdr, 0, clr, s), "memset header + status words")) return BKE_ERR_CUDA;
+            k_front<<<T, BLOCK + 32, 0, s>>>(p);
+        } else {
+            if (!(a.phase & 8)) {                   // bit 8: the header reset and pass A have run already (bke_resample_shard_stage)
+                if (check_cuda(cudaMemsetAsync(p.ws.hdr, 0, sizeof(Header), s), "memset header")) return BKE_ERR_CUDA;
+                k_tile_sums<<<T, BLOCK, 0, s>>>(p);
+            }
+            k_scan_tiles<<<1, CHAIN_THREADS, 0, s>>>(p);
+            k_tile_maps_fast<<<T < sms * 3 ? T : sms * 3, BLOCK, 0, s>>>(p);
         }
-        k_scan_tiles<<<1, CHAIN_THREADS, 0, s>>>(p);
-        k_tile_maps_fast<<<T < sms * 3 ? T : sms * 3, BLOCK, 0, s>>>(p);
         k_tile_maps<<<slow_grid, BLOCK, 0, s>>>(p);
     }
     if (a.phase & 2) {
-        if (a.U) k_chain<true><<<1, CHAIN_THREADS, 0, s>>>(p);
+        // a cluster of CHAIN_CTAS CTAs once there are enough tiles to share out (BKE_RS_CHAIN=1: always one CTA)
+        static const bool one_cta = [] { const char *e = getenv("BKE_RS_CHAIN"); return e && e[0] == '1'; }();
+        if (T >= 2048 && !one_cta) {
+            if (a.U) k_chain_cluster<true><<<CHAIN_CTAS, CHAIN_THREADS, 0, s>>>(p);
+            else k_chain_cluster<false><<<CHAIN_CTAS, CHAIN_THREADS, 0, s>>>(p);
+        } else if (a.U) k_chain<true><<<1, CHAIN_THREADS, 0, s>>>(p);
         else k_chain<false><<<1, CHAIN_THREADS, 0, s>>>(p);
     }
     if (a.phase & 4) {
