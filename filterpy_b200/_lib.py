@@ -16,6 +16,7 @@ BKE_STATUS_OK, BKE_STATUS_SINGULAR_S, BKE_STATUS_NOT_PD = 0, 1, 2
 BKE_DO_PREDICT, BKE_DO_UPDATE, BKE_UPDATE_FIRST = 1, 2, 4
 BKE_FX_LINEAR, BKE_FX_CONST_VEL = 0, 1
 BKE_HX_LINEAR, BKE_HX_RANGE_AZ_EL, BKE_HX_RANGE_BEARING = 0, 1, 2
+BKE_FX_USER = BKE_HX_USER = 100
 
 # every symbol include/bke.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
@@ -25,6 +26,8 @@ EXPORTED_SYMBOLS = [
     "bke_weights_sum", "bke_weights_scale", "bke_resample_shard", "bke_resample_normalized",
     "bke_resample_composite_bytes", "bke_resample_shard_compose", "bke_resample_compose_carry", "bke_resample_shard_stage",
     "bke_merwe_sigma_points", "bke_unscented_transform",
+    "bke_ukf_model_compile", "bke_ukf_model_log", "bke_ukf_model_registers", "bke_ukf_model_free", "bke_ukf_step_model",
+    "bke_debug_ukf_model_cubin_bytes",
     "bke_kf_rts_smoother", "bke_ukf_rts_smoother", "bke_mm_probabilities", "bke_mm_mix", "bke_mm_estimate", "bke_cumsum_exact", "bke_searchsorted", "bke_multinomial_resample", "bke_gather_rows",
 ]
 
@@ -162,6 +165,26 @@ def lib_path():
     return _build.LIB
 
 
+def _point_at_nvrtc():
+    """User-supplied UKF models are compiled by NVRTC, which libbke.so dlopens on first use: prefer the toolkit's
+    copy, else the one pip installed next to torch's CUDA libraries (BKE_NVRTC_LIB overrides both)."""
+    if os.environ.get("BKE_NVRTC_LIB"):
+        return
+    import glob
+    import sys
+    cands = sorted(glob.glob("/usr/local/cuda/lib64/libnvrtc.so.1*"))
+    for sp in sys.path:
+        cands += sorted(glob.glob(os.path.join(sp, "nvidia", "cuda_nvrtc", "lib", "libnvrtc.so.1*")))
+    if cands:
+        os.environ["BKE_NVRTC_LIB"] = cands[0]
+
+
+def kernel_include_dirs():
+    """Directories NVRTC reads the engine's kernel headers from (bke_ukf_model_compile)."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    return os.path.join(here, "csrc") + ":" + os.path.join(os.path.dirname(here), "include")
+
+
 def load():
     """Load (building first if the sources are newer) and type the library."""
     global _lib
@@ -179,6 +202,7 @@ def load():
         if not os.path.exists(path):
             raise BkeError("libbke.so is missing and could not be built (%s); the engine has no "
                            "CPU fallback" % e)
+    _point_at_nvrtc()
     lib = ctypes.CDLL(path)
     lib.bke_abi_version.restype = ctypes.c_int
     lib.bke_last_error.restype = ctypes.c_char_p
@@ -189,6 +213,19 @@ def load():
     lib.bke_kf_batch_filter.restype = ctypes.c_int
     lib.bke_ukf_step.argtypes = [ctypes.POINTER(UkfArgs), c_void_p]
     lib.bke_ukf_step.restype = ctypes.c_int
+    lib.bke_ukf_model_compile.argtypes = [c_int32, c_int32, c_int32, c_int32, c_int32, ctypes.c_char_p, ctypes.c_char_p,
+                                          ctypes.POINTER(c_void_p)]
+    lib.bke_ukf_model_compile.restype = ctypes.c_int
+    lib.bke_ukf_model_log.argtypes = [c_void_p]
+    lib.bke_ukf_model_log.restype = ctypes.c_char_p
+    lib.bke_ukf_model_registers.argtypes = [c_void_p, c_int32]
+    lib.bke_ukf_model_registers.restype = ctypes.c_int
+    lib.bke_ukf_model_free.argtypes = [c_void_p]
+    lib.bke_ukf_model_free.restype = None
+    lib.bke_ukf_step_model.argtypes = [ctypes.POINTER(UkfArgs), c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]
+    lib.bke_ukf_step_model.restype = ctypes.c_int
+    lib.bke_debug_ukf_model_cubin_bytes.argtypes = [c_int32, c_int32, c_int32, c_int32, c_int32, ctypes.c_char_p, ctypes.c_char_p]
+    lib.bke_debug_ukf_model_cubin_bytes.restype = c_size_t
     lib.bke_resample_workspace_bytes.argtypes = [c_int64]
     lib.bke_resample_workspace_bytes.restype = c_size_t
     lib.bke_systematic_resample.argtypes = [c_int64, c_void_p, c_double, c_void_p, c_void_p, c_size_t,

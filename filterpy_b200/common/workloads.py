@@ -156,6 +156,70 @@ def ukf_bank_cv3d(N, seed=2468, steps=1, dt=0.1, dtype=np.float64, linear_hx=Fal
     return {k: np.ascontiguousarray(v, dtype=dtype) for k, v in out.items()}
 
 
+# ----------------------------------------------------------------------------- user-supplied UKF models
+# A process / measurement pair outside the built-in set, once as CUDA source text (DeviceFx / DeviceHx)
+# and once as the Python callables the reference takes (tests/golden/make_golden.py runs those).
+CT_FX_SOURCE = """
+// coordinated turn, state (px, vx, py, vy); args[0] = turn rate omega [rad/s]
+__device__ void fx(const real *x, real *out, real dt, const real *args)
+{
+    const real w = args[0], s = sin(w * dt), c = cos(w * dt);
+    out[0] = x[0] + (s / w) * x[1] - ((1 - c) / w) * x[3];
+    out[1] = c * x[1] - s * x[3];
+    out[2] = x[2] + ((1 - c) / w) * x[1] + (s / w) * x[3];
+    out[3] = s * x[1] + c * x[3];
+}
+"""
+OFFSET_RB_HX_SOURCE = """
+// range and bearing from a sensor at (args[0], args[1])
+__device__ void hx(const real *x, real *z, const real *args)
+{
+    const real dx = x[0] - args[0], dy = x[2] - args[1];
+    z[0] = sqrt(dx * dx + dy * dy);
+    z[1] = atan2(dy, dx);
+}
+"""
+
+
+def ct_fx(x, dt, omega):
+    s, c = np.sin(omega * dt), np.cos(omega * dt)
+    return np.array([x[0] + (s / omega) * x[1] - ((1 - c) / omega) * x[3],
+                     c * x[1] - s * x[3],
+                     x[2] + ((1 - c) / omega) * x[1] + (s / omega) * x[3],
+                     s * x[1] + c * x[3]])
+
+
+def offset_rb_hx(x, sx, sy):
+    dx, dy = x[0] - sx, x[2] - sy
+    return np.array([np.sqrt(dx * dx + dy * dy), np.arctan2(dy, dx)])
+
+
+def ukf_bank_ct2d(N, seed=9753, steps=1, dt=0.5, dtype=np.float64, linear_hx=False):
+    """N coordinated-turn targets (per-filter turn rate ``omega``) seen by a range / bearing sensor at
+    ``sensor`` (or, ``linear_hx``, by a position sensor); targets stay right of the sensor, away from
+    the +-pi bearing cut (the default residual does not wrap, UKF.py:327-335)."""
+    rng = np.random.default_rng(seed)
+    sensor = np.array([-50.0, 20.0])
+    omega = rng.uniform(0.02, 0.12, N) * rng.choice([-1.0, 1.0], N)
+    xt = np.stack([rng.uniform(200, 600, N), rng.uniform(-8, 8, N), rng.uniform(-200, 200, N), rng.uniform(-8, 8, N)], 1)
+    x0 = xt + rng.standard_normal((N, 4)) * np.array([3, .5, 3, .5])
+    P0 = np.zeros((N, 4, 4))
+    P0[:, np.arange(4), np.arange(4)] = rng.uniform(1.0, 16.0, (N, 4))
+    q = np.exp(rng.uniform(np.log(1e-3), np.log(1e-1), N))
+    qb = q_white_noise_block(2, np.full(N, dt), q)
+    Q = _block_diag([qb, qb])
+    sig = np.array([1.0, 1.0]) if linear_hx else np.array([1.5, 0.004])
+    R = np.broadcast_to(np.diag(sig ** 2), (N, 2, 2)).copy()
+    zs = np.zeros((steps, N, 2))
+    for t in range(steps):
+        xt = np.stack([ct_fx(xt[f], dt, omega[f]) for f in range(N)])
+        h = xt[:, [0, 2]] if linear_hx else np.stack([offset_rb_hx(xt[f], *sensor) for f in range(N)])
+        zs[t] = h + sig * rng.standard_normal((N, 2))
+    Hlin = np.zeros((2, 4)); Hlin[0, 0] = Hlin[1, 2] = 1
+    out = dict(x=x0, P=P0, Q=Q, R=R, zs=zs, H=Hlin, omega=omega, sensor=sensor)
+    return {k: np.ascontiguousarray(v, dtype=dtype) for k, v in out.items()}
+
+
 def resample_weights(N, kind="heavy", seed=97):
     """Config C5 weights (fp64, normalised on the host with ``w /= w.sum()``)."""
     rng = np.random.default_rng(seed)

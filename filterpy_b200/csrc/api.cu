@@ -6,7 +6,7 @@
 
 namespace bke {
 
-static thread_local char g_err[512] = "";
+static thread_local char g_err[8192] = "";     // room for an NVRTC log (bke_ukf_model_compile)
 
 void set_error(const char *fmt, ...)
 {

@@ -1,17 +1,21 @@
 // Internal helpers shared by the sm_100a kernels of the engine (not part of the C-ABI).
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#endif
 #include "../../include/bke.h"
 
 namespace bke {
 
+#ifndef __CUDACC_RTC__
 void set_error(const char *fmt, ...);
 int check_cuda(cudaError_t e, const char *what);
 
 // Number of SMs of the current device (cached).
 int sm_count();
+#endif
 
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -22,6 +26,7 @@ template <> struct DType<double> { static constexpr int id = BKE_F64; };
 // log(2*pi)
 constexpr double LOG_2PI = 1.8378770664093454835606594728112;
 
+#ifndef __CUDACC_RTC__
 // ---- launchers implemented in the .cu files ---------------------------------------------
 int launch_kf_generic(const bke_kf_args &a, cudaStream_t s);
 // returns BKE_ERR_UNSUPPORTED when the specialised kernel does not cover the call
@@ -32,5 +37,6 @@ int launch_kf_direct(const bke_kf_args &a, cudaStream_t s);
 int launch_kf_any(const bke_kf_args &a, cudaStream_t s);
 int launch_kf_batch(const bke_kf_batch_args &a, cudaStream_t s);
 int launch_ukf(const bke_ukf_args &a, cudaStream_t s);
+#endif
 
 }  // namespace bke

@@ -28,7 +28,8 @@ from .. import _lib
 from .._dev import bke_dtype, ptr, require_cuda, resolve_dtype, stream_ptr, to_dev
 from .kalman_filter import _Linked
 
-__all__ = ["UnscentedKalmanFilter", "LinearFx", "ConstVelFx", "LinearHx", "RangeAzElHx", "RangeBearingHx"]
+__all__ = ["UnscentedKalmanFilter", "LinearFx", "ConstVelFx", "LinearHx", "RangeAzElHx", "RangeBearingHx",
+           "DeviceFx", "DeviceHx"]
 
 
 class LinearFx(object):
@@ -60,6 +61,79 @@ class RangeBearingHx(object):
     H = None
 
 
+class _DeviceModel(object):
+    """A process / measurement function given as CUDA C++ source text (the reference takes Python callables:
+    UKF.py:284-288, called per sigma point at :521-522 / :463-464).  The text defines, for the element
+    type ``real`` (float or double, whichever the filter uses; ``BKE_DIM_X`` / ``BKE_DIM_Z`` are defined)::
+
+        __device__ void fx(const real *x, real *x_out, real dt, const real *args)      # DeviceFx
+        __device__ void hx(const real *x, real *z_out, const real *args)               # DeviceHx
+
+    ``arg_names`` are the keyword arguments of the reference's callable (``predict(**fx_args)`` /
+    ``update(z, **hx_args)``), delivered to the function as ``args[0..]`` in that order; ``defaults`` gives
+    their values until a call overrides them.  A value is a scalar (whole bank) or an array ``(N,)``
+    (one per filter).  The text is compiled at run time into an instance of the same kernel the built-in
+    models use (NVRTC, sm_100a; ``csrc/ukf_rtc.cu``)."""
+    F = None
+    H = None
+
+    def __init__(self, source, arg_names=(), **defaults):
+        self.source = str(source)
+        self.arg_names = tuple(arg_names)
+        unknown = set(defaults) - set(self.arg_names)
+        if unknown:
+            raise TypeError("defaults for unknown arguments: %s" % sorted(unknown))
+        self.values = dict(defaults)
+
+    def pack(self, overrides, n_filters, dtype, device):
+        """args vector(s) for the kernel: (tensor or None, stride)."""
+        unknown = set(overrides) - set(self.arg_names)
+        if unknown:
+            raise TypeError("unexpected keyword arguments %s (declared: %s)" % (sorted(unknown), list(self.arg_names)))
+        self.values.update(overrides)
+        if not self.arg_names:
+            return None, 0
+        missing = [k for k in self.arg_names if k not in self.values]
+        if missing:
+            raise TypeError("missing values for the model arguments %s" % missing)
+        vals = [self.values[k] for k in self.arg_names]
+        if all(np.ndim(v) == 0 and not isinstance(v, torch.Tensor) for v in vals):
+            return torch.tensor([float(v) for v in vals], dtype=dtype, device=device), 0
+        cols = []
+        for k, v in zip(self.arg_names, vals):
+            t = torch.as_tensor(v, device=device).to(dtype).reshape(-1)
+            if t.numel() == 1:
+                t = t.expand(n_filters)
+            if t.numel() != n_filters:
+                raise ValueError("argument %s must be a scalar or have one value per filter (%d)" % (k, n_filters))
+            cols.append(t)
+        return torch.stack(cols, dim=1).contiguous(), len(cols)
+
+
+class DeviceFx(_DeviceModel):
+    model = _lib.BKE_FX_USER
+
+
+class DeviceHx(_DeviceModel):
+    model = _lib.BKE_HX_USER
+
+
+_compiled_models = {}
+
+
+def _compile_model(lib, dim_x, dim_z, dtype_id, fx, hx):
+    """One NVRTC build per (shape, dtype, source); shared by every filter object that uses it."""
+    src = "\n".join(m.source for m in (fx, hx) if isinstance(m, _DeviceModel))
+    key = (dim_x, dim_z, dtype_id, fx.model, hx.model, src)
+    h = _compiled_models.get(key)
+    if h is None:
+        out = ctypes.c_void_p()
+        _lib.check(lib.bke_ukf_model_compile(dim_x, dim_z, dtype_id, fx.model, hx.model, src.encode(),
+                                             _lib.kernel_include_dirs().encode(), ctypes.byref(out)))
+        h = _compiled_models[key] = out
+    return h
+
+
 def _no_hook(name, v):
     if v is not None:
         raise NotImplementedError(
@@ -77,8 +151,8 @@ class UnscentedKalmanFilter(object):
         if not hasattr(fx, "model") or not hasattr(hx, "model"):
             raise NotImplementedError(
                 "fx / hx must be device-side models (LinearFx, ConstVelFx, LinearHx, RangeAzElHx, "
-                "RangeBearingHx): Python callables cannot run inside the CUDA kernel and there is no "
-                "CPU fallback")
+                "RangeBearingHx, or DeviceFx / DeviceHx around CUDA source text): Python callables cannot "
+                "run inside the CUDA kernel and there is no CPU fallback")
         if points.n != dim_x:
             raise ValueError("expected size(x) {}, but size is {}".format(points.n, dim_x))   # sigma_points.py:153
         self._dim_x, self._dim_z = int(dim_x), int(dim_z)
@@ -103,6 +177,15 @@ class UnscentedKalmanFilter(object):
         self._H = None if hx.H is None else self._model(hx.H, m, n, "H")
         self._pending = None
         self._z = None
+        self._user_model = None
+        self._fx_args = self._hx_args = (None, 0)
+        if isinstance(fx, _DeviceModel) or isinstance(hx, _DeviceModel):
+            with torch.cuda.device(self._device):
+                self._user_model = _compile_model(self._lib, n, m, bke_dtype(self._dtype), fx, hx)
+            if isinstance(fx, _DeviceModel):
+                self._fx_args = fx.pack({}, N, self._dtype, self._device) if all(k in fx.values for k in fx.arg_names) else (None, 0)
+            if isinstance(hx, _DeviceModel):
+                self._hx_args = hx.pack({}, N, self._dtype, self._device) if all(k in hx.values for k in hx.arg_names) else (None, 0)
         if self.diagnostics:
             self._x_prior = self._x.clone(); self._P_prior = self._P.clone()
             self._x_post = self._x.clone(); self._P_post = self._P.clone()
@@ -230,8 +313,11 @@ class UnscentedKalmanFilter(object):
         """UKF.py:364-411 (deferred and fused with the next ``update``)."""
         _no_hook("UT", UT); _no_hook("fx", fx)
         if fx_args:
-            raise NotImplementedError("fx_args are arguments of a Python callback; not available on the GPU path")
+            if not isinstance(self.fx, _DeviceModel):
+                raise NotImplementedError("fx_args are arguments of a Python callback; the built-in process models take none")
         self._flush()
+        if fx_args:
+            self._fx_args = self.fx.pack(fx_args, self.n_filters, self._dtype, self._device)
         self._pending = self._dt if dt is None else dt
 
     def _flush(self):
@@ -248,7 +334,9 @@ class UnscentedKalmanFilter(object):
         fresh object).  After ``predict(); update(z)`` the two agree."""
         _no_hook("UT", UT); _no_hook("hx", hx)
         if hx_args:
-            raise NotImplementedError("hx_args are arguments of a Python callback; not available on the GPU path")
+            if not isinstance(self.hx, _DeviceModel):
+                raise NotImplementedError("hx_args are arguments of a Python callback; the built-in measurement models take none")
+            self._hx_args = self.hx.pack(hx_args, self.n_filters, self._dtype, self._device)
         dt, self._pending = self._pending, None
         if z is None:                                            # UKF.py:442-446
             if dt is not None:
@@ -295,7 +383,14 @@ class UnscentedKalmanFilter(object):
                 a.log_likelihood = ptr(self._ll)
             a.status = ptr(self._status)
         with torch.cuda.device(self._device):
-            _lib.check(self._lib.bke_ukf_step(a, stream_ptr(self._device)))
+            if self._user_model is not None:
+                for nm, mdl, (t, _) in (("fx", self.fx, self._fx_args), ("hx", self.hx, self._hx_args)):
+                    if isinstance(mdl, _DeviceModel) and mdl.arg_names and t is None:
+                        raise TypeError("%s needs values for its arguments %s" % (nm, list(mdl.arg_names)))
+                _lib.check(self._lib.bke_ukf_step_model(a, self._user_model, ptr(self._fx_args[0]), self._fx_args[1],
+                                                        ptr(self._hx_args[0]), self._hx_args[1], stream_ptr(self._device)))
+            else:
+                _lib.check(self._lib.bke_ukf_step(a, stream_ptr(self._device)))
         if self.diagnostics and (flags & _lib.BKE_DO_UPDATE):
             self._x_post.copy_(self._x); self._P_post.copy_(self._P)
         if self.diagnostics and self._single:
@@ -307,6 +402,8 @@ class UnscentedKalmanFilter(object):
         ``(T,n,n)``.  ``dts``: None (the filter's dt), a scalar, or one value per epoch.  ``Qs`` is
         accepted and, exactly like the reference (:715 uses ``self.Q``), not used."""
         _no_hook("UT", UT)
+        if isinstance(self.fx, _DeviceModel):
+            raise NotImplementedError("rts_smoother runs the built-in process models only (csrc/kf_rts.cu)")
         if len(Xs) != len(Ps):
             raise ValueError('Xs and Ps must have the same length')
         self._flush()

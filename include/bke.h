@@ -23,8 +23,13 @@
 #ifndef BKE_H_
 #define BKE_H_
 
+#ifndef __CUDACC_RTC__
 #include <stddef.h>
 #include <stdint.h>
+#else   /* NVRTC (run-time compiled UKF models, bke_ukf_model_compile) has no libc headers */
+typedef signed char int8_t; typedef unsigned char uint8_t; typedef int int32_t; typedef unsigned int uint32_t;
+typedef long long int64_t; typedef unsigned long long uint64_t; typedef unsigned long size_t;
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -134,6 +139,8 @@ int bke_kf_batch_filter(const bke_kf_batch_args *args, void *stream);
 #define BKE_HX_LINEAR 0          /* z = H x                       (H[m,n]) */
 #define BKE_HX_RANGE_AZ_EL 1     /* n=6 (x,vx,y,vy,z,vz) -> (range, azimuth, elevation), m=3 */
 #define BKE_HX_RANGE_BEARING 2   /* n=4 (x,vx,y,vy) -> (range, bearing), m=2 */
+#define BKE_FX_USER 100          /* device function supplied as source text: bke_ukf_model_compile (below) */
+#define BKE_HX_USER 100
 
 typedef struct bke_ukf_args {
     int64_t n_filters;
@@ -158,6 +165,32 @@ typedef struct bke_ukf_args {
 } bke_ukf_args;
 
 int bke_ukf_step(const bke_ukf_args *args, void *stream);
+
+/* User-supplied process / measurement functions.
+ * The reference's UnscentedKalmanFilter takes fx(x, dt, **fx_args) and hx(x, **hx_args) as Python
+ * callables (filterpy/kalman/UKF.py:284-288; called once per sigma point at :521-522 and :463-464).  The
+ * drop-in takes them as CUDA C++ source text and compiles a kernel instance around them at run time
+ * (NVRTC, sm_100a; the same kernel text as the pre-built instances).  `source` defines, for the element
+ * type `real` (a typedef of float / double the program text provides; BKE_DIM_X / BKE_DIM_Z are
+ * #defined):
+ *     __device__ void fx(const real *x, real *x_out, real dt, const real *args);     when fx_model == BKE_FX_USER
+ *     __device__ void hx(const real *x, real *z_out, const real *args);              when hx_model == BKE_HX_USER
+ * The other function may be one of the built-ins (BKE_FX_LINEAR, BKE_FX_CONST_VEL, BKE_HX_LINEAR).
+ * `include_dirs`: ':'-separated directories holding the engine's kernel headers (filterpy_b200/csrc).
+ * `args` of bke_ukf_step_model: device vectors handed to fx / hx (the keyword arguments of the reference's
+ * callables), one for the bank (stride 0) or one per filter (stride = elements per filter); may be NULL.
+ * A source that does not compile returns BKE_ERR_BAD_ARG with the compiler log in bke_last_error(). */
+typedef struct bke_ukf_model bke_ukf_model;
+int bke_ukf_model_compile(int32_t dim_x, int32_t dim_z, int32_t dtype, int32_t fx_model, int32_t hx_model, const char *source,
+                          const char *include_dirs, bke_ukf_model **out);
+const char *bke_ukf_model_log(const bke_ukf_model *model);                 /* NVRTC's log (warnings) */
+int bke_ukf_model_registers(const bke_ukf_model *model, int32_t extras);   /* registers per thread of the instance */
+void bke_ukf_model_free(bke_ukf_model *model);
+int bke_ukf_step_model(const bke_ukf_args *args, const bke_ukf_model *model, const void *fx_args, int64_t fx_args_stride,
+                       const void *hx_args, int64_t hx_args_stride, void *stream);
+/* the NVRTC half alone (needs no GPU): size of the sm_100a cubin, 0 on failure (log in bke_last_error()) */
+size_t bke_debug_ukf_model_cubin_bytes(int32_t dim_x, int32_t dim_z, int32_t dtype, int32_t fx_model, int32_t hx_model,
+                                       const char *source, const char *include_dirs);
 
 /* Stand-alone pieces of the unscented path for callers that use them directly:
  *   MerweScaledSigmaPoints.sigma_points(x, P)   filterpy/kalman/sigma_points.py:124-177

@@ -200,6 +200,40 @@ def gen_ukf_julier():
         save(name, **w, valid=valid, dt=dt, kappa=kappa, **{"ref_" + k: np.array(v) for k, v in out.items()})
 
 
+def gen_ukf_user():
+    """UKF banks with fx / hx OUTSIDE the built-in set: the reference runs the Python callables of
+    workloads.py (coordinated turn with a per-filter turn rate passed as fx_args, range / bearing from
+    an offset sensor passed as hx_args); the GPU side compiles the CUDA text of the same functions."""
+    for name, linear in (("ukf_user_ct_rb", False), ("ukf_user_ct_lin", True)):
+        N, steps, dt = 16, 6, 0.5
+        w = wl.ukf_bank_ct2d(N, steps=steps, dt=dt, linear_hx=linear)
+        Hlin, sensor = w["H"], w["sensor"]
+        hx = (lambda s: Hlin @ s) if linear else wl.offset_rb_hx
+        valid = np.random.default_rng(5).random((steps, N)) >= 0.1
+        keys = ["x", "P", "x_prior", "P_prior", "K", "S", "y"]
+        out = {k: [] for k in keys}
+        ukfs = []
+        for f in range(N):
+            u = UnscentedKalmanFilter(4, 2, dt, hx, wl.ct_fx, MerweScaledSigmaPoints(4, 0.5, 2.0, 0.0))
+            u.x = w["x"][f].copy(); u.P = w["P"][f].copy(); u.Q = w["Q"][f]; u.R = w["R"][f]
+            ukfs.append(u)
+        for t in range(steps):
+            rec = {k: [] for k in keys}
+            for f, u in enumerate(ukfs):
+                u.predict(omega=w["omega"][f])
+                z = w["zs"][t, f] if valid[t, f] else None
+                if linear:
+                    u.update(z)
+                else:
+                    u.update(z, sx=sensor[0], sy=sensor[1])
+                for k in keys:
+                    rec[k].append(np.array(getattr(u, k), float).copy())
+            for k in keys:
+                out[k].append(np.array(rec[k]))
+        save(name, **w, valid=valid, dt=dt, alpha=0.5, beta=2.0, kappa=0.0,
+             **{"ref_" + k: np.array(v) for k, v in out.items()})
+
+
 # ----------------------------------------------------------------------------- resampling
 def gen_resample():
     cases = {}
@@ -397,3 +431,4 @@ if __name__ == "__main__":
     gen_ukf_rts()
     gen_mm()
     gen_ukf_julier()
+    gen_ukf_user()

@@ -62,6 +62,56 @@ def test_ukf_julier_bank_vs_reference_golden(golden, name, kind, dtype):
         assert int(u.status.sum().item()) == 0
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("name,linear", [("ukf_user_ct_rb", False), ("ukf_user_ct_lin", True)])
+def test_ukf_user_models_vs_reference_golden(golden, name, linear, dtype):
+    """fx / hx OUTSIDE the built-in set, compiled at run time from CUDA text (NVRTC): coordinated turn with a
+    per-filter turn rate (fx_args of UKF.predict, UKF.py:364) and range / bearing from an offset sensor
+    (hx_args of UKF.update, UKF.py:413) — against the reference run with the same functions as Python
+    callables; the second case pairs the user fx with the built-in linear hx."""
+    from filterpy_b200.kalman import UnscentedKalmanFilter, MerweScaledSigmaPoints, DeviceFx, DeviceHx, LinearHx
+    from filterpy_b200.common import workloads as wl
+    g = golden(name)
+    N = g["x"].shape[0]
+    fx = DeviceFx(wl.CT_FX_SOURCE, arg_names=("omega",))
+    hx = LinearHx(g["H"]) if linear else DeviceHx(wl.OFFSET_RB_HX_SOURCE, arg_names=("sx", "sy"))
+    pts = MerweScaledSigmaPoints(4, float(g["alpha"]), float(g["beta"]), float(g["kappa"]))
+    u = UnscentedKalmanFilter(4, 2, float(g["dt"]), hx, fx, pts, n_filters=N, dtype=dtype)
+    u.x = g["x"]; u.P = g["P"]; u.Q = g["Q"]; u.R = g["R"]
+    rtol = RTOL[dtype]
+    for t in range(g["zs"].shape[0]):
+        v = g["valid"][t]
+        u.predict(omega=g["omega"])
+        if linear:
+            u.update(g["zs"][t], valid=v)
+        else:
+            u.update(g["zs"][t], valid=v, sx=float(g["sensor"][0]), sy=float(g["sensor"][1]))
+        rel_close(u.x.cpu().numpy(), g["ref_x"][t], rtol, "x t=%d" % t)
+        rel_close(u.P.cpu().numpy(), g["ref_P"][t], rtol, "P t=%d" % t)
+        rel_close(u.x_prior.cpu().numpy(), g["ref_x_prior"][t], rtol, "x_prior")
+        rel_close(u.P_prior.cpu().numpy(), g["ref_P_prior"][t], rtol, "P_prior")
+        rel_close(u.K.cpu().numpy()[v], g["ref_K"][t][v], max(rtol, 1e-5), "K")
+        rel_close(u.S.cpu().numpy()[v], g["ref_S"][t][v], max(rtol, 1e-5), "S")
+        assert int(u.status.sum().item()) == 0
+
+
+def test_ukf_user_model_errors():
+    from filterpy_b200 import _lib
+    from filterpy_b200.kalman import UnscentedKalmanFilter, MerweScaledSigmaPoints, DeviceFx, LinearHx
+    from filterpy_b200.common import workloads as wl
+    pts = MerweScaledSigmaPoints(4, .5, 2., 0.)
+    H = np.eye(2, 4)
+    with pytest.raises(_lib.BkeError, match="no_such_thing"):     # the compiler's message reaches the caller
+        UnscentedKalmanFilter(4, 2, .1, LinearHx(H), DeviceFx("__device__ void fx(const real *x, real *o, real dt, const real *a) { o[0] = no_such_thing; }"),
+                              pts, n_filters=4)
+    u = UnscentedKalmanFilter(4, 2, .1, LinearHx(H), DeviceFx(wl.CT_FX_SOURCE, arg_names=("omega",)), pts, n_filters=4)
+    u.predict()
+    with pytest.raises(TypeError, match="omega"):                 # the model's argument has no value
+        u.update(np.zeros((4, 2)))
+    with pytest.raises(NotImplementedError):
+        u.rts_smoother(np.zeros((2, 4, 4)), np.zeros((2, 4, 4, 4)))
+
+
 def test_julier_sigma_points_standalone(golden):
     from filterpy_b200.kalman import JulierSigmaPoints
     g = golden("julier_sigma")

@@ -156,3 +156,43 @@ def test_exchange_plan_covers_every_output_exactly_once():
                     g_lo, g_hi = b[r] + lo, b[r] + hi
                     assert out_ranges[src][0] <= g_lo and g_hi <= out_ranges[src][1]
             assert (got == 1).all()
+
+
+# ------------------------------------------------------------------ user-supplied UKF models (NVRTC half, no GPU)
+def test_user_ukf_model_text_compiles_for_sm100a():
+    """The program text bke_ukf_model_compile builds around DeviceFx / DeviceHx sources compiles with NVRTC for
+    sm_100a (both element types, user fx + user hx and user fx + built-in hx); a broken source comes back
+    with the compiler's message."""
+    from filterpy_b200 import _lib
+    from filterpy_b200.common import workloads as wl
+    lib = _lib.load()
+    inc = _lib.kernel_include_dirs().encode()
+    src = (wl.CT_FX_SOURCE + wl.OFFSET_RB_HX_SOURCE).encode()
+    for dt in (_lib.BKE_F32, _lib.BKE_F64):
+        assert lib.bke_debug_ukf_model_cubin_bytes(4, 2, dt, _lib.BKE_FX_USER, _lib.BKE_HX_USER, src, inc) > 10000, lib.bke_last_error()
+    assert lib.bke_debug_ukf_model_cubin_bytes(4, 2, _lib.BKE_F64, _lib.BKE_FX_USER, _lib.BKE_HX_LINEAR, wl.CT_FX_SOURCE.encode(), inc) > 10000
+    bad = b"__device__ void fx(const real *x, real *out, real dt, const real *args) { out[0] = undefined_symbol; }"
+    assert lib.bke_debug_ukf_model_cubin_bytes(4, 2, _lib.BKE_F64, _lib.BKE_FX_USER, _lib.BKE_HX_LINEAR, bad, inc) == 0
+    msg = lib.bke_last_error().decode()
+    assert "undefined_symbol" in msg and "user_model.cu" in msg
+    # neither function user-supplied / unsupported built-in partner: refused before NVRTC runs
+    assert lib.bke_debug_ukf_model_cubin_bytes(4, 2, _lib.BKE_F64, _lib.BKE_FX_LINEAR, _lib.BKE_HX_LINEAR, src, inc) == 0
+    assert lib.bke_debug_ukf_model_cubin_bytes(4, 2, _lib.BKE_F64, _lib.BKE_FX_USER, _lib.BKE_HX_RANGE_BEARING, src, inc) == 0
+
+
+def test_device_model_argument_packing():
+    import torch
+    from filterpy_b200.kalman import DeviceFx
+    m = DeviceFx("", arg_names=("a", "b"), a=1.5)
+    with pytest.raises(TypeError):
+        m.pack({}, 4, torch.float64, "cpu")                      # b has no value yet
+    t, stride = m.pack({"b": 2.0}, 4, torch.float64, "cpu")
+    assert stride == 0 and t.tolist() == [1.5, 2.0]
+    t, stride = m.pack({"a": np.arange(4.0)}, 4, torch.float32, "cpu")
+    assert stride == 2 and t.shape == (4, 2) and t[:, 0].tolist() == [0, 1, 2, 3] and t[:, 1].tolist() == [2.0] * 4
+    with pytest.raises(TypeError):
+        m.pack({"c": 1.0}, 4, torch.float64, "cpu")
+    with pytest.raises(ValueError):
+        m.pack({"a": np.arange(3.0)}, 4, torch.float64, "cpu")
+    with pytest.raises(TypeError):
+        DeviceFx("", arg_names=("a",), z=1)

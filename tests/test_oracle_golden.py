@@ -133,6 +133,26 @@ def test_julier_weights_and_sigma_points(golden):
         JulierSigmaPoints(4, 0., sqrt_method=np.linalg.cholesky)
 
 
+@pytest.mark.parametrize("name,linear", [("ukf_user_ct_rb", False), ("ukf_user_ct_lin", True)])
+def test_ukf_user_models_oracle_vs_reference(golden, name, linear):
+    """fx / hx outside the built-in set (coordinated turn with a per-filter rate, offset range / bearing):
+    the oracle's single-filter path with the Python callables of workloads.py against the reference."""
+    from filterpy_b200.common import workloads as wl
+    g = golden(name)
+    a, b, k, dt = float(g["alpha"]), float(g["beta"]), float(g["kappa"]), float(g["dt"])
+    H, sensor = g["H"], g["sensor"]
+    hx = (lambda s: H @ s) if linear else (lambda s: wl.offset_rb_hx(s, sensor[0], sensor[1]))
+    for f in range(0, g["x"].shape[0], 5):
+        x, P = g["x"][f], g["P"][f]
+        om = float(g["omega"][f])
+        for t in range(g["zs"].shape[0]):
+            x, P, sf = oukf.ukf_predict_single(x, P, g["Q"][f], lambda s, dt: wl.ct_fx(s, dt, om), dt, a, b, k)
+            close(x, g["ref_x_prior"][t, f], 1e-9, 1e-9); close(P, g["ref_P_prior"][t, f], 1e-8, 1e-9)
+            if g["valid"][t, f]:
+                x, P = oukf.ukf_update_single(x, P, sf, g["zs"][t, f], g["R"][f], hx, a, b, k)[:2]
+            close(x, g["ref_x"][t, f], 1e-9, 1e-9); close(P, g["ref_P"][t, f], 1e-8, 1e-9)
+
+
 def test_ukf_single_matches_bank(golden):
     g = golden("ukf_bank_lin")
     a, b, k, dt = float(g["alpha"]), float(g["beta"]), float(g["kappa"]), float(g["dt"])
