@@ -4,9 +4,15 @@
 // epoch streams z[t] in (coalesced: consecutive threads read consecutive filters) and the four
 // outputs means/covariances/means_p/covariances_p out.  Algorithmic traffic per filter-step is
 // (m + 2n + 2n^2) scalars (168 B for 4/2 fp32) instead of the 344 B of a stand-alone step.
+// The outputs are 95 % of that traffic: a full warp stages its 32 filters' four output blocks of an
+// epoch in shared memory (they are dense [32][n] / [32][n][n] pieces of the output arrays) and one
+// lane sends them off with four bulk copies (cp.async.bulk.global.shared::cta), double-buffered so
+// that epoch t+1 computes while epoch t's copies drain.  (Per-thread 16-byte stores put 32 half-filled
+// sectors on the wire per instruction.)
 //
 // Shapes without a register-tiled instantiation fall back to looping bke_kf_step on the host
 // (still on the GPU, one launch per epoch).
+#include <stdlib.h>
 #include <type_traits>
 #include "bke_internal.cuh"
 #include "kf_regtile.cuh"
@@ -25,6 +31,16 @@ struct BatchP {
     T *x_out, *P_out, *means, *covs, *means_p, *covs_p;
     int32_t *status;
 };
+
+__device__ __forceinline__ uint32_t bsmem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void b_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void b_bulk_store(void *dst, const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(bsmem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void b_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void b_bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void b_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 template <typename T, int CNT>
 __device__ __forceinline__ void load_vec(T *dst, const T *src)
@@ -46,10 +62,26 @@ __device__ __forceinline__ void store_vec(T *dst, const T *src)
     }
 }
 
-template <typename T, int N, int M>
+// per-warp staging of one epoch's outputs: [means_p | covs_p | means | covs], each 32 filters deep
+template <typename T, int N>
+struct BatchStage {
+    static constexpr int XB = 32 * N * (int)sizeof(T), PB = 32 * N * N * (int)sizeof(T);
+    static constexpr int O_XP = 0, O_PP = XB, O_X = XB + PB, O_P = 2 * XB + PB;
+    static constexpr int BYTES = 2 * (XB + PB);
+    static_assert(XB % 16 == 0 && PB % 16 == 0, "bulk copies move multiples of 16 bytes");
+};
+
+template <typename T, int N, int M, bool STAGED>
 __global__ void __launch_bounds__(128) kf_batch_kernel(BatchP<T> p)
 {
+    using St = BatchStage<T, N>;
+    extern __shared__ __align__(128) unsigned char bsm[];
     const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t f0 = f - lane;                              // the warp's first filter
+    // a full warp sends its outputs through shared memory and bulk copies; a ragged last warp stores directly
+    const bool staged = STAGED && (f0 + 32 <= p.N);
+    unsigned char *wst = bsm + (size_t)(threadIdx.x >> 5) * 2 * St::BYTES;
     if (f >= p.N) return;
     T x[N], P[N][N], F[N][N], Q[N][N], H[M][N], R[M][M];
     load_vec<T, N>(x, p.x + f * N);
@@ -69,6 +101,11 @@ __global__ void __launch_bounds__(128) kf_batch_kernel(BatchP<T> p)
     }
     for (int64_t t = 0; t < p.Tn; t++) {
         const int64_t tf = t * p.N + f;
+        unsigned char *buf = wst + (t & 1) * St::BYTES;
+        if (staged) {
+            if (lane == 0) b_bulk_wait_read1();               // the copies of epoch t-2 have read this buffer
+            __syncwarp();
+        }
         T z[M];
 #pragma unroll
         for (int a = 0; a < M; a++) z[a] = zn[a];
@@ -83,16 +120,39 @@ __global__ void __launch_bounds__(128) kf_batch_kernel(BatchP<T> p)
                 reg_update<T, N, M>(x, P, H, R, z, o);
                 if (!o.ok) st = BKE_STATUS_SINGULAR_S;
             }
-            if (p.means) store_vec<T, N>(p.means + tf * N, x);
-            if (p.covs) store_vec<T, N * N>(p.covs + tf * N * N, &P[0][0]);
+            if (staged) {
+                store_vec<T, N>(reinterpret_cast<T *>(buf + St::O_X) + lane * N, x);
+                store_vec<T, N * N>(reinterpret_cast<T *>(buf + St::O_P) + lane * N * N, &P[0][0]);
+            } else {
+                if (p.means) store_vec<T, N>(p.means + tf * N, x);
+                if (p.covs) store_vec<T, N * N>(p.covs + tf * N * N, &P[0][0]);
+            }
         };
         auto pred = [&]() {
             reg_predict<T, N>(x, P, F, Q, p.alpha_sq);
-            if (p.means_p) store_vec<T, N>(p.means_p + tf * N, x);
-            if (p.covs_p) store_vec<T, N * N>(p.covs_p + tf * N * N, &P[0][0]);
+            if (staged) {
+                store_vec<T, N>(reinterpret_cast<T *>(buf + St::O_XP) + lane * N, x);
+                store_vec<T, N * N>(reinterpret_cast<T *>(buf + St::O_PP) + lane * N * N, &P[0][0]);
+            } else {
+                if (p.means_p) store_vec<T, N>(p.means_p + tf * N, x);
+                if (p.covs_p) store_vec<T, N * N>(p.covs_p + tf * N * N, &P[0][0]);
+            }
         };
         if (p.update_first) { upd(); pred(); } else { pred(); upd(); }
+        if (staged) {
+            b_fence_proxy_async();                            // the staged rows become visible to the copy engine
+            __syncwarp();
+            if (lane == 0) {
+                const int64_t e0 = t * p.N + f0;
+                if (p.means_p) b_bulk_store(p.means_p + e0 * N, buf + St::O_XP, St::XB);
+                if (p.covs_p) b_bulk_store(p.covs_p + e0 * N * N, buf + St::O_PP, St::PB);
+                if (p.means) b_bulk_store(p.means + e0 * N, buf + St::O_X, St::XB);
+                if (p.covs) b_bulk_store(p.covs + e0 * N * N, buf + St::O_P, St::PB);
+                b_bulk_commit();
+            }
+        }
     }
+    if (staged && lane == 0) b_bulk_wait_all();
     store_vec<T, N>(p.x_out + f * N, x);
     store_vec<T, N * N>(p.P_out + f * N * N, &P[0][0]);
     if (p.status) p.status[f] = st;
@@ -113,7 +173,18 @@ int launch_reg(const bke_kf_batch_args &a, cudaStream_t s)
     p.means = (T *)a.means; p.covs = (T *)a.covariances; p.means_p = (T *)a.means_p; p.covs_p = (T *)a.covariances_p;
     p.status = k.status;
     int64_t grid = (p.N + 127) / 128;
-    kf_batch_kernel<T, N, M><<<(unsigned)grid, 128, 0, s>>>(p);
+    // an epoch's slice of every output array must start on a 16-byte boundary for the bulk copies (the arrays
+    // themselves are checked by the caller); BKE_BATCH_DIRECT=1 keeps the per-thread stores (A/B measurements)
+    static const bool direct = [] { const char *e = getenv("BKE_BATCH_DIRECT"); return e && e[0] == '1'; }();
+    const bool staged = !direct && ((size_t)p.N * N * sizeof(T)) % 16 == 0 && p.N >= 32;
+    if (staged) {
+        constexpr int smem = 4 * 2 * BatchStage<T, N>::BYTES;
+        auto kern = kf_batch_kernel<T, N, M, true>;
+        if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
+        kern<<<(unsigned)grid, 128, smem, s>>>(p);
+    } else {
+        kf_batch_kernel<T, N, M, false><<<(unsigned)grid, 128, 0, s>>>(p);
+    }
     return check_cuda(cudaGetLastError(), "kf_batch_kernel launch");
 }
 

@@ -111,6 +111,16 @@ struct RbGeom {
     // one copy of F, Q, H, R per warp for banks that share their models (kept for the whole launch)
     static constexpr int SH_ELEMS = 2 * N * N + M * N + M * M;
     static constexpr int SH_BYTES = a16(SH_ELEMS * (int)sizeof(T));
+    // optional outputs (EXTRAS instances): K, y, S, SI, log-likelihood of the warp's FPW filters, staged
+    // contiguously so that they leave with bulk stores like the posterior
+    static constexpr int LLB = FPW * (int)sizeof(T);
+    static constexpr bool LL_BULK = LLB % 16 == 0;
+    static constexpr int EK = 0;
+    static constexpr int EY = EK + a16(HB);          // K[N][M] has H's size
+    static constexpr int ES = EY + a16(ZB);
+    static constexpr int ESI = ES + a16(RBY);
+    static constexpr int ELL = ESI + a16(RBY);
+    static constexpr int EX_BYTES = a16(ELL + a16(LLB));
     static constexpr uint32_t TX = XB + 3 * PB + HB + RBY + ZB;
     static_assert(N % RPL == 0 && G >= 1 && G <= 32 && FPW >= 1, "bad row-block shape");
     static_assert(XB % 16 == 0 && PB % 16 == 0 && HB % 16 == 0 && RBY % 16 == 0 && ZB % 16 == 0, "bulk copies need 16-byte multiples");
@@ -132,8 +142,10 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
     __shared__ __align__(8) uint64_t bars[RB_WARPS][RB_STAGES];
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    unsigned char *wbase = smem + (size_t)wib * Gm::WARP_BYTES;
+    constexpr int WB = Gm::WARP_BYTES + (EXTRAS ? Gm::EX_BYTES : 0);
+    unsigned char *wbase = smem + (size_t)wib * WB;
     unsigned char *outb = wbase + RB_STAGES * Gm::STAGE;
+    unsigned char *exb = wbase + Gm::WARP_BYTES;             // EXTRAS: staging of K, y, S, SI, log-likelihood
     uint64_t *bar = bars[wib];
     const bool active = lane < FPW * G;
     const int fl = active ? lane / G : FPW - 1;            // filter within the tile (idle lanes mirror the last one)
@@ -164,7 +176,7 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
     };
 
     // the shared models of this warp: after all warps' stages (generic-proxy loads and stores only)
-    T *shF = reinterpret_cast<T *>(smem + (size_t)RB_WARPS * Gm::WARP_BYTES + (size_t)wib * Gm::SH_BYTES);
+    T *shF = reinterpret_cast<T *>(smem + (size_t)RB_WARPS * WB + (size_t)wib * Gm::SH_BYTES);
     T *shQ = shF + N * N, *shH = shQ + N * N, *shR = shH + M * N;
     if constexpr (SHARED) {
         for (int e = lane; e < N * N; e += 32) {
@@ -263,22 +275,25 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
             }
         }
         __syncwarp();                               // every lane is done reading x, P (and F rows it needed as B)
-        if (EXTRAS && active && (p.x_prior || p.P_prior)) {   // optional outputs: every lane stores its own rows
-#pragma unroll
-            for (int i = 0; i < RPL; i++) {
-                if (p.x_prior) p.x_prior[f * N + r0 + i] = xr[i];
-                if (p.P_prior) {
-#pragma unroll
-                    for (int j = 0; j < N; j++) p.P_prior[f * N * N + (r0 + i) * N + j] = A[i][j];
-                }
-            }
-        }
         if (active) {
 #pragma unroll
             for (int i = 0; i < RPL; i++) {
                 sx[r0 + i] = xr[i];
 #pragma unroll
                 for (int j = 0; j < N; j++) sP[(r0 + i) * N + j] = A[i][j];          // P' overwrites P
+            }
+        }
+        if (EXTRAS && (p.x_prior || p.P_prior)) {
+            // optional outputs: the prior sits in the stage exactly as x_prior / P_prior want it (FPW filters,
+            // dense) — two bulk stores; they have the whole update to read the stage before the posterior
+            // (1 stage) or the next tile's loads (ring) overwrite it
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                const int64_t f0 = tile * FPW;
+                if (p.x_prior) bulk_store(p.x_prior + f0 * N, sb + Gm::OX, Gm::XB);
+                if (p.P_prior) bulk_store(p.P_prior + f0 * N * N, sb + Gm::OP, Gm::PB);
+                bulk_commit();
             }
         }
         __syncwarp();
@@ -369,34 +384,47 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
                     C[i][j] = s;                                   // own rows of I - K H
                 }
             if (EXTRAS && active && (p.K || p.y || p.S || p.SI || p.ll)) {
-                // optional outputs (kalman_filter.py:533-544 attributes): S always, the rest when S was invertible
-                if (rb == 0 && p.S) {
+                // optional outputs (kalman_filter.py:533-544 attributes) -> the warp's staging area; S always,
+                // the rest when S was invertible (else what the arrays held stays: it is staged from there)
+                T *eK = reinterpret_cast<T *>(exb + Gm::EK) + fl * N * M, *eY = reinterpret_cast<T *>(exb + Gm::EY) + fl * M;
+                T *eS = reinterpret_cast<T *>(exb + Gm::ES) + fl * M * M, *eSI = reinterpret_cast<T *>(exb + Gm::ESI) + fl * M * M;
+                T *eLL = reinterpret_cast<T *>(exb + Gm::ELL) + fl;
+                if (rb == 0) {
 #pragma unroll
                     for (int a = 0; a < M; a++)
 #pragma unroll
-                        for (int b = 0; b < M; b++) p.S[f * M * M + a * M + b] = o.S[a][b];
+                        for (int b = 0; b < M; b++) eS[a * M + b] = o.S[a][b];
                 }
                 if (o.ok) {
-                    if (p.K) {
 #pragma unroll
-                        for (int i = 0; i < RPL; i++)
+                    for (int i = 0; i < RPL; i++)
 #pragma unroll
-                            for (int a = 0; a < M; a++) p.K[f * N * M + (r0 + i) * M + a] = Kr[i][a];
-                    }
+                        for (int a = 0; a < M; a++) eK[(r0 + i) * M + a] = Kr[i][a];
                     if (rb == 0) {
-                        if (p.y) for (int a = 0; a < M; a++) p.y[f * M + a] = y[a];
-                        if (p.SI) for (int a = 0; a < M; a++) for (int b = 0; b < M; b++) p.SI[f * M * M + a * M + b] = o.SI[a][b];
-                        if (p.ll) {
-                            T q = T(0);
 #pragma unroll
-                            for (int a = 0; a < M; a++) {
-                                T sq = T(0);
+                        for (int a = 0; a < M; a++) eY[a] = y[a];
 #pragma unroll
-                                for (int b = 0; b < M; b++) sq += o.SI[a][b] * y[b];
-                                q += y[a] * sq;
-                            }
-                            p.ll[f] = T(-0.5) * (q + o.logdet + T(M) * T(LOG_2PI));
+                        for (int a = 0; a < M; a++)
+#pragma unroll
+                            for (int b = 0; b < M; b++) eSI[a * M + b] = o.SI[a][b];
+                        T q = T(0);
+#pragma unroll
+                        for (int a = 0; a < M; a++) {
+                            T sq = T(0);
+#pragma unroll
+                            for (int b = 0; b < M; b++) sq += o.SI[a][b] * y[b];
+                            q += y[a] * sq;
                         }
+                        const T llv = T(-0.5) * (q + o.logdet + T(M) * T(LOG_2PI));
+                        if (Gm::LL_BULK) *eLL = llv; else if (p.ll) p.ll[f] = llv;
+                    }
+                } else {
+                    for (int i = 0; i < RPL; i++)
+                        for (int a = 0; a < M; a++) eK[(r0 + i) * M + a] = p.K ? p.K[f * N * M + (r0 + i) * M + a] : T(0);
+                    if (rb == 0) {
+                        for (int a = 0; a < M; a++) eY[a] = p.y ? p.y[f * M + a] : T(0);
+                        for (int e = 0; e < M * M; e++) eSI[e] = p.SI ? p.SI[f * M * M + e] : T(0);
+                        if (Gm::LL_BULK) *eLL = p.ll ? p.ll[f] : T(0);
                     }
                 }
             }
@@ -454,11 +482,23 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
                 }
             }
         }
-        if (EXTRAS && (MODE & 2) && !has_z && active && rb == 0 && p.y) {  // z is None: y = 0 (kalman_filter.py:515-520)
-            for (int a = 0; a < M; a++) p.y[f * M + a] = T(0);
+        if (EXTRAS && (MODE & 2) && !has_z && active && (p.K || p.y || p.S || p.SI || p.ll)) {
+            // z is None: y = 0, K / S / SI / log-likelihood keep their values (kalman_filter.py:515-520) — staged
+            // from the arrays so that the tile's bulk stores write them back unchanged
+            T *eK = reinterpret_cast<T *>(exb + Gm::EK) + fl * N * M, *eY = reinterpret_cast<T *>(exb + Gm::EY) + fl * M;
+            T *eS = reinterpret_cast<T *>(exb + Gm::ES) + fl * M * M, *eSI = reinterpret_cast<T *>(exb + Gm::ESI) + fl * M * M;
+            for (int i = 0; i < RPL; i++)
+                for (int a = 0; a < M; a++) eK[(r0 + i) * M + a] = p.K ? p.K[f * N * M + (r0 + i) * M + a] : T(0);
+            if (rb == 0) {
+                for (int a = 0; a < M; a++) eY[a] = T(0);
+                for (int e = 0; e < M * M; e++) { eS[e] = p.S ? p.S[f * M * M + e] : T(0); eSI[e] = p.SI ? p.SI[f * M * M + e] : T(0); }
+                if (Gm::LL_BULK) reinterpret_cast<T *>(exb + Gm::ELL)[fl] = p.ll ? p.ll[f] : T(0);
+            }
         }
         // ---------------- posterior rows -> staging -> bulk TMA store ---------------------------
-        if (RB_STAGES > 1 && it > 0 && lane == 0) bulk_wait_read();   // the previous tile's stores have read the staging buffer
+        // the previous tile's stores have read the staging buffer (ring) / the prior's stores have read the
+        // stage slots the posterior is about to overwrite (one stage, optional outputs)
+        if (lane == 0 && ((RB_STAGES > 1 && it > 0) || (EXTRAS && RB_STAGES == 1))) bulk_wait_read();
         __syncwarp();                                       // every lane is done with P', (I-KH), K in the stage
         if (active) {
 #pragma unroll
@@ -475,8 +515,17 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
             const int64_t f0 = tile * FPW;
             bulk_store(p.x_out + f0 * N, out_x, Gm::XB);
             bulk_store(p.P_out + f0 * N * N, out_P, Gm::PB);
+            if (EXTRAS && (MODE & 2)) {
+                if (p.K) bulk_store(p.K + f0 * N * M, exb + Gm::EK, Gm::HB);
+                if (p.y) bulk_store(p.y + f0 * M, exb + Gm::EY, Gm::ZB);
+                if (p.S) bulk_store(p.S + f0 * M * M, exb + Gm::ES, Gm::RBY);
+                if (p.SI) bulk_store(p.SI + f0 * M * M, exb + Gm::ESI, Gm::RBY);
+                if (Gm::LL_BULK && p.ll) bulk_store(p.ll + f0, exb + Gm::ELL, Gm::LLB);
+            }
             bulk_commit();
-            if (RB_STAGES == 1) bulk_wait_read();           // the stores have read the stage: it may be refilled
+            // the stores have read the stage (one stage) / the stage's prior and the staging area (optional
+            // outputs): it may be refilled
+            if (RB_STAGES == 1 || EXTRAS) bulk_wait_read();
             const int64_t nt = tile + RB_STAGES * wstride;
             if (nt < tiles) issue(nt, stage);
         }
@@ -513,7 +562,8 @@ int launch_rb(const bke_kf_args &a, cudaStream_t s)
             if (mode == 1) kern = kf_rowblock_kernel<T, N, M, RPL, RB_STAGES, RB_WARPS, true, 1, true>;
             if (mode == 2) kern = kf_rowblock_kernel<T, N, M, RPL, RB_STAGES, RB_WARPS, true, 2, true>;
         }
-        const int smem = RB_WARPS * (Gm::WARP_BYTES + (shared ? Gm::SH_BYTES : 0));
+        const bool kern_extras = extras || mode != 3 || shared;      // the instance selected above carries them
+        const int smem = RB_WARPS * (Gm::WARP_BYTES + (kern_extras ? Gm::EX_BYTES : 0) + (shared ? Gm::SH_BYTES : 0));
         const int cfg = (mode == 3 ? (int)extras : 1 + mode) + (shared ? 4 : 0);
         static bool configured[8][64] = {{false}};
         int dev = 0;
@@ -567,6 +617,8 @@ int launch_kf_rowblock(const bke_kf_args &a, cudaStream_t s)
     if (dp && a.F_stride && !(al16(a.F) && al16(a.Q))) return BKE_ERR_UNSUPPORTED;
     if (du && a.H_stride && !(al16(a.H) && al16(a.R))) return BKE_ERR_UNSUPPORTED;
     if (du && !al16(a.z)) return BKE_ERR_UNSUPPORTED;
+    // the optional outputs leave with bulk stores too
+    if (!(al16(a.x_prior) && al16(a.P_prior) && al16(a.K) && al16(a.y) && al16(a.S) && al16(a.SI) && al16(a.log_likelihood))) return BKE_ERR_UNSUPPORTED;
     const int n = a.dim_x, m = a.dim_z;
     // 9/3 fp64: one stage per warp and 8 warps per SM (two per scheduler: the FP64 pipe of one warp's
     // dependent DFMA chains is covered by the other) beat a 2-stage ring with 4 warps; BKE_RB_RING=1

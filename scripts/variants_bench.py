@@ -73,6 +73,12 @@ def main():
         setattr(kf, k, w[k])
     zs = torch.from_numpy(w["zs"]).cuda()
     report("batch_filter 4/2 f32 2^18 x 32 epochs (per filter-step)", timeit(lambda: kf.batch_filter(zs), reps=5), N * T, (2 + 2 * 4 + 2 * 16) * 4)
+    w = wl.kf_bank_cv2d(N, steps=T, dtype=np.float64)
+    kf = KalmanFilter(4, 2, n_filters=N, dtype=np.float64, diagnostics=False)
+    for k in "xPFHQR":
+        setattr(kf, k, w[k])
+    zs = torch.from_numpy(w["zs"]).cuda()
+    report("batch_filter 4/2 f64 2^18 x 32 epochs (per filter-step)", timeit(lambda: kf.batch_filter(zs), reps=5), N * T, (2 + 2 * 4 + 2 * 16) * 8)
     # UKF (config C4)
     for dtype in (np.float64, np.float32):
         N = 1 << 18
