@@ -548,7 +548,34 @@ def extra_legs(dev, rank, world, peak, max_over_ranks, barrier):
     out["kf_c3"] = {"workload": "config 3: 9/3 fp64, per-filter F/H/Q/R, 1.25 M filters per GPU (10 M over 8)",
                     "filters_per_gpu": N3, "value": world * N3 / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "dtype": "f64",
                     "roofline": roof(ms, N3, bpu3, "kf_rowblock_kernel<double,9,3>")}
-    del kf3, z3, w3, small
+    # C3 the drop-in way (diagnostics=True): the optional outputs are staged in shared memory and leave with bulk stores
+    kf3d = KalmanFilter(9, 3, n_filters=N3, dtype=np.float64, device=dev, diagnostics=True)
+    for k in "xPFHQR":
+        setattr(kf3d, k, w3[k])
+
+    def step3d():
+        kf3d.predict(); kf3d.update(z3)
+    ms = timed_steps(step3d, 10, 3, dev, max_over_ranks, barrier)
+    extra3 = (9 + 81 + 27 + 3 + 2 * 9 + 1) * 8 + 4            # priors, K, y, S, SI, loglik, status
+    out["kf_c3_diagnostics"] = {"workload": "config 3 with diagnostics=True (x_prior, P_prior, K, y, S, SI, log-likelihood, status written)",
+                                "filters_per_gpu": N3, "value": world * N3 / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "dtype": "f64",
+                                "roofline": roof(ms, N3, bpu3 + extra3, "kf_rowblock_kernel<double,9,3,EXTRAS>")}
+    del kf3, kf3d, z3, w3, small
+    torch.cuda.empty_cache()
+
+    # batch_filter (BASELINE configs[0]'s call, as a bank): 2^18 filters x 32 epochs inside ONE kernel, 4/2 fp32
+    Nb, Tb = 1 << 18, 32
+    wb = wl.kf_bank_cv2d(Nb, seed=99 + rank, steps=Tb, dtype=np.float32)
+    kfb = KalmanFilter(DIM_X, DIM_Z, n_filters=Nb, dtype=np.float32, device=dev, diagnostics=False)
+    for k in "xPFHQR":
+        setattr(kfb, k, wb[k])
+    zsb = torch.from_numpy(wb["zs"]).to(dev)
+    ms = timed_steps(lambda: kfb.batch_filter(zsb), 5, 3, dev, max_over_ranks, barrier)
+    bpub = (DIM_Z + 2 * DIM_X + 2 * DIM_X * DIM_X) * 4          # z in; means, covariances, means_p, covariances_p out
+    out["kf_batch_filter"] = {"workload": "KalmanFilter.batch_filter, 2^18 filters x 32 epochs per call and GPU, 4/2 fp32, time loop in the kernel",
+                              "filters_per_gpu": Nb, "epochs": Tb, "value": world * Nb * Tb / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                              "dtype": "f32", "roofline": roof(ms, Nb * Tb, bpub, "kf_batch_kernel<float,4,2,staged>")}
+    del kfb, zsb, wb
     torch.cuda.empty_cache()
 
     # C4: UKF Merwe 6/3, 2^18 filters, CV + range/azimuth/elevation, fp64

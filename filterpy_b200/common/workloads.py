@@ -208,7 +208,7 @@ def ukf_bank_ct2d(N, seed=9753, steps=1, dt=0.5, dtype=np.float64, linear_hx=Fal
     q = np.exp(rng.uniform(np.log(1e-3), np.log(1e-1), N))
     qb = q_white_noise_block(2, np.full(N, dt), q)
     Q = _block_diag([qb, qb])
-    sig = np.array([1.0, 1.0]) if linear_hx else np.array([1.5, 0.004])
+    sig = np.array([2.5, 2.5]) if linear_hx else np.array([1.5, 0.004])
     R = np.broadcast_to(np.diag(sig ** 2), (N, 2, 2)).copy()
     zs = np.zeros((steps, N, 2))
     for t in range(steps):

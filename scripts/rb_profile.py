@@ -6,7 +6,7 @@ from filterpy_b200.common import workloads as wl
 N = 500000
 w = wl.kf_bank_ca3d(50000, steps=1)
 r = N // 50000
-kf = KalmanFilter(9, 3, n_filters=N, dtype=np.float64, diagnostics=False)
+kf = KalmanFilter(9, 3, n_filters=N, dtype=np.float64, diagnostics=len(sys.argv) > 1 and sys.argv[1] == "diag")
 for k in "xPFHQR":
     a = w[k]
     setattr(kf, k, np.tile(a, (r,) + (1,) * (a.ndim - 1)))
