@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "bke_resample_composite_bytes", "bke_resample_shard_compose", "bke_resample_compose_carry", "bke_resample_shard_stage",
     "bke_merwe_sigma_points", "bke_unscented_transform",
     "bke_ukf_model_compile", "bke_ukf_model_log", "bke_ukf_model_registers", "bke_ukf_model_free", "bke_ukf_step_model",
-    "bke_debug_ukf_model_cubin_bytes",
+    "bke_debug_ukf_model_cubin_bytes", "bke_ukf_rts_smoother_model",
     "bke_kf_rts_smoother", "bke_ukf_rts_smoother", "bke_mm_probabilities", "bke_mm_mix", "bke_mm_estimate", "bke_cumsum_exact", "bke_searchsorted", "bke_multinomial_resample", "bke_gather_rows",
 ]
 
@@ -224,6 +224,8 @@ def load():
     lib.bke_ukf_model_free.restype = None
     lib.bke_ukf_step_model.argtypes = [ctypes.POINTER(UkfArgs), c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]
     lib.bke_ukf_step_model.restype = ctypes.c_int
+    lib.bke_ukf_rts_smoother_model.argtypes = [ctypes.POINTER(UkfRtsArgs), c_void_p, c_void_p, c_int64, c_void_p]
+    lib.bke_ukf_rts_smoother_model.restype = ctypes.c_int
     lib.bke_debug_ukf_model_cubin_bytes.argtypes = [c_int32, c_int32, c_int32, c_int32, c_int32, ctypes.c_char_p, ctypes.c_char_p]
     lib.bke_debug_ukf_model_cubin_bytes.restype = c_size_t
     lib.bke_resample_workspace_bytes.argtypes = [c_int64]

@@ -21,11 +21,13 @@
 #include <string>
 #include <vector>
 #include "ukf_launch.cuh"
+#include "ukf_rts_launch.cuh"
 
 struct bke_ukf_model {
     int n, m, dtype, fx_model, hx_model;
     cudaLibrary_t lib;
     cudaKernel_t kern[2];          // [0] plain, [1] with the optional outputs
+    cudaKernel_t kern_rts;         // RTS smoother around the user's fx (NULL: fx is built in, or dim_x > UR_MAXN)
     int regs[2];
     std::string log;
 };
@@ -110,7 +112,7 @@ extern "C" {
 // NVRTC half of bke_ukf_model_compile (needs no GPU): program text -> sm_100a cubin + the lowered names
 // of the two kernel instances
 static int compile_cubin(int32_t dim_x, int32_t dim_z, int32_t dtype, int32_t fx_model, int32_t hx_model, const char *source,
-                         const char *include_dirs, std::vector<char> &cubin, std::string (&lowered)[2], std::string &log)
+                         const char *include_dirs, std::vector<char> &cubin, std::string (&lowered)[3], std::string &log)
 {
     if (dim_x < 1 || dim_x > 16 || dim_z < 1 || dim_z > dim_x + 8) { set_error("bke_ukf_model_compile: 1 <= dim_x <= 16, 1 <= dim_z"); return BKE_ERR_BAD_ARG; }
     if (dtype != BKE_F32 && dtype != BKE_F64) { set_error("dtype must be BKE_F32 or BKE_F64"); return BKE_ERR_BAD_ARG; }
@@ -128,7 +130,7 @@ static int compile_cubin(int32_t dim_x, int32_t dim_z, int32_t dtype, int32_t fx
     std::string text;
     text += dtype == BKE_F64 ? "typedef double real;\n" : "typedef float real;\n";
     text += "#define BKE_DIM_X " + std::to_string(dim_x) + "\n#define BKE_DIM_Z " + std::to_string(dim_z) + "\n";
-    text += "#include \"ukf_kernel.cuh\"\n";
+    text += "#include \"ukf_kernel.cuh\"\n#include \"ukf_rts_kernel.cuh\"\n";
     text += "#line 1 \"user_model.cu\"\n";
     text += source;
     text += "\n#line 1 \"bke_glue.cu\"\nnamespace bke { namespace ukfk {\n";
@@ -156,8 +158,11 @@ static int compile_cubin(int32_t dim_x, int32_t dim_z, int32_t dtype, int32_t fx
     }
     std::vector<const char *> copts;
     for (auto &o : opts) copts.push_back(o.c_str());
-    const std::string names[2] = {kernel_name(tmp, occ, false), kernel_name(tmp, occ, true)};
-    for (int i = 0; i < 2; i++) rt->add_name(prog, names[i].c_str());
+    // the step kernel with / without the optional outputs and, around a user fx, the RTS smoother
+    const bool with_rts = ufx && dim_x <= UR_MAXN;
+    const int n_names = with_rts ? 3 : 2;
+    const std::string names[3] = {kernel_name(tmp, occ, false), kernel_name(tmp, occ, true), "bke::ukf_rts_kernel<real, true>"};
+    for (int i = 0; i < n_names; i++) rt->add_name(prog, names[i].c_str());
     r = rt->compile(prog, (int)copts.size(), copts.data());
     size_t lsz = 0;
     rt->log_size(prog, &lsz);
@@ -172,7 +177,8 @@ static int compile_cubin(int32_t dim_x, int32_t dim_z, int32_t dtype, int32_t fx
     rt->cubin_size(prog, &csz);
     cubin.resize(csz);
     rt->cubin(prog, cubin.data());
-    for (int i = 0; i < 2; i++) {
+    lowered[2].clear();
+    for (int i = 0; i < n_names; i++) {
         const char *ln = nullptr;
         if (rt->lowered(prog, names[i].c_str(), &ln) != NVRTC_SUCCESS || !ln) {
             set_error("nvrtcGetLoweredName failed for %s", names[i].c_str());
@@ -191,11 +197,12 @@ int bke_ukf_model_compile(int32_t dim_x, int32_t dim_z, int32_t dtype, int32_t f
     if (!out) { set_error("out is NULL"); return BKE_ERR_BAD_ARG; }
     *out = nullptr;
     std::vector<char> cubin;
-    std::string lowered[2], log;
+    std::string lowered[3], log;
     int rc = compile_cubin(dim_x, dim_z, dtype, fx_model, hx_model, source, include_dirs, cubin, lowered, log);
     if (rc != BKE_OK) return rc;
     bke_ukf_model *m = new bke_ukf_model();
     m->n = dim_x; m->m = dim_z; m->dtype = dtype; m->fx_model = fx_model; m->hx_model = hx_model; m->lib = nullptr; m->log = log;
+    m->kern_rts = nullptr;
     if (check_cuda(cudaLibraryLoadData(&m->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0), "cudaLibraryLoadData")) { delete m; return BKE_ERR_CUDA; }
     for (int i = 0; i < 2; i++) {
         if (check_cuda(cudaLibraryGetKernel(&m->kern[i], m->lib, lowered[i].c_str()), "cudaLibraryGetKernel")) {
@@ -204,6 +211,10 @@ int bke_ukf_model_compile(int32_t dim_x, int32_t dim_z, int32_t dtype, int32_t f
         }
         cudaFuncAttributes fa;
         m->regs[i] = cudaFuncGetAttributes(&fa, (const void *)m->kern[i]) == cudaSuccess ? fa.numRegs : -1;
+    }
+    if (!lowered[2].empty() && check_cuda(cudaLibraryGetKernel(&m->kern_rts, m->lib, lowered[2].c_str()), "cudaLibraryGetKernel (rts)")) {
+        cudaLibraryUnload(m->lib); delete m;
+        return BKE_ERR_CUDA;
     }
     cudaGetLastError();
     *out = m;
@@ -215,7 +226,7 @@ size_t bke_debug_ukf_model_cubin_bytes(int32_t dim_x, int32_t dim_z, int32_t dty
                                        const char *include_dirs)
 {
     std::vector<char> cubin;
-    std::string lowered[2], log;
+    std::string lowered[3], log;
     if (compile_cubin(dim_x, dim_z, dtype, fx_model, hx_model, source, include_dirs, cubin, lowered, log) != BKE_OK) return 0;
     return cubin.size();
 }
@@ -255,6 +266,25 @@ int bke_ukf_step_model(const bke_ukf_args *args, const bke_ukf_model *model, con
     if (a.n_filters == 0) return BKE_OK;
     return a.dtype == BKE_F32 ? launch_model<float>(a, *model, fx_args, fx_args_stride, hx_args, hx_args_stride, (cudaStream_t)stream)
                               : launch_model<double>(a, *model, fx_args, fx_args_stride, hx_args, hx_args_stride, (cudaStream_t)stream);
+}
+
+int bke_ukf_rts_smoother_model(const bke_ukf_rts_args *args, const bke_ukf_model *model, const void *fx_args, int64_t fx_args_stride,
+                               void *stream)
+{
+    if (!args || !model) { set_error("args / model is NULL"); return BKE_ERR_BAD_ARG; }
+    const bke_ukf_rts_args &a = *args;
+    if (!model->kern_rts) { set_error("bke_ukf_rts_smoother_model: the model has no user fx (use bke_ukf_rts_smoother) or dim_x > %d", UR_MAXN); return BKE_ERR_UNSUPPORTED; }
+    if (a.dim_x != model->n || a.dtype != model->dtype || a.fx_model != BKE_FX_USER) { set_error("bke_ukf_rts_smoother_model: args do not match the compiled model"); return BKE_ERR_BAD_ARG; }
+    if (a.n_filters < 0 || a.n_steps < 0 || fx_args_stride < 0 || a.Q_stride < 0) { set_error("negative sizes"); return BKE_ERR_BAD_ARG; }
+    if (a.n_filters == 0 || a.n_steps == 0) return BKE_OK;
+    if (!a.Xs || !a.Ps || !a.Q || !a.x_out || !a.P_out) { set_error("NULL argument"); return BKE_ERR_BAD_ARG; }
+    void *params[1];
+    UrP<float> pf; UrP<double> pd;
+    if (a.dtype == BKE_F32) { ukf_rts_fill_params<float>(a, pf); pf.fx_args = (const float *)fx_args; pf.s_fx_args = fx_args_stride; params[0] = &pf; }
+    else { ukf_rts_fill_params<double>(a, pd); pd.fx_args = (const double *)fx_args; pd.s_fx_args = fx_args_stride; params[0] = &pd; }
+    if (check_cuda(cudaLaunchKernel((const void *)model->kern_rts, dim3((unsigned)((a.n_filters + 63) / 64)), dim3(64), params, 0, (cudaStream_t)stream),
+                   "ukf rts model launch")) return BKE_ERR_CUDA;
+    return BKE_OK;
 }
 
 }  // extern "C"

@@ -402,8 +402,6 @@ class UnscentedKalmanFilter(object):
         ``(T,n,n)``.  ``dts``: None (the filter's dt), a scalar, or one value per epoch.  ``Qs`` is
         accepted and, exactly like the reference (:715 uses ``self.Q``), not used."""
         _no_hook("UT", UT)
-        if isinstance(self.fx, _DeviceModel):
-            raise NotImplementedError("rts_smoother runs the built-in process models only (csrc/kf_rts.cu)")
         if len(Xs) != len(Ps):
             raise ValueError('Xs and Ps must have the same length')
         self._flush()
@@ -442,7 +440,15 @@ class UnscentedKalmanFilter(object):
         a.x_out, a.P_out, a.K = ptr(xs), ptr(Pso), ptr(Ks)
         a.status = ptr(status)
         with torch.cuda.device(self._device):
-            _lib.check(self._lib.bke_ukf_rts_smoother(ctypes.byref(a), stream_ptr(self._device)))
+            if isinstance(self.fx, _DeviceModel):
+                # the reference calls self.fx(sigma, dt) without keyword arguments here (UKF.py:712): the model's
+                # current argument values stand in for the defaults of its callable
+                if self.fx.arg_names and self._fx_args[0] is None:
+                    raise TypeError("fx needs values for its arguments %s" % list(self.fx.arg_names))
+                _lib.check(self._lib.bke_ukf_rts_smoother_model(ctypes.byref(a), self._user_model, ptr(self._fx_args[0]),
+                                                                self._fx_args[1], stream_ptr(self._device)))
+            else:
+                _lib.check(self._lib.bke_ukf_rts_smoother(ctypes.byref(a), stream_ptr(self._device)))
         if not self._single:
             return xs, Pso, Ks
         if int(status[0].item()) != 0:

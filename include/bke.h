@@ -362,6 +362,11 @@ typedef struct {
 } bke_ukf_rts_args;
 
 int bke_ukf_rts_smoother(const bke_ukf_rts_args *args, void *stream);
+/* the same around a user-supplied fx (fx_model = BKE_FX_USER, a model from bke_ukf_model_compile; dim_x <= 8).  The
+ * reference calls self.fx(sigma, dts[k]) WITHOUT keyword arguments here (UKF.py:712): fx_args are the values its
+ * callable would default to. */
+int bke_ukf_rts_smoother_model(const bke_ukf_rts_args *args, const bke_ukf_model *model, const void *fx_args,
+                               int64_t fx_args_stride, void *stream);
 
 /* ---- bank-level model mixing: IMMEstimator / MMAEFilterBank ------------
  *

@@ -232,6 +232,22 @@ def gen_ukf_user():
                 out[k].append(np.array(rec[k]))
         save(name, **w, valid=valid, dt=dt, alpha=0.5, beta=2.0, kappa=0.0,
              **{"ref_" + k: np.array(v) for k, v in out.items()})
+    # RTS smoother around the user fx: the reference calls fx(sigma, dt) without keyword arguments there
+    # (UKF.py:712), so the turn rate is the callable's default
+    N, steps, dt, om = 6, 10, 0.5, 0.07
+    w = wl.ukf_bank_ct2d(N, seed=1122, steps=steps, dt=dt, linear_hx=True)
+    Hlin = w["H"]
+    Xs = np.zeros((steps, N, 4)); Ps = np.zeros((steps, N, 4, 4))
+    sm = [np.zeros((steps, N, 4)), np.zeros((steps, N, 4, 4)), np.zeros((steps, N, 4, 4))]
+    for f in range(N):
+        u = UnscentedKalmanFilter(4, 2, dt, lambda s: Hlin @ s, lambda s, dt, omega=om: wl.ct_fx(s, dt, omega),
+                                  MerweScaledSigmaPoints(4, 0.5, 2.0, 0.0))
+        u.x = w["x"][f].copy(); u.P = w["P"][f].copy(); u.Q = w["Q"][f]; u.R = w["R"][f]
+        mu, cov = u.batch_filter(list(w["zs"][:, f]))
+        Xs[:, f] = mu; Ps[:, f] = cov
+        for o, v in zip(sm, u.rts_smoother(mu, cov)):
+            o[:, f] = v
+    save("ukf_user_rts", Xs=Xs, Ps=Ps, x=sm[0], P=sm[1], K=sm[2], Q=w["Q"], H=Hlin, dt=dt, omega=om, alpha=0.5, beta=2.0, kappa=0.0)
 
 
 # ----------------------------------------------------------------------------- resampling

@@ -108,8 +108,25 @@ def test_ukf_user_model_errors():
     u.predict()
     with pytest.raises(TypeError, match="omega"):                 # the model's argument has no value
         u.update(np.zeros((4, 2)))
-    with pytest.raises(NotImplementedError):
-        u.rts_smoother(np.zeros((2, 4, 4)), np.zeros((2, 4, 4, 4)))
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-6), (np.float32, 2e-3)])
+def test_ukf_user_fx_rts_smoother_vs_reference_golden(golden, dtype, tol):
+    """UKF.rts_smoother (UKF.py:634-739) around a user-supplied fx: the smoother kernel is compiled at run
+    time with the same text; the reference ran the Python callable with its default turn rate (:712)."""
+    import torch
+    from filterpy_b200.kalman import UnscentedKalmanFilter, MerweScaledSigmaPoints, DeviceFx, LinearHx
+    from filterpy_b200.common import workloads as wl
+    g = golden("ukf_user_rts")
+    T, N, n = g["Xs"].shape
+    u = UnscentedKalmanFilter(4, 2, float(g["dt"]), LinearHx(g["H"]), DeviceFx(wl.CT_FX_SOURCE, arg_names=("omega",), omega=float(g["omega"])),
+                              MerweScaledSigmaPoints(4, float(g["alpha"]), float(g["beta"]), float(g["kappa"])), n_filters=N, dtype=dtype)
+    u.Q = g["Q"]
+    x, P, K = u.rts_smoother(torch.from_numpy(g["Xs"]), torch.from_numpy(g["Ps"]))
+    from test_gpu_next_rows import rel_close as close_abs          # the built-in models' RTS tests use the same measure
+    close_abs(x.cpu().numpy(), g["x"], tol)
+    close_abs(P.cpu().numpy(), g["P"], tol, atol_scale=4.0 if dtype == np.float32 else 1.0)
+    close_abs(K.cpu().numpy(), g["K"], tol * 10, atol_scale=4.0)
 
 
 def test_julier_sigma_points_standalone(golden):
