@@ -101,7 +101,7 @@ def test_ukf_user_model_errors():
     from filterpy_b200.common import workloads as wl
     pts = MerweScaledSigmaPoints(4, .5, 2., 0.)
     H = np.eye(2, 4)
-XX
+    with pytest.raises(ValueError, match="no_such_thing"):      # the compiler's message reaches the caller
         UnscentedKalmanFilter(4, 2, .1, LinearHx(H), DeviceFx("__device__ void fx(const real *x, real *o, real dt, const real *a) { o[0] = no_such_thing; }"),
                               pts, n_filters=4)
     u = UnscentedKalmanFilter(4, 2, .1, LinearHx(H), DeviceFx(wl.CT_FX_SOURCE, arg_names=("omega",)), pts, n_filters=4)
