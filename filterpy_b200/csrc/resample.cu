@@ -406,6 +406,47 @@ __global__ void __launch_bounds__(BLOCK, 3) k_tile_maps_fast(Params p)
     }
 }
 
+// The same, one tile per CTA and no register double-buffer (the default): fewer registers, more resident CTAs —
+// the way pass A reaches the HBM roofline.
+__global__ void __launch_bounds__(BLOCK, 5) k_tile_maps_fast1(Params p)
+{
+    __shared__ i64 shi[BLOCK / 32 + 1];
+    const int t = blockIdx.x;
+    const double tp = p.ws.tile_prefix[t], tp_next = p.ws.tile_prefix[t + 1];
+    double2 g[IPT / 2];
+    fetch_tile(p, t, g);
+    if (p.ws.hdr->fallback) return;
+    int e0;
+    const bool tile_clean = clean_add(tp, tp_next, p.eb, &e0);
+    const i64 base = (i64)e0 << 52;
+    const double B0 = __longlong_as_double(base), B1 = __longlong_as_double(base + 1);
+    i64 acc = 0;
+    bool ok = tile_clean, nz = false;
+#pragma unroll
+    for (int i = 0; i < IPT / 2; i++) {
+        const double w2[2] = {g[i].x, g[i].y};
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const i64 d0 = __double_as_longlong(__dadd_rn(B0, w2[h])) - base;
+            const i64 d1 = __double_as_longlong(__dadd_rn(B1, w2[h])) - (base + 1);
+            ok = ok && (d0 == d1);
+            nz = nz || (w2[h] != 0.0);
+            acc += d0;
+        }
+    }
+    if (__syncthreads_and(ok)) {
+        i64 total;
+        block_excl_scan_i64(acc, &total, shi);
+        const int any_nz = __syncthreads_or(nz);
+        if (threadIdx.x == 0) {
+            p.ws.tile_k[t] = any_nz ? e0 : K_ID; p.ws.tile_d[t] = total; p.ws.tile_t[t] = 0;
+            p.ws.tile_slot[t] = SLOT_FAST;
+        }
+    } else if (threadIdx.x == 0) {
+        p.ws.slow_list[atomicAdd(&p.ws.hdr->n_slow, 1)] = t;
+    }
+}
+
 // ------------------------------------------------------------------ passes A + B + C in one launch
 // One CTA per tile, in blockIdx order.  The tile is read ONCE: its sum is published as a 64-bit status
 // word (value with the two low mantissa bits replaced by a flag: 1 = aggregate, 2 = inclusive prefix;
@@ -1743,7 +1784,11 @@ int run(const RunArgs &a, cudaStream_t s)
                 k_tile_sums<<<T, BLOCK, 0, s>>>(p);
             }
             k_scan_tiles<<<1, CHAIN_THREADS, 0, s>>>(p);
-            k_tile_maps_fast<<<T < sms * 3 ? T : sms * 3, BLOCK, 0, s>>>(p);
+            // one tile per CTA (47 registers, 5 CTAs/SM): 83 us at 2^26 against 97 us for the persistent kernel with a
+            // register double-buffer (80 registers, 3 CTAs/SM; BKE_RS_MAPS=0 keeps it for comparison)
+            static const bool maps_persistent = [] { const char *e = getenv("BKE_RS_MAPS"); return e && e[0] == '0'; }();
+            if (maps_persistent) k_tile_maps_fast<<<T < sms * 3 ? T : sms * 3, BLOCK, 0, s>>>(p);
+            else k_tile_maps_fast1<<<T, BLOCK, 0, s>>>(p);
         }
         k_tile_maps<<<slow_grid, BLOCK, 0, s>>>(p);
     }
