@@ -29,6 +29,7 @@ EXPORTED_SYMBOLS = [
     "bke_ukf_model_compile", "bke_ukf_model_log", "bke_ukf_model_registers", "bke_ukf_model_free", "bke_ukf_step_model",
     "bke_debug_ukf_model_cubin_bytes", "bke_ukf_rts_smoother_model",
     "bke_kf_rts_smoother", "bke_ukf_rts_smoother", "bke_mm_probabilities", "bke_mm_mix", "bke_mm_estimate", "bke_cumsum_exact", "bke_searchsorted", "bke_multinomial_resample", "bke_gather_rows",
+    "bke_residual_workspace_bytes", "bke_residual_prepare", "bke_searchsorted_bracket_sweep",
 ]
 
 
@@ -276,6 +277,14 @@ def load():
     lib.bke_gather_rows.argtypes = [c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
                                     c_void_p]
     lib.bke_gather_rows.restype = ctypes.c_int
+    lib.bke_residual_workspace_bytes.argtypes = [c_int64]
+    lib.bke_residual_workspace_bytes.restype = c_size_t
+    lib.bke_residual_prepare.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                         c_void_p]
+    lib.bke_residual_prepare.restype = ctypes.c_int
+    lib.bke_searchsorted_bracket_sweep.argtypes = [c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                   c_void_p, c_void_p]
+    lib.bke_searchsorted_bracket_sweep.restype = ctypes.c_int
     if lib.bke_abi_version() != 1:
         raise BkeError("libbke.so ABI version mismatch")
     _lib = lib

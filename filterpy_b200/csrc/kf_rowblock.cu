@@ -308,17 +308,23 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
         for (int i = 0; i < RPL; i++) xo[i] = xr[i];
         // A holds this lane's rows of P'; they become the output unless the update succeeds
         if (has_z) {
-            T Hm[M][N];
+            // H in registers while it is at most 64 of them; larger (16/4 fp64) it is read from shared memory
+            // where it is used (the lanes of a filter read the same address: a broadcast)
+            constexpr bool H_IN_REGS = M * N * (int)sizeof(T) <= 256;
+            T Hreg[H_IN_REGS ? M : 1][H_IN_REGS ? N : 1];
+            if constexpr (H_IN_REGS) {
 #pragma unroll
-            for (int a = 0; a < M; a++)
+                for (int a = 0; a < M; a++)
 #pragma unroll
-                for (int k = 0; k < N; k++) Hm[a][k] = sH[a * N + k];
+                    for (int k = 0; k < N; k++) Hreg[a][k] = sH[a * N + k];
+            }
+            auto Hm = [&](int a, int k) -> T { if constexpr (H_IN_REGS) return Hreg[a][k]; else return sH[a * N + k]; };
             T y[M];
 #pragma unroll
             for (int a = 0; a < M; a++) {
                 T s = T(0);
 #pragma unroll
-                for (int k = 0; k < N; k++) s += Hm[a][k] * sx[k];
+                for (int k = 0; k < N; k++) s += Hm(a, k) * sx[k];
                 y[a] = sz[a] - s;
             }
             // own rows of P H'  -> parked in the Q slot (offset 0)
@@ -329,7 +335,7 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
                 for (int a = 0; a < M; a++) {
                     T s = T(0);
 #pragma unroll
-                    for (int k = 0; k < N; k++) s += A[i][k] * Hm[a][k];
+                    for (int k = 0; k < N; k++) s += A[i][k] * Hm(a, k);
                     PHT[i][a] = s;
                 }
             T *sPHT = sQ;                     // [N][M]
@@ -349,7 +355,7 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
                 for (int b = 0; b < M; b++) {
                     T s = sR[a * M + b];
 #pragma unroll
-                    for (int k = 0; k < N; k++) s += Hm[a][k] * sPHT[k * M + b];
+                    for (int k = 0; k < N; k++) s += Hm(a, k) * sPHT[k * M + b];
                     o.S[a][b] = s;
                 }
             o.ok = reg_inverse<T, M>(o.S, o.SI, o.logdet);
@@ -380,7 +386,7 @@ __global__ void __launch_bounds__(RB_WARPS * 32, 1) kf_rowblock_kernel(RbP<T> p)
                 for (int j = 0; j < N; j++) {
                     T s = ((r0 + i) == j) ? T(1) : T(0);
 #pragma unroll
-                    for (int a = 0; a < M; a++) s -= Kr[i][a] * Hm[a][j];
+                    for (int a = 0; a < M; a++) s -= Kr[i][a] * Hm(a, j);
                     C[i][j] = s;                                   // own rows of I - K H
                 }
             if (EXTRAS && active && (p.K || p.y || p.S || p.SI || p.ll)) {
@@ -629,7 +635,12 @@ int launch_kf_rowblock(const bke_kf_args &a, cudaStream_t s)
         if (n == 9 && m == 3) return ring ? launch_rb<double, 9, 3, 3, 2, 4>(a, s) : launch_rb<double, 9, 3, 3, 1, 8>(a, s);
         if (n == 4 && m == 2) return ring ? launch_rb<double, 4, 2, 2, 2, 4>(a, s) : launch_rb<double, 4, 2, 2, 1, 8>(a, s);
         if (n == 6 && m == 3) return ring ? launch_rb<double, 6, 3, 3, 2, 4>(a, s) : launch_rb<double, 6, 3, 3, 1, 8>(a, s);
+        // dim_x = 16 (SURVEY §2 "K1-MMA" shapes): one row per lane, 16 lanes per filter, 2 filters per warp tile
+        if (n == 16 && m == 4) return launch_rb<double, 16, 4, 1, 1, 8>(a, s);
+        if (n == 16 && m == 2) return launch_rb<double, 16, 2, 1, 1, 8>(a, s);
     } else {
+        if (n == 16 && m == 4) return launch_rb<float, 16, 4, 2, 1, 8>(a, s);   // two rows per lane, 4 filters per warp tile
+        if (n == 16 && m == 2) return launch_rb<float, 16, 2, 2, 1, 8>(a, s);
         if (n == 6 && m == 3) return ring ? launch_rb<float, 6, 3, 3, 2, 4>(a, s) : launch_rb<float, 6, 3, 3, 1, 8>(a, s);
         if (n == 9 && m == 3) return launch_rb<float, 9, 3, 3, 1, 8>(a, s);        // 8 filters per warp tile (see pick_fpw)
     }

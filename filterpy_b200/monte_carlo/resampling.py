@@ -18,7 +18,8 @@ from .. import _lib
 from .._dev import require_cuda, stream_ptr
 
 __all__ = ["systematic_resample", "stratified_resample", "multinomial_resample", "residual_resample",
-           "gather_particles", "exact_cumsum", "ResamplePlan", "normalize_weights"]
+           "gather_particles", "exact_cumsum", "ResamplePlan", "normalize_weights",
+           "residual_resample_with_uniforms"]
 
 
 class ResamplePlan(object):
@@ -186,13 +187,66 @@ def multinomial_resample(weights):
     return idx if is_torch else idx.cpu().numpy()
 
 
+def residual_resample_with_uniforms(weights, uniforms_fn=random, max_sweeps=10000):
+    """residual_resample for uniforms drawn by ``uniforms_fn(N - k)`` (the reference: ``random``);
+    returns (indexes, info) with info = dict(k, sweeps, residual_sum)."""
+    is_torch, w, dev = _weights_on_device(weights)
+    n = w.numel()
+    if n == 0:
+        # resampling.py:70-72 on empty arrays: sum([]) = 0, cumulative_sum[-1] raises IndexError
+        raise IndexError("index -1 is out of bounds for axis 0 with size 0")
+    lib = _lib.load()
+    ws_bytes = int(lib.bke_residual_workspace_bytes(n))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    idx = torch.zeros(n, dtype=torch.int32, device=dev)              # np.zeros(N, 'i') (:52)
+    csum = torch.empty(n, dtype=torch.float64, device=dev)
+    k_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+    rsum = torch.zeros(1, dtype=torch.float64, device=dev)
+    st = stream_ptr(dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.bke_residual_prepare(n, w.data_ptr(), idx.data_ptr(), csum.data_ptr(), k_dev.data_ptr(),
+                                            rsum.data_ptr(), ws.data_ptr(), ws_bytes, st))
+        k = int(k_dev.item())
+        if k > n:                                                     # indexes[k] = i runs off the end (:61)
+            raise IndexError("index %d is out of bounds for axis 0 with size %d" % (n, n))
+        m = n - k
+        U = np.atleast_1d(uniforms_fn(m))                             # resampling.py:74: random(N - k)
+        sweeps = 0
+        if m > 0:
+            keys = torch.from_numpy(np.ascontiguousarray(U, dtype=np.float64)).to(dev)
+            r = [torch.empty(m, dtype=torch.int64, device=dev), torch.empty(m, dtype=torch.int64, device=dev)]
+            changed = torch.zeros(1, dtype=torch.int32, device=dev)
+            tail = idx[k:]
+            # the int32 copies land directly in indexes[k:N] when that view is 4-byte aligned (always)
+            _lib.check(lib.bke_searchsorted_bracket_sweep(n, csum.data_ptr(), m, keys.data_ptr(), None,
+                                                          r[0].data_ptr(), tail.data_ptr(), changed.data_ptr(), st))
+            cur = 0
+            while True:
+                sweeps += 1
+                changed.zero_()
+                _lib.check(lib.bke_searchsorted_bracket_sweep(n, csum.data_ptr(), m, keys.data_ptr(), r[cur].data_ptr(),
+                                                              r[1 - cur].data_ptr(), tail.data_ptr(),
+                                                              changed.data_ptr(), st))
+                cur = 1 - cur
+                if int(changed.item()) == 0:
+                    break
+                if sweeps >= max_sweeps:
+                    raise RuntimeError("residual_resample: the bracket recurrence did not settle in %d sweeps"
+                                       % max_sweeps)
+    info = {"k": k, "sweeps": sweeps, "residual_sum": float(rsum.item())}
+    return (idx if is_torch else idx.cpu().numpy()), info
+
+
 def residual_resample(weights):
-    """resampling.py:27-76 is NOT offered: it forms ``residual = weights - num_copies`` (:69), which is
-    negative for every particle with N*w >= 1, so its cumulative sum is not monotone and the result of
-    ``np.searchsorted`` on it (:74) depends on NumPy's probing order and on the previous key — there
-    is no algorithm-level answer to be bit-exact against."""
-    raise NotImplementedError("residual_resample: the reference's result is implementation-defined "
-                              "(searchsorted over a non-monotone array, resampling.py:69-74)")
+    """resampling.py:27-76 on the GPU, same call, same result for the same ``np.random`` state.
+
+    The reference's ``residual = weights - num_copies`` (:69; not ``N*weights - num_copies``) is negative
+    for every particle that got a copy, so the cumulative sum it bisects (:74) is not monotone and
+    ``np.searchsorted``'s answer depends on the bracket NumPy carries from key to key.  The engine
+    reproduces exactly that: the order-dependent sums in the reference's order, and NumPy's bracket
+    recurrence as a parallel fixed-point iteration (csrc/residual.cu).  Returns ``ndarray`` int32 (or a
+    CUDA tensor when given one)."""
+    return residual_resample_with_uniforms(weights, random)[0]
 
 
 def exact_cumsum(weights, last_one=False):

@@ -428,6 +428,28 @@ int bke_multinomial_resample(int64_t n, const double *weights, const double *uni
 int bke_gather_rows(int64_t n_out, int64_t n_src, int64_t row_bytes, const void *src, const void *indexes,
                     int32_t index_is_64, void *dst, int32_t *err, void *stream);
 
+/* ---- residual_resample (filterpy/monte_carlo/resampling.py:27-76) --------------------------------
+ *
+ * bke_residual_prepare: everything of residual_resample that does not need the uniforms —
+ *   num_copies = floor(N*w) (:57), indexes[0:k] = repeat(arange(N), num_copies) (:58-62; int32 like the
+ *   reference's np.zeros(N, 'i')), *n_copies_out = k, residual = w - num_copies (:69),
+ *   *residual_sum_out = sum(residual) in the builtin's left-to-right fp64 order (:70) and
+ *   cumsum_out = np.cumsum(residual / sum) with the last element set to 1 (:71-72), bit for bit.
+ *   The caller draws random(N - k) (:74) after reading k.  workspace: bke_residual_workspace_bytes(n).
+ * bke_searchsorted_bracket_sweep: np.searchsorted(arr, keys) (side='left') for an array that need NOT
+ *   be sorted — residual's cumulative sum is not monotone, and NumPy's bisection carries its bracket
+ *   from one key to the next (npy_binsearch: [r[i-1], n) if key[i-1] < key[i], else [0, r[i-1]+1)), so
+ *   result i depends on result i-1.  One call evaluates that recurrence for all keys in parallel from
+ *   the previous sweep's results `prev` (NULL for the first sweep: every key over [0, n)), writes `next`
+ *   (and int32 copies to indexes32 when given) and sets *changed to 1 if any entry differs from prev.
+ *   Repeat with prev/next swapped until *changed stays 0 (caller zeroes it before each sweep): the
+ *   fixed point is NumPy's result, reached after at most n_keys sweeps, two or three in practice. */
+size_t bke_residual_workspace_bytes(int64_t n);
+int bke_residual_prepare(int64_t n, const double *weights, int32_t *indexes, double *cumsum_out, int64_t *n_copies_out,
+                         double *residual_sum_out, void *workspace, size_t workspace_bytes, void *stream);
+int bke_searchsorted_bracket_sweep(int64_t n, const double *arr, int64_t n_keys, const double *keys, const int64_t *prev,
+                                   int64_t *next, int32_t *indexes32, int32_t *changed, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

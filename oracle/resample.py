@@ -5,6 +5,7 @@ Restates ``filterpy/monte_carlo/resampling.py`` (reference @ 3b51149):
 * ``systematic_resample``  resampling.py:117-150
 * ``stratified_resample``  resampling.py:80-114
 * ``multinomial_resample`` resampling.py:153-176
+* ``residual_resample``    resampling.py:27-76 (+ NumPy's ``npy_binsearch``, restated below)
 
 The reference draws its uniforms from the process-global legacy RandomState
 (resampling.py:24,103,139); here the uniform(s) are explicit arguments so that a
@@ -106,6 +107,71 @@ def multinomial_resample_loop(weights, U):
                 hi = mid
         out[q] = lo
     return out
+
+
+def binsearch_left(arr, keys):
+    """``np.searchsorted(arr, keys)`` (side='left') as NumPy computes it, for ANY ``arr`` (sorted or
+    not): numpy/_core/src/npysort/binsearch.cpp ``binsearch<Tag, side>`` (NumPy 2.3) keeps the bracket of
+    the previous key — ``[min_idx, arr_len)`` if ``last_key < key`` else ``[0, max_idx + 1)`` — and
+    orders doubles with NaN last.  On a sorted array the bracket is irrelevant; on residual_resample's
+    non-monotone cumulative sum (resampling.py:69-74) it decides the answer."""
+    def lt(a, b):
+        return a < b or (b != b and a == a)
+    n = len(arr)
+    out = np.empty(len(keys), np.int64)
+    if len(keys) == 0:
+        return out
+    lo, hi = 0, n
+    last = keys[0]
+    for i, key in enumerate(keys):
+        if lt(last, key):
+            hi = n
+        else:
+            lo = 0
+            hi = hi + 1 if hi < n else n
+        last = key
+        while lo < hi:
+            mid = lo + ((hi - lo) >> 1)
+            if lt(arr[mid], key):
+                lo = mid + 1
+            else:
+                hi = mid
+        out[i] = lo
+    return out
+
+
+def residual_prepare(weights):
+    """resampling.py:52-72 without the uniforms: (indexes with the first k entries filled, k,
+    cumulative_sum, sum(residual)); every sum in the reference's order (builtin ``sum`` :70 and
+    ``np.cumsum`` :71 are both one fp64 add at a time)."""
+    weights = np.asarray(weights, dtype=np.float64)
+    N = len(weights)
+    indexes = np.zeros(N, 'i')
+    num_copies = (np.floor(N * weights)).astype(int)
+    k = int(np.maximum(num_copies, 0).sum())
+    if k > N:
+        raise IndexError("index %d is out of bounds for axis 0 with size %d" % (N, N))
+    indexes[:k] = np.repeat(np.arange(N), np.maximum(num_copies, 0))
+    residual = weights - num_copies
+    s = 0.0
+    for r in residual:                       # builtin sum(): left to right
+        s = s + r
+    with np.errstate(all="ignore"):
+        residual = residual / s
+    cumulative_sum = np.cumsum(residual)
+    cumulative_sum[-1] = 1.
+    return indexes, k, cumulative_sum, s
+
+
+def residual_resample_vec(weights, U):
+    """resampling.py:27-76 with the uniforms ``random(N - k)`` passed in; the bisection by the
+    restatement above (``binsearch_left``), not by NumPy."""
+    indexes, k, cumulative_sum, _ = residual_prepare(weights)
+    N = len(indexes)
+    U = np.atleast_1d(U)
+    assert len(U) == N - k
+    indexes[k:N] = binsearch_left(cumulative_sum, U)
+    return indexes
 
 
 # --------------------------------------------------------------------------- C port

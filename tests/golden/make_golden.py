@@ -23,6 +23,7 @@ sys.path.insert(0, "/root/reference")
 from filterpy.kalman import KalmanFilter, UnscentedKalmanFilter, MerweScaledSigmaPoints  # noqa: E402
 from filterpy.kalman import predict as kf_predict_proc, update as kf_update_proc          # noqa: E402
 from filterpy.monte_carlo import systematic_resample, stratified_resample, multinomial_resample  # noqa: E402
+from filterpy.monte_carlo import residual_resample                                                  # noqa: E402
 from filterpy.kalman import rts_smoother as rts_proc                                      # noqa: E402
 import filterpy                                                                            # noqa: E402
 
@@ -305,6 +306,26 @@ def gen_multinomial():
     save("resample_multinomial", meta=np.array(meta), **cases)
 
 
+def gen_residual():
+    """residual_resample (resampling.py:27-76) on the weight families of the resample goldens: the
+    reference's result, the uniforms it drew (random(N - k) after seeding) and k."""
+    cases = {}
+    meta = []
+    i = 0
+    for kind in ["heavy", "uniform", "zeros", "degenerate", "dyadic"]:
+        for N in [1, 2, 7, 100, 1000, 4097, 20011]:
+            w = wl.resample_weights(N, kind, seed=57 + N)
+            np.random.seed(300 + i)
+            idx = residual_resample(w.copy())
+            k = int(np.floor(N * w).astype(int).sum())
+            np.random.seed(300 + i)
+            U = np.random.random(N - k)
+            cases["w%d" % i] = w; cases["U%d" % i] = U; cases["idx%d" % i] = idx
+            meta.append((i, N, 300 + i, k))
+            i += 1
+    save("resample_residual", meta=np.array(meta), **cases)
+
+
 # ----------------------------------------------------------------------------- RTS smoother
 def gen_rts():
     out = {}
@@ -443,6 +464,7 @@ if __name__ == "__main__":
     gen_ukf()
     gen_resample()
     gen_multinomial()
+    gen_residual()
     gen_rts()
     gen_ukf_rts()
     gen_mm()

@@ -367,7 +367,8 @@ def test_shared_models_in_launch_parameters_equal_device_models(golden, diagnost
     np.testing.assert_allclose(outs[0][0], x, rtol=1e-3, atol=1e-3 * np.abs(x).max())
 
 
-@pytest.mark.parametrize("n,m", [(1, 1), (2, 1), (2, 2), (3, 1), (4, 1), (4, 2), (4, 4), (6, 2), (6, 3), (9, 3)])
+@pytest.mark.parametrize("n,m", [(1, 1), (2, 1), (2, 2), (3, 1), (4, 1), (4, 2), (4, 4), (6, 2), (6, 3), (9, 3),
+                                 (16, 4), (16, 2), (12, 3)])      # 16/x: row-block instances; 12/3: catch-all
 @pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-6), (np.float32, 1e-3)])
 @pytest.mark.parametrize("shared", [False, True])
 def test_small_shapes_random_models_vs_oracle(n, m, dtype, tol, shared):
@@ -405,7 +406,8 @@ def test_small_shapes_random_models_vs_oracle(n, m, dtype, tol, shared):
         assert np.all(np.abs(got - want) <= tol * (np.abs(want) + 0.05 * ref_mag + 1e-12)), (n, m, dtype)
 
 
-@pytest.mark.parametrize("n,m,dtype", [(9, 3, np.float64), (9, 3, np.float32), (6, 3, np.float64)])
+@pytest.mark.parametrize("n,m,dtype", [(9, 3, np.float64), (9, 3, np.float32), (6, 3, np.float64),
+                                       (16, 4, np.float64), (16, 4, np.float32), (16, 2, np.float64)])
 @pytest.mark.parametrize("diagnostics", [False, True])
 @pytest.mark.parametrize("shared", [False, True])
 def test_rowblock_separate_predict_and_update_match_fused(n, m, dtype, diagnostics, shared):

@@ -68,8 +68,90 @@ def test_multinomial_public_function_reproduces_reference_rng_stream(golden):
         np.random.seed(int(seed))
         got = multinomial_resample(g["w%d" % i])
         assert got.dtype == np.int64 and np.array_equal(got, g["idx%d" % i])
-    with pytest.raises(NotImplementedError):
-        residual_resample([.5, .5])
+
+
+def test_residual_resample_vs_reference_golden(golden):
+    """resampling.py:27-76 through the public mirror with the reference's RNG stream: bit-equal int32
+    indexes on every golden case (23 of the 35 cumulative sums are not monotone)."""
+    from filterpy_b200.monte_carlo import residual_resample
+    g = golden("resample_residual")
+    for (i, N, seed, k) in g["meta"]:
+        np.random.seed(int(seed))
+        got = residual_resample(g["w%d" % i])
+        assert got.dtype == np.int32 and got.shape == (N,)
+        assert np.array_equal(got, g["idx%d" % i]), (i, N)
+    # the stream position afterwards is the reference's too: exactly N - k uniforms were drawn
+    (i, N, seed, k) = g["meta"][10]
+    np.random.seed(int(seed)); residual_resample(g["w%d" % i]); nxt = np.random.random()
+    np.random.seed(int(seed)); np.random.random(int(N - k)); assert nxt == np.random.random()
+    with pytest.raises(IndexError):
+        residual_resample(np.zeros(0))
+
+
+@pytest.mark.parametrize("kind", ["heavy", "uniform", "zeros", "degenerate"])
+def test_residual_resample_large_vs_oracle(kind):
+    """2^20 particles: the deterministic copies, sum(residual), the cumulative sum (bit patterns) and the
+    bracket-carrying bisection against the oracle / NumPy's searchsorted on the oracle's cumulative sum."""
+    import torch
+    from filterpy_b200.monte_carlo import residual_resample_with_uniforms
+    from filterpy_b200.common import workloads as wl
+    N = 1 << 20
+    w = wl.resample_weights(N, kind, seed=77)
+    with np.errstate(all="ignore"):
+        idx0, k, c, s = ors.residual_prepare(w)
+    rng = np.random.default_rng(12)
+    U = rng.random(N - k)
+    got, info = residual_resample_with_uniforms(torch.from_numpy(w).cuda(), lambda m: U[:m])
+    got = got.cpu().numpy()
+    assert info["k"] == k
+    assert info["residual_sum"] == s or (np.isnan(s) and np.isnan(info["residual_sum"]))
+    assert np.array_equal(got[:k], idx0[:k])
+    assert np.array_equal(got[k:], np.searchsorted(c, U).astype(np.int32))
+    assert 1 <= info["sweeps"] <= 64
+
+
+def test_residual_cumsum_bits_and_sweep_abi():
+    """The C-ABI pieces directly: cumulative_sum bit for bit (incl. the forced last 1.0) and one
+    bracket sweep from a deliberately wrong `prev` moves towards NumPy's answer."""
+    import torch
+    from filterpy_b200 import _lib
+    from filterpy_b200._dev import stream_ptr
+    lib = _lib.load()
+    rng = np.random.default_rng(8)
+    for N in [1, 2, 33, 1024, 1025, 5000]:
+        w = rng.random(N) ** 5
+        w /= w.sum()
+        with np.errstate(all="ignore"):
+            idx0, k, c, s = ors.residual_prepare(w)
+        wd = torch.from_numpy(w).cuda()
+        idx = torch.full((N,), -7, dtype=torch.int32, device="cuda")
+        cs = torch.empty(N, dtype=torch.float64, device="cuda")
+        kd = torch.zeros(1, dtype=torch.int64, device="cuda")
+        sd = torch.zeros(1, dtype=torch.float64, device="cuda")
+        nb = int(lib.bke_residual_workspace_bytes(N))
+        ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+        _lib.check(lib.bke_residual_prepare(N, wd.data_ptr(), idx.data_ptr(), cs.data_ptr(), kd.data_ptr(), sd.data_ptr(),
+                                            ws.data_ptr(), nb, stream_ptr(wd.device)))
+        assert int(kd.item()) == k
+        assert np.array_equal(idx.cpu().numpy()[:k], idx0[:k]) and np.all(idx.cpu().numpy()[k:] == -7)
+        assert np.array_equal(cs.cpu().numpy().view(np.int64), c.view(np.int64))      # NaNs included
+        m = N - k
+        if m == 0:
+            continue
+        U = rng.random(m)
+        ref = np.searchsorted(c, U)
+        keys = torch.from_numpy(U).cuda()
+        prev = torch.zeros(m, dtype=torch.int64, device="cuda")                       # wrong on purpose
+        nxt = torch.empty_like(prev)
+        ch = torch.zeros(1, dtype=torch.int32, device="cuda")
+        for _ in range(m + 2):
+            ch.zero_()
+            _lib.check(lib.bke_searchsorted_bracket_sweep(N, cs.data_ptr(), m, keys.data_ptr(), prev.data_ptr(),
+                                                          nxt.data_ptr(), None, ch.data_ptr(), stream_ptr(wd.device)))
+            prev, nxt = nxt, prev
+            if int(ch.item()) == 0:
+                break
+        assert np.array_equal(prev.cpu().numpy(), ref)
 
 
 def test_searchsorted_matches_numpy_both_sides():

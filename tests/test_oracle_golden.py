@@ -224,6 +224,45 @@ def test_multinomial_oracle_vs_reference_vectors(golden):
             assert np.array_equal(ors.multinomial_resample_loop(w, U), ref)
 
 
+def test_residual_oracle_vs_reference_vectors(golden):
+    """resampling.py:27-76: the restatement (reference-order sums + NumPy's bracket-carrying bisection,
+    oracle/resample.py:binsearch_left) reproduces the reference on every golden case; most of these
+    cumulative sums are NOT monotone and on at least one the carried bracket decides the answer."""
+    g = golden("resample_residual")
+    nonmono = dep = 0
+    for (i, N, seed, k) in g["meta"]:
+        w, U, ref = g["w%d" % i], g["U%d" % i], g["idx%d" % i]
+        assert ref.dtype == np.int32 and len(U) == N - k
+        with np.errstate(all="ignore"):
+            assert np.array_equal(ors.residual_resample_vec(w, U), ref)
+            _, k2, c, _ = ors.residual_prepare(w)
+        assert k2 == k
+        nonmono += bool(np.any(np.diff(c) < 0))
+        # NumPy's own searchsorted on the oracle's cumulative sum agrees with the restated bisection
+        assert np.array_equal(np.searchsorted(c, U), ref[k:])
+        if N <= 4097 and len(U):
+            ind = np.array([ors.binsearch_left(c, [u])[0] for u in U])
+            dep += not np.array_equal(ind, ref[k:])
+    assert nonmono >= 10 and dep >= 1
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree not present")
+def test_residual_live_reference():
+    sys.path.insert(0, "/root/reference")
+    try:
+        from filterpy.monte_carlo import residual_resample
+    finally:
+        sys.path.remove("/root/reference")
+    rng = np.random.default_rng(5)
+    for N in [3, 50, 3001]:
+        w = rng.random(N) ** 3
+        w /= w.sum()
+        np.random.seed(21); ref = residual_resample(w.copy())
+        k = int(np.floor(N * w).astype(int).sum())
+        np.random.seed(21); U = np.random.random(N - k)
+        assert np.array_equal(ors.residual_resample_vec(w, U), ref)
+
+
 def test_rts_oracle_vs_reference_vectors(golden):
     g = golden("rts")
     T = g["c1_means"].shape[0]
