@@ -83,7 +83,8 @@ using namespace bke;
 namespace bke {
 int launch_kf_any(const bke_kf_args &a, cudaStream_t s)
 {
-    int rc = launch_kf_fast(a, s);
+    int rc = launch_kf_tc(a, s);
+    if (rc == BKE_ERR_UNSUPPORTED) rc = launch_kf_fast(a, s);
     if (rc == BKE_ERR_UNSUPPORTED) rc = launch_kf_direct(a, s);
     if (rc == BKE_ERR_UNSUPPORTED) rc = launch_kf_rowblock(a, s);
     if (rc == BKE_ERR_UNSUPPORTED) rc = launch_kf_generic(a, s);

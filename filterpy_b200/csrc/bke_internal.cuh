@@ -33,7 +33,11 @@ int launch_kf_generic(const bke_kf_args &a, cudaStream_t s);
 int launch_kf_fast(const bke_kf_args &a, cudaStream_t s);
 int launch_kf_rowblock(const bke_kf_args &a, cudaStream_t s);
 int launch_kf_direct(const bke_kf_args &a, cudaStream_t s);
-// the dispatch order of bke_kf_step: TMA-staged 4/2 fp32 -> register tile with direct loads -> row-block -> catch-all
+// tcgen05 covariance propagation for shared-model fp32 banks with dim_x = 16 / 32 (kf_tc.cu); a fused step runs
+// its update through launch_kf_any afterwards
+int launch_kf_tc(const bke_kf_args &a, cudaStream_t s);
+// the dispatch order of bke_kf_step: tensor-core predict (dim_x 16 / 32, shared models) -> TMA-staged 4/2 fp32 ->
+// register tile with direct loads -> row-block -> catch-all
 int launch_kf_any(const bke_kf_args &a, cudaStream_t s);
 int launch_kf_batch(const bke_kf_batch_args &a, cudaStream_t s);
 int launch_ukf(const bke_ukf_args &a, cudaStream_t s);
