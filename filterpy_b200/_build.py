@@ -93,6 +93,44 @@ def _build_locked(nvcc, force, verbose, extra_flags):
     return LIB
 
 
+TORCH_OPS_SRC = os.path.join(HERE, "torch_ops", "bke_torch_ops.cpp")
+TORCH_OPS_LIB = os.path.join(OUT_DIR, "libbke_torch_ops.so")
+
+
+def build_torch_ops(force=False):
+    """Compile the torch.ops.bke.* twin of the C-ABI (torch_ops/bke_torch_ops.cpp) against the installed
+    PyTorch and link it to libbke.so (rpath $ORIGIN).  g++ only: the file holds no device code."""
+    build()
+    deps = [TORCH_OPS_SRC, os.path.join(os.path.dirname(HERE), "include", "bke.h")]
+    if (not force and os.path.exists(TORCH_OPS_LIB)
+            and all(os.path.getmtime(TORCH_OPS_LIB) > os.path.getmtime(d) for d in deps)):
+        return TORCH_OPS_LIB
+    gxx = shutil.which("g++")
+    if gxx is None:
+        raise RuntimeError("g++ not found and %s is missing or stale" % TORCH_OPS_LIB)
+    import torch
+    from torch.utils import cpp_extension as ce
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    cmd = [gxx, "-O2", "-std=c++17", "-fPIC", "-shared",
+           "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI)]
+    cmd += ["-I" + d for d in ce.include_paths()] + ["-I" + cuda_inc, TORCH_OPS_SRC, "-o", TORCH_OPS_LIB + ".tmp",
+            "-L" + OUT_DIR, "-lbke", "-L" + tlib, "-ltorch", "-ltorch_cpu", "-ltorch_cuda", "-lc10", "-lc10_cuda",
+            "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + tlib]
+    import fcntl
+    lock = open(os.path.join(OUT_DIR, ".build_ops.lock"), "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("g++ failed for the torch.ops twin:\n%s\n%s" % (r.stdout, r.stderr))
+        os.replace(TORCH_OPS_LIB + ".tmp", TORCH_OPS_LIB)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+    return TORCH_OPS_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True,
                 extra_flags=["-Xptxas", "-v"] if "--ptxas-v" in sys.argv else []))
