@@ -46,9 +46,12 @@ struct Geom {
     static constexpr int B_BYTES = NX * NX * 4;
     static constexpr int SBO = 128;                 // bytes between 8-row groups (core matrices are contiguous)
     static constexpr int TMEM_COLS = 2 * NX;        // D1 in columns [0, NX), D2 in [NX, 2 NX): 32 or 64 (powers of two)
-    // shared memory: A_hi | A_lo | F_hi | F_lo | F (plain, for x' = F x) | Q | mbarrier, TMEM slot
+    // shared memory: A_hi | A_lo | F_hi | F_lo | F (plain, rows padded to NX + 1 words: x' = F x reads row r in
+    // thread r) | Q | transposition scratch [128][NX + 1] | mbarrier, TMEM slot
+    static constexpr int FP = NX + 1;
     static constexpr int O_AHI = 0, O_ALO = O_AHI + A_BYTES, O_FHI = O_ALO + A_BYTES, O_FLO = O_FHI + B_BYTES;
-    static constexpr int O_F = O_FLO + B_BYTES, O_Q = O_F + B_BYTES, O_BAR = O_Q + B_BYTES, SMEM = O_BAR + 64;
+    static constexpr int O_F = O_FLO + B_BYTES, O_Q = O_F + ((NX * FP * 4 + 15) & ~15), O_T = O_Q + B_BYTES;
+    static constexpr int O_BAR = O_T + ((128 * FP * 4 + 15) & ~15), SMEM = O_BAR + 64;
     // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D = f32 (bits 4-5 = 1), A = B = tf32
     // (bits 7-9 / 10-12 = 2), both K-major (bits 15, 16 = 0), N >> 3 at bit 17, M >> 4 at bit 24
     static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NX >> 3) << 17) | ((128u >> 4) << 24);
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__(128, 4) kf_cov_tc_kernel(TcP p)
         const float hi = tf32_hi(f);
         *reinterpret_cast<float *>(smem + G::O_FHI + op_off(n, k, G::B_LBO)) = hi;
         *reinterpret_cast<float *>(smem + G::O_FLO + op_off(n, k, G::B_LBO)) = f - hi;
-        Fs[e] = f;
+        Fs[n * G::FP + k] = f;
         Qs[e] = p.Q[e];
     }
     if (tid == 0) {
@@ -215,34 +218,47 @@ __global__ void __launch_bounds__(128, 4) kf_cov_tc_kernel(TcP p)
             if (live) {
                 const float *xf = p.x + f * NX;
 #pragma unroll
-                for (int k = 0; k < NX; k++) xr += Fs[r * NX + k] * xf[k];
+                for (int k = 0; k < NX; k++) xr += Fs[r * G::FP + k] * xf[k];
             }
         }
         tc_fence_before();
         fence_proxy_async();          // generic-proxy writes of the operands -> visible to the tensor core (async proxy)
         __syncthreads();
         // ---- 2. D1 = P F'  (rows (i,r), columns c)
-        if (tid == 0) { tc_fence_after(); issue_product(0); }
+        if (warp == 0) {                 // lane 0 issues; its warp waits for it before polling the barrier
+            if (tid == 0) { tc_fence_after(); issue_product(0); }
+            __syncwarp();
+        }
         ok = mbar_wait(bar, phase); phase ^= 1;
         if (!ok) break;
         tc_fence_after();
         {
+            // ---- 3. transpose every filter's block on the way back: A2[(i,c)][k] = Y_i[k][c].  Rows go to a padded
+            // scratch (conflict-free), then thread (i,c) gathers column c and writes ITS operand row as 16-byte chunks
             float y[NX];
             tmem_ld_row<NX>(lane_base + 0, y);
-            // ---- 3. transpose the filter's block on the way back: A2[(i,c)][k = r] = Y_i[r][c]
+            float *Ts = reinterpret_cast<float *>(smem + G::O_T);
 #pragma unroll
-            for (int c = 0; c < NX; c++) {
-                const float h = tf32_hi(y[c]);
-                const int off = op_off(i_in_tile * NX + c, r, G::A_LBO);
-                *reinterpret_cast<float *>(smem + G::O_AHI + off) = h;
-                *reinterpret_cast<float *>(smem + G::O_ALO + off) = y[c] - h;
+            for (int c = 0; c < NX; c++) Ts[tid * G::FP + c] = y[c];
+            __syncthreads();
+            const float *col = Ts + (i_in_tile * NX) * G::FP + r;          // Y_i[k][c = r], k = 0 .. NX-1
+#pragma unroll
+            for (int kc = 0; kc < G::KC; kc++) {
+                const float4 v = make_float4(col[(kc * 4 + 0) * G::FP], col[(kc * 4 + 1) * G::FP], col[(kc * 4 + 2) * G::FP], col[(kc * 4 + 3) * G::FP]);
+                const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+                const int off = kc * G::A_LBO + (tid >> 3) * 128 + (tid & 7) * 16;
+                *reinterpret_cast<float4 *>(smem + G::O_AHI + off) = h;
+                *reinterpret_cast<float4 *>(smem + G::O_ALO + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
             }
         }
         tc_fence_before();
         fence_proxy_async();
         __syncthreads();
         // ---- 4. D2 = (F P) F'  (rows (i,c), columns j)
-        if (tid == 0) { tc_fence_after(); issue_product(NX); }
+        if (warp == 0) {
+            if (tid == 0) { tc_fence_after(); issue_product(NX); }
+            __syncwarp();
+        }
         ok = mbar_wait(bar, phase); phase ^= 1;
         if (!ok) break;
         tc_fence_after();
@@ -298,11 +314,14 @@ int launch_t(const TcP &p, cudaStream_t s)
 
 static bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// BKE_KF_TC=0 keeps the CUDA-core kernels for these shapes (A/B measurements)
+// BKE_KF_TC=0 keeps the CUDA-core kernels for these shapes, =2 takes every eligible call (A/B measurements).
+// Default: every eligible predict-only call, and the fused step where no row-block instance covers the shape
+// (16/4 and 16/2 have one whose single launch beats predict-here + update-there).
 int launch_kf_tc(const bke_kf_args &a, cudaStream_t s)
 {
-    static const bool off = [] { const char *e = getenv("BKE_KF_TC"); return e && e[0] == '0'; }();
-    if (off) return BKE_ERR_UNSUPPORTED;
+    static const int mode = [] { const char *e = getenv("BKE_KF_TC"); return e ? atoi(e) : 1; }();
+    if (mode == 0) return BKE_ERR_UNSUPPORTED;
+    if (mode == 1 && (a.flags & BKE_DO_UPDATE) && a.dim_x == 16 && (a.dim_z == 4 || a.dim_z == 2)) return BKE_ERR_UNSUPPORTED;
     if (a.dtype != BKE_F32 || !(a.dim_x == 16 || a.dim_x == 32)) return BKE_ERR_UNSUPPORTED;
     if (!(a.flags & BKE_DO_PREDICT) || (a.flags & BKE_UPDATE_FIRST)) return BKE_ERR_UNSUPPORTED;
     if (a.F_stride != 0 || a.Q_stride != 0 || (a.B && a.u)) return BKE_ERR_UNSUPPORTED;

@@ -95,6 +95,7 @@ def test_residual_resample_large_vs_oracle(kind):
     import torch
     from filterpy_b200.monte_carlo import residual_resample_with_uniforms
     from filterpy_b200.common import workloads as wl
+    from oracle import resample as ors
     N = 1 << 20
     w = wl.resample_weights(N, kind, seed=77)
     with np.errstate(all="ignore"):
@@ -107,7 +108,7 @@ def test_residual_resample_large_vs_oracle(kind):
     assert info["residual_sum"] == s or (np.isnan(s) and np.isnan(info["residual_sum"]))
     assert np.array_equal(got[:k], idx0[:k])
     assert np.array_equal(got[k:], np.searchsorted(c, U).astype(np.int32))
-    assert 1 <= info["sweeps"] <= 64
+    assert info["sweeps"] <= 64 and (info["sweeps"] >= 1 or k == N)
 
 
 def test_residual_cumsum_bits_and_sweep_abi():
@@ -116,6 +117,7 @@ def test_residual_cumsum_bits_and_sweep_abi():
     import torch
     from filterpy_b200 import _lib
     from filterpy_b200._dev import stream_ptr
+    from oracle import resample as ors
     lib = _lib.load()
     rng = np.random.default_rng(8)
     for N in [1, 2, 33, 1024, 1025, 5000]:
