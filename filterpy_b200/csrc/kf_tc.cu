@@ -47,11 +47,13 @@ struct Geom {
     static constexpr int SBO = 128;                 // bytes between 8-row groups (core matrices are contiguous)
     static constexpr int TMEM_COLS = 2 * NX;        // D1 in columns [0, NX), D2 in [NX, 2 NX): 32 or 64 (powers of two)
     // shared memory: A_hi | A_lo | F_hi | F_lo | F (plain, rows padded to NX + 1 words: x' = F x reads row r in
-    // thread r) | Q | transposition scratch [128][NX + 1] | mbarrier, TMEM slot
-    static constexpr int FP = NX + 1;
+    // thread r) | Q (rows padded to NX + 4 words: conflict-free 16-byte reads) | mbarrier, TMEM slot.  The
+    // transposition scratch [128][NX + 1] lies over A_hi | A_lo (free between the two products).
+    static constexpr int FP = NX + 1, QP = NX + 4;
     static constexpr int O_AHI = 0, O_ALO = O_AHI + A_BYTES, O_FHI = O_ALO + A_BYTES, O_FLO = O_FHI + B_BYTES;
-    static constexpr int O_F = O_FLO + B_BYTES, O_Q = O_F + ((NX * FP * 4 + 15) & ~15), O_T = O_Q + B_BYTES;
-    static constexpr int O_BAR = O_T + ((128 * FP * 4 + 15) & ~15), SMEM = O_BAR + 64;
+    static constexpr int O_F = O_FLO + B_BYTES, O_Q = O_F + ((NX * FP * 4 + 15) & ~15), O_T = O_AHI;
+    static constexpr int O_BAR = O_Q + NX * QP * 4, SMEM = O_BAR + 64;
+    static_assert(128 * FP * 4 <= 2 * A_BYTES, "the scratch fits the two operand buffers");
     // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D = f32 (bits 4-5 = 1), A = B = tf32
     // (bits 7-9 / 10-12 = 2), both K-major (bits 15, 16 = 0), N >> 3 at bit 17, M >> 4 at bit 24
     static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NX >> 3) << 17) | ((128u >> 4) << 24);
@@ -142,7 +144,7 @@ struct TcP {
 };
 
 template <int NX>
-__global__ void __launch_bounds__(128, 4) kf_cov_tc_kernel(TcP p)
+__global__ void __launch_bounds__(128, NX == 16 ? 8 : 4) kf_cov_tc_kernel(TcP p)
 {
     using G = Geom<NX>;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(128, 4) kf_cov_tc_kernel(TcP p)
         *reinterpret_cast<float *>(smem + G::O_FHI + op_off(n, k, G::B_LBO)) = hi;
         *reinterpret_cast<float *>(smem + G::O_FLO + op_off(n, k, G::B_LBO)) = f - hi;
         Fs[n * G::FP + k] = f;
-        Qs[e] = p.Q[e];
+        Qs[n * G::QP + k] = p.Q[e];
     }
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(1u));
@@ -199,6 +201,15 @@ __global__ void __launch_bounds__(128, 4) kf_cov_tc_kernel(TcP p)
     const int i_in_tile = tid / NX, r = tid % NX;         // this thread's row of the tile: filter i, matrix row r
     uint32_t phase = 0;
     bool ok = true;
+    // this thread's row of the NEXT tile is fetched while the current tile's products run
+    float4 pre[G::KC];
+    auto fetch_row = [&](int64_t tile) {
+        const int64_t row = tile * 128 + tid;
+        const float4 *src = reinterpret_cast<const float4 *>(p.P + row * NX);
+#pragma unroll
+        for (int kc = 0; kc < G::KC; kc++) pre[kc] = (row < rows) ? src[kc] : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    if ((int64_t)blockIdx.x < tiles) fetch_row(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < tiles && ok; tile += gridDim.x) {
         const int64_t row = tile * 128 + tid;
         const bool live = row < rows;
@@ -206,15 +217,15 @@ __global__ void __launch_bounds__(128, 4) kf_cov_tc_kernel(TcP p)
         // ---- 1. this thread's row of P -> hi / lo parts in the A-operand layout; x' = F x (own component)
         float xr = 0.f;
         {
-            const float4 *src = reinterpret_cast<const float4 *>(p.P + row * NX);
 #pragma unroll
             for (int kc = 0; kc < G::KC; kc++) {
-                const float4 v = live ? src[kc] : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 v = pre[kc];
                 const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
                 const int off = kc * G::A_LBO + (tid >> 3) * 128 + (tid & 7) * 16;
                 *reinterpret_cast<float4 *>(smem + G::O_AHI + off) = h;
                 *reinterpret_cast<float4 *>(smem + G::O_ALO + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
             }
+            if (tile + gridDim.x < tiles) fetch_row(tile + gridDim.x);
             if (live) {
                 const float *xf = p.x + f * NX;
 #pragma unroll
@@ -237,14 +248,17 @@ __global__ void __launch_bounds__(128, 4) kf_cov_tc_kernel(TcP p)
             // scratch (conflict-free), then thread (i,c) gathers column c and writes ITS operand row as 16-byte chunks
             float y[NX];
             tmem_ld_row<NX>(lane_base + 0, y);
-            float *Ts = reinterpret_cast<float *>(smem + G::O_T);
+            float *Ts = reinterpret_cast<float *>(smem + G::O_T);          // over A_hi | A_lo: the first product has read them
 #pragma unroll
             for (int c = 0; c < NX; c++) Ts[tid * G::FP + c] = y[c];
             __syncthreads();
             const float *col = Ts + (i_in_tile * NX) * G::FP + r;          // Y_i[k][c = r], k = 0 .. NX-1
 #pragma unroll
+            for (int k = 0; k < NX; k++) y[k] = col[k * G::FP];
+            __syncthreads();                                               // every column is in registers: the scratch may go
+#pragma unroll
             for (int kc = 0; kc < G::KC; kc++) {
-                const float4 v = make_float4(col[(kc * 4 + 0) * G::FP], col[(kc * 4 + 1) * G::FP], col[(kc * 4 + 2) * G::FP], col[(kc * 4 + 3) * G::FP]);
+                const float4 v = make_float4(y[kc * 4 + 0], y[kc * 4 + 1], y[kc * 4 + 2], y[kc * 4 + 3]);
                 const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
                 const int off = kc * G::A_LBO + (tid >> 3) * 128 + (tid & 7) * 16;
                 *reinterpret_cast<float4 *>(smem + G::O_AHI + off) = h;
@@ -270,7 +284,7 @@ __global__ void __launch_bounds__(128, 4) kf_cov_tc_kernel(TcP p)
                 float4 *dst2 = p.P_prior ? reinterpret_cast<float4 *>(p.P_prior + row * NX) : nullptr;
 #pragma unroll
                 for (int kc = 0; kc < G::KC; kc++) {
-                    const float4 q = *reinterpret_cast<const float4 *>(Qs + r * NX + kc * 4);
+                    const float4 q = *reinterpret_cast<const float4 *>(Qs + r * G::QP + kc * 4);
                     const float4 o = make_float4(fmaf(p.alpha_sq, v[kc * 4 + 0], q.x), fmaf(p.alpha_sq, v[kc * 4 + 1], q.y),
                                                  fmaf(p.alpha_sq, v[kc * 4 + 2], q.z), fmaf(p.alpha_sq, v[kc * 4 + 3], q.w));
                     dst[kc] = o;
@@ -305,7 +319,14 @@ int launch_t(const TcP &p, cudaStream_t s)
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     const int64_t tiles = (p.N * NX + 127) / 128;
-    const int64_t cap = (int64_t)sm_count() * 4;
+    static int per_sm[64] = {0};
+    int occ = (dev >= 0 && dev < 64) ? per_sm[dev] : 0;
+    if (occ == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kf_cov_tc_kernel<NX>, 128, G::SMEM) != cudaSuccess || occ < 1) occ = 1;
+        if (occ > 512 / G::TMEM_COLS) occ = 512 / G::TMEM_COLS;            // every CTA holds TMEM_COLS of the SM's 512 columns
+        if (dev >= 0 && dev < 64) per_sm[dev] = occ;
+    }
+    const int64_t cap = (int64_t)sm_count() * occ;
     kf_cov_tc_kernel<NX><<<(unsigned)(tiles < cap ? tiles : cap), 128, G::SMEM, s>>>(p);
     return check_cuda(cudaGetLastError(), "kf_cov_tc_kernel launch");
 }
