@@ -593,6 +593,29 @@ def extra_legs(dev, rank, world, peak, max_over_ranks, barrier):
     out["ukf_c4"] = {"workload": "config 4: UKF MerweScaledSigmaPoints(6, .5, 2, 0), CV + range/azimuth/elevation, 2^18 filters per GPU",
                      "filters_per_gpu": N4, "value": world * N4 / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "dtype": "f64",
                      "roofline": roof(ms, N4, bpu4, "ukf_kernel<double,6,3,CV,RangeAzEl>")}
+    del u, z4, uw
+    torch.cuda.empty_cache()
+
+    # the tensor-core tile: predict of shared-model fp32 banks with dim_x = 16 / 32 on tcgen05.mma
+    # (three-term TF32 split); algorithmic bytes per filter: x and P in, x and P out
+    for n_tc, N_tc in ((16, 1 << 19), (32, 1 << 17)):
+        rng = np.random.default_rng(77 + rank)
+        a = rng.normal(size=(2048, n_tc, n_tc)).astype(np.float32)
+        P0 = np.tile(2.0 * (a @ np.swapaxes(a, -1, -2) / n_tc + np.eye(n_tc, dtype=np.float32)), (N_tc // 2048, 1, 1))
+        kt = KalmanFilter(n_tc, 4, n_filters=N_tc, dtype=np.float32, device=dev, diagnostics=False)
+        kt.x, kt.P = np.tile(rng.normal(size=(2048, n_tc)).astype(np.float32), (N_tc // 2048, 1)), P0
+        kt.F, kt.H = np.eye(n_tc) + 0.05 * rng.normal(size=(n_tc, n_tc)), rng.normal(size=(4, n_tc))
+        kt.Q, kt.R = 0.05 * np.eye(n_tc), 0.5 * np.eye(4)
+
+        def step_tc():
+            kt.predict(); kt._flush()
+        ms = timed_steps(step_tc, 20, 3, dev, max_over_ranks, barrier)
+        out["kf_tc_predict_%d" % n_tc] = {
+            "workload": "KalmanFilter.predict of a shared-model fp32 bank, dim_x = %d, %d filters per GPU, on tcgen05.mma (kind::tf32, 3-term split)" % (n_tc, N_tc),
+            "filters_per_gpu": N_tc, "value": world * N_tc / (ms * 1e-3), "unit": "filter-predicts/s", "ms_per_step": ms, "dtype": "f32 (tf32x3 products, f32 accumulate)",
+            "roofline": roof(ms, N_tc, (2 * n_tc + 2 * n_tc * n_tc) * 4, "kf_cov_tc_kernel<%d>" % n_tc)}
+        del kt, P0, a
+        torch.cuda.empty_cache()
     return out
 
 

@@ -52,7 +52,7 @@ struct Geom {
     static constexpr int FP = NX + 1, QP = NX + 4;
     static constexpr int O_AHI = 0, O_ALO = O_AHI + A_BYTES, O_FHI = O_ALO + A_BYTES, O_FLO = O_FHI + B_BYTES;
     static constexpr int O_F = O_FLO + B_BYTES, O_Q = O_F + ((NX * FP * 4 + 15) & ~15), O_T = O_AHI;
-    static constexpr int O_BAR = O_Q + NX * QP * 4, SMEM = O_BAR + 64;
+    static constexpr int O_BAR = O_Q + NX * QP * 4, O_X = O_BAR + 64, SMEM = O_X + 128 * 4;      // x of the tile's filters
     static_assert(128 * FP * 4 <= 2 * A_BYTES, "the scratch fits the two operand buffers");
     // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D = f32 (bits 4-5 = 1), A = B = tf32
     // (bits 7-9 / 10-12 = 2), both K-major (bits 15, 16 = 0), N >> 3 at bit 17, M >> 4 at bit 24
@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(128, NX == 16 ? 8 : 4) kf_cov_tc_kernel(TcP p)
     using G = Geom<NX>;
     extern __shared__ __align__(1024) unsigned char smem[];
     float *Fs = reinterpret_cast<float *>(smem + G::O_F), *Qs = reinterpret_cast<float *>(smem + G::O_Q);
+    float *xs = reinterpret_cast<float *>(smem + G::O_X);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + G::O_BAR);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + G::O_BAR + 16);
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -203,11 +204,13 @@ __global__ void __launch_bounds__(128, NX == 16 ? 8 : 4) kf_cov_tc_kernel(TcP p)
     bool ok = true;
     // this thread's row of the NEXT tile is fetched while the current tile's products run
     float4 pre[G::KC];
+    float xpre = 0.f;                 // x[(tile * FPT + i) * NX + r] = x[tile * 128 + tid]: the thread's own component, coalesced
     auto fetch_row = [&](int64_t tile) {
         const int64_t row = tile * 128 + tid;
         const float4 *src = reinterpret_cast<const float4 *>(p.P + row * NX);
 #pragma unroll
         for (int kc = 0; kc < G::KC; kc++) pre[kc] = (row < rows) ? src[kc] : make_float4(0.f, 0.f, 0.f, 0.f);
+        xpre = (row < rows) ? p.x[row] : 0.f;
     };
     if ((int64_t)blockIdx.x < tiles) fetch_row(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < tiles && ok; tile += gridDim.x) {
@@ -225,12 +228,8 @@ __global__ void __launch_bounds__(128, NX == 16 ? 8 : 4) kf_cov_tc_kernel(TcP p)
                 *reinterpret_cast<float4 *>(smem + G::O_AHI + off) = h;
                 *reinterpret_cast<float4 *>(smem + G::O_ALO + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
             }
+            xs[tid] = xpre;
             if (tile + gridDim.x < tiles) fetch_row(tile + gridDim.x);
-            if (live) {
-                const float *xf = p.x + f * NX;
-#pragma unroll
-                for (int k = 0; k < NX; k++) xr += Fs[r * G::FP + k] * xf[k];
-            }
         }
         tc_fence_before();
         fence_proxy_async();          // generic-proxy writes of the operands -> visible to the tensor core (async proxy)
@@ -239,6 +238,11 @@ __global__ void __launch_bounds__(128, NX == 16 ? 8 : 4) kf_cov_tc_kernel(TcP p)
         if (warp == 0) {                 // lane 0 issues; its warp waits for it before polling the barrier
             if (tid == 0) { tc_fence_after(); issue_product(0); }
             __syncwarp();
+        }
+        {   // x' = F x from the staged state while the tensor core works (the barrier above published xs)
+            const float *xf = xs + i_in_tile * NX;
+#pragma unroll
+            for (int k = 0; k < NX; k++) xr += Fs[r * G::FP + k] * xf[k];
         }
         ok = mbar_wait(bar, phase); phase ^= 1;
         if (!ok) break;
@@ -319,13 +323,13 @@ int launch_t(const TcP &p, cudaStream_t s)
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     const int64_t tiles = (p.N * NX + 127) / 128;
-    static int per_sm[64] = {0};
-    int occ = (dev >= 0 && dev < 64) ? per_sm[dev] : 0;
-    if (occ == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kf_cov_tc_kernel<NX>, 128, G::SMEM) != cudaSuccess || occ < 1) occ = 1;
-        if (occ > 512 / G::TMEM_COLS) occ = 512 / G::TMEM_COLS;            // every CTA holds TMEM_COLS of the SM's 512 columns
-        if (dev >= 0 && dev < 64) per_sm[dev] = occ;
-    }
+    // CTAs per SM: registers (launch bounds), shared memory (+1 KB the runtime reserves per CTA) and TMEM columns;
+    // BKE_KF_TC_CTAS overrides (tuning)
+    static const int env_ctas = [] { const char *e = getenv("BKE_KF_TC_CTAS"); return e ? atoi(e) : 0; }();
+    int occ = NX == 16 ? 8 : 4;
+    if (occ > (227 * 1024) / (G::SMEM + 1024)) occ = (227 * 1024) / (G::SMEM + 1024);
+    if (occ > 512 / G::TMEM_COLS) occ = 512 / G::TMEM_COLS;
+    if (env_ctas > 0 && env_ctas < occ) occ = env_ctas;
     const int64_t cap = (int64_t)sm_count() * occ;
     kf_cov_tc_kernel<NX><<<(unsigned)(tiles < cap ? tiles : cap), 128, G::SMEM, s>>>(p);
     return check_cuda(cudaGetLastError(), "kf_cov_tc_kernel launch");

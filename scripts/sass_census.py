@@ -7,7 +7,7 @@ import sys
 import os
 
 LIB = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "filterpy_b200", "_C", "libbke.so")
-KEYS = ["UTMALDG", "UTMASTG", "UBLKCP", "UTMAPF", "SYNCS", "UCGABAR", "UTCMMA", "UTCHMMA", "LDTM", "HMMA", "DFMA", "DADD", "DMUL",
+KEYS = ["UTMALDG", "UTMASTG", "UBLKCP", "UTMAPF", "SYNCS", "UCGABAR", "UTCMMA", "UTCHMMA", "UTCBAR", "UTCATOMSWS", "LDTM", "HMMA", "DFMA", "DADD", "DMUL",
         "LDS", "STS", "LDG", "STG", "BAR", "SHFL", "LDL", "STL", "MUFU", "ATOM", "RED", "MEMBAR", "FENCE", "NANOSLEEP"]
 out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
 per = collections.OrderedDict()
@@ -31,7 +31,8 @@ for c in per.values():
     tot.update(c)
 print("# SASS instruction census of filterpy_b200/_C/libbke.so (sm_100a): cuobjdump -sass, per-kernel counts")
 print("# TMA: UTMALDG (tensor) / UBLKCP (bulk) / UTMAPF (prefetch); mbarrier: SYNCS; cluster barrier: UCGABAR;")
-print("# tensor memory / 5th-gen MMA (UTCMMA, UTCHMMA, LDTM) and HMMA: none expected — nothing on this path fills an MMA fragment")
+print("# tensor memory / 5th-gen MMA: UTCHMMA (tcgen05.mma kind::tf32), LDTM (tcgen05.ld), UTCBAR (tcgen05.commit), UTCATOMSWS (TMEM alloc) —")
+print("# only in kf_cov_tc_kernel<16|32> (csrc/kf_tc.cu), the one shape class that fills an MMA fragment; no HMMA / mma.sync anywhere")
 print()
 print("kernels: %d   total: " % len(per) + ", ".join("%s=%d" % (k, tot[k]) for k in ["instr"] + KEYS if tot[k]))
 print()

@@ -437,6 +437,11 @@ def test_rowblock_separate_predict_and_update_match_fused(n, m, dtype, diagnosti
             kf.update(torch.from_numpy(zs[t]), valid=valid[t])
         banks.append(kf)
     tol = 1e-9 if dtype is np.float64 else 1e-4
+    if n == 16 and shared and dtype is np.float32:
+        # the stand-alone predict of a shared-model fp32 bank with dim_x = 16 runs on the tensor cores (csrc/kf_tc.cu,
+        # three-term TF32 products, ~1.6e-6 of the largest entry), the fused step on the CUDA cores: different
+        # arithmetic, compared at north_star's fp32 bound
+        tol = 1e-3
     a, b = banks
     rel_close(b.x.cpu().numpy(), a.x.cpu().numpy(), tol, "x")
     rel_close(b.P.cpu().numpy(), a.P.cpu().numpy(), tol, "P")
