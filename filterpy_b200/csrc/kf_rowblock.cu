@@ -641,6 +641,8 @@ int launch_kf_rowblock(const bke_kf_args &a, cudaStream_t s)
     } else {
         if (n == 16 && m == 4) return launch_rb<float, 16, 4, 2, 1, 8>(a, s);   // two rows per lane, 4 filters per warp tile
         if (n == 16 && m == 2) return launch_rb<float, 16, 2, 2, 1, 8>(a, s);
+        // dim_x = 32: one row per lane, the whole warp on one filter (the update half of the tensor-core predict, kf_tc.cu)
+        if (n == 32 && m == 4) return launch_rb<float, 32, 4, 1, 1, 8>(a, s);
         if (n == 6 && m == 3) return ring ? launch_rb<float, 6, 3, 3, 2, 4>(a, s) : launch_rb<float, 6, 3, 3, 1, 8>(a, s);
         if (n == 9 && m == 3) return launch_rb<float, 9, 3, 3, 1, 8>(a, s);        // 8 filters per warp tile (see pick_fpw)
     }

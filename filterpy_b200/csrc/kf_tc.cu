@@ -300,8 +300,10 @@ __global__ void __launch_bounds__(128, NX == 16 ? 8 : 4) kf_cov_tc_kernel(TcP p)
                 if (p.status && r == 0 && !p.sticky) p.status[f] = BKE_STATUS_OK;
             }
         }
+        // no barrier here: the operand buffers are free (the second product's commit was awaited), the next tile's
+        // products are issued only after barriers every warp reaches after these TMEM reads, and xs was read before
+        // this tile's second barrier
         tc_fence_before();
-        __syncthreads();              // the next tile's operand writes and MMAs follow every warp's TMEM reads
     }
     if (!ok && p.err) *p.err = 1;
     tc_fence_before();

@@ -368,7 +368,7 @@ def test_shared_models_in_launch_parameters_equal_device_models(golden, diagnost
 
 
 @pytest.mark.parametrize("n,m", [(1, 1), (2, 1), (2, 2), (3, 1), (4, 1), (4, 2), (4, 4), (6, 2), (6, 3), (9, 3),
-                                 (16, 4), (16, 2), (12, 3)])      # 16/x: row-block instances; 12/3: catch-all
+                                 (16, 4), (16, 2), (12, 3), (32, 4)])      # 16/x, 32/4 fp32: row-block instances; 12/3: catch-all
 @pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-6), (np.float32, 1e-3)])
 @pytest.mark.parametrize("shared", [False, True])
 def test_small_shapes_random_models_vs_oracle(n, m, dtype, tol, shared):
