@@ -45,9 +45,6 @@ struct Geom {
     static constexpr int B_LBO = NX * 16;           // the same for the NX-row operand (F)
     static constexpr int B_BYTES = NX * NX * 4;
     static constexpr int SBO = 128;                 // bytes between 8-row groups (core matrices are contiguous)
-    // M-major form of the 128-row operand (second product, MN variant): core matrix = 8 K-rows x 16 bytes (4 rows of the
-    // tile), the 32 row chunks of a K group back to back, K groups 4 KB apart
-    static constexpr int MN_SBO = 128, MN_LBO = 32 * 128;
     static constexpr int TMEM_COLS = 2 * NX;        // D1 in columns [0, NX), D2 in [NX, 2 NX): 32 or 64 (powers of two)
     // shared memory: A_hi | A_lo | F_hi | F_lo | F (plain, rows padded to NX + 1 words: x' = F x reads row r in
     // thread r) | Q (rows padded to NX + 4 words: conflict-free 16-byte reads) | mbarrier, TMEM slot.  The
@@ -146,7 +143,7 @@ struct TcP {
     int *err;                        // device flag: a wait timed out
 };
 
-template <int NX, bool MN>
+template <int NX>
 __global__ void __launch_bounds__(128, NX == 16 ? 8 : 4) kf_cov_tc_kernel(TcP p)
 {
     using G = Geom<NX>;
@@ -184,10 +181,7 @@ __global__ void __launch_bounds__(128, NX == 16 ? 8 : 4) kf_cov_tc_kernel(TcP p)
 
     const uint32_t a_hi = smem_u32(smem + G::O_AHI), a_lo = smem_u32(smem + G::O_ALO);
     const uint32_t f_hi = smem_u32(smem + G::O_FHI), f_lo = smem_u32(smem + G::O_FLO);
-    // mn_a: the 128-row operand is M-major (second product of the MN variant): 16-byte chunks of 4 consecutive rows,
-    // 8 K-rows per core matrix; descriptor SBO = distance between row chunks, LBO = distance between 8-deep K groups,
-    // one K group per instruction
-    auto issue_product = [&](uint32_t d_col, bool mn_a) {
+    auto issue_product = [&](uint32_t d_col) {
         // D = A_lo F_hi' + A_hi F_lo' + A_hi F_hi'   (small terms first), K = NX in steps of 8
         uint32_t acc = 0;
 #pragma unroll
@@ -195,10 +189,8 @@ __global__ void __launch_bounds__(128, NX == 16 ? 8 : 4) kf_cov_tc_kernel(TcP p)
             const uint32_t a = term == 0 ? a_lo : a_hi, b = term == 1 ? f_lo : f_hi;
 #pragma unroll
             for (int ks = 0; ks < G::KS; ks++) {
-                const uint64_t ad = mn_a ? smem_desc(a + ks * G::MN_LBO, G::MN_LBO, G::MN_SBO)
-                                         : smem_desc(a + ks * 2 * G::A_LBO, G::A_LBO, G::SBO);
-                mma_tf32(tmem + d_col, ad, smem_desc(b + ks * 2 * G::B_LBO, G::B_LBO, G::SBO),
-                         mn_a ? (G::IDESC | (1u << 15)) : G::IDESC, acc);
+                mma_tf32(tmem + d_col, smem_desc(a + ks * 2 * G::A_LBO, G::A_LBO, G::SBO),
+                         smem_desc(b + ks * 2 * G::B_LBO, G::B_LBO, G::SBO), G::IDESC, acc);
                 acc = 1;
             }
         }
@@ -244,7 +236,7 @@ __global__ void __launch_bounds__(128, NX == 16 ? 8 : 4) kf_cov_tc_kernel(TcP p)
         __syncthreads();
         // ---- 2. D1 = P F'  (rows (i,r), columns c)
         if (warp == 0) {                 // lane 0 issues; its warp waits for it before polling the barrier
-            if (tid == 0) { tc_fence_after(); issue_product(0, false); }
+            if (tid == 0) { tc_fence_after(); issue_product(0); }
             __syncwarp();
         }
         {   // x' = F x from the staged state while the tensor core works (the barrier above published xs)
@@ -255,21 +247,7 @@ __global__ void __launch_bounds__(128, NX == 16 ? 8 : 4) kf_cov_tc_kernel(TcP p)
         ok = mbar_wait(bar, phase); phase ^= 1;
         if (!ok) break;
         tc_fence_after();
-        if constexpr (MN) {
-            // ---- 3 (MN variant). no transposition: the second product reads its 128-row operand M-major.  Thread (i, r)
-            // holds Y_i[r][0..n): row k = r of the K dimension, n consecutive rows m = (i, c) of the operand — its 16-byte
-            // chunks go straight into the M-major core matrices (a quarter warp writes 128 contiguous bytes)
-            float y[NX];
-            tmem_ld_row<NX>(lane_base + 0, y);
-#pragma unroll
-            for (int cc = 0; cc < G::KC; cc++) {
-                const float4 v = make_float4(y[cc * 4 + 0], y[cc * 4 + 1], y[cc * 4 + 2], y[cc * 4 + 3]);
-                const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-                const int off = (i_in_tile * G::KC + cc) * G::MN_SBO + (r >> 3) * G::MN_LBO + (r & 7) * 16;
-                *reinterpret_cast<float4 *>(smem + G::O_AHI + off) = h;
-                *reinterpret_cast<float4 *>(smem + G::O_ALO + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-            }
-        } else {
+        {
             // ---- 3. transpose every filter's block on the way back: A2[(i,c)][k] = Y_i[k][c].  Rows go to a padded
             // scratch (conflict-free), then thread (i,c) gathers column c and writes ITS operand row as 16-byte chunks
             float y[NX];
@@ -296,7 +274,7 @@ __global__ void __launch_bounds__(128, NX == 16 ? 8 : 4) kf_cov_tc_kernel(TcP p)
         __syncthreads();
         // ---- 4. D2 = (F P) F'  (rows (i,c), columns j)
         if (warp == 0) {
-            if (tid == 0) { tc_fence_after(); issue_product(NX, MN); }
+            if (tid == 0) { tc_fence_after(); issue_product(NX); }
             __syncwarp();
         }
         ok = mbar_wait(bar, phase); phase ^= 1;
@@ -335,7 +313,7 @@ __global__ void __launch_bounds__(128, NX == 16 ? 8 : 4) kf_cov_tc_kernel(TcP p)
     }
 }
 
-template <int NX, bool MN>
+template <int NX>
 int launch_t(const TcP &p, cudaStream_t s)
 {
     using G = Geom<NX>;
@@ -343,7 +321,7 @@ int launch_t(const TcP &p, cudaStream_t s)
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        if (check_cuda(cudaFuncSetAttribute(kf_cov_tc_kernel<NX, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
+        if (check_cuda(cudaFuncSetAttribute(kf_cov_tc_kernel<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     const int64_t tiles = (p.N * NX + 127) / 128;
@@ -355,7 +333,7 @@ int launch_t(const TcP &p, cudaStream_t s)
     if (occ > 512 / G::TMEM_COLS) occ = 512 / G::TMEM_COLS;
     if (env_ctas > 0 && env_ctas < occ) occ = env_ctas;
     const int64_t cap = (int64_t)sm_count() * occ;
-    kf_cov_tc_kernel<NX, MN><<<(unsigned)(tiles < cap ? tiles : cap), 128, G::SMEM, s>>>(p);
+    kf_cov_tc_kernel<NX><<<(unsigned)(tiles < cap ? tiles : cap), 128, G::SMEM, s>>>(p);
     return check_cuda(cudaGetLastError(), "kf_cov_tc_kernel launch");
 }
 
@@ -384,10 +362,7 @@ int launch_kf_tc(const bke_kf_args &a, cudaStream_t s)
     p.status = fused ? nullptr : a.status;            // the update that follows owns the status of a fused step
     p.sticky = (a.flags & BKE_STATUS_STICKY) ? 1 : 0;
     p.err = nullptr;
-    // BKE_KF_TC_MN=1: the second product reads its operand M-major (no transposition through shared memory)
-    static const bool mn = [] { const char *e = getenv("BKE_KF_TC_MN"); return e && e[0] == '1'; }();
-    int rc = a.dim_x == 16 ? (mn ? tc::launch_t<16, true>(p, s) : tc::launch_t<16, false>(p, s))
-                           : (mn ? tc::launch_t<32, true>(p, s) : tc::launch_t<32, false>(p, s));
+    int rc = a.dim_x == 16 ? tc::launch_t<16>(p, s) : tc::launch_t<32>(p, s);
     if (rc != BKE_OK || !fused) return rc;
     // fused step: the update runs on the prior this launch left in x_out / P_out (stream order)
     bke_kf_args u = a;
