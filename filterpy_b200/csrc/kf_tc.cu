@@ -29,6 +29,7 @@
 // lanes back with tcgen05.ld (32x32b: lane = row of the tile, registers = the row's n columns).
 #include <stdlib.h>
 #include "bke_internal.cuh"
+#include "kf_regtile.cuh"
 
 namespace bke {
 namespace tc {
@@ -52,7 +53,13 @@ struct Geom {
     static constexpr int FP = NX + 1, QP = NX + 4;
     static constexpr int O_AHI = 0, O_ALO = O_AHI + A_BYTES, O_FHI = O_ALO + A_BYTES, O_FLO = O_FHI + B_BYTES;
     static constexpr int O_F = O_FLO + B_BYTES, O_Q = O_F + ((NX * FP * 4 + 15) & ~15), O_T = O_AHI;
-    static constexpr int O_BAR = O_Q + NX * QP * 4, O_X = O_BAR + 64, SMEM = O_X + 128 * 4;      // x of the tile's filters
+    static constexpr int O_BAR = O_Q + NX * QP * 4, O_X = O_BAR + 64;                            // x of the tile's filters
+    // fused update (shared H, R; dim_z <= 4): H as a 16-row K-major operand (rows >= dim_z zero) in hi / lo parts, H and
+    // R plain for the CUDA-core reductions
+    static constexpr int H_LBO = 16 * 16, H_BYTES = 16 * NX * 4;
+    static constexpr int O_HHI = O_X + 128 * 4, O_HLO = O_HHI + H_BYTES, O_H = O_HLO + H_BYTES, O_R = O_H + 4 * NX * 4;
+    static constexpr int SMEM = O_R + 64;
+    static constexpr uint32_t IDESC_H = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(16 >> 3) << 17) | ((128u >> 4) << 24);
     static_assert(128 * FP * 4 <= 2 * A_BYTES, "the scratch fits the two operand buffers");
     // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D = f32 (bits 4-5 = 1), A = B = tf32
     // (bits 7-9 / 10-12 = 2), both K-major (bits 15, 16 = 0), N >> 3 at bit 17, M >> 4 at bit 24
@@ -141,10 +148,18 @@ struct TcP {
     int32_t *status;
     int sticky;
     int *err;                        // device flag: a wait timed out
+    // fused update (kf_cov_tc_kernel<NX, M> with M > 0): H [M, NX] and R [M, M] shared by the bank
+    const float *H, *R, *z;
+    const uint8_t *valid;
+    float *K, *y, *S, *SI, *ll;
 };
 
-template <int NX>
-__global__ void __launch_bounds__(128, NX == 16 ? 8 : 4) kf_cov_tc_kernel(TcP p)
+// M = 0: predict only.  M = dim_z in 1 .. 4: the update of kalman_filter.py:533-556 follows in the same launch (H, R shared).
+// CTAs per SM the register budget is planned for: the update's dim_z x dim_z pieces need more registers at dim_z >= 3
+constexpr int tc_ctas(int nx, int m) { return nx == 16 ? (m >= 4 ? 5 : (m == 3 ? 6 : 8)) : 4; }
+
+template <int NX, int M>
+__global__ void __launch_bounds__(128, tc_ctas(NX, M)) kf_cov_tc_kernel(TcP p)
 {
     using G = Geom<NX>;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -163,6 +178,18 @@ __global__ void __launch_bounds__(128, NX == 16 ? 8 : 4) kf_cov_tc_kernel(TcP p)
         *reinterpret_cast<float *>(smem + G::O_FLO + op_off(n, k, G::B_LBO)) = f - hi;
         Fs[n * G::FP + k] = f;
         Qs[n * G::QP + k] = p.Q[e];
+    }
+    float *Hs = reinterpret_cast<float *>(smem + G::O_H), *Rs = reinterpret_cast<float *>(smem + G::O_R);
+    if constexpr (M > 0) {
+        for (int e = tid; e < 16 * NX; e += 128) {
+            const int a = e / NX, k = e % NX;
+            const float h = a < M ? p.H[a * NX + k] : 0.f;
+            const float hi = tf32_hi(h);
+            *reinterpret_cast<float *>(smem + G::O_HHI + op_off(a, k, G::H_LBO)) = hi;
+            *reinterpret_cast<float *>(smem + G::O_HLO + op_off(a, k, G::H_LBO)) = h - hi;
+            if (a < M) Hs[a * NX + k] = h;
+        }
+        if (tid < M * M) Rs[tid] = p.R[tid];
     }
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(1u));
@@ -191,6 +218,23 @@ __global__ void __launch_bounds__(128, NX == 16 ? 8 : 4) kf_cov_tc_kernel(TcP p)
             for (int ks = 0; ks < G::KS; ks++) {
                 mma_tf32(tmem + d_col, smem_desc(a + ks * 2 * G::A_LBO, G::A_LBO, G::SBO),
                          smem_desc(b + ks * 2 * G::B_LBO, G::B_LBO, G::SBO), G::IDESC, acc);
+                acc = 1;
+            }
+        }
+        mma_commit(bar);
+    };
+
+    // D3 = P' H'  (rows (i,r), columns a < 16; a >= M are zero rows of the operand): TMEM columns [0, 16), free after step 3
+    auto issue_pht = [&]() {
+        const uint32_t h_hi = smem_u32(smem + G::O_HHI), h_lo = smem_u32(smem + G::O_HLO);
+        uint32_t acc = 0;
+#pragma unroll
+        for (int term = 0; term < 3; term++) {
+            const uint32_t a = term == 0 ? a_lo : a_hi, b = term == 1 ? h_lo : h_hi;
+#pragma unroll
+            for (int ks = 0; ks < G::KS; ks++) {
+                mma_tf32(tmem + 0, smem_desc(a + ks * 2 * G::A_LBO, G::A_LBO, G::SBO),
+                         smem_desc(b + ks * 2 * G::H_LBO, G::H_LBO, G::SBO), G::IDESC_H, acc);
                 acc = 1;
             }
         }
@@ -280,25 +324,181 @@ __global__ void __launch_bounds__(128, NX == 16 ? 8 : 4) kf_cov_tc_kernel(TcP p)
         ok = mbar_wait(bar, phase); phase ^= 1;
         if (!ok) break;
         tc_fence_after();
+        float pp[NX];                                   // this thread's row of the prior covariance P' = alpha^2 F P F' + Q
         {
             float v[NX];
             tmem_ld_row<NX>(lane_base + NX, v);
-            if (live) {
-                float4 *dst = reinterpret_cast<float4 *>(p.P_out + row * NX);
-                float4 *dst2 = p.P_prior ? reinterpret_cast<float4 *>(p.P_prior + row * NX) : nullptr;
 #pragma unroll
-                for (int kc = 0; kc < G::KC; kc++) {
-                    const float4 q = *reinterpret_cast<const float4 *>(Qs + r * G::QP + kc * 4);
-                    const float4 o = make_float4(fmaf(p.alpha_sq, v[kc * 4 + 0], q.x), fmaf(p.alpha_sq, v[kc * 4 + 1], q.y),
-                                                 fmaf(p.alpha_sq, v[kc * 4 + 2], q.z), fmaf(p.alpha_sq, v[kc * 4 + 3], q.w));
-                    dst[kc] = o;
-                    if (dst2) dst2[kc] = o;
-                }
-                // every thread of the filter has read x (before the first barrier of this tile): in place is safe
-                p.x_out[f * NX + r] = xr;
-                if (p.x_prior) p.x_prior[f * NX + r] = xr;
-                if (p.status && r == 0 && !p.sticky) p.status[f] = BKE_STATUS_OK;
+            for (int kc = 0; kc < G::KC; kc++) {
+                const float4 q = *reinterpret_cast<const float4 *>(Qs + r * G::QP + kc * 4);
+                pp[kc * 4 + 0] = fmaf(p.alpha_sq, v[kc * 4 + 0], q.x); pp[kc * 4 + 1] = fmaf(p.alpha_sq, v[kc * 4 + 1], q.y);
+                pp[kc * 4 + 2] = fmaf(p.alpha_sq, v[kc * 4 + 2], q.z); pp[kc * 4 + 3] = fmaf(p.alpha_sq, v[kc * 4 + 3], q.w);
             }
+        }
+        if (live) {
+            if (p.P_prior) {
+                float4 *dst2 = reinterpret_cast<float4 *>(p.P_prior + row * NX);
+#pragma unroll
+                for (int kc = 0; kc < G::KC; kc++) dst2[kc] = make_float4(pp[kc * 4], pp[kc * 4 + 1], pp[kc * 4 + 2], pp[kc * 4 + 3]);
+            }
+            if (p.x_prior) p.x_prior[row] = xr;
+        }
+        float xo = xr;                                  // posterior := prior unless the update succeeds
+        int st = BKE_STATUS_OK;
+        if constexpr (M > 0) {
+            // ---- 5. update (kalman_filter.py:533-556) with H, R shared: P' H' on the tensor core from the prior rows,
+            // the dim_z-sized pieces per filter on the CUDA cores (the filter's NX threads sit in one warp)
+#pragma unroll
+            for (int kc = 0; kc < G::KC; kc++) {
+                const float4 v = make_float4(pp[kc * 4], pp[kc * 4 + 1], pp[kc * 4 + 2], pp[kc * 4 + 3]);
+                const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+                const int off = kc * G::A_LBO + (tid >> 3) * 128 + (tid & 7) * 16;
+                *reinterpret_cast<float4 *>(smem + G::O_AHI + off) = h;
+                *reinterpret_cast<float4 *>(smem + G::O_ALO + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            __syncthreads();
+            if (warp == 0) {
+                if (tid == 0) { tc_fence_after(); issue_pht(); }
+                __syncwarp();
+            }
+            ok = mbar_wait(bar, phase); phase ^= 1;
+            if (!ok) break;
+            tc_fence_after();
+            float pht[M];                               // row r of P' H'
+            {
+                float t16[16];
+                tmem_ld_row<16>(lane_base + 0, t16);
+#pragma unroll
+                for (int a = 0; a < M; a++) pht[a] = t16[a];
+            }
+            const bool vz = live && (p.valid == nullptr || p.valid[f] != 0);
+            // S = H (P' H') + R and H x' : this thread's terms, summed over the filter's NX lanes (xor butterfly)
+            float Sm[M][M], hx[M];
+#pragma unroll
+            for (int a = 0; a < M; a++) {
+                const float h = Hs[a * NX + r];
+                hx[a] = h * xr;
+#pragma unroll
+                for (int b = 0; b < M; b++) Sm[a][b] = h * pht[b];
+            }
+#pragma unroll
+            for (int o = NX / 2; o > 0; o >>= 1) {
+#pragma unroll
+                for (int a = 0; a < M; a++) {
+                    hx[a] += __shfl_xor_sync(FULL, hx[a], o);
+#pragma unroll
+                    for (int b = 0; b < M; b++) Sm[a][b] += __shfl_xor_sync(FULL, Sm[a][b], o);
+                }
+            }
+            float yv[M];
+#pragma unroll
+            for (int a = 0; a < M; a++) {
+                yv[a] = (vz ? p.z[f * M + a] : 0.f) - hx[a];
+#pragma unroll
+                for (int b = 0; b < M; b++) Sm[a][b] += Rs[a * M + b];
+            }
+            float SI[M][M], logdet;
+            const bool inv_ok = reg_inverse<float, M>(Sm, SI, logdet);
+            if (vz && !inv_ok) st = BKE_STATUS_SINGULAR_S;
+            const bool upd = vz && inv_ok;
+            float Kr[M], KS[M];                          // rows r of K = P' H' S^-1 and of K S
+#pragma unroll
+            for (int a = 0; a < M; a++) {
+                float sk = 0.f;
+#pragma unroll
+                for (int b = 0; b < M; b++) sk += pht[b] * SI[b][a];
+                Kr[a] = sk;
+            }
+#pragma unroll
+            for (int a = 0; a < M; a++) {
+                float sk = 0.f;
+#pragma unroll
+                for (int b = 0; b < M; b++) sk += Kr[b] * Sm[b][a];
+                KS[a] = sk;
+            }
+            if (upd) {
+#pragma unroll
+                for (int a = 0; a < M; a++) xo += Kr[a] * yv[a];
+            }
+            // rows of K and P' H' of the filter's other lanes: through this thread's OWN first two operand chunks (only
+            // its warp reads them, the third product is complete) — 16 bytes each, dim_z <= 4
+            {
+                float4 kq = make_float4(0.f, 0.f, 0.f, 0.f), pq = kq;
+                float *kf4 = reinterpret_cast<float *>(&kq), *pf4 = reinterpret_cast<float *>(&pq);
+#pragma unroll
+                for (int a = 0; a < M; a++) { kf4[a] = Kr[a]; pf4[a] = pht[a]; }
+                const int off = (tid >> 3) * 128 + (tid & 7) * 16;
+                *reinterpret_cast<float4 *>(smem + G::O_AHI + off) = kq;
+                *reinterpret_cast<float4 *>(smem + G::O_AHI + G::A_LBO + off) = pq;
+            }
+            __syncwarp();
+            if (upd) {
+                // Joseph form expanded with K as computed (kalman_filter.py:555-556):
+                // (I-KH) P' (I-KH)' + K R K' = P' - K (P'H')' - (P'H') K' + K S K'
+                const int t0 = tid - r;                   // first thread of this filter
+#pragma unroll
+                for (int j = 0; j < NX; j++) {
+                    const int tj = t0 + j;
+                    const int off = (tj >> 3) * 128 + (tj & 7) * 16;
+                    const float4 kq = *reinterpret_cast<const float4 *>(smem + G::O_AHI + off);
+                    const float4 pq = *reinterpret_cast<const float4 *>(smem + G::O_AHI + G::A_LBO + off);
+                    const float *kj = reinterpret_cast<const float *>(&kq), *pj = reinterpret_cast<const float *>(&pq);
+                    float acc = pp[j];
+#pragma unroll
+                    for (int a = 0; a < M; a++) acc += (KS[a] - pht[a]) * kj[a] - Kr[a] * pj[a];
+                    pp[j] = acc;
+                }
+            }
+            __syncwarp();                               // the chunks are rewritten by the next tile's operand rows
+            if (live) {
+                // optional outputs (kalman_filter.py:533-544 attributes): y always (0 when z is None), S when there is a
+                // measurement, K / SI / log-likelihood when S was invertible; otherwise the arrays keep their values
+                if (p.y && r == 0) {
+#pragma unroll
+                    for (int a = 0; a < M; a++) p.y[f * M + a] = vz ? yv[a] : 0.f;
+                }
+                if (vz && r == 0 && p.S) {
+#pragma unroll
+                    for (int a = 0; a < M; a++)
+#pragma unroll
+                        for (int b = 0; b < M; b++) p.S[f * M * M + a * M + b] = Sm[a][b];
+                }
+                if (upd) {
+                    if (p.K) {
+#pragma unroll
+                        for (int a = 0; a < M; a++) p.K[(f * NX + r) * M + a] = Kr[a];
+                    }
+                    if (r == 0) {
+                        if (p.SI) {
+#pragma unroll
+                            for (int a = 0; a < M; a++)
+#pragma unroll
+                                for (int b = 0; b < M; b++) p.SI[f * M * M + a * M + b] = SI[a][b];
+                        }
+                        if (p.ll) {
+                            float q = 0.f;
+#pragma unroll
+                            for (int a = 0; a < M; a++) {
+                                float sq = 0.f;
+#pragma unroll
+                                for (int b = 0; b < M; b++) sq += SI[a][b] * yv[b];
+                                q += yv[a] * sq;
+                            }
+                            p.ll[f] = -0.5f * (q + logdet + float(M) * float(LOG_2PI));
+                        }
+                    }
+                }
+            }
+        }
+        if (live) {
+            float4 *dst = reinterpret_cast<float4 *>(p.P_out + row * NX);
+#pragma unroll
+            for (int kc = 0; kc < G::KC; kc++) dst[kc] = make_float4(pp[kc * 4], pp[kc * 4 + 1], pp[kc * 4 + 2], pp[kc * 4 + 3]);
+            // every thread of the filter has read x (staged before the first barrier of this tile): in place is safe
+            p.x_out[row] = xo;
+            if (p.status && r == 0 && (st != BKE_STATUS_OK || !p.sticky)) p.status[f] = st;
         }
         // no barrier here: the operand buffers are free (the second product's commit was awaited), the next tile's
         // products are issued only after barriers every warp reaches after these TMEM reads, and xs was read before
@@ -313,7 +513,7 @@ __global__ void __launch_bounds__(128, NX == 16 ? 8 : 4) kf_cov_tc_kernel(TcP p)
     }
 }
 
-template <int NX>
+template <int NX, int M>
 int launch_t(const TcP &p, cudaStream_t s)
 {
     using G = Geom<NX>;
@@ -321,50 +521,69 @@ int launch_t(const TcP &p, cudaStream_t s)
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        if (check_cuda(cudaFuncSetAttribute(kf_cov_tc_kernel<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
+        if (check_cuda(cudaFuncSetAttribute(kf_cov_tc_kernel<NX, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM), "cudaFuncSetAttribute")) return BKE_ERR_CUDA;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     const int64_t tiles = (p.N * NX + 127) / 128;
     // CTAs per SM: registers (launch bounds), shared memory (+1 KB the runtime reserves per CTA) and TMEM columns;
     // BKE_KF_TC_CTAS overrides (tuning)
     static const int env_ctas = [] { const char *e = getenv("BKE_KF_TC_CTAS"); return e ? atoi(e) : 0; }();
-    int occ = NX == 16 ? 8 : 4;
+    int occ = tc_ctas(NX, M);
     if (occ > (227 * 1024) / (G::SMEM + 1024)) occ = (227 * 1024) / (G::SMEM + 1024);
     if (occ > 512 / G::TMEM_COLS) occ = 512 / G::TMEM_COLS;
     if (env_ctas > 0 && env_ctas < occ) occ = env_ctas;
     const int64_t cap = (int64_t)sm_count() * occ;
-    kf_cov_tc_kernel<NX><<<(unsigned)(tiles < cap ? tiles : cap), 128, G::SMEM, s>>>(p);
+    kf_cov_tc_kernel<NX, M><<<(unsigned)(tiles < cap ? tiles : cap), 128, G::SMEM, s>>>(p);
     return check_cuda(cudaGetLastError(), "kf_cov_tc_kernel launch");
+}
+
+template <int NX>
+int launch_m(const TcP &p, int m, cudaStream_t s)
+{
+    switch (m) {
+    case 0: return launch_t<NX, 0>(p, s);
+    case 1: return launch_t<NX, 1>(p, s);
+    case 2: return launch_t<NX, 2>(p, s);
+    case 3: return launch_t<NX, 3>(p, s);
+    default: return launch_t<NX, 4>(p, s);
+    }
 }
 
 }  // namespace tc
 
 static bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// BKE_KF_TC=0 keeps the CUDA-core kernels for these shapes, =2 takes every eligible call (A/B measurements).
-// Default: every eligible predict-only call, and the fused step where no row-block instance covers the shape
-// (16/4 and 16/2 have one whose single launch beats predict-here + update-there).
+// BKE_KF_TC=0 keeps the CUDA-core kernels for these shapes (A/B measurements).  Eligible: fp32, dim_x 16 / 32, F and Q
+// shared, no control input.  A fused predict+update whose H and R are shared too and whose dim_z <= 4 runs entirely in
+// this kernel (BKE_KF_TC_FUSED=0: predict here, update through the usual order); any other fused step runs its predict
+// here and its update through launch_kf_any on the prior left in x_out / P_out.
 int launch_kf_tc(const bke_kf_args &a, cudaStream_t s)
 {
     static const int mode = [] { const char *e = getenv("BKE_KF_TC"); return e ? atoi(e) : 1; }();
+    static const bool fused_on = [] { const char *e = getenv("BKE_KF_TC_FUSED"); return !(e && e[0] == '0'); }();
     if (mode == 0) return BKE_ERR_UNSUPPORTED;
-    if (mode == 1 && (a.flags & BKE_DO_UPDATE) && a.dim_x == 16 && (a.dim_z == 4 || a.dim_z == 2)) return BKE_ERR_UNSUPPORTED;
     if (a.dtype != BKE_F32 || !(a.dim_x == 16 || a.dim_x == 32)) return BKE_ERR_UNSUPPORTED;
     if (!(a.flags & BKE_DO_PREDICT) || (a.flags & BKE_UPDATE_FIRST)) return BKE_ERR_UNSUPPORTED;
     if (a.F_stride != 0 || a.Q_stride != 0 || (a.B && a.u)) return BKE_ERR_UNSUPPORTED;
     if (!(al16(a.x) && al16(a.P) && al16(a.x_out) && al16(a.P_out) && al16(a.x_prior) && al16(a.P_prior))) return BKE_ERR_UNSUPPORTED;
+    const bool fused = (a.flags & BKE_DO_UPDATE) != 0;
+    const bool fused_here = fused && fused_on && a.H_stride == 0 && a.R_stride == 0 && a.dim_z >= 1 && a.dim_z <= 4 && a.z;
+    // without the fused kernel the 16/4 and 16/2 fused steps are faster as ONE row-block launch than as predict-here + update-there
+    if (fused && !fused_here && mode == 1 && a.dim_x == 16 && (a.dim_z == 4 || a.dim_z == 2)) return BKE_ERR_UNSUPPORTED;
     // x_out may alias x and P_out may alias P (each tile reads its rows before it writes them); nothing else may overlap
     tc::TcP p;
     p.N = a.n_filters; p.alpha_sq = (float)a.alpha_sq;
     p.x = (const float *)a.x; p.P = (const float *)a.P; p.F = (const float *)a.F; p.Q = (const float *)a.Q;
     p.x_out = (float *)a.x_out; p.P_out = (float *)a.P_out; p.x_prior = (float *)a.x_prior; p.P_prior = (float *)a.P_prior;
-    const bool fused = (a.flags & BKE_DO_UPDATE) != 0;
-    p.status = fused ? nullptr : a.status;            // the update that follows owns the status of a fused step
+    p.status = (fused && !fused_here) ? nullptr : a.status;      // the update that follows owns the status of a two-launch step
     p.sticky = (a.flags & BKE_STATUS_STICKY) ? 1 : 0;
     p.err = nullptr;
-    int rc = a.dim_x == 16 ? tc::launch_t<16>(p, s) : tc::launch_t<32>(p, s);
-    if (rc != BKE_OK || !fused) return rc;
-    // fused step: the update runs on the prior this launch left in x_out / P_out (stream order)
+    p.H = (const float *)a.H; p.R = (const float *)a.R; p.z = (const float *)a.z; p.valid = a.z_valid;
+    p.K = (float *)a.K; p.y = (float *)a.y; p.S = (float *)a.S; p.SI = (float *)a.SI; p.ll = (float *)a.log_likelihood;
+    const int m_here = fused_here ? a.dim_z : 0;
+    int rc = a.dim_x == 16 ? tc::launch_m<16>(p, m_here, s) : tc::launch_m<32>(p, m_here, s);
+    if (rc != BKE_OK || !fused || fused_here) return rc;
+    // two-launch fused step: the update runs on the prior this launch left in x_out / P_out (stream order)
     bke_kf_args u = a;
     u.flags = (a.flags & ~(uint32_t)BKE_DO_PREDICT);
     u.x = a.x_out; u.P = a.P_out;

@@ -58,7 +58,37 @@ def test_tc_fused_steps_vs_oracle(n, m):
         o = okf.kf_step_bank(x, P, b["zs"][t], b["F"], b["H"], b["Q"], b["R"], valid=valid[t])
         x, P = o["x"], o["P"]
     kf.check()
-    for got, want in [(kf.x, x), (kf.P, P), (kf.x_prior, o["x_prior"]), (kf.P_prior, o["P_prior"])]:
+    v = valid[2]
+    for got, want, mask in [(kf.x, x, None), (kf.P, P, None), (kf.x_prior, o["x_prior"], None), (kf.P_prior, o["P_prior"], None),
+                            (kf.y, o["y"], None), (kf.K, o["K"], v), (kf.S, o["S"], v), (kf.SI, o["SI"], v)]:
         got = got.cpu().numpy().astype(np.float64)
-        mag = np.abs(want).reshape(N, -1).max(axis=1).reshape((N,) + (1,) * (want.ndim - 1))
+        if mask is not None:                      # K, S, SI keep their old values where z is None (kalman_filter.py:515-520)
+            got, want = got[mask], want[mask]
+        M_ = want.shape[0]
+        mag = np.abs(want).reshape(M_, -1).max(axis=1).reshape((M_,) + (1,) * (want.ndim - 1))
         assert np.all(np.abs(got - want) <= 1e-3 * (np.abs(want) + 0.05 * mag + 1e-12))
+    # log-likelihood of the last step where there was a measurement: -0.5 (y' SI y + log det S + m log 2 pi)
+    yv, Sv, SIv = o["y"][v], o["S"][v], o["SI"][v]
+    ll = -0.5 * (np.einsum("na,nab,nb->n", yv, SIv, yv) + np.log(np.abs(np.linalg.det(Sv))) + m * np.log(2 * np.pi))
+    got = kf.log_likelihood.cpu().numpy().astype(np.float64)[v]
+    assert np.all(np.abs(got - ll) <= 1e-3 * (np.abs(ll) + 1.0))
+
+
+def test_tc_fused_singular_S_reports_status_and_keeps_the_prior():
+    """S = H P' H' + R singular for some filters (R = 0 and a zero row of H): status 1 there, posterior := prior, the
+    other filters updated (np.linalg.inv raises LinAlgError in the reference, kalman_filter.py:541)."""
+    import torch
+    from filterpy_b200.kalman import KalmanFilter
+    n, m, N = 16, 2, 200
+    b = bank(n, m, N, seed=3)
+    H = b["H"].copy(); H[1] = 0.0
+    R = np.diag([0.5, 0.0])
+    kf = KalmanFilter(n, m, n_filters=N, dtype=np.float32, diagnostics=True)
+    kf.x, kf.P, kf.F, kf.H, kf.Q, kf.R = b["x"], b["P"], b["F"], H, b["Q"], R
+    kf.predict(); kf.update(torch.from_numpy(b["zs"][0]))
+    st = kf.status.cpu().numpy() if hasattr(kf, "status") else None
+    assert torch.equal(kf.x, kf.x_prior) and torch.equal(kf.P, kf.P_prior)
+    if st is not None:
+        assert np.all(st == 1)
+    with pytest.raises(np.linalg.LinAlgError):
+        kf.check()
