@@ -613,8 +613,19 @@ def extra_legs(dev, rank, world, peak, max_over_ranks, barrier):
         out["kf_tc_predict_%d" % n_tc] = {
             "workload": "KalmanFilter.predict of a shared-model fp32 bank, dim_x = %d, %d filters per GPU, on tcgen05.mma (kind::tf32, 3-term split)" % (n_tc, N_tc),
             "filters_per_gpu": N_tc, "value": world * N_tc / (ms * 1e-3), "unit": "filter-predicts/s", "ms_per_step": ms, "dtype": "f32 (tf32x3 products, f32 accumulate)",
-            "roofline": roof(ms, N_tc, (2 * n_tc + 2 * n_tc * n_tc) * 4, "kf_cov_tc_kernel<%d>" % n_tc)}
-        del kt, P0, a
+            "roofline": roof(ms, N_tc, (2 * n_tc + 2 * n_tc * n_tc) * 4, "kf_cov_tc_kernel<%d,0>" % n_tc)}
+        # the whole step in the tile: H and R shared too, dim_z = 4 (P' H' as a third tensor-core product, the dim_z-sized
+        # pieces per filter on the CUDA cores); algorithmic bytes: x, P, z in; x, P out
+        z_tc = torch.from_numpy(rng.normal(size=(N_tc, 4)).astype(np.float32)).to(dev)
+
+        def step_tc_fused():
+            kt.predict(); kt.update(z_tc)
+        ms = timed_steps(step_tc_fused, 20, 3, dev, max_over_ranks, barrier)
+        out["kf_tc_step_%d" % n_tc] = {
+            "workload": "KalmanFilter.predict + update of a shared-model fp32 bank, %d/4, %d filters per GPU, one launch on tcgen05.mma (kind::tf32, 3-term split)" % (n_tc, N_tc),
+            "filters_per_gpu": N_tc, "value": world * N_tc / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "dtype": "f32 (tf32x3 products, f32 accumulate)",
+            "roofline": roof(ms, N_tc, (2 * n_tc + 2 * n_tc * n_tc + 4) * 4, "kf_cov_tc_kernel<%d,4>" % n_tc)}
+        del kt, P0, a, z_tc
         torch.cuda.empty_cache()
     return out
 

@@ -438,10 +438,19 @@ def test_rowblock_separate_predict_and_update_match_fused(n, m, dtype, diagnosti
         banks.append(kf)
     tol = 1e-9 if dtype is np.float64 else 1e-4
     if n == 16 and shared and dtype is np.float32:
-        # the stand-alone predict of a shared-model fp32 bank with dim_x = 16 runs on the tensor cores (csrc/kf_tc.cu,
-        # three-term TF32 products, ~1.6e-6 of the largest entry), the fused step on the CUDA cores: different
-        # arithmetic, compared at north_star's fp32 bound
-        tol = 1e-3
+        # shared-model fp32 banks with dim_x = 16 run on the tensor cores (csrc/kf_tc.cu): the stand-alone predict as
+        # three-term TF32 products, the fused step with the Joseph form expanded — different arithmetic from the
+        # row-block update of the two-launch sequence, so each bank is held to north_star's fp32 bound against the fp64
+        # oracle instead of to the other bank (fp32 itself sits at 3e-4 under this metric: x has cancelling entries)
+        from oracle import kf as okf
+        x, P = x0, P0
+        for t in range(3):
+            o = okf.kf_step_bank(x, P, zs[t], F[0], H[0], Q[0], R[0], valid=valid[t])
+            x, P = o["x"], o["P"]
+        for kf in banks:
+            rel_close(kf.x.cpu().numpy(), x, 1e-3, "x vs oracle")
+            rel_close(kf.P.cpu().numpy(), P, 1e-3, "P vs oracle")
+        return
     a, b = banks
     rel_close(b.x.cpu().numpy(), a.x.cpu().numpy(), tol, "x")
     rel_close(b.P.cpu().numpy(), a.P.cpu().numpy(), tol, "P")
