@@ -54,12 +54,9 @@ struct Geom {
     static constexpr int O_AHI = 0, O_ALO = O_AHI + A_BYTES, O_FHI = O_ALO + A_BYTES, O_FLO = O_FHI + B_BYTES;
     static constexpr int O_F = O_FLO + B_BYTES, O_Q = O_F + ((NX * FP * 4 + 15) & ~15), O_T = O_AHI;
     static constexpr int O_BAR = O_Q + NX * QP * 4, O_X = O_BAR + 64;                            // x of the tile's filters
-    // fused update (shared H, R; dim_z <= 4): H as a 16-row K-major operand (rows >= dim_z zero) in hi / lo parts, H and
-    // R plain for the CUDA-core reductions
-    static constexpr int H_LBO = 16 * 16, H_BYTES = 16 * NX * 4;
-    static constexpr int O_HHI = O_X + 128 * 4, O_HLO = O_HHI + H_BYTES, O_H = O_HLO + H_BYTES, O_R = O_H + 4 * NX * 4;
+    // fused update (shared H, R; dim_z <= 4): H and R plain, for the CUDA-core part
+    static constexpr int O_H = O_X + 128 * 4, O_R = O_H + 4 * NX * 4;
     static constexpr int SMEM = O_R + 64;
-    static constexpr uint32_t IDESC_H = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(16 >> 3) << 17) | ((128u >> 4) << 24);
     static_assert(128 * FP * 4 <= 2 * A_BYTES, "the scratch fits the two operand buffers");
     // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D = f32 (bits 4-5 = 1), A = B = tf32
     // (bits 7-9 / 10-12 = 2), both K-major (bits 15, 16 = 0), N >> 3 at bit 17, M >> 4 at bit 24
@@ -138,7 +135,15 @@ template <> __device__ __forceinline__ void tmem_ld_row<32>(uint32_t taddr, floa
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+// round to TF32 (10 mantissa bits, round to nearest, ties away): the tensor core reads exactly these bits, the low 13 are 0
+__device__ __forceinline__ float tf32_hi(float v)
+{
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    return __uint_as_float(u);
+}
+// the remainder v - hi is exact in fp32 (|.| <= 2^-11 |v|); rounded to TF32 itself it leaves 2^-22 |v|
+__device__ __forceinline__ float tf32_lo(float v, float hi) { return tf32_hi(v - hi); }
 
 struct TcP {
     int64_t N;                       // filters
@@ -175,20 +180,13 @@ __global__ void __launch_bounds__(128, tc_ctas(NX, M)) kf_cov_tc_kernel(TcP p)
         const int n = e / NX, k = e % NX;
         const float hi = tf32_hi(f);
         *reinterpret_cast<float *>(smem + G::O_FHI + op_off(n, k, G::B_LBO)) = hi;
-        *reinterpret_cast<float *>(smem + G::O_FLO + op_off(n, k, G::B_LBO)) = f - hi;
+        *reinterpret_cast<float *>(smem + G::O_FLO + op_off(n, k, G::B_LBO)) = tf32_lo(f, hi);
         Fs[n * G::FP + k] = f;
         Qs[n * G::QP + k] = p.Q[e];
     }
     float *Hs = reinterpret_cast<float *>(smem + G::O_H), *Rs = reinterpret_cast<float *>(smem + G::O_R);
     if constexpr (M > 0) {
-        for (int e = tid; e < 16 * NX; e += 128) {
-            const int a = e / NX, k = e % NX;
-            const float h = a < M ? p.H[a * NX + k] : 0.f;
-            const float hi = tf32_hi(h);
-            *reinterpret_cast<float *>(smem + G::O_HHI + op_off(a, k, G::H_LBO)) = hi;
-            *reinterpret_cast<float *>(smem + G::O_HLO + op_off(a, k, G::H_LBO)) = h - hi;
-            if (a < M) Hs[a * NX + k] = h;
-        }
+        for (int e = tid; e < M * NX; e += 128) Hs[e] = p.H[e];
         if (tid < M * M) Rs[tid] = p.R[tid];
     }
     if (tid == 0) {
@@ -224,23 +222,6 @@ __global__ void __launch_bounds__(128, tc_ctas(NX, M)) kf_cov_tc_kernel(TcP p)
         mma_commit(bar);
     };
 
-    // D3 = P' H'  (rows (i,r), columns a < 16; a >= M are zero rows of the operand): TMEM columns [0, 16), free after step 3
-    auto issue_pht = [&]() {
-        const uint32_t h_hi = smem_u32(smem + G::O_HHI), h_lo = smem_u32(smem + G::O_HLO);
-        uint32_t acc = 0;
-#pragma unroll
-        for (int term = 0; term < 3; term++) {
-            const uint32_t a = term == 0 ? a_lo : a_hi, b = term == 1 ? h_lo : h_hi;
-#pragma unroll
-            for (int ks = 0; ks < G::KS; ks++) {
-                mma_tf32(tmem + 0, smem_desc(a + ks * 2 * G::A_LBO, G::A_LBO, G::SBO),
-                         smem_desc(b + ks * 2 * G::H_LBO, G::H_LBO, G::SBO), G::IDESC_H, acc);
-                acc = 1;
-            }
-        }
-        mma_commit(bar);
-    };
-
     const int64_t rows = p.N * NX;
     const int64_t tiles = (rows + 127) / 128;
     const int i_in_tile = tid / NX, r = tid % NX;         // this thread's row of the tile: filter i, matrix row r
@@ -270,7 +251,7 @@ __global__ void __launch_bounds__(128, tc_ctas(NX, M)) kf_cov_tc_kernel(TcP p)
                 const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
                 const int off = kc * G::A_LBO + (tid >> 3) * 128 + (tid & 7) * 16;
                 *reinterpret_cast<float4 *>(smem + G::O_AHI + off) = h;
-                *reinterpret_cast<float4 *>(smem + G::O_ALO + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                *reinterpret_cast<float4 *>(smem + G::O_ALO + off) = make_float4(tf32_lo(v.x, h.x), tf32_lo(v.y, h.y), tf32_lo(v.z, h.z), tf32_lo(v.w, h.w));
             }
             xs[tid] = xpre;
             if (tile + gridDim.x < tiles) fetch_row(tile + gridDim.x);
@@ -310,7 +291,7 @@ __global__ void __launch_bounds__(128, tc_ctas(NX, M)) kf_cov_tc_kernel(TcP p)
                 const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
                 const int off = kc * G::A_LBO + (tid >> 3) * 128 + (tid & 7) * 16;
                 *reinterpret_cast<float4 *>(smem + G::O_AHI + off) = h;
-                *reinterpret_cast<float4 *>(smem + G::O_ALO + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                *reinterpret_cast<float4 *>(smem + G::O_ALO + off) = make_float4(tf32_lo(v.x, h.x), tf32_lo(v.y, h.y), tf32_lo(v.z, h.z), tf32_lo(v.w, h.w));
             }
         }
         tc_fence_before();
@@ -346,32 +327,17 @@ __global__ void __launch_bounds__(128, tc_ctas(NX, M)) kf_cov_tc_kernel(TcP p)
         float xo = xr;                                  // posterior := prior unless the update succeeds
         int st = BKE_STATUS_OK;
         if constexpr (M > 0) {
-            // ---- 5. update (kalman_filter.py:533-556) with H, R shared: P' H' on the tensor core from the prior rows,
-            // the dim_z-sized pieces per filter on the CUDA cores (the filter's NX threads sit in one warp)
+            // ---- 5. update (kalman_filter.py:533-556) with H, R shared, on the CUDA cores: everything is dim_z-sized per
+            // filter and the filter's NX threads sit in one warp.  Row r of P' H' is a thin product (NX x dim_z FMAs per
+            // thread, H broadcast from shared memory) — in plain fp32 from the row the thread already holds, so that K, S
+            // and the covariance correction are mutually consistent to fp32 rounding
+            float pht[M];
 #pragma unroll
-            for (int kc = 0; kc < G::KC; kc++) {
-                const float4 v = make_float4(pp[kc * 4], pp[kc * 4 + 1], pp[kc * 4 + 2], pp[kc * 4 + 3]);
-                const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-                const int off = kc * G::A_LBO + (tid >> 3) * 128 + (tid & 7) * 16;
-                *reinterpret_cast<float4 *>(smem + G::O_AHI + off) = h;
-                *reinterpret_cast<float4 *>(smem + G::O_ALO + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-            }
-            tc_fence_before();
-            fence_proxy_async();
-            __syncthreads();
-            if (warp == 0) {
-                if (tid == 0) { tc_fence_after(); issue_pht(); }
-                __syncwarp();
-            }
-            ok = mbar_wait(bar, phase); phase ^= 1;
-            if (!ok) break;
-            tc_fence_after();
-            float pht[M];                               // row r of P' H'
-            {
-                float t16[16];
-                tmem_ld_row<16>(lane_base + 0, t16);
+            for (int a = 0; a < M; a++) {
+                float sacc = 0.f;
 #pragma unroll
-                for (int a = 0; a < M; a++) pht[a] = t16[a];
+                for (int j = 0; j < NX; j++) sacc = fmaf(pp[j], Hs[a * NX + j], sacc);
+                pht[a] = sacc;
             }
             const bool vz = live && (p.valid == nullptr || p.valid[f] != 0);
             // S = H (P' H') + R and H x' : this thread's terms, summed over the filter's NX lanes (xor butterfly)
@@ -403,7 +369,7 @@ __global__ void __launch_bounds__(128, tc_ctas(NX, M)) kf_cov_tc_kernel(TcP p)
             const bool inv_ok = reg_inverse<float, M>(Sm, SI, logdet);
             if (vz && !inv_ok) st = BKE_STATUS_SINGULAR_S;
             const bool upd = vz && inv_ok;
-            float Kr[M], KS[M];                          // rows r of K = P' H' S^-1 and of K S
+            float Kr[M];                                 // row r of K = P' H' S^-1
 #pragma unroll
             for (int a = 0; a < M; a++) {
                 float sk = 0.f;
@@ -411,19 +377,12 @@ __global__ void __launch_bounds__(128, tc_ctas(NX, M)) kf_cov_tc_kernel(TcP p)
                 for (int b = 0; b < M; b++) sk += pht[b] * SI[b][a];
                 Kr[a] = sk;
             }
-#pragma unroll
-            for (int a = 0; a < M; a++) {
-                float sk = 0.f;
-#pragma unroll
-                for (int b = 0; b < M; b++) sk += Kr[b] * Sm[b][a];
-                KS[a] = sk;
-            }
             if (upd) {
 #pragma unroll
                 for (int a = 0; a < M; a++) xo += Kr[a] * yv[a];
             }
             // rows of K and P' H' of the filter's other lanes: through this thread's OWN first two operand chunks (only
-            // its warp reads them, the third product is complete) — 16 bytes each, dim_z <= 4
+            // its warp reads them, the second product is complete) — 16 bytes each, dim_z <= 4
             {
                 float4 kq = make_float4(0.f, 0.f, 0.f, 0.f), pq = kq;
                 float *kf4 = reinterpret_cast<float *>(&kq), *pf4 = reinterpret_cast<float *>(&pq);
@@ -435,19 +394,39 @@ __global__ void __launch_bounds__(128, tc_ctas(NX, M)) kf_cov_tc_kernel(TcP p)
             }
             __syncwarp();
             if (upd) {
-                // Joseph form expanded with K as computed (kalman_filter.py:555-556):
-                // (I-KH) P' (I-KH)' + K R K' = P' - K (P'H')' - (P'H') K' + K S K'
+                // Joseph form in the reference's order, with thin products (kalman_filter.py:555-556):
+                //   T1 = (I - K H) P' = P' - K (P'H')'          row r: P'[r][j] - sum_a K[r][a] (P'H')[j][a]
+                //   P  = T1 (I - K H)' + (K R) K'               row r: T1[r][j] + sum_a ((K R)[r][a] - (T1 H')[r][a]) K[j][a]
+                // errors of K enter quadratically, as in the reference — not linearly as in P' - K S K'
                 const int t0 = tid - r;                   // first thread of this filter
 #pragma unroll
                 for (int j = 0; j < NX; j++) {
                     const int tj = t0 + j;
-                    const int off = (tj >> 3) * 128 + (tj & 7) * 16;
-                    const float4 kq = *reinterpret_cast<const float4 *>(smem + G::O_AHI + off);
-                    const float4 pq = *reinterpret_cast<const float4 *>(smem + G::O_AHI + G::A_LBO + off);
-                    const float *kj = reinterpret_cast<const float *>(&kq), *pj = reinterpret_cast<const float *>(&pq);
+                    const float4 pq = *reinterpret_cast<const float4 *>(smem + G::O_AHI + G::A_LBO + (tj >> 3) * 128 + (tj & 7) * 16);
+                    const float *pj = reinterpret_cast<const float *>(&pq);
                     float acc = pp[j];
 #pragma unroll
-                    for (int a = 0; a < M; a++) acc += (KS[a] - pht[a]) * kj[a] - Kr[a] * pj[a];
+                    for (int a = 0; a < M; a++) acc = fmaf(-Kr[a], pj[a], acc);
+                    pp[j] = acc;
+                }
+                float g[M];                               // (K R)[r][a] - (T1 H')[r][a]
+#pragma unroll
+                for (int a = 0; a < M; a++) {
+                    float t1h = 0.f, kr = 0.f;
+#pragma unroll
+                    for (int j = 0; j < NX; j++) t1h = fmaf(pp[j], Hs[a * NX + j], t1h);
+#pragma unroll
+                    for (int b = 0; b < M; b++) kr = fmaf(Kr[b], Rs[b * M + a], kr);
+                    g[a] = kr - t1h;
+                }
+#pragma unroll
+                for (int j = 0; j < NX; j++) {
+                    const int tj = t0 + j;
+                    const float4 kq = *reinterpret_cast<const float4 *>(smem + G::O_AHI + (tj >> 3) * 128 + (tj & 7) * 16);
+                    const float *kj = reinterpret_cast<const float *>(&kq);
+                    float acc = pp[j];
+#pragma unroll
+                    for (int a = 0; a < M; a++) acc = fmaf(g[a], kj[a], acc);
                     pp[j] = acc;
                 }
             }
