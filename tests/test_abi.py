@@ -89,6 +89,13 @@ def test_no_cpu_fallback():
         KalmanFilter(2, 1)
     with pytest.raises(_lib.BkeError):
         systematic_resample([.5, .5])
+    from filterpy_b200.monte_carlo import residual_resample, multinomial_resample
+    for fn in (residual_resample, multinomial_resample):
+        with pytest.raises(_lib.BkeError):
+            fn([.5, .5])
+    # the filter whose steps run on the tensor-core tile has no CPU path either
+    with pytest.raises(_lib.BkeError):
+        KalmanFilter(16, 4, n_filters=8, dtype=np.float32)
 
 
 def test_product_never_imports_oracle():
